@@ -1,0 +1,1994 @@
+/*
+ *  fiasco_oracle.c -- CPU restatement (in our own words) of the FIASCO encoder hot path:
+ *  bintree subdivision, matching pursuit, inner-product tables, domain-pool and
+ *  coefficient rate models.  Sequential, single-threaded, plain C.
+ *
+ *  TEST INFRASTRUCTURE ONLY (see fiasco_oracle.h).  Parity: PINNED against the
+ *  reference binary built in oracle/_ref (tests/test_oracle_vs_reference.py and the
+ *  committed golden dumps/traces in tests/golden/).
+ *
+ *  Every function cites the reference file:line whose behaviour it restates.  Floating
+ *  point follows SURVEY.md Appendix A.7: real_t = float, every operation rounded to
+ *  fp32, no contraction (built with -ffp-contract=off), double only inside log2().
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <setjmp.h>
+#include <stdarg.h>
+#include <stddef.h>
+
+#include "fiasco_oracle.h"
+
+#define MAXEDGES  FO_MAXEDGES
+#define MAXSTATES FO_MAXSTATES
+#define MAXLABELS FO_MAXLABELS
+#define MAXLEVEL  FO_MAXLEVEL
+#define NO_EDGE	  (-1)
+#define RANGE	  (-1)
+#define AUXILIARY_MASK	1
+#define USE_DOMAIN_MASK 2
+#define MAXCOSTS  1e20f		/* codec/coder.c:53 */
+
+#define width_of_level(l)   (1u << ((l) >> 1))		/* lib/macros.h:48 */
+#define height_of_level(l)  (1u << (((l) + 1) >> 1))	/* lib/macros.h:49 */
+#define size_of_level(l)    (1u << (l))
+#define address_of_level(l) (size_of_level (l) - 1)
+#define size_of_tree(l)	    (address_of_level ((l) + 1))
+#define fmin2(a, b)	    ((a) > (b) ? (b) : (a))	/* macros.h:56 'min' */
+
+/*****************************************************************************
+			reduced precision format  (lib/rpf.c)
+*****************************************************************************/
+
+typedef struct rpf
+{
+   unsigned mantissa_bits;
+   float    range;
+} rpf_t;
+
+static float
+rpf_range_value (int range_e)	/* lib/rpf.c:202-222 */
+{
+   switch (range_e)
+   {
+      case 0:  return 0.75f;
+      case 1:  return 1.00f;
+      case 2:  return 1.50f;
+      case 3:  return 2.00f;
+      default: return 1.00f;
+   }
+}
+
+static rpf_t
+make_rpf (unsigned mantissa, int range_e) /* alloc_rpf, lib/rpf.c:171-199 */
+{
+   rpf_t r;
+
+   if (mantissa < 2)
+      mantissa = 2;
+   else if (mantissa > 8)
+      mantissa = 2;		/* sic: the reference "clamps" > 8 to 2 (quirk C4) */
+   r.mantissa_bits = mantissa;
+   r.range	   = rpf_range_value (range_e);
+   return r;
+}
+
+static int
+rtob (float f, const rpf_t *rpf)
+/*
+ *  lib/rpf.c:59-111.  The reference shifts a 32 bit word by 'exponent' which may
+ *  exceed 31; compiled for x86-64 that is a 'shl/shr %cl' whose count is taken
+ *  modulo 32.  We make that explicit so the restatement is well defined.
+ */
+{
+   uint32_t u, mantissa;
+   int	    exponent, sign;
+
+   f /= rpf->range;
+   memcpy (&u, &f, 4);
+   mantissa = u & 0x7fffffu;
+   exponent = (int) ((u >> 23) & 0xffu) - 126;
+   sign	    = (int) (u >> 31);
+
+   mantissa >>= 1;
+   mantissa  |= 1u << 22;
+   if (exponent > 0)
+      mantissa <<= (exponent & 31);
+   else
+      mantissa >>= ((-exponent) & 31);
+   mantissa >>= (23 - rpf->mantissa_bits - 1);
+   mantissa  += 1;
+   mantissa >>= 1;
+
+   if (mantissa == 0)
+      return -1;		/* RPF_ZERO */
+   else if (mantissa >= (1u << rpf->mantissa_bits))
+      return sign;
+   else
+      return (int) (((mantissa & ((1u << rpf->mantissa_bits) - 1)) << 1) | sign);
+}
+
+static float
+btor (int binary, const rpf_t *rpf) /* lib/rpf.c:113-169 */
+{
+   uint32_t mantissa, u;
+   int	    sign, exponent;
+   float    v;
+
+   if (binary == -1)
+      return 0;
+   sign	      = binary & 1;
+   mantissa   = ((unsigned) binary & ((1u << (rpf->mantissa_bits + 1)) - 1)) >> 1;
+   mantissa <<= (23 - rpf->mantissa_bits);
+   exponent   = 0;
+   if (mantissa == 0)
+      v = sign ? -1.0f : 1.0f;
+   else
+   {
+      while (!(mantissa & (1u << 22)))
+      {
+	 exponent--;
+	 mantissa <<= 1;
+      }
+      mantissa <<= 1;
+      u = ((uint32_t) sign << 31) | ((uint32_t) (exponent + 126) << 23)
+	  | (mantissa & 0x7fffffu);
+      memcpy (&v, &u, 4);
+   }
+   return v * rpf->range;
+}
+
+int
+fo_rtob (float f, unsigned mantissa_bits, int range_e)
+{
+   rpf_t r = make_rpf (mantissa_bits, range_e);
+   return rtob (f, &r);
+}
+
+float
+fo_btor (int b, unsigned mantissa_bits, int range_e)
+{
+   rpf_t r = make_rpf (mantissa_bits, range_e);
+   return btor (b, &r);
+}
+
+/*****************************************************************************
+			     misc  (lib/misc.c)
+*****************************************************************************/
+
+static unsigned
+bits_bin_code (unsigned value, unsigned maxval) /* lib/misc.c:296-315 */
+{
+   unsigned k = (unsigned) log2 ((double) (maxval + 1));
+   unsigned r = (maxval + 1) % (1u << k);
+
+   return value < maxval + 1 - 2 * r ? k : k + 1;
+}
+
+unsigned
+fo_bits_bin_code (unsigned value, unsigned maxval)
+{
+   return bits_bin_code (value, maxval);
+}
+
+/*****************************************************************************
+			   tree model  (codec/bintree.c)
+*****************************************************************************/
+
+typedef struct tree_model
+{
+   unsigned counts [MAXLEVEL];
+   unsigned total [MAXLEVEL];
+} tree_model_t;
+
+static void
+init_tree_model (tree_model_t *t) /* codec/bintree.c:70-93 */
+{
+   static const unsigned c0 [MAXLEVEL] = {20, 17, 15, 10, 5, 4, 3, 2, 1, 1, 1,
+					  1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};
+   static const unsigned c1 [MAXLEVEL] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 3, 5,
+					  10, 15, 20, 25, 30, 35, 60, 60, 60,
+					  60};
+   unsigned l;
+
+   for (l = 0; l < MAXLEVEL; l++)
+   {
+      t->counts [l] = c1 [l];
+      t->total [l]  = c0 [l] + c1 [l];
+   }
+}
+
+static float
+tree_bits (int child, unsigned level, const tree_model_t *t) /* bintree.c:55-68 */
+{
+   float prob = t->counts [level] / (float) t->total [level];
+
+   return child ? (float) -log2 ((double) prob)
+		: (float) -log2 ((double) (1 - prob));
+}
+
+static void
+tree_update (int child, unsigned level, tree_model_t *t) /* bintree.c:35-53 */
+{
+   if (child)
+      t->counts [level]++;
+   t->total [level]++;
+}
+
+void
+fo_tree_model_kat (unsigned level, unsigned *counts, unsigned *total,
+		   float *child_bits, float *leaf_bits)
+{
+   tree_model_t t;
+
+   init_tree_model (&t);
+   *counts     = t.counts [level];
+   *total      = t.total [level];
+   *child_bits = tree_bits (1, level, &t);
+   *leaf_bits  = tree_bits (0, level, &t);
+}
+
+/*****************************************************************************
+		 coefficient model "adaptive"  (codec/coeff.c:185-330)
+*****************************************************************************/
+
+#define AAC_MAXCOUNTS (1 + (1 << 9) + (MAXLEVEL + 1) * (1 << 9))
+
+typedef struct aac_model
+{
+   /* counts_mem[0] is a pad slot: the reference can (in principle) index counts[-1]
+      with the RPF_ZERO code; keep that read inside our own memory */
+   int16_t counts_mem [AAC_MAXCOUNTS];
+   int16_t totals [MAXLEVEL + 2];
+} aac_model_t;
+
+typedef struct coeff
+{
+   rpf_t    rpf, dc_rpf;
+   unsigned min_level, max_level;
+   aac_model_t model;
+} coeff_t;
+
+static void
+aac_init (coeff_t *c, rpf_t rpf, rpf_t dc_rpf, unsigned min_level,
+	  unsigned max_level) /* coeff.c:285-313 */
+{
+   unsigned size, n;
+
+   c->rpf	= rpf;
+   c->dc_rpf	= dc_rpf;
+   c->min_level = min_level;
+   c->max_level = max_level;
+   size = (max_level - min_level + 1) * (1u << (1 + rpf.mantissa_bits))
+	  + (1u << (1 + dc_rpf.mantissa_bits));
+   memset (&c->model, 0, sizeof c->model);
+   for (n = 0; n < size + 1; n++)
+      c->model.counts_mem [n] = 1;
+   c->model.totals [0] = (int16_t) (1 << (1 + dc_rpf.mantissa_bits));
+   for (n = min_level; n <= max_level; n++)
+      c->model.totals [n - min_level + 1]
+	 = (int16_t) (1 << (1 + rpf.mantissa_bits));
+}
+
+static float
+aac_bits (const float *used_coeff, const int16_t *used_states, unsigned level,
+	  const coeff_t *c) /* coeff.c:215-240 */
+{
+   float	  bits = 0;
+   unsigned	  edge;
+   int		  state;
+   const int16_t *base	 = c->model.counts_mem + 1;
+   const int16_t *counts = base + (1 << (1 + c->dc_rpf.mantissa_bits))
+			   + ((level - c->min_level)
+			      * (1 << (1 + c->rpf.mantissa_bits)));
+
+   for (edge = 0; (state = used_states [edge]) != NO_EDGE; edge++)
+      if (state)
+	 bits = (float) ((double) bits
+			 - log2 ((double) (counts [rtob (used_coeff [edge], &c->rpf)]
+					   / (float) c->model.totals [level - c->min_level + 1])));
+      else
+	 bits = (float) ((double) bits
+			 - log2 ((double) (base [rtob (used_coeff [edge], &c->dc_rpf)]
+					   / (float) c->model.totals [0])));
+   return bits;
+}
+
+static void
+aac_update (const float *used_coeff, const int16_t *used_states,
+	    unsigned level, coeff_t *c) /* coeff.c:242-267 */
+{
+   unsigned edge;
+   int	    state;
+   int16_t *base   = c->model.counts_mem + 1;
+   int16_t *counts = base + (1 << (1 + c->dc_rpf.mantissa_bits))
+		     + ((level - c->min_level)
+			* (1 << (1 + c->rpf.mantissa_bits)));
+
+   for (edge = 0; (state = used_states [edge]) != NO_EDGE; edge++)
+      if (state)
+      {
+	 counts [rtob (used_coeff [edge], &c->rpf)]++;
+	 c->model.totals [level - c->min_level + 1]++;
+      }
+      else
+      {
+	 base [rtob (used_coeff [edge], &c->dc_rpf)]++;
+	 c->model.totals [0]++;
+      }
+}
+
+/*****************************************************************************
+	      domain pool "rle" (+ its 1-entry "adaptive" DC model)
+			(codec/domain-pool.c:621-879, :259-498, :970-999)
+*****************************************************************************/
+
+static float matrix_0 [1 << 10], matrix_1 [1 << 10];
+
+static void
+init_matrix_probabilities (void) /* domain-pool.c:970-999 */
+{
+   unsigned index = 0, n, e;
+
+   for (n = 1; n <= 9; n++)
+      for (e = 0; e < 1u << n; e++, index++)
+      {
+	 matrix_1 [index] = (float) -log2 ((double) (1 / (float) (1 << n)));
+	 matrix_0 [index] = (float) -log2 ((double) (1 - 1 / (float) (1 << n)));
+      }
+}
+
+typedef struct rle_model
+{
+   int16_t  count [MAXEDGES + 1];
+   uint16_t total;
+   uint16_t n;
+   uint16_t max_domains;
+   uint16_t y_index;
+   int16_t  states [MAXSTATES];
+   /* domain_0: qac model with max_domains == 1 (domain-pool.c:655) */
+   uint16_t d0_n;
+   int16_t  d0_index;
+   uint16_t d0_y_index;
+} rle_model_t;
+
+/* copying only the live part of states[] is equivalent to rle_model_duplicate
+   (domain-pool.c:686-705): entries >= n are never read before being rewritten */
+static void
+rle_copy (rle_model_t *dst, const rle_model_t *src)
+{
+   memcpy (dst, src, offsetof (rle_model_t, states));
+   memcpy (dst->states, src->states, src->n * sizeof (int16_t));
+   dst->d0_n	   = src->d0_n;
+   dst->d0_index   = src->d0_index;
+   dst->d0_y_index = src->d0_y_index;
+}
+
+static void
+rle_init (rle_model_t *m, unsigned max_domains) /* domain-pool.c:655-672 */
+{
+   unsigned k;
+
+   memset (m, 0, sizeof *m);
+   for (k = m->total = 0; k < MAXEDGES + 1; k++, m->total++)
+      m->count [k] = 1;
+   m->max_domains = (uint16_t) max_domains;
+}
+
+static int
+rle_append (rle_model_t *m, unsigned new_state) /* domain-pool.c:832-852, :467-484 */
+{
+   if (m->n >= m->max_domains)
+      return 0;
+   m->states [m->n] = (int16_t) new_state;
+   m->n++;
+   if (new_state == 0)
+   {
+      if (m->d0_n < 1)		/* qac_append into the 1-entry model */
+      {
+	 m->d0_index = 0;
+	 m->d0_n     = 1;
+      }
+   }
+   return 1;
+}
+
+/* rle_generate, domain-pool.c:707-735.  'domains' must hold n + 2 entries. */
+static void
+rle_generate (int16_t *domains, int y_state, const uint8_t *domain_type,
+	      const rle_model_t *m)
+{
+   unsigned n;
+   int	    y_is_domain = 0;
+
+   if (y_state >= 0 && !(domain_type [y_state] & USE_DOMAIN_MASK))
+      y_state = -1;
+   memcpy (domains, m->states, m->n * sizeof (int16_t));
+   for (n = 0; n < m->n; n++)
+      if (domains [n] == y_state)
+	 y_is_domain = 1;
+   if (y_is_domain)
+      domains [m->n] = -1;
+   else
+   {
+      domains [m->n]	 = (int16_t) y_state;
+      domains [m->n + 1] = -1;
+   }
+}
+
+/* qac_bits (domain-pool.c:367-402) specialised to how rle_bits calls it for the DC
+   model: domains = {0,-1}, used = {0,-1} (dc_used) or {-1} */
+static float
+d0_bits (int dc_used, int y_state, const rle_model_t *m)
+{
+   float bits = 0;
+
+   if (m->d0_n > 0 && 0 != y_state)		/* states[0] == 0 */
+      bits += matrix_0 [m->d0_index];
+   if (y_state >= 0)
+      bits += matrix_0 [m->d0_y_index];
+   if (dc_used)
+   {
+      if (0 == y_state)				/* domains[0] == y_state */
+      {
+	 bits -= matrix_0 [m->d0_y_index];
+	 bits += matrix_1 [m->d0_y_index];
+      }
+      else
+      {
+	 bits -= matrix_0 [m->d0_index];
+	 bits += matrix_1 [m->d0_index];
+      }
+   }
+   return bits;
+}
+
+static int
+cmp_word (const void *a, const void *b)
+{
+   return (int) *(const int16_t *) a - (int) *(const int16_t *) b;
+}
+
+static float
+rle_bits (const int16_t *domains, const int16_t *used_domains, int y_state,
+	  const uint8_t *domain_type, const rle_model_t *m)
+/* domain-pool.c:737-793, including the overwrite of 'bits' (quirk C2) */
+{
+   unsigned edge, n = 0, last;
+   float    bits = 0;
+   int16_t  sorted [MAXEDGES + 1];
+   int	    into;
+
+   if (y_state >= 0 && !(domain_type [y_state] & USE_DOMAIN_MASK))
+      y_state = -1;
+   if (used_domains)
+   {
+      int16_t domain;
+
+      for (edge = n = 0; (domain = used_domains [edge]) != NO_EDGE; edge++)
+	 if (domains [domain] != y_state)
+	    sorted [n++] = used_domains [edge];
+      if (n > 1)
+	 qsort (sorted, n, sizeof (int16_t), cmp_word);
+   }
+   bits = (float) -log2 ((double) (m->count [n] / (float) m->total));
+   if (used_domains && n && sorted [0] == 0)
+      bits += d0_bits (1, y_state, m);
+   else
+      bits += d0_bits (0, y_state, m);
+
+   last = 1;
+   for (edge = 0; edge < n; edge++)
+      if ((into = sorted [edge]) && (unsigned) m->n - 1 - last)
+      {
+	 bits += bits_bin_code ((unsigned) into - last, (unsigned) m->n - 1 - last);
+	 last  = (unsigned) into + 1;
+      }
+   return bits;
+}
+
+static void
+rle_update (const int16_t *domains, const int16_t *used_domains, int y_state,
+	    const uint8_t *domain_type, rle_model_t *m)
+/* domain-pool.c:795-830 with qac_update (:404-446) inlined for the DC model */
+{
+   int	    state_0 = 0, state_y = 0;
+   unsigned edge    = 0;
+
+   if (y_state >= 0 && !(domain_type [y_state] & USE_DOMAIN_MASK))
+      y_state = -1;
+   if (used_domains)
+   {
+      int16_t domain;
+
+      for (edge = 0; (domain = used_domains [edge]) != NO_EDGE; edge++)
+	 if (domains [domain] == 0)
+	    state_0 = 1;
+	 else if (domains [domain] == y_state)
+	    state_y = 1;
+   }
+   m->count [edge]++;
+   m->total++;
+
+   /* qac_update (array0, array0 + (state_0 ? 0 : 1), ...) on domain_0 */
+   {
+      int y_is_domain = 0, used_y = 0;
+
+      if (m->d0_n > 0)
+      {
+	 m->d0_index++;
+	 if (0 == y_state)
+	    y_is_domain = 1;
+      }
+      if (state_0)		/* one used domain: index 0, domains[0] == 0 */
+      {
+	 if (0 == y_state)
+	 {
+	    if (y_is_domain)
+	       m->d0_index--;
+	    m->d0_y_index >>= 1;
+	    used_y = 1;
+	 }
+	 else
+	 {
+	    m->d0_index--;
+	    m->d0_index >>= 1;
+	 }
+      }
+      if (y_state >= 0 && !used_y)
+	 m->d0_y_index++;
+      if (m->d0_n > 0 && m->d0_index > 1020)
+	 m->d0_index = 1020;
+      if (m->d0_y_index > 1020)
+	 m->d0_y_index = 1020;
+   }
+   if (state_y)
+      m->y_index >>= 1;
+   else
+      m->y_index++;
+   if (m->y_index > 1020)
+      m->y_index = 1020;
+}
+
+/*****************************************************************************
+			       coder state
+*****************************************************************************/
+
+typedef struct range
+{
+   unsigned x, y, image, address, level;
+   float    weight [MAXEDGES + 1];
+   int16_t  into [MAXEDGES + 1];
+   int	    tree;
+   float    err, tree_bits, matrix_bits, weights_bits;
+   /* mv_tree_bits, mv_coord_bits, nd_tree_bits, nd_weights_bits are identically 0 on
+      the still-image path without prediction; they are kept as explicit zeros in the
+      sums below so that the order of fp32 additions matches cwfa.h:46-75 users */
+} range_t;
+
+typedef struct coder
+{
+   fo_params_t	opt;		/* clamped copy (coder.c:260-296) */
+   float	price;
+   unsigned	level;		/* image level */
+   unsigned	products_level;
+   unsigned	coeff_min_level, coeff_max_level;
+   rpf_t	rpf, dc_rpf;
+   const int16_t *planes [3];
+   float       *pixels;		/* current lc_max block in bintree order */
+   float       *images_of_state [MAXSTATES];
+   float       *ip_images_state [MAXSTATES];
+   float       *ip_states_state [MAXSTATES][MAXLEVEL];
+   tree_model_t tree;
+   rle_model_t	pool;
+   coeff_t	coeff;
+   fo_wfa_t    *wfa;
+   fo_stats_t  *st;
+   FILE	       *trace;
+   unsigned	lc_calls, ipis_calls;
+   jmp_buf	env;
+   char	       *errbuf;
+   size_t	errlen;
+} coder_t;
+
+static void
+fail (coder_t *c, const char *fmt, ...)
+{
+   va_list ap;
+
+   va_start (ap, fmt);
+   if (c->errbuf && c->errlen)
+      vsnprintf (c->errbuf, c->errlen, fmt, ap);
+   va_end (ap);
+   longjmp (c->env, 1);
+}
+
+static uint32_t
+fbits (float f)
+{
+   uint32_t u;
+   memcpy (&u, &f, 4);
+   return u;
+}
+
+#define need_image(s, w) ((w)->domain_type [s] & (AUXILIARY_MASK | USE_DOMAIN_MASK))
+#define usedomain(s, w)	 ((w)->domain_type [s] & USE_DOMAIN_MASK)
+
+static void
+clear_or_alloc (float **ptr, size_t size) /* control.c:259-271 */
+{
+   if (*ptr == NULL)
+      *ptr = calloc (size ? size : 1, sizeof (float));
+   else
+      memset (*ptr, 0, size * sizeof (float));
+}
+
+/*****************************************************************************
+			inner products  (codec/ip.c)
+*****************************************************************************/
+
+static float
+standard_ip_image_state (unsigned address, unsigned level, unsigned domain,
+			 coder_t *c) /* ip.c:268-295 */
+{
+   unsigned	i;
+   float	ip = 0;
+   const float *im = &c->pixels [address * size_of_level (level)];
+   const float *st = c->images_of_state [domain] + address_of_level (level);
+
+   for (i = size_of_level (level); i; i--)
+      ip += *im++ * *st++;
+   c->st->leaf_dots++;
+   return ip;
+}
+
+static float
+standard_ip_state_state (unsigned d1, unsigned d2, unsigned level,
+			 const coder_t *c) /* ip.c:297-323 */
+{
+   unsigned	i;
+   float	ip = 0;
+   const float *s1 = c->images_of_state [d1] + address_of_level (level);
+   const float *s2 = c->images_of_state [d2] + address_of_level (level);
+
+   for (i = size_of_level (level); i; i--)
+      ip += *s1++ * *s2++;
+   return ip;
+}
+
+static float
+get_ip_image_state (unsigned image, unsigned address, unsigned level,
+		    unsigned domain, coder_t *c) /* ip.c:46-70 */
+{
+   if (level <= (unsigned) c->opt.images_level)
+      return standard_ip_image_state (address, level, domain, c);
+   return c->ip_images_state [domain][image];
+}
+
+static float
+get_ip_state_state (unsigned d1, unsigned d2, unsigned level,
+		    const coder_t *c) /* ip.c:156-182 */
+{
+   c->st->ipss_lookups++;
+   if (level <= (unsigned) c->opt.images_level)
+      return standard_ip_state_state (d1, d2, level, c);
+   if (d2 < d1)
+      return c->ip_states_state [d1][level][d2];
+   return c->ip_states_state [d2][level][d1];
+}
+
+static void
+compute_ip_images_state (unsigned image, unsigned address, unsigned level,
+			 unsigned n, unsigned from, coder_t *c) /* ip.c:72-154 */
+{
+   const fo_wfa_t *w  = c->wfa;
+   const unsigned  il = (unsigned) c->opt.images_level;
+   unsigned	   state, label;
+
+   if (level <= il)
+      return;
+   if (level > il + 1)
+      compute_ip_images_state (MAXLABELS * image + 1, address * MAXLABELS,
+			       level - 1, MAXLABELS * n, from, c);
+   for (label = 0; label < MAXLABELS; label++)
+      for (state = from; state < w->states; state++)
+	 if (need_image (state, w))
+	 {
+	    unsigned edge, count;
+	    int	     domain;
+	    float   *dst, *src;
+
+	    if ((domain = w->tree [state][label]) != RANGE)
+	    {
+	       dst = c->ip_images_state [state] + image;
+	       if (level > il + 1)
+	       {
+		  src = c->ip_images_state [domain] + image * MAXLABELS + label + 1;
+		  for (count = n; count; count--, src += MAXLABELS)
+		     *dst++ += *src;
+	       }
+	       else
+	       {
+		  unsigned newadr = address * MAXLABELS + label;
+
+		  for (count = n; count; count--, newadr += MAXLABELS)
+		     *dst++ += standard_ip_image_state (newadr, level - 1,
+							(unsigned) domain, c);
+	       }
+	    }
+	    for (edge = 0; (domain = w->into [state][label][edge]) != NO_EDGE;
+		 edge++)
+	    {
+	       float weight = w->weight [state][label][edge];
+
+	       dst = c->ip_images_state [state] + image;
+	       if (level > il + 1)
+	       {
+		  src = c->ip_images_state [domain] + image * MAXLABELS + label + 1;
+		  for (count = n; count; count--, src += MAXLABELS)
+		     *dst++ += *src * weight;
+	       }
+	       else
+	       {
+		  unsigned newadr = address * MAXLABELS + label;
+
+		  for (count = n; count; count--, newadr += MAXLABELS)
+		     *dst++ += weight * standard_ip_image_state (newadr, level - 1,
+								 (unsigned) domain, c);
+	       }
+	    }
+	 }
+}
+
+static void
+compute_ip_states_state (unsigned from, unsigned to, coder_t *c) /* ip.c:184-260 */
+{
+   const fo_wfa_t *w = c->wfa;
+   unsigned	   level, s1, s2;
+
+   for (level = (unsigned) c->opt.images_level + 1;
+	level <= (unsigned) c->opt.lc_max_level; level++)
+      for (s1 = from; s1 <= to; s1++)
+	 for (s2 = 0; s2 <= s1; s2++)
+	    if (need_image (s2, w))
+	    {
+	       unsigned label;
+	       float	ip = 0;
+
+	       for (label = 0; label < MAXLABELS; label++)
+	       {
+		  int	   d1, d2;
+		  unsigned e1, e2;
+		  float	   sum, w2;
+
+		  if ((d1 = w->tree [s1][label]) != RANGE)
+		  {
+		     sum = 0;
+		     if ((d2 = w->tree [s2][label]) != RANGE)
+			sum = get_ip_state_state ((unsigned) d1, (unsigned) d2,
+						  level - 1, c);
+		     for (e2 = 0; (d2 = w->into [s2][label][e2]) != NO_EDGE; e2++)
+		     {
+			w2   = w->weight [s2][label][e2];
+			sum += w2 * get_ip_state_state ((unsigned) d1, (unsigned) d2,
+							level - 1, c);
+		     }
+		     ip += sum;
+		  }
+		  for (e1 = 0; (d1 = w->into [s1][label][e1]) != NO_EDGE; e1++)
+		  {
+		     float w1 = w->weight [s1][label][e1];
+
+		     sum = 0;
+		     if ((d2 = w->tree [s2][label]) != RANGE)
+			sum = get_ip_state_state ((unsigned) d1, (unsigned) d2,
+						  level - 1, c);
+		     for (e2 = 0; (d2 = w->into [s2][label][e2]) != NO_EDGE; e2++)
+		     {
+			w2   = w->weight [s2][label][e2];
+			sum += w2 * get_ip_state_state ((unsigned) d1, (unsigned) d2,
+							level - 1, c);
+		     }
+		     ip += w1 * sum;
+		  }
+	       }
+	       c->ip_states_state [s1][level][s2] = ip;
+	    }
+}
+
+/*****************************************************************************
+		    state bookkeeping  (codec/control.c, wfalib.c)
+*****************************************************************************/
+
+static void
+compute_images (unsigned from, unsigned to, coder_t *c) /* control.c:205-257 */
+{
+   const fo_wfa_t *w = c->wfa;
+   unsigned	   label, level, state;
+
+   for (level = 1; level <= (unsigned) c->opt.images_level; level++)
+      for (state = from; state <= to; state++)
+	 for (label = 0; label < MAXLABELS; label++)
+	 {
+	    float   *dst, *src;
+	    unsigned edge, n;
+	    int	     domain;
+
+	    if ((domain = w->tree [state][label]) != RANGE)
+	    {
+	       dst = c->images_of_state [state] + address_of_level (level)
+		     + label * size_of_level (level - 1);
+	       src = c->images_of_state [domain] + address_of_level (level - 1);
+	       memcpy (dst, src, size_of_level (level - 1) * sizeof (float));
+	    }
+	    for (edge = 0; (domain = w->into [state][label][edge]) != NO_EDGE;
+		 edge++)
+	    {
+	       float weight = w->weight [state][label][edge];
+
+	       dst = c->images_of_state [state] + address_of_level (level)
+		     + label * size_of_level (level - 1);
+	       src = c->images_of_state [domain] + address_of_level (level - 1);
+	       for (n = size_of_level (level - 1); n; n--)
+		  *dst++ += *src++ * weight;
+	    }
+	 }
+}
+
+static float
+compute_final_distribution (unsigned state, const fo_wfa_t *w) /* wfalib.c:154-180 */
+{
+   unsigned label, edge;
+   float    final = 0;
+   int	    domain;
+
+   for (label = 0; label < MAXLABELS; label++)
+   {
+      if ((domain = w->tree [state][label]) != RANGE)
+	 final += w->final_distribution [domain];
+      for (edge = 0; (domain = w->into [state][label][edge]) != NO_EDGE; edge++)
+	 final += w->weight [state][label][edge] * w->final_distribution [domain];
+   }
+   return final / MAXLABELS;
+}
+
+static void
+append_edge (unsigned from, unsigned into, float weight, unsigned label,
+	     fo_wfa_t *w) /* wfalib.c:233-274 */
+{
+   unsigned new, edge;
+
+   for (new = 0; (w->into [from][label][new] != NO_EDGE
+		  && w->into [from][label][new] < (int) into); new++)
+      ;
+   for (edge = new; w->into [from][label][edge] != NO_EDGE; edge++)
+      ;
+   for (edge++; edge != new; edge--)
+   {
+      w->into [from][label][edge]   = w->into [from][label][edge - 1];
+      w->weight [from][label][edge] = w->weight [from][label][edge - 1];
+   }
+   w->into [from][label][edge]	 = (int16_t) into;
+   w->weight [from][label][edge] = weight;
+}
+
+static void
+remove_states (unsigned from, fo_wfa_t *w) /* wfalib.c:276-310 */
+{
+   unsigned state, label;
+
+   for (state = from; state < w->states; state++)
+   {
+      for (label = 0; label < MAXLABELS; label++)
+      {
+	 w->into [state][label][0] = NO_EDGE;
+	 w->tree [state][label]	   = RANGE;
+	 w->y_state [state][label] = RANGE;
+      }
+      w->domain_type [state] = 0;
+   }
+   w->states = from;
+}
+
+static void
+trace_state (coder_t *c, unsigned state, int auxiliary, unsigned level, float final)
+{
+   const fo_wfa_t *w = c->wfa;
+
+   if (!c->trace)
+      return;
+   fprintf (c->trace, "st %u %d %u %08x %d %d\n", state, auxiliary, level,
+	    fbits (final), (int) w->tree [state][0], (int) w->tree [state][1]);
+   if (!auxiliary && state < 12)
+   {
+      unsigned i, l, t;
+
+      fprintf (c->trace, "img %u", state);
+      for (i = 0; i < size_of_tree ((unsigned) c->opt.images_level); i++)
+	 fprintf (c->trace, " %08x", fbits (c->images_of_state [state][i]));
+      fprintf (c->trace, "\n");
+      for (l = (unsigned) c->opt.images_level + 1;
+	   l <= (unsigned) c->opt.lc_max_level; l++)
+      {
+	 fprintf (c->trace, "ipss %u %u", state, l);
+	 for (t = 0; t <= state; t++)
+	    fprintf (c->trace, " %08x",
+		     need_image (t, w) ? fbits (c->ip_states_state [state][l][t]) : 0);
+	 fprintf (c->trace, "\n");
+      }
+   }
+}
+
+static void
+append_state (int auxiliary, float final, unsigned level_of_state,
+	      coder_t *c) /* control.c:48-131 */
+{
+   fo_wfa_t *w = c->wfa;
+   unsigned  s = w->states, level;
+
+   w->final_distribution [s] = final;
+   w->level_of_state [s]     = (uint8_t) level_of_state;
+   if (!auxiliary)
+   {
+      w->domain_type [s] = USE_DOMAIN_MASK;
+      clear_or_alloc (&c->images_of_state [s],
+		      size_of_tree ((unsigned) c->opt.images_level));
+      for (level = (unsigned) c->opt.images_level + 1;
+	   level <= (unsigned) c->opt.lc_max_level; level++)
+	 clear_or_alloc (&c->ip_states_state [s][level], s + 1);
+      clear_or_alloc (&c->ip_images_state [s], size_of_tree (c->products_level));
+      c->images_of_state [s][0] = final;
+      compute_images (s, s, c);
+      compute_ip_states_state (s, s, c);
+   }
+   else
+   {
+      w->domain_type [s] = 0;
+      free (c->images_of_state [s]);
+      c->images_of_state [s] = NULL;
+      for (level = 0; level < MAXLEVEL; level++)
+      {
+	 free (c->ip_states_state [s][level]);
+	 c->ip_states_state [s][level] = NULL;
+      }
+      free (c->ip_images_state [s]);
+      c->ip_images_state [s] = NULL;
+   }
+   c->st->append_states++;
+   trace_state (c, s, auxiliary, level_of_state, final);
+   w->states++;
+   if (w->states >= MAXSTATES)
+      fail (c, "Maximum number of states reached!");
+}
+
+static void
+append_basis_states (coder_t *c) /* control.c:133-173 + input/basis.c:76-104,126-131 */
+{
+   fo_wfa_t *w = c->wfa;
+   unsigned  state, level;
+
+   /* "small.fco": state 0 = constant 128; s1, s2 as in input/basis.c:126-131 */
+   w->basis_states = w->states = 3;
+   w->domain_type [0]	     = USE_DOMAIN_MASK;
+   w->final_distribution [0] = 128;
+   append_edge (0, 0, 1.0f, 0, w);
+   append_edge (0, 0, 1.0f, 1, w);
+   w->final_distribution [1] = 64;
+   w->final_distribution [2] = 64;
+   w->domain_type [1]	     = USE_DOMAIN_MASK;
+   w->domain_type [2]	     = USE_DOMAIN_MASK;
+   append_edge (1, 2, 0.5f, 0, w);
+   append_edge (1, 2, 0.5f, 1, w);
+   append_edge (1, 0, 0.5f, 1, w);
+   append_edge (2, 1, 1.0f, 0, w);
+   append_edge (2, 1, 1.0f, 1, w);
+
+   for (state = 0; state < w->basis_states; state++)
+   {
+      clear_or_alloc (&c->images_of_state [state],
+		      size_of_tree ((unsigned) c->opt.images_level));
+      for (level = (unsigned) c->opt.images_level + 1;
+	   level <= (unsigned) c->opt.lc_max_level; level++)
+	 clear_or_alloc (&c->ip_states_state [state][level], state + 1);
+      clear_or_alloc (&c->ip_images_state [state],
+		      size_of_tree (c->products_level));
+      c->images_of_state [state][0] = w->final_distribution [state];
+      w->level_of_state [state]	    = (uint8_t) -1;
+   }
+   compute_images (0, w->basis_states - 1, c);
+   compute_ip_states_state (0, w->basis_states - 1, c);
+}
+
+/*****************************************************************************
+		     matching pursuit  (codec/approx.c)
+*****************************************************************************/
+
+typedef struct mp
+{
+   int16_t exclude [MAXEDGES];
+   int16_t indices [MAXEDGES + 1];
+   int16_t into [MAXEDGES + 1];
+   float   weight [MAXEDGES];
+   float   matrix_bits, weights_bits, err, costs;
+} mp_t;
+
+/* file-static work arrays of approx.c:279-305 */
+static float   norm_ortho_vector [MAXSTATES];
+static float   ip_image_ortho_vector [MAXEDGES];
+static float   ip_domain_ortho_vector [MAXSTATES][MAXEDGES];
+static float   rem_denominator [MAXSTATES];
+static float   rem_numerator [MAXSTATES];
+static uint8_t used [MAXSTATES];
+
+static void
+orthogonalize (unsigned index, unsigned n, unsigned level, float min_norm,
+	       const int16_t *domain_blocks, coder_t *c) /* approx.c:644-699 */
+{
+   unsigned domain;
+
+   ip_image_ortho_vector [n] = rem_numerator [index];
+   norm_ortho_vector [n]     = rem_denominator [index];
+   c->st->ortho_steps++;
+
+   for (domain = 0; domain_blocks [domain] >= 0; domain++)
+      if (!used [domain])
+      {
+	 unsigned k;
+	 float	  tmp = get_ip_state_state ((unsigned) domain_blocks [index],
+					    (unsigned) domain_blocks [domain],
+					    level, c);
+
+	 for (k = 0; k < n; k++)
+	    tmp -= ip_domain_ortho_vector [domain][k] / norm_ortho_vector [k]
+		   * ip_domain_ortho_vector [index][k];
+	 ip_domain_ortho_vector [domain][n] = tmp;
+	 rem_denominator [domain] -= (tmp * tmp) / norm_ortho_vector [n];
+	 rem_numerator [domain]	  -= ip_image_ortho_vector [n]
+				     / norm_ortho_vector [n]
+				     * ip_domain_ortho_vector [domain][n];
+	 if (rem_denominator [domain] / size_of_level (level) < min_norm)
+	    used [domain] = 1;
+      }
+}
+
+static void
+matching_pursuit (mp_t *mp, int full_search, float price, unsigned max_edges,
+		  int y_state, const range_t *range, coder_t *c)
+/* approx.c:317-642 */
+{
+   const fo_wfa_t *w = c->wfa;
+   unsigned	   n, domain, best_n = 0;
+   int		   index;
+   float	   norm, additional_bits;
+   const float	   min_norm = 2e-3f;
+   const unsigned  size	    = size_of_level (range->level);
+   static int16_t  domain_blocks [MAXSTATES + 2];
+
+   c->st->mp_calls++;
+   rle_generate (domain_blocks, y_state, w->domain_type, &c->pool);
+   for (domain = 0; domain_blocks [domain] >= 0; domain++)
+   {
+      used [domain] = 0;
+      rem_denominator [domain]
+	 = get_ip_state_state ((unsigned) domain_blocks [domain],
+			       (unsigned) domain_blocks [domain], range->level, c);
+      if (rem_denominator [domain] / size < min_norm)
+	 used [domain] = 1;
+      else
+	 rem_numerator [domain]
+	    = get_ip_image_state (range->image, range->address, range->level,
+				  (unsigned) domain_blocks [domain], c);
+      if (!used [domain] && fabs ((double) rem_numerator [domain]) < min_norm)
+	 used [domain] = 1;
+   }
+   c->st->mp_domains += domain;
+
+   for (n = 0; mp->exclude [n] != NO_EDGE; n++)
+      used [mp->exclude [n]] = 1;
+
+   for (norm = 0, n = 0; n < size; n++)
+      norm += c->pixels [range->address * size + n]
+	      * c->pixels [range->address * size + n];
+
+   additional_bits = range->tree_bits + 0.0f + 0.0f + 0.0f + 0.0f;
+
+   mp->err	    = norm;
+   mp->weights_bits = 0;
+   mp->matrix_bits  = rle_bits (domain_blocks, NULL, y_state, w->domain_type,
+				&c->pool);
+   mp->costs	    = (mp->matrix_bits + mp->weights_bits + additional_bits)
+		      * price + mp->err;
+
+   n = 0;
+   do
+   {
+      float min_matrix_bits = 0, min_weights_bits = 0, min_error = 0;
+      float min_weight [MAXEDGES];
+      float min_costs = full_search ? MAXCOSTS : mp->costs;
+
+      for (index = -1, domain = 0; domain_blocks [domain] >= 0; domain++)
+	 if (!used [domain])
+	 {
+	    float matrix_bits, weights_bits;
+
+	    c->st->pass1++;
+	    {
+	       int16_t	vectors [MAXEDGES + 1], states [MAXEDGES + 1];
+	       float	weights [MAXEDGES + 1];
+	       unsigned i, k;
+
+	       for (i = 0, k = 0; k < n; k++)
+		  if (mp->weight [k] != 0)
+		  {
+		     vectors [i] = mp->indices [k];
+		     states [i]	 = domain_blocks [vectors [i]];
+		     weights [i] = mp->weight [k];
+		     i++;
+		  }
+	       vectors [i]     = (int16_t) domain;
+	       states [i]      = domain_blocks [domain];
+	       weights [i]     = 0.5f;
+	       vectors [i + 1] = -1;
+	       states [i + 1]  = -1;
+
+	       weights_bits = aac_bits (weights, states, range->level, &c->coeff);
+	       matrix_bits  = rle_bits (domain_blocks, vectors, y_state,
+					w->domain_type, &c->pool);
+	    }
+	    if (((matrix_bits + weights_bits + additional_bits) * price
+		 + mp->err
+		 - (rem_numerator [domain] * rem_numerator [domain])
+		 / rem_denominator [domain]) < min_costs)
+	    {
+	       unsigned k;
+	       int	l;
+	       float	m_bits, w_bits, costs, m_err;
+	       float	r [MAXEDGES], f [MAXEDGES];
+	       int	v [MAXEDGES];
+
+	       c->st->pass2++;
+	       f [n] = rem_numerator [domain] / rem_denominator [domain];
+	       v [n] = (int) domain;
+	       for (k = 0; k < n; k++)
+	       {
+		  f [k] = ip_image_ortho_vector [k] / norm_ortho_vector [k];
+		  v [k] = mp->indices [k];
+	       }
+	       for (l = (int) n; l >= 0; l--)
+	       {
+		  const rpf_t *rpf = domain_blocks [v [l]] ? &c->coeff.rpf
+							   : &c->coeff.dc_rpf;
+
+		  r [l] = f [l] = btor (rtob (f [l], rpf), rpf);
+		  for (k = 0; k < (unsigned) l; k++)
+		     f [k] -= f [l] * ip_domain_ortho_vector [v [l]][k]
+			      / norm_ortho_vector [k];
+	       }
+	       {
+		  int16_t vectors [MAXEDGES + 1], states [MAXEDGES + 1];
+		  float	  weights [MAXEDGES + 1];
+		  int	  i;
+
+		  for (i = 0, k = 0; k <= n; k++)
+		     if (f [k] != 0)
+		     {
+			vectors [i] = (int16_t) v [k];
+			states [i]  = domain_blocks [v [k]];
+			weights [i] = f [k];
+			i++;
+		     }
+		  vectors [i] = -1;
+		  states [i]  = -1;
+		  w_bits = aac_bits (weights, states, range->level, &c->coeff);
+		  m_bits = rle_bits (domain_blocks, vectors, y_state,
+				     w->domain_type, &c->pool);
+	       }
+	       /* the <v_l, o_n> loop of approx.c:554-569 only writes entries [..][n]
+		  that are never read again; it is kept because it is
+		  cheap here and keeps the work arrays bit-identical to the reference's */
+	       for (l = 0; (unsigned) l <= n; l++)
+	       {
+		  float a = get_ip_state_state ((unsigned) domain_blocks [v [l]],
+						(unsigned) domain_blocks [domain],
+						range->level, c);
+
+		  for (k = 0; k < n; k++)
+		     a -= ip_domain_ortho_vector [v [l]][k] / norm_ortho_vector [k]
+			  * ip_domain_ortho_vector [domain][k];
+		  ip_domain_ortho_vector [v [l]][n] = a;
+	       }
+	       norm_ortho_vector [n]	 = rem_denominator [domain];
+	       ip_image_ortho_vector [n] = rem_numerator [domain];
+
+	       for (k = 0; k <= n; k++)
+		  for (l = (int) k + 1; (unsigned) l <= n; l++)
+		     r [k] += ip_domain_ortho_vector [v [l]][k] * r [l]
+			      / norm_ortho_vector [k];
+	       m_err = norm;
+	       for (k = 0; k <= n; k++)
+		  m_err += (r [k] * r [k]) * norm_ortho_vector [k]
+			   - 2 * r [k] * ip_image_ortho_vector [k];
+
+	       costs = (m_bits + w_bits + additional_bits) * price + m_err;
+	       if (costs < min_costs)
+	       {
+		  index		   = (int) domain;
+		  min_costs	   = costs;
+		  min_matrix_bits  = m_bits;
+		  min_weights_bits = w_bits;
+		  min_error	   = m_err;
+		  for (k = 0; k <= n; k++)
+		     min_weight [k] = f [k];
+	       }
+	    }
+	 }
+
+      if (index >= 0)
+      {
+	 if (min_costs < mp->costs)
+	 {
+	    unsigned k;
+
+	    mp->costs	     = min_costs;
+	    mp->err	     = min_error;
+	    mp->matrix_bits  = min_matrix_bits;
+	    mp->weights_bits = min_weights_bits;
+	    for (k = 0; k <= n; k++)
+	       mp->weight [k] = min_weight [k];
+	    best_n = n + 1;
+	 }
+	 mp->indices [n] = (int16_t) index;
+	 mp->into [n]	 = domain_blocks [index];
+	 used [index]	 = 1;
+	 orthogonalize ((unsigned) index, n, range->level, min_norm,
+			domain_blocks, c);
+	 n++;
+      }
+   }
+   while (n < max_edges && index >= 0);
+
+   mp->indices [best_n] = NO_EDGE;
+   mp->costs = (mp->matrix_bits + mp->weights_bits + additional_bits) * price
+	       + mp->err;
+}
+
+static int
+is_overflow_weight (float weight, int index, const coder_t *c) /* approx.c:172-176 */
+{
+   const rpf_t *rpf = index ? &c->coeff.rpf : &c->coeff.dc_rpf;
+
+   return weight == btor (rtob (200, rpf), rpf)
+	  || weight == btor (rtob (-200, rpf), rpf);
+}
+
+static float
+approximate_range (float max_costs, float price, int max_edges, int y_state,
+		   range_t *range, coder_t *c) /* approx.c:74-271 */
+{
+   const fo_wfa_t *w = c->wfa;
+   mp_t		   mp;
+
+   memset (&mp, 0, sizeof mp);	/* the reference leaves it uninitialised (quirk C11) */
+   mp.exclude [0] = NO_EDGE;
+   matching_pursuit (&mp, c->opt.full_search, price, (unsigned) max_edges,
+		     y_state, range, c);
+
+   if (c->opt.second_domain_block)
+   {
+      mp_t tmp = mp;
+
+      tmp.exclude [0] = tmp.indices [0];
+      tmp.exclude [1] = NO_EDGE;
+      matching_pursuit (&tmp, c->opt.full_search, price, (unsigned) max_edges,
+			y_state, range, c);
+      if (tmp.costs < mp.costs)
+	 mp = tmp;
+   }
+   if (c->opt.check_for_underflow)
+   {
+      int  iteration = -1;
+      mp_t tmp	     = mp;
+
+      do
+      {
+	 int i;
+
+	 iteration++;
+	 tmp.exclude [iteration] = NO_EDGE;
+	 for (i = 0; tmp.indices [i] != NO_EDGE; i++)
+	    if (tmp.weight [i] == 0)
+	    {
+	       tmp.exclude [iteration] = tmp.indices [i];
+	       break;
+	    }
+	 if (tmp.exclude [iteration] != NO_EDGE)
+	 {
+	    tmp.exclude [iteration + 1] = NO_EDGE;
+	    matching_pursuit (&tmp, c->opt.full_search, price,
+			      (unsigned) max_edges, y_state, range, c);
+	    if (tmp.costs < mp.costs)
+	       mp = tmp;
+	 }
+      }
+      while (tmp.exclude [iteration] != NO_EDGE && iteration < MAXEDGES - 1);
+   }
+   if (c->opt.check_for_overflow)
+   {
+      int  iteration = -1;
+      mp_t tmp	     = mp;
+
+      do
+      {
+	 int i;
+
+	 iteration++;
+	 tmp.exclude [iteration] = NO_EDGE;
+	 for (i = 0; tmp.indices [i] != NO_EDGE; i++)
+	    if (is_overflow_weight (tmp.weight [i], tmp.indices [i], c))
+	    {
+	       tmp.exclude [iteration] = tmp.indices [i];
+	       break;
+	    }
+	 if (tmp.exclude [iteration] != NO_EDGE)
+	 {
+	    tmp.exclude [iteration + 1] = NO_EDGE;
+	    matching_pursuit (&tmp, c->opt.full_search, price,
+			      (unsigned) max_edges, y_state, range, c);
+	    if (tmp.costs < mp.costs)
+	       mp = tmp;
+	 }
+      }
+      while (tmp.exclude [iteration] != NO_EDGE && iteration < MAXEDGES - 1);
+   }
+
+   if (mp.costs < max_costs)
+   {
+      int	     edge, new_index = 0, old_index;
+      static int16_t domain_blocks [MAXSTATES + 2];
+
+      for (old_index = 0; mp.indices [old_index] != NO_EDGE; old_index++)
+	 if (mp.weight [old_index] != 0)
+	 {
+	    mp.indices [new_index] = mp.indices [old_index];
+	    mp.into [new_index]	   = mp.into [old_index];
+	    mp.weight [new_index]  = mp.weight [old_index];
+	    new_index++;
+	 }
+      mp.indices [new_index] = NO_EDGE;
+      mp.into [new_index]    = NO_EDGE;
+
+      rle_generate (domain_blocks, y_state, w->domain_type, &c->pool);
+      rle_update (domain_blocks, mp.indices, y_state, w->domain_type, &c->pool);
+      aac_update (mp.weight, mp.into, range->level, &c->coeff);
+
+      for (edge = 0; mp.indices [edge] != NO_EDGE; edge++)
+      {
+	 range->into [edge]   = mp.into [edge];
+	 range->weight [edge] = mp.weight [edge];
+      }
+      range->into [edge]  = NO_EDGE;
+      range->matrix_bits  = mp.matrix_bits;
+      range->weights_bits = mp.weights_bits;
+      range->err	  = mp.err;
+      c->st->accepted++;
+   }
+   else
+   {
+      range->into [0] = NO_EDGE;
+      mp.costs	      = MAXCOSTS;
+   }
+   return mp.costs;
+}
+
+/*****************************************************************************
+		   bintree subdivision  (codec/subdivide.c)
+*****************************************************************************/
+
+static void
+cut_to_bintree (float *dst, const int16_t *src, unsigned src_width,
+		unsigned src_height, unsigned x0, unsigned y0, unsigned width,
+		unsigned height) /* subdivide.c:504-541 */
+{
+   const unsigned mask01 = 0x555555, mask10 = 0xaaaaaa;
+   unsigned	  x, y, xmask, ymask;
+
+   ymask = 0;
+   for (y = y0; y < y0 + height; y++, ymask = (ymask + mask10 + 1) & mask01)
+   {
+      xmask = 0;
+      for (x = x0; x < x0 + width; x++, xmask = (xmask + mask01 + 1) & mask10)
+	 if (y >= src_height || x >= src_width)
+	    dst [xmask | ymask] = 0;
+	 else
+	    dst [xmask | ymask] = (float) (src [y * src_width + x] / 16);
+   }
+}
+
+static void
+init_range (range_t *range, unsigned band, coder_t *c) /* subdivide.c:612-644 */
+{
+   const fo_wfa_t *w = c->wfa;
+   unsigned	   state, nstates = 0;
+
+   for (state = 0; state < w->states; state++)
+      if (need_image (state, w))
+      {
+	 memset (c->ip_images_state [state], 0,
+		 size_of_tree (c->products_level) * sizeof (float));
+	 nstates++;
+      }
+   cut_to_bintree (c->pixels, c->planes [band], (unsigned) c->opt.width,
+		   (unsigned) c->opt.height, range->x, range->y,
+		   width_of_level (range->level), height_of_level (range->level));
+   range->address = range->image = 0;
+   compute_ip_images_state (0, 0, range->level, 1, 0, c);
+
+   c->st->blocks++;
+   c->st->ip_bytes += 4ull * size_of_level (range->level)
+		      + 4ull * (size_of_tree ((unsigned) c->opt.images_level)
+				+ size_of_tree (c->products_level)) * nstates;
+   if (c->trace && c->ipis_calls < 4)
+   {
+      unsigned i;
+
+      fprintf (c->trace, "pix %u", c->ipis_calls);
+      for (i = 0; i < size_of_level (range->level); i++)
+	 fprintf (c->trace, " %d", (int) c->pixels [i]);
+      fprintf (c->trace, "\n");
+      for (state = 0; state < w->states && state < 40; state++)
+	 if (need_image (state, w))
+	 {
+	    fprintf (c->trace, "ipis %u %u", c->ipis_calls, state);
+	    for (i = 0; i < size_of_tree (c->products_level); i++)
+	       fprintf (c->trace, " %08x", fbits (c->ip_images_state [state][i]));
+	    fprintf (c->trace, "\n");
+	 }
+      c->ipis_calls++;
+   }
+}
+
+static void
+init_new_state (int auxiliary_state, range_t *range, const range_t *child,
+		const int *y_state, coder_t *c) /* subdivide.c:549-610 */
+{
+   fo_wfa_t *w = c->wfa;
+   unsigned  label, edge;
+   int	     state_is_domain = 0;
+
+   if (!auxiliary_state)
+      state_is_domain = rle_append (&c->pool, w->states);
+   /* the delta pool on a still is the "constant" pool whose append() always says
+      YES (domain-pool.c:962-967, coder.c:720-725; options.normal_domains = YES) */
+   if (!auxiliary_state)
+      state_is_domain = 1 || state_is_domain;
+
+   range->into [0] = NO_EDGE;
+   range->tree	   = (int) w->states;
+   for (label = 0; label < MAXLABELS; label++)
+   {
+      w->tree [w->states][label]    = (int16_t) child [label].tree;
+      w->y_state [w->states][label] = (int16_t) y_state [label];
+      w->x [w->states][label]	    = (uint16_t) child [label].x;
+      w->y [w->states][label]	    = (uint16_t) child [label].y;
+      /* append_transitions, control.c:175-197 */
+      w->y_column [w->states][label] = 0;
+      for (edge = 0; child [label].into [edge] != NO_EDGE; edge++)
+      {
+	 append_edge (w->states, (unsigned) child [label].into [edge],
+		      child [label].weight [edge], label, w);
+	 if (child [label].into [edge] == w->y_state [w->states][label])
+	    w->y_column [w->states][label] = 1;
+      }
+   }
+   append_state (!state_is_domain, compute_final_distribution (w->states, w),
+		 range->level, c);
+}
+
+static float
+subdivide (float max_costs, unsigned band, int y_state, range_t *range,
+	   coder_t *c) /* subdivide.c:60-502, still-image path (no prediction) */
+{
+   fo_wfa_t    *w = c->wfa;
+   float	subdivide_costs, lincomb_costs, price;
+   int		new_y_state [MAXLABELS];
+   unsigned	states;
+   rle_model_t *domain_model, *lc_domain_model;
+   aac_model_t	coeff_model, lc_coeff_model;
+   tree_model_t tree_model;
+   range_t	lrange, rrange, child [MAXLABELS];
+
+   c->st->subdivide_calls++;
+   range->into [0] = NO_EDGE;
+   range->tree	   = RANGE;
+   if (range->level < 3)
+      return MAXCOSTS;
+   if (range->x >= (unsigned) c->opt.width || range->y >= (unsigned) c->opt.height)
+      return 0;
+
+   if (range->level == (unsigned) c->opt.lc_max_level)
+      init_range (range, band, c);
+
+   price = c->price;
+   if (band != 0)
+      price *= c->opt.chroma_decrease;
+
+   if (band != 0)
+   {
+      unsigned label;
+
+      for (label = 0; label < MAXLABELS; label++)
+	 if (y_state != RANGE)
+	    new_y_state [label] = w->tree [y_state][label];
+	 else
+	    new_y_state [label] = RANGE;
+   }
+   else
+      new_y_state [0] = new_y_state [1] = RANGE;
+
+   /* snapshot of every model the recursion may modify (subdivide.c:188-194) */
+   domain_model	   = malloc (sizeof (rle_model_t));
+   lc_domain_model = malloc (sizeof (rle_model_t));
+   rle_copy (domain_model, &c->pool);
+   coeff_model = c->coeff.model;
+   tree_model  = c->tree;
+   states      = w->states;
+
+   /* alternative 1: linear combination */
+   if (range->level <= (unsigned) c->opt.lc_max_level)
+   {
+      lrange		  = *range;
+      lrange.tree	  = RANGE;
+      lrange.tree_bits	  = tree_bits (0, lrange.level, &c->tree);
+      lrange.matrix_bits  = 0;
+      lrange.weights_bits = 0;
+      lincomb_costs = approximate_range (max_costs, price, c->opt.max_elements,
+					 y_state, &lrange, c);
+      if (c->trace)
+      {
+	 int e;
+
+	 fprintf (c->trace, "lc %u %u %u %u %u %u %d %u %08x %08x %08x",
+		  c->lc_calls, lrange.level, lrange.image, lrange.address,
+		  lrange.x, lrange.y, y_state, w->states, fbits (max_costs),
+		  fbits (price), fbits (lincomb_costs));
+	 if (lrange.into [0] != NO_EDGE)
+	 {
+	    fprintf (c->trace, " %08x %08x %08x :", fbits (lrange.err),
+		     fbits (lrange.matrix_bits), fbits (lrange.weights_bits));
+	    for (e = 0; lrange.into [e] != NO_EDGE; e++)
+	       fprintf (c->trace, " %d:%08x", (int) lrange.into [e],
+			fbits (lrange.weight [e]));
+	 }
+	 fprintf (c->trace, "\n");
+      }
+      c->lc_calls++;
+   }
+   else
+      lincomb_costs = MAXCOSTS;
+
+   /* keep the "lc" models, restore the snapshot (subdivide.c:226-237) */
+   rle_copy (lc_domain_model, &c->pool);
+   lc_coeff_model = c->coeff.model;
+   rle_copy (&c->pool, domain_model);
+   c->coeff.model = coeff_model;
+
+   /* alternative 2: recursive subdivision */
+   if (range->level > (unsigned) c->opt.lc_min_level)
+   {
+      unsigned label;
+
+      memset (child, 0, sizeof child);
+      rrange		  = *range;
+      rrange.tree_bits	  = tree_bits (1, rrange.level, &c->tree);
+      rrange.matrix_bits  = 0;
+      rrange.weights_bits = 0;
+      rrange.err	  = 0;
+      subdivide_costs = (rrange.tree_bits + rrange.weights_bits
+			 + rrange.matrix_bits + 0.0f + 0.0f + 0.0f + 0.0f) * price;
+
+      for (label = 0; label < MAXLABELS; label++)
+      {
+	 float remaining_costs;
+
+	 child [label].image   = rrange.image * MAXLABELS + label + 1;
+	 child [label].address = rrange.address * MAXLABELS + label;
+	 child [label].level   = rrange.level - 1;
+	 child [label].x = rrange.level & 1
+			   ? rrange.x
+			   : rrange.x + label * width_of_level (rrange.level - 1);
+	 child [label].y = rrange.level & 1
+			   ? rrange.y + label * height_of_level (rrange.level - 1)
+			   : rrange.y;
+
+	 if (label && rrange.level <= (unsigned) c->opt.lc_max_level)
+	    compute_ip_images_state (child [label].image, child [label].address,
+				     child [label].level, 1, states, c);
+
+	 remaining_costs = fmin2 (lincomb_costs, max_costs) - subdivide_costs;
+	 if (remaining_costs > 0)
+	    subdivide_costs += subdivide (remaining_costs, band,
+					  new_y_state [label], &child [label], c);
+
+	 if (subdivide_costs >= fmin2 (lincomb_costs, max_costs))
+	 {
+	    subdivide_costs = MAXCOSTS;
+	    break;
+	 }
+	 rrange.err	     += child [label].err;
+	 rrange.tree_bits    += child [label].tree_bits;
+	 rrange.matrix_bits  += child [label].matrix_bits;
+	 rrange.weights_bits += child [label].weights_bits;
+
+	 tree_update (child [label].tree != RANGE, child [label].level, &c->tree);
+      }
+   }
+   else
+      subdivide_costs = MAXCOSTS;
+
+   if (lincomb_costs >= MAXCOSTS && subdivide_costs >= MAXCOSTS)
+   {
+      rle_copy (&c->pool, domain_model);
+      c->coeff.model = coeff_model;
+      c->tree	     = tree_model;
+      if (w->states != states)
+	 remove_states (states, w);
+      free (domain_model);
+      free (lc_domain_model);
+      return MAXCOSTS;
+   }
+   else if (lincomb_costs < subdivide_costs)
+   {
+      rle_copy (&c->pool, lc_domain_model);
+      c->coeff.model = lc_coeff_model;
+      c->tree	     = tree_model;
+      *range	     = lrange;
+      if (w->states != states)
+	 remove_states (states, w);
+      free (domain_model);
+      free (lc_domain_model);
+      return lincomb_costs;
+   }
+   else
+   {
+      int aux = band > 0
+		|| range->x + width_of_level (range->level) > (unsigned) c->opt.width
+		|| range->y + height_of_level (range->level) > (unsigned) c->opt.height;
+
+      init_new_state (aux, &rrange, child, new_y_state, c);
+      *range = rrange;
+      free (domain_model);
+      free (lc_domain_model);
+      return subdivide_costs;
+   }
+}
+
+/*****************************************************************************
+		  chroma pool  (domain-pool.c:854-879, wfalib.c:182-231)
+*****************************************************************************/
+
+typedef struct pair
+{
+   int16_t key, value;
+} pair_t;
+
+static int
+cmp_desc_pair (const void *a, const void *b) /* lib/misc.c sort_desc_pair */
+{
+   return (int) ((const pair_t *) b)->key - (int) ((const pair_t *) a)->key;
+}
+
+static void
+rle_chroma (unsigned max_domains, coder_t *c)
+{
+   const fo_wfa_t *w = c->wfa;
+   rle_model_t	  *m = &c->pool;
+
+   if (max_domains < m->n)
+   {
+      /* compute_hits (basis_states, states - 1, max_domains) */
+      unsigned from = w->basis_states, to = w->states - 1, n = max_domains;
+      unsigned state, label, edge;
+      int      domain;
+      pair_t  *hits    = calloc (to, sizeof (pair_t));
+      int16_t *domains;
+
+      for (domain = 0; domain < (int) to; domain++)
+      {
+	 hits [domain].value = (int16_t) domain;
+	 hits [domain].key   = 0;
+      }
+      for (state = from; state <= to; state++)
+	 for (label = 0; label < MAXLABELS; label++)
+	    for (edge = 0; (domain = w->into [state][label][edge]) != NO_EDGE;
+		 edge++)
+	       hits [domain].key++;
+      qsort (hits + 1, to - 1, sizeof (pair_t), cmp_desc_pair);
+      n	      = fmin2 (to, n);
+      domains = calloc (n + 1, sizeof (int16_t));
+      for (domain = 0; domain < (int) n && (!domain || hits [domain].key);
+	   domain++)
+	 domains [domain] = hits [domain].value;
+      n = (unsigned) domain;
+      qsort (domains, n, sizeof (int16_t), cmp_word);
+      domains [n] = -1;
+      free (hits);
+
+      for (n = 0; n < max_domains && domains [n] >= 0; n++)
+	 m->states [n] = domains [n];
+      max_domains = fmin2 (max_domains, n);
+      free (domains);
+      m->n = (uint16_t) max_domains;
+   }
+   m->y_index	  = 0;
+   m->max_domains = m->n;
+}
+
+/*****************************************************************************
+				public code
+*****************************************************************************/
+
+unsigned
+fo_image_level (unsigned width, unsigned height) /* coder.c:249-256 */
+{
+   unsigned lx = (unsigned) (log2 ((double) (width - 1)) + 1);
+   unsigned ly = (unsigned) (log2 ((double) (height - 1)) + 1);
+
+   return (lx > ly ? lx : ly) * 2 - ((ly == lx + 1) ? 1 : 0);
+}
+
+void
+fo_default_params (fo_params_t *p, int width, int height, int color,
+		   float quality, int optimize)
+/* CLI defaults: bin/cwfa.c:36-90 and :326-345 */
+{
+   memset (p, 0, sizeof *p);
+   p->width		= width;
+   p->height		= height;
+   p->color		= color;
+   p->quality		= quality;
+   p->images_level	= 5;
+   p->max_states	= 10000;
+   p->chroma_max_states = 40;
+   p->chroma_decrease	= 2.0f;
+   p->rpf_mantissa	= 3;
+   p->rpf_range_e	= 2;
+   p->dc_rpf_mantissa	= 5;
+   p->dc_rpf_range_e	= 1;
+   if (optimize <= 0)
+   {
+      p->lc_min_level = 6;
+      p->lc_max_level = 10;
+      p->max_elements = 3;
+      optimize	      = 0;
+   }
+   else
+   {
+      p->lc_min_level = 4;
+      p->lc_max_level = 12;
+      p->max_elements = 5;
+      optimize	     -= 1;
+   }
+   p->second_domain_block = optimize > 0;
+   p->check_for_overflow  = optimize > 1;
+   p->check_for_underflow = optimize > 1;
+   p->full_search	  = optimize > 1;
+}
+
+void
+fo_grey_to_plane (const uint8_t *grey, size_t n, int16_t *plane) /* image.c:352-363 */
+{
+   size_t i;
+
+   for (i = 0; i < n; i++)
+      plane [i] = (int16_t) (((int) grey [i] - 128) * 16);
+}
+
+void
+fo_rgb_to_planes (const uint8_t *rgb, size_t n, int16_t *y, int16_t *cb,
+		  int16_t *cr) /* image.c:365-386 */
+{
+   size_t i;
+
+   for (i = 0; i < n; i++)
+   {
+      int red = rgb [3 * i], green = rgb [3 * i + 1], blue = rgb [3 * i + 2];
+
+      y [i]  = (int16_t) ((+0.2989 * red + 0.5866 * green + 0.1145 * blue - 128) * 16);
+      cb [i] = (int16_t) ((-0.1687 * red - 0.3312 * green + 0.5000 * blue) * 16);
+      cr [i] = (int16_t) ((+0.5000 * red - 0.4183 * green - 0.0816 * blue) * 16);
+   }
+}
+
+int
+fo_encode (const fo_params_t *p, const int16_t *const planes [3], fo_wfa_t *out,
+	   fo_stats_t *stats, FILE *trace, char *errbuf, size_t errlen)
+{
+   static int  tables_ready = 0;
+   coder_t    *c	    = calloc (1, sizeof (coder_t));
+   fo_stats_t  dummy;
+   fo_wfa_t   *w = out;
+   unsigned    state, label, level;
+   int	       rc = 0;
+
+   if (!tables_ready)
+   {
+      init_matrix_probabilities ();
+      tables_ready = 1;
+   }
+   memset (&dummy, 0, sizeof dummy);
+   if (stats)
+      memset (stats, 0, sizeof *stats);
+   c->st     = stats ? stats : &dummy;
+   c->trace  = trace;
+   c->errbuf = errbuf;
+   c->errlen = errlen;
+   c->wfa    = w;
+   c->opt    = *p;
+
+   if (setjmp (c->env))
+   {
+      rc = 1;
+      goto cleanup;
+   }
+   if ((p->width & 1) || (p->height & 1))
+      fail (c, "Width and height of images must be even numbers.");
+   if (p->quality <= 0)
+      fail (c, "Compression quality has to be positive.");
+
+   /* alloc_wfa (wfalib.c:45-121) */
+   memset (w, 0, sizeof *w);
+   for (state = 0; state < MAXSTATES; state++)
+      for (label = 0; label < MAXLABELS; label++)
+      {
+	 w->into [state][label][0] = NO_EDGE;
+	 w->tree [state][label]	   = RANGE;
+	 w->y_state [state][label] = RANGE;
+      }
+
+   /* alloc_coder (coder.c:249-327) */
+   c->level = w->level = fo_image_level ((unsigned) p->width, (unsigned) p->height);
+   c->opt.lc_min_level = p->lc_min_level > 3 ? p->lc_min_level : 3;
+   c->opt.lc_max_level = fmin2 (p->lc_max_level, (int) c->level - 1);
+   /* tiling->exponent is always 0 (quirk C1), so coder.c:273-279 reduces to: */
+   if (c->opt.lc_max_level >= (int) c->level)
+      c->opt.lc_max_level = (int) c->level - 1;
+   if (c->opt.lc_min_level > c->opt.lc_max_level)
+      c->opt.lc_min_level = c->opt.lc_max_level;
+   c->opt.images_level = fmin2 (p->images_level, c->opt.lc_max_level - 1);
+   c->products_level
+      = (unsigned) (c->opt.lc_max_level - c->opt.images_level - 1 > 0
+		    ? c->opt.lc_max_level - c->opt.images_level - 1 : 0);
+   c->pixels = calloc (size_of_level ((unsigned) c->opt.lc_max_level),
+		       sizeof (float));
+   {
+      int ms = fmin2 (p->max_states, MAXSTATES);
+      c->opt.max_states = ms > 1 ? ms : 1;
+      ms = fmin2 (p->max_elements, MAXEDGES);
+      c->opt.max_elements = ms > 1 ? ms : 1;
+      c->opt.chroma_max_states = p->chroma_max_states > 1 ? p->chroma_max_states : 1;
+   }
+   c->rpf    = make_rpf ((unsigned) p->rpf_mantissa, p->rpf_range_e);
+   c->dc_rpf = make_rpf ((unsigned) p->dc_rpf_mantissa, p->dc_rpf_range_e);
+   for (state = 0; state < 3; state++)
+      c->planes [state] = planes [state];
+
+   append_basis_states (c);			/* coder.c:161-162 */
+   c->price = 128 * 64 / p->quality;		/* coder.c:164 */
+
+   /* frame_coder (coder.c:692-892) */
+   init_tree_model (&c->tree);
+   rle_init (&c->pool, (unsigned) c->opt.max_states);
+   for (state = 0; state < w->basis_states; state++)
+      if (usedomain (state, w))
+	 rle_append (&c->pool, state);
+   aac_init (&c->coeff, c->rpf, c->dc_rpf, (unsigned) c->opt.lc_min_level,
+	     (unsigned) c->opt.lc_max_level);
+
+   if (!p->color)
+   {
+      range_t range;
+
+      memset (&range, 0, sizeof range);
+      range.level = c->level;
+      out->costs [0] = subdivide (MAXCOSTS, 0, RANGE, &range, c);
+      if (range.tree == RANGE)
+	 fail (c, "No root state generated!");
+      w->root_state	    = (unsigned) range.tree;
+      out->err [0]	    = range.err;
+      out->tree_bits [0]    = range.tree_bits;
+      out->matrix_bits [0]  = range.matrix_bits;
+      out->weights_bits [0] = range.weights_bits;
+   }
+   else
+   {
+      int      YCb_node = -1, tree [3];
+      unsigned band;
+
+      for (band = 0; band < 3; band++)
+      {
+	 range_t range;
+
+	 tree [band] = RANGE;
+	 if (band == 1)
+	 {
+	    unsigned min_level;
+
+	    rle_chroma ((unsigned) c->opt.chroma_max_states, c);
+	    for (min_level = MAXLEVEL, state = w->basis_states;
+		 state < w->states; state++)
+	    {
+	       unsigned lincomb = 0;
+
+	       for (label = 0; label < MAXLABELS; label++)
+		  lincomb += w->tree [state][label] == RANGE ? 1 : 0;
+	       if (lincomb)
+		  min_level = fmin2 (min_level,
+				     (unsigned) (w->level_of_state [state] - 1));
+	    }
+	    c->opt.lc_min_level = (int) min_level;
+	 }
+	 memset (&range, 0, sizeof range);
+	 range.level = c->level;
+	 out->costs [band] = subdivide (MAXCOSTS, band, tree [0], &range, c);
+	 out->err [band]	  = range.err;
+	 out->tree_bits [band]	  = range.tree_bits;
+	 out->matrix_bits [band]  = range.matrix_bits;
+	 out->weights_bits [band] = range.weights_bits;
+	 if (range.tree == RANGE)
+	    fail (c, "No root state generated for color component %d!", band);
+	 tree [band] = range.tree;
+	 if (band == 1)
+	 {
+	    w->tree [w->states][0] = (int16_t) tree [0];
+	    w->tree [w->states][1] = (int16_t) tree [1];
+	    YCb_node		   = (int) w->states;
+	    append_state (1, compute_final_distribution (w->states, w),
+			  c->level + 1, c);
+	 }
+      }
+      w->tree [w->states][0] = (int16_t) tree [2];
+      w->tree [w->states][1] = RANGE;
+      append_state (1, compute_final_distribution (w->states, w), c->level + 1, c);
+      w->tree [w->states][0] = (int16_t) YCb_node;
+      w->tree [w->states][1] = (int16_t) (w->states - 1);
+      append_state (1, compute_final_distribution (w->states, w), c->level + 2, c);
+      w->root_state = w->states - 1;
+   }
+
+cleanup:
+   for (state = 0; state < MAXSTATES; state++)
+   {
+      free (c->images_of_state [state]);
+      free (c->ip_images_state [state]);
+      for (level = 0; level < MAXLEVEL; level++)
+	 free (c->ip_states_state [state][level]);
+   }
+   free (c->pixels);
+   free (c);
+   return rc;
+}
+
+void
+fo_dump_wfa (const fo_wfa_t *w, const fo_params_t *p, FILE *f)
+{
+   unsigned state, label, edge;
+
+   (void) p;
+   fprintf (f, "frame 0 0 %u %u\n", w->states, w->root_state);
+   for (state = w->basis_states; state < w->states; state++)
+   {
+      fprintf (f, "s %u %d %d %d %u %u %u %u 0 0\n", state,
+	       (int) w->level_of_state [state], (int) w->tree [state][0],
+	       (int) w->tree [state][1], (unsigned) w->x [state][0],
+	       (unsigned) w->y [state][0], (unsigned) w->x [state][1],
+	       (unsigned) w->y [state][1]);
+      for (label = 0; label < MAXLABELS; label++)
+	 for (edge = 0; w->into [state][label][edge] != NO_EDGE; edge++)
+	    fprintf (f, "e %u %u %d %08x %.9g\n", state, label,
+		     (int) w->into [state][label][edge],
+		     fbits (w->weight [state][label][edge]),
+		     (double) w->weight [state][label][edge]);
+   }
+   fprintf (f, "end\n");
+}

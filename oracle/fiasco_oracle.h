@@ -1,0 +1,116 @@
+/*
+ *  fiasco_oracle.h -- CPU restatement of the FIASCO encoder hot path.
+ *
+ *  TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's
+ *  cpu_baseline / --impl reference legs may build, load or call this.  The product
+ *  (fiasco_b200/) never includes, links or falls back to anything in oracle/.
+ *
+ *  Parity status: PINNED -- against the reference itself, which compiles here
+ *  (oracle/_ref, built in place from /root/reference by oracle/Makefile): the WFA this
+ *  restatement produces is compared state-for-state / edge-for-edge / bit-for-bit with
+ *  the reference's own output (oracle/_ref/wfadump of the reference .fco) and its
+ *  per-range trace with the reference's (oracle/_ref/seamdump, ld --wrap on the
+ *  unmodified objects); the golden copies live in tests/golden/.
+ */
+#ifndef FIASCO_ORACLE_H
+#define FIASCO_ORACLE_H
+
+#include <stdint.h>
+#include <stdio.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FO_MAXEDGES  5		/* codec/wfa.h:20 */
+#define FO_MAXSTATES 6000	/* codec/wfa.h:21 */
+#define FO_MAXLABELS 2		/* codec/wfa.h:22 */
+#define FO_MAXLEVEL  22		/* codec/wfa.h:23 */
+
+/* coder options after the CLI / fiasco_c_options_* layer, before the clamping of
+   codec/coder.c:260-296 (fo_encode applies that clamping itself) */
+typedef struct fo_params
+{
+   int	 width, height;		/* image geometry (even numbers) */
+   int	 color;			/* 0: one grey band, 1: Y, Cb, Cr (4:4:4) */
+   float quality;		/* price = 128 * 64 / quality (coder.c:164) */
+   int	 lc_min_level;		/* options.c:67-74 / cwfa.c:332-345 */
+   int	 lc_max_level;
+   int	 images_level;		/* 5 */
+   int	 max_elements;		/* edges per linear combination */
+   int	 max_states;		/* dictionary size */
+   int	 chroma_max_states;	/* 40 */
+   float chroma_decrease;	/* 2.0 */
+   int	 rpf_mantissa;		/* 3 */
+   int	 rpf_range_e;		/* fiasco_rpf_range_e: 0=.75 1=1.0 2=1.5 3=2.0 */
+   int	 dc_rpf_mantissa;	/* 5 */
+   int	 dc_rpf_range_e;	/* 1 */
+   int	 second_domain_block;	/* optimisation level >= 1 */
+   int	 check_for_underflow;	/* optimisation level >= 2 */
+   int	 check_for_overflow;	/* optimisation level >= 2 */
+   int	 full_search;		/* optimisation level >= 2 (UB in the reference) */
+} fo_params_t;
+
+/* the finished automaton (codec/wfa.h:112-138, the fields the still-image path fills) */
+typedef struct fo_wfa
+{
+   unsigned states, basis_states, root_state;
+   unsigned level;		/* image level (wfainfo->level) */
+   float    final_distribution [FO_MAXSTATES];
+   uint8_t  level_of_state [FO_MAXSTATES];
+   uint8_t  domain_type [FO_MAXSTATES];
+   int16_t  tree [FO_MAXSTATES][FO_MAXLABELS];
+   uint16_t x [FO_MAXSTATES][FO_MAXLABELS];
+   uint16_t y [FO_MAXSTATES][FO_MAXLABELS];
+   int16_t  into [FO_MAXSTATES][FO_MAXLABELS][FO_MAXEDGES + 1];
+   float    weight [FO_MAXSTATES][FO_MAXLABELS][FO_MAXEDGES + 1];
+   int16_t  y_state [FO_MAXSTATES][FO_MAXLABELS];
+   uint8_t  y_column [FO_MAXSTATES][FO_MAXLABELS];
+   /* root range summary per band (what print_statistics reports, coder.c:894) */
+   float    costs [3], err [3], tree_bits [3], matrix_bits [3], weights_bits [3];
+} fo_wfa_t;
+
+/* work counters */
+typedef struct fo_stats
+{
+   uint64_t subdivide_calls, mp_calls, pass1, pass2, ortho_steps, accepted,
+	    append_states, leaf_dots, ipss_lookups, mp_domains;
+   uint64_t ip_bytes;		/* algorithmic bytes of the range x state kernel:
+				   sum over lc_max blocks of 4*2^lc_max + 376*S_b */
+   uint64_t blocks;
+} fo_stats_t;
+
+void fo_default_params (fo_params_t *p, int width, int height, int color,
+			float quality, int optimize /* CLI -z, 0..3 */);
+
+/*
+ *  Encode one still frame.  planes[b] are the frame's bands in the reference's internal
+ *  pixel format (lib/image.c:362,383-385: 12.4 fixed point shorts, row-major,
+ *  width*height each; 1 band grey, 3 bands Y Cb Cr).  Returns 0 on success, else an
+ *  error code (message in errbuf).  If trace != NULL a per-seam trace in the format of
+ *  oracle/seamdump.c is written.
+ */
+int fo_encode (const fo_params_t *p, const int16_t *const planes [3],
+	       fo_wfa_t *out, fo_stats_t *stats, FILE *trace,
+	       char *errbuf, size_t errlen);
+
+/* pixel format conversion of lib/image.c:352-386 (8-bit PNM samples -> shorts) */
+void fo_grey_to_plane (const uint8_t *grey, size_t n, int16_t *plane);
+void fo_rgb_to_planes (const uint8_t *rgb, size_t n, int16_t *y, int16_t *cb,
+		       int16_t *cr);
+
+/* small pure functions of the path, exported for known-answer tests */
+int	 fo_rtob (float f, unsigned mantissa_bits, int range_e);  /* lib/rpf.c:59 */
+float	 fo_btor (int b, unsigned mantissa_bits, int range_e);	  /* lib/rpf.c:113 */
+unsigned fo_bits_bin_code (unsigned value, unsigned maxval);	  /* lib/misc.c:296 */
+void	 fo_tree_model_kat (unsigned level, unsigned *counts, unsigned *total,
+			    float *child_bits, float *leaf_bits); /* bintree.c:55,70 */
+unsigned fo_image_level (unsigned width, unsigned height);	  /* coder.c:249-256 */
+
+/* canonical text dump, same grammar as oracle/wfadump.c ("s"/"e" lines of one frame) */
+void fo_dump_wfa (const fo_wfa_t *wfa, const fo_params_t *p, FILE *f);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
