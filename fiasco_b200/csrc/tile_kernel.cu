@@ -1,0 +1,2036 @@
+/*
+ *  tile_kernel.cu -- the persistent FIASCO tile kernel for sm_100a.
+ *
+ *  One thread block encodes one independent tile / frame: it walks the whole bintree
+ *  recursion of codec/subdivide.c on the device with an explicit DFS stack, and spreads
+ *  the data-parallel parts over its threads:
+ *
+ *    - range x state products of an lc_max block (codec/ip.c:72 compute_ip_images_state):
+ *	threads span the states, block pixels staged in shared memory;
+ *    - state x state rows of a new state (codec/ip.c:184 compute_ip_states_state,
+ *	codec/control.c:205 compute_images): threads span (level, partner state);
+ *    - matching pursuit (codec/approx.c:317): threads span the domain pool; pass-1 bound,
+ *	pass-2 quantised evaluation, an ordered warp-level resolution that reproduces the
+ *	reference's index-ordered running minimum, and the Gram-Schmidt update
+ *	(codec/approx.c:644) across the pool.
+ *
+ *  Many tiles run concurrently (grid = number of tiles).  All arithmetic that decides an
+ *  index is plain fp32 with the reference's operation order (compiled with -fmad=false,
+ *  IEEE division), double only inside log2, so the automaton is bit-identical to the
+ *  reference CPU coder's.
+ *
+ *  Conventions inside this file: functions whose name starts with cta_ are executed by
+ *  the whole block, begin after a barrier and end with a barrier.  t0_ functions are
+ *  executed by thread 0 only, between barriers.
+ */
+#include <stdio.h>
+#include <math.h>
+#include "tile_kernel.cuh"
+
+namespace {
+
+/*****************************************************************************
+				small helpers
+*****************************************************************************/
+
+__device__ __forceinline__ unsigned width_of_level (int l)  { return 1u << (l >> 1); }
+__device__ __forceinline__ unsigned height_of_level (int l) { return 1u << ((l + 1) >> 1); }
+__device__ __forceinline__ float fmin2 (float a, float b)   { return a > b ? b : a; }
+
+/* -log2 (x) rounded to fp32 the way the reference does it: double log2, negate, narrow */
+__device__ __forceinline__ float neg_log2f_via_double (float x)
+{
+   return (float) (-log2 ((double) x));
+}
+
+/* lib/rpf.c:59-111 (rtob); shifts follow x86 semantics (count mod 32), see oracle */
+__device__ __forceinline__ int dev_rtob (float f, int mantissa_bits, float range)
+{
+   f = f / range;
+   unsigned u	     = __float_as_uint (f);
+   unsigned mantissa = u & 0x7fffffu;
+   int	    exponent = (int) ((u >> 23) & 0xffu) - 126;
+   int	    sign     = (int) (u >> 31);
+
+   mantissa >>= 1;
+   mantissa  |= 1u << 22;
+   if (exponent > 0)
+      mantissa <<= (exponent & 31);
+   else
+      mantissa >>= ((-exponent) & 31);
+   mantissa >>= (23 - mantissa_bits - 1);
+   mantissa  += 1;
+   mantissa >>= 1;
+   if (mantissa == 0)
+      return -1;
+   else if (mantissa >= (1u << mantissa_bits))
+      return sign;
+   else
+      return (int) (((mantissa & ((1u << mantissa_bits) - 1)) << 1) | (unsigned) sign);
+}
+
+/* lib/rpf.c:113-169 (btor) */
+__device__ __forceinline__ float dev_btor (int binary, int mantissa_bits, float range)
+{
+   if (binary == -1)
+      return 0.0f;
+   int	    sign     = binary & 1;
+   unsigned mantissa = (((unsigned) binary) & ((1u << (mantissa_bits + 1)) - 1)) >> 1;
+   float    v;
+
+   mantissa <<= (23 - mantissa_bits);
+   if (mantissa == 0)
+      v = sign ? -1.0f : 1.0f;
+   else
+   {
+      int exponent = 0;
+
+      while (!(mantissa & (1u << 22)))
+      {
+	 exponent--;
+	 mantissa <<= 1;
+      }
+      mantissa <<= 1;
+      v = __uint_as_float (((unsigned) sign << 31)
+			   | ((unsigned) (exponent + 126) << 23)
+			   | (mantissa & 0x7fffffu));
+   }
+   return v * range;
+}
+
+/* lib/misc.c:296-315 */
+__device__ __forceinline__ unsigned dev_bits_bin_code (unsigned value, unsigned maxval)
+{
+   unsigned k = 31u - (unsigned) __clz ((int) (maxval + 1));
+   unsigned r = (maxval + 1) - (1u << k);
+
+   return value < maxval + 1 - 2 * r ? k : k + 1;
+}
+
+/*****************************************************************************
+			     shared memory layout
+*****************************************************************************/
+
+struct RangeRes			/* the range_t fields the still-image path uses */
+{
+   float	  weight [FB_MAXEDGES + 1];
+   float	  err, tree_bits, matrix_bits, weights_bits;
+   short	  into [FB_MAXEDGES + 1];
+   short	  tree;
+   unsigned short x, y;
+};
+
+struct Frame			/* one activation record of subdivide() */
+{
+   float    max_costs, lincomb_costs, subdivide_costs;
+   unsigned x, y, image, address;
+   int	    level, y_state, label;
+   int	    new_y_state [2];
+   unsigned states_snap;
+   float    r_err, r_tree_bits, r_matrix_bits, r_weights_bits; /* rrange sums */
+   RangeRes lrange;
+   RangeRes child [2];
+};
+
+struct MpRes			/* mp_t, codec/approx.c:41-51 */
+{
+   short exclude [FB_MAXEDGES];
+   short indices [FB_MAXEDGES + 1];
+   short into [FB_MAXEDGES + 1];
+   float weight [FB_MAXEDGES];
+   float matrix_bits, weights_bits, err, costs;
+};
+
+struct MpWork
+{
+   float  B [FB_MAXEDGES];	/* ip_image_ortho_vector */
+   float  N [FB_MAXEDGES];	/* norm_ortho_vector */
+   float  fB [FB_MAXEDGES];	/* B[k] / N[k] */
+   float  mbase [FB_MAXEDGES + 2]; /* -log2 (count[k] / total) */
+   float  d0b [2];		/* DC-column bits: [0] unused, [1] used */
+   double l2_dc [512];		/* log2 (count / total) per DC code */
+   double l2_lv [512];		/* same for the context of the current level */
+   float  additional_bits, price, norm, min_costs;
+   float  wb_dc, wb_nd;		/* pass-1 weights bits of a DC / other candidate */
+   int	  nc;			/* chosen vectors with non-zero weight */
+   short  cvec [FB_MAXEDGES + 1];
+   short  csorted [FB_MAXEDGES + 1];
+   int	  ncs;			/* of which not the y-state */
+   int	  n;			/* current step */
+   int	  D, pool_n, ydom, y_state, level, li, size;
+   int	  index;		/* winner of the current step or -1 */
+   float  best_f [FB_MAXEDGES];
+   float  best_mbits, best_wbits, best_err, best_costs;
+};
+
+struct ShHdr
+{
+   int	    state [2];
+   int	    depthv [2];
+   int	    status;
+   int	    band;
+   float    ret_costs;
+   float    price;		/* price of the current band */
+   unsigned states;		/* wfa->states */
+   unsigned tree_counts [FB200_MAXLEVEL];
+   unsigned tree_total [FB200_MAXLEVEL];
+   int	    trace_len;
+   unsigned long long mp_calls, mp_steps, pass2, blocks, ip_bytes;
+   MpRes    mp, tmp;
+   MpWork   w;
+   RangeRes root;
+   Frame    frames [FB_MAXDEPTH];
+};
+
+struct Sh			/* pointers into dynamic shared memory */
+{
+   ShHdr   *h;
+   float   *num, *den, *G;	/* [dcap], [dcap], [5][dcap] */
+   unsigned char *used;		/* [dcap] */
+   short   *pool;		/* [s_cap] domain index -> state */
+   float   *pixels;		/* [2^lc_max] */
+   int	   *norm_i;		/* [tn] integer sum of squares per node */
+   float   *slot;		/* [10][NT] pass-2 results of the current chunk */
+   float   *wmin;		/* [32] per-warp minimum key */
+   short   *blob;		/* [blob_len] current probability models */
+   int	    dcap;
+};
+
+__host__ __device__ inline size_t align16 (size_t x) { return (x + 15) & ~(size_t) 15; }
+
+__host__ __device__ inline size_t
+smem_layout (const DevParams &p, int nt, size_t *off /* [11] */)
+{
+   size_t o    = 0;
+   size_t dcap = (size_t) p.s_cap + 1;
+
+   off [0] = o; o += align16 (sizeof (ShHdr));
+   off [1] = o; o += align16 (dcap * 4);			/* num */
+   off [2] = o; o += align16 (dcap * 4);			/* den */
+   off [3] = o; o += align16 (dcap * 4 * FB_MAXEDGES);		/* G */
+   off [4] = o; o += align16 (dcap);				/* used */
+   off [5] = o; o += align16 ((size_t) p.s_cap * 2);		/* pool */
+   off [6] = o; o += align16 (((size_t) 1 << p.lc_max) * 4);	/* pixels */
+   off [7] = o; o += align16 ((size_t) p.tn * 4);		/* norm_i */
+   off [8] = o; o += align16 ((size_t) nt * 4 * 10);		/* slot */
+   off [9] = o; o += align16 (32 * 4);				/* wmin */
+   off [10] = o; o += align16 ((size_t) p.blob_len * 2);	/* blob */
+   return o;
+}
+
+__device__ __forceinline__ Sh
+carve (unsigned char *base, const DevParams &p, int nt)
+{
+   size_t off [11];
+   Sh	  s;
+
+   smem_layout (p, nt, off);
+   s.h	    = (ShHdr *) (base + off [0]);
+   s.num    = (float *) (base + off [1]);
+   s.den    = (float *) (base + off [2]);
+   s.G	    = (float *) (base + off [3]);
+   s.used   = (unsigned char *) (base + off [4]);
+   s.pool   = (short *) (base + off [5]);
+   s.pixels = (float *) (base + off [6]);
+   s.norm_i = (int *) (base + off [7]);
+   s.slot   = (float *) (base + off [8]);
+   s.wmin   = (float *) (base + off [9]);
+   s.blob   = (short *) (base + off [10]);
+   s.dcap   = p.s_cap + 1;
+   return s;
+}
+
+/* accessors of the model blob */
+#define BLOB_U16(sh, i) (((unsigned short *) (sh).blob) [i])
+#define BLOB_S16(sh, i) ((sh).blob [i])
+
+enum { ST_ENTER, ST_CHILD, ST_AFTER_CHILD, ST_DECIDE, ST_RETURN, ST_DONE, ST_ABORT };
+
+/*****************************************************************************
+		    probability models (thread-0 scalar code)
+*****************************************************************************/
+
+/* codec/bintree.c:55-68 */
+__device__ float t0_tree_bits (const ShHdr *h, int child, int level)
+{
+   float prob = h->tree_counts [level] / (float) h->tree_total [level];
+
+   return child ? neg_log2f_via_double (prob) : neg_log2f_via_double (1 - prob);
+}
+
+/* qac_bits (domain-pool.c:367-402) as rle_bits calls it on the 1-entry DC model */
+__device__ float t0_d0_bits (const Sh &sh, int dc_used, int y_state,
+			     const float *m0, const float *m1)
+{
+   float bits = 0;
+
+   if (BLOB_U16 (sh, MB_D0N) > 0 && 0 != y_state)
+      bits += m0 [BLOB_S16 (sh, MB_D0INDEX)];
+   if (y_state >= 0)
+      bits += m0 [BLOB_U16 (sh, MB_D0YINDEX)];
+   if (dc_used)
+   {
+      if (0 == y_state)
+      {
+	 bits -= m0 [BLOB_U16 (sh, MB_D0YINDEX)];
+	 bits += m1 [BLOB_U16 (sh, MB_D0YINDEX)];
+      }
+      else
+      {
+	 bits -= m0 [BLOB_S16 (sh, MB_D0INDEX)];
+	 bits += m1 [BLOB_S16 (sh, MB_D0INDEX)];
+      }
+   }
+   return bits;
+}
+
+/*
+ *  rle_bits (domain-pool.c:737-793) for a used-domain list that is already sorted and
+ *  already stripped of the y-state domain.  mbase / d0b are per-call tables.
+ */
+__device__ __forceinline__ float
+dev_rle_bits (const float *mbase, const float *d0b, const short *sorted, int n,
+	      unsigned pool_n)
+{
+   float    bits = mbase [n];
+   unsigned last = 1;
+
+   bits += (n && sorted [0] == 0) ? d0b [1] : d0b [0];
+#pragma unroll
+   for (int e = 0; e < FB_MAXEDGES + 1; e++)
+      if (e < n)
+      {
+	 int into = sorted [e];
+
+	 if (into && (pool_n - 1 - last))
+	 {
+	    bits += (float) dev_bits_bin_code ((unsigned) into - last, pool_n - 1 - last);
+	    last  = (unsigned) into + 1;
+	 }
+      }
+   return bits;
+}
+
+__constant__ float c_matrix_0 [1024];	/* domain-pool.c:970-999 */
+__constant__ float c_matrix_1 [1024];
+
+/*****************************************************************************
+		range x state products of a block  (codec/ip.c:72-154)
+*****************************************************************************/
+
+/*
+ *  Fill T[node][s] for the nodes of the subtree rooted at (node_root, level_root) of the
+ *  current lc_max block and every state s >= from whose image is needed.
+ *  Levels <= il are direct dot products with the state images (ip.c:268-295), higher
+ *  levels the weighted sums over the state's transitions (ip.c:98-151), each entry
+ *  accumulated in the reference's order: label 0 child, label 0 edges, label 1 ...
+ */
+template <int NT>
+__device__ void
+cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
+	       unsigned node_root, int level_root)
+{
+   const int	 tid	= threadIdx.x;
+   const unsigned S	= sh.h->states;
+   const unsigned scap	= (unsigned) P.s_cap;
+
+   if (from >= S)
+      return;			/* uniform: nothing to do, no barrier needed */
+
+   /* direct levels */
+   for (int l = P.lmin; l <= P.il && l <= level_root; l++)
+   {
+      const unsigned nn	   = 1u << (level_root - l);
+      const unsigned node0 = ((node_root + 1) << (level_root - l)) - 1;
+      const unsigned adr0  = node0 - ((1u << (P.lc_max - l)) - 1);
+      const unsigned len   = 1u << l;
+      const unsigned ns	   = S - from;
+
+      if (ns >= 32)
+      {
+	 /* a warp covers 32 consecutive states and walks the nodes together: pixel
+	    reads are shared-memory broadcasts, product writes are coalesced */
+	 for (unsigned s = from + tid; s < S; s += NT)
+	 {
+	    if (!W.domain_type [s])
+	       continue;
+	    const float *im = W.img + (size_t) s * FB_IMG_STRIDE + (len - 1);
+	    if (l == 5)
+	    {
+	       float r [32];
+	       const float4 *im4 = (const float4 *) (W.img + (size_t) s * FB_IMG_STRIDE + 32);
+	       /* level-5 part starts at float 31; rows are 256 B aligned, so read the
+		  aligned float4s 7..15 and shift by one */
+	       float prev = W.img [(size_t) s * FB_IMG_STRIDE + 31];
+#pragma unroll
+	       for (int q = 0; q < 8; q++)
+	       {
+		  float4 v = im4 [q];
+		  r [4 * q]	= prev;
+		  r [4 * q + 1] = v.x;
+		  r [4 * q + 2] = v.y;
+		  r [4 * q + 3] = v.z;
+		  prev		= v.w;
+	       }
+	       for (unsigned k = 0; k < nn; k++)
+	       {
+		  const float4 *px = (const float4 *) (sh.pixels + (size_t) (adr0 + k) * 32);
+		  float		ip = 0;
+#pragma unroll
+		  for (int q = 0; q < 8; q++)
+		  {
+		     const float4 p4 = px [q];
+		     ip += p4.x * r [4 * q];
+		     ip += p4.y * r [4 * q + 1];
+		     ip += p4.z * r [4 * q + 2];
+		     ip += p4.w * r [4 * q + 3];
+		  }
+		  W.T [(size_t) (node0 + k) * scap + s] = ip;
+	       }
+	    }
+	    else
+	    {
+	       for (unsigned k = 0; k < nn; k++)
+	       {
+		  const float *px = sh.pixels + (size_t) (adr0 + k) * len;
+		  float	       ip = 0;
+		  for (unsigned i = 0; i < len; i++)
+		     ip += px [i] * im [i];
+		  W.T [(size_t) (node0 + k) * scap + s] = ip;
+	       }
+	    }
+	 }
+      }
+      else
+      {
+	 /* few new states: spread (state, node) pairs over the threads */
+	 for (unsigned item = tid; item < ns * nn; item += NT)
+	 {
+	    const unsigned s = from + item / nn;
+	    const unsigned k = item % nn;
+
+	    if (!W.domain_type [s])
+	       continue;
+	    const float *im = W.img + (size_t) s * FB_IMG_STRIDE + (len - 1);
+	    const float *px = sh.pixels + (size_t) (adr0 + k) * len;
+	    float	 ip = 0;
+	    for (unsigned i = 0; i < len; i++)
+	       ip += px [i] * im [i];
+	    W.T [(size_t) (node0 + k) * scap + s] = ip;
+	 }
+      }
+   }
+   __syncthreads ();
+
+   /* upsweep */
+   for (int l = (P.il + 1 > P.lmin ? P.il + 1 : P.lmin); l <= level_root; l++)
+   {
+      const unsigned nn	   = 1u << (level_root - l);
+      const unsigned node0 = ((node_root + 1) << (level_root - l)) - 1;
+      const unsigned ns	   = S - from;
+
+      for (unsigned item = tid; item < ns * nn; item += NT)
+      {
+	 const unsigned s    = from + item % ns;
+	 const unsigned node = node0 + item / ns;
+
+	 if (!W.domain_type [s])
+	    continue;
+	 float acc = 0;
+#pragma unroll
+	 for (int label = 0; label < 2; label++)
+	 {
+	    const float *src = W.T + (size_t) (2 * node + 1 + label) * scap;
+	    int		 dom = W.tree [2 * s + label];
+
+	    if (dom != FB_RANGE)
+	       acc += src [dom];
+	    const short *in = W.into + (size_t) (2 * s + label) * 6;
+	    const float *wt = W.weight + (size_t) (2 * s + label) * 6;
+	    for (int e = 0; (dom = in [e]) != FB_NO_EDGE; e++)
+	       acc += src [dom] * wt [e];
+	 }
+	 W.T [(size_t) node * scap + s] = acc;
+      }
+      __syncthreads ();
+   }
+}
+
+/* codec/subdivide.c:612-644 (init_range) + :504-541 (cut_to_bintree) */
+template <int NT>
+__device__ void
+cta_init_range (const DevParams &P, const TileWs &W, const Sh &sh, unsigned x0,
+		unsigned y0, int band)
+{
+   const int	  tid  = threadIdx.x;
+   const unsigned size = 1u << P.lc_max;
+   const int16_t *src  = W.pix + (size_t) band * P.width * P.height;
+
+   for (unsigned i = tid; i < size; i += NT)
+   {
+      /* bintree order: y in the even address bits, x in the odd ones */
+      unsigned yy = 0, xx = 0;
+      for (int b = 0; b < 11; b++)
+      {
+	 yy |= ((i >> (2 * b)) & 1u) << b;
+	 xx |= ((i >> (2 * b + 1)) & 1u) << b;
+      }
+      const unsigned px = x0 + xx, py = y0 + yy;
+      float	     v	= 0;
+
+      if (py < (unsigned) P.height && px < (unsigned) P.width)
+	 v = (float) ((int) src [(size_t) py * P.width + px] / 16);
+      sh.pixels [i] = v;
+   }
+   __syncthreads ();
+
+   /* integer sums of squares per node (pixels are integers here); bottom level first */
+   {
+      const unsigned nleaf = 1u << (P.lc_max - P.lmin);
+      const unsigned len   = 1u << P.lmin;
+
+      for (unsigned k = tid; k < nleaf; k += NT)
+      {
+	 int acc = 0;
+	 for (unsigned i = 0; i < len; i++)
+	 {
+	    int v = (int) sh.pixels [k * len + i];
+	    acc += v * v;
+	 }
+	 sh.norm_i [nleaf - 1 + k] = acc;
+      }
+      __syncthreads ();
+      for (int l = P.lmin + 1; l <= P.lc_max; l++)
+      {
+	 const unsigned nn    = 1u << (P.lc_max - l);
+	 const unsigned node0 = nn - 1;
+	 for (unsigned k = tid; k < nn; k += NT)
+	    sh.norm_i [node0 + k] = sh.norm_i [2 * (node0 + k) + 1]
+				    + sh.norm_i [2 * (node0 + k) + 2];
+	 __syncthreads ();
+      }
+   }
+   if (tid == 0)
+   {
+      unsigned ns = 0;
+      /* need_image states: all states inside the image; count for the byte model */
+      ns = sh.h->states;
+      sh.h->blocks++;
+      sh.h->ip_bytes += 4ull * size + 4ull * (63 + (unsigned) ((1 << (P.lc_max - P.il)) - 1)) * ns;
+   }
+   cta_compute_T<NT> (P, W, sh, 0, 0, P.lc_max);
+}
+
+/* exact fp32 left-to-right sum of squares of a node (approx.c:388-389) */
+__device__ float
+t0_node_norm (const DevParams &P, const Sh &sh, unsigned image, unsigned address, int level)
+{
+   int s = sh.norm_i [image];
+
+   if (s <= (1 << 24))
+      return (float) s;		/* every partial sum is an exactly representable integer */
+   const float *px = sh.pixels + ((size_t) address << level);
+   float	norm = 0;
+   for (unsigned i = 0; i < (1u << level); i++)
+      norm += px [i] * px [i];
+   return norm;
+}
+
+/*****************************************************************************
+	    new state: images and state x state rows  (codec/control.c, ip.c)
+*****************************************************************************/
+
+/* state x state product of states a, b at table level index li (symmetric storage) */
+__device__ __forceinline__ float
+ss_get (const DevParams &P, const TileWs &W, int li, unsigned a, unsigned b)
+{
+   return W.SS [((size_t) li * P.s_cap + a) * P.s_cap + b];
+}
+
+/* one entry <s, t> at level lmin + li for a state s whose images exist
+   (ip.c:213-258 for levels > il, ip.c:297-323 below) */
+__device__ float
+dev_ss_entry (const DevParams &P, const TileWs &W, int li, unsigned s, unsigned t)
+{
+   const int level = P.lmin + li;
+
+   if (level <= P.il)
+   {
+      const unsigned len = 1u << level;
+      const float   *a	 = W.img + (size_t) s * FB_IMG_STRIDE + (len - 1);
+      const float   *b	 = W.img + (size_t) t * FB_IMG_STRIDE + (len - 1);
+      float	     ip	 = 0;
+      for (unsigned i = 0; i < len; i++)
+	 ip += a [i] * b [i];
+      return ip;
+   }
+   float ip = 0;
+   for (int label = 0; label < 2; label++)
+   {
+      const short *in1 = W.into + (size_t) (2 * s + label) * 6;
+      const float *wt1 = W.weight + (size_t) (2 * s + label) * 6;
+      const short *in2 = W.into + (size_t) (2 * t + label) * 6;
+      const float *wt2 = W.weight + (size_t) (2 * t + label) * 6;
+      const int	   c2  = W.tree [2 * t + label];
+      int	   d1, d2;
+      float	   sum;
+
+      if ((d1 = W.tree [2 * s + label]) != FB_RANGE)
+      {
+	 sum = 0;
+	 if (c2 != FB_RANGE)
+	    sum = ss_get (P, W, li - 1, (unsigned) d1, (unsigned) c2);
+	 for (int e2 = 0; (d2 = in2 [e2]) != FB_NO_EDGE; e2++)
+	    sum += wt2 [e2] * ss_get (P, W, li - 1, (unsigned) d1, (unsigned) d2);
+	 ip += sum;
+      }
+      for (int e1 = 0; (d1 = in1 [e1]) != FB_NO_EDGE; e1++)
+      {
+	 sum = 0;
+	 if (c2 != FB_RANGE)
+	    sum = ss_get (P, W, li - 1, (unsigned) d1, (unsigned) c2);
+	 for (int e2 = 0; (d2 = in2 [e2]) != FB_NO_EDGE; e2++)
+	    sum += wt2 [e2] * ss_get (P, W, li - 1, (unsigned) d1, (unsigned) d2);
+	 ip += wt1 [e1] * sum;
+      }
+   }
+   return ip;
+}
+
+/* codec/control.c:205-257 (compute_images) for one new state: every element of levels
+   1..il is (child's element) + sum over edges of (domain element * weight) */
+template <int NT>
+__device__ void
+cta_state_images (const DevParams &P, const TileWs &W, unsigned s)
+{
+   const int tid = threadIdx.x;
+   const int tot = (1 << (P.il + 1)) - 1;
+
+   for (int e = 1 + tid; e < tot; e += NT)
+   {
+      const int level = 31 - __clz (e + 1);	   /* e in [2^level - 1, 2^(level+1) - 1) */
+      const int pos   = e - ((1 << level) - 1);
+      const int half  = 1 << (level - 1);
+      const int label = pos >= half;
+      const int i     = pos - label * half;
+      const int so    = (half - 1) + i;		   /* offset in the source image */
+      int	dom   = W.tree [2 * s + label];
+      float	v     = 0;
+
+      if (dom != FB_RANGE)
+	 v = W.img [(size_t) dom * FB_IMG_STRIDE + so];
+      const short *in = W.into + (size_t) (2 * s + label) * 6;
+      const float *wt = W.weight + (size_t) (2 * s + label) * 6;
+      for (int k = 0; (dom = in [k]) != FB_NO_EDGE; k++)
+	 v += W.img [(size_t) dom * FB_IMG_STRIDE + so] * wt [k];
+      W.img [(size_t) s * FB_IMG_STRIDE + e] = v;
+   }
+   __syncthreads ();
+}
+
+/* codec/ip.c:184-260 for from == to == s: all levels are independent of each other
+   because every term refers to states < s */
+template <int NT>
+__device__ void
+cta_state_products (const DevParams &P, const TileWs &W, unsigned s)
+{
+   const int	  tid	= threadIdx.x;
+   const unsigned items = (unsigned) P.nlev * (s + 1);
+
+   for (unsigned item = tid; item < items; item += NT)
+   {
+      const int	     li = (int) (item / (s + 1));
+      const unsigned t	= item % (s + 1);
+
+      if (!W.domain_type [t])
+	 continue;
+      const float ip = dev_ss_entry (P, W, li, s, t);
+      W.SS [((size_t) li * P.s_cap + s) * P.s_cap + t] = ip;
+      W.SS [((size_t) li * P.s_cap + t) * P.s_cap + s] = ip;
+      if (t == s)
+	 W.diag [(size_t) li * P.s_cap + s] = ip;
+   }
+   __syncthreads ();
+}
+
+/* codec/wfalib.c:154-180 */
+__device__ float
+t0_final_distribution (const TileWs &W, unsigned s)
+{
+   float final = 0;
+
+   for (int label = 0; label < 2; label++)
+   {
+      int dom = W.tree [2 * s + label];
+
+      if (dom != FB_RANGE)
+	 final += W.final_d [dom];
+      const short *in = W.into + (size_t) (2 * s + label) * 6;
+      const float *wt = W.weight + (size_t) (2 * s + label) * 6;
+      for (int e = 0; (dom = in [e]) != FB_NO_EDGE; e++)
+	 final += wt [e] * W.final_d [dom];
+   }
+   return final / 2;
+}
+
+/* codec/wfalib.c:233-274 (edges kept sorted by target state) */
+__device__ void
+t0_append_edge (const TileWs &W, unsigned from, int into, float weight, int label)
+{
+   short *in = W.into + (size_t) (2 * from + label) * 6;
+   float *wt = W.weight + (size_t) (2 * from + label) * 6;
+   int	  pos, edge;
+
+   for (pos = 0; in [pos] != FB_NO_EDGE && in [pos] < into; pos++)
+      ;
+   for (edge = pos; in [edge] != FB_NO_EDGE; edge++)
+      ;
+   for (edge++; edge != pos; edge--)
+   {
+      in [edge] = in [edge - 1];
+      wt [edge] = wt [edge - 1];
+   }
+   in [edge] = (short) into;
+   wt [edge] = weight;
+}
+
+/*
+ *  codec/control.c:48-131 (append_state).  The state's tree / edges are already in place.
+ *  Must be called by all threads; 'auxiliary' and 'level' are uniform.
+ */
+template <int NT>
+__device__ void
+cta_append_state (const DevParams &P, const TileWs &W, const Sh &sh, int auxiliary,
+		  int level_of_state)
+{
+   const unsigned s = sh.h->states;
+
+   if (threadIdx.x == 0)
+   {
+      const float final = t0_final_distribution (W, s);
+
+      W.final_d [s]	   = final;
+      W.level_of_state [s] = (uint8_t) level_of_state;
+      W.domain_type [s]	   = auxiliary ? 0 : 2;
+      if (!auxiliary)
+	 W.img [(size_t) s * FB_IMG_STRIDE] = final;
+   }
+   __syncthreads ();
+   if (!auxiliary)
+   {
+      cta_state_images<NT> (P, W, s);
+      cta_state_products<NT> (P, W, s);
+   }
+   if (threadIdx.x == 0)
+   {
+      sh.h->states = s + 1;
+      if (s + 1 >= FB200_MAXSTATES)
+	 sh.h->status = FB200_EMAXSTATES;
+      else if (s + 1 >= (unsigned) P.s_cap)
+	 sh.h->status = FB200_ECAPACITY;
+   }
+   __syncthreads ();
+}
+
+/* the built-in initial basis "small.fco" (input/basis.c:76-104,126-131) and
+   append_basis_states (control.c:133-173) */
+template <int NT>
+__device__ void
+cta_init_basis (const DevParams &P, const TileWs &W, const Sh &sh)
+{
+   const int tid = threadIdx.x;
+
+   /* empty automaton (alloc_wfa, wfalib.c:98-113) for the states we may touch */
+   for (unsigned i = tid; i < (unsigned) P.s_cap * 2; i += NT)
+   {
+      W.tree [i]     = FB_RANGE;
+      W.y_state [i]  = FB_RANGE;
+      W.into [(size_t) i * 6] = FB_NO_EDGE;
+      W.y_column [i] = 0;
+      W.x [i] = 0;
+      W.y [i] = 0;
+   }
+   for (unsigned i = tid; i < (unsigned) P.s_cap; i += NT)
+   {
+      W.domain_type [i]	   = 0;
+      W.final_d [i]	   = 0;
+      W.level_of_state [i] = 0;
+   }
+   __syncthreads ();
+   if (tid == 0)
+   {
+      W.domain_type [0] = 2;
+      W.final_d [0]	= 128;
+      t0_append_edge (W, 0, 0, 1.0f, 0);
+      t0_append_edge (W, 0, 0, 1.0f, 1);
+      W.final_d [1] = 64;
+      W.final_d [2] = 64;
+      W.domain_type [1] = 2;
+      W.domain_type [2] = 2;
+      t0_append_edge (W, 1, 2, 0.5f, 0);
+      t0_append_edge (W, 1, 2, 0.5f, 1);
+      t0_append_edge (W, 1, 0, 0.5f, 1);
+      t0_append_edge (W, 2, 1, 1.0f, 0);
+      t0_append_edge (W, 2, 1, 1.0f, 1);
+      for (unsigned s = 0; s < 3; s++)
+      {
+	 W.img [(size_t) s * FB_IMG_STRIDE] = W.final_d [s];
+	 W.level_of_state [s]		    = (uint8_t) -1;
+      }
+      /* compute_images (0, 2): level outermost because the basis states refer to
+	 each other */
+      for (int level = 1; level <= P.il; level++)
+	 for (unsigned s = 0; s < 3; s++)
+	    for (int label = 0; label < 2; label++)
+	    {
+	       const int half = 1 << (level - 1);
+	       float	*dst  = W.img + (size_t) s * FB_IMG_STRIDE + ((1 << level) - 1)
+				+ label * half;
+	       int	 dom  = W.tree [2 * s + label];
+
+	       for (int i = 0; i < half; i++)
+		  dst [i] = dom != FB_RANGE
+			    ? W.img [(size_t) dom * FB_IMG_STRIDE + (half - 1) + i] : 0.0f;
+	       const short *in = W.into + (size_t) (2 * s + label) * 6;
+	       const float *wt = W.weight + (size_t) (2 * s + label) * 6;
+	       for (int e = 0; (dom = in [e]) != FB_NO_EDGE; e++)
+		  for (int i = 0; i < half; i++)
+		     dst [i] += W.img [(size_t) dom * FB_IMG_STRIDE + (half - 1) + i] * wt [e];
+	    }
+      /* compute_ip_states_state (0, 2): level outermost */
+      for (int li = 0; li < P.nlev; li++)
+	 for (unsigned s1 = 0; s1 < 3; s1++)
+	    for (unsigned s2 = 0; s2 <= s1; s2++)
+	    {
+	       const float ip = dev_ss_entry (P, W, li, s1, s2);
+
+	       W.SS [((size_t) li * P.s_cap + s1) * P.s_cap + s2] = ip;
+	       W.SS [((size_t) li * P.s_cap + s2) * P.s_cap + s1] = ip;
+	       if (s1 == s2)
+		  W.diag [(size_t) li * P.s_cap + s1] = ip;
+	    }
+      sh.h->states = 3;
+   }
+   __syncthreads ();
+}
+
+/*****************************************************************************
+		     matching pursuit  (codec/approx.c:317-642)
+*****************************************************************************/
+
+__device__ __forceinline__ int
+dom_state (const Sh &sh, const MpWork &w, int d)
+{
+   return d < w.pool_n ? (int) sh.pool [d] : w.y_state;
+}
+
+/* per-step scalars every candidate needs (thread 0) */
+__device__ void
+t0_mp_prepare_step (const DevParams &P, const Sh &sh, MpRes &mp, int n)
+{
+   MpWork &w = sh.h->w;
+   int	   nc = 0, ncs = 0;
+   float   prefix = 0;
+
+   w.n = n;
+   for (int k = 0; k < n; k++)
+   {
+      w.fB [k] = w.B [k] / w.N [k];
+      if (mp.weight [k] != 0)
+      {
+	 const int idx = mp.indices [k];
+	 const int st  = dom_state (sh, w, idx);
+
+	 w.cvec [nc++] = (short) idx;
+	 if (st != w.y_state || w.y_state < 0)
+	 {
+	    /* insertion sort by domain index (rle_bits sorts with qsort) */
+	    int p = ncs++;
+	    while (p > 0 && w.csorted [p - 1] > idx)
+	    {
+	       w.csorted [p] = w.csorted [p - 1];
+	       p--;
+	    }
+	    w.csorted [p] = (short) idx;
+	 }
+	 /* aac_bits prefix over the chosen weights (coeff.c:230-237) */
+	 if (st)
+	    prefix = (float) ((double) prefix
+			      - w.l2_lv [dev_rtob (mp.weight [k], P.rpf_m, P.rpf_range)]);
+	 else
+	    prefix = (float) ((double) prefix
+			      - w.l2_dc [dev_rtob (mp.weight [k], P.dc_m, P.dc_range)]);
+      }
+   }
+   w.nc	   = nc;
+   w.ncs   = ncs;
+   w.wb_nd = (float) ((double) prefix - w.l2_lv [dev_rtob (0.5f, P.rpf_m, P.rpf_range)]);
+   w.wb_dc = (float) ((double) prefix - w.l2_dc [dev_rtob (0.5f, P.dc_m, P.dc_range)]);
+}
+
+/*
+ *  One matching pursuit over the current pool for the range (level, image, address).
+ *  'mp' lives in shared memory; mp.exclude must be set by the caller.
+ */
+template <int NT>
+__device__ void
+cta_matching_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &mp,
+		      int level, unsigned image, unsigned address, float tree_bits,
+		      float price, int y_state_in)
+{
+   const int	tid	 = threadIdx.x;
+   const int	lane	 = tid & 31;
+   const int	warp	 = tid >> 5;
+   MpWork      &w	 = sh.h->w;
+   const float	min_norm = 2e-3f;
+   const int	dcap	 = sh.dcap;
+
+   /* ---- prologue: per-call tables ---- */
+   if (tid == 0)
+   {
+      int y_state = y_state_in;
+
+      if (y_state >= 0 && !(W.domain_type [y_state] & 2))
+	 y_state = -1;
+      w.y_state = y_state;
+      w.pool_n	= BLOB_U16 (sh, MB_N);
+      w.ydom	= -1;
+      w.D	= w.pool_n;
+      if (y_state >= 0)
+      {
+	 /* rle_generate (domain-pool.c:707-735): the y-state is an extra domain unless
+	    it already is a pool member */
+	 int member = -1;
+	 for (int d = 0; d < w.pool_n; d++)
+	    if (sh.pool [d] == y_state)
+	       member = d;
+	 if (member >= 0)
+	    w.ydom = member;
+	 else
+	 {
+	    w.ydom = w.pool_n;
+	    w.D	   = w.pool_n + 1;
+	 }
+      }
+      w.level = level;
+      w.li    = level - P.lmin;
+      w.size  = 1 << level;
+      w.price = price;
+      w.norm  = t0_node_norm (P, sh, image, address, level);
+      w.additional_bits = tree_bits + 0.0f + 0.0f + 0.0f + 0.0f;
+      w.d0b [0] = t0_d0_bits (sh, 0, y_state, c_matrix_0, c_matrix_1);
+      w.d0b [1] = t0_d0_bits (sh, 1, y_state, c_matrix_0, c_matrix_1);
+      sh.h->mp_calls++;
+   }
+   /* log2 tables of the models (the models do not change during one pursuit) */
+   {
+      const int	   ctx	  = level - P.coeff_min_level;
+      const short *counts = sh.blob + MB_COUNTS;
+      const short *lv	  = counts + P.aac_dc_size + ctx * P.aac_lvl_size;
+
+      for (int i = tid; i < P.aac_dc_size + P.aac_lvl_size + FB_MAXEDGES + 2; i += NT)
+      {
+	 if (i < P.aac_dc_size)
+	    w.l2_dc [i] = log2 ((double) (counts [i] / (float) sh.blob [MB_TOTALS]));
+	 else if (i < P.aac_dc_size + P.aac_lvl_size)
+	 {
+	    const int c = i - P.aac_dc_size;
+	    w.l2_lv [c] = log2 ((double) (lv [c] / (float) sh.blob [MB_TOTALS + ctx + 1]));
+	 }
+	 else
+	 {
+	    const int k = i - P.aac_dc_size - P.aac_lvl_size;
+	    w.mbase [k] = neg_log2f_via_double (BLOB_S16 (sh, MB_COUNT + (k <= FB_MAXEDGES ? k : FB_MAXEDGES))
+						/ (float) BLOB_U16 (sh, MB_TOTAL));
+	 }
+      }
+   }
+   __syncthreads ();
+
+   const int   D     = w.D;
+   const int   li    = w.li;
+   const float fsize = (float) w.size;
+
+   /* ---- numerators / denominators (approx.c:358-374) ---- */
+   for (int d = tid; d < D; d += NT)
+   {
+      const int	    st	 = dom_state (sh, w, d);
+      const float   den	 = W.diag [(size_t) li * P.s_cap + st];
+      unsigned char used = 0;
+      float	    num	 = 0;
+
+      if (den / fsize < min_norm)
+	 used = 1;
+      else
+      {
+	 num = W.T [(size_t) image * P.s_cap + st];
+	 if (fabsf (num) < min_norm)
+	    used = 1;
+      }
+      for (int e = 0; e < FB_MAXEDGES && mp.exclude [e] != FB_NO_EDGE; e++)
+	 if (mp.exclude [e] == d)
+	    used = 1;
+      sh.num [d]  = num;
+      sh.den [d]  = den;
+      sh.used [d] = used;
+   }
+   if (tid == 0)
+   {
+      /* costs of the empty linear combination (approx.c:391-400) */
+      mp.err	      = w.norm;
+      mp.weights_bits = 0;
+      mp.matrix_bits  = dev_rle_bits (w.mbase, w.d0b, w.csorted, 0, (unsigned) w.pool_n);
+      mp.costs	      = (mp.matrix_bits + mp.weights_bits + w.additional_bits) * price
+			+ mp.err;
+      t0_mp_prepare_step (P, sh, mp, 0);
+      w.min_costs = mp.costs;
+   }
+   __syncthreads ();
+
+   int n = 0;
+   for (;;)
+   {
+      /* ---- candidates, chunk by chunk in index order ---- */
+      for (int base = 0; base < D; base += NT)
+      {
+	 const int   d	      = base + tid;
+	 float	     key      = INFINITY;
+	 const float cur_min  = w.min_costs;
+
+	 if (d < D && !sh.used [d])
+	 {
+	    const int	st    = dom_state (sh, w, d);
+	    const float num   = sh.num [d], den = sh.den [d];
+	    const bool	is_y  = (d == w.ydom);
+	    short	sorted [FB_MAXEDGES + 1];
+	    int		ns    = w.ncs;
+
+	    /* pass 1 (approx.c:433-462): rate with a dummy weight 0.5 */
+	    {
+	       int p = 0;
+#pragma unroll
+	       for (int e = 0; e < FB_MAXEDGES + 1; e++)
+		  sorted [e] = e < ns ? w.csorted [e] : (short) 0x7fff;
+	       if (!is_y)
+	       {
+		  /* insert d */
+		  p = ns;
+#pragma unroll
+		  for (int e = FB_MAXEDGES; e > 0; e--)
+		     if (e <= p && sorted [e - 1] > d)
+		     {
+			sorted [e] = sorted [e - 1];
+			p	   = e - 1;
+		     }
+#pragma unroll
+		  for (int e = 0; e < FB_MAXEDGES + 1; e++)
+		     if (e == p)
+			sorted [e] = (short) d;
+		  ns++;
+	       }
+	    }
+	    const float mb1 = dev_rle_bits (w.mbase, w.d0b, sorted, ns, (unsigned) w.pool_n);
+	    const float wb1 = st ? w.wb_nd : w.wb_dc;
+	    const float bound = ((mb1 + wb1 + w.additional_bits) * price + mp.err)
+				- (num * num) / den;
+
+	    if (bound < cur_min)
+	    {
+	       /* pass 2 (approx.c:463-602) */
+	       float f [FB_MAXEDGES], r [FB_MAXEDGES];
+	       int   v [FB_MAXEDGES];
+
+#pragma unroll
+	       for (int k = 0; k < FB_MAXEDGES; k++)
+	       {
+		  f [k] = k < n ? w.fB [k] : 0.0f;
+		  v [k] = k < n ? (int) mp.indices [k] : d;
+		  r [k] = 0.0f;
+	       }
+#pragma unroll
+	       for (int k = 0; k < FB_MAXEDGES; k++)
+		  if (k == n)
+		     f [k] = num / den;
+#pragma unroll
+	       for (int l = FB_MAXEDGES - 1; l >= 0; l--)
+		  if (l <= n)
+		  {
+		     const int	 stl = dom_state (sh, w, v [l]);
+		     const float q   = stl ? dev_btor (dev_rtob (f [l], P.rpf_m, P.rpf_range),
+						       P.rpf_m, P.rpf_range)
+					   : dev_btor (dev_rtob (f [l], P.dc_m, P.dc_range),
+						       P.dc_m, P.dc_range);
+		     f [l] = q;
+		     r [l] = q;
+#pragma unroll
+		     for (int k = 0; k < FB_MAXEDGES - 1; k++)
+			if (k < l)
+			   f [k] -= q * sh.G [k * dcap + v [l]] / w.N [k];
+		  }
+	       /* rate of the quantised combination */
+	       float w_bits = 0, m_bits;
+	       {
+		  short srt [FB_MAXEDGES + 1];
+		  int	cnt = 0;
+
+#pragma unroll
+		  for (int e = 0; e < FB_MAXEDGES + 1; e++)
+		     srt [e] = (short) 0x7fff;
+#pragma unroll
+		  for (int k = 0; k < FB_MAXEDGES; k++)
+		     if (k <= n && f [k] != 0)
+		     {
+			const int stk = dom_state (sh, w, v [k]);
+
+			if (stk)
+			   w_bits = (float) ((double) w_bits
+					     - w.l2_lv [dev_rtob (f [k], P.rpf_m, P.rpf_range)]);
+			else
+			   w_bits = (float) ((double) w_bits
+					     - w.l2_dc [dev_rtob (f [k], P.dc_m, P.dc_range)]);
+			if (v [k] != w.ydom)
+			{
+			   /* insertion sort */
+			   int p = cnt;
+#pragma unroll
+			   for (int e = FB_MAXEDGES; e > 0; e--)
+			      if (e <= p && srt [e - 1] > v [k])
+			      {
+				 srt [e] = srt [e - 1];
+				 p	 = e - 1;
+			      }
+#pragma unroll
+			   for (int e = 0; e < FB_MAXEDGES + 1; e++)
+			      if (e == p)
+				 srt [e] = (short) v [k];
+			   cnt++;
+			}
+		     }
+		  m_bits = dev_rle_bits (w.mbase, w.d0b, srt, cnt, (unsigned) w.pool_n);
+	       }
+	       /* back to the orthogonal basis, error (approx.c:571-586) */
+#pragma unroll
+	       for (int k = 0; k < FB_MAXEDGES - 1; k++)
+#pragma unroll
+		  for (int l = k + 1; l < FB_MAXEDGES; l++)
+		     if (l <= n)
+			r [k] += sh.G [k * dcap + v [l]] * r [l] / w.N [k];
+	       float m_err = w.norm;
+#pragma unroll
+	       for (int k = 0; k < FB_MAXEDGES; k++)
+		  if (k <= n)
+		  {
+		     const float Nk = k == n ? den : w.N [k];
+		     const float Bk = k == n ? num : w.B [k];
+		     m_err += (r [k] * r [k]) * Nk - 2 * r [k] * Bk;
+		  }
+	       const float costs = (m_bits + w_bits + w.additional_bits) * price + m_err;
+
+	       key = bound > costs ? bound : costs; /* both must beat the running min */
+#pragma unroll
+	       for (int k = 0; k < FB_MAXEDGES; k++)
+		  sh.slot [k * NT + tid] = f [k];
+	       sh.slot [5 * NT + tid] = m_bits;
+	       sh.slot [6 * NT + tid] = w_bits;
+	       sh.slot [7 * NT + tid] = m_err;
+	       sh.slot [8 * NT + tid] = costs;
+	    }
+	 }
+	 sh.slot [9 * NT + tid] = key;
+	 {
+	    float m = key;
+#pragma unroll
+	    for (int o = 16; o; o >>= 1)
+	       m = fminf (m, __shfl_xor_sync (0xffffffffu, m, o));
+	    if (lane == 0)
+	       sh.wmin [warp] = m;
+	 }
+	 __syncthreads ();
+
+	 /* ---- ordered resolution by warp 0: candidates in index order against the
+		running minimum (approx.c:422-603 processes domains sequentially) ---- */
+	 if (warp == 0)
+	 {
+	    float m	 = w.min_costs;
+	    int	  winner = -1;
+	    float wm	 = lane < NT / 32 ? sh.wmin [lane] : INFINITY;
+	    int	  cur	 = 0;
+
+	    for (;;)
+	    {
+	       unsigned mask = __ballot_sync (0xffffffffu, wm < m && lane >= cur);
+	       if (!mask)
+		  break;
+	       const int   ww	= __ffs (mask) - 1;
+	       const float k2	= sh.slot [9 * NT + ww * 32 + lane];
+	       const float c2	= sh.slot [8 * NT + ww * 32 + lane];
+	       int	   last = -1;
+
+	       for (;;)
+	       {
+		  unsigned m2 = __ballot_sync (0xffffffffu, k2 < m && lane > last);
+		  if (!m2)
+		     break;
+		  last	 = __ffs (m2) - 1;
+		  m	 = __shfl_sync (0xffffffffu, c2, last);
+		  winner = ww * 32 + last;
+	       }
+	       cur = ww + 1;
+	    }
+	    if (winner >= 0)
+	    {
+	       if (lane < 5)
+		  w.best_f [lane] = sh.slot [lane * NT + winner];
+	       else if (lane == 5)
+		  w.best_mbits = sh.slot [5 * NT + winner];
+	       else if (lane == 6)
+		  w.best_wbits = sh.slot [6 * NT + winner];
+	       else if (lane == 7)
+		  w.best_err = sh.slot [7 * NT + winner];
+	       else if (lane == 8)
+	       {
+		  w.best_costs = m;
+		  w.min_costs  = m;
+		  w.index      = base + winner;
+	       }
+	    }
+	    else if (base == 0 && lane == 8)
+	       w.index = -1;	/* first chunk of a step: no winner yet */
+	 }
+	 __syncthreads ();
+      }
+
+      /* ---- commit the step (approx.c:605-632) ---- */
+      const int index = w.index;
+      if (index < 0)
+	 break;
+      if (tid == 0)
+      {
+	 /* not full_search: a found vector always improves the total */
+	 mp.costs	 = w.best_costs;
+	 mp.err		 = w.best_err;
+	 mp.matrix_bits	 = w.best_mbits;
+	 mp.weights_bits = w.best_wbits;
+	 for (int k = 0; k <= n; k++)
+	    mp.weight [k] = w.best_f [k];
+	 mp.indices [n] = (short) index;
+	 mp.into [n]	= (short) dom_state (sh, w, index);
+	 sh.used [index] = 1;
+	 w.B [n] = sh.num [index];
+	 w.N [n] = sh.den [index];
+	 sh.h->mp_steps++;
+	 if (n + 1 < P.max_elements)
+	    t0_mp_prepare_step (P, sh, mp, n + 1);
+      }
+      __syncthreads ();
+      if (n + 1 >= P.max_elements)
+      {
+	 n++;
+	 break;
+      }
+      /* ---- Gram-Schmidt step n over the pool (approx.c:644-699) ---- */
+      {
+	 const int   sidx = dom_state (sh, w, index);
+	 const float Nn	  = w.N [n], Bn = w.B [n];
+	 const float *row = W.SS + ((size_t) li * P.s_cap + sidx) * P.s_cap;
+
+	 for (int d = tid; d < D; d += NT)
+	    if (!sh.used [d])
+	    {
+	       float tmp = row [dom_state (sh, w, d)];
+
+	       for (int k = 0; k < n; k++)
+		  tmp -= sh.G [k * dcap + d] / w.N [k] * sh.G [k * dcap + index];
+	       sh.G [n * dcap + d] = tmp;
+	       const float den = sh.den [d] - (tmp * tmp) / Nn;
+	       sh.den [d] = den;
+	       sh.num [d] = sh.num [d] - Bn / Nn * tmp;
+	       if (den / fsize < min_norm)
+		  sh.used [d] = 1;
+	    }
+      }
+      n++;
+      /* no barrier needed here: the next pass touches only the thread's own domains
+	 (same tid -> same d) plus data published before the last barrier */
+   }
+
+   if (tid == 0)
+   {
+      mp.indices [n] = FB_NO_EDGE;	/* best_n == n without full_search */
+      mp.costs = (mp.matrix_bits + mp.weights_bits + w.additional_bits) * price + mp.err;
+   }
+   __syncthreads ();
+}
+
+/* rle_update (domain-pool.c:795-830) + inlined qac_update of the DC model (:404-446) */
+__device__ void
+t0_rle_update (const Sh &sh, const MpWork &w, const short *used_domains)
+{
+   int	    state_0 = 0, state_y = 0, edge = 0;
+   const int y_state = w.y_state;
+
+   for (edge = 0; used_domains [edge] != FB_NO_EDGE; edge++)
+   {
+      const int st = dom_state (sh, w, used_domains [edge]);
+
+      if (st == 0)
+	 state_0 = 1;
+      else if (st == y_state)
+	 state_y = 1;
+   }
+   BLOB_S16 (sh, MB_COUNT + edge)++;
+   BLOB_U16 (sh, MB_TOTAL)++;
+   {
+      int y_is_domain = 0, used_y = 0;
+
+      if (BLOB_U16 (sh, MB_D0N) > 0)
+      {
+	 BLOB_S16 (sh, MB_D0INDEX)++;
+	 if (0 == y_state)
+	    y_is_domain = 1;
+      }
+      if (state_0)
+      {
+	 if (0 == y_state)
+	 {
+	    if (y_is_domain)
+	       BLOB_S16 (sh, MB_D0INDEX)--;
+	    BLOB_U16 (sh, MB_D0YINDEX) >>= 1;
+	    used_y = 1;
+	 }
+	 else
+	 {
+	    BLOB_S16 (sh, MB_D0INDEX)--;
+	    BLOB_S16 (sh, MB_D0INDEX) >>= 1;
+	 }
+      }
+      if (y_state >= 0 && !used_y)
+	 BLOB_U16 (sh, MB_D0YINDEX)++;
+      if (BLOB_U16 (sh, MB_D0N) > 0 && BLOB_S16 (sh, MB_D0INDEX) > 1020)
+	 BLOB_S16 (sh, MB_D0INDEX) = 1020;
+      if (BLOB_U16 (sh, MB_D0YINDEX) > 1020)
+	 BLOB_U16 (sh, MB_D0YINDEX) = 1020;
+   }
+   if (state_y)
+      BLOB_U16 (sh, MB_YINDEX) >>= 1;
+   else
+      BLOB_U16 (sh, MB_YINDEX)++;
+   if (BLOB_U16 (sh, MB_YINDEX) > 1020)
+      BLOB_U16 (sh, MB_YINDEX) = 1020;
+}
+
+/* coeff.c:242-267 */
+__device__ void
+t0_aac_update (const DevParams &P, const Sh &sh, const float *weight, const short *into,
+	       int level)
+{
+   const int ctx    = level - P.coeff_min_level;
+   short    *counts = sh.blob + MB_COUNTS;
+   short    *lv	    = counts + P.aac_dc_size + ctx * P.aac_lvl_size;
+
+   for (int e = 0; into [e] != FB_NO_EDGE; e++)
+      if (into [e])
+      {
+	 lv [dev_rtob (weight [e], P.rpf_m, P.rpf_range)]++;
+	 sh.blob [MB_TOTALS + ctx + 1]++;
+      }
+      else
+      {
+	 counts [dev_rtob (weight [e], P.dc_m, P.dc_range)]++;
+	 sh.blob [MB_TOTALS]++;
+      }
+}
+
+/*
+ *  codec/approx.c:74-271 (approximate_range) for the still-image option set
+ *  (second_domain_block optional).  Result in 'out' / return value in sh.h->ret_costs.
+ */
+template <int NT>
+__device__ void
+cta_approximate_range (const DevParams &P, const TileWs &W, const Sh &sh, float max_costs,
+		       float price, int y_state, RangeRes *out, int level, unsigned image,
+		       unsigned address, unsigned x, unsigned y)
+{
+   ShHdr *h = sh.h;
+
+   if (threadIdx.x == 0)
+      h->mp.exclude [0] = FB_NO_EDGE;
+   /* (the prologue of the pursuit starts with thread-0 work followed by a barrier) */
+   cta_matching_pursuit<NT> (P, W, sh, h->mp, level, image, address, out->tree_bits,
+			     price, y_state);
+   if (P.second_domain_block)
+   {
+      if (threadIdx.x == 0)
+      {
+	 h->tmp		    = h->mp;
+	 h->tmp.exclude [0] = h->tmp.indices [0];
+	 h->tmp.exclude [1] = FB_NO_EDGE;
+      }
+      __syncthreads ();
+      cta_matching_pursuit<NT> (P, W, sh, h->tmp, level, image, address, out->tree_bits,
+				price, y_state);
+      if (threadIdx.x == 0 && h->tmp.costs < h->mp.costs)
+	 h->mp = h->tmp;
+      __syncthreads ();
+   }
+   if (threadIdx.x == 0)
+   {
+      MpRes &mp = h->mp;
+      float  costs;
+      int    n_edges = -1;
+
+      if (mp.costs < max_costs)
+      {
+	 int new_index = 0, edge;
+
+	 for (int old = 0; mp.indices [old] != FB_NO_EDGE; old++)
+	    if (mp.weight [old] != 0)
+	    {
+	       mp.indices [new_index] = mp.indices [old];
+	       mp.into [new_index]    = mp.into [old];
+	       mp.weight [new_index]  = mp.weight [old];
+	       new_index++;
+	    }
+	 mp.indices [new_index] = FB_NO_EDGE;
+	 mp.into [new_index]	= FB_NO_EDGE;
+	 t0_rle_update (sh, h->w, mp.indices);
+	 t0_aac_update (P, sh, mp.weight, mp.into, level);
+	 for (edge = 0; mp.indices [edge] != FB_NO_EDGE; edge++)
+	 {
+	    out->into [edge]   = mp.into [edge];
+	    out->weight [edge] = mp.weight [edge];
+	 }
+	 out->into [edge]  = FB_NO_EDGE;
+	 out->matrix_bits  = mp.matrix_bits;
+	 out->weights_bits = mp.weights_bits;
+	 out->err	   = mp.err;
+	 costs		   = mp.costs;
+	 n_edges	   = edge;
+      }
+      else
+      {
+	 out->into [0] = FB_NO_EDGE;
+	 costs	       = FB_MAXCOSTS;
+      }
+      h->ret_costs = costs;
+      if (W.trace && h->trace_len < P.trace_cap)
+      {
+	 fb200_trace_rec_t *t = W.trace + h->trace_len;
+
+	 t->level   = (uint16_t) level;
+	 t->image   = (uint16_t) image;
+	 t->address = (uint16_t) address;
+	 t->x	    = (uint16_t) x;
+	 t->y	    = (uint16_t) y;
+	 t->y_state = (int16_t) y_state;
+	 t->states  = (uint16_t) h->states;
+	 t->n_edges = (int16_t) n_edges;
+	 t->max_costs	 = max_costs;
+	 t->price	 = price;
+	 t->costs	 = costs;
+	 t->err		 = n_edges >= 0 ? out->err : 0;
+	 t->matrix_bits	 = n_edges >= 0 ? out->matrix_bits : 0;
+	 t->weights_bits = n_edges >= 0 ? out->weights_bits : 0;
+	 for (int e = 0; e < 6; e++)
+	 {
+	    t->into [e]	  = e < n_edges ? out->into [e] : (int16_t) -1;
+	    t->weight [e] = e < n_edges ? out->weight [e] : 0;
+	 }
+      }
+      if (W.trace)
+	 h->trace_len++;
+   }
+   __syncthreads ();
+}
+
+/*****************************************************************************
+		     model snapshots (subdivide.c:188-237)
+*****************************************************************************/
+
+template <int NT>
+__device__ void
+cta_copy_s16 (short *dst, const short *src, int n)
+{
+   for (int i = threadIdx.x; i < n; i += NT)
+      dst [i] = src [i];
+}
+
+/*****************************************************************************
+		   the bintree recursion  (codec/subdivide.c:60-502)
+*****************************************************************************/
+
+template <int NT>
+__device__ void
+cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
+		    int root_y_state)
+{
+   ShHdr    *h	 = sh.h;
+   const int tid = threadIdx.x;
+   int	     it	 = 0;
+
+   if (tid == 0)
+   {
+      Frame &F = h->frames [0];
+
+      F.max_costs = FB_MAXCOSTS;
+      F.x = F.y = F.image = F.address = 0;
+      F.level	= P.level;
+      F.y_state = root_y_state;
+      h->depthv [0] = 0;
+      h->state [0]  = ST_ENTER;
+      h->band	= band;
+      h->price	= band ? P.price * P.chroma_decrease : P.price;
+   }
+   __syncthreads ();
+
+   for (;; it++)
+   {
+      const int state = h->state [it & 1];
+      const int depth = h->depthv [it & 1];
+      Frame    &F     = h->frames [depth];
+      RangeRes *res   = depth ? &h->frames [depth - 1].child [h->frames [depth - 1].label]
+			      : &h->root;
+      int      &next  = h->state [(it + 1) & 1];
+      int      &ndepth = h->depthv [(it + 1) & 1];
+
+      if (threadIdx.x == 0)
+	 ndepth = depth;	/* default: stay at this depth */
+
+      if (state == ST_DONE || state == ST_ABORT)
+	 break;
+      if (h->status != FB200_OK)
+	 break;
+
+      switch (state)
+      {
+	 case ST_ENTER:
+	 {
+	    const int level = F.level;
+	    bool      leave = false;
+
+	    if (tid == 0)
+	    {
+	       res->into [0] = FB_NO_EDGE;
+	       res->tree     = FB_RANGE;
+	    }
+	    if (level < 3)
+	    {
+	       if (tid == 0)
+	       {
+		  h->ret_costs = FB_MAXCOSTS;
+		  next	       = ST_RETURN;
+	       }
+	       leave = true;
+	    }
+	    else if (F.x >= (unsigned) P.width || F.y >= (unsigned) P.height)
+	    {
+	       if (tid == 0)
+	       {
+		  h->ret_costs = 0;
+		  next	       = ST_RETURN;
+	       }
+	       leave = true;
+	    }
+	    if (leave)
+	    {
+	       __syncthreads ();
+	       break;
+	    }
+	    if (level == P.lc_max)
+	    {
+	       if (tid == 0)
+		  F.address = F.image = 0;
+	       __syncthreads ();
+	       cta_init_range<NT> (P, W, sh, F.x, F.y, band);
+	    }
+	    /* snapshot of the models (subdivide.c:188-194) */
+	    {
+	       short	*snap  = W.snap + (size_t) depth * 2 * P.blob_len;
+	       unsigned *tsnap = W.treesnap + (size_t) depth * 2 * FB200_MAXLEVEL;
+
+	       cta_copy_s16<NT> (snap, sh.blob, P.blob_len);
+	       for (int i = tid; i < FB200_MAXLEVEL; i += NT)
+	       {
+		  tsnap [i]		     = h->tree_counts [i];
+		  tsnap [FB200_MAXLEVEL + i] = h->tree_total [i];
+	       }
+	       if (tid == 0)
+		  F.states_snap = h->states;
+	    }
+	    /* y states of the children (subdivide.c:172-183) */
+	    if (tid == 0)
+	    {
+	       for (int label = 0; label < 2; label++)
+		  F.new_y_state [label] = (band != 0 && F.y_state != FB_RANGE)
+					  ? (int) W.tree [2 * F.y_state + label] : FB_RANGE;
+	    }
+	    /* alternative 1: linear combination (subdivide.c:200-221) */
+	    if (level <= P.lc_max)
+	    {
+	       if (tid == 0)
+	       {
+		  F.lrange.tree		= FB_RANGE;
+		  F.lrange.x		= (unsigned short) F.x;
+		  F.lrange.y		= (unsigned short) F.y;
+		  F.lrange.tree_bits	= t0_tree_bits (h, 0, level);
+		  F.lrange.matrix_bits	= 0;
+		  F.lrange.weights_bits = 0;
+		  F.lrange.err		= 0;
+		  F.lrange.into [0]	= FB_NO_EDGE;
+	       }
+	       __syncthreads ();
+	       cta_approximate_range<NT> (P, W, sh, F.max_costs, h->price, F.y_state,
+					  &F.lrange, level, F.image, F.address, F.x, F.y);
+	       if (tid == 0)
+		  F.lincomb_costs = h->ret_costs;
+	    }
+	    else if (tid == 0)
+	       F.lincomb_costs = FB_MAXCOSTS;
+	    __syncthreads ();
+	    /* keep the "lc" models, restore the snapshot (subdivide.c:226-237) */
+	    {
+	       short *snap = W.snap + (size_t) depth * 2 * P.blob_len;
+
+	       cta_copy_s16<NT> (snap + P.blob_len, sh.blob, P.blob_len);
+	       __syncthreads ();
+	       cta_copy_s16<NT> (sh.blob, snap, P.blob_len);
+	    }
+	    if (tid == 0)
+	    {
+	       if (level > P.lc_min)
+	       {
+		  /* alternative 2: recursive subdivision (subdivide.c:243-272) */
+		  F.r_tree_bits	   = t0_tree_bits (h, 1, level);
+		  F.r_matrix_bits  = 0;
+		  F.r_weights_bits = 0;
+		  F.r_err	   = 0;
+		  F.subdivide_costs = (F.r_tree_bits + F.r_weights_bits + F.r_matrix_bits
+				       + 0.0f + 0.0f + 0.0f + 0.0f) * h->price;
+		  F.label = 0;
+		  for (int label = 0; label < 2; label++)
+		  {
+		     RangeRes &c = F.child [label];
+		     c.tree = 0;	/* memset (child, 0) */
+		     c.into [0] = 0;
+		     c.err = c.tree_bits = c.matrix_bits = c.weights_bits = 0;
+		  }
+		  next = ST_CHILD;
+	       }
+	       else
+	       {
+		  F.subdivide_costs = FB_MAXCOSTS;
+		  next		    = ST_DECIDE;
+	       }
+	    }
+	    __syncthreads ();
+	    break;
+	 }
+
+	 case ST_CHILD:
+	 {
+	    const int	   label = F.label;
+	    const int	   level = F.level;
+	    const unsigned cimg	 = F.image * 2 + label + 1;
+	    const unsigned cadr	 = F.address * 2 + label;
+	    const unsigned cx	 = (level & 1) ? F.x : F.x + label * width_of_level (level - 1);
+	    const unsigned cy	 = (level & 1) ? F.y + label * height_of_level (level - 1) : F.y;
+
+	    /* products of the states born in child 0 (subdivide.c:295-297) */
+	    if (label && level <= P.lc_max)
+	       cta_compute_T<NT> (P, W, sh, F.states_snap, cimg, level - 1);
+	    if (tid == 0)
+	    {
+	       const float remaining = fmin2 (F.lincomb_costs, F.max_costs) - F.subdivide_costs;
+
+	       F.child [label].x = (unsigned short) cx;
+	       F.child [label].y = (unsigned short) cy;
+	       if (remaining > 0)
+	       {
+		  Frame &C = h->frames [depth + 1];
+
+		  C.max_costs = remaining;
+		  C.x	      = cx;
+		  C.y	      = cy;
+		  C.image     = cimg;
+		  C.address   = cadr;
+		  C.level     = level - 1;
+		  C.y_state   = F.new_y_state [label];
+		  ndepth      = depth + 1;
+		  next	      = ST_ENTER;
+	       }
+	       else
+	       {
+		  h->ret_costs = 0;	/* subdivide() not called: costs unchanged */
+		  next	       = ST_AFTER_CHILD;
+	       }
+	    }
+	    __syncthreads ();
+	    break;
+	 }
+
+	 case ST_AFTER_CHILD:
+	 {
+	    if (tid == 0)
+	    {
+	       const int label = F.label;
+	       RangeRes &c     = F.child [label];
+
+	       if (F.subdivide_costs >= fmin2 (F.lincomb_costs, F.max_costs))
+	       {
+		  F.subdivide_costs = FB_MAXCOSTS;
+		  next		    = ST_DECIDE;
+	       }
+	       else
+	       {
+		  F.r_err	   += c.err;
+		  F.r_tree_bits	   += c.tree_bits;
+		  F.r_matrix_bits  += c.matrix_bits;
+		  F.r_weights_bits += c.weights_bits;
+		  /* tree_update (bintree.c:35-53) */
+		  if (c.tree != FB_RANGE)
+		     h->tree_counts [F.level - 1]++;
+		  h->tree_total [F.level - 1]++;
+		  F.label = label + 1;
+		  next	  = F.label < 2 ? ST_CHILD : ST_DECIDE;
+	       }
+	    }
+	    __syncthreads ();
+	    break;
+	 }
+
+	 case ST_DECIDE:
+	 {
+	    const float lin = F.lincomb_costs, sub = F.subdivide_costs;
+	    short      *snap  = W.snap + (size_t) depth * 2 * P.blob_len;
+	    unsigned   *tsnap = W.treesnap + (size_t) depth * 2 * FB200_MAXLEVEL;
+
+	    if ((lin >= FB_MAXCOSTS && sub >= FB_MAXCOSTS) || lin < sub)
+	    {
+	       const bool fail = (lin >= FB_MAXCOSTS && sub >= FB_MAXCOSTS);
+
+	       /* restore snapshot or adopt the lc models; restore the tree model; drop
+		  the states created below this node (subdivide.c:409-467) */
+	       cta_copy_s16<NT> (sh.blob, fail ? snap : snap + P.blob_len, P.blob_len);
+	       for (int i = tid; i < FB200_MAXLEVEL; i += NT)
+	       {
+		  h->tree_counts [i] = tsnap [i];
+		  h->tree_total [i]  = tsnap [FB200_MAXLEVEL + i];
+	       }
+	       if (tid == 0)
+	       {
+		  h->states = F.states_snap;	/* remove_states (wfalib.c:276-310) */
+		  if (fail)
+		     h->ret_costs = FB_MAXCOSTS;
+		  else
+		  {
+		     const unsigned short rx = (unsigned short) F.x, ry = (unsigned short) F.y;
+		     *res      = F.lrange;
+		     res->tree = FB_RANGE;
+		     res->x    = rx;
+		     res->y    = ry;
+		     h->ret_costs = lin;
+		  }
+		  next = ST_RETURN;
+	       }
+	       __syncthreads ();
+	    }
+	    else
+	    {
+	       /* new state (subdivide.c:468-501, init_new_state :549-610) */
+	       const int aux = band > 0
+			       || F.x + width_of_level (F.level) > (unsigned) P.width
+			       || F.y + height_of_level (F.level) > (unsigned) P.height;
+
+	       if (tid == 0)
+	       {
+		  const unsigned s = h->states;
+
+		  if (!aux)
+		  {
+		     /* rle_append (domain-pool.c:832-852) */
+		     const unsigned n = BLOB_U16 (sh, MB_N);
+		     if (n < BLOB_U16 (sh, MB_MAXDOM))
+		     {
+			sh.pool [n]	    = (short) s;
+			BLOB_U16 (sh, MB_N) = (unsigned short) (n + 1);
+		     }
+		  }
+		  for (int label = 0; label < 2; label++)
+		  {
+		     const RangeRes &c = F.child [label];
+
+		     W.tree [2 * s + label]    = c.tree;
+		     W.y_state [2 * s + label] = (short) F.new_y_state [label];
+		     W.x [2 * s + label]       = c.x;
+		     W.y [2 * s + label]       = c.y;
+		     W.y_column [2 * s + label] = 0;
+		     W.into [(size_t) (2 * s + label) * 6] = FB_NO_EDGE;
+		     for (int e = 0; c.into [e] != FB_NO_EDGE; e++)
+		     {
+			t0_append_edge (W, s, c.into [e], c.weight [e], label);
+			if (c.into [e] == F.new_y_state [label])
+			   W.y_column [2 * s + label] = 1;
+		     }
+		  }
+		  res->into [0]	    = FB_NO_EDGE;
+		  res->tree	    = (short) s;
+		  res->x	    = (unsigned short) F.x;
+		  res->y	    = (unsigned short) F.y;
+		  res->err	    = F.r_err;
+		  res->tree_bits    = F.r_tree_bits;
+		  res->matrix_bits  = F.r_matrix_bits;
+		  res->weights_bits = F.r_weights_bits;
+		  h->ret_costs	    = sub;
+		  next		    = ST_RETURN;
+	       }
+	       __syncthreads ();
+	       cta_append_state<NT> (P, W, sh, aux, F.level);
+	    }
+	    break;
+	 }
+
+	 case ST_RETURN:
+	 {
+	    if (tid == 0)
+	    {
+	       if (depth == 0)
+		  next = ST_DONE;
+	       else
+	       {
+		  Frame &Pf = h->frames [depth - 1];
+
+		  Pf.subdivide_costs += h->ret_costs;
+		  ndepth   = depth - 1;
+		  next	   = ST_AFTER_CHILD;
+	       }
+	    }
+	    __syncthreads ();
+	    break;
+	 }
+      }
+   }
+   __syncthreads ();
+}
+
+/*****************************************************************************
+				the kernel
+*****************************************************************************/
+
+template <int NT>
+__global__ void __launch_bounds__ (NT, 1)
+fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
+{
+   extern __shared__ __align__ (16) unsigned char smem_raw [];
+   const TileWs W   = ws_array [blockIdx.x];
+   const Sh	sh  = carve (smem_raw, P, NT);
+   ShHdr       *h   = sh.h;
+   const int	tid = threadIdx.x;
+
+   if (tid == 0)
+   {
+      h->status	   = FB200_OK;
+      h->trace_len = 0;
+      h->mp_calls = h->mp_steps = h->pass2 = h->blocks = h->ip_bytes = 0;
+      h->states	   = 0;
+   }
+   __syncthreads ();
+
+   if (P.first_band == 0)
+   {
+      cta_init_basis<NT> (P, W, sh);
+      /* init_tree_model (bintree.c:70-93), rle_model_alloc (domain-pool.c:655-672),
+	 aac_model_alloc (coeff.c:285-313) */
+      if (tid == 0)
+      {
+	 const unsigned c0 [FB200_MAXLEVEL] = {20, 17, 15, 10, 5, 4, 3, 2, 1, 1, 1,
+					       1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};
+	 const unsigned c1 [FB200_MAXLEVEL] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 3, 5,
+					       10, 15, 20, 25, 30, 35, 60, 60, 60, 60};
+	 for (int l = 0; l < FB200_MAXLEVEL; l++)
+	 {
+	    h->tree_counts [l] = c1 [l];
+	    h->tree_total [l]  = c0 [l] + c1 [l];
+	 }
+      }
+      for (int i = tid; i < P.blob_len; i += NT)
+	 sh.blob [i] = i >= MB_COUNTS - 1 ? 1 : 0;
+      __syncthreads ();
+      if (tid == 0)
+      {
+	 for (int k = 0; k < FB_MAXEDGES + 1; k++)
+	    BLOB_S16 (sh, MB_COUNT + k) = 1;
+	 BLOB_U16 (sh, MB_TOTAL)  = FB_MAXEDGES + 1;
+	 BLOB_U16 (sh, MB_MAXDOM) = (unsigned short) P.max_domains;
+	 /* the basis states that may be used as domains: 0, 1, 2 */
+	 for (unsigned s = 0; s < 3; s++)
+	    if (BLOB_U16 (sh, MB_N) < BLOB_U16 (sh, MB_MAXDOM))
+	    {
+	       sh.pool [BLOB_U16 (sh, MB_N)] = (short) s;
+	       BLOB_U16 (sh, MB_N)++;
+	       if (s == 0)
+	       {
+		  BLOB_S16 (sh, MB_D0INDEX) = 0;
+		  BLOB_U16 (sh, MB_D0N)	    = 1;
+	       }
+	    }
+	 sh.blob [MB_TOTALS] = (short) P.aac_dc_size;
+	 for (int l = P.lc_min; l <= P.lc_max; l++)
+	    sh.blob [MB_TOTALS + l - P.coeff_min_level + 1] = (short) P.aac_lvl_size;
+      }
+      __syncthreads ();
+   }
+
+   /* grey: one band */
+   cta_subdivide_band<NT> (P, W, sh, 0, FB_RANGE);
+
+   if (tid == 0)
+   {
+      TileResult *r = W.result;
+
+      if (h->status == FB200_OK && h->root.tree == FB_RANGE)
+	 h->status = FB200_ENOROOT;
+      r->status	      = h->status;
+      r->states	      = h->states;
+      r->basis_states = 3;
+      r->root_state   = h->root.tree >= 0 ? (unsigned) h->root.tree : 0;
+      r->costs [0]	  = h->ret_costs;
+      r->err [0]	  = h->root.err;
+      r->tree_bits [0]	  = h->root.tree_bits;
+      r->matrix_bits [0]  = h->root.matrix_bits;
+      r->weights_bits [0] = h->root.weights_bits;
+      r->trace_len = h->trace_len;
+      r->mp_calls  = h->mp_calls;
+      r->mp_steps  = h->mp_steps;
+      r->pass2	   = h->pass2;
+      r->blocks	   = h->blocks;
+      r->ip_bytes  = h->ip_bytes;
+   }
+}
+
+/*****************************************************************************
+			       probe kernel
+*****************************************************************************/
+
+__device__ __forceinline__ float range_of_enum (int e)
+{
+   return e == 0 ? 0.75f : e == 2 ? 1.5f : e == 3 ? 2.0f : 1.0f;
+}
+
+__global__ void
+fiasco_probe_kernel (int kind, int n, const float *f, const int *a, const int *b,
+		     const int *c, int *out_i, float *out_f)
+{
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+
+   if (i >= n)
+      return;
+   switch (kind)
+   {
+      case 0:
+	 out_i [i] = dev_rtob (f [i], a [i], range_of_enum (b [i]));
+	 break;
+      case 1:
+	 out_f [i] = dev_btor (a [i], b [i], range_of_enum (c [i]));
+	 break;
+      case 2:
+	 out_i [i] = (int) dev_bits_bin_code ((unsigned) a [i], (unsigned) b [i]);
+	 break;
+      case 3:
+	 out_f [i] = neg_log2f_via_double (a [i] / (float) b [i]);
+	 break;
+   }
+}
+
+} /* namespace */
+
+/*****************************************************************************
+				host launchers
+*****************************************************************************/
+
+int
+fb_tile_kernel_threads (const DevParams &p)
+{
+   /* threads span the domain pool: small tiles have ~100-250 domains, a 1024^2 frame
+      up to ~1500 */
+   if (p.s_cap <= 384)
+      return 128;
+   if (p.s_cap <= 1024)
+      return 256;
+   return 512;
+}
+
+size_t
+fb_tile_kernel_smem (const DevParams &p, int nt)
+{
+   size_t off [11];
+
+   return smem_layout (p, nt, off);
+}
+
+static bool g_tables_ready [64];
+
+static cudaError_t
+upload_tables (void)
+{
+   int dev = 0;
+   cudaError_t e = cudaGetDevice (&dev);
+   if (e != cudaSuccess)
+      return e;
+   if (dev >= 0 && dev < 64 && g_tables_ready [dev])
+      return cudaSuccess;
+   /* init_matrix_probabilities (domain-pool.c:970-999) */
+   static float m0 [1024], m1 [1024];
+   unsigned	index = 0;
+   for (unsigned n = 1; n <= 9; n++)
+      for (unsigned ex = 0; ex < 1u << n; ex++, index++)
+      {
+	 m1 [index] = (float) -log2 ((double) (1 / (float) (1 << n)));
+	 m0 [index] = (float) -log2 ((double) (1 - 1 / (float) (1 << n)));
+      }
+   e = cudaMemcpyToSymbol (c_matrix_0, m0, sizeof m0);
+   if (e != cudaSuccess)
+      return e;
+   e = cudaMemcpyToSymbol (c_matrix_1, m1, sizeof m1);
+   if (e != cudaSuccess)
+      return e;
+   if (dev >= 0 && dev < 64)
+      g_tables_ready [dev] = true;
+   return cudaSuccess;
+}
+
+template <int NT>
+static cudaError_t
+launch_nt (const DevParams &p, const TileWs *d_ws, int n_tiles, cudaStream_t stream)
+{
+   const size_t smem = fb_tile_kernel_smem (p, NT);
+   cudaError_t	e    = cudaFuncSetAttribute (fiasco_tile_kernel<NT>,
+					     cudaFuncAttributeMaxDynamicSharedMemorySize,
+					     (int) smem);
+   if (e != cudaSuccess)
+      return e;
+   fiasco_tile_kernel<NT><<<n_tiles, NT, smem, stream>>> (p, d_ws);
+   return cudaGetLastError ();
+}
+
+cudaError_t
+fb_launch_tile_kernel (const DevParams &p, const TileWs *d_ws, int n_tiles,
+		       cudaStream_t stream)
+{
+   cudaError_t e = upload_tables ();
+   if (e != cudaSuccess)
+      return e;
+   switch (fb_tile_kernel_threads (p))
+   {
+      case 128: return launch_nt<128> (p, d_ws, n_tiles, stream);
+      case 256: return launch_nt<256> (p, d_ws, n_tiles, stream);
+      default:	return launch_nt<512> (p, d_ws, n_tiles, stream);
+   }
+}
+
+cudaError_t
+fb_launch_probe (int kind, int n, const float *f, const int *a, const int *b,
+		 const int *c, int *out_i, float *out_f)
+{
+   fiasco_probe_kernel<<<(n + 255) / 256, 256>>> (kind, n, f, a, b, c, out_i, out_f);
+   return cudaGetLastError ();
+}

@@ -1,0 +1,97 @@
+/*
+ *  tile_kernel.cuh -- shared declarations of the persistent tile kernel and its host
+ *  launcher (internal; the public boundary is include/fiasco_b200.h).
+ */
+#ifndef FB200_TILE_KERNEL_CUH
+#define FB200_TILE_KERNEL_CUH
+
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include "fiasco_b200.h"
+
+#define FB_MAXEDGES  5
+#define FB_NO_EDGE   (-1)
+#define FB_RANGE     (-1)
+#define FB_MAXCOSTS  1e20f		/* codec/coder.c:53 */
+#define FB_MAXDEPTH  (FB200_MAXLEVEL + 2)
+#define FB_IMG_STRIDE 64		/* floats per state image row (63 used, il <= 5) */
+
+/* layout of the probability-model blob (int16 units) */
+#define MB_COUNT      0			/* rle count[6]	  (domain-pool.c:623) */
+#define MB_TOTAL      6			/* rle total (u16) */
+#define MB_N	      7			/* rle n (u16) */
+#define MB_MAXDOM     8			/* rle max_domains (u16) */
+#define MB_YINDEX     9			/* rle y_index (u16) */
+#define MB_D0N	      10		/* DC qac model: n */
+#define MB_D0INDEX    11		/* DC qac model: index[0] */
+#define MB_D0YINDEX   12		/* DC qac model: y_index (u16) */
+#define MB_TOTALS     16		/* aac totals[1 + levels] */
+#define MB_TOTALS_MAX 24
+#define MB_COUNTS     (MB_TOTALS + MB_TOTALS_MAX + 1) /* aac counts, 1 pad slot before */
+
+struct DevParams
+{
+   int	 width, height, level, bands;
+   int	 lc_min, lc_max, il;	/* range levels, images level */
+   int	 lmin;			/* lowest level with tables = min (lc_min, il) */
+   int	 nlev;			/* lc_max - lmin + 1 */
+   int	 tn;			/* nodes of the per-block product tree: 2^nlev - 1 */
+   int	 max_elements, max_domains, chroma_max_states;
+   float price, chroma_decrease;
+   int	 rpf_m, dc_m;
+   float rpf_range, dc_range;
+   int	 second_domain_block;
+   int	 s_cap;			/* state capacity */
+   int	 coeff_min_level;	/* context base of the aac model (coder.c:731) */
+   int	 aac_dc_size, aac_lvl_size, blob_len;
+   int	 trace_cap;
+   int	 first_band, last_band; /* bands processed by this launch */
+};
+
+/* per-tile device workspace (all pointers device memory) */
+struct TileWs
+{
+   const int16_t *pix;		/* [bands][width*height] */
+   float   *img;		/* [s_cap][64]		  state images, levels 0..il */
+   float   *T;			/* [tn][s_cap]		  range x state products */
+   float   *SS;			/* [nlev][s_cap][s_cap]	  state x state products */
+   float   *diag;		/* [nlev][s_cap]	  <s,s> */
+   /* automaton */
+   float   *final_d;		/* [s_cap] */
+   uint8_t *level_of_state;	/* [s_cap] */
+   uint8_t *domain_type;	/* [s_cap] */
+   int16_t *tree;		/* [s_cap][2] */
+   uint16_t *x, *y;		/* [s_cap][2] */
+   int16_t *into;		/* [s_cap][2][6] */
+   float   *weight;		/* [s_cap][2][6] */
+   int16_t *y_state;		/* [s_cap][2] */
+   uint8_t *y_column;		/* [s_cap][2] */
+   /* model snapshots of the DFS */
+   int16_t *snap;		/* [FB_MAXDEPTH][2][blob_len] */
+   unsigned *treesnap;		/* [FB_MAXDEPTH][2 * MAXLEVEL] */
+   /* persistent coder state between band launches */
+   int16_t *blob_save;		/* [blob_len] */
+   unsigned *tree_save;		/* [2 * MAXLEVEL] */
+   int16_t *pool_save;		/* [s_cap] */
+   struct TileResult *result;
+   fb200_trace_rec_t *trace;	/* [trace_cap] or NULL */
+};
+
+struct TileResult
+{
+   int	    status;
+   unsigned states, basis_states, root_state;
+   float    costs [3], err [3], tree_bits [3], matrix_bits [3], weights_bits [3];
+   int	    band_root [3];
+   int	    trace_len;
+   unsigned long long mp_calls, mp_steps, pass2, blocks, ip_bytes;
+};
+
+size_t fb_tile_kernel_smem (const DevParams &p, int nt);
+int    fb_tile_kernel_threads (const DevParams &p);
+cudaError_t fb_launch_tile_kernel (const DevParams &p, const TileWs *d_ws, int n_tiles,
+				   cudaStream_t stream);
+cudaError_t fb_launch_probe (int kind, int n, const float *f, const int *a, const int *b,
+			     const int *c, int *out_i, float *out_f);
+
+#endif

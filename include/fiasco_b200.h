@@ -1,0 +1,190 @@
+/*
+ *  fiasco_b200.h -- C ABI of the B200-native FIASCO encoder hot path.
+ *
+ *  This is the drop-in boundary below the public libfiasco API: one call encodes the
+ *  bintree subdivision of whole frames / independent tiles on the GPU.  It replaces, in
+ *  the reference coder, the call
+ *
+ *      costs = subdivide (MAXCOSTS, GRAY, RANGE, &range, wfa, c, ..., NO);
+ *                                              /root/reference/codec/coder.c:743 (grey)
+ *                                              /root/reference/codec/coder.c:805 (per band)
+ *
+ *  together with everything that call reaches: codec/subdivide.c:60 (subdivide),
+ *  codec/approx.c:74,317,644 (approximate_range, matching_pursuit, orthogonalize),
+ *  codec/ip.c:72,184 (compute_ip_images_state, compute_ip_states_state),
+ *  codec/domain-pool.c:707-852 (rle pool: generate/bits/update/append),
+ *  codec/coeff.c:215-267 (adaptive coefficient model), codec/control.c:48 (append_state),
+ *  codec/bintree.c:35,55 (tree model), lib/rpf.c:59,113 (rtob/btor).
+ *
+ *  Plain C types only: pointers and sizes, no CUDA or torch types in any signature
+ *  (a cudaStream_t travels as void *).  All functions return 0 on success and a
+ *  non-zero FB200_E* code on failure, with a message in the caller's err buffer --
+ *  the host library maps that to libfiasco's "return 0 + fiasco_get_error_message()"
+ *  convention (/root/reference/lib/error.c:113,178).
+ *
+ *  There is NO CPU fallback: if no CUDA device / driver is present every entry point
+ *  that needs one fails with FB200_ENODEVICE.
+ */
+#ifndef FIASCO_B200_H
+#define FIASCO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FB200_MAXEDGES	5	/* codec/wfa.h:20 */
+#define FB200_MAXSTATES 6000	/* codec/wfa.h:21 */
+#define FB200_MAXLABELS 2	/* codec/wfa.h:22 */
+#define FB200_MAXLEVEL	22	/* codec/wfa.h:23 */
+
+enum
+{
+   FB200_OK	     = 0,
+   FB200_EINVAL	     = 1,	/* bad parameter */
+   FB200_ENODEVICE   = 2,	/* no usable CUDA device */
+   FB200_ECUDA	     = 3,	/* CUDA runtime error (message has the details) */
+   FB200_ECAPACITY   = 4,	/* a tile needed more states than 'state_capacity' */
+   FB200_EMAXSTATES  = 5,	/* "Maximum number of states reached!" (control.c:129) */
+   FB200_ENOROOT     = 6,	/* "No root state generated!" (coder.c:751) */
+   FB200_EUNSUPPORTED = 7	/* option outside the supported set (see below) */
+};
+
+/*
+ *  Coder parameters of one job; every tile of a job shares them.  The values are the
+ *  ones found in the reference's coding_t / c_options_t AFTER alloc_coder()'s clamping
+ *  (codec/coder.c:249-327); fb200_params_init() performs exactly that clamping from
+ *  user-level options.
+ */
+typedef struct fb200_params
+{
+   int	 width, height;		/* tile geometry in pixels (even numbers) */
+   int	 bands;			/* 1 = grey; 3 = Y,Cb,Cr 4:4:4 (lib/image.c:348) */
+   int	 level;			/* bintree level of the tile (coder.c:249-256) */
+   int	 lc_min_level;		/* smallest range level (c->options.lc_min_level) */
+   int	 lc_max_level;		/* largest range level */
+   int	 images_level;		/* state images kept up to this level (5) */
+   int	 max_elements;		/* edges per linear combination, 1..5 */
+   int	 max_states;		/* dictionary size (wfainfo->max_states) */
+   int	 chroma_max_states;	/* chroma dictionary size (40) */
+   float price;			/* 128 * 64 / quality (coder.c:164) */
+   float chroma_decrease;	/* price multiplier for Cb/Cr (subdivide.c:166) */
+   int	 rpf_mantissa;		/* lib/rpf.c: bits of the weight quantiser */
+   float rpf_range;
+   int	 dc_rpf_mantissa;
+   float dc_rpf_range;
+   int	 second_domain_block;	/* approx.c:103 (CLI -z 2) */
+   int	 state_capacity;	/* workspace states per tile; 0 = pick from geometry */
+} fb200_params_t;
+
+/*
+ *  Finished automaton of one tile, caller-allocated arrays of 'capacity' states
+ *  (same meaning and element types as wfa_t, codec/wfa.h:112-138).  fb200_wfa_alloc()
+ *  / fb200_wfa_free() are conveniences for C callers; foreign callers may fill the
+ *  pointers themselves.
+ */
+typedef struct fb200_wfa
+{
+   int	     capacity;		/* in: states the arrays can hold */
+   int	     status;		/* out: FB200_OK or the tile's own error */
+   unsigned  states;		/* out */
+   unsigned  basis_states;	/* out (3: the built-in "small.fco", input/basis.c:126) */
+   unsigned  root_state;	/* out */
+   float     costs [3];		/* out: subdivide() return value per band */
+   float     err [3];		/* out: root range err / bits per band */
+   float     tree_bits [3];
+   float     matrix_bits [3];
+   float     weights_bits [3];
+   float    *final_distribution;	     /* [capacity] */
+   uint8_t  *level_of_state;		     /* [capacity] */
+   uint8_t  *domain_type;		     /* [capacity] */
+   int16_t  *tree;			     /* [capacity][2] */
+   uint16_t *x, *y;			     /* [capacity][2] */
+   int16_t  *into;			     /* [capacity][2][6], -1 terminated */
+   float    *weight;			     /* [capacity][2][6] */
+   int16_t  *y_state;			     /* [capacity][2] */
+   uint8_t  *y_column;			     /* [capacity][2] */
+} fb200_wfa_t;
+
+/* one record per approximate_range() call (debug / parity tracing, optional) */
+typedef struct fb200_trace_rec
+{
+   uint16_t level, image, address, x, y;
+   int16_t  y_state;
+   uint16_t states;
+   int16_t  n_edges;		/* -1: costs >= max_costs (no approximation kept) */
+   float    max_costs, price, costs, err, matrix_bits, weights_bits;
+   int16_t  into [6];
+   float    weight [6];
+} fb200_trace_rec_t;
+
+typedef struct fb200_ctx fb200_ctx_t;	/* opaque: device workspace for up to N tiles */
+
+/* work / timing counters of the last launch */
+typedef struct fb200_stats
+{
+   float    kernel_ms;		/* CUDA-event time of the tile kernel(s) */
+   float    h2d_ms, d2h_ms;
+   uint64_t h2d_bytes, d2h_bytes;
+   uint64_t ip_bytes;		/* algorithmic bytes of the range x state products */
+   uint64_t mp_calls, mp_steps, pass2, blocks, states;
+   int	    kernel_launches;
+} fb200_stats_t;
+
+/* Fill 'p' from user-level options the way alloc_coder() does (coder.c:249-327).
+   optimize follows the CLI: 0 => levels [6,10], 3 edges; 1 => [4,12], 5 edges;
+   2 => 1 + second_domain_block; >= 3 => FB200_EUNSUPPORTED (full_search has
+   undefined behaviour in the reference). */
+int fb200_params_init (fb200_params_t *p, int width, int height, int bands,
+		       float quality, int optimize, char *err, size_t errlen);
+
+/* number of usable CUDA devices (0 if none / no driver) */
+int fb200_device_count (void);
+
+/* Create / destroy a device workspace for up to max_tiles tiles of geometry 'p' on
+   CUDA device 'device'. */
+int  fb200_create (fb200_ctx_t **ctx, const fb200_params_t *p, int max_tiles,
+		   int device, char *err, size_t errlen);
+void fb200_destroy (fb200_ctx_t *ctx);
+
+/* Host-buffer path (what libfiasco's fiasco_coder() uses): planes[t * bands + b] is the
+   b-th band of tile t in the reference's internal pixel format (int16 12.4 fixed
+   point, lib/image.c:362,383-385), width*height each.  Copies in, runs, copies the
+   automata out.  trace / trace_cap may be NULL / 0. */
+int fb200_encode_tiles (fb200_ctx_t *ctx, int n_tiles,
+			const int16_t *const *planes, fb200_wfa_t *out,
+			fb200_trace_rec_t *trace, int trace_cap, int *trace_len,
+			char *err, size_t errlen);
+
+/* Device-resident path (benchmarks, callers that already hold frames in HBM):
+   upload once, launch any number of times on a caller stream, download when needed. */
+int fb200_upload (fb200_ctx_t *ctx, int n_tiles, const int16_t *const *planes,
+		  char *err, size_t errlen);
+int fb200_launch (fb200_ctx_t *ctx, int n_tiles, void *cuda_stream,
+		  char *err, size_t errlen);
+int fb200_download (fb200_ctx_t *ctx, int n_tiles, fb200_wfa_t *out,
+		    fb200_trace_rec_t *trace, int trace_cap, int *trace_len,
+		    char *err, size_t errlen);
+int fb200_sync (fb200_ctx_t *ctx, char *err, size_t errlen);
+void fb200_get_stats (const fb200_ctx_t *ctx, fb200_stats_t *stats);
+
+/* helpers for C callers */
+int  fb200_wfa_alloc (fb200_wfa_t *wfa, int capacity);
+void fb200_wfa_free (fb200_wfa_t *wfa);
+
+/* pure-function probes (known-answer tests of the device arithmetic): evaluate n values
+   on the GPU.  kind: 0 rtob(f[i]; mantissa a[i], range_e b[i]) -> out_i
+		      1 btor(a[i]; mantissa b[i], range_e c[i]) -> out_f
+		      2 bits_bin_code(a[i], b[i]) -> out_i
+		      3 -log2(a[i] / (float) b[i]) as fp32 -> out_f  (tree/aac/rle rate terms) */
+int fb200_probe (int kind, int n, const float *f, const int *a, const int *b,
+		 const int *c, int *out_i, float *out_f, char *err, size_t errlen);
+
+const char *fb200_version (void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FIASCO_B200_H */
