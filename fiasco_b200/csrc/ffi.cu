@@ -524,6 +524,8 @@ fb200_download (fb200_ctx_t *c, int n_tiles, fb200_wfa_t *out, fb200_trace_rec_t
    int rc = FB200_OK;
    c->stats.ip_bytes = c->stats.mp_calls = c->stats.mp_steps = c->stats.pass2 = 0;
    c->stats.blocks = c->stats.states = 0;
+   c->stats.mp_bytes = c->stats.ss_bytes = 0;
+   c->stats.cyc_total = c->stats.cyc_T = c->stats.cyc_mp = c->stats.cyc_append = 0;
    for (int t = 0; t < n_tiles; t++)
    {
       const TileResult	  &r  = c->h_results [t];
@@ -548,6 +550,12 @@ fb200_download (fb200_ctx_t *c, int n_tiles, fb200_wfa_t *out, fb200_trace_rec_t
       c->stats.pass2	+= r.pass2;
       c->stats.blocks	+= r.blocks;
       c->stats.states	+= r.states;
+      c->stats.mp_bytes += r.mp_bytes;
+      c->stats.ss_bytes += r.ss_bytes;
+      c->stats.cyc_total  += r.cyc_total;
+      c->stats.cyc_T	  += r.cyc_T;
+      c->stats.cyc_mp	  += r.cyc_mp;
+      c->stats.cyc_append += r.cyc_append;
       if (r.status != FB200_OK)
       {
 	 if (rc == FB200_OK)

@@ -43,7 +43,8 @@ __device__ __forceinline__ float neg_log2f_via_double (float x)
    return (float) (-log2 ((double) x));
 }
 
-/* lib/rpf.c:59-111 (rtob); shifts follow x86 semantics (count mod 32), see oracle */
+/* lib/rpf.c:59-111 (rtob); the reference shifts by more than 31 bits for tiny/huge
+   inputs; on x86-64 that is a shift by (count mod 32), reproduced here explicitly */
 __device__ __forceinline__ int dev_rtob (float f, int mantissa_bits, float range)
 {
    f = f / range;
@@ -175,7 +176,8 @@ struct ShHdr
    unsigned tree_counts [FB200_MAXLEVEL];
    unsigned tree_total [FB200_MAXLEVEL];
    int	    trace_len;
-   unsigned long long mp_calls, mp_steps, pass2, blocks, ip_bytes;
+   unsigned long long mp_calls, mp_steps, pass2, blocks, ip_bytes, mp_bytes, ss_bytes;
+   long long cyc_T, cyc_mp, cyc_append, cyc_start;
    MpRes    mp, tmp;
    MpWork   w;
    RangeRes root;
@@ -723,6 +725,8 @@ cta_append_state (const DevParams &P, const TileWs &W, const Sh &sh, int auxilia
    }
    if (threadIdx.x == 0)
    {
+      if (!auxiliary)
+	 sh.h->ss_bytes += 4ull * (unsigned) P.nlev * (s + 1);
       sh.h->states = s + 1;
       if (s + 1 >= FB200_MAXSTATES)
 	 sh.h->status = FB200_EMAXSTATES;
@@ -921,6 +925,7 @@ cta_matching_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &
       w.d0b [0] = t0_d0_bits (sh, 0, y_state, c_matrix_0, c_matrix_1);
       w.d0b [1] = t0_d0_bits (sh, 1, y_state, c_matrix_0, c_matrix_1);
       sh.h->mp_calls++;
+      sh.h->mp_bytes += 8ull * (unsigned) w.D;
    }
    /* log2 tables of the models (the models do not change during one pursuit) */
    {
@@ -1219,6 +1224,7 @@ cta_matching_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &
 	 w.B [n] = sh.num [index];
 	 w.N [n] = sh.den [index];
 	 sh.h->mp_steps++;
+	 sh.h->mp_bytes += 4ull * (unsigned) w.D;
 	 if (n + 1 < P.max_elements)
 	    t0_mp_prepare_step (P, sh, mp, n + 1);
       }
@@ -1541,7 +1547,10 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 	       if (tid == 0)
 		  F.address = F.image = 0;
 	       __syncthreads ();
+	       const long long t0c = clock64 ();
 	       cta_init_range<NT> (P, W, sh, F.x, F.y, band);
+	       if (tid == 0)
+		  h->cyc_T += clock64 () - t0c;
 	    }
 	    /* snapshot of the models (subdivide.c:188-194) */
 	    {
@@ -1579,10 +1588,14 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 		  F.lrange.into [0]	= FB_NO_EDGE;
 	       }
 	       __syncthreads ();
+	       const long long t0c = clock64 ();
 	       cta_approximate_range<NT> (P, W, sh, F.max_costs, h->price, F.y_state,
 					  &F.lrange, level, F.image, F.address, F.x, F.y);
 	       if (tid == 0)
+	       {
 		  F.lincomb_costs = h->ret_costs;
+		  h->cyc_mp += clock64 () - t0c;
+	       }
 	    }
 	    else if (tid == 0)
 	       F.lincomb_costs = FB_MAXCOSTS;
@@ -1637,7 +1650,12 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 
 	    /* products of the states born in child 0 (subdivide.c:295-297) */
 	    if (label && level <= P.lc_max)
+	    {
+	       const long long t0c = clock64 ();
 	       cta_compute_T<NT> (P, W, sh, F.states_snap, cimg, level - 1);
+	       if (tid == 0)
+		  h->cyc_T += clock64 () - t0c;
+	    }
 	    if (tid == 0)
 	    {
 	       const float remaining = fmin2 (F.lincomb_costs, F.max_costs) - F.subdivide_costs;
@@ -1784,7 +1802,10 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 		  next		    = ST_RETURN;
 	       }
 	       __syncthreads ();
+	       const long long t0c = clock64 ();
 	       cta_append_state<NT> (P, W, sh, aux, F.level);
+	       if (tid == 0)
+		  h->cyc_append += clock64 () - t0c;
 	    }
 	    break;
 	 }
@@ -1831,6 +1852,9 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
       h->status	   = FB200_OK;
       h->trace_len = 0;
       h->mp_calls = h->mp_steps = h->pass2 = h->blocks = h->ip_bytes = 0;
+      h->mp_bytes = h->ss_bytes = 0;
+      h->cyc_T = h->cyc_mp = h->cyc_append = 0;
+      h->cyc_start = clock64 ();
       h->states	   = 0;
    }
    __syncthreads ();
@@ -1904,6 +1928,12 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
       r->pass2	   = h->pass2;
       r->blocks	   = h->blocks;
       r->ip_bytes  = h->ip_bytes;
+      r->mp_bytes  = h->mp_bytes;
+      r->ss_bytes  = h->ss_bytes;
+      r->cyc_total  = (unsigned long long) (clock64 () - h->cyc_start);
+      r->cyc_T	    = (unsigned long long) h->cyc_T;
+      r->cyc_mp	    = (unsigned long long) h->cyc_mp;
+      r->cyc_append = (unsigned long long) h->cyc_append;
    }
 }
 

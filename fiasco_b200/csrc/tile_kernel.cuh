@@ -85,6 +85,8 @@ struct TileResult
    int	    band_root [3];
    int	    trace_len;
    unsigned long long mp_calls, mp_steps, pass2, blocks, ip_bytes;
+   unsigned long long mp_bytes, ss_bytes;	/* algorithmic bytes of the other phases */
+   unsigned long long cyc_total, cyc_T, cyc_mp, cyc_append; /* SM cycles per phase */
 };
 
 size_t fb_tile_kernel_smem (const DevParams &p, int nt);

@@ -57,7 +57,9 @@ class Stats(C.Structure):
         ("kernel_ms", C.c_float), ("h2d_ms", C.c_float), ("d2h_ms", C.c_float),
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("ip_bytes", C.c_uint64),
         ("mp_calls", C.c_uint64), ("mp_steps", C.c_uint64), ("pass2", C.c_uint64),
-        ("blocks", C.c_uint64), ("states", C.c_uint64), ("kernel_launches", C.c_int),
+        ("blocks", C.c_uint64), ("states", C.c_uint64), ("mp_bytes", C.c_uint64), ("ss_bytes", C.c_uint64),
+        ("cyc_total", C.c_uint64), ("cyc_T", C.c_uint64), ("cyc_mp", C.c_uint64), ("cyc_append", C.c_uint64),
+        ("kernel_launches", C.c_int),
     ]
 
 
@@ -249,7 +251,7 @@ def probe(kind, f=None, a=None, b=None, c=None):
 
 
 def wfa_lines(w, image_level=None):
-    """Canonical 's' / 'e' lines of oracle/wfadump.c for one automaton (dict from TileEncoder)."""
+    """Canonical text form of one automaton (dict from TileEncoder): "s" state lines, "e" edge lines."""
     out = []
     fb = w["weight"].view(np.uint32)
     for s in range(w["basis_states"], w["states"]):

@@ -130,6 +130,9 @@ typedef struct fb200_stats
    uint64_t h2d_bytes, d2h_bytes;
    uint64_t ip_bytes;		/* algorithmic bytes of the range x state products */
    uint64_t mp_calls, mp_steps, pass2, blocks, states;
+   uint64_t mp_bytes;		/* algorithmic bytes of the pursuits: 8 D per call + 4 D per step */
+   uint64_t ss_bytes;		/* algorithmic bytes of the state x state rows */
+   uint64_t cyc_total, cyc_T, cyc_mp, cyc_append; /* SM cycles per phase, summed over tiles */
    int	    kernel_launches;
 } fb200_stats_t;
 

@@ -172,6 +172,14 @@ fo_bits_bin_code (unsigned value, unsigned maxval)
    return bits_bin_code (value, maxval);
 }
 
+/* the form every rate term takes in the reference (bintree.c:64-67, coeff.c:231-236,
+   domain-pool.c:774): -log2 (count / (real_t) total), double log2, narrowed to fp32 */
+float
+fo_neg_log2f (int count, int total)
+{
+   return (float) -log2 ((double) (count / (float) total));
+}
+
 /*****************************************************************************
 			   tree model  (codec/bintree.c)
 *****************************************************************************/

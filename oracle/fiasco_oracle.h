@@ -103,6 +103,7 @@ void fo_rgb_to_planes (const uint8_t *rgb, size_t n, int16_t *y, int16_t *cb,
 int	 fo_rtob (float f, unsigned mantissa_bits, int range_e);  /* lib/rpf.c:59 */
 float	 fo_btor (int b, unsigned mantissa_bits, int range_e);	  /* lib/rpf.c:113 */
 unsigned fo_bits_bin_code (unsigned value, unsigned maxval);	  /* lib/misc.c:296 */
+float	 fo_neg_log2f (int count, int total);	/* -log2 (count / (real_t) total) */
 void	 fo_tree_model_kat (unsigned level, unsigned *counts, unsigned *total,
 			    float *child_bits, float *leaf_bits); /* bintree.c:55,70 */
 unsigned fo_image_level (unsigned width, unsigned height);	  /* coder.c:249-256 */

@@ -78,6 +78,8 @@ def lib():
         L.fo_btor.restype = C.c_float
         L.fo_bits_bin_code.argtypes = [C.c_uint, C.c_uint]
         L.fo_bits_bin_code.restype = C.c_uint
+        L.fo_neg_log2f.argtypes = [C.c_int, C.c_int]
+        L.fo_neg_log2f.restype = C.c_float
         L.fo_image_level.argtypes = [C.c_uint, C.c_uint]
         L.fo_image_level.restype = C.c_uint
         L.fo_tree_model_kat.argtypes = [C.c_uint, C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(C.c_float),

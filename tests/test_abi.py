@@ -1,0 +1,95 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/fiasco_b200.h declares, clamps parameters like the reference's alloc_coder(), and fails
+loudly (no CPU fallback) when there is no CUDA device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import fiasco_b200 as F
+from fiasco_b200 import ffi
+import oracle_lib as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols(header):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(fb200_[a-z0-9_]+|fiasco_[a-z0-9_]+|open_file)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = F.load()
+    syms = declared_symbols("fiasco_b200.h")
+    assert len(syms) >= 14, syms
+    for s in syms:
+        assert hasattr(lib, s), "missing export " + s
+    assert b"sm_100a" in lib.fb200_version()
+
+
+def test_sass_is_sm100a():
+    """The shipped library must carry sm_100a code (not PTX for another arch)."""
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", F.lib_path()], capture_output=True, text=True).stdout
+    assert "sm_100a" in out, out
+
+
+@pytest.mark.parametrize("w,h", [(256, 256), (512, 512), (1024, 1024), (64, 64), (200, 136), (720, 576), (32, 32),
+                                 (2048, 2048), (96, 64)])
+@pytest.mark.parametrize("z", [0, 1, 2])
+def test_params_clamping_matches_alloc_coder(w, h, z):
+    """fb200_params_init follows codec/coder.c:249-296 (checked against the oracle's restatement,
+    which is pinned to the reference)."""
+    p = ffi.make_params(w, h, 1, 20.0, z)
+    L = O.lib()
+    level = L.fo_image_level(w, h)
+    assert p.level == level
+    lc_min, lc_max, edges = ((6, 10, 3) if z == 0 else (4, 12, 5))
+    exp_max = min(lc_max, level - 1)
+    exp_min = min(max(lc_min, 3), exp_max)
+    assert (p.lc_min_level, p.lc_max_level) == (exp_min, exp_max)
+    assert p.images_level == min(5, exp_max - 1)
+    assert p.max_elements == edges
+    assert p.second_domain_block == (1 if z == 2 else 0)
+    import numpy as np
+    assert np.float32(p.price) == np.float32(128 * 64) / np.float32(20.0)
+
+
+def test_params_errors():
+    with pytest.raises(F.FB200Error) as e:
+        ffi.make_params(255, 256)
+    assert "even" in str(e.value)
+    with pytest.raises(F.FB200Error) as e:
+        ffi.make_params(256, 256, 1, 0.0)
+    assert "positive" in str(e.value)
+    with pytest.raises(F.FB200Error) as e:
+        ffi.make_params(256, 256, 1, 20.0, 3)
+    assert e.value.code == ffi.EUNSUPPORTED
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the compute entry points must refuse, not silently compute."""
+    if F.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    p = ffi.make_params(64, 64)
+    with pytest.raises(F.FB200Error) as e:
+        F.TileEncoder(p, 1)
+    assert e.value.code == ffi.ENODEVICE
+    with pytest.raises(F.FB200Error) as e:
+        F.probe(2, a=[1, 2], b=[3, 4])
+    assert e.value.code == ffi.ENODEVICE
+
+
+def test_product_does_not_reference_oracle():
+    """Nothing under fiasco_b200/ or include/ may include, link or import the oracle."""
+    bad = []
+    for base in ("fiasco_b200", "include"):
+        for dp, _, fs in os.walk(os.path.join(ROOT, base)):
+            for f in fs:
+                if f.endswith((".c", ".h", ".cu", ".cuh", ".py", ".mk")) or f == "Makefile":
+                    txt = open(os.path.join(dp, f), errors="replace").read()
+                    if re.search(r"fiasco_oracle|oracle_lib|liboracle|oracle/", txt):
+                        bad.append(os.path.join(dp, f))
+    assert not bad, bad
