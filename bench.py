@@ -183,7 +183,12 @@ def run_ours(args):
 
     p = ffi.make_params(W_, H_, 1, QUALITY, 0)
     enc = F.TileEncoder(p, B, device=local)
-    stream = torch.cuda.current_stream().cuda_stream
+    # a dedicated (non-default) torch stream: the kernel, the L2 flush and the timing events all go
+    # through it, so torch.cuda.Event brackets exactly our launches
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     def barrier():
         torch.cuda.synchronize()

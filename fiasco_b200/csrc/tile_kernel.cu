@@ -160,6 +160,7 @@ struct MpWork
    int	  n;			/* current step */
    int	  D, pool_n, ydom, y_state, level, li, size;
    int	  index;		/* winner of the current step or -1 */
+   int	  wave_pos, wave_done;	/* lazy pass-2 waves: next start index, finished flag */
    float  best_f [FB_MAXEDGES];
    float  best_mbits, best_wbits, best_err, best_costs;
 };
@@ -192,8 +193,9 @@ struct Sh			/* pointers into dynamic shared memory */
    short   *pool;		/* [s_cap] domain index -> state */
    float   *pixels;		/* [2^lc_max] */
    int	   *norm_i;		/* [tn] integer sum of squares per node */
-   float   *slot;		/* [10][NT] pass-2 results of the current chunk */
-   float   *wmin;		/* [32] per-warp minimum key */
+   float   *bnd;		/* [dcap32] pass-1 bound per domain (INF: not usable) */
+   unsigned *cmask;		/* [dcap32 / 32] candidate bit masks of the current wave */
+   int	   *cand;		/* [32] candidates of the current wave, index order */
    short   *blob;		/* [blob_len] current probability models */
    int	    dcap;
 };
@@ -214,8 +216,8 @@ smem_layout (const DevParams &p, int nt, size_t *off /* [11] */)
    off [5] = o; o += align16 ((size_t) p.s_cap * 2);		/* pool */
    off [6] = o; o += align16 (((size_t) 1 << p.lc_max) * 4);	/* pixels */
    off [7] = o; o += align16 ((size_t) p.tn * 4);		/* norm_i */
-   off [8] = o; o += align16 ((size_t) nt * 4 * 10);		/* slot */
-   off [9] = o; o += align16 (32 * 4);				/* wmin */
+   off [8] = o; o += align16 (((dcap + 31) / 32 * 32) * 4);	/* bnd */
+   off [9] = o; o += align16 (((dcap + 31) / 32) * 4 + 32 * 4);	/* cmask, cand */
    off [10] = o; o += align16 ((size_t) p.blob_len * 2);	/* blob */
    return o;
 }
@@ -235,8 +237,9 @@ carve (unsigned char *base, const DevParams &p, int nt)
    s.pool   = (short *) (base + off [5]);
    s.pixels = (float *) (base + off [6]);
    s.norm_i = (int *) (base + off [7]);
-   s.slot   = (float *) (base + off [8]);
-   s.wmin   = (float *) (base + off [9]);
+   s.bnd    = (float *) (base + off [8]);
+   s.cmask  = (unsigned *) (base + off [9]);
+   s.cand   = (int *) (s.cmask + ((size_t) p.s_cap + 1 + 31) / 32);
    s.blob   = (short *) (base + off [10]);
    s.dcap   = p.s_cap + 1;
    return s;
@@ -288,8 +291,10 @@ __device__ float t0_d0_bits (const Sh &sh, int dc_used, int y_state,
 
 /*
  *  rle_bits (domain-pool.c:737-793) for a used-domain list that is already sorted and
- *  already stripped of the y-state domain.  mbase / d0b are per-call tables.
+ *  already stripped of the y-state domain.  mbase / d0b are per-call tables.  M bounds
+ *  the list length at compile time.
  */
+template <int M>
 __device__ __forceinline__ float
 dev_rle_bits (const float *mbase, const float *d0b, const short *sorted, int n,
 	      unsigned pool_n)
@@ -299,7 +304,7 @@ dev_rle_bits (const float *mbase, const float *d0b, const short *sorted, int n,
 
    bits += (n && sorted [0] == 0) ? d0b [1] : d0b [0];
 #pragma unroll
-   for (int e = 0; e < FB_MAXEDGES + 1; e++)
+   for (int e = 0; e < M; e++)
       if (e < n)
       {
 	 int into = sorted [e];
@@ -311,6 +316,27 @@ dev_rle_bits (const float *mbase, const float *d0b, const short *sorted, int n,
 	 }
       }
    return bits;
+}
+
+/* insert d into the ascending list srt[0..ns) of capacity M */
+template <int M>
+__device__ __forceinline__ void
+sorted_insert (short (&srt) [M], int &ns, int d)
+{
+   int p = ns;
+
+#pragma unroll
+   for (int e = M - 1; e > 0; e--)
+      if (e <= p && srt [e - 1] > d)
+      {
+	 srt [e] = srt [e - 1];
+	 p	 = e - 1;
+      }
+#pragma unroll
+   for (int e = 0; e < M; e++)
+      if (e == p)
+	 srt [e] = (short) d;
+   ns++;
 }
 
 __constant__ float c_matrix_0 [1024];	/* domain-pool.c:970-999 */
@@ -873,6 +899,245 @@ t0_mp_prepare_step (const DevParams &P, const Sh &sh, MpRes &mp, int n)
 }
 
 /*
+ *  Pass 1 for domain d at step N (approx.c:433-462): rate of "chosen vectors + d with a
+ *  dummy weight 0.5", turned into the optimistic cost bound.
+ */
+template <int N>
+__device__ __forceinline__ float
+mp_pass1 (const MpWork &w, int d, int st, float num, float den, float price, float err)
+{
+   short srt [N + 1];
+   int	 ns = w.ncs;
+
+#pragma unroll
+   for (int e = 0; e < N + 1; e++)
+      srt [e] = (e < N && e < ns) ? w.csorted [e] : (short) 0x7fff;
+   if (d != w.ydom)
+      sorted_insert<N + 1> (srt, ns, d);
+   const float mb = dev_rle_bits<N + 1> (w.mbase, w.d0b, srt, ns, (unsigned) w.pool_n);
+   const float wb = st ? w.wb_nd : w.wb_dc;
+
+   return ((mb + wb + w.additional_bits) * price + err) - (num * num) / den;
+}
+
+/*
+ *  Pass 2 for domain d at step N (approx.c:463-602): quantised weights by back
+ *  substitution, true rate, true error.  Returns the costs; weights / bits / err in out[].
+ *  out: [0..4] weights, [5] matrix bits, [6] weights bits, [7] err.
+ */
+template <int N>
+__device__ __forceinline__ float
+mp_pass2 (const DevParams &P, const Sh &sh, const MpWork &w, const MpRes &mp, int d,
+	  float num, float den, float price, float *out)
+{
+   const int dcap = sh.dcap;
+   float     f [N + 1], r [N + 1];
+   int	     v [N + 1];
+
+#pragma unroll
+   for (int k = 0; k < N; k++)
+   {
+      f [k] = w.fB [k];
+      v [k] = mp.indices [k];
+   }
+   f [N] = num / den;
+   v [N] = d;
+#pragma unroll
+   for (int l = N; l >= 0; l--)
+   {
+      const int	  stl = dom_state (sh, w, v [l]);
+      const float q   = stl ? dev_btor (dev_rtob (f [l], P.rpf_m, P.rpf_range), P.rpf_m,
+					P.rpf_range)
+			    : dev_btor (dev_rtob (f [l], P.dc_m, P.dc_range), P.dc_m,
+					P.dc_range);
+      f [l] = q;
+      r [l] = q;
+#pragma unroll
+      for (int k = 0; k < l; k++)
+	 f [k] -= q * sh.G [k * dcap + v [l]] / w.N [k];
+   }
+   /* rate of the quantised combination */
+   float w_bits = 0, m_bits;
+   {
+      short srt [N + 1];
+      int   cnt = 0;
+
+#pragma unroll
+      for (int e = 0; e < N + 1; e++)
+	 srt [e] = (short) 0x7fff;
+#pragma unroll
+      for (int k = 0; k <= N; k++)
+	 if (f [k] != 0)
+	 {
+	    const int stk = dom_state (sh, w, v [k]);
+
+	    if (stk)
+	       w_bits = (float) ((double) w_bits
+				 - w.l2_lv [dev_rtob (f [k], P.rpf_m, P.rpf_range)]);
+	    else
+	       w_bits = (float) ((double) w_bits
+				 - w.l2_dc [dev_rtob (f [k], P.dc_m, P.dc_range)]);
+	    if (v [k] != w.ydom)
+	       sorted_insert<N + 1> (srt, cnt, v [k]);
+	 }
+      m_bits = dev_rle_bits<N + 1> (w.mbase, w.d0b, srt, cnt, (unsigned) w.pool_n);
+   }
+   /* back to the orthogonal basis, error (approx.c:571-586) */
+#pragma unroll
+   for (int k = 0; k < N; k++)
+#pragma unroll
+      for (int l = k + 1; l <= N; l++)
+	 r [k] += sh.G [k * dcap + v [l]] * r [l] / w.N [k];
+   float m_err = w.norm;
+#pragma unroll
+   for (int k = 0; k <= N; k++)
+   {
+      const float Nk = k == N ? den : w.N [k];
+      const float Bk = k == N ? num : w.B [k];
+      m_err += (r [k] * r [k]) * Nk - 2 * r [k] * Bk;
+   }
+#pragma unroll
+   for (int k = 0; k < FB_MAXEDGES; k++)
+      out [k] = k <= N ? f [k] : 0.0f;
+   out [5] = m_bits;
+   out [6] = w_bits;
+   out [7] = m_err;
+   return (m_bits + w_bits + w.additional_bits) * price + m_err;
+}
+
+/*
+ *  Step N of the pursuit: find the domain the reference's index-ordered scan with its
+ *  running minimum (approx.c:420-603) would select.
+ *
+ *  Phase 1: every thread computes the pass-1 bound of its domains.
+ *  Waves:   the (few) domains whose bound beats the running minimum are evaluated lazily
+ *	     in index order, 32 at a time, by warp 0; after each wave the minimum has
+ *	     dropped and most remaining domains no longer qualify -- exactly the set the
+ *	     sequential scan would have evaluated, plus at most 31 speculative ones per wave.
+ *  Result in w.index / w.best_* / w.min_costs.  Ends with a barrier.
+ */
+template <int NT, int N>
+__device__ void
+cta_mp_find (const DevParams &P, const Sh &sh, MpRes &mp, float price)
+{
+   const int tid  = threadIdx.x;
+   const int lane = tid & 31;
+   const int warp = tid >> 5;
+   MpWork   &w	  = sh.h->w;
+   const int D	  = w.D;
+   const int D32  = (D + 31) & ~31;
+   const float err = mp.err;
+
+   for (int d = tid; d < D32; d += NT)
+   {
+      float b = INFINITY;
+
+      if (d < D && !sh.used [d])
+	 b = mp_pass1<N> (w, d, dom_state (sh, w, d), sh.num [d], sh.den [d], price, err);
+      sh.bnd [d] = b;
+   }
+   float m     = w.min_costs;
+   int	 pos   = 0;
+   bool	 first = true;
+
+   for (;;)
+   {
+      for (int d = tid; d < D32; d += NT)
+      {
+	 const unsigned mask = __ballot_sync (0xffffffffu, d >= pos && sh.bnd [d] < m);
+	 if (lane == 0)
+	    sh.cmask [d >> 5] = mask;
+      }
+      __syncthreads ();
+      if (warp == 0)
+      {
+	 const int nwords = D32 >> 5;
+	 int	   taken  = 0;
+	 bool	   more	  = false;
+
+	 for (int g = 0; g < nwords && !more; g += 32)
+	 {
+	    const unsigned word = (g + lane < nwords) ? sh.cmask [g + lane] : 0u;
+	    const int	   cnt	= __popc (word);
+	    int		   incl = cnt;
+#pragma unroll
+	    for (int o = 1; o < 32; o <<= 1)
+	    {
+	       const int t = __shfl_up_sync (0xffffffffu, incl, o);
+	       if (lane >= o)
+		  incl += t;
+	    }
+	    const int total = __shfl_sync (0xffffffffu, incl, 31);
+	    int	      rk    = taken + incl - cnt;
+	    unsigned  bits  = word;
+
+	    while (bits && rk < 32)
+	    {
+	       sh.cand [rk] = ((g + lane) << 5) + (__ffs ((int) bits) - 1);
+	       bits &= bits - 1;
+	       rk++;
+	    }
+	    if (taken + total > 32)
+	       more = true;
+	    taken = taken + total > 32 ? 32 : taken + total;
+	    if (taken == 32 && g + 32 < nwords)
+	       more = true;	/* unscanned words may hold further candidates */
+	 }
+	 __syncwarp ();
+	 float key = INFINITY, costs = 0;
+	 float res [8];
+	 int   d = -1;
+
+	 if (lane < taken)
+	 {
+	    d = sh.cand [lane];
+	    const float b = sh.bnd [d];
+	    costs = mp_pass2<N> (P, sh, w, mp, d, sh.num [d], sh.den [d], price, res);
+	    key	  = b > costs ? b : costs;	/* both must beat the running minimum */
+	 }
+	 /* ordered resolution (lanes are in index order) */
+	 int winlane = -1, last = -1;
+	 for (;;)
+	 {
+	    const unsigned m2 = __ballot_sync (0xffffffffu, key < m && lane > last);
+	    if (!m2)
+	       break;
+	    last    = __ffs ((int) m2) - 1;
+	    m	    = __shfl_sync (0xffffffffu, costs, last);
+	    winlane = last;
+	 }
+	 if (lane == winlane)
+	 {
+#pragma unroll
+	    for (int k = 0; k < FB_MAXEDGES; k++)
+	       w.best_f [k] = res [k];
+	    w.best_mbits = res [5];
+	    w.best_wbits = res [6];
+	    w.best_err	 = res [7];
+	    w.best_costs = m;
+	    w.min_costs	 = m;
+	    w.index	 = d;
+	 }
+	 if (lane == 0)
+	 {
+	    if (first && winlane < 0)
+	       w.index = -1;
+	    w.wave_done = !more;
+	    w.wave_pos	= more ? sh.cand [31] + 1 : D;
+	    if (taken)
+	       sh.h->pass2 += (unsigned) taken;
+	 }
+      }
+      __syncthreads ();
+      if (w.wave_done)
+	 break;
+      m	    = w.min_costs;
+      pos   = w.wave_pos;
+      first = false;
+   }
+}
+
+/*
  *  One matching pursuit over the current pool for the range (level, image, address).
  *  'mp' lives in shared memory; mp.exclude must be set by the caller.
  */
@@ -984,7 +1249,7 @@ cta_matching_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &
       /* costs of the empty linear combination (approx.c:391-400) */
       mp.err	      = w.norm;
       mp.weights_bits = 0;
-      mp.matrix_bits  = dev_rle_bits (w.mbase, w.d0b, w.csorted, 0, (unsigned) w.pool_n);
+      mp.matrix_bits  = dev_rle_bits<1> (w.mbase, w.d0b, w.csorted, 0, (unsigned) w.pool_n);
       mp.costs	      = (mp.matrix_bits + mp.weights_bits + w.additional_bits) * price
 			+ mp.err;
       t0_mp_prepare_step (P, sh, mp, 0);
@@ -995,214 +1260,13 @@ cta_matching_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &
    int n = 0;
    for (;;)
    {
-      /* ---- candidates, chunk by chunk in index order ---- */
-      for (int base = 0; base < D; base += NT)
+      switch (n)
       {
-	 const int   d	      = base + tid;
-	 float	     key      = INFINITY;
-	 const float cur_min  = w.min_costs;
-
-	 if (d < D && !sh.used [d])
-	 {
-	    const int	st    = dom_state (sh, w, d);
-	    const float num   = sh.num [d], den = sh.den [d];
-	    const bool	is_y  = (d == w.ydom);
-	    short	sorted [FB_MAXEDGES + 1];
-	    int		ns    = w.ncs;
-
-	    /* pass 1 (approx.c:433-462): rate with a dummy weight 0.5 */
-	    {
-	       int p = 0;
-#pragma unroll
-	       for (int e = 0; e < FB_MAXEDGES + 1; e++)
-		  sorted [e] = e < ns ? w.csorted [e] : (short) 0x7fff;
-	       if (!is_y)
-	       {
-		  /* insert d */
-		  p = ns;
-#pragma unroll
-		  for (int e = FB_MAXEDGES; e > 0; e--)
-		     if (e <= p && sorted [e - 1] > d)
-		     {
-			sorted [e] = sorted [e - 1];
-			p	   = e - 1;
-		     }
-#pragma unroll
-		  for (int e = 0; e < FB_MAXEDGES + 1; e++)
-		     if (e == p)
-			sorted [e] = (short) d;
-		  ns++;
-	       }
-	    }
-	    const float mb1 = dev_rle_bits (w.mbase, w.d0b, sorted, ns, (unsigned) w.pool_n);
-	    const float wb1 = st ? w.wb_nd : w.wb_dc;
-	    const float bound = ((mb1 + wb1 + w.additional_bits) * price + mp.err)
-				- (num * num) / den;
-
-	    if (bound < cur_min)
-	    {
-	       /* pass 2 (approx.c:463-602) */
-	       float f [FB_MAXEDGES], r [FB_MAXEDGES];
-	       int   v [FB_MAXEDGES];
-
-#pragma unroll
-	       for (int k = 0; k < FB_MAXEDGES; k++)
-	       {
-		  f [k] = k < n ? w.fB [k] : 0.0f;
-		  v [k] = k < n ? (int) mp.indices [k] : d;
-		  r [k] = 0.0f;
-	       }
-#pragma unroll
-	       for (int k = 0; k < FB_MAXEDGES; k++)
-		  if (k == n)
-		     f [k] = num / den;
-#pragma unroll
-	       for (int l = FB_MAXEDGES - 1; l >= 0; l--)
-		  if (l <= n)
-		  {
-		     const int	 stl = dom_state (sh, w, v [l]);
-		     const float q   = stl ? dev_btor (dev_rtob (f [l], P.rpf_m, P.rpf_range),
-						       P.rpf_m, P.rpf_range)
-					   : dev_btor (dev_rtob (f [l], P.dc_m, P.dc_range),
-						       P.dc_m, P.dc_range);
-		     f [l] = q;
-		     r [l] = q;
-#pragma unroll
-		     for (int k = 0; k < FB_MAXEDGES - 1; k++)
-			if (k < l)
-			   f [k] -= q * sh.G [k * dcap + v [l]] / w.N [k];
-		  }
-	       /* rate of the quantised combination */
-	       float w_bits = 0, m_bits;
-	       {
-		  short srt [FB_MAXEDGES + 1];
-		  int	cnt = 0;
-
-#pragma unroll
-		  for (int e = 0; e < FB_MAXEDGES + 1; e++)
-		     srt [e] = (short) 0x7fff;
-#pragma unroll
-		  for (int k = 0; k < FB_MAXEDGES; k++)
-		     if (k <= n && f [k] != 0)
-		     {
-			const int stk = dom_state (sh, w, v [k]);
-
-			if (stk)
-			   w_bits = (float) ((double) w_bits
-					     - w.l2_lv [dev_rtob (f [k], P.rpf_m, P.rpf_range)]);
-			else
-			   w_bits = (float) ((double) w_bits
-					     - w.l2_dc [dev_rtob (f [k], P.dc_m, P.dc_range)]);
-			if (v [k] != w.ydom)
-			{
-			   /* insertion sort */
-			   int p = cnt;
-#pragma unroll
-			   for (int e = FB_MAXEDGES; e > 0; e--)
-			      if (e <= p && srt [e - 1] > v [k])
-			      {
-				 srt [e] = srt [e - 1];
-				 p	 = e - 1;
-			      }
-#pragma unroll
-			   for (int e = 0; e < FB_MAXEDGES + 1; e++)
-			      if (e == p)
-				 srt [e] = (short) v [k];
-			   cnt++;
-			}
-		     }
-		  m_bits = dev_rle_bits (w.mbase, w.d0b, srt, cnt, (unsigned) w.pool_n);
-	       }
-	       /* back to the orthogonal basis, error (approx.c:571-586) */
-#pragma unroll
-	       for (int k = 0; k < FB_MAXEDGES - 1; k++)
-#pragma unroll
-		  for (int l = k + 1; l < FB_MAXEDGES; l++)
-		     if (l <= n)
-			r [k] += sh.G [k * dcap + v [l]] * r [l] / w.N [k];
-	       float m_err = w.norm;
-#pragma unroll
-	       for (int k = 0; k < FB_MAXEDGES; k++)
-		  if (k <= n)
-		  {
-		     const float Nk = k == n ? den : w.N [k];
-		     const float Bk = k == n ? num : w.B [k];
-		     m_err += (r [k] * r [k]) * Nk - 2 * r [k] * Bk;
-		  }
-	       const float costs = (m_bits + w_bits + w.additional_bits) * price + m_err;
-
-	       key = bound > costs ? bound : costs; /* both must beat the running min */
-#pragma unroll
-	       for (int k = 0; k < FB_MAXEDGES; k++)
-		  sh.slot [k * NT + tid] = f [k];
-	       sh.slot [5 * NT + tid] = m_bits;
-	       sh.slot [6 * NT + tid] = w_bits;
-	       sh.slot [7 * NT + tid] = m_err;
-	       sh.slot [8 * NT + tid] = costs;
-	    }
-	 }
-	 sh.slot [9 * NT + tid] = key;
-	 {
-	    float m = key;
-#pragma unroll
-	    for (int o = 16; o; o >>= 1)
-	       m = fminf (m, __shfl_xor_sync (0xffffffffu, m, o));
-	    if (lane == 0)
-	       sh.wmin [warp] = m;
-	 }
-	 __syncthreads ();
-
-	 /* ---- ordered resolution by warp 0: candidates in index order against the
-		running minimum (approx.c:422-603 processes domains sequentially) ---- */
-	 if (warp == 0)
-	 {
-	    float m	 = w.min_costs;
-	    int	  winner = -1;
-	    float wm	 = lane < NT / 32 ? sh.wmin [lane] : INFINITY;
-	    int	  cur	 = 0;
-
-	    for (;;)
-	    {
-	       unsigned mask = __ballot_sync (0xffffffffu, wm < m && lane >= cur);
-	       if (!mask)
-		  break;
-	       const int   ww	= __ffs (mask) - 1;
-	       const float k2	= sh.slot [9 * NT + ww * 32 + lane];
-	       const float c2	= sh.slot [8 * NT + ww * 32 + lane];
-	       int	   last = -1;
-
-	       for (;;)
-	       {
-		  unsigned m2 = __ballot_sync (0xffffffffu, k2 < m && lane > last);
-		  if (!m2)
-		     break;
-		  last	 = __ffs (m2) - 1;
-		  m	 = __shfl_sync (0xffffffffu, c2, last);
-		  winner = ww * 32 + last;
-	       }
-	       cur = ww + 1;
-	    }
-	    if (winner >= 0)
-	    {
-	       if (lane < 5)
-		  w.best_f [lane] = sh.slot [lane * NT + winner];
-	       else if (lane == 5)
-		  w.best_mbits = sh.slot [5 * NT + winner];
-	       else if (lane == 6)
-		  w.best_wbits = sh.slot [6 * NT + winner];
-	       else if (lane == 7)
-		  w.best_err = sh.slot [7 * NT + winner];
-	       else if (lane == 8)
-	       {
-		  w.best_costs = m;
-		  w.min_costs  = m;
-		  w.index      = base + winner;
-	       }
-	    }
-	    else if (base == 0 && lane == 8)
-	       w.index = -1;	/* first chunk of a step: no winner yet */
-	 }
-	 __syncthreads ();
+	 case 0:  cta_mp_find<NT, 0> (P, sh, mp, price); break;
+	 case 1:  cta_mp_find<NT, 1> (P, sh, mp, price); break;
+	 case 2:  cta_mp_find<NT, 2> (P, sh, mp, price); break;
+	 case 3:  cta_mp_find<NT, 3> (P, sh, mp, price); break;
+	 default: cta_mp_find<NT, 4> (P, sh, mp, price); break;
       }
 
       /* ---- commit the step (approx.c:605-632) ---- */
