@@ -526,6 +526,7 @@ fb200_download (fb200_ctx_t *c, int n_tiles, fb200_wfa_t *out, fb200_trace_rec_t
    c->stats.blocks = c->stats.states = 0;
    c->stats.mp_bytes = c->stats.ss_bytes = 0;
    c->stats.cyc_total = c->stats.cyc_T = c->stats.cyc_mp = c->stats.cyc_append = 0;
+   memset (c->stats.lap, 0, sizeof c->stats.lap);
    for (int t = 0; t < n_tiles; t++)
    {
       const TileResult	  &r  = c->h_results [t];
@@ -556,6 +557,8 @@ fb200_download (fb200_ctx_t *c, int n_tiles, fb200_wfa_t *out, fb200_trace_rec_t
       c->stats.cyc_T	  += r.cyc_T;
       c->stats.cyc_mp	  += r.cyc_mp;
       c->stats.cyc_append += r.cyc_append;
+      for (int i = 0; i < 16; i++)
+	 c->stats.lap [i] += r.lap [i];
       if (r.status != FB200_OK)
       {
 	 if (rc == FB200_OK)

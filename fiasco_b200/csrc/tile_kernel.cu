@@ -24,6 +24,7 @@
  *  executed by thread 0 only, between barriers.
  */
 #include <stdio.h>
+#include <stdlib.h>
 #include <math.h>
 #include "tile_kernel.cuh"
 
@@ -131,6 +132,7 @@ struct Frame			/* one activation record of subdivide() */
    float    r_err, r_tree_bits, r_matrix_bits, r_weights_bits; /* rrange sums */
    RangeRes lrange;
    RangeRes child [2];
+   unsigned tsnap [2 * FB200_MAXLEVEL];	/* tree model at entry (subdivide.c:192) */
 };
 
 struct MpRes			/* mp_t, codec/approx.c:41-51 */
@@ -179,6 +181,14 @@ struct ShHdr
    int	    trace_len;
    unsigned long long mp_calls, mp_steps, pass2, blocks, ip_bytes, mp_bytes, ss_bytes;
    long long cyc_T, cyc_mp, cyc_append, cyc_start;
+   long long lap [16], lap_last;	/* thread-0 lap timer per sub-phase */
+   /* sources of the state being appended (cta_state_products) */
+   short    ap_dom [2][FB_MAXEDGES + 1];
+   float    ap_w [2][FB_MAXEDGES + 1];
+   signed char ap_row [2][FB_MAXEDGES + 1];
+   unsigned char ap_cnt [2], ap_child [2];
+   short    ap_src [2 * (FB_MAXEDGES + 1)];
+   int	    ap_nsrc;
    MpRes    mp, tmp;
    MpWork   w;
    RangeRes root;
@@ -197,13 +207,14 @@ struct Sh			/* pointers into dynamic shared memory */
    unsigned *cmask;		/* [dcap32 / 32] candidate bit masks of the current wave */
    int	   *cand;		/* [32] candidates of the current wave, index order */
    short   *blob;		/* [blob_len] current probability models */
+   short   *snaps;		/* [ndepth][2][blob_len] model snapshots of the DFS, or NULL */
    int	    dcap;
 };
 
 __host__ __device__ inline size_t align16 (size_t x) { return (x + 15) & ~(size_t) 15; }
 
 __host__ __device__ inline size_t
-smem_layout (const DevParams &p, int nt, size_t *off /* [11] */)
+smem_layout (const DevParams &p, int nt, size_t *off /* [12] */)
 {
    size_t o    = 0;
    size_t dcap = (size_t) p.s_cap + 1;
@@ -211,7 +222,7 @@ smem_layout (const DevParams &p, int nt, size_t *off /* [11] */)
    off [0] = o; o += align16 (sizeof (ShHdr));
    off [1] = o; o += align16 (dcap * 4);			/* num */
    off [2] = o; o += align16 (dcap * 4);			/* den */
-   off [3] = o; o += align16 (dcap * 4 * FB_MAXEDGES);		/* G */
+   off [3] = o; o += align16 (dcap * 4 * (p.max_elements > 1 ? p.max_elements - 1 : 1)); /* G */
    off [4] = o; o += align16 (dcap);				/* used */
    off [5] = o; o += align16 ((size_t) p.s_cap * 2);		/* pool */
    off [6] = o; o += align16 (((size_t) 1 << p.lc_max) * 4);	/* pixels */
@@ -219,13 +230,21 @@ smem_layout (const DevParams &p, int nt, size_t *off /* [11] */)
    off [8] = o; o += align16 (((dcap + 31) / 32 * 32) * 4);	/* bnd */
    off [9] = o; o += align16 (((dcap + 31) / 32) * 4 + 32 * 4);	/* cmask, cand */
    off [10] = o; o += align16 ((size_t) p.blob_len * 2);	/* blob */
+   {
+      /* model snapshots of the DFS stay on chip when they are small (default models:
+	 376 B each), else they live in the tile's global workspace */
+      const size_t need = (size_t) (p.level - p.lc_min + 2) * 2 * p.blob_len * 2;
+      off [11] = need <= 24 * 1024 ? o : (size_t) -1;
+      if (need <= 24 * 1024)
+	 o += align16 (need);
+   }
    return o;
 }
 
 __device__ __forceinline__ Sh
 carve (unsigned char *base, const DevParams &p, int nt)
 {
-   size_t off [11];
+   size_t off [12];
    Sh	  s;
 
    smem_layout (p, nt, off);
@@ -241,6 +260,7 @@ carve (unsigned char *base, const DevParams &p, int nt)
    s.cmask  = (unsigned *) (base + off [9]);
    s.cand   = (int *) (s.cmask + ((size_t) p.s_cap + 1 + 31) / 32);
    s.blob   = (short *) (base + off [10]);
+   s.snaps  = off [11] == (size_t) -1 ? (short *) 0 : (short *) (base + off [11]);
    s.dcap   = p.s_cap + 1;
    return s;
 }
@@ -248,6 +268,11 @@ carve (unsigned char *base, const DevParams &p, int nt)
 /* accessors of the model blob */
 #define BLOB_U16(sh, i) (((unsigned short *) (sh).blob) [i])
 #define BLOB_S16(sh, i) ((sh).blob [i])
+
+/* thread-0 lap timer: time since the previous LAP goes to bucket i */
+#define LAP(h, i) do { if (threadIdx.x == 0) { const long long now_ = clock64 (); (h)->lap [i] += now_ - (h)->lap_last; (h)->lap_last = now_; } } while (0)
+enum { LAP_CTRL, LAP_PIX, LAP_DOTS, LAP_UPSWEEP, LAP_ENTER, LAP_MP_PRO, LAP_MP_P1, LAP_MP_WAVES,
+       LAP_MP_COMMIT, LAP_MP_ORTHO, LAP_AR_EPI, LAP_AP_IMG, LAP_AP_DIRECT, LAP_AP_STAGED, LAP_DECIDE, LAP_N };
 
 enum { ST_ENTER, ST_CHILD, ST_AFTER_CHILD, ST_DECIDE, ST_RETURN, ST_DONE, ST_ABORT };
 
@@ -364,6 +389,7 @@ cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
 
    if (from >= S)
       return;			/* uniform: nothing to do, no barrier needed */
+   LAP (sh.h, LAP_CTRL);
 
    /* direct levels */
    for (int l = P.lmin; l <= P.il && l <= level_root; l++)
@@ -449,6 +475,7 @@ cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
       }
    }
    __syncthreads ();
+   LAP (sh.h, LAP_DOTS);
 
    /* upsweep */
    for (int l = (P.il + 1 > P.lmin ? P.il + 1 : P.lmin); l <= level_root; l++)
@@ -457,31 +484,82 @@ cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
       const unsigned node0 = ((node_root + 1) << (level_root - l)) - 1;
       const unsigned ns	   = S - from;
 
-      for (unsigned item = tid; item < ns * nn; item += NT)
+      if (ns >= (unsigned) NT / 2)
       {
-	 const unsigned s    = from + item % ns;
-	 const unsigned node = node0 + item / ns;
-
-	 if (!W.domain_type [s])
-	    continue;
-	 float acc = 0;
-#pragma unroll
-	 for (int label = 0; label < 2; label++)
+	 /* many states: a thread keeps one state's transitions in registers and walks
+	    the nodes of this level; the gathers hit the two child rows of a node */
+	 for (unsigned s = from + tid; s < S; s += NT)
 	 {
-	    const float *src = W.T + (size_t) (2 * node + 1 + label) * scap;
-	    int		 dom = W.tree [2 * s + label];
+	    if (!W.domain_type [s])
+	       continue;
+	    int	  child [2], dom [2][FB_MAXEDGES];
+	    float wt [2][FB_MAXEDGES];
+#pragma unroll
+	    for (int label = 0; label < 2; label++)
+	    {
+	       const short *in = W.into + (size_t) (2 * s + label) * 6;
+	       const float *wp = W.weight + (size_t) (2 * s + label) * 6;
+	       bool	    end = false;
 
-	    if (dom != FB_RANGE)
-	       acc += src [dom];
-	    const short *in = W.into + (size_t) (2 * s + label) * 6;
-	    const float *wt = W.weight + (size_t) (2 * s + label) * 6;
-	    for (int e = 0; (dom = in [e]) != FB_NO_EDGE; e++)
-	       acc += src [dom] * wt [e];
+	       child [label] = W.tree [2 * s + label];
+#pragma unroll
+	       for (int e = 0; e < FB_MAXEDGES; e++)
+	       {
+		  const int d = end ? FB_NO_EDGE : (int) in [e];
+		  end	      = end || d == FB_NO_EDGE;
+		  dom [label][e] = d;
+		  wt [label][e]	 = end ? 0.0f : wp [e];
+	       }
+	    }
+	    for (unsigned k = 0; k < nn; k++)
+	    {
+	       const unsigned node = node0 + k;
+	       float	      acc  = 0;
+#pragma unroll
+	       for (int label = 0; label < 2; label++)
+	       {
+		  const float *src = W.T + (size_t) (2 * node + 1 + label) * scap;
+
+		  if (child [label] != FB_RANGE)
+		     acc += src [child [label]];
+#pragma unroll
+		  for (int e = 0; e < FB_MAXEDGES; e++)
+		     if (dom [label][e] != FB_NO_EDGE)
+			acc += src [dom [label][e]] * wt [label][e];
+	       }
+	       W.T [(size_t) node * scap + s] = acc;
+	    }
 	 }
-	 W.T [(size_t) node * scap + s] = acc;
+      }
+      else
+      {
+	 for (unsigned item = tid; item < ns * nn; item += NT)
+	 {
+	    const unsigned s	= from + item % ns;
+	    const unsigned node = node0 + item / ns;
+
+	    if (!W.domain_type [s])
+	       continue;
+	    float acc = 0;
+#pragma unroll
+	    for (int label = 0; label < 2; label++)
+	    {
+	       const float *src = W.T + (size_t) (2 * node + 1 + label) * scap;
+	       int	    dom = W.tree [2 * s + label];
+
+	       if (dom != FB_RANGE)
+		  acc += src [dom];
+	       const short *in = W.into + (size_t) (2 * s + label) * 6;
+	       const float *wt = W.weight + (size_t) (2 * s + label) * 6;
+	       for (int e = 0; (dom = in [e]) != FB_NO_EDGE; e++)
+		  acc += src [dom] * wt [e];
+	    }
+	    W.T [(size_t) node * scap + s] = acc;
+	 }
       }
       __syncthreads ();
    }
+   LAP (sh.h, LAP_UPSWEEP);
 }
 
 /* codec/subdivide.c:612-644 (init_range) + :504-541 (cut_to_bintree) */
@@ -546,6 +624,7 @@ cta_init_range (const DevParams &P, const TileWs &W, const Sh &sh, unsigned x0,
       sh.h->blocks++;
       sh.h->ip_bytes += 4ull * size + 4ull * (63 + (unsigned) ((1 << (P.lc_max - P.il)) - 1)) * ns;
    }
+   LAP (sh.h, LAP_PIX);
    cta_compute_T<NT> (P, W, sh, 0, 0, P.lc_max);
 }
 
@@ -656,29 +735,142 @@ cta_state_images (const DevParams &P, const TileWs &W, unsigned s)
    __syncthreads ();
 }
 
-/* codec/ip.c:184-260 for from == to == s: all levels are independent of each other
-   because every term refers to states < s */
+/*
+ *  codec/ip.c:184-260 for from == to == s.  Every term of the new row refers to states
+ *  < s, so the levels do not depend on each other.  For a table level the needed rows
+ *  <d1, .> of the level below (d1 = the new state's child / edge targets, a handful) are
+ *  staged in shared memory with coalesced loads, then every partner state t gathers from
+ *  them.  The summation order of ip.c:213-258 is kept: per label, per source of s, the
+ *  inner sum over t's child and edges, scaled by the source's weight.
+ */
 template <int NT>
 __device__ void
-cta_state_products (const DevParams &P, const TileWs &W, unsigned s)
+cta_state_products (const DevParams &P, const TileWs &W, const Sh &sh, unsigned s)
 {
-   const int	  tid	= threadIdx.x;
-   const unsigned items = (unsigned) P.nlev * (s + 1);
+   const int tid  = threadIdx.x;
+   ShHdr    *h	  = sh.h;
+   const int dcap = sh.dcap;
+   /* scratch rows: the pursuit's work arrays are idle while a state is appended */
+   const int NR = 3 + (P.max_elements > 1 ? P.max_elements - 1 : 1);
 
-   for (unsigned item = tid; item < items; item += NT)
+   if (tid == 0)
    {
-      const int	     li = (int) (item / (s + 1));
-      const unsigned t	= item % (s + 1);
+      int nsrc = 0;
 
-      if (!W.domain_type [t])
-	 continue;
-      const float ip = dev_ss_entry (P, W, li, s, t);
-      W.SS [((size_t) li * P.s_cap + s) * P.s_cap + t] = ip;
-      W.SS [((size_t) li * P.s_cap + t) * P.s_cap + s] = ip;
-      if (t == s)
-	 W.diag [(size_t) li * P.s_cap + s] = ip;
+      for (int label = 0; label < 2; label++)
+      {
+	 int	      n	 = 0;
+	 const int    c	 = W.tree [2 * s + label];
+	 const short *in = W.into + (size_t) (2 * s + label) * 6;
+	 const float *wp = W.weight + (size_t) (2 * s + label) * 6;
+
+	 h->ap_child [label] = c != FB_RANGE;
+	 if (c != FB_RANGE)
+	 {
+	    h->ap_dom [label][n] = (short) c;
+	    h->ap_w [label][n]	 = 1.0f;
+	    n++;
+	 }
+	 for (int e = 0; in [e] != FB_NO_EDGE && n < FB_MAXEDGES + 1; e++)
+	 {
+	    h->ap_dom [label][n] = in [e];
+	    h->ap_w [label][n]	 = wp [e];
+	    n++;
+	 }
+	 h->ap_cnt [label] = (unsigned char) n;
+	 for (int k = 0; k < n; k++)
+	 {
+	    int j;
+	    for (j = 0; j < nsrc; j++)
+	       if (h->ap_src [j] == h->ap_dom [label][k])
+		  break;
+	    if (j == nsrc)
+	       h->ap_src [nsrc++] = h->ap_dom [label][k];
+	    h->ap_row [label][k] = (signed char) (j < NR ? j : -1);
+	 }
+      }
+      h->ap_nsrc = nsrc;
    }
    __syncthreads ();
+
+   for (int li = 0; li < P.nlev; li++)
+   {
+      const int level = P.lmin + li;
+
+      if (level <= P.il)
+      {
+	 /* direct dot products of the state images (ip.c:297-323) */
+	 const unsigned len = 1u << level;
+	 const float   *a   = W.img + (size_t) s * FB_IMG_STRIDE + (len - 1);
+
+	 for (unsigned t = tid; t <= s; t += NT)
+	 {
+	    if (!W.domain_type [t])
+	       continue;
+	    const float *b  = W.img + (size_t) t * FB_IMG_STRIDE + (len - 1);
+	    float	 ip = 0;
+	    for (unsigned i = 0; i < len; i++)
+	       ip += a [i] * b [i];
+	    W.SS [((size_t) li * P.s_cap + s) * P.s_cap + t] = ip;
+	    W.SS [((size_t) li * P.s_cap + t) * P.s_cap + s] = ip;
+	    if (t == s)
+	       W.diag [(size_t) li * P.s_cap + s] = ip;
+	 }
+	 LAP (h, LAP_AP_DIRECT);
+	 continue;
+      }
+      /* stage the source rows of the level below */
+      const int nsrc = h->ap_nsrc < NR ? h->ap_nsrc : NR;
+      for (int j = 0; j < nsrc; j++)
+      {
+	 float	     *row = j == 0 ? sh.num : j == 1 ? sh.den : j == 2 ? sh.bnd
+						 : sh.G + (size_t) (j - 3) * dcap;
+	 const float *src = W.SS + ((size_t) (li - 1) * P.s_cap + h->ap_src [j]) * P.s_cap;
+	 for (unsigned t = tid; t <= s; t += NT)
+	    row [t] = src [t];
+      }
+      __syncthreads ();
+      for (unsigned t = tid; t <= s; t += NT)
+      {
+	 if (!W.domain_type [t])
+	    continue;
+	 float ip = 0;
+#pragma unroll
+	 for (int label = 0; label < 2; label++)
+	 {
+	    const short *in2 = W.into + (size_t) (2 * t + label) * 6;
+	    const float *wt2 = W.weight + (size_t) (2 * t + label) * 6;
+	    const int	 c2  = W.tree [2 * t + label];
+	    const int	 n1  = h->ap_cnt [label];
+
+	    for (int k = 0; k < n1; k++)
+	    {
+	       const int    j	= h->ap_row [label][k];
+	       const float *row = j < 0 ? W.SS + ((size_t) (li - 1) * P.s_cap
+						  + h->ap_dom [label][k]) * P.s_cap
+					: j == 0 ? sh.num : j == 1 ? sh.den : j == 2 ? sh.bnd
+					: sh.G + (size_t) (j - 3) * dcap;
+	       float sum = 0;
+	       int   d2;
+
+	       if (c2 != FB_RANGE)
+		  sum = row [c2];
+	       for (int e2 = 0; (d2 = in2 [e2]) != FB_NO_EDGE; e2++)
+		  sum += wt2 [e2] * row [d2];
+	       if (k == 0 && h->ap_child [label])
+		  ip += sum;
+	       else
+		  ip += h->ap_w [label][k] * sum;
+	    }
+	 }
+	 W.SS [((size_t) li * P.s_cap + s) * P.s_cap + t] = ip;
+	 W.SS [((size_t) li * P.s_cap + t) * P.s_cap + s] = ip;
+	 if (t == s)
+	    W.diag [(size_t) li * P.s_cap + s] = ip;
+      }
+      __syncthreads ();
+      LAP (h, LAP_AP_STAGED);
+   }
 }
 
 /* codec/wfalib.c:154-180 */
@@ -746,8 +938,10 @@ cta_append_state (const DevParams &P, const TileWs &W, const Sh &sh, int auxilia
    __syncthreads ();
    if (!auxiliary)
    {
+      LAP (sh.h, LAP_DECIDE);
       cta_state_images<NT> (P, W, s);
-      cta_state_products<NT> (P, W, s);
+      LAP (sh.h, LAP_AP_IMG);
+      cta_state_products<NT> (P, W, sh, s);
    }
    if (threadIdx.x == 0)
    {
@@ -1036,6 +1230,7 @@ cta_mp_find (const DevParams &P, const Sh &sh, MpRes &mp, float price)
 	 b = mp_pass1<N> (w, d, dom_state (sh, w, d), sh.num [d], sh.den [d], price, err);
       sh.bnd [d] = b;
    }
+   LAP (sh.h, LAP_MP_P1);
    float m     = w.min_costs;
    int	 pos   = 0;
    bool	 first = true;
@@ -1154,6 +1349,7 @@ cta_matching_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &
    const float	min_norm = 2e-3f;
    const int	dcap	 = sh.dcap;
 
+   LAP (sh.h, LAP_ENTER);
    /* ---- prologue: per-call tables ---- */
    if (tid == 0)
    {
@@ -1256,6 +1452,7 @@ cta_matching_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &
       w.min_costs = mp.costs;
    }
    __syncthreads ();
+   LAP (sh.h, LAP_MP_PRO);
 
    int n = 0;
    for (;;)
@@ -1271,6 +1468,7 @@ cta_matching_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &
 
       /* ---- commit the step (approx.c:605-632) ---- */
       const int index = w.index;
+      LAP (sh.h, LAP_MP_WAVES);
       if (index < 0)
 	 break;
       if (tid == 0)
@@ -1293,6 +1491,7 @@ cta_matching_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &
 	    t0_mp_prepare_step (P, sh, mp, n + 1);
       }
       __syncthreads ();
+      LAP (sh.h, LAP_MP_COMMIT);
       if (n + 1 >= P.max_elements)
       {
 	 n++;
@@ -1319,6 +1518,7 @@ cta_matching_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &
 		  sh.used [d] = 1;
 	    }
       }
+      LAP (sh.h, LAP_MP_ORTHO);
       n++;
       /* no barrier needed here: the next pass touches only the thread's own domains
 	 (same tid -> same d) plus data published before the last barrier */
@@ -1511,6 +1711,7 @@ cta_approximate_range (const DevParams &P, const TileWs &W, const Sh &sh, float 
 	 h->trace_len++;
    }
    __syncthreads ();
+   LAP (h, LAP_AR_EPI);
 }
 
 /*****************************************************************************
@@ -1529,6 +1730,123 @@ cta_copy_s16 (short *dst, const short *src, int n)
 		   the bintree recursion  (codec/subdivide.c:60-502)
 *****************************************************************************/
 
+enum { ST_CHILD_T = 16, ST_CHILD2 = 17 };
+
+/*
+ *  Thread 0: run the scalar part of subdivide()'s control flow -- returns, cost
+ *  bookkeeping between the two children, tree-model updates, child geometry, early
+ *  exits -- until the block as a whole is needed again:
+ *    ST_ENTER    a visible range of level >= 3: snapshot, linear combination, ...
+ *    ST_CHILD_T  products of the states born in child 0 for child 1's subtree
+ *    ST_DECIDE   restore / adopt models or append a new state
+ *    ST_DONE
+ */
+__device__ void
+t0_advance (const DevParams &P, const TileWs &W, ShHdr *h, int &state, int &depth)
+{
+   for (;;)
+   {
+      Frame &F = h->frames [depth];
+
+      if (state == ST_ENTER)
+      {
+	 RangeRes *res = depth ? &h->frames [depth - 1].child [h->frames [depth - 1].label]
+			       : &h->root;
+
+	 res->into [0] = FB_NO_EDGE;
+	 res->tree     = FB_RANGE;
+	 if (F.level < 3)			/* subdivide.c:113 */
+	 {
+	    h->ret_costs = FB_MAXCOSTS;
+	    state	 = ST_RETURN;
+	 }
+	 else if (F.x >= (unsigned) P.width || F.y >= (unsigned) P.height)
+	 {
+	    h->ret_costs = 0;			/* subdivide.c:133-135 */
+	    state	 = ST_RETURN;
+	 }
+	 else
+	    return;
+      }
+      else if (state == ST_RETURN)
+      {
+	 if (depth == 0)
+	 {
+	    state = ST_DONE;
+	    return;
+	 }
+	 h->frames [depth - 1].subdivide_costs += h->ret_costs;
+	 depth--;
+	 state = ST_AFTER_CHILD;
+      }
+      else if (state == ST_AFTER_CHILD)
+      {
+	 const int label = F.label;
+	 RangeRes &c	 = F.child [label];
+
+	 if (F.subdivide_costs >= fmin2 (F.lincomb_costs, F.max_costs))
+	 {
+	    F.subdivide_costs = FB_MAXCOSTS;	/* subdivide.c:355-359 */
+	    state	      = ST_DECIDE;
+	    return;
+	 }
+	 F.r_err	  += c.err;
+	 F.r_tree_bits	  += c.tree_bits;
+	 F.r_matrix_bits  += c.matrix_bits;
+	 F.r_weights_bits += c.weights_bits;
+	 /* tree_update (bintree.c:35-53) */
+	 if (c.tree != FB_RANGE)
+	    h->tree_counts [F.level - 1]++;
+	 h->tree_total [F.level - 1]++;
+	 F.label = label + 1;
+	 if (F.label >= 2)
+	 {
+	    state = ST_DECIDE;
+	    return;
+	 }
+	 state = ST_CHILD;
+      }
+      else if (state == ST_CHILD || state == ST_CHILD2)
+      {
+	 const int	label = F.label;
+	 const int	level = F.level;
+	 const unsigned cimg  = F.image * 2 + label + 1;
+	 const unsigned cadr  = F.address * 2 + label;
+	 const unsigned cx    = (level & 1) ? F.x : F.x + label * width_of_level (level - 1);
+	 const unsigned cy    = (level & 1) ? F.y + label * height_of_level (level - 1) : F.y;
+
+	 /* products of the states born in child 0 (subdivide.c:295-297) */
+	 if (state == ST_CHILD && label && level <= P.lc_max && F.states_snap < h->states)
+	 {
+	    state = ST_CHILD_T;
+	    return;
+	 }
+	 const float remaining = fmin2 (F.lincomb_costs, F.max_costs) - F.subdivide_costs;
+
+	 F.child [label].x = (unsigned short) cx;
+	 F.child [label].y = (unsigned short) cy;
+	 if (remaining > 0)
+	 {
+	    Frame &C = h->frames [depth + 1];
+
+	    C.max_costs = remaining;
+	    C.x		= cx;
+	    C.y		= cy;
+	    C.image	= cimg;
+	    C.address	= cadr;
+	    C.level	= level - 1;
+	    C.y_state	= F.new_y_state [label];
+	    depth++;
+	    state = ST_ENTER;
+	 }
+	 else
+	    state = ST_AFTER_CHILD;	/* subdivide() not called: costs unchanged */
+      }
+      else
+	 return;
+   }
+}
+
 template <int NT>
 __device__ void
 cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
@@ -1541,15 +1859,17 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
    if (tid == 0)
    {
       Frame &F = h->frames [0];
+      int    st = ST_ENTER, dp = 0;
 
       F.max_costs = FB_MAXCOSTS;
       F.x = F.y = F.image = F.address = 0;
       F.level	= P.level;
       F.y_state = root_y_state;
-      h->depthv [0] = 0;
-      h->state [0]  = ST_ENTER;
       h->band	= band;
       h->price	= band ? P.price * P.chroma_decrease : P.price;
+      t0_advance (P, W, h, st, dp);
+      h->state [0]  = st;
+      h->depthv [0] = dp;
    }
    __syncthreads ();
 
@@ -1560,87 +1880,45 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
       Frame    &F     = h->frames [depth];
       RangeRes *res   = depth ? &h->frames [depth - 1].child [h->frames [depth - 1].label]
 			      : &h->root;
-      int      &next  = h->state [(it + 1) & 1];
-      int      &ndepth = h->depthv [(it + 1) & 1];
+      int	nstate = state;		/* thread 0: state after this action */
 
-      if (threadIdx.x == 0)
-	 ndepth = depth;	/* default: stay at this depth */
-
-      if (state == ST_DONE || state == ST_ABORT)
+      if (state == ST_DONE || h->status != FB200_OK)
 	 break;
-      if (h->status != FB200_OK)
-	 break;
+      LAP (h, LAP_CTRL);
 
       switch (state)
       {
 	 case ST_ENTER:
 	 {
 	    const int level = F.level;
-	    bool      leave = false;
+	    short    *snap  = (sh.snaps ? sh.snaps : W.snap) + (size_t) depth * 2 * P.blob_len;
 
-	    if (tid == 0)
-	    {
-	       res->into [0] = FB_NO_EDGE;
-	       res->tree     = FB_RANGE;
-	    }
-	    if (level < 3)
-	    {
-	       if (tid == 0)
-	       {
-		  h->ret_costs = FB_MAXCOSTS;
-		  next	       = ST_RETURN;
-	       }
-	       leave = true;
-	    }
-	    else if (F.x >= (unsigned) P.width || F.y >= (unsigned) P.height)
-	    {
-	       if (tid == 0)
-	       {
-		  h->ret_costs = 0;
-		  next	       = ST_RETURN;
-	       }
-	       leave = true;
-	    }
-	    if (leave)
-	    {
-	       __syncthreads ();
-	       break;
-	    }
 	    if (level == P.lc_max)
 	    {
-	       if (tid == 0)
-		  F.address = F.image = 0;
-	       __syncthreads ();
 	       const long long t0c = clock64 ();
 	       cta_init_range<NT> (P, W, sh, F.x, F.y, band);
 	       if (tid == 0)
+	       {
+		  F.address = F.image = 0;
 		  h->cyc_T += clock64 () - t0c;
+	       }
 	    }
 	    /* snapshot of the models (subdivide.c:188-194) */
-	    {
-	       short	*snap  = W.snap + (size_t) depth * 2 * P.blob_len;
-	       unsigned *tsnap = W.treesnap + (size_t) depth * 2 * FB200_MAXLEVEL;
-
-	       cta_copy_s16<NT> (snap, sh.blob, P.blob_len);
-	       for (int i = tid; i < FB200_MAXLEVEL; i += NT)
-	       {
-		  tsnap [i]		     = h->tree_counts [i];
-		  tsnap [FB200_MAXLEVEL + i] = h->tree_total [i];
-	       }
-	       if (tid == 0)
-		  F.states_snap = h->states;
-	    }
-	    /* y states of the children (subdivide.c:172-183) */
+	    cta_copy_s16<NT> (snap, sh.blob, P.blob_len);
 	    if (tid == 0)
 	    {
+	       for (int i = 0; i < FB200_MAXLEVEL; i++)
+	       {
+		  F.tsnap [i]		       = h->tree_counts [i];
+		  F.tsnap [FB200_MAXLEVEL + i] = h->tree_total [i];
+	       }
+	       F.states_snap = h->states;
+	       /* y states of the children (subdivide.c:172-183) */
 	       for (int label = 0; label < 2; label++)
 		  F.new_y_state [label] = (band != 0 && F.y_state != FB_RANGE)
 					  ? (int) W.tree [2 * F.y_state + label] : FB_RANGE;
-	    }
-	    /* alternative 1: linear combination (subdivide.c:200-221) */
-	    if (level <= P.lc_max)
-	    {
-	       if (tid == 0)
+	       F.lincomb_costs = FB_MAXCOSTS;
+	       if (level <= P.lc_max)
 	       {
 		  F.lrange.tree		= FB_RANGE;
 		  F.lrange.x		= (unsigned short) F.x;
@@ -1651,7 +1929,11 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 		  F.lrange.err		= 0;
 		  F.lrange.into [0]	= FB_NO_EDGE;
 	       }
-	       __syncthreads ();
+	    }
+	    __syncthreads ();
+	    /* alternative 1: linear combination (subdivide.c:200-221) */
+	    if (level <= P.lc_max)
+	    {
 	       const long long t0c = clock64 ();
 	       cta_approximate_range<NT> (P, W, sh, F.max_costs, h->price, F.y_state,
 					  &F.lrange, level, F.image, F.address, F.x, F.y);
@@ -1661,16 +1943,12 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 		  h->cyc_mp += clock64 () - t0c;
 	       }
 	    }
-	    else if (tid == 0)
-	       F.lincomb_costs = FB_MAXCOSTS;
-	    __syncthreads ();
-	    /* keep the "lc" models, restore the snapshot (subdivide.c:226-237) */
+	    /* keep the "lc" models, restore the snapshot (subdivide.c:226-237); element i
+	       is handled by one thread for both copies */
+	    for (int i = tid; i < P.blob_len; i += NT)
 	    {
-	       short *snap = W.snap + (size_t) depth * 2 * P.blob_len;
-
-	       cta_copy_s16<NT> (snap + P.blob_len, sh.blob, P.blob_len);
-	       __syncthreads ();
-	       cta_copy_s16<NT> (sh.blob, snap, P.blob_len);
+	       snap [P.blob_len + i] = sh.blob [i];
+	       sh.blob [i]	     = snap [i];
 	    }
 	    if (tid == 0)
 	    {
@@ -1691,100 +1969,34 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 		     c.into [0] = 0;
 		     c.err = c.tree_bits = c.matrix_bits = c.weights_bits = 0;
 		  }
-		  next = ST_CHILD;
+		  nstate = ST_CHILD;
 	       }
 	       else
 	       {
 		  F.subdivide_costs = FB_MAXCOSTS;
-		  next		    = ST_DECIDE;
+		  nstate	    = ST_DECIDE;
 	       }
 	    }
-	    __syncthreads ();
 	    break;
 	 }
 
-	 case ST_CHILD:
+	 case ST_CHILD_T:
 	 {
-	    const int	   label = F.label;
-	    const int	   level = F.level;
-	    const unsigned cimg	 = F.image * 2 + label + 1;
-	    const unsigned cadr	 = F.address * 2 + label;
-	    const unsigned cx	 = (level & 1) ? F.x : F.x + label * width_of_level (level - 1);
-	    const unsigned cy	 = (level & 1) ? F.y + label * height_of_level (level - 1) : F.y;
-
-	    /* products of the states born in child 0 (subdivide.c:295-297) */
-	    if (label && level <= P.lc_max)
-	    {
-	       const long long t0c = clock64 ();
-	       cta_compute_T<NT> (P, W, sh, F.states_snap, cimg, level - 1);
-	       if (tid == 0)
-		  h->cyc_T += clock64 () - t0c;
-	    }
+	    const long long t0c = clock64 ();
+	    cta_compute_T<NT> (P, W, sh, F.states_snap, F.image * 2 + F.label + 1,
+			       F.level - 1);
 	    if (tid == 0)
 	    {
-	       const float remaining = fmin2 (F.lincomb_costs, F.max_costs) - F.subdivide_costs;
-
-	       F.child [label].x = (unsigned short) cx;
-	       F.child [label].y = (unsigned short) cy;
-	       if (remaining > 0)
-	       {
-		  Frame &C = h->frames [depth + 1];
-
-		  C.max_costs = remaining;
-		  C.x	      = cx;
-		  C.y	      = cy;
-		  C.image     = cimg;
-		  C.address   = cadr;
-		  C.level     = level - 1;
-		  C.y_state   = F.new_y_state [label];
-		  ndepth      = depth + 1;
-		  next	      = ST_ENTER;
-	       }
-	       else
-	       {
-		  h->ret_costs = 0;	/* subdivide() not called: costs unchanged */
-		  next	       = ST_AFTER_CHILD;
-	       }
+	       h->cyc_T += clock64 () - t0c;
+	       nstate = ST_CHILD2;
 	    }
-	    __syncthreads ();
-	    break;
-	 }
-
-	 case ST_AFTER_CHILD:
-	 {
-	    if (tid == 0)
-	    {
-	       const int label = F.label;
-	       RangeRes &c     = F.child [label];
-
-	       if (F.subdivide_costs >= fmin2 (F.lincomb_costs, F.max_costs))
-	       {
-		  F.subdivide_costs = FB_MAXCOSTS;
-		  next		    = ST_DECIDE;
-	       }
-	       else
-	       {
-		  F.r_err	   += c.err;
-		  F.r_tree_bits	   += c.tree_bits;
-		  F.r_matrix_bits  += c.matrix_bits;
-		  F.r_weights_bits += c.weights_bits;
-		  /* tree_update (bintree.c:35-53) */
-		  if (c.tree != FB_RANGE)
-		     h->tree_counts [F.level - 1]++;
-		  h->tree_total [F.level - 1]++;
-		  F.label = label + 1;
-		  next	  = F.label < 2 ? ST_CHILD : ST_DECIDE;
-	       }
-	    }
-	    __syncthreads ();
 	    break;
 	 }
 
 	 case ST_DECIDE:
 	 {
 	    const float lin = F.lincomb_costs, sub = F.subdivide_costs;
-	    short      *snap  = W.snap + (size_t) depth * 2 * P.blob_len;
-	    unsigned   *tsnap = W.treesnap + (size_t) depth * 2 * FB200_MAXLEVEL;
+	    short      *snap  = (sh.snaps ? sh.snaps : W.snap) + (size_t) depth * 2 * P.blob_len;
 
 	    if ((lin >= FB_MAXCOSTS && sub >= FB_MAXCOSTS) || lin < sub)
 	    {
@@ -1793,13 +2005,13 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 	       /* restore snapshot or adopt the lc models; restore the tree model; drop
 		  the states created below this node (subdivide.c:409-467) */
 	       cta_copy_s16<NT> (sh.blob, fail ? snap : snap + P.blob_len, P.blob_len);
-	       for (int i = tid; i < FB200_MAXLEVEL; i += NT)
-	       {
-		  h->tree_counts [i] = tsnap [i];
-		  h->tree_total [i]  = tsnap [FB200_MAXLEVEL + i];
-	       }
 	       if (tid == 0)
 	       {
+		  for (int i = 0; i < FB200_MAXLEVEL; i++)
+		  {
+		     h->tree_counts [i] = F.tsnap [i];
+		     h->tree_total [i]	= F.tsnap [FB200_MAXLEVEL + i];
+		  }
 		  h->states = F.states_snap;	/* remove_states (wfalib.c:276-310) */
 		  if (fail)
 		     h->ret_costs = FB_MAXCOSTS;
@@ -1812,9 +2024,8 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 		     res->y    = ry;
 		     h->ret_costs = lin;
 		  }
-		  next = ST_RETURN;
+		  nstate = ST_RETURN;
 	       }
-	       __syncthreads ();
 	    }
 	    else
 	    {
@@ -1863,7 +2074,7 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 		  res->matrix_bits  = F.r_matrix_bits;
 		  res->weights_bits = F.r_weights_bits;
 		  h->ret_costs	    = sub;
-		  next		    = ST_RETURN;
+		  nstate	    = ST_RETURN;
 	       }
 	       __syncthreads ();
 	       const long long t0c = clock64 ();
@@ -1873,26 +2084,17 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 	    }
 	    break;
 	 }
-
-	 case ST_RETURN:
-	 {
-	    if (tid == 0)
-	    {
-	       if (depth == 0)
-		  next = ST_DONE;
-	       else
-	       {
-		  Frame &Pf = h->frames [depth - 1];
-
-		  Pf.subdivide_costs += h->ret_costs;
-		  ndepth   = depth - 1;
-		  next	   = ST_AFTER_CHILD;
-	       }
-	    }
-	    __syncthreads ();
-	    break;
-	 }
       }
+      /* thread 0 continues with the scalar part of the control flow */
+      if (tid == 0)
+      {
+	 int dp = depth;
+
+	 t0_advance (P, W, h, nstate, dp);
+	 h->state [(it + 1) & 1]  = nstate;
+	 h->depthv [(it + 1) & 1] = dp;
+      }
+      __syncthreads ();
    }
    __syncthreads ();
 }
@@ -1902,7 +2104,7 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 *****************************************************************************/
 
 template <int NT>
-__global__ void __launch_bounds__ (NT, 1)
+__global__ void __launch_bounds__ (NT, (NT >= 512 ? 1 : NT >= 256 ? 2 : 4))
 fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
 {
    extern __shared__ __align__ (16) unsigned char smem_raw [];
@@ -1919,6 +2121,9 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
       h->mp_bytes = h->ss_bytes = 0;
       h->cyc_T = h->cyc_mp = h->cyc_append = 0;
       h->cyc_start = clock64 ();
+      h->lap_last  = h->cyc_start;
+      for (int i = 0; i < 16; i++)
+	 h->lap [i] = 0;
       h->states	   = 0;
    }
    __syncthreads ();
@@ -1998,6 +2203,8 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
       r->cyc_T	    = (unsigned long long) h->cyc_T;
       r->cyc_mp	    = (unsigned long long) h->cyc_mp;
       r->cyc_append = (unsigned long long) h->cyc_append;
+      for (int i = 0; i < 16; i++)
+	 r->lap [i] = (unsigned long long) h->lap [i];
    }
 }
 
@@ -2046,17 +2253,18 @@ fb_tile_kernel_threads (const DevParams &p)
 {
    /* threads span the domain pool: small tiles have ~100-250 domains, a 1024^2 frame
       up to ~1500 */
+   const char *e = getenv ("FB200_NT");	/* experiments only */
+   if (e && (atoi (e) == 128 || atoi (e) == 256 || atoi (e) == 512))
+      return atoi (e);
    if (p.s_cap <= 384)
       return 128;
-   if (p.s_cap <= 1024)
-      return 256;
-   return 512;
+   return 256;
 }
 
 size_t
 fb_tile_kernel_smem (const DevParams &p, int nt)
 {
-   size_t off [11];
+   size_t off [12];
 
    return smem_layout (p, nt, off);
 }

@@ -87,6 +87,7 @@ struct TileResult
    unsigned long long mp_calls, mp_steps, pass2, blocks, ip_bytes;
    unsigned long long mp_bytes, ss_bytes;	/* algorithmic bytes of the other phases */
    unsigned long long cyc_total, cyc_T, cyc_mp, cyc_append; /* SM cycles per phase */
+   unsigned long long lap [16];	/* thread-0 lap timer per sub-phase */
 };
 
 size_t fb_tile_kernel_smem (const DevParams &p, int nt);

@@ -59,6 +59,7 @@ class Stats(C.Structure):
         ("mp_calls", C.c_uint64), ("mp_steps", C.c_uint64), ("pass2", C.c_uint64),
         ("blocks", C.c_uint64), ("states", C.c_uint64), ("mp_bytes", C.c_uint64), ("ss_bytes", C.c_uint64),
         ("cyc_total", C.c_uint64), ("cyc_T", C.c_uint64), ("cyc_mp", C.c_uint64), ("cyc_append", C.c_uint64),
+        ("lap", C.c_uint64 * 16),
         ("kernel_launches", C.c_int),
     ]
 
@@ -229,7 +230,9 @@ class TileEncoder:
     def stats(self):
         s = Stats()
         self.lib.fb200_get_stats(self.ctx, C.byref(s))
-        return {k: getattr(s, k) for k, _ in Stats._fields_}
+        d = {k: getattr(s, k) for k, _ in Stats._fields_}
+        d["lap"] = list(s.lap)
+        return d
 
 
 def probe(kind, f=None, a=None, b=None, c=None):

@@ -133,6 +133,7 @@ typedef struct fb200_stats
    uint64_t mp_bytes;		/* algorithmic bytes of the pursuits: 8 D per call + 4 D per step */
    uint64_t ss_bytes;		/* algorithmic bytes of the state x state rows */
    uint64_t cyc_total, cyc_T, cyc_mp, cyc_append; /* SM cycles per phase, summed over tiles */
+   uint64_t lap [16];		/* thread-0 cycles per sub-phase (profiling aid) */
    int	    kernel_launches;
 } fb200_stats_t;
 
