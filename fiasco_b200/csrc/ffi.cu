@@ -39,6 +39,7 @@ struct fb200_ctx
    fb200_stats_t  stats;
    int		  launched_tiles;
    cudaStream_t	  last_stream;
+   int		  auto_grow;	/* capacity was chosen by us: grow and retry on overflow */
 };
 
 static void
@@ -174,7 +175,7 @@ default_capacity (const fb200_params_t *p)
    /* measured on the synthetic frames at q=20: 236 states for 256^2, 481 for 512^2,
       1487 for 1024^2, 4755 for 2048^2 -- roughly 1.1-3.7 per 32x32 block */
    const double blocks = ((double) p->width * p->height) / 1024.0;
-   int		cap    = (int) (192 + 2.25 * blocks);
+   int		cap    = (int) (128 + 1.75 * blocks);
 
    cap = (cap + 63) / 64 * 64;
    if (cap > FB200_MAXSTATES)
@@ -262,6 +263,7 @@ work_layout (const DevParams &d, size_t *off /* [10] */)
    off [6] = o; o += up256 ((size_t) d.blob_len * 2);			/* blob_save */
    off [7] = o; o += up256 ((size_t) 2 * FB200_MAXLEVEL * 4);		/* tree_save */
    off [8] = o; o += up256 (sc * 2);					/* pool_save */
+   off [9] = o; o += up256 (sc * sizeof (Trans));			/* trans */
    return o;
 }
 
@@ -307,6 +309,110 @@ fb200_destroy (fb200_ctx_t *c)
    delete c;
 }
 
+static int
+ctx_alloc (fb200_ctx_t *c, char *err, size_t errlen)
+{
+   const DevParams &d	   = c->dp;
+   const int	    device = c->device, max_tiles = c->max_tiles;
+
+   CUDA_TRY (cudaSetDevice (device));
+   c->nt   = 512;
+   c->smem = fb_tile_kernel_smem (d, c->nt);
+   {
+      int max_smem = 0;
+      cudaDeviceGetAttribute (&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+      if ((size_t) max_smem < c->smem)
+      {
+	 set_err (err, errlen, "state capacity %d needs %zu bytes of shared memory, device "
+		  "offers %d", d.s_cap, c->smem, max_smem);
+	 return FB200_EINVAL;
+      }
+   }
+   size_t woff [10], aoff [10];
+   c->work_stride = work_layout (d, woff);
+   c->wfa_block	  = wfa_layout (d, aoff);
+   c->pix_elems	  = (size_t) d.bands * d.width * d.height;
+
+   CUDA_TRY (cudaMalloc (&c->d_work, c->work_stride * max_tiles));
+   CUDA_TRY (cudaMalloc (&c->d_wfa, c->wfa_block * max_tiles));
+   CUDA_TRY (cudaMallocHost (&c->h_wfa, c->wfa_block * max_tiles));
+   if (!c->d_pix)
+   {
+      CUDA_TRY (cudaMalloc (&c->d_pix, c->pix_elems * 2 * max_tiles));
+      CUDA_TRY (cudaMalloc (&c->d_results, sizeof (TileResult) * max_tiles));
+      CUDA_TRY (cudaMalloc (&c->d_ws, sizeof (TileWs) * max_tiles));
+      CUDA_TRY (cudaMallocHost (&c->h_pix, c->pix_elems * 2 * max_tiles));
+      CUDA_TRY (cudaMallocHost (&c->h_results, sizeof (TileResult) * max_tiles));
+      CUDA_TRY (cudaStreamCreateWithFlags (&c->stream, cudaStreamNonBlocking));
+      for (int i = 0; i < 6; i++)
+	 CUDA_TRY (cudaEventCreate (&c->ev [i]));
+   }
+   c->ws.resize (max_tiles);
+   for (int t = 0; t < max_tiles; t++)
+   {
+      unsigned char *wb = c->d_work + c->work_stride * t;
+      unsigned char *ab = c->d_wfa + c->wfa_block * t;
+      TileWs	    &w	= c->ws [t];
+
+      memset (&w, 0, sizeof w);
+      w.pix	  = c->d_pix + c->pix_elems * t;
+      w.img	  = (float *) (wb + woff [0]);
+      w.T	  = (float *) (wb + woff [1]);
+      w.SS	  = (float *) (wb + woff [2]);
+      w.diag	  = (float *) (wb + woff [3]);
+      w.snap	  = (int16_t *) (wb + woff [4]);
+      w.treesnap  = (unsigned *) (wb + woff [5]);
+      w.blob_save = (int16_t *) (wb + woff [6]);
+      w.tree_save = (unsigned *) (wb + woff [7]);
+      w.pool_save = (int16_t *) (wb + woff [8]);
+      w.trans	  = (Trans *) (wb + woff [9]);
+      w.final_d	       = (float *) (ab + aoff [0]);
+      w.weight	       = (float *) (ab + aoff [1]);
+      w.into	       = (int16_t *) (ab + aoff [2]);
+      w.tree	       = (int16_t *) (ab + aoff [3]);
+      w.x	       = (uint16_t *) (ab + aoff [4]);
+      w.y	       = (uint16_t *) (ab + aoff [5]);
+      w.y_state	       = (int16_t *) (ab + aoff [6]);
+      w.level_of_state = (uint8_t *) (ab + aoff [7]);
+      w.domain_type    = (uint8_t *) (ab + aoff [8]);
+      w.y_column       = (uint8_t *) (ab + aoff [9]);
+      w.result	       = c->d_results + t;
+      w.trace	       = t == 0 ? c->d_trace : NULL;
+   }
+   CUDA_TRY (cudaMemcpy (c->d_ws, c->ws.data (), sizeof (TileWs) * max_tiles,
+			 cudaMemcpyHostToDevice));
+   return FB200_OK;
+}
+
+/* grow the per-tile state capacity (after FB200_ECAPACITY); pixels stay resident */
+static int
+ctx_grow (fb200_ctx_t *c, char *err, size_t errlen)
+{
+   fb200_params_t p = c->params;
+   DevParams	  d;
+   int		  cap = c->dp.s_cap + c->dp.s_cap / 2;
+
+   if (c->dp.s_cap >= FB200_MAXSTATES)
+      return FB200_ECAPACITY;
+   if (cap > FB200_MAXSTATES)
+      cap = FB200_MAXSTATES;
+   p.state_capacity = cap;
+   int rc = derive (&p, &d, err, errlen);
+   if (rc)
+      return rc;
+   d.trace_cap = c->dp.trace_cap;
+   CUDA_TRY (cudaSetDevice (c->device));
+   cudaFree (c->d_work);
+   cudaFree (c->d_wfa);
+   cudaFreeHost (c->h_wfa);
+   c->d_work = NULL;
+   c->d_wfa  = NULL;
+   c->h_wfa  = NULL;
+   c->dp     = d;
+   c->params.state_capacity = cap;
+   return ctx_alloc (c, err, errlen);
+}
+
 extern "C" int
 fb200_create (fb200_ctx_t **out, const fb200_params_t *p, int max_tiles, int device,
 	      char *err, size_t errlen)
@@ -327,89 +433,20 @@ fb200_create (fb200_ctx_t **out, const fb200_params_t *p, int max_tiles, int dev
 	       device);
       return FB200_ENODEVICE;
    }
-   CUDA_TRY (cudaSetDevice (device));
-
    fb200_ctx_t *c = new fb200_ctx_t ();
    c->params	  = *p;
    c->dp	  = d;
    c->max_tiles	  = max_tiles;
    c->device	  = device;
-   c->nt	  = fb_tile_kernel_threads (d);
-   c->smem	  = fb_tile_kernel_smem (d, c->nt);
    c->trace_cap	  = 0;
-   {
-      int max_smem = 0;
-      cudaDeviceGetAttribute (&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-      if ((size_t) max_smem < c->smem)
-      {
-	 set_err (err, errlen, "state capacity %d needs %zu bytes of shared memory, device "
-		  "offers %d", d.s_cap, c->smem, max_smem);
-	 delete c;
-	 return FB200_EINVAL;
-      }
-   }
-   size_t woff [10], aoff [10];
-   c->work_stride = work_layout (d, woff);
-   c->wfa_block	  = wfa_layout (d, aoff);
-   c->pix_elems	  = (size_t) d.bands * d.width * d.height;
-
-#define CTX_TRY(call)                                                               \
-   do {                                                                             \
-      cudaError_t e_ = (call);                                                      \
-      if (e_ != cudaSuccess) {                                                      \
-	 set_err (err, errlen, "CUDA error %s at %s:%d (%s)", cudaGetErrorName (e_), \
-		  __FILE__, __LINE__, cudaGetErrorString (e_));                     \
-	 fb200_destroy (c);                                                         \
-	 return FB200_ECUDA;                                                        \
-      }                                                                             \
-   } while (0)
-
-   CTX_TRY (cudaMalloc (&c->d_work, c->work_stride * max_tiles));
-   CTX_TRY (cudaMalloc (&c->d_pix, c->pix_elems * 2 * max_tiles));
-   CTX_TRY (cudaMalloc (&c->d_wfa, c->wfa_block * max_tiles));
-   CTX_TRY (cudaMalloc (&c->d_results, sizeof (TileResult) * max_tiles));
-   CTX_TRY (cudaMalloc (&c->d_ws, sizeof (TileWs) * max_tiles));
-   CTX_TRY (cudaMallocHost (&c->h_pix, c->pix_elems * 2 * max_tiles));
-   CTX_TRY (cudaMallocHost (&c->h_wfa, c->wfa_block * max_tiles));
-   CTX_TRY (cudaMallocHost (&c->h_results, sizeof (TileResult) * max_tiles));
-   CTX_TRY (cudaStreamCreateWithFlags (&c->stream, cudaStreamNonBlocking));
-   for (int i = 0; i < 6; i++)
-      CTX_TRY (cudaEventCreate (&c->ev [i]));
-
-   c->ws.resize (max_tiles);
-   for (int t = 0; t < max_tiles; t++)
-   {
-      unsigned char *wb = c->d_work + c->work_stride * t;
-      unsigned char *ab = c->d_wfa + c->wfa_block * t;
-      TileWs	    &w	= c->ws [t];
-
-      memset (&w, 0, sizeof w);
-      w.pix	  = c->d_pix + c->pix_elems * t;
-      w.img	  = (float *) (wb + woff [0]);
-      w.T	  = (float *) (wb + woff [1]);
-      w.SS	  = (float *) (wb + woff [2]);
-      w.diag	  = (float *) (wb + woff [3]);
-      w.snap	  = (int16_t *) (wb + woff [4]);
-      w.treesnap  = (unsigned *) (wb + woff [5]);
-      w.blob_save = (int16_t *) (wb + woff [6]);
-      w.tree_save = (unsigned *) (wb + woff [7]);
-      w.pool_save = (int16_t *) (wb + woff [8]);
-      w.final_d	       = (float *) (ab + aoff [0]);
-      w.weight	       = (float *) (ab + aoff [1]);
-      w.into	       = (int16_t *) (ab + aoff [2]);
-      w.tree	       = (int16_t *) (ab + aoff [3]);
-      w.x	       = (uint16_t *) (ab + aoff [4]);
-      w.y	       = (uint16_t *) (ab + aoff [5]);
-      w.y_state	       = (int16_t *) (ab + aoff [6]);
-      w.level_of_state = (uint8_t *) (ab + aoff [7]);
-      w.domain_type    = (uint8_t *) (ab + aoff [8]);
-      w.y_column       = (uint8_t *) (ab + aoff [9]);
-      w.result	       = c->d_results + t;
-      w.trace	       = NULL;
-   }
-   CTX_TRY (cudaMemcpy (c->d_ws, c->ws.data (), sizeof (TileWs) * max_tiles,
-			cudaMemcpyHostToDevice));
+   c->auto_grow	  = p->state_capacity <= 0;
    memset (&c->stats, 0, sizeof c->stats);
+   rc = ctx_alloc (c, err, errlen);
+   if (rc)
+   {
+      fb200_destroy (c);
+      return rc;
+   }
    *out = c;
    return FB200_OK;
 }
@@ -628,9 +665,34 @@ fb200_encode_tiles (fb200_ctx_t *c, int n_tiles, const int16_t *const *planes,
       c->dp.trace_cap = 0;
    if ((rc = fb200_upload (c, n_tiles, planes, err, errlen)))
       return rc;
-   if ((rc = fb200_launch (c, n_tiles, NULL, err, errlen)))
-      return rc;
-   return fb200_download (c, n_tiles, out, trace, trace_cap, trace_len, err, errlen);
+   for (;;)
+   {
+      if ((rc = fb200_launch (c, n_tiles, NULL, err, errlen)))
+	 return rc;
+      rc = fb200_download (c, n_tiles, out, trace, trace_cap, trace_len, err, errlen);
+      if (rc != FB200_ECAPACITY || !c->auto_grow)
+	 return rc;
+      /* a tile outgrew the workspace we sized ourselves: enlarge it and run again */
+      if ((rc = ctx_grow (c, err, errlen)))
+	 return rc;
+   }
+}
+
+extern "C" int
+fb200_resident_tiles (const fb200_ctx_t *c)
+{
+   int sms = 0;
+
+   if (!c || cudaSetDevice (c->device) != cudaSuccess)
+      return 0;
+   cudaDeviceGetAttribute (&sms, cudaDevAttrMultiProcessorCount, c->device);
+   return sms * fb_tile_kernel_occupancy (c->dp);
+}
+
+extern "C" int
+fb200_state_capacity (const fb200_ctx_t *c)
+{
+   return c ? c->dp.s_cap : 0;
 }
 
 extern "C" void

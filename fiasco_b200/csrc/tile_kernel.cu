@@ -109,6 +109,74 @@ __device__ __forceinline__ unsigned dev_bits_bin_code (unsigned value, unsigned 
    return value < maxval + 1 - 2 * r ? k : k + 1;
 }
 
+/* transitions of a state in registers */
+struct TransReg
+{
+   int	 child [2];
+   int	 into [2][FB_MAXEDGES];	/* FB_NO_EDGE from the first unused slot on */
+   float w [2][FB_MAXEDGES];
+};
+
+__device__ __forceinline__ void
+load_trans (const Trans *p, TransReg &r)
+{
+   const uint4 *q = (const uint4 *) p;
+   const uint4	a = q [0], b = q [1], c = q [2], d = q [3];	/* one 64-byte line */
+   const unsigned sh [12] = {a.x, a.y, a.z, a.w, b.x, b.y};
+   short	  v [12];
+
+#pragma unroll
+   for (int i = 0; i < 6; i++)
+   {
+      v [2 * i]	    = (short) (sh [i] & 0xffffu);
+      v [2 * i + 1] = (short) (sh [i] >> 16);
+   }
+   r.child [0] = v [0];
+   r.child [1] = v [1];
+   bool end0 = false, end1 = false;
+#pragma unroll
+   for (int e = 0; e < FB_MAXEDGES; e++)
+   {
+      end0 = end0 || v [2 + e] == FB_NO_EDGE;
+      end1 = end1 || v [7 + e] == FB_NO_EDGE;
+      r.into [0][e] = end0 ? FB_NO_EDGE : (int) v [2 + e];
+      r.into [1][e] = end1 ? FB_NO_EDGE : (int) v [7 + e];
+   }
+   r.w [0][0] = __uint_as_float (b.z);
+   r.w [0][1] = __uint_as_float (b.w);
+   r.w [0][2] = __uint_as_float (c.x);
+   r.w [0][3] = __uint_as_float (c.y);
+   r.w [0][4] = __uint_as_float (c.z);
+   r.w [1][0] = __uint_as_float (c.w);
+   r.w [1][1] = __uint_as_float (d.x);
+   r.w [1][2] = __uint_as_float (d.y);
+   r.w [1][3] = __uint_as_float (d.z);
+   r.w [1][4] = __uint_as_float (d.w);
+}
+
+/* thread 0: pack the transitions of state s (already in the automaton arrays) */
+__device__ void
+t0_store_trans (const TileWs &W, unsigned s)
+{
+   Trans t;
+
+   for (int label = 0; label < 2; label++)
+   {
+      const short *in = W.into + (size_t) (2 * s + label) * 6;
+      const float *wt = W.weight + (size_t) (2 * s + label) * 6;
+      bool	   end = false;
+
+      t.child [label] = W.tree [2 * s + label];
+      for (int e = 0; e < FB_MAXEDGES; e++)
+      {
+	 end = end || in [e] == FB_NO_EDGE;
+	 t.into [label][e] = end ? (short) FB_NO_EDGE : in [e];
+	 t.w [label][e]	   = end ? 0.0f : wt [e];
+      }
+   }
+   W.trans [s] = t;
+}
+
 /*****************************************************************************
 			     shared memory layout
 *****************************************************************************/
@@ -151,8 +219,8 @@ struct MpWork
    float  fB [FB_MAXEDGES];	/* B[k] / N[k] */
    float  mbase [FB_MAXEDGES + 2]; /* -log2 (count[k] / total) */
    float  d0b [2];		/* DC-column bits: [0] unused, [1] used */
-   double l2_dc [512];		/* log2 (count / total) per DC code */
-   double l2_lv [512];		/* same for the context of the current level */
+   double *l2_dc;		/* [aac_dc_size] log2 (count / total) per DC code */
+   double *l2_lv;		/* [aac_lvl_size] same for the context of the current level */
    float  additional_bits, price, norm, min_costs;
    float  wb_dc, wb_nd;		/* pass-1 weights bits of a DC / other candidate */
    int	  nc;			/* chosen vectors with non-zero weight */
@@ -192,7 +260,7 @@ struct ShHdr
    MpRes    mp, tmp;
    MpWork   w;
    RangeRes root;
-   Frame    frames [FB_MAXDEPTH];
+   Frame   *frames;		/* [level - lc_min + 2] */
 };
 
 struct Sh			/* pointers into dynamic shared memory */
@@ -208,13 +276,15 @@ struct Sh			/* pointers into dynamic shared memory */
    int	   *cand;		/* [32] candidates of the current wave, index order */
    short   *blob;		/* [blob_len] current probability models */
    short   *snaps;		/* [ndepth][2][blob_len] model snapshots of the DFS, or NULL */
+   double  *l2;			/* [aac_dc_size + aac_lvl_size] */
+   Frame   *frames;
    int	    dcap;
 };
 
 __host__ __device__ inline size_t align16 (size_t x) { return (x + 15) & ~(size_t) 15; }
 
 __host__ __device__ inline size_t
-smem_layout (const DevParams &p, int nt, size_t *off /* [12] */)
+smem_layout (const DevParams &p, int nt, size_t *off /* [14] */)
 {
    size_t o    = 0;
    size_t dcap = (size_t) p.s_cap + 1;
@@ -238,13 +308,15 @@ smem_layout (const DevParams &p, int nt, size_t *off /* [12] */)
       if (need <= 24 * 1024)
 	 o += align16 (need);
    }
+   off [12] = o; o += align16 ((size_t) (p.aac_dc_size + p.aac_lvl_size) * 8);	/* log2 tables */
+   off [13] = o; o += align16 ((size_t) (p.level - p.lc_min + 2) * sizeof (Frame));	/* DFS frames */
    return o;
 }
 
 __device__ __forceinline__ Sh
 carve (unsigned char *base, const DevParams &p, int nt)
 {
-   size_t off [12];
+   size_t off [14];
    Sh	  s;
 
    smem_layout (p, nt, off);
@@ -262,6 +334,8 @@ carve (unsigned char *base, const DevParams &p, int nt)
    s.blob   = (short *) (base + off [10]);
    s.snaps  = off [11] == (size_t) -1 ? (short *) 0 : (short *) (base + off [11]);
    s.dcap   = p.s_cap + 1;
+   s.l2	    = (double *) (base + off [12]);
+   s.frames = (Frame *) (base + off [13]);
    return s;
 }
 
@@ -492,25 +566,9 @@ cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
 	 {
 	    if (!W.domain_type [s])
 	       continue;
-	    int	  child [2], dom [2][FB_MAXEDGES];
-	    float wt [2][FB_MAXEDGES];
-#pragma unroll
-	    for (int label = 0; label < 2; label++)
-	    {
-	       const short *in = W.into + (size_t) (2 * s + label) * 6;
-	       const float *wp = W.weight + (size_t) (2 * s + label) * 6;
-	       bool	    end = false;
+	    TransReg tr;
 
-	       child [label] = W.tree [2 * s + label];
-#pragma unroll
-	       for (int e = 0; e < FB_MAXEDGES; e++)
-	       {
-		  const int d = end ? FB_NO_EDGE : (int) in [e];
-		  end	      = end || d == FB_NO_EDGE;
-		  dom [label][e] = d;
-		  wt [label][e]	 = end ? 0.0f : wp [e];
-	       }
-	    }
+	    load_trans (W.trans + s, tr);
 	    for (unsigned k = 0; k < nn; k++)
 	    {
 	       const unsigned node = node0 + k;
@@ -520,12 +578,12 @@ cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
 	       {
 		  const float *src = W.T + (size_t) (2 * node + 1 + label) * scap;
 
-		  if (child [label] != FB_RANGE)
-		     acc += src [child [label]];
+		  if (tr.child [label] != FB_RANGE)
+		     acc += src [tr.child [label]];
 #pragma unroll
 		  for (int e = 0; e < FB_MAXEDGES; e++)
-		     if (dom [label][e] != FB_NO_EDGE)
-			acc += src [dom [label][e]] * wt [label][e];
+		     if (tr.into [label][e] != FB_NO_EDGE)
+			acc += src [tr.into [label][e]] * tr.w [label][e];
 	       }
 	       W.T [(size_t) node * scap + s] = acc;
 	    }
@@ -540,19 +598,21 @@ cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
 
 	    if (!W.domain_type [s])
 	       continue;
-	    float acc = 0;
+	    TransReg tr;
+	    float    acc = 0;
+
+	    load_trans (W.trans + s, tr);
 #pragma unroll
 	    for (int label = 0; label < 2; label++)
 	    {
 	       const float *src = W.T + (size_t) (2 * node + 1 + label) * scap;
-	       int	    dom = W.tree [2 * s + label];
 
-	       if (dom != FB_RANGE)
-		  acc += src [dom];
-	       const short *in = W.into + (size_t) (2 * s + label) * 6;
-	       const float *wt = W.weight + (size_t) (2 * s + label) * 6;
-	       for (int e = 0; (dom = in [e]) != FB_NO_EDGE; e++)
-		  acc += src [dom] * wt [e];
+	       if (tr.child [label] != FB_RANGE)
+		  acc += src [tr.child [label]];
+#pragma unroll
+	       for (int e = 0; e < FB_MAXEDGES; e++)
+		  if (tr.into [label][e] != FB_NO_EDGE)
+		     acc += src [tr.into [label][e]] * tr.w [label][e];
 	    }
 	    W.T [(size_t) node * scap + s] = acc;
 	 }
@@ -809,8 +869,29 @@ cta_state_products (const DevParams &P, const TileWs &W, const Sh &sh, unsigned 
 	       continue;
 	    const float *b  = W.img + (size_t) t * FB_IMG_STRIDE + (len - 1);
 	    float	 ip = 0;
-	    for (unsigned i = 0; i < len; i++)
-	       ip += a [i] * b [i];
+	    if (level == 5)
+	    {
+	       /* the level-5 part is floats 31..62 of a 256-byte row: load the whole
+		  upper half with aligned float4s (independent loads, one L2 round trip) */
+	       const float4 *b4 = (const float4 *) (W.img + (size_t) t * FB_IMG_STRIDE + 32);
+	       float4	     v [8];
+	       float	     prev = W.img [(size_t) t * FB_IMG_STRIDE + 31];
+#pragma unroll
+	       for (int q = 0; q < 8; q++)
+		  v [q] = b4 [q];
+#pragma unroll
+	       for (int q = 0; q < 8; q++)
+	       {
+		  ip += a [4 * q] * prev;
+		  ip += a [4 * q + 1] * v [q].x;
+		  ip += a [4 * q + 2] * v [q].y;
+		  ip += a [4 * q + 3] * v [q].z;
+		  prev = v [q].w;
+	       }
+	    }
+	    else
+	       for (unsigned i = 0; i < len; i++)
+		  ip += a [i] * b [i];
 	    W.SS [((size_t) li * P.s_cap + s) * P.s_cap + t] = ip;
 	    W.SS [((size_t) li * P.s_cap + t) * P.s_cap + s] = ip;
 	    if (t == s)
@@ -834,14 +915,15 @@ cta_state_products (const DevParams &P, const TileWs &W, const Sh &sh, unsigned 
       {
 	 if (!W.domain_type [t])
 	    continue;
-	 float ip = 0;
+	 float	  ip = 0;
+	 TransReg tr;
+
+	 load_trans (W.trans + t, tr);
 #pragma unroll
 	 for (int label = 0; label < 2; label++)
 	 {
-	    const short *in2 = W.into + (size_t) (2 * t + label) * 6;
-	    const float *wt2 = W.weight + (size_t) (2 * t + label) * 6;
-	    const int	 c2  = W.tree [2 * t + label];
-	    const int	 n1  = h->ap_cnt [label];
+	    const int c2 = tr.child [label];
+	    const int n1 = h->ap_cnt [label];
 
 	    for (int k = 0; k < n1; k++)
 	    {
@@ -851,12 +933,13 @@ cta_state_products (const DevParams &P, const TileWs &W, const Sh &sh, unsigned 
 					: j == 0 ? sh.num : j == 1 ? sh.den : j == 2 ? sh.bnd
 					: sh.G + (size_t) (j - 3) * dcap;
 	       float sum = 0;
-	       int   d2;
 
 	       if (c2 != FB_RANGE)
 		  sum = row [c2];
-	       for (int e2 = 0; (d2 = in2 [e2]) != FB_NO_EDGE; e2++)
-		  sum += wt2 [e2] * row [d2];
+#pragma unroll
+	       for (int e2 = 0; e2 < FB_MAXEDGES; e2++)
+		  if (tr.into [label][e2] != FB_NO_EDGE)
+		     sum += tr.w [label][e2] * row [tr.into [label][e2]];
 	       if (k == 0 && h->ap_child [label])
 		  ip += sum;
 	       else
@@ -998,6 +1081,7 @@ cta_init_basis (const DevParams &P, const TileWs &W, const Sh &sh)
       t0_append_edge (W, 2, 1, 1.0f, 1);
       for (unsigned s = 0; s < 3; s++)
       {
+	 t0_store_trans (W, s);
 	 W.img [(size_t) s * FB_IMG_STRIDE] = W.final_d [s];
 	 W.level_of_state [s]		    = (uint8_t) -1;
       }
@@ -1425,14 +1509,13 @@ cta_matching_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &
       unsigned char used = 0;
       float	    num	 = 0;
 
+      /* both loads are issued up front (one L2 round trip); a numerator that belongs
+	 to an unusable domain is never looked at */
+      num = W.T [(size_t) image * P.s_cap + st];
       if (den / fsize < min_norm)
 	 used = 1;
-      else
-      {
-	 num = W.T [(size_t) image * P.s_cap + st];
-	 if (fabsf (num) < min_norm)
-	    used = 1;
-      }
+      else if (fabsf (num) < min_norm)
+	 used = 1;
       for (int e = 0; e < FB_MAXEDGES && mp.exclude [e] != FB_NO_EDGE; e++)
 	 if (mp.exclude [e] == d)
 	    used = 1;
@@ -2065,6 +2148,7 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 			   W.y_column [2 * s + label] = 1;
 		     }
 		  }
+		  t0_store_trans (W, s);
 		  res->into [0]	    = FB_NO_EDGE;
 		  res->tree	    = (short) s;
 		  res->x	    = (unsigned short) F.x;
@@ -2116,6 +2200,9 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
    if (tid == 0)
    {
       h->status	   = FB200_OK;
+      h->frames	   = sh.frames;
+      h->w.l2_dc   = sh.l2;
+      h->w.l2_lv   = sh.l2 + P.aac_dc_size;
       h->trace_len = 0;
       h->mp_calls = h->mp_steps = h->pass2 = h->blocks = h->ip_bytes = 0;
       h->mp_bytes = h->ss_bytes = 0;
@@ -2249,22 +2336,27 @@ fiasco_probe_kernel (int kind, int n, const float *f, const int *a, const int *b
 *****************************************************************************/
 
 int
-fb_tile_kernel_threads (const DevParams &p)
+fb_tile_kernel_threads (const DevParams &p, int n_tiles)
 {
    /* threads span the domain pool: small tiles have ~100-250 domains, a 1024^2 frame
       up to ~1500 */
    const char *e = getenv ("FB200_NT");	/* experiments only */
    if (e && (atoi (e) == 128 || atoi (e) == 256 || atoi (e) == 512))
       return atoi (e);
-   if (p.s_cap <= 384)
-      return 128;
-   return 256;
+   (void) p;
+   /* few tiles: latency matters, give each tile a whole SM's worth of threads; a full
+      batch: 128 threads per tile and several tiles resident per SM hide each other's
+      serial phases ("thread-block shape") */
+   int sms = 148, dev = 0;
+   if (cudaGetDevice (&dev) == cudaSuccess)
+      cudaDeviceGetAttribute (&sms, cudaDevAttrMultiProcessorCount, dev);
+   return n_tiles < sms ? 512 : 128;
 }
 
 size_t
 fb_tile_kernel_smem (const DevParams &p, int nt)
 {
-   size_t off [12];
+   size_t off [14];
 
    return smem_layout (p, nt, off);
 }
@@ -2321,11 +2413,40 @@ fb_launch_tile_kernel (const DevParams &p, const TileWs *d_ws, int n_tiles,
    cudaError_t e = upload_tables ();
    if (e != cudaSuccess)
       return e;
-   switch (fb_tile_kernel_threads (p))
+   switch (fb_tile_kernel_threads (p, n_tiles))
    {
       case 128: return launch_nt<128> (p, d_ws, n_tiles, stream);
       case 256: return launch_nt<256> (p, d_ws, n_tiles, stream);
       default:	return launch_nt<512> (p, d_ws, n_tiles, stream);
+   }
+}
+
+template <int NT>
+static int
+occupancy_nt (const DevParams &p)
+{
+   int	  n    = 0;
+   size_t smem = fb_tile_kernel_smem (p, NT);
+
+   if (cudaFuncSetAttribute (fiasco_tile_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+			     (int) smem) != cudaSuccess
+       || cudaOccupancyMaxActiveBlocksPerMultiprocessor (&n, fiasco_tile_kernel<NT>, NT, smem)
+	  != cudaSuccess)
+   {
+      cudaGetLastError ();
+      return 0;
+   }
+   return n;
+}
+
+int
+fb_tile_kernel_occupancy (const DevParams &p)
+{
+   switch (fb_tile_kernel_threads (p, 1 << 20))
+   {
+      case 128: return occupancy_nt<128> (p);
+      case 256: return occupancy_nt<256> (p);
+      default:	return occupancy_nt<512> (p);
    }
 }
 

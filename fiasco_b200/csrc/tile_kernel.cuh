@@ -48,6 +48,14 @@ struct DevParams
    int	 first_band, last_band; /* bands processed by this launch */
 };
 
+/* all transitions of one state in one 64-byte line: what the inner-product kernels gather */
+struct __align__ (64) Trans
+{
+   short child [2];		/* wfa->tree [s][label] */
+   short into [2][FB_MAXEDGES];	/* -1 terminated unless all 5 are used */
+   float w [2][FB_MAXEDGES];
+};
+
 /* per-tile device workspace (all pointers device memory) */
 struct TileWs
 {
@@ -56,6 +64,7 @@ struct TileWs
    float   *T;			/* [tn][s_cap]		  range x state products */
    float   *SS;			/* [nlev][s_cap][s_cap]	  state x state products */
    float   *diag;		/* [nlev][s_cap]	  <s,s> */
+   Trans   *trans;		/* [s_cap]		  packed transitions */
    /* automaton */
    float   *final_d;		/* [s_cap] */
    uint8_t *level_of_state;	/* [s_cap] */
@@ -91,7 +100,8 @@ struct TileResult
 };
 
 size_t fb_tile_kernel_smem (const DevParams &p, int nt);
-int    fb_tile_kernel_threads (const DevParams &p);
+int    fb_tile_kernel_threads (const DevParams &p, int n_tiles);
+int    fb_tile_kernel_occupancy (const DevParams &p);	/* resident tiles per SM */
 cudaError_t fb_launch_tile_kernel (const DevParams &p, const TileWs *d_ws, int n_tiles,
 				   cudaStream_t stream);
 cudaError_t fb_launch_probe (int kind, int n, const float *f, const int *a, const int *b,

@@ -92,6 +92,8 @@ def load():
     lib.fb200_sync.argtypes = [vp, cp, C.c_size_t]
     lib.fb200_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.fb200_get_stats.restype = None
+    lib.fb200_resident_tiles.argtypes = [vp]
+    lib.fb200_state_capacity.argtypes = [vp]
     lib.fb200_probe.argtypes = [ip, ip, vp, vp, vp, vp, vp, vp, cp, C.c_size_t]
     _LIB = lib
     return lib
@@ -226,6 +228,12 @@ class TileEncoder:
         tl = C.c_int(0)
         _check(self.lib.fb200_download(self.ctx, n_tiles, self._wfas, None, 0, C.byref(tl), err, 512), err)
         return self._collect(n_tiles, None, tl)[0]
+
+    def resident_tiles(self):
+        return self.lib.fb200_resident_tiles(self.ctx)
+
+    def state_capacity(self):
+        return self.lib.fb200_state_capacity(self.ctx)
 
     def stats(self):
         s = Stats()

@@ -173,6 +173,10 @@ int fb200_download (fb200_ctx_t *ctx, int n_tiles, fb200_wfa_t *out,
 		    char *err, size_t errlen);
 int fb200_sync (fb200_ctx_t *ctx, char *err, size_t errlen);
 void fb200_get_stats (const fb200_ctx_t *ctx, fb200_stats_t *stats);
+/* tiles the device keeps resident at once (SM count x thread blocks per SM): the batch
+   size that fills one wave */
+int fb200_resident_tiles (const fb200_ctx_t *ctx);
+int fb200_state_capacity (const fb200_ctx_t *ctx);
 
 /* helpers for C callers */
 int  fb200_wfa_alloc (fb200_wfa_t *wfa, int capacity);
