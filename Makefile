@@ -14,7 +14,36 @@ KOBJ     := $(LIBDIR)/tile_kernel.o $(LIBDIR)/ffi.o
 .PHONY: all product oracle clean ptxas
 all: product oracle
 
-product: $(LIBDIR)/libfiasco_b200.so
+product: $(LIBDIR)/libfiasco_b200.so $(LIBDIR)/libfiasco.so cfiasco
+
+# host side of libfiasco (plain C): options, PNM input, .fco writer, fiasco_coder()
+HOST     := fiasco_b200/host
+HOSTSRC  := messages host_util c_options pnm_input bitstream fco_writer coder_api
+HOSTOBJ  := $(addprefix $(LIBDIR)/host_,$(addsuffix .o,$(HOSTSRC)))
+HCFLAGS  := -O2 -g -std=gnu11 -fPIC -Wall -Wno-unused-function -ffp-contract=off -Iinclude -I$(HOST)
+
+$(LIBDIR)/host_%.o: $(HOST)/%.c $(HOST)/fi_internal.h include/fiasco.h include/fiasco_b200.h | $(LIBDIR)/.dir
+	gcc $(HCFLAGS) -c $< -o $@
+
+$(LIBDIR)/libfiasco.so: $(HOSTOBJ) $(LIBDIR)/libfiasco_b200.so
+	gcc -shared -o $@ $(HOSTOBJ) -L$(LIBDIR) -lfiasco_b200 -Wl,-rpath,'$$ORIGIN' -lm
+
+# The reference command line front end, compiled UNCHANGED from where it lies, against OUR
+# include/fiasco.h and linked against OUR libfiasco.  Only possible where
+# /root/reference exists; the binary travels to the GPU box with the snapshot.
+REF      ?= /root/reference
+CLI_SRC  := cwfa params binerror getopt getopt1
+.PHONY: cfiasco
+ifneq ($(wildcard $(REF)/bin/cwfa.c),)
+cfiasco: $(LIBDIR)/cfiasco
+$(LIBDIR)/cfiasco: $(addprefix $(REF)/bin/,$(addsuffix .c,$(CLI_SRC))) $(LIBDIR)/libfiasco.so
+	gcc -O2 -w -fcommon -Iinclude -Ioracle/refcfg -I$(REF)/lib -I$(REF)/bin \
+	    -o $@ $(addprefix $(REF)/bin/,$(addsuffix .c,$(CLI_SRC))) \
+	    -L$(LIBDIR) -lfiasco -lfiasco_b200 -Wl,-rpath,'$$ORIGIN' -lm
+else
+cfiasco:
+	@echo "cfiasco: $(REF) not present -- using prebuilt $(LIBDIR)/cfiasco (if any)"
+endif
 
 $(LIBDIR)/.dir:
 	mkdir -p $(LIBDIR) && touch $@

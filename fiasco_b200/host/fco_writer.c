@@ -1,0 +1,579 @@
+/*
+ *  fco_writer.c -- serialises a finished automaton into the FIASCO bit stream (.fco).
+ *
+ *  The stream layout and every coding decision must equal the reference's writer so that
+ *  the files are byte-identical and decodable by the reference dfiasco:
+ *    header / frame header   output/write.c:53-213
+ *    bintree		      output/tree.c:46-190      (breadth first, adaptive binary coder)
+ *    matrices		      output/matrices.c:53-536  (DC column, #edges, index deltas, chroma)
+ *    weights		      output/weights.c:38-200   (per-level adaptive array coder)
+ *  Only what an intra frame without nondeterministic prediction needs is written (the
+ *  flags for ND prediction / tiling are emitted as 0, like the reference does for such a
+ *  frame).
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "fi_internal.h"
+
+#define RICE_K	   8
+#define MIN_PROB   1
+#define MAX_PROB   9
+#define isrange(x) ((x) == FI_RANGE)
+#define usedomain(s, w) ((w)->domain_type [s] & FI_USE_DOMAIN)
+
+void
+fi_write_header (const fi_wfainfo_t *wi, fi_bits_t *out)
+{
+   const char *t;
+
+   for (t = "FIASCO"; *t; t++)
+      fi_put_bits (out, (unsigned char) *t, 8);
+   fi_put_bits (out, '\n', 8);
+   for (t = wi->basis_name; *t; t++)
+      fi_put_bits (out, (unsigned char) *t, 8);
+   fi_put_bits (out, 0, 8);
+
+   fi_write_rice (out, 2, RICE_K);		/* FIASCO_BINFILE_RELEASE */
+   fi_write_rice (out, 1, RICE_K);		/* HEADER_TITLE */
+   for (t = wi->title; t && *t && t - wi->title < FI_MAXSTRLEN - 2; t++)
+      fi_put_bits (out, (unsigned char) *t, 8);
+   fi_put_bits (out, 0, 8);
+   fi_write_rice (out, 2, RICE_K);		/* HEADER_COMMENT */
+   for (t = wi->comment; t && *t && t - wi->comment < FI_MAXSTRLEN - 2; t++)
+      fi_put_bits (out, (unsigned char) *t, 8);
+   fi_put_bits (out, 0, 8);
+   fi_write_rice (out, 0, RICE_K);		/* HEADER_END */
+
+   fi_write_rice (out, wi->max_states, RICE_K);
+   fi_put_bit (out, wi->color ? 1 : 0);
+   fi_write_rice (out, wi->width, RICE_K);
+   fi_write_rice (out, wi->height, RICE_K);
+   if (wi->color)
+      fi_write_rice (out, wi->chroma_max_states, RICE_K);
+   fi_write_rice (out, wi->p_min_level, RICE_K);
+   fi_write_rice (out, wi->p_max_level, RICE_K);
+   fi_write_rice (out, wi->frames, RICE_K);
+   fi_write_rice (out, wi->smoothing, RICE_K);
+
+   fi_put_bits (out, wi->rpf.mantissa_bits - 2, 3);
+   fi_put_bits (out, (unsigned) wi->rpf.range_e, 2);
+   {
+      const fi_rpf_t *pair [3][2] = {{&wi->rpf, &wi->dc_rpf},
+				     {&wi->rpf, &wi->d_rpf},
+				     {&wi->dc_rpf, &wi->d_dc_rpf}};
+      int i;
+
+      for (i = 0; i < 3; i++)
+	 if (pair [i][0]->mantissa_bits != pair [i][1]->mantissa_bits
+	     || pair [i][0]->range != pair [i][1]->range)
+	 {
+	    fi_put_bit (out, 1);
+	    fi_put_bits (out, pair [i][1]->mantissa_bits - 2, 3);
+	    fi_put_bits (out, (unsigned) pair [i][1]->range_e, 2);
+	 }
+	 else
+	    fi_put_bit (out, 0);
+   }
+   if (wi->frames > 1)
+   {
+      fi_write_rice (out, wi->fps, RICE_K);
+      fi_write_rice (out, wi->search_range, RICE_K);
+      fi_put_bit (out, wi->half_pixel ? 1 : 0);
+      fi_put_bit (out, wi->B_as_past_ref ? 1 : 0);
+   }
+   fi_byte_align (out);
+}
+
+/* ---------------------------------------------------------------- bintree ---- */
+
+static void
+write_tree (const fi_wfa_t *wfa, fi_bits_t *out)
+{
+   unsigned *queue = fiasco_calloc (FI_MAXSTATES, sizeof (unsigned));
+   uint8_t  *bits  = fiasco_calloc (FI_MAXSTATES * FI_MAXLABELS, 1);
+   unsigned  last = 1, current, label, total = 0, n;
+   fi_ac_t   ac;
+   uint16_t  sum0 = 1, sum1 = 11;
+   unsigned  scaling;
+
+   /* breadth first order from the root: 1 = inner node, 0 = range */
+   queue [0] = wfa->root_state;
+   for (current = 0; current < last; current++)
+      for (label = 0; label < FI_MAXLABELS; label++)
+      {
+	 const int into = wfa->tree [queue [current]][label];
+
+	 if (!isrange (into))
+	 {
+	    queue [last++] = (unsigned) into;
+	    bits [total++] = 1;
+	 }
+	 else
+	    bits [total++] = 0;
+      }
+   if (total != (wfa->states - wfa->basis_states) * FI_MAXLABELS)
+      fi_error ("total [%d] != (states - basis_states) * 2 [%d]", total,
+		(wfa->states - wfa->basis_states) * FI_MAXLABELS);
+
+   /* adaptive binary interval coder, counts (1, 11), halved beyond total / 20 */
+   scaling = total / 20;
+   fi_ac_init (&ac, out);
+   for (n = 0; n < total; n++)
+   {
+      const unsigned range = (unsigned) (ac.high - ac.low) + 1;
+
+      if (!bits [n])
+      {
+	 ac.high = (uint16_t) (ac.low + (uint16_t) ((range * sum0) / sum1 - 1));
+	 fi_ac_rescale (&ac);
+	 sum0++;
+      }
+      else
+      {
+	 ac.low = (uint16_t) (ac.low + (uint16_t) ((range * sum0) / sum1));
+	 fi_ac_rescale (&ac);
+      }
+      sum1++;
+      if (sum1 > scaling)
+      {
+	 sum0 >>= 1;
+	 sum1 >>= 1;
+	 if (!sum0)
+	    sum0 = 1;
+	 if (sum0 >= sum1)
+	    sum1 = (uint16_t) (sum0 + 1);
+      }
+   }
+   fi_ac_flush (&ac);
+   free (queue);
+   free (bits);
+}
+
+/* --------------------------------------------------------------- matrices ---- */
+
+/* quasi arithmetic coder state used for the sparse 0/1 columns: the probability of the
+   '1' symbol is 2^-prob[index], index walks up on '0' and is halved on '1' */
+typedef struct qac
+{
+   fi_ac_t  ac;
+   unsigned index;
+} qac_t;
+
+static unsigned prob_table [1 << (MAX_PROB + 1)];
+
+static void
+init_prob_table (void)
+{
+   unsigned index = 0, n, e;
+
+   for (n = MIN_PROB; n <= MAX_PROB; n++)
+      for (e = 0; e < 1u << n; e++, index++)
+	 prob_table [index] = n;
+}
+
+static void
+qac_encode (qac_t *q, int one)
+{
+   fi_ac_t *ac = &q->ac;
+
+   if (!one)
+   {
+      ac->high = (uint16_t) (ac->high - ((ac->high - ac->low) >> prob_table [q->index]) - 1);
+      fi_ac_rescale (ac);
+      if (q->index < 1020)
+	 q->index++;
+   }
+   else
+   {
+      ac->low = (uint16_t) (ac->high - ((ac->high - ac->low) >> prob_table [q->index]));
+      fi_ac_rescale (ac);
+      q->index >>= 1;
+   }
+}
+
+static unsigned
+n_edges (const fi_wfa_t *wfa, unsigned state, unsigned label)
+{
+   unsigned e = 0;
+
+   while (wfa->into [state][label][e] != FI_NO_EDGE)
+      e++;
+   return e;
+}
+
+/* which ranges use the DC domain (state 0): one QAC bit per range of the luminance part */
+static unsigned
+column_0_encoding (const fi_wfa_t *wfa, unsigned last_row, fi_bits_t *out)
+{
+   qac_t    q;
+   unsigned row, label, total = 0;
+
+   fi_ac_init (&q.ac, out);
+   q.index = 0;
+   for (row = wfa->basis_states; row <= last_row; row++)
+      for (label = 0; label < FI_MAXLABELS; label++)
+	 if (isrange (wfa->tree [row][label]))
+	 {
+	    const int one = wfa->into [row][label][0] == 0;
+
+	    qac_encode (&q, one);
+	    total += (unsigned) one;
+	 }
+   fi_ac_flush (&q.ac);
+   return total;
+}
+
+/* ranges in coder order with the largest domain each of them could refer to
+   (codec/wfalib.c:659-696, including the slot reuse for a subdivided label 0) */
+typedef struct range_list
+{
+   uint16_t *state, *max_domain;
+   uint8_t  *label, *subdivided;
+   unsigned  n;
+} range_list_t;
+
+static void
+sort_ranges (unsigned state, unsigned *domain, range_list_t *rs, const fi_wfa_t *wfa)
+{
+   unsigned label;
+
+   for (label = 0; label < FI_MAXLABELS; label++)
+   {
+      if (isrange (wfa->tree [state][label]))
+	 rs->subdivided [rs->n] = 0;
+      else
+      {
+	 sort_ranges ((unsigned) wfa->tree [state][label], domain, rs, wfa);
+	 rs->subdivided [rs->n] = 1;
+      }
+      rs->state [rs->n]	     = (uint16_t) state;
+      rs->label [rs->n]	     = (uint8_t) label;
+      rs->max_domain [rs->n] = (uint16_t) *domain;
+      while (!usedomain (rs->max_domain [rs->n], wfa))
+	 rs->max_domain [rs->n]--;
+      if (label == 1 || !rs->subdivided [rs->n])
+	 rs->n++;
+   }
+   (*domain)++;
+}
+
+static unsigned
+delta_encoding (int use_normal_domains, int use_delta_domains, const fi_wfa_t *wfa,
+		unsigned last_domain, fi_bits_t *out)
+{
+   range_list_t rs;
+   unsigned	max_domain, total = 0;
+   unsigned	count [FI_MAXEDGES + 1];
+   unsigned	state, label, n, M = 0, range;
+   const size_t slots = (size_t) (last_domain + 1) * FI_MAXLABELS;
+
+   rs.state	 = fiasco_calloc (slots, sizeof (uint16_t));
+   rs.max_domain = fiasco_calloc (slots, sizeof (uint16_t));
+   rs.label	 = fiasco_calloc (slots, 1);
+   rs.subdivided = fiasco_calloc (slots, 1);
+   rs.n		 = 0;
+   max_domain	 = wfa->basis_states - 1;
+   sort_ranges (last_domain, &max_domain, &rs, wfa);
+
+   /* distribution of the number of edges per range, then the numbers themselves with a
+      static model built from that distribution */
+   for (n = 0; n < FI_MAXEDGES + 1; n++)
+      count [n] = 0;
+   for (state = wfa->basis_states; state <= last_domain; state++)
+      for (label = 0; label < FI_MAXLABELS; label++)
+	 if (isrange (wfa->tree [state][label]))
+	 {
+	    const unsigned e = n_edges (wfa, state, label);
+
+	    count [e]++;
+	    if (e > M)
+	       M = e;
+	 }
+   fi_write_rice (out, M, 3);
+   for (n = 0; n <= M; n++)
+      fi_write_rice (out, count [n], (unsigned) ((int) log2 ((double) last_domain) - 2));
+   {
+      /* static order-0 model: cumulative counts, symbol s owns [cum[s], cum[s+1]) */
+      unsigned cum [FI_MAXEDGES + 2];
+      fi_ac_t  ac;
+
+      cum [0] = 0;
+      for (n = 0; n <= M; n++)
+	 cum [n + 1] = cum [n] + count [n];
+      fi_ac_init (&ac, out);
+      for (range = 0; range < rs.n; range++)
+	 if (!rs.subdivided [range])
+	 {
+	    const unsigned e	 = n_edges (wfa, rs.state [range], rs.label [range]);
+	    const unsigned width = (unsigned) (ac.high - ac.low) + 1;
+	    const uint16_t scale = (uint16_t) cum [M + 1];
+	    const uint16_t lo	 = (uint16_t) cum [e], hi = (uint16_t) cum [e + 1];
+
+	    ac.high = (uint16_t) (ac.low + (uint16_t) ((width * hi) / scale - 1));
+	    ac.low  = (uint16_t) (ac.low + (uint16_t) ((width * lo) / scale));
+	    fi_ac_rescale (&ac);
+	 }
+      fi_ac_flush (&ac);
+   }
+
+   /* the domain indices: ascending per range, coded as differences with an adjusted
+      binary code whose alphabet shrinks to what is still possible */
+   {
+      uint16_t *mapping1 = fiasco_calloc (wfa->states, sizeof (uint16_t));
+      uint16_t *mapping2 = fiasco_calloc (wfa->states, sizeof (uint16_t));
+      unsigned	n1 = 0, n2 = 0;
+
+      fi_put_bit (out, (unsigned) use_normal_domains);
+      fi_put_bit (out, (unsigned) use_delta_domains);
+      /* no delta states on an intra frame without prediction: both mappings count the
+	 usable domains below each state */
+      for (state = 0; state < wfa->states; state++)
+      {
+	 mapping1 [state] = (uint16_t) n1;
+	 if (usedomain (state, wfa))
+	    n1++;
+	 mapping2 [state] = (uint16_t) n2;
+	 if (usedomain (state, wfa)
+	     && (state < wfa->basis_states || use_normal_domains))
+	    n2++;
+      }
+      for (range = 0; range < rs.n; range++)
+	 if (!rs.subdivided [range])
+	 {
+	    const unsigned st	     = rs.state [range], lb = rs.label [range];
+	    const unsigned max_value = mapping1 [rs.max_domain [range]];
+	    unsigned	   last	     = 1, edge;
+	    int		   domain;
+
+	    for (edge = 0; (domain = wfa->into [st][lb][edge]) != FI_NO_EDGE; edge++)
+	       if (domain > 0)
+	       {
+		  total++;
+		  if (max_value - last)
+		  {
+		     fi_write_bin_code (out, mapping1 [domain] - last, max_value - last);
+		     last = mapping1 [domain] + 1u;
+		  }
+	       }
+	 }
+      free (mapping1);
+      free (mapping2);
+   }
+   free (rs.state);
+   free (rs.max_domain);
+   free (rs.label);
+   free (rs.subdivided);
+   return total;
+}
+
+static int
+cmp_hits (const void *a, const void *b)
+{
+   /* descending by hit count (lib/misc.c sort_desc_pair) */
+   return (int) ((const int16_t *) b) [0] - (int) ((const int16_t *) a) [0];
+}
+
+static int
+cmp_word (const void *a, const void *b)
+{
+   return (int) *(const int16_t *) a - (int) *(const int16_t *) b;
+}
+
+/* the n most referenced states among the luminance states (codec/wfalib.c:182-231) */
+static int16_t *
+compute_hits (unsigned from, unsigned to, unsigned n, const fi_wfa_t *wfa)
+{
+   int16_t (*hits) [2] = fiasco_calloc (to, sizeof *hits);	/* {key, value} */
+   int16_t *domains;
+   unsigned state, label, edge;
+   int	    domain;
+
+   for (domain = 0; domain < (int) to; domain++)
+   {
+      hits [domain][0] = 0;
+      hits [domain][1] = (int16_t) domain;
+   }
+   for (state = from; state <= to; state++)
+      for (label = 0; label < FI_MAXLABELS; label++)
+	 for (edge = 0; (domain = wfa->into [state][label][edge]) != FI_NO_EDGE; edge++)
+	    hits [domain][0]++;
+   qsort (hits + 1, to - 1, sizeof *hits, cmp_hits);
+   if (n > to)
+      n = to;
+   domains = fiasco_calloc (n + 1, sizeof (int16_t));
+   for (domain = 0; domain < (int) n && (!domain || hits [domain][0]); domain++)
+      domains [domain] = hits [domain][1];
+   n = (unsigned) domain;
+   qsort (domains, n, sizeof (int16_t), cmp_word);
+   domains [n] = -1;
+   free (hits);
+   return domains;
+}
+
+static unsigned
+chroma_encoding (const fi_wfa_t *wfa, fi_bits_t *out)
+{
+   const unsigned y_root = (unsigned) wfa->tree [wfa->tree [wfa->root_state][0]][0];
+   int16_t	 *y_domains = compute_hits (wfa->basis_states, y_root,
+					    wfa->info->chroma_max_states, wfa);
+   qac_t	  q;
+   unsigned	  domain, row, label, total = 0, next_index = 0;
+
+   fi_ac_init (&q.ac, out);
+   q.index = 0;
+   /* one column per admitted domain; the probability index restarts for every column
+      at the value it had after the first row of the previous column */
+   for (domain = 0; y_domains [domain] != -1; domain++)
+   {
+      int save_index = 1;
+
+      q.index = next_index;
+      for (row = y_root + 1; row < wfa->states; row++)
+      {
+	 for (label = 0; label < FI_MAXLABELS; label++)
+	    if (isrange (wfa->tree [row][label]))
+	    {
+	       unsigned edge;
+	       int	into, match = 0;
+
+	       for (edge = 0; (into = wfa->into [row][label][edge]) != FI_NO_EDGE
+			      && (unsigned) into < row; edge++)
+		  if (into == y_domains [domain] && into != wfa->y_state [row][label])
+		     match = 1;
+	       qac_encode (&q, match);
+	       total += (unsigned) match;
+	    }
+	 if (save_index)
+	 {
+	    next_index = q.index;
+	    save_index = 0;
+	 }
+      }
+   }
+   /* the extra column: does the range refer to the state at the same position in Y? */
+   q.index = 0;
+   for (row = y_root + 1; row < wfa->states; row++)
+      for (label = 0; label < FI_MAXLABELS; label++)
+      {
+	 const int one = wfa->y_column [row][label] != 0;
+
+	 qac_encode (&q, one);
+	 total += (unsigned) one;
+      }
+   fi_ac_flush (&q.ac);
+   free (y_domains);
+   return total;
+}
+
+static unsigned
+write_matrices (int use_normal_domains, int use_delta_domains, const fi_wfa_t *wfa,
+		fi_bits_t *out)
+{
+   const unsigned root = wfa->info->color
+			 ? (unsigned) wfa->tree [wfa->tree [wfa->root_state][0]][0]
+			 : wfa->root_state;
+   unsigned total;
+
+   total  = column_0_encoding (wfa, root, out);
+   total += delta_encoding (use_normal_domains, use_delta_domains, wfa, root, out);
+   if (wfa->info->color)
+      total += chroma_encoding (wfa, out);
+   return total;
+}
+
+/* ---------------------------------------------------------------- weights ---- */
+
+static void
+write_weights (unsigned total, const fi_wfa_t *wfa, fi_bits_t *out)
+{
+   unsigned  state, label, offset1, offset2, offset3, i;
+   unsigned *weights = fiasco_calloc (total, sizeof (unsigned));
+   unsigned *levels  = fiasco_calloc (total, sizeof (unsigned));
+   unsigned *c_symbols;
+   unsigned  n = 0;
+   int	     min_level = FI_MAXLEVEL, max_level = 0, dc = 0;
+
+   for (state = wfa->basis_states; state < wfa->states; state++)
+      for (label = 0; label < FI_MAXLABELS; label++)
+	 if (isrange (wfa->tree [state][label]))
+	 {
+	    const int l = (int) wfa->level_of_state [state] - 1;
+
+	    if (l < min_level)
+	       min_level = l;
+	    if (l > max_level)
+	       max_level = l;
+	    if (wfa->into [state][label][0] == 0)
+	       dc = 1;
+	 }
+   if (min_level > max_level)
+      max_level = min_level - 1;
+   /* contexts: [0] DC weights, then one per range level (no delta contexts on an
+      intra frame; their level interval is empty: d_max = d_min - 1) */
+   offset1 = dc ? 1 : 0;
+   offset2 = offset1;
+   offset3 = offset2 + (unsigned) (max_level - min_level + 1);
+
+   for (state = wfa->basis_states; state < wfa->states; state++)
+      for (label = 0; label < FI_MAXLABELS; label++)
+	 if (isrange (wfa->tree [state][label]))
+	 {
+	    unsigned edge;
+	    int	     domain;
+
+	    for (edge = 0; (domain = wfa->into [state][label][edge]) != FI_NO_EDGE; edge++)
+	    {
+	       if (n >= total)
+		  fi_error ("Can't write more than %d weights.", total);
+	       if (domain)
+	       {
+		  weights [n] = (unsigned) fi_rtob (wfa->weight [state][label][edge],
+						    &wfa->info->rpf);
+		  levels [n]  = offset2 + (unsigned) ((int) wfa->level_of_state [state]
+						      - 1 - min_level);
+	       }
+	       else
+	       {
+		  weights [n] = (unsigned) fi_rtob (wfa->weight [state][label][edge],
+						    &wfa->info->dc_rpf);
+		  levels [n]  = 0;
+	       }
+	       n++;
+	    }
+	 }
+   c_symbols	 = fiasco_calloc (offset3 ? offset3 : 1, sizeof (unsigned));
+   c_symbols [0] = 1u << (wfa->info->dc_rpf.mantissa_bits + 1);
+   for (i = offset2; i < offset3; i++)
+      c_symbols [i] = 1u << (wfa->info->rpf.mantissa_bits + 1);
+   fi_encode_array (out, weights, levels, c_symbols, offset3, total, 500);
+   free (c_symbols);
+   free (weights);
+   free (levels);
+}
+
+/* ------------------------------------------------------------------ frame ---- */
+
+void
+fi_write_next_wfa (const fi_wfa_t *wfa, unsigned frame_number, int first,
+		   int normal_domains, int delta_domains, fi_bits_t *out)
+{
+   unsigned edges;
+
+   if (!prob_table [0])
+      init_prob_table ();
+   if (first)
+      fi_write_header (wfa->info, out);
+   fi_write_rice (out, wfa->states, RICE_K);
+   fi_write_rice (out, 0, RICE_K);		/* frame type: I_FRAME */
+   fi_write_rice (out, frame_number, RICE_K);
+   fi_byte_align (out);
+   fi_put_bit (out, 0);				/* no tiling permutation */
+   fi_byte_align (out);
+   write_tree (wfa, out);
+   fi_put_bit (out, 0);				/* no nondeterministic prediction */
+   edges = write_matrices (normal_domains, delta_domains, wfa, out);
+   if (edges)
+      write_weights (edges, wfa, out);
+}

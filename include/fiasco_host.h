@@ -1,0 +1,48 @@
+/*
+ *  fiasco_host.h -- host-side helpers of libfiasco (B200 build) that sit between the C ABI
+ *  of the GPU path (fiasco_b200.h) and the FIASCO stream format: serialise automata that
+ *  fb200_encode_tiles() returned.  fiasco_coder() uses exactly this internally; callers
+ *  that drive the GPU path themselves (tile-split mode: one independent FIASCO stream per
+ *  tile) use it to obtain ordinary .fco files that the reference dfiasco
+ *  decodes.
+ */
+#ifndef FIASCO_HOST_H
+#define FIASCO_HOST_H
+
+#include "fiasco_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* stream-level parameters that are not part of the automaton (reference wfa_info_t,
+   codec/wfa.h:86-110, as far as an intra stream needs them) */
+typedef struct fiasco_stream_info
+{
+   int	       width, height, color;
+   unsigned    max_states;		/* as written in the header (min (dictionary, 6000)) */
+   unsigned    chroma_max_states;
+   unsigned    p_min_level, p_max_level;
+   unsigned    smoothing;		/* 70 */
+   unsigned    fps;			/* 25 */
+   int	       rpf_mantissa, rpf_range_e, dc_rpf_mantissa, dc_rpf_range_e;
+   const char *title, *comment;		/* may be NULL */
+} fiasco_stream_info_t;
+
+/* defaults of the reference command line front end for a stream coded with params 'p'
+   (bin/cwfa.c:36-90, codec/coder.c:285-296) */
+void fiasco_stream_info_init (fiasco_stream_info_t *info, const fb200_params_t *p);
+
+/*
+ *  Write n_frames intra automata (one per frame, same geometry) as one FIASCO stream to
+ *  'filename' ("-" = stdout; searched like the coder's output name).  Returns 1 on
+ *  success, 0 on failure (text from fiasco_get_error_message()).  The bytes equal what
+ *  the reference coder writes for the same automata (output/write.c:53).
+ */
+int fiasco_write_stream (const char *filename, const fiasco_stream_info_t *info,
+			 const fb200_wfa_t *frames, int n_frames);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

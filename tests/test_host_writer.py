@@ -1,0 +1,101 @@
+"""Host side of libfiasco (product code, CPU): the .fco writer must be byte-identical to the
+reference's.  Input automata come from the oracle (itself pinned to the reference), the expected
+md5 of the stream from the reference binary (tests/golden/manifest.json).  Also checks that the
+public API of include/fiasco.h / fiasco_host.h is exported and behaves like the reference's."""
+import ctypes as C
+import hashlib
+import os
+import re
+
+import pytest
+
+from fiasco_b200 import ffi, hostlib
+import oracle_lib as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("name", ["g256_q20_z0", "g256_q20_z1", "g256_q20_z2", "g512_q20_z0", "g1024t0_q20_z0",
+                                  "g1024t15_q20_z0", "g1024r_q20_z0", "g1024s_q40_z0", "g4096t0_q20_z0",
+                                  "c256_q20_z0", "c256_q30_z0", "c2048t0_q30_z0"])
+def test_writer_is_byte_identical_to_reference(name, tmp_path):
+    m = O.manifest()[name]
+    img = O.case_image(name)
+    w = O.encode(img, quality=m["quality"], optimize=m["optimize"])
+    p = ffi.make_params(m["width"], m["height"], 3 if m["color"] else 1, float(m["quality"]), m["optimize"])
+    out = str(tmp_path / (name + ".fco"))
+    hostlib.write_stream(out, p, [w])
+    data = open(out, "rb").read()
+    assert len(data) == m["fco_bytes"]
+    assert hashlib.md5(data).hexdigest() == m["fco_md5"]
+
+
+def test_full_frame_stream_1024(tmp_path):
+    name = "g1024_q20_z0"
+    m = O.manifest()[name]
+    w = O.encode(O.case_image(name), quality=20, optimize=0)
+    out = str(tmp_path / "g1024.fco")
+    hostlib.write_stream(out, ffi.make_params(1024, 1024, 1, 20.0, 0), [w])
+    assert hashlib.md5(open(out, "rb").read()).hexdigest() == m["fco_md5"]   # c5f96a1d...
+
+
+def test_public_api_exports():
+    L = hostlib.load()
+    for header in ("fiasco.h", "fiasco_host.h"):
+        txt = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", header)).read(), flags=re.S)
+        names = set(re.findall(r"\b(fiasco_[a-z0-9_]+)\s*\(", txt))
+        assert names, header
+        for n in names:
+            assert hasattr(L, n), "missing export " + n
+    # the two extra symbols the reference CLI links
+    assert hasattr(L, "fiasco_calloc") and hasattr(L, "open_file") and hasattr(L, "fiasco_free")
+
+
+def test_option_setters_follow_reference_contract():
+    L = hostlib.load()
+    o = L.fiasco_c_options_new()
+    assert L.fiasco_c_options_set_optimizations(o, 6, 10, 3, 10000, 0) == 1
+    assert L.fiasco_c_options_set_optimizations(o, 3, 10, 3, 10000, 0) == 0
+    assert "at least level 4" in hostlib.error_message()
+    assert L.fiasco_c_options_set_optimizations(o, 8, 6, 3, 10000, 0) == 0
+    assert L.fiasco_c_options_set_quantization(o, 9, 2, 5, 1) == 0
+    assert "[2,8]" in hostlib.error_message()
+    assert L.fiasco_c_options_set_frame_pattern(o, b"ixp") == 0
+    assert "invalid character `x'" in hostlib.error_message()
+    assert L.fiasco_c_options_set_frame_pattern(o, b"IbP") == 1
+    assert L.fiasco_c_options_set_smoothing(o, 101) == 0
+    assert L.fiasco_c_options_set_chroma_quality(o, 0.0, 40) == 0
+    assert L.fiasco_c_options_set_prediction(o, 0, 5, 10) == 0
+    assert L.fiasco_c_options_set_tiling(o, 7, 4) == 0
+    L.fiasco_c_options_delete(o)
+
+
+def test_coder_errors_return_zero_with_message(tmp_path):
+    ok, msg = hostlib.coder([str(tmp_path / "missing.pgm")], str(tmp_path / "o.fco"))
+    assert not ok and "missing.pgm" in msg
+    ok, msg = hostlib.coder([str(tmp_path / "missing.pgm")], str(tmp_path / "o.fco"), quality=0.0)
+    assert not ok and "positive" in msg
+
+
+def test_coder_refuses_without_gpu(tmp_path):
+    """fiasco_coder() has no CPU fallback: on a box without a CUDA device it fails loudly."""
+    import fiasco_b200 as F
+    if F.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    import gen_frames
+    p = str(tmp_path / "g.pgm")
+    gen_frames.write_pnm(p, gen_frames.frame("g256")[:64, :64])
+    ok, msg = hostlib.coder([p], str(tmp_path / "o.fco"))
+    assert not ok and "CUDA" in msg
+
+
+def test_cfiasco_links_unchanged():
+    """The reference CLI (compiled unchanged from /root/reference/bin) links against our library."""
+    exe = os.path.join(ROOT, "fiasco_b200", "lib", "cfiasco")
+    assert os.path.exists(exe), "run `make product` where /root/reference is available"
+    import subprocess
+    out = subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
+    assert "libfiasco.so" in out and "libfiasco_b200.so" in out
+    sy = subprocess.run(["nm", "-D", "--undefined-only", exe], capture_output=True, text=True).stdout
+    for s in ("fiasco_coder", "fiasco_c_options_new", "fiasco_c_options_set_optimizations", "fiasco_calloc", "open_file"):
+        assert s in sy
