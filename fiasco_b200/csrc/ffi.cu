@@ -198,10 +198,10 @@ derive (const fb200_params_t *p, DevParams *d, char *err, size_t errlen)
       set_err (err, errlen, "parameters outside the supported range");
       return FB200_EINVAL;
    }
-   if (p->bands != 1)
+   if (p->bands != 1 && p->bands != 3)
    {
-      set_err (err, errlen, "colour bands are not implemented on the device yet");
-      return FB200_EUNSUPPORTED;
+      set_err (err, errlen, "bands must be 1 (grey) or 3 (Y, Cb, Cr)");
+      return FB200_EINVAL;
    }
    d->width  = p->width;
    d->height = p->height;

@@ -243,6 +243,8 @@ struct ShHdr
    int	    band;
    float    ret_costs;
    float    price;		/* price of the current band */
+   unsigned y_states;		/* states at the end of the luminance band */
+   int	    lc_min;		/* current lc_min_level (raised for the chroma bands, coder.c:785-797) */
    unsigned states;		/* wfa->states */
    unsigned tree_counts [FB200_MAXLEVEL];
    unsigned tree_total [FB200_MAXLEVEL];
@@ -680,7 +682,7 @@ cta_init_range (const DevParams &P, const TileWs &W, const Sh &sh, unsigned x0,
    {
       unsigned ns = 0;
       /* need_image states: all states inside the image; count for the byte model */
-      ns = sh.h->states;
+      ns = band ? sh.h->y_states : sh.h->states;
       sh.h->blocks++;
       sh.h->ip_bytes += 4ull * size + 4ull * (63 + (unsigned) ((1 << (P.lc_max - P.il)) - 1)) * ns;
    }
@@ -2035,7 +2037,7 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 	    }
 	    if (tid == 0)
 	    {
-	       if (level > P.lc_min)
+	       if (level > h->lc_min)
 	       {
 		  /* alternative 2: recursive subdivision (subdivide.c:243-272) */
 		  F.r_tree_bits	   = t0_tree_bits (h, 1, level);
@@ -2184,6 +2186,112 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 }
 
 /*****************************************************************************
+	      colour: chroma dictionary and virtual root states (thread 0)
+*****************************************************************************/
+
+/*
+ *  Before the Cb band (codec/coder.c:776-800): shrink the pool to the chroma_max_states
+ *  most referenced luminance states -- rle_chroma (domain-pool.c:854-879) with
+ *  compute_hits (wfalib.c:182-231): state 0 first, then by hit count descending (ties in
+ *  ascending state order, the order a stable sort of the reference's hit list gives),
+ *  stopping at the first unreferenced state; the survivors sorted by state number -- and
+ *  raise lc_min_level to the finest level the luminance used.  'hits' is block-wide
+ *  scratch of at least 'states' ints.
+ */
+__device__ void
+t0_chroma_setup (const DevParams &P, const TileWs &W, const Sh &sh, int *hits)
+{
+   ShHdr	 *h	 = sh.h;
+   const unsigned states = h->states;
+   unsigned	  max_domains = (unsigned) P.chroma_max_states;
+   const unsigned n_pool = BLOB_U16 (sh, MB_N);
+
+   if (max_domains < n_pool)
+   {
+      const unsigned from = 3, to = states - 1;
+      unsigned	     n	  = max_domains < to ? max_domains : to;
+      unsigned	     cnt  = 1;
+
+      for (unsigned d = 0; d < to; d++)
+	 hits [d] = 0;
+      for (unsigned s = from; s <= to; s++)
+	 for (int label = 0; label < 2; label++)
+	 {
+	    const short *in = W.into + (size_t) (2 * s + label) * 6;
+	    for (int e = 0; in [e] != FB_NO_EDGE; e++)
+	       hits [in [e]]++;
+	 }
+      /* selection in the order of the stable descending sort; chosen entries are
+	 marked by a negative count */
+      sh.pool [0] = 0;
+      while (cnt < n)
+      {
+	 int best = -1, bestkey = 0;
+	 for (unsigned d = 1; d < to; d++)
+	    if (hits [d] > bestkey)
+	    {
+	       best    = (int) d;
+	       bestkey = hits [d];
+	    }
+	 if (best < 0)
+	    break;
+	 hits [best] = -1;
+	 cnt++;
+      }
+      /* ascending state order */
+      cnt = 1;
+      for (unsigned d = 1; d < to; d++)
+	 if (hits [d] < 0)
+	    sh.pool [cnt++] = (short) d;
+      BLOB_U16 (sh, MB_N) = (unsigned short) cnt;
+   }
+   BLOB_U16 (sh, MB_YINDEX) = 0;
+   BLOB_U16 (sh, MB_MAXDOM) = BLOB_U16 (sh, MB_N);
+
+   /* don't partition the chroma bands finer than the luminance band */
+   {
+      unsigned min_level = FB200_MAXLEVEL;
+
+      for (unsigned s = 3; s < states; s++)
+	 if (W.tree [2 * s] == FB_RANGE || W.tree [2 * s + 1] == FB_RANGE)
+	 {
+	    const unsigned l = (unsigned) W.level_of_state [s] - 1;
+	    if (l < min_level)
+	       min_level = l;
+	 }
+      h->lc_min = (int) min_level;
+   }
+   h->y_states = states;
+}
+
+/* thread 0: a virtual state whose two children are given states (coder.c:821-848) */
+__device__ int
+t0_virtual_state (const DevParams &P, const TileWs &W, ShHdr *h, int child0, int child1,
+		  int level)
+{
+   const unsigned s = h->states;
+
+   for (int label = 0; label < 2; label++)
+   {
+      W.tree [2 * s + label]	 = (short) (label ? child1 : child0);
+      W.y_state [2 * s + label]	 = FB_RANGE;
+      W.x [2 * s + label]	 = 0;
+      W.y [2 * s + label]	 = 0;
+      W.y_column [2 * s + label] = 0;
+      W.into [(size_t) (2 * s + label) * 6] = FB_NO_EDGE;
+   }
+   W.final_d [s]	= t0_final_distribution (W, s);
+   W.level_of_state [s] = (uint8_t) level;
+   W.domain_type [s]	= 0;
+   h->states		= s + 1;
+   if (s + 1 >= FB200_MAXSTATES)
+      h->status = FB200_EMAXSTATES;
+   else if (s + 1 >= (unsigned) P.s_cap)
+      h->status = FB200_ECAPACITY;
+   return (int) s;
+}
+
+/*****************************************************************************
 				the kernel
 *****************************************************************************/
 
@@ -2260,24 +2368,59 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
       __syncthreads ();
    }
 
-   /* grey: one band */
-   cta_subdivide_band<NT> (P, W, sh, 0, FB_RANGE);
+   /* the bands of the frame, one subdivide() pass each (coder.c:738-849) */
+   int band_tree [3] = {FB_RANGE, FB_RANGE, FB_RANGE};
+   int ycb_node	     = -1;
+
+   if (tid == 0)
+      h->lc_min = P.lc_min;
+   __syncthreads ();
+   for (int band = 0; band < P.bands && h->status == FB200_OK; band++)
+   {
+      if (band == 1)
+      {
+	 if (tid == 0)
+	    t0_chroma_setup (P, W, sh, (int *) sh.bnd);
+	 __syncthreads ();
+      }
+      cta_subdivide_band<NT> (P, W, sh, band, band ? band_tree [0] : FB_RANGE);
+      if (h->status != FB200_OK)
+	 break;
+      band_tree [band] = h->root.tree;
+      if (tid == 0)
+      {
+	 TileResult *r = W.result;
+
+	 if (h->root.tree == FB_RANGE)
+	    h->status = FB200_ENOROOT;
+	 r->costs [band]	= h->ret_costs;
+	 r->err [band]		= h->root.err;
+	 r->tree_bits [band]	= h->root.tree_bits;
+	 r->matrix_bits [band]	= h->root.matrix_bits;
+	 r->weights_bits [band] = h->root.weights_bits;
+	 if (band == 1 && h->status == FB200_OK)
+	    h->w.index = t0_virtual_state (P, W, h, band_tree [0], band_tree [1], P.level + 1);
+      }
+      __syncthreads ();
+      if (band == 1)
+	 ycb_node = h->w.index;
+   }
+   if (P.bands == 3 && tid == 0 && h->status == FB200_OK)
+   {
+      const int cr = t0_virtual_state (P, W, h, band_tree [2], FB_RANGE, P.level + 1);
+      if (h->status == FB200_OK)
+	 h->root.tree = (short) t0_virtual_state (P, W, h, ycb_node, cr, P.level + 2);
+   }
+   __syncthreads ();
 
    if (tid == 0)
    {
       TileResult *r = W.result;
 
-      if (h->status == FB200_OK && h->root.tree == FB_RANGE)
-	 h->status = FB200_ENOROOT;
       r->status	      = h->status;
       r->states	      = h->states;
       r->basis_states = 3;
       r->root_state   = h->root.tree >= 0 ? (unsigned) h->root.tree : 0;
-      r->costs [0]	  = h->ret_costs;
-      r->err [0]	  = h->root.err;
-      r->tree_bits [0]	  = h->root.tree_bits;
-      r->matrix_bits [0]  = h->root.matrix_bits;
-      r->weights_bits [0] = h->root.weights_bits;
       r->trace_len = h->trace_len;
       r->mp_calls  = h->mp_calls;
       r->mp_steps  = h->mp_steps;

@@ -35,6 +35,17 @@ def test_fiasco_coder_stream_md5(name, tmp_path):
     assert md5(out) == m["fco_md5"]
 
 
+@pytest.mark.parametrize("name", ["c256_q20_z0", "c256_q30_z0", "c2048t0_q30_z0"])
+def test_fiasco_coder_colour_stream_md5(name, tmp_path):
+    m = O.manifest()[name]
+    pnm = str(tmp_path / (name + ".ppm"))
+    gen_frames.write_pnm(pnm, O.case_image(name))
+    out = str(tmp_path / (name + ".fco"))
+    ok, msg = hostlib.coder([pnm], out, quality=float(m["quality"]), optimize=m["optimize"])
+    assert ok, msg
+    assert md5(out) == m["fco_md5"]
+
+
 def test_fiasco_coder_1024_md5(tmp_path):
     """BASELINE.json config[1] end to end: same bytes as the reference cfiasco (c5f96a1d...)."""
     name = "g1024_q20_z0"

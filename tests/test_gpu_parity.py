@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 
 def gpu_encode(img, quality=20.0, optimize=0, cap=0, trace=False):
     h, w = img.shape[:2]
-    p = ffi.make_params(w, h, 1, quality, optimize, cap)
+    p = ffi.make_params(w, h, 3 if img.ndim == 3 else 1, quality, optimize, cap)
     enc = F.TileEncoder(p, 1)
     try:
         ws, tr = enc.encode(O.planes_of(img), trace_cap=300000 if trace else 0)
@@ -40,7 +40,7 @@ def trace_line(i, r):
     return s
 
 
-def assert_same_wfa(gw, ow):
+def assert_same_wfa(gw, ow, bands=1):
     assert gw["status"] == 0
     assert gw["states"] == ow["states"]
     assert gw["root_state"] == ow["root_state"]
@@ -48,10 +48,13 @@ def assert_same_wfa(gw, ow):
     n = ow["states"]
     assert np.array_equal(gw["final_distribution"].view(np.uint32), ow["final_distribution"].view(np.uint32))
     assert np.array_equal(gw["domain_type"][:n], ow["domain_type"][:n])
-    assert fb(gw["costs"][0]) == fb(ow["costs"][0])
-    assert fb(gw["err"][0]) == fb(ow["err"][0])
-    for k in ("tree_bits", "matrix_bits", "weights_bits"):
-        assert fb(gw[k][0]) == fb(ow[k][0]), k
+    assert np.array_equal(gw["y_state"][:n], ow["y_state"][:n])
+    assert np.array_equal(gw["y_column"][:n], ow["y_column"][:n])
+    for band in range(bands):
+        assert fb(gw["costs"][band]) == fb(ow["costs"][band])
+        assert fb(gw["err"][band]) == fb(ow["err"][band])
+        for k in ("tree_bits", "matrix_bits", "weights_bits"):
+            assert fb(gw[k][band]) == fb(ow[k][band]), (k, band)
 
 
 # ------------------------------------------------------------------ device arithmetic
@@ -114,6 +117,32 @@ def test_gpu_matches_oracle_trace_and_wfa(frame, x0, y0, w, h, q, z):
         assert a == b, "first divergence at approximate_range call %d" % i
     assert len(olc) == len(glc)
     assert_same_wfa(gw, ow)
+
+
+COLOUR = [("c256", 0, 0, 64, 64, 20, 0), ("c256", 64, 128, 128, 128, 20, 0), ("c256", 0, 0, 256, 256, 20, 0),
+          ("c256", 0, 0, 256, 256, 30, 0), ("c256", 32, 16, 96, 64, 45, 0), ("c256", 0, 0, 128, 128, 20, 1)]
+
+
+@pytest.mark.parametrize("frame,x0,y0,w,h,q,z", COLOUR)
+def test_gpu_colour_matches_oracle(frame, x0, y0, w, h, q, z):
+    """Y, Cb, Cr bands (4:4:4) with the chroma dictionary and the y-state threading."""
+    img = np.ascontiguousarray(gen_frames.frame(frame)[y0:y0 + h, x0:x0 + w])
+    ow = O.encode(img, quality=q, optimize=z, want_trace=True)
+    gw, tr, _ = gpu_encode(img, q, z, trace=True)
+    olc = O.lc_lines(ow["trace"])
+    glc = [trace_line(i, r) for i, r in enumerate(tr)]
+    for i, (a, b) in enumerate(zip(olc, glc)):
+        assert a == b, "first divergence at approximate_range call %d" % i
+    assert len(olc) == len(glc)
+    assert_same_wfa(gw, ow, bands=3)
+
+
+@pytest.mark.parametrize("name", ["c256_q20_z0", "c256_q30_z0", "c2048t0_q30_z0"])
+def test_gpu_colour_matches_reference_golden(name):
+    m = O.manifest()[name]
+    gw, _, _ = gpu_encode(O.case_image(name), m["quality"], m["optimize"])
+    level = O.lib().fo_image_level(m["width"], m["height"])
+    assert O.mask_virtual(F.wfa_lines(gw), level) == O.golden_wfa_lines(name)
 
 
 def test_gpu_flat_and_noise_edge_cases():

@@ -35,7 +35,7 @@ def run_case(img, quality=20.0, optimize=0, label="", cap=0):
     t0 = time.time()
     ow = O.encode(img, quality=quality, optimize=optimize, want_trace=True)
     t1 = time.time()
-    p = ffi.make_params(w, h, 1, quality, optimize, cap)
+    p = ffi.make_params(w, h, 3 if img.ndim == 3 else 1, quality, optimize, cap)
     enc = F.TileEncoder(p, 1)
     gw, tr = enc.encode(O.planes_of(img), trace_cap=200000)
     st = enc.stats()
@@ -87,6 +87,9 @@ def main():
     ]
     if len(sys.argv) > 1 and sys.argv[1] == "big":
         cases = [("g1024", g1024, 20, 0)]
+    if len(sys.argv) > 1 and sys.argv[1] == "colour":
+        c256 = gen_frames.frame("c256")
+        cases = [("c64", c256[0:64, 0:64], 20, 0), ("c128", c256[64:192, 128:256], 20, 0), ("c256", c256, 20, 0)]
     if len(sys.argv) > 1 and sys.argv[1] == "z":
         cases = [("g256z1", gen_frames.frame("g256"), 20, 1), ("g256z2", gen_frames.frame("g256"), 20, 2)]
     allok = True
