@@ -237,6 +237,7 @@ derive (const fb200_params_t *p, DevParams *d, char *err, size_t errlen)
    d->blob_len	   = MB_COUNTS + d->aac_dc_size
 		     + (d->lc_max - d->lc_min + 1) * d->aac_lvl_size;
    d->blob_len	   = (d->blob_len + 7) / 8 * 8;
+   d->big	   = d->s_cap > 768;
    d->first_band   = 0;
    d->last_band	   = p->bands - 1;
    return FB200_OK;
@@ -250,7 +251,7 @@ up256 (size_t x)
 
 /* carve the private tables of one tile out of d_work */
 static size_t
-work_layout (const DevParams &d, size_t *off /* [10] */)
+work_layout (const DevParams &d, size_t *off /* [12] */)
 {
    size_t o = 0, sc = (size_t) d.s_cap;
 
@@ -264,6 +265,8 @@ work_layout (const DevParams &d, size_t *off /* [10] */)
    off [7] = o; o += up256 ((size_t) 2 * FB200_MAXLEVEL * 4);		/* tree_save */
    off [8] = o; o += up256 (sc * 2);					/* pool_save */
    off [9] = o; o += up256 (sc * sizeof (Trans));			/* trans */
+   off [10] = o; o += up256 ((sc + 1) * 4 * FB_MAXEDGES);		/* Gglob */
+   off [11] = o; o += up256 ((sc + 64) * 4);				/* bndglob */
    return o;
 }
 
@@ -328,7 +331,7 @@ ctx_alloc (fb200_ctx_t *c, char *err, size_t errlen)
 	 return FB200_EINVAL;
       }
    }
-   size_t woff [10], aoff [10];
+   size_t woff [12], aoff [10];
    c->work_stride = work_layout (d, woff);
    c->wfa_block	  = wfa_layout (d, aoff);
    c->pix_elems	  = (size_t) d.bands * d.width * d.height;
@@ -366,6 +369,8 @@ ctx_alloc (fb200_ctx_t *c, char *err, size_t errlen)
       w.tree_save = (unsigned *) (wb + woff [7]);
       w.pool_save = (int16_t *) (wb + woff [8]);
       w.trans	  = (Trans *) (wb + woff [9]);
+      w.Gglob	  = (float *) (wb + woff [10]);
+      w.bndglob	  = (float *) (wb + woff [11]);
       w.final_d	       = (float *) (ab + aoff [0]);
       w.weight	       = (float *) (ab + aoff [1]);
       w.into	       = (int16_t *) (ab + aoff [2]);

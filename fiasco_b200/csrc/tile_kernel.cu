@@ -200,7 +200,6 @@ struct Frame			/* one activation record of subdivide() */
    float    r_err, r_tree_bits, r_matrix_bits, r_weights_bits; /* rrange sums */
    RangeRes lrange;
    RangeRes child [2];
-   unsigned tsnap [2 * FB200_MAXLEVEL];	/* tree model at entry (subdivide.c:192) */
 };
 
 struct MpRes			/* mp_t, codec/approx.c:41-51 */
@@ -294,7 +293,7 @@ smem_layout (const DevParams &p, int nt, size_t *off /* [14] */)
    off [0] = o; o += align16 (sizeof (ShHdr));
    off [1] = o; o += align16 (dcap * 4);			/* num */
    off [2] = o; o += align16 (dcap * 4);			/* den */
-   off [3] = o; o += align16 (dcap * 4 * (p.max_elements > 1 ? p.max_elements - 1 : 1)); /* G */
+   off [3] = o; o += p.big ? 0 : align16 (dcap * 4 * (p.max_elements > 1 ? p.max_elements - 1 : 1)); /* G */
    off [4] = o; o += align16 (dcap);				/* used */
    off [5] = o; o += align16 ((size_t) p.s_cap * 2);		/* pool */
    off [6] = o; o += align16 (((size_t) 1 << p.lc_max) * 4);	/* pixels */
@@ -306,8 +305,9 @@ smem_layout (const DevParams &p, int nt, size_t *off /* [14] */)
       /* model snapshots of the DFS stay on chip when they are small (default models:
 	 376 B each), else they live in the tile's global workspace */
       const size_t need = (size_t) (p.level - p.lc_min + 2) * 2 * p.blob_len * 2;
-      off [11] = need <= 24 * 1024 ? o : (size_t) -1;
-      if (need <= 24 * 1024)
+      const bool on_chip = need <= 24 * 1024 && !p.big;
+      off [11] = on_chip ? o : (size_t) -1;
+      if (on_chip)
 	 o += align16 (need);
    }
    off [12] = o; o += align16 ((size_t) (p.aac_dc_size + p.aac_lvl_size) * 8);	/* log2 tables */
@@ -316,7 +316,7 @@ smem_layout (const DevParams &p, int nt, size_t *off /* [14] */)
 }
 
 __device__ __forceinline__ Sh
-carve (unsigned char *base, const DevParams &p, int nt)
+carve (unsigned char *base, const DevParams &p, int nt, float *gglob, float *bndglob)
 {
    size_t off [14];
    Sh	  s;
@@ -325,11 +325,12 @@ carve (unsigned char *base, const DevParams &p, int nt)
    s.h	    = (ShHdr *) (base + off [0]);
    s.num    = (float *) (base + off [1]);
    s.den    = (float *) (base + off [2]);
-   s.G	    = (float *) (base + off [3]);
+   s.G	    = p.big ? gglob : (float *) (base + off [3]);
    s.used   = (unsigned char *) (base + off [4]);
    s.pool   = (short *) (base + off [5]);
    s.pixels = (float *) (base + off [6]);
    s.norm_i = (int *) (base + off [7]);
+   (void) bndglob;
    s.bnd    = (float *) (base + off [8]);
    s.cmask  = (unsigned *) (base + off [9]);
    s.cand   = (int *) (s.cmask + ((size_t) p.s_cap + 1 + 31) / 32);
@@ -571,21 +572,41 @@ cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
 	    TransReg tr;
 
 	    load_trans (W.trans + s, tr);
+	    /* gather indices with the unused slots pointing at entry 0 (always valid): the
+	       loads are unconditional and independent, so several nodes' worth of L2 round
+	       trips overlap; only the additions are predicated (the value stays exact) */
+	    int idx [2][FB_MAXEDGES + 1];
+#pragma unroll
+	    for (int label = 0; label < 2; label++)
+	    {
+	       idx [label][0] = tr.child [label] != FB_RANGE ? tr.child [label] : 0;
+#pragma unroll
+	       for (int e = 0; e < FB_MAXEDGES; e++)
+		  idx [label][e + 1] = tr.into [label][e] != FB_NO_EDGE ? tr.into [label][e] : 0;
+	    }
+#pragma unroll 1
 	    for (unsigned k = 0; k < nn; k++)
 	    {
 	       const unsigned node = node0 + k;
-	       float	      acc  = 0;
+	       float	      v [2][FB_MAXEDGES + 1];
+	       float	      acc = 0;
 #pragma unroll
 	       for (int label = 0; label < 2; label++)
 	       {
 		  const float *src = W.T + (size_t) (2 * node + 1 + label) * scap;
-
+#pragma unroll
+		  for (int e = 0; e < FB_MAXEDGES + 1; e++)
+		     v [label][e] = src [idx [label][e]];
+	       }
+#pragma unroll
+	       for (int label = 0; label < 2; label++)
+	       {
 		  if (tr.child [label] != FB_RANGE)
-		     acc += src [tr.child [label]];
+		     acc += v [label][0];
 #pragma unroll
 		  for (int e = 0; e < FB_MAXEDGES; e++)
 		     if (tr.into [label][e] != FB_NO_EDGE)
-			acc += src [tr.into [label][e]] * tr.w [label][e];
+			acc += v [label][e + 1] * tr.w [label][e];
 	       }
 	       W.T [(size_t) node * scap + s] = acc;
 	    }
@@ -813,7 +834,7 @@ cta_state_products (const DevParams &P, const TileWs &W, const Sh &sh, unsigned 
    ShHdr    *h	  = sh.h;
    const int dcap = sh.dcap;
    /* scratch rows: the pursuit's work arrays are idle while a state is appended */
-   const int NR = 3 + (P.max_elements > 1 ? P.max_elements - 1 : 1);
+   const int NR = P.big ? 3 : 3 + (P.max_elements > 1 ? P.max_elements - 1 : 1);
 
    if (tid == 0)
    {
@@ -1977,6 +1998,7 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 	 {
 	    const int level = F.level;
 	    short    *snap  = (sh.snaps ? sh.snaps : W.snap) + (size_t) depth * 2 * P.blob_len;
+	    unsigned *tsnap = W.treesnap + (size_t) depth * 2 * FB200_MAXLEVEL;
 
 	    if (level == P.lc_max)
 	    {
@@ -1994,8 +2016,8 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 	    {
 	       for (int i = 0; i < FB200_MAXLEVEL; i++)
 	       {
-		  F.tsnap [i]		       = h->tree_counts [i];
-		  F.tsnap [FB200_MAXLEVEL + i] = h->tree_total [i];
+		  tsnap [i]		     = h->tree_counts [i];
+		  tsnap [FB200_MAXLEVEL + i] = h->tree_total [i];
 	       }
 	       F.states_snap = h->states;
 	       /* y states of the children (subdivide.c:172-183) */
@@ -2082,6 +2104,7 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 	 {
 	    const float lin = F.lincomb_costs, sub = F.subdivide_costs;
 	    short      *snap  = (sh.snaps ? sh.snaps : W.snap) + (size_t) depth * 2 * P.blob_len;
+	    unsigned   *tsnap = W.treesnap + (size_t) depth * 2 * FB200_MAXLEVEL;
 
 	    if ((lin >= FB_MAXCOSTS && sub >= FB_MAXCOSTS) || lin < sub)
 	    {
@@ -2094,8 +2117,8 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 	       {
 		  for (int i = 0; i < FB200_MAXLEVEL; i++)
 		  {
-		     h->tree_counts [i] = F.tsnap [i];
-		     h->tree_total [i]	= F.tsnap [FB200_MAXLEVEL + i];
+		     h->tree_counts [i] = tsnap [i];
+		     h->tree_total [i]	= tsnap [FB200_MAXLEVEL + i];
 		  }
 		  h->states = F.states_snap;	/* remove_states (wfalib.c:276-310) */
 		  if (fail)
@@ -2301,7 +2324,7 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
 {
    extern __shared__ __align__ (16) unsigned char smem_raw [];
    const TileWs W   = ws_array [blockIdx.x];
-   const Sh	sh  = carve (smem_raw, P, NT);
+   const Sh	sh  = carve (smem_raw, P, NT, W.Gglob, W.bndglob);
    ShHdr       *h   = sh.h;
    const int	tid = threadIdx.x;
 

@@ -46,6 +46,8 @@ struct DevParams
    int	 aac_dc_size, aac_lvl_size, blob_len;
    int	 trace_cap;
    int	 first_band, last_band; /* bands processed by this launch */
+   int	 big;			/* large state capacity: Gram rows and model snapshots live in
+				   global memory so that more tiles fit on an SM */
 };
 
 /* all transitions of one state in one 64-byte line: what the inner-product kernels gather */
@@ -65,6 +67,8 @@ struct TileWs
    float   *SS;			/* [nlev][s_cap][s_cap]	  state x state products */
    float   *diag;		/* [nlev][s_cap]	  <s,s> */
    Trans   *trans;		/* [s_cap]		  packed transitions */
+   float   *bndglob;		/* [s_cap+32] pass-1 bounds when not in smem */
+   float   *Gglob;		/* [max_elements-1][s_cap+1] Gram-Schmidt rows when not in smem */
    /* automaton */
    float   *final_d;		/* [s_cap] */
    uint8_t *level_of_state;	/* [s_cap] */
