@@ -32,6 +32,8 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 W_ = H_ = 1024
 QUALITY = 20.0
+LAP_NAMES = ["ctrl", "pix", "dots", "upsweep", "enter", "mp_pro", "mp_p1", "mp_waves", "mp_commit", "mp_ortho",
+             "ar_epi", "ap_img", "ap_direct", "ap_staged", "decide"]
 METRIC = "encoder Mpixels/s at fixed PSNR (1024^2 grey, q=20)"
 
 
@@ -283,6 +285,7 @@ def run_ours(args):
         "clocks": clocks,
         "phase_cycles": {k: int(st[k]) for k in ("cyc_total", "cyc_T", "cyc_mp", "cyc_append")},
         "work": {k: int(st[k]) for k in ("mp_calls", "mp_steps", "blocks", "states")},
+        "lap_share": {n: round(v / (float(sum(st["lap"])) or 1.0), 4) for n, v in zip(LAP_NAMES, st["lap"])},
     }
     print(json.dumps(line), flush=True)
     if world > 1:

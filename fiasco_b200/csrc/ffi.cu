@@ -237,7 +237,12 @@ derive (const fb200_params_t *p, DevParams *d, char *err, size_t errlen)
    d->blob_len	   = MB_COUNTS + d->aac_dc_size
 		     + (d->lc_max - d->lc_min + 1) * d->aac_lvl_size;
    d->blob_len	   = (d->blob_len + 7) / 8 * 8;
-   d->big	   = d->s_cap > 768;
+   d->big	   = d->s_cap > 768 ? 3 : 0;
+   {
+      const char *e = getenv ("FB200_BIG");	/* experiments only */
+      if (e)
+	 d->big = atoi (e);
+   }
    d->first_band   = 0;
    d->last_band	   = p->bands - 1;
    return FB200_OK;

@@ -38,15 +38,25 @@ __device__ __forceinline__ unsigned width_of_level (int l)  { return 1u << (l >>
 __device__ __forceinline__ unsigned height_of_level (int l) { return 1u << ((l + 1) >> 1); }
 __device__ __forceinline__ float fmin2 (float a, float b)   { return a > b ? b : a; }
 
+/*
+ *  The helpers below are deliberately NOT inlined: the kernel is one long serial chain whose
+ *  speed is set by instruction fetch (ncu: "no instruction" is the top stall of the working
+ *  warp), so one shared copy of log2 / rtob beats fifty inlined ones.
+ */
+__device__ __noinline__ double dev_log2d (float x)
+{
+   return log2 ((double) x);
+}
+
 /* -log2 (x) rounded to fp32 the way the reference does it: double log2, negate, narrow */
 __device__ __forceinline__ float neg_log2f_via_double (float x)
 {
-   return (float) (-log2 ((double) x));
+   return (float) (-dev_log2d (x));
 }
 
 /* lib/rpf.c:59-111 (rtob); the reference shifts by more than 31 bits for tiny/huge
    inputs; on x86-64 that is a shift by (count mod 32), reproduced here explicitly */
-__device__ __forceinline__ int dev_rtob (float f, int mantissa_bits, float range)
+__device__ __noinline__ int dev_rtob (float f, int mantissa_bits, float range)
 {
    f = f / range;
    unsigned u	     = __float_as_uint (f);
@@ -72,7 +82,7 @@ __device__ __forceinline__ int dev_rtob (float f, int mantissa_bits, float range
 }
 
 /* lib/rpf.c:113-169 (btor) */
-__device__ __forceinline__ float dev_btor (int binary, int mantissa_bits, float range)
+__device__ __noinline__ float dev_btor (int binary, int mantissa_bits, float range)
 {
    if (binary == -1)
       return 0.0f;
@@ -208,6 +218,7 @@ struct MpRes			/* mp_t, codec/approx.c:41-51 */
    short indices [FB_MAXEDGES + 1];
    short into [FB_MAXEDGES + 1];
    float weight [FB_MAXEDGES];
+   short code [FB_MAXEDGES];	/* rtob (weight) with the rpf of the domain's kind */
    float matrix_bits, weights_bits, err, costs;
 };
 
@@ -231,6 +242,8 @@ struct MpWork
    int	  index;		/* winner of the current step or -1 */
    int	  wave_pos, wave_done;	/* lazy pass-2 waves: next start index, finished flag */
    float  best_f [FB_MAXEDGES];
+   short  best_c [FB_MAXEDGES];
+   short  half_lv, half_dc;	/* rtob (0.5) of the two quantisers */
    float  best_mbits, best_wbits, best_err, best_costs;
 };
 
@@ -278,6 +291,7 @@ struct Sh			/* pointers into dynamic shared memory */
    short   *blob;		/* [blob_len] current probability models */
    short   *snaps;		/* [ndepth][2][blob_len] model snapshots of the DFS, or NULL */
    double  *l2;			/* [aac_dc_size + aac_lvl_size] */
+   float   *qt_dc, *qt_lv;	/* [aac_dc_size], [aac_lvl_size]: btor (code), lib/rpf.c:113 */
    Frame   *frames;
    int	    dcap;
 };
@@ -285,7 +299,7 @@ struct Sh			/* pointers into dynamic shared memory */
 __host__ __device__ inline size_t align16 (size_t x) { return (x + 15) & ~(size_t) 15; }
 
 __host__ __device__ inline size_t
-smem_layout (const DevParams &p, int nt, size_t *off /* [14] */)
+smem_layout (const DevParams &p, int nt, size_t *off /* [15] */)
 {
    size_t o    = 0;
    size_t dcap = (size_t) p.s_cap + 1;
@@ -293,7 +307,7 @@ smem_layout (const DevParams &p, int nt, size_t *off /* [14] */)
    off [0] = o; o += align16 (sizeof (ShHdr));
    off [1] = o; o += align16 (dcap * 4);			/* num */
    off [2] = o; o += align16 (dcap * 4);			/* den */
-   off [3] = o; o += p.big ? 0 : align16 (dcap * 4 * (p.max_elements > 1 ? p.max_elements - 1 : 1)); /* G */
+   off [3] = o; o += (p.big & 1) ? 0 : align16 (dcap * 4 * (p.max_elements > 1 ? p.max_elements - 1 : 1)); /* G */
    off [4] = o; o += align16 (dcap);				/* used */
    off [5] = o; o += align16 ((size_t) p.s_cap * 2);		/* pool */
    off [6] = o; o += align16 (((size_t) 1 << p.lc_max) * 4);	/* pixels */
@@ -305,27 +319,28 @@ smem_layout (const DevParams &p, int nt, size_t *off /* [14] */)
       /* model snapshots of the DFS stay on chip when they are small (default models:
 	 376 B each), else they live in the tile's global workspace */
       const size_t need = (size_t) (p.level - p.lc_min + 2) * 2 * p.blob_len * 2;
-      const bool on_chip = need <= 24 * 1024 && !p.big;
+      const bool on_chip = need <= 24 * 1024 && !(p.big & 2);
       off [11] = on_chip ? o : (size_t) -1;
       if (on_chip)
 	 o += align16 (need);
    }
    off [12] = o; o += align16 ((size_t) (p.aac_dc_size + p.aac_lvl_size) * 8);	/* log2 tables */
    off [13] = o; o += align16 ((size_t) (p.level - p.lc_min + 2) * sizeof (Frame));	/* DFS frames */
+   off [14] = o; o += align16 ((size_t) (p.aac_dc_size + p.aac_lvl_size) * 4);	/* quantiser tables */
    return o;
 }
 
 __device__ __forceinline__ Sh
 carve (unsigned char *base, const DevParams &p, int nt, float *gglob, float *bndglob)
 {
-   size_t off [14];
+   size_t off [15];
    Sh	  s;
 
    smem_layout (p, nt, off);
    s.h	    = (ShHdr *) (base + off [0]);
    s.num    = (float *) (base + off [1]);
    s.den    = (float *) (base + off [2]);
-   s.G	    = p.big ? gglob : (float *) (base + off [3]);
+   s.G	    = (p.big & 1) ? gglob : (float *) (base + off [3]);
    s.used   = (unsigned char *) (base + off [4]);
    s.pool   = (short *) (base + off [5]);
    s.pixels = (float *) (base + off [6]);
@@ -339,6 +354,8 @@ carve (unsigned char *base, const DevParams &p, int nt, float *gglob, float *bnd
    s.dcap   = p.s_cap + 1;
    s.l2	    = (double *) (base + off [12]);
    s.frames = (Frame *) (base + off [13]);
+   s.qt_dc  = (float *) (base + off [14]);
+   s.qt_lv  = s.qt_dc + p.aac_dc_size;
    return s;
 }
 
@@ -834,7 +851,7 @@ cta_state_products (const DevParams &P, const TileWs &W, const Sh &sh, unsigned 
    ShHdr    *h	  = sh.h;
    const int dcap = sh.dcap;
    /* scratch rows: the pursuit's work arrays are idle while a state is appended */
-   const int NR = P.big ? 3 : 3 + (P.max_elements > 1 ? P.max_elements - 1 : 1);
+   const int NR = (P.big & 1) ? 3 : 3 + (P.max_elements > 1 ? P.max_elements - 1 : 1);
 
    if (tid == 0)
    {
@@ -1152,7 +1169,8 @@ cta_init_basis (const DevParams &P, const TileWs &W, const Sh &sh)
 __device__ __forceinline__ int
 dom_state (const Sh &sh, const MpWork &w, int d)
 {
-   return d < w.pool_n ? (int) sh.pool [d] : w.y_state;
+   /* the y-state, when it is an extra domain, sits in slot pool_n (set per pursuit) */
+   return (int) sh.pool [d];
 }
 
 /* per-step scalars every candidate needs (thread 0) */
@@ -1185,18 +1203,13 @@ t0_mp_prepare_step (const DevParams &P, const Sh &sh, MpRes &mp, int n)
 	    w.csorted [p] = (short) idx;
 	 }
 	 /* aac_bits prefix over the chosen weights (coeff.c:230-237) */
-	 if (st)
-	    prefix = (float) ((double) prefix
-			      - w.l2_lv [dev_rtob (mp.weight [k], P.rpf_m, P.rpf_range)]);
-	 else
-	    prefix = (float) ((double) prefix
-			      - w.l2_dc [dev_rtob (mp.weight [k], P.dc_m, P.dc_range)]);
+	 prefix = (float) ((double) prefix - (st ? w.l2_lv : w.l2_dc) [mp.code [k]]);
       }
    }
    w.nc	   = nc;
    w.ncs   = ncs;
-   w.wb_nd = (float) ((double) prefix - w.l2_lv [dev_rtob (0.5f, P.rpf_m, P.rpf_range)]);
-   w.wb_dc = (float) ((double) prefix - w.l2_dc [dev_rtob (0.5f, P.dc_m, P.dc_range)]);
+   w.wb_nd = (float) ((double) prefix - w.l2_lv [w.half_lv]);
+   w.wb_dc = (float) ((double) prefix - w.l2_dc [w.half_dc]);
 }
 
 /*
@@ -1229,11 +1242,12 @@ mp_pass1 (const MpWork &w, int d, int st, float num, float den, float price, flo
 template <int N>
 __device__ __forceinline__ float
 mp_pass2 (const DevParams &P, const Sh &sh, const MpWork &w, const MpRes &mp, int d,
-	  float num, float den, float price, float *out)
+	  float num, float den, float price, float *out, int *cod)
 {
    const int dcap = sh.dcap;
    float     f [N + 1], r [N + 1];
-   int	     v [N + 1];
+   int	     v [N + 1], c [N + 1];
+   bool	     nd [N + 1];	/* not the DC domain: ordinary quantiser */
 
 #pragma unroll
    for (int k = 0; k < N; k++)
@@ -1246,11 +1260,11 @@ mp_pass2 (const DevParams &P, const Sh &sh, const MpWork &w, const MpRes &mp, in
 #pragma unroll
    for (int l = N; l >= 0; l--)
    {
-      const int	  stl = dom_state (sh, w, v [l]);
-      const float q   = stl ? dev_btor (dev_rtob (f [l], P.rpf_m, P.rpf_range), P.rpf_m,
-					P.rpf_range)
-			    : dev_btor (dev_rtob (f [l], P.dc_m, P.dc_range), P.dc_m,
-					P.dc_range);
+      /* btor (rtob (x)): the code, then its value from the table (rtob o btor is the
+	 identity on codes, tests/test_oracle_golden.py) */
+      nd [l] = dom_state (sh, w, v [l]) != 0;
+      c [l]  = dev_rtob (f [l], nd [l] ? P.rpf_m : P.dc_m, nd [l] ? P.rpf_range : P.dc_range);
+      const float q = c [l] < 0 ? 0.0f : (nd [l] ? sh.qt_lv : sh.qt_dc) [c [l]];
       f [l] = q;
       r [l] = q;
 #pragma unroll
@@ -1268,16 +1282,9 @@ mp_pass2 (const DevParams &P, const Sh &sh, const MpWork &w, const MpRes &mp, in
 	 srt [e] = (short) 0x7fff;
 #pragma unroll
       for (int k = 0; k <= N; k++)
-	 if (f [k] != 0)
+	 if (c [k] >= 0)
 	 {
-	    const int stk = dom_state (sh, w, v [k]);
-
-	    if (stk)
-	       w_bits = (float) ((double) w_bits
-				 - w.l2_lv [dev_rtob (f [k], P.rpf_m, P.rpf_range)]);
-	    else
-	       w_bits = (float) ((double) w_bits
-				 - w.l2_dc [dev_rtob (f [k], P.dc_m, P.dc_range)]);
+	    w_bits = (float) ((double) w_bits - (nd [k] ? w.l2_lv : w.l2_dc) [c [k]]);
 	    if (v [k] != w.ydom)
 	       sorted_insert<N + 1> (srt, cnt, v [k]);
 	 }
@@ -1299,7 +1306,10 @@ mp_pass2 (const DevParams &P, const Sh &sh, const MpWork &w, const MpRes &mp, in
    }
 #pragma unroll
    for (int k = 0; k < FB_MAXEDGES; k++)
+   {
       out [k] = k <= N ? f [k] : 0.0f;
+      cod [k] = k <= N ? c [k] : -1;
+   }
    out [5] = m_bits;
    out [6] = w_bits;
    out [7] = m_err;
@@ -1388,13 +1398,14 @@ cta_mp_find (const DevParams &P, const Sh &sh, MpRes &mp, float price)
 	 __syncwarp ();
 	 float key = INFINITY, costs = 0;
 	 float res [8];
+	 int   cod [FB_MAXEDGES];
 	 int   d = -1;
 
 	 if (lane < taken)
 	 {
 	    d = sh.cand [lane];
 	    const float b = sh.bnd [d];
-	    costs = mp_pass2<N> (P, sh, w, mp, d, sh.num [d], sh.den [d], price, res);
+	    costs = mp_pass2<N> (P, sh, w, mp, d, sh.num [d], sh.den [d], price, res, cod);
 	    key	  = b > costs ? b : costs;	/* both must beat the running minimum */
 	 }
 	 /* ordered resolution (lanes are in index order) */
@@ -1412,7 +1423,10 @@ cta_mp_find (const DevParams &P, const Sh &sh, MpRes &mp, float price)
 	 {
 #pragma unroll
 	    for (int k = 0; k < FB_MAXEDGES; k++)
+	    {
 	       w.best_f [k] = res [k];
+	       w.best_c [k] = (short) cod [k];
+	    }
 	    w.best_mbits = res [5];
 	    w.best_wbits = res [6];
 	    w.best_err	 = res [7];
@@ -1482,6 +1496,7 @@ cta_matching_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &
 	 {
 	    w.ydom = w.pool_n;
 	    w.D	   = w.pool_n + 1;
+	    sh.pool [w.pool_n] = (short) y_state;
 	 }
       }
       w.level = level;
@@ -1504,11 +1519,11 @@ cta_matching_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &
       for (int i = tid; i < P.aac_dc_size + P.aac_lvl_size + FB_MAXEDGES + 2; i += NT)
       {
 	 if (i < P.aac_dc_size)
-	    w.l2_dc [i] = log2 ((double) (counts [i] / (float) sh.blob [MB_TOTALS]));
+	    w.l2_dc [i] = dev_log2d (counts [i] / (float) sh.blob [MB_TOTALS]);
 	 else if (i < P.aac_dc_size + P.aac_lvl_size)
 	 {
 	    const int c = i - P.aac_dc_size;
-	    w.l2_lv [c] = log2 ((double) (lv [c] / (float) sh.blob [MB_TOTALS + ctx + 1]));
+	    w.l2_lv [c] = dev_log2d (lv [c] / (float) sh.blob [MB_TOTALS + ctx + 1]);
 	 }
 	 else
 	 {
@@ -1585,7 +1600,10 @@ cta_matching_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &
 	 mp.matrix_bits	 = w.best_mbits;
 	 mp.weights_bits = w.best_wbits;
 	 for (int k = 0; k <= n; k++)
+	 {
 	    mp.weight [k] = w.best_f [k];
+	    mp.code [k]	  = w.best_c [k];
+	 }
 	 mp.indices [n] = (short) index;
 	 mp.into [n]	= (short) dom_state (sh, w, index);
 	 sh.used [index] = 1;
@@ -1697,7 +1715,7 @@ t0_rle_update (const Sh &sh, const MpWork &w, const short *used_domains)
 
 /* coeff.c:242-267 */
 __device__ void
-t0_aac_update (const DevParams &P, const Sh &sh, const float *weight, const short *into,
+t0_aac_update (const DevParams &P, const Sh &sh, const short *code, const short *into,
 	       int level)
 {
    const int ctx    = level - P.coeff_min_level;
@@ -1707,12 +1725,12 @@ t0_aac_update (const DevParams &P, const Sh &sh, const float *weight, const shor
    for (int e = 0; into [e] != FB_NO_EDGE; e++)
       if (into [e])
       {
-	 lv [dev_rtob (weight [e], P.rpf_m, P.rpf_range)]++;
+	 lv [code [e]]++;
 	 sh.blob [MB_TOTALS + ctx + 1]++;
       }
       else
       {
-	 counts [dev_rtob (weight [e], P.dc_m, P.dc_range)]++;
+	 counts [code [e]]++;
 	 sh.blob [MB_TOTALS]++;
       }
 }
@@ -1765,12 +1783,13 @@ cta_approximate_range (const DevParams &P, const TileWs &W, const Sh &sh, float 
 	       mp.indices [new_index] = mp.indices [old];
 	       mp.into [new_index]    = mp.into [old];
 	       mp.weight [new_index]  = mp.weight [old];
+	       mp.code [new_index]    = mp.code [old];
 	       new_index++;
 	    }
 	 mp.indices [new_index] = FB_NO_EDGE;
 	 mp.into [new_index]	= FB_NO_EDGE;
 	 t0_rle_update (sh, h->w, mp.indices);
-	 t0_aac_update (P, sh, mp.weight, mp.into, level);
+	 t0_aac_update (P, sh, mp.code, mp.into, level);
 	 for (edge = 0; mp.indices [edge] != FB_NO_EDGE; edge++)
 	 {
 	    out->into [edge]   = mp.into [edge];
@@ -2346,6 +2365,17 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
    }
    __syncthreads ();
 
+   /* quantiser value tables and the codes of the pass-1 dummy weight 0.5 */
+   for (int i = tid; i < P.aac_dc_size + P.aac_lvl_size; i += NT)
+      sh.qt_dc [i] = i < P.aac_dc_size ? dev_btor (i, P.dc_m, P.dc_range)
+				       : dev_btor (i - P.aac_dc_size, P.rpf_m, P.rpf_range);
+   if (tid == 0)
+   {
+      h->w.half_lv = (short) dev_rtob (0.5f, P.rpf_m, P.rpf_range);
+      h->w.half_dc = (short) dev_rtob (0.5f, P.dc_m, P.dc_range);
+   }
+   __syncthreads ();
+
    if (P.first_band == 0)
    {
       cta_init_basis<NT> (P, W, sh);
@@ -2522,7 +2552,7 @@ fb_tile_kernel_threads (const DevParams &p, int n_tiles)
 size_t
 fb_tile_kernel_smem (const DevParams &p, int nt)
 {
-   size_t off [14];
+   size_t off [15];
 
    return smem_layout (p, nt, off);
 }

@@ -46,8 +46,8 @@ struct DevParams
    int	 aac_dc_size, aac_lvl_size, blob_len;
    int	 trace_cap;
    int	 first_band, last_band; /* bands processed by this launch */
-   int	 big;			/* large state capacity: Gram rows and model snapshots live in
-				   global memory so that more tiles fit on an SM */
+   int	 big;			/* large state capacity, so that more tiles fit on an SM: bit 0 =
+				   Gram rows in global memory, bit 1 = model snapshots in global */
 };
 
 /* all transitions of one state in one 64-byte line: what the inner-product kernels gather */
