@@ -285,8 +285,9 @@ def run_ours(args):
         "clocks": clocks,
         "phase_cycles": {k: int(st[k]) for k in ("cyc_total", "cyc_T", "cyc_mp", "cyc_append")},
         "work": {k: int(st[k]) for k in ("mp_calls", "mp_steps", "blocks", "states")},
-        "lap_share": {n: round(v / (float(sum(st["lap"])) or 1.0), 4) for n, v in zip(LAP_NAMES, st["lap"])},
     }
+    if sum(st["lap"]):                            # only a -DFB200_LAPS diagnostics build fills the lap timers
+        line["lap_share"] = {n: round(v / float(sum(st["lap"])), 4) for n, v in zip(LAP_NAMES, st["lap"])}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

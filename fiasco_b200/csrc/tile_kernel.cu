@@ -364,7 +364,11 @@ carve (unsigned char *base, const DevParams &p, int nt, float *gglob, float *bnd
 #define BLOB_S16(sh, i) ((sh).blob [i])
 
 /* thread-0 lap timer: time since the previous LAP goes to bucket i */
+#ifndef FB200_LAPS	/* diagnostics build only: the timers cost 2-3 % */
+#define LAP(h, i) do { } while (0)
+#else
 #define LAP(h, i) do { if (threadIdx.x == 0) { const long long now_ = clock64 (); (h)->lap [i] += now_ - (h)->lap_last; (h)->lap_last = now_; } } while (0)
+#endif
 enum { LAP_CTRL, LAP_PIX, LAP_DOTS, LAP_UPSWEEP, LAP_ENTER, LAP_MP_PRO, LAP_MP_P1, LAP_MP_WAVES,
        LAP_MP_COMMIT, LAP_MP_ORTHO, LAP_AR_EPI, LAP_AP_IMG, LAP_AP_DIRECT, LAP_AP_STAGED, LAP_DECIDE, LAP_N };
 
@@ -464,6 +468,66 @@ __constant__ float c_matrix_1 [1024];
 /*****************************************************************************
 		range x state products of a block  (codec/ip.c:72-154)
 *****************************************************************************/
+
+/*
+ *  Upsweep of U consecutive nodes of one level for state s (ip.c:98-151): the gathers of all
+ *  U nodes are issued before the first addition, so their L2 round trips overlap; each
+ *  entry is still accumulated in the reference's order.
+ */
+template <int U>
+__device__ __forceinline__ void
+upsweep_nodes (float *T, unsigned scap, unsigned node, unsigned s, const TransReg &tr,
+	       const int (&idx) [2][FB_MAXEDGES + 1])
+{
+   float v [U][2][FB_MAXEDGES + 1];
+
+#pragma unroll
+   for (int u = 0; u < U; u++)
+#pragma unroll
+      for (int label = 0; label < 2; label++)
+      {
+	 const float *src = T + (size_t) (2 * (node + u) + 1 + label) * scap;
+#pragma unroll
+	 for (int e = 0; e < FB_MAXEDGES + 1; e++)
+	    v [u][label][e] = src [idx [label][e]];
+      }
+#pragma unroll
+   for (int u = 0; u < U; u++)
+   {
+      float acc = 0;
+#pragma unroll
+      for (int label = 0; label < 2; label++)
+      {
+	 if (tr.child [label] != FB_RANGE)
+	    acc += v [u][label][0];
+#pragma unroll
+	 for (int e = 0; e < FB_MAXEDGES; e++)
+	    if (tr.into [label][e] != FB_NO_EDGE)
+	       acc += v [u][label][e + 1] * tr.w [label][e];
+      }
+      T [(size_t) (node + u) * scap + s] = acc;
+   }
+}
+
+/* block-wide copy of n floats with four independent loads in flight per thread */
+template <int NT>
+__device__ __forceinline__ void
+cta_copy_f32 (float *dst, const float *src, unsigned n)
+{
+   unsigned t = threadIdx.x;
+
+   for (; t + 3 * NT < n; t += 4 * NT)
+   {
+      const float a = src [t], b = src [t + NT], c = src [t + 2 * NT], d = src [t + 3 * NT];
+
+      dst [t]	       = a;
+      dst [t + NT]     = b;
+      dst [t + 2 * NT] = c;
+      dst [t + 3 * NT] = d;
+   }
+   for (; t < n; t += NT)
+      dst [t] = src [t];
+}
 
 /*
  *  Fill T[node][s] for the nodes of the subtree rooted at (node_root, level_root) of the
@@ -601,32 +665,14 @@ cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
 	       for (int e = 0; e < FB_MAXEDGES; e++)
 		  idx [label][e + 1] = tr.into [label][e] != FB_NO_EDGE ? tr.into [label][e] : 0;
 	    }
+	    if (nn >= 2)
 #pragma unroll 1
-	    for (unsigned k = 0; k < nn; k++)
-	    {
-	       const unsigned node = node0 + k;
-	       float	      v [2][FB_MAXEDGES + 1];
-	       float	      acc = 0;
-#pragma unroll
-	       for (int label = 0; label < 2; label++)
-	       {
-		  const float *src = W.T + (size_t) (2 * node + 1 + label) * scap;
-#pragma unroll
-		  for (int e = 0; e < FB_MAXEDGES + 1; e++)
-		     v [label][e] = src [idx [label][e]];
-	       }
-#pragma unroll
-	       for (int label = 0; label < 2; label++)
-	       {
-		  if (tr.child [label] != FB_RANGE)
-		     acc += v [label][0];
-#pragma unroll
-		  for (int e = 0; e < FB_MAXEDGES; e++)
-		     if (tr.into [label][e] != FB_NO_EDGE)
-			acc += v [label][e + 1] * tr.w [label][e];
-	       }
-	       W.T [(size_t) node * scap + s] = acc;
-	    }
+	       for (unsigned k = 0; k < nn; k += 2)
+		  upsweep_nodes<2> (W.T, scap, node0 + k, s, tr, idx);
+	    else
+#pragma unroll 1
+	       for (unsigned k = 0; k < nn; k++)
+		  upsweep_nodes<1> (W.T, scap, node0 + k, s, tr, idx);
 	 }
       }
       else
@@ -947,8 +993,7 @@ cta_state_products (const DevParams &P, const TileWs &W, const Sh &sh, unsigned 
 	 float	     *row = j == 0 ? sh.num : j == 1 ? sh.den : j == 2 ? sh.bnd
 						 : sh.G + (size_t) (j - 3) * dcap;
 	 const float *src = W.SS + ((size_t) (li - 1) * P.s_cap + h->ap_src [j]) * P.s_cap;
-	 for (unsigned t = tid; t <= s; t += NT)
-	    row [t] = src [t];
+	 cta_copy_f32<NT> (row, src, s + 1);
       }
       __syncthreads ();
       for (unsigned t = tid; t <= s; t += NT)
@@ -1213,8 +1258,10 @@ t0_mp_prepare_step (const DevParams &P, const Sh &sh, MpRes &mp, int n)
 }
 
 /*
- *  Pass 1 for domain d at step N (approx.c:433-462): rate of "chosen vectors + d with a
- *  dummy weight 0.5", turned into the optimistic cost bound.
+ *  Pass 1 for domain d (approx.c:433-462): rate of "chosen vectors + d with a dummy weight
+ *  0.5", turned into the optimistic cost bound.  N = the largest step number of the
+ *  configuration (max_elements - 1): ONE body serves every step of a pursuit, so that the
+ *  second and third step find their code in the instruction cache.
  */
 template <int N>
 __device__ __forceinline__ float
@@ -1235,80 +1282,85 @@ mp_pass1 (const MpWork &w, int d, int st, float num, float den, float price, flo
 }
 
 /*
- *  Pass 2 for domain d at step N (approx.c:463-602): quantised weights by back
+ *  Pass 2 for domain d at step n <= MAXN (approx.c:463-602): quantised weights by back
  *  substitution, true rate, true error.  Returns the costs; weights / bits / err in out[].
- *  out: [0..4] weights, [5] matrix bits, [6] weights bits, [7] err.
+ *  out: [0..4] weights, [5] matrix bits, [6] weights bits, [7] err.  One body for all steps
+ *  (see mp_pass1); the loops are unrolled to MAXN and guarded by the (uniform) step number.
  */
-template <int N>
+template <int MAXN>
 __device__ __forceinline__ float
-mp_pass2 (const DevParams &P, const Sh &sh, const MpWork &w, const MpRes &mp, int d,
+mp_pass2 (const DevParams &P, const Sh &sh, const MpWork &w, const MpRes &mp, int n, int d,
 	  float num, float den, float price, float *out, int *cod)
 {
    const int dcap = sh.dcap;
-   float     f [N + 1], r [N + 1];
-   int	     v [N + 1], c [N + 1];
-   bool	     nd [N + 1];	/* not the DC domain: ordinary quantiser */
+   float     f [MAXN + 1], r [MAXN + 1];
+   int	     v [MAXN + 1], c [MAXN + 1];
+   bool	     nd [MAXN + 1];	/* not the DC domain: ordinary quantiser */
 
 #pragma unroll
-   for (int k = 0; k < N; k++)
+   for (int k = 0; k <= MAXN; k++)
    {
-      f [k] = w.fB [k];
-      v [k] = mp.indices [k];
+      f [k]  = k < n ? w.fB [k] : num / den;
+      v [k]  = k < n ? (int) mp.indices [k] : d;
+      c [k]  = -1;
+      r [k]  = 0;
+      nd [k] = false;
    }
-   f [N] = num / den;
-   v [N] = d;
 #pragma unroll
-   for (int l = N; l >= 0; l--)
-   {
-      /* btor (rtob (x)): the code, then its value from the table (rtob o btor is the
-	 identity on codes, tests/test_oracle_golden.py) */
-      nd [l] = dom_state (sh, w, v [l]) != 0;
-      c [l]  = dev_rtob (f [l], nd [l] ? P.rpf_m : P.dc_m, nd [l] ? P.rpf_range : P.dc_range);
-      const float q = c [l] < 0 ? 0.0f : (nd [l] ? sh.qt_lv : sh.qt_dc) [c [l]];
-      f [l] = q;
-      r [l] = q;
+   for (int l = MAXN; l >= 0; l--)
+      if (l <= n)
+      {
+	 /* btor (rtob (x)): the code, then its value from the table (rtob o btor is the
+	    identity on codes, tests/test_oracle_golden.py) */
+	 nd [l] = dom_state (sh, w, v [l]) != 0;
+	 c [l]	= dev_rtob (f [l], nd [l] ? P.rpf_m : P.dc_m, nd [l] ? P.rpf_range : P.dc_range);
+	 const float q = c [l] < 0 ? 0.0f : (nd [l] ? sh.qt_lv : sh.qt_dc) [c [l]];
+	 f [l] = q;
+	 r [l] = q;
 #pragma unroll
-      for (int k = 0; k < l; k++)
-	 f [k] -= q * sh.G [k * dcap + v [l]] / w.N [k];
-   }
+	 for (int k = 0; k < l; k++)
+	    f [k] -= q * sh.G [k * dcap + v [l]] / w.N [k];
+      }
    /* rate of the quantised combination */
    float w_bits = 0, m_bits;
    {
-      short srt [N + 1];
+      short srt [MAXN + 1];
       int   cnt = 0;
 
 #pragma unroll
-      for (int e = 0; e < N + 1; e++)
+      for (int e = 0; e < MAXN + 1; e++)
 	 srt [e] = (short) 0x7fff;
 #pragma unroll
-      for (int k = 0; k <= N; k++)
-	 if (c [k] >= 0)
+      for (int k = 0; k <= MAXN; k++)
+	 if (k <= n && c [k] >= 0)
 	 {
 	    w_bits = (float) ((double) w_bits - (nd [k] ? w.l2_lv : w.l2_dc) [c [k]]);
 	    if (v [k] != w.ydom)
-	       sorted_insert<N + 1> (srt, cnt, v [k]);
+	       sorted_insert<MAXN + 1> (srt, cnt, v [k]);
 	 }
-      m_bits = dev_rle_bits<N + 1> (w.mbase, w.d0b, srt, cnt, (unsigned) w.pool_n);
+      m_bits = dev_rle_bits<MAXN + 1> (w.mbase, w.d0b, srt, cnt, (unsigned) w.pool_n);
    }
    /* back to the orthogonal basis, error (approx.c:571-586) */
 #pragma unroll
-   for (int k = 0; k < N; k++)
+   for (int k = 0; k < MAXN; k++)
 #pragma unroll
-      for (int l = k + 1; l <= N; l++)
-	 r [k] += sh.G [k * dcap + v [l]] * r [l] / w.N [k];
+      for (int l = k + 1; l <= MAXN; l++)
+	 if (l <= n)
+	    r [k] += sh.G [k * dcap + v [l]] * r [l] / w.N [k];
    float m_err = w.norm;
 #pragma unroll
-   for (int k = 0; k <= N; k++)
-   {
-      const float Nk = k == N ? den : w.N [k];
-      const float Bk = k == N ? num : w.B [k];
-      m_err += (r [k] * r [k]) * Nk - 2 * r [k] * Bk;
-   }
+   for (int k = 0; k <= MAXN; k++)
+      if (k <= n)
+      {
+	 const float Nk = k == n ? den : w.N [k];
+	 const float Bk = k == n ? num : w.B [k];
+	 m_err += (r [k] * r [k]) * Nk - 2 * r [k] * Bk;
+      }
 #pragma unroll
    for (int k = 0; k < FB_MAXEDGES; k++)
    {
-      out [k] = k <= N ? f [k] : 0.0f;
-      cod [k] = k <= N ? c [k] : -1;
+      out [k] = (k <= MAXN && k <= n) ? f [k < MAXN ? k : MAXN] : 0.0f;
+      cod [k] = (k <= MAXN && k <= n) ? c [k < MAXN ? k : MAXN] : -1;
    }
    out [5] = m_bits;
    out [6] = w_bits;
@@ -1317,7 +1369,7 @@ mp_pass2 (const DevParams &P, const Sh &sh, const MpWork &w, const MpRes &mp, in
 }
 
 /*
- *  Step N of the pursuit: find the domain the reference's index-ordered scan with its
+ *  Step n (<= N) of the pursuit: find the domain the reference's index-ordered scan with its
  *  running minimum (approx.c:420-603) would select.
  *
  *  Phase 1: every thread computes the pass-1 bound of its domains.
@@ -1329,7 +1381,7 @@ mp_pass2 (const DevParams &P, const Sh &sh, const MpWork &w, const MpRes &mp, in
  */
 template <int NT, int N>
 __device__ void
-cta_mp_find (const DevParams &P, const Sh &sh, MpRes &mp, float price)
+cta_mp_find (const DevParams &P, const Sh &sh, MpRes &mp, float price, int n)
 {
    const int tid  = threadIdx.x;
    const int lane = tid & 31;
@@ -1344,7 +1396,11 @@ cta_mp_find (const DevParams &P, const Sh &sh, MpRes &mp, float price)
       float b = INFINITY;
 
       if (d < D && !sh.used [d])
-	 b = mp_pass1<N> (w, d, dom_state (sh, w, d), sh.num [d], sh.den [d], price, err);
+      {
+	 const int   st	 = dom_state (sh, w, d);
+	 const float num = sh.num [d], den = sh.den [d];
+	    b = mp_pass1<N> (w, d, st, num, den, price, err);
+      }
       sh.bnd [d] = b;
    }
    LAP (sh.h, LAP_MP_P1);
@@ -1405,7 +1461,7 @@ cta_mp_find (const DevParams &P, const Sh &sh, MpRes &mp, float price)
 	 {
 	    d = sh.cand [lane];
 	    const float b = sh.bnd [d];
-	    costs = mp_pass2<N> (P, sh, w, mp, d, sh.num [d], sh.den [d], price, res, cod);
+	    costs = mp_pass2<N> (P, sh, w, mp, n, d, sh.num [d], sh.den [d], price, res, cod);
 	    key	  = b > costs ? b : costs;	/* both must beat the running minimum */
 	 }
 	 /* ordered resolution (lanes are in index order) */
@@ -1540,26 +1596,42 @@ cta_matching_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &
    const float fsize = (float) w.size;
 
    /* ---- numerators / denominators (approx.c:358-374) ---- */
-   for (int d = tid; d < D; d += NT)
+   for (int d0 = tid; d0 < D; d0 += 4 * NT)
    {
-      const int	    st	 = dom_state (sh, w, d);
-      const float   den	 = W.diag [(size_t) li * P.s_cap + st];
-      unsigned char used = 0;
-      float	    num	 = 0;
+      /* four domains per round: all eight gathers are issued up front (one L2 round
+	 trip); a numerator that belongs to an unusable domain is never looked at */
+      float dn [4], nm [4];
 
-      /* both loads are issued up front (one L2 round trip); a numerator that belongs
-	 to an unusable domain is never looked at */
-      num = W.T [(size_t) image * P.s_cap + st];
-      if (den / fsize < min_norm)
-	 used = 1;
-      else if (fabsf (num) < min_norm)
-	 used = 1;
-      for (int e = 0; e < FB_MAXEDGES && mp.exclude [e] != FB_NO_EDGE; e++)
-	 if (mp.exclude [e] == d)
-	    used = 1;
-      sh.num [d]  = num;
-      sh.den [d]  = den;
-      sh.used [d] = used;
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+      {
+	 const int d  = d0 + u * NT;
+	 const int st = d < D ? dom_state (sh, w, d) : 0;
+
+	 dn [u] = W.diag [(size_t) li * P.s_cap + st];
+	 nm [u] = W.T [(size_t) image * P.s_cap + st];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+      {
+	 const int d = d0 + u * NT;
+
+	 if (d < D)
+	 {
+	    unsigned char used = 0;
+
+	    if (dn [u] / fsize < min_norm)
+	       used = 1;
+	    else if (fabsf (nm [u]) < min_norm)
+	       used = 1;
+	    for (int e = 0; e < FB_MAXEDGES && mp.exclude [e] != FB_NO_EDGE; e++)
+	       if (mp.exclude [e] == d)
+		  used = 1;
+	    sh.num [d]	= nm [u];
+	    sh.den [d]	= dn [u];
+	    sh.used [d] = used;
+	 }
+      }
    }
    if (tid == 0)
    {
@@ -1578,14 +1650,10 @@ cta_matching_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &
    int n = 0;
    for (;;)
    {
-      switch (n)
-      {
-	 case 0:  cta_mp_find<NT, 0> (P, sh, mp, price); break;
-	 case 1:  cta_mp_find<NT, 1> (P, sh, mp, price); break;
-	 case 2:  cta_mp_find<NT, 2> (P, sh, mp, price); break;
-	 case 3:  cta_mp_find<NT, 3> (P, sh, mp, price); break;
-	 default: cta_mp_find<NT, 4> (P, sh, mp, price); break;
-      }
+      if (P.max_elements <= 3)
+	 cta_mp_find<NT, 2> (P, sh, mp, price, n);
+      else
+	 cta_mp_find<NT, 4> (P, sh, mp, price, n);
 
       /* ---- commit the step (approx.c:605-632) ---- */
       const int index = w.index;
@@ -1599,6 +1667,7 @@ cta_matching_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &
 	 mp.err		 = w.best_err;
 	 mp.matrix_bits	 = w.best_mbits;
 	 mp.weights_bits = w.best_wbits;
+#pragma unroll 1
 	 for (int k = 0; k <= n; k++)
 	 {
 	    mp.weight [k] = w.best_f [k];
@@ -1632,6 +1701,7 @@ cta_matching_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &
 	    {
 	       float tmp = row [dom_state (sh, w, d)];
 
+#pragma unroll 1
 	       for (int k = 0; k < n; k++)
 		  tmp -= sh.G [k * dcap + d] / w.N [k] * sh.G [k * dcap + index];
 	       sh.G [n * dcap + d] = tmp;
@@ -1747,22 +1817,31 @@ cta_approximate_range (const DevParams &P, const TileWs &W, const Sh &sh, float 
 {
    ShHdr *h = sh.h;
 
-   if (threadIdx.x == 0)
-      h->mp.exclude [0] = FB_NO_EDGE;
-   /* (the prologue of the pursuit starts with thread-0 work followed by a barrier) */
-   cta_matching_pursuit<NT> (P, W, sh, h->mp, level, image, address, out->tree_bits,
-			     price, y_state);
-   if (P.second_domain_block)
+   /* one call site (one copy of the pursuit's code); the second round is the
+      second_domain_block retry without the first domain (approx.c:103-127) */
+   for (int round = 0; round <= (P.second_domain_block ? 1 : 0); round++)
    {
+      MpRes &m = round ? h->tmp : h->mp;
+
       if (threadIdx.x == 0)
       {
-	 h->tmp		    = h->mp;
-	 h->tmp.exclude [0] = h->tmp.indices [0];
-	 h->tmp.exclude [1] = FB_NO_EDGE;
+	 if (round)
+	 {
+	    h->tmp	       = h->mp;
+	    h->tmp.exclude [0] = h->tmp.indices [0];
+	    h->tmp.exclude [1] = FB_NO_EDGE;
+	 }
+	 else
+	    h->mp.exclude [0] = FB_NO_EDGE;
       }
-      __syncthreads ();
-      cta_matching_pursuit<NT> (P, W, sh, h->tmp, level, image, address, out->tree_bits,
-				price, y_state);
+      if (round)
+	 __syncthreads ();
+      /* (the prologue of the pursuit starts with thread-0 work followed by a barrier) */
+      cta_matching_pursuit<NT> (P, W, sh, m, level, image, address, out->tree_bits, price,
+				y_state);
+   }
+   if (P.second_domain_block)
+   {
       if (threadIdx.x == 0 && h->tmp.costs < h->mp.costs)
 	 h->mp = h->tmp;
       __syncthreads ();
@@ -2011,6 +2090,26 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 	 break;
       LAP (h, LAP_CTRL);
 
+      /* range x state products: the whole block when an lc_max range is entered
+	 (init_range, subdivide.c:612-644), or the states born in child 0 for child 1's
+	 subtree (subdivide.c:295-297); one call site = one copy of the code */
+      if (state == ST_CHILD_T || (state == ST_ENTER && F.level == P.lc_max))
+      {
+	 const long long t0c   = clock64 ();
+	 const bool	 block = state == ST_ENTER;
+
+	 if (block)
+	    cta_init_range<NT> (P, W, sh, F.x, F.y, band);
+	 else
+	    cta_compute_T<NT> (P, W, sh, F.states_snap, F.image * 2 + F.label + 1, F.level - 1);
+	 if (tid == 0)
+	 {
+	    if (block)
+	       F.address = F.image = 0;
+	    h->cyc_T += clock64 () - t0c;
+	 }
+      }
+
       switch (state)
       {
 	 case ST_ENTER:
@@ -2019,16 +2118,6 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 	    short    *snap  = (sh.snaps ? sh.snaps : W.snap) + (size_t) depth * 2 * P.blob_len;
 	    unsigned *tsnap = W.treesnap + (size_t) depth * 2 * FB200_MAXLEVEL;
 
-	    if (level == P.lc_max)
-	    {
-	       const long long t0c = clock64 ();
-	       cta_init_range<NT> (P, W, sh, F.x, F.y, band);
-	       if (tid == 0)
-	       {
-		  F.address = F.image = 0;
-		  h->cyc_T += clock64 () - t0c;
-	       }
-	    }
 	    /* snapshot of the models (subdivide.c:188-194) */
 	    cta_copy_s16<NT> (snap, sh.blob, P.blob_len);
 	    if (tid == 0)
@@ -2108,14 +2197,8 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 
 	 case ST_CHILD_T:
 	 {
-	    const long long t0c = clock64 ();
-	    cta_compute_T<NT> (P, W, sh, F.states_snap, F.image * 2 + F.label + 1,
-			       F.level - 1);
 	    if (tid == 0)
-	    {
-	       h->cyc_T += clock64 () - t0c;
 	       nstate = ST_CHILD2;
-	    }
 	    break;
 	 }
 

@@ -29,6 +29,8 @@ NAMES = ["ctrl", "pix", "dots", "upsweep", "enter", "mp_pro", "mp_p1", "mp_waves
 
 
 def main():
+    if os.environ.get("FB200_LIB"):              # experiment builds (tools/build_variant.sh)
+        ffi.lib_path = lambda: os.path.join(ROOT, os.environ["FB200_LIB"])
     per_sm = int(sys.argv[1]) if len(sys.argv) > 1 else 0
     distinct = int(sys.argv[2]) if len(sys.argv) > 2 else 74
     p = ffi.make_params(1024, 1024, 1, 20.0, 0)
@@ -56,8 +58,8 @@ def main():
     lines = F.wfa_lines(w)
     ok = lines == O.golden_wfa_lines("g1024_q20_z0")
     tot = float(sum(st["lap"])) or 1.0
-    print("NT=%s BIG=%s resident=%d B=%d (%.1f/SM): %.1f Mpx/s (launch %.1f ms) parity(frame0)=%s states0=%d md5=%s" % (
-        os.environ.get("FB200_NT", "-"), os.environ.get("FB200_BIG", "-"), res, B, B / sms,
+    print("%s NT=%s BIG=%s resident=%d B=%d (%.1f/SM): %.1f Mpx/s (launch %.1f ms) parity(frame0)=%s states0=%d md5=%s" % (
+        os.environ.get("FB200_LIB", "product"), os.environ.get("FB200_NT", "-"), os.environ.get("FB200_BIG", "-"), res, B, B / sms,
         B * 1.048576 / min(t), 1e3 * min(t), ok, w["states"], hashlib.md5("\n".join(lines).encode()).hexdigest()[:8]),
         flush=True)
     print("   laps: " + " ".join("%s=%.1f" % (n, 100 * v / tot) for n, v in zip(NAMES, st["lap"])), flush=True)
