@@ -26,6 +26,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <math.h>
+#include <stddef.h>
 #include "tile_kernel.cuh"
 
 namespace {
@@ -277,6 +278,9 @@ struct ShHdr
    Frame   *frames;		/* [level - lc_min + 2] */
 };
 
+static_assert (offsetof (ShHdr, tree_total) == offsetof (ShHdr, tree_counts) + FB200_MAXLEVEL * sizeof (unsigned),
+	       "the tree model is copied as one array of 2 * MAXLEVEL counters");
+
 struct Sh			/* pointers into dynamic shared memory */
 {
    ShHdr   *h;
@@ -292,6 +296,7 @@ struct Sh			/* pointers into dynamic shared memory */
    short   *snaps;		/* [ndepth][2][blob_len] model snapshots of the DFS, or NULL */
    double  *l2;			/* [aac_dc_size + aac_lvl_size] */
    float   *qt_dc, *qt_lv;	/* [aac_dc_size], [aac_lvl_size]: btor (code), lib/rpf.c:113 */
+   unsigned *tsnap;		/* [ndepth][2 * MAXLEVEL] tree-model snapshots of the DFS */
    Frame   *frames;
    int	    dcap;
 };
@@ -299,7 +304,7 @@ struct Sh			/* pointers into dynamic shared memory */
 __host__ __device__ inline size_t align16 (size_t x) { return (x + 15) & ~(size_t) 15; }
 
 __host__ __device__ inline size_t
-smem_layout (const DevParams &p, int nt, size_t *off /* [15] */)
+smem_layout (const DevParams &p, int nt, size_t *off /* [16] */)
 {
    size_t o    = 0;
    size_t dcap = (size_t) p.s_cap + 1;
@@ -327,13 +332,14 @@ smem_layout (const DevParams &p, int nt, size_t *off /* [15] */)
    off [12] = o; o += align16 ((size_t) (p.aac_dc_size + p.aac_lvl_size) * 8);	/* log2 tables */
    off [13] = o; o += align16 ((size_t) (p.level - p.lc_min + 2) * sizeof (Frame));	/* DFS frames */
    off [14] = o; o += align16 ((size_t) (p.aac_dc_size + p.aac_lvl_size) * 4);	/* quantiser tables */
+   off [15] = o; o += align16 ((size_t) (p.level - p.lc_min + 2) * 2 * FB200_MAXLEVEL * 4); /* tsnap */
    return o;
 }
 
 __device__ __forceinline__ Sh
 carve (unsigned char *base, const DevParams &p, int nt, float *gglob, float *bndglob)
 {
-   size_t off [15];
+   size_t off [16];
    Sh	  s;
 
    smem_layout (p, nt, off);
@@ -356,6 +362,7 @@ carve (unsigned char *base, const DevParams &p, int nt, float *gglob, float *bnd
    s.frames = (Frame *) (base + off [13]);
    s.qt_dc  = (float *) (base + off [14]);
    s.qt_lv  = s.qt_dc + p.aac_dc_size;
+   s.tsnap  = (unsigned *) (base + off [15]);
    return s;
 }
 
@@ -1390,6 +1397,7 @@ cta_mp_find (const DevParams &P, const Sh &sh, MpRes &mp, float price, int n)
    const int D	  = w.D;
    const int D32  = (D + 31) & ~31;
    const float err = mp.err;
+   float       m   = w.min_costs;
 
    for (int d = tid; d < D32; d += NT)
    {
@@ -1397,30 +1405,32 @@ cta_mp_find (const DevParams &P, const Sh &sh, MpRes &mp, float price, int n)
 
       if (d < D && !sh.used [d])
       {
-	 const int   st	 = dom_state (sh, w, d);
-	 const float num = sh.num [d], den = sh.den [d];
-	    b = mp_pass1<N> (w, d, st, num, den, price, err);
+	 b = mp_pass1<N> (w, d, dom_state (sh, w, d), sh.num [d], sh.den [d], price, err);
       }
       sh.bnd [d] = b;
+      /* candidates of the first wave (a warp covers one 32-domain word) */
+      const unsigned mask = __ballot_sync (0xffffffffu, b < m);
+      if (lane == 0)
+	 sh.cmask [d >> 5] = mask;
    }
    LAP (sh.h, LAP_MP_P1);
-   float m     = w.min_costs;
-   int	 pos   = 0;
-   bool	 first = true;
+   int	pos   = 0;
+   bool first = true;
 
    for (;;)
    {
-      for (int d = tid; d < D32; d += NT)
-      {
-	 const unsigned mask = __ballot_sync (0xffffffffu, d >= pos && sh.bnd [d] < m);
-	 if (lane == 0)
-	    sh.cmask [d >> 5] = mask;
-      }
+      if (!first)
+	 for (int d = tid; d < D32; d += NT)
+	 {
+	    const unsigned mask = __ballot_sync (0xffffffffu, d >= pos && sh.bnd [d] < m);
+	    if (lane == 0)
+	       sh.cmask [d >> 5] = mask;
+	 }
       __syncthreads ();
       if (warp == 0)
       {
 	 const int nwords = D32 >> 5;
-	 int	   taken  = 0;
+	 int	   taken  = 0, cand = -1;
 	 bool	   more	  = false;
 
 	 for (int g = 0; g < nwords && !more; g += 32)
@@ -1436,30 +1446,37 @@ cta_mp_find (const DevParams &P, const Sh &sh, MpRes &mp, float price, int n)
 		  incl += t;
 	    }
 	    const int total = __shfl_sync (0xffffffffu, incl, 31);
-	    int	      rk    = taken + incl - cnt;
-	    unsigned  bits  = word;
-
-	    while (bits && rk < 32)
+	    /* lane j takes candidate number j - taken of this group of words: the word is
+	       the first whose inclusive prefix count exceeds that rank */
+	    const int r	 = lane - taken;
+	    int	      lo = 0, hi = 31;
+#pragma unroll
+	    for (int it = 0; it < 5; it++)
 	    {
-	       sh.cand [rk] = ((g + lane) << 5) + (__ffs ((int) bits) - 1);
-	       bits &= bits - 1;
-	       rk++;
+	       const int mid = (lo + hi) >> 1;
+	       const int v   = __shfl_sync (0xffffffffu, incl, mid);
+	       if (v > r)
+		  hi = mid;
+	       else
+		  lo = mid + 1;
 	    }
+	    const unsigned wsel = __shfl_sync (0xffffffffu, word, lo);
+	    const int	   esel = __shfl_sync (0xffffffffu, incl - cnt, lo);
+	    if (r >= 0 && r < total)
+	       cand = ((g + lo) << 5) + (int) __fns (wsel, 0, r - esel + 1);
 	    if (taken + total > 32)
 	       more = true;
 	    taken = taken + total > 32 ? 32 : taken + total;
 	    if (taken == 32 && g + 32 < nwords)
 	       more = true;	/* unscanned words may hold further candidates */
 	 }
-	 __syncwarp ();
-	 float key = INFINITY, costs = 0;
-	 float res [8];
-	 int   cod [FB_MAXEDGES];
-	 int   d = -1;
+	 float	   key = INFINITY, costs = 0;
+	 float	   res [8];
+	 int	   cod [FB_MAXEDGES];
+	 const int d = cand;
 
 	 if (lane < taken)
 	 {
-	    d = sh.cand [lane];
 	    const float b = sh.bnd [d];
 	    costs = mp_pass2<N> (P, sh, w, mp, n, d, sh.num [d], sh.den [d], price, res, cod);
 	    key	  = b > costs ? b : costs;	/* both must beat the running minimum */
@@ -1490,12 +1507,13 @@ cta_mp_find (const DevParams &P, const Sh &sh, MpRes &mp, float price, int n)
 	    w.min_costs	 = m;
 	    w.index	 = d;
 	 }
+	 const int last_cand = __shfl_sync (0xffffffffu, cand, 31);
 	 if (lane == 0)
 	 {
 	    if (first && winlane < 0)
 	       w.index = -1;
 	    w.wave_done = !more;
-	    w.wave_pos	= more ? sh.cand [31] + 1 : D;
+	    w.wave_pos	= more ? last_cand + 1 : D;
 	    if (taken)
 	       sh.h->pass2 += (unsigned) taken;
 	 }
@@ -2116,17 +2134,21 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 	 {
 	    const int level = F.level;
 	    short    *snap  = (sh.snaps ? sh.snaps : W.snap) + (size_t) depth * 2 * P.blob_len;
-	    unsigned *tsnap = W.treesnap + (size_t) depth * 2 * FB200_MAXLEVEL;
+	    unsigned *tsnap = sh.tsnap + (size_t) depth * 2 * FB200_MAXLEVEL;
 
-	    /* snapshot of the models (subdivide.c:188-194) */
+	    /* snapshot of the models (subdivide.c:188-194); tree_counts and tree_total are
+	       adjacent in the header */
 	    cta_copy_s16<NT> (snap, sh.blob, P.blob_len);
+	    if (tid < 32)
+	    {
+	       const unsigned *tm = (const unsigned *) ((const char *) h + offsetof (ShHdr, tree_counts));
+
+	       for (int i = tid; i < 2 * FB200_MAXLEVEL; i += 32)
+		  tsnap [i] = tm [i];
+	       __syncwarp ();
+	    }
 	    if (tid == 0)
 	    {
-	       for (int i = 0; i < FB200_MAXLEVEL; i++)
-	       {
-		  tsnap [i]		     = h->tree_counts [i];
-		  tsnap [FB200_MAXLEVEL + i] = h->tree_total [i];
-	       }
 	       F.states_snap = h->states;
 	       /* y states of the children (subdivide.c:172-183) */
 	       for (int label = 0; label < 2; label++)
@@ -2206,7 +2228,7 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 	 {
 	    const float lin = F.lincomb_costs, sub = F.subdivide_costs;
 	    short      *snap  = (sh.snaps ? sh.snaps : W.snap) + (size_t) depth * 2 * P.blob_len;
-	    unsigned   *tsnap = W.treesnap + (size_t) depth * 2 * FB200_MAXLEVEL;
+	    unsigned   *tsnap = sh.tsnap + (size_t) depth * 2 * FB200_MAXLEVEL;
 
 	    if ((lin >= FB_MAXCOSTS && sub >= FB_MAXCOSTS) || lin < sub)
 	    {
@@ -2215,13 +2237,18 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 	       /* restore snapshot or adopt the lc models; restore the tree model; drop
 		  the states created below this node (subdivide.c:409-467) */
 	       cta_copy_s16<NT> (sh.blob, fail ? snap : snap + P.blob_len, P.blob_len);
+	       if (tid < 32)
+	       {
+		  /* warp 0 only: thread 0 goes on to update the tree model without a
+		     block-wide barrier in between */
+		  unsigned *tm = (unsigned *) ((char *) h + offsetof (ShHdr, tree_counts));
+
+		  for (int i = tid; i < 2 * FB200_MAXLEVEL; i += 32)
+		     tm [i] = tsnap [i];
+		  __syncwarp ();
+	       }
 	       if (tid == 0)
 	       {
-		  for (int i = 0; i < FB200_MAXLEVEL; i++)
-		  {
-		     h->tree_counts [i] = tsnap [i];
-		     h->tree_total [i]	= tsnap [FB200_MAXLEVEL + i];
-		  }
 		  h->states = F.states_snap;	/* remove_states (wfalib.c:276-310) */
 		  if (fail)
 		     h->ret_costs = FB_MAXCOSTS;
@@ -2635,7 +2662,7 @@ fb_tile_kernel_threads (const DevParams &p, int n_tiles)
 size_t
 fb_tile_kernel_smem (const DevParams &p, int nt)
 {
-   size_t off [15];
+   size_t off [16];
 
    return smem_layout (p, nt, off);
 }
