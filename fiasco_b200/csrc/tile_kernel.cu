@@ -29,6 +29,10 @@
 #include <stddef.h>
 #include "tile_kernel.cuh"
 
+#ifndef FB200_MINB
+#define FB200_MINB 4		/* resident 128-thread blocks per SM the register budget is set for */
+#endif
+
 namespace {
 
 /*****************************************************************************
@@ -2448,7 +2452,7 @@ t0_virtual_state (const DevParams &P, const TileWs &W, ShHdr *h, int child0, int
 *****************************************************************************/
 
 template <int NT>
-__global__ void __launch_bounds__ (NT, (NT >= 512 ? 1 : NT >= 256 ? 2 : 4))
+__global__ void __launch_bounds__ (NT, (NT >= 512 ? 1 : NT >= 256 ? 2 : FB200_MINB))
 fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
 {
    extern __shared__ __align__ (16) unsigned char smem_raw [];
@@ -2708,6 +2712,11 @@ launch_nt (const DevParams &p, const TileWs *d_ws, int n_tiles, cudaStream_t str
 					     (int) smem);
    if (e != cudaSuccess)
       return e;
+   {
+      const char *cv = getenv ("FB200_CARVE");	/* experiments only: shared-memory carve-out in % */
+      if (cv)
+	 cudaFuncSetAttribute (fiasco_tile_kernel<NT>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi (cv));
+   }
    fiasco_tile_kernel<NT><<<n_tiles, NT, smem, stream>>> (p, d_ws);
    return cudaGetLastError ();
 }
