@@ -19,8 +19,10 @@ struct fb200_ctx
    int		  max_tiles, device, nt;
    size_t	  smem;
    /* device memory */
-   unsigned char *d_work;	/* per-tile private tables */
+   unsigned char *d_work;	/* [n_slots] private tables of the tiles in flight */
    size_t	  work_stride;
+   int		  n_slots;	/* workspaces: min (max_tiles, tiles that can be resident at once) */
+   int		 *d_slot_flags;	/* [n_slots] 0 = free; taken and released by the kernel's blocks */
    int16_t	 *d_pix;	/* [tiles][bands][w*h] */
    size_t	  pix_elems;	/* per tile */
    unsigned char *d_wfa;	/* [tiles][wfa_block] */
@@ -30,7 +32,6 @@ struct fb200_ctx
    int		  trace_cap;
    TileWs	 *d_ws;
    /* pinned host staging */
-   int16_t	 *h_pix;
    unsigned char *h_wfa;
    TileResult	 *h_results;
    std::vector<TileWs> ws;
@@ -301,12 +302,12 @@ fb200_destroy (fb200_ctx_t *c)
       return;
    cudaSetDevice (c->device);
    cudaFree (c->d_work);
+   cudaFree (c->d_slot_flags);
    cudaFree (c->d_pix);
    cudaFree (c->d_wfa);
    cudaFree (c->d_results);
    cudaFree (c->d_trace);
    cudaFree (c->d_ws);
-   cudaFreeHost (c->h_pix);
    cudaFreeHost (c->h_wfa);
    cudaFreeHost (c->h_results);
    for (int i = 0; i < 6; i++)
@@ -341,7 +342,23 @@ ctx_alloc (fb200_ctx_t *c, char *err, size_t errlen)
    c->wfa_block	  = wfa_layout (d, aoff);
    c->pix_elems	  = (size_t) d.bands * d.width * d.height;
 
-   CUDA_TRY (cudaMalloc (&c->d_work, c->work_stride * max_tiles));
+   /* The big tables (88 MB per 1024^2 frame) exist once per tile IN FLIGHT, not once per tile
+      of the batch: a block takes a free workspace when it starts and hands it back when its
+      frame is done, so a launch may hold any number of tiles (several waves even out the
+      different running times of the frames). */
+   {
+      int sms = 0;
+      cudaDeviceGetAttribute (&sms, cudaDevAttrMultiProcessorCount, device);
+      const int resident = sms * fb_tile_kernel_occupancy (d);
+      c->n_slots = (resident > 0 && resident < max_tiles) ? resident : max_tiles;
+   }
+   CUDA_TRY (cudaMalloc (&c->d_work, c->work_stride * c->n_slots));
+   cudaFree (c->d_slot_flags);
+   c->d_slot_flags = NULL;
+   CUDA_TRY (cudaMalloc (&c->d_slot_flags, sizeof (int) * c->n_slots));
+   CUDA_TRY (cudaMemset (c->d_slot_flags, 0, sizeof (int) * c->n_slots));
+   c->dp.n_slots    = c->n_slots;
+   c->dp.slot_flags = c->d_slot_flags;
    CUDA_TRY (cudaMalloc (&c->d_wfa, c->wfa_block * max_tiles));
    CUDA_TRY (cudaMallocHost (&c->h_wfa, c->wfa_block * max_tiles));
    if (!c->d_pix)
@@ -349,7 +366,6 @@ ctx_alloc (fb200_ctx_t *c, char *err, size_t errlen)
       CUDA_TRY (cudaMalloc (&c->d_pix, c->pix_elems * 2 * max_tiles));
       CUDA_TRY (cudaMalloc (&c->d_results, sizeof (TileResult) * max_tiles));
       CUDA_TRY (cudaMalloc (&c->d_ws, sizeof (TileWs) * max_tiles));
-      CUDA_TRY (cudaMallocHost (&c->h_pix, c->pix_elems * 2 * max_tiles));
       CUDA_TRY (cudaMallocHost (&c->h_results, sizeof (TileResult) * max_tiles));
       CUDA_TRY (cudaStreamCreateWithFlags (&c->stream, cudaStreamNonBlocking));
       for (int i = 0; i < 6; i++)
@@ -358,7 +374,8 @@ ctx_alloc (fb200_ctx_t *c, char *err, size_t errlen)
    c->ws.resize (max_tiles);
    for (int t = 0; t < max_tiles; t++)
    {
-      unsigned char *wb = c->d_work + c->work_stride * t;
+      /* tile t's entry also describes workspace t (for t < n_slots) */
+      unsigned char *wb = c->d_work + c->work_stride * (t < c->n_slots ? t : 0);
       unsigned char *ab = c->d_wfa + c->wfa_block * t;
       TileWs	    &w	= c->ws [t];
 
@@ -487,13 +504,14 @@ fb200_upload (fb200_ctx_t *c, int n_tiles, const int16_t *const *planes, char *e
    }
    CUDA_TRY (cudaSetDevice (c->device));
    const size_t plane = (size_t) c->dp.width * c->dp.height;
+   /* straight from the caller's planes: a true asynchronous DMA when they are pinned, the
+      driver's own staging when they are pageable -- no second copy through a buffer of ours */
+   CUDA_TRY (cudaEventRecord (c->ev [0], c->stream));
    for (int t = 0; t < n_tiles; t++)
       for (int b = 0; b < c->dp.bands; b++)
-	 memcpy (c->h_pix + c->pix_elems * t + plane * b, planes [t * c->dp.bands + b],
-		 plane * 2);
-   CUDA_TRY (cudaEventRecord (c->ev [0], c->stream));
-   CUDA_TRY (cudaMemcpyAsync (c->d_pix, c->h_pix, c->pix_elems * 2 * n_tiles,
-			      cudaMemcpyHostToDevice, c->stream));
+	 CUDA_TRY (cudaMemcpyAsync (c->d_pix + c->pix_elems * t + plane * b,
+				    planes [t * c->dp.bands + b], plane * 2,
+				    cudaMemcpyHostToDevice, c->stream));
    CUDA_TRY (cudaEventRecord (c->ev [1], c->stream));
    CUDA_TRY (cudaStreamSynchronize (c->stream));
    cudaEventElapsedTime (&c->stats.h2d_ms, c->ev [0], c->ev [1]);
@@ -512,6 +530,8 @@ fb200_launch (fb200_ctx_t *c, int n_tiles, void *cuda_stream, char *err, size_t 
    CUDA_TRY (cudaSetDevice (c->device));
    cudaStream_t s = cuda_stream ? (cudaStream_t) cuda_stream : c->stream;
    CUDA_TRY (cudaEventRecord (c->ev [2], s));
+   if (n_tiles > c->n_slots)	/* a launch that died may have left workspaces marked busy */
+      CUDA_TRY (cudaMemsetAsync (c->d_slot_flags, 0, sizeof (int) * c->n_slots, s));
    CUDA_TRY (fb_launch_tile_kernel (c->dp, c->d_ws, n_tiles, s));
    CUDA_TRY (cudaEventRecord (c->ev [3], s));
    c->launched_tiles	    = n_tiles;

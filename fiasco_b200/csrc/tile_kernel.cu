@@ -303,6 +303,7 @@ struct Sh			/* pointers into dynamic shared memory */
    unsigned *tsnap;		/* [ndepth][2 * MAXLEVEL] tree-model snapshots of the DFS */
    Frame   *frames;
    int	    dcap;
+   int	    scratch_len;	/* floats from num to the end of bnd / G: row scratch of append_state */
 };
 
 __host__ __device__ inline size_t align16 (size_t x) { return (x + 15) & ~(size_t) 15; }
@@ -316,12 +317,12 @@ smem_layout (const DevParams &p, int nt, size_t *off /* [16] */)
    off [0] = o; o += align16 (sizeof (ShHdr));
    off [1] = o; o += align16 (dcap * 4);			/* num */
    off [2] = o; o += align16 (dcap * 4);			/* den */
+   off [8] = o; o += align16 (((dcap + 31) / 32 * 32) * 4);	/* bnd */
    off [3] = o; o += (p.big & 1) ? 0 : align16 (dcap * 4 * (p.max_elements > 1 ? p.max_elements - 1 : 1)); /* G */
    off [4] = o; o += align16 (dcap);				/* used */
    off [5] = o; o += align16 ((size_t) p.s_cap * 2);		/* pool */
    off [6] = o; o += align16 (((size_t) 1 << p.lc_max) * 4);	/* pixels */
    off [7] = o; o += align16 ((size_t) p.tn * 4);		/* norm_i */
-   off [8] = o; o += align16 (((dcap + 31) / 32 * 32) * 4);	/* bnd */
    off [9] = o; o += align16 (((dcap + 31) / 32) * 4 + 32 * 4);	/* cmask, cand */
    off [10] = o; o += align16 ((size_t) p.blob_len * 2);	/* blob */
    {
@@ -362,6 +363,7 @@ carve (unsigned char *base, const DevParams &p, int nt, float *gglob, float *bnd
    s.blob   = (short *) (base + off [10]);
    s.snaps  = off [11] == (size_t) -1 ? (short *) 0 : (short *) (base + off [11]);
    s.dcap   = p.s_cap + 1;
+   s.scratch_len = (int) ((off [4] - off [1]) / 4);
    s.l2	    = (double *) (base + off [12]);
    s.frames = (Frame *) (base + off [13]);
    s.qt_dc  = (float *) (base + off [14]);
@@ -908,7 +910,11 @@ cta_state_products (const DevParams &P, const TileWs &W, const Sh &sh, unsigned 
    ShHdr    *h	  = sh.h;
    const int dcap = sh.dcap;
    /* scratch rows: the pursuit's work arrays are idle while a state is appended */
-   const int NR = (P.big & 1) ? 3 : 3 + (P.max_elements > 1 ? P.max_elements - 1 : 1);
+   /* scratch rows: the pursuit's work arrays (one contiguous area) are idle while a state is
+      appended; rows of s + 1 floats are packed into it, so the shorter the rows the more
+      source rows of the level below can be staged */
+   const int stride = (int) ((s + 1 + 3) & ~3u);
+   const int NR	    = min (2 * (FB_MAXEDGES + 1), sh.scratch_len / stride);
 
    if (tid == 0)
    {
@@ -1001,8 +1007,7 @@ cta_state_products (const DevParams &P, const TileWs &W, const Sh &sh, unsigned 
       const int nsrc = h->ap_nsrc < NR ? h->ap_nsrc : NR;
       for (int j = 0; j < nsrc; j++)
       {
-	 float	     *row = j == 0 ? sh.num : j == 1 ? sh.den : j == 2 ? sh.bnd
-						 : sh.G + (size_t) (j - 3) * dcap;
+	 float	     *row = sh.num + (size_t) j * stride;
 	 const float *src = W.SS + ((size_t) (li - 1) * P.s_cap + h->ap_src [j]) * P.s_cap;
 	 cta_copy_f32<NT> (row, src, s + 1);
       }
@@ -1026,8 +1031,7 @@ cta_state_products (const DevParams &P, const TileWs &W, const Sh &sh, unsigned 
 	       const int    j	= h->ap_row [label][k];
 	       const float *row = j < 0 ? W.SS + ((size_t) (li - 1) * P.s_cap
 						  + h->ap_dom [label][k]) * P.s_cap
-					: j == 0 ? sh.num : j == 1 ? sh.den : j == 2 ? sh.bnd
-					: sh.G + (size_t) (j - 3) * dcap;
+					: sh.num + (size_t) j * stride;
 	       float sum = 0;
 
 	       if (c2 != FB_RANGE)
@@ -1539,7 +1543,7 @@ template <int NT>
 __device__ void
 cta_matching_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &mp,
 		      int level, unsigned image, unsigned address, float tree_bits,
-		      float price, int y_state_in)
+		      float price, int y_state_in, int excluded)
 {
    const int	tid	 = threadIdx.x;
    const int	lane	 = tid & 31;
@@ -1588,13 +1592,23 @@ cta_matching_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &
       sh.h->mp_calls++;
       sh.h->mp_bytes += 8ull * (unsigned) w.D;
    }
-   /* log2 tables of the models (the models do not change during one pursuit) */
+   /*
+    *  Grey bands (no y-state): nothing the other threads need depends on thread 0's scalars,
+    *  so the tables and the gathers below proceed next to them; with a y-state the pool
+    *  size and the y-slot come from thread 0 first.
+    */
+   const bool grey = y_state_in < 0;	/* uniform */
+
+   if (!grey)
+      __syncthreads ();
+   /* log2 tables of the models (the models do not change during one pursuit); entries are
+      handed out from the last thread down: warp 0 is busy with the scalars */
    {
       const int	   ctx	  = level - P.coeff_min_level;
       const short *counts = sh.blob + MB_COUNTS;
       const short *lv	  = counts + P.aac_dc_size + ctx * P.aac_lvl_size;
 
-      for (int i = tid; i < P.aac_dc_size + P.aac_lvl_size + FB_MAXEDGES + 2; i += NT)
+      for (int i = NT - 1 - tid; i < P.aac_dc_size + P.aac_lvl_size + FB_MAXEDGES + 2; i += NT)
       {
 	 if (i < P.aac_dc_size)
 	    w.l2_dc [i] = dev_log2d (counts [i] / (float) sh.blob [MB_TOTALS]);
@@ -1611,11 +1625,9 @@ cta_matching_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &
 	 }
       }
    }
-   __syncthreads ();
-
-   const int   D     = w.D;
-   const int   li    = w.li;
-   const float fsize = (float) w.size;
+   const int   D     = grey ? (int) BLOB_U16 (sh, MB_N) : w.D;
+   const int   li    = level - P.lmin;
+   const float fsize = (float) (1 << level);
 
    /* ---- numerators / denominators (approx.c:358-374) ---- */
    for (int d0 = tid; d0 < D; d0 += 4 * NT)
@@ -1646,15 +1658,15 @@ cta_matching_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &
 	       used = 1;
 	    else if (fabsf (nm [u]) < min_norm)
 	       used = 1;
-	    for (int e = 0; e < FB_MAXEDGES && mp.exclude [e] != FB_NO_EDGE; e++)
-	       if (mp.exclude [e] == d)
-		  used = 1;
+	    if (d == excluded)
+	       used = 1;
 	    sh.num [d]	= nm [u];
 	    sh.den [d]	= dn [u];
 	    sh.used [d] = used;
 	 }
       }
    }
+   __syncthreads ();
    if (tid == 0)
    {
       /* costs of the empty linear combination (approx.c:391-400) */
@@ -1860,7 +1872,7 @@ cta_approximate_range (const DevParams &P, const TileWs &W, const Sh &sh, float 
 	 __syncthreads ();
       /* (the prologue of the pursuit starts with thread-0 work followed by a barrier) */
       cta_matching_pursuit<NT> (P, W, sh, m, level, image, address, out->tree_bits, price,
-				y_state);
+				y_state, round ? (int) h->mp.indices [0] : -1);
    }
    if (P.second_domain_block)
    {
@@ -2456,7 +2468,45 @@ __global__ void __launch_bounds__ (NT, (NT >= 512 ? 1 : NT >= 256 ? 2 : FB200_MI
 fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
 {
    extern __shared__ __align__ (16) unsigned char smem_raw [];
-   const TileWs W   = ws_array [blockIdx.x];
+   TileWs	W    = ws_array [blockIdx.x];
+   int		slot = -1;
+
+   /*
+    *  More tiles than workspaces: take a free one (entry i of ws_array also describes
+    *  workspace i).  At most n_slots blocks are resident at any time, so a free one exists;
+    *  the scan starts at a different place on every SM.  Everything the kernel reads from a
+    *  workspace it has written itself before, so the previous user's data never shows.
+    */
+   if ((int) gridDim.x > P.n_slots)	/* uniform */
+   {
+      __shared__ int s_slot;
+
+      if (threadIdx.x == 0)
+      {
+	 unsigned smid;
+	 asm volatile ("mov.u32 %0, %%smid;" : "=r" (smid));
+	 int i = (int) ((smid * 4u) % (unsigned) P.n_slots);
+	 while (atomicCAS (P.slot_flags + i, 0, 1) != 0)
+	    i = i + 1 == P.n_slots ? 0 : i + 1;
+	 __threadfence ();
+	 s_slot = i;
+      }
+      __syncthreads ();
+      slot = s_slot;
+      const TileWs &S = ws_array [slot];
+      W.img	  = S.img;
+      W.T	  = S.T;
+      W.SS	  = S.SS;
+      W.diag	  = S.diag;
+      W.trans	  = S.trans;
+      W.bndglob	  = S.bndglob;
+      W.Gglob	  = S.Gglob;
+      W.snap	  = S.snap;
+      W.treesnap  = S.treesnap;
+      W.blob_save = S.blob_save;
+      W.tree_save = S.tree_save;
+      W.pool_save = S.pool_save;
+   }
    const Sh	sh  = carve (smem_raw, P, NT, W.Gglob, W.bndglob);
    ShHdr       *h   = sh.h;
    const int	tid = threadIdx.x;
@@ -2602,6 +2652,15 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
       r->cyc_append = (unsigned long long) h->cyc_append;
       for (int i = 0; i < 16; i++)
 	 r->lap [i] = (unsigned long long) h->lap [i];
+   }
+   if (slot >= 0)
+   {
+      __syncthreads ();
+      if (tid == 0)
+      {
+	 __threadfence ();
+	 atomicExch (P.slot_flags + slot, 0);
+      }
    }
 }
 

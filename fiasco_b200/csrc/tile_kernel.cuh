@@ -46,6 +46,8 @@ struct DevParams
    int	 aac_dc_size, aac_lvl_size, blob_len;
    int	 trace_cap;
    int	 first_band, last_band; /* bands processed by this launch */
+   int	 n_slots;		/* workspaces (img, T, SS, ...); tiles beyond that share them */
+   int	*slot_flags;		/* [n_slots] 0 = free */
    int	 big;			/* large state capacity, so that more tiles fit on an SM: bit 0 =
 				   Gram rows in global memory, bit 1 = model snapshots in global */
 };

@@ -39,7 +39,7 @@ def main():
     probe.close()
     sms = 148
     B = sms * per_sm if per_sm else res
-    B = min(B, 1700)                    # 88 MB of tables per frame: stay well inside 180 GB
+    B = min(B, 8192)
     planes = [ffi.pixels_from_grey(gen_frames.chan(1024, 1024, 3 + k)).reshape(-1) for k in range(distinct)]
     planes = [planes[i % distinct] for i in range(B)]
     enc = F.TileEncoder(p, B)
