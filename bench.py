@@ -277,6 +277,11 @@ def run_ours(args):
     value = mpx_step * args.steps / (step_ms_max / 1e3)
     e2e_value = mpx_step * e2e_steps / e2e_max
     peak, peak_src = peaks()
+    traffic, traffic_src = None, None
+    tj = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tj):                        # DRAM bytes per frame measured by ncu (never under this run)
+        t_ = json.load(open(tj))
+        traffic, traffic_src = t_["dram_bytes_per_frame"] * B, t_["source"]
     alg_bytes = st["ip_bytes"] + st["mp_bytes"] + st["ss_bytes"]      # per launch, this rank
     launch_ms = step_ms / args.steps
     achieved = alg_bytes / (launch_ms / 1e3) / 1e9
@@ -299,11 +304,13 @@ def run_ours(args):
                 "note": "fb200_encode_tiles(): pinned host int16 planes -> H2D -> tile kernel -> D2H automata"},
         "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "fiasco_tile_kernel",
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "fiasco_tile_kernel",
                      "algorithmic_bytes_per_launch": int(alg_bytes),
                      "bytes_model": "sum over lc_max blocks (4*2^lc_max + 376*S_b) + 8D per pursuit + 4D per "
                                     "Gram-Schmidt step + 4*levels*(s+1) per new state (SURVEY.md 8d)",
-                     "note": "the path is latency bound (dependent chain of ~20k pursuits per frame), not HBM bound"},
+                     "note": "the path is bound by its serial chain (~20k dependent pursuits per frame; ncu: barrier waits, "
+                             "instruction fetch, fixed-latency dependencies), not by HBM; traffic > algorithmic bytes "
+                             "because the tables of the frames in flight exceed L2 (profiles/README.md)"},
         "cpu_baseline": {"value": cpu_value, "unit": "Mpixels/s", "cores": 1, "kind": kind,
                          "sample": "2 of the %d frames, one single-threaded process (%.1f s)" % (B, cpu_s)},
         "clocks": clocks,
