@@ -200,6 +200,41 @@ def test_gpu_batch_of_tiles_equals_individual_streams():
     assert F.wfa_lines(ws[15]) == O.golden_wfa_lines("g1024t15_q20_z0")
 
 
+def test_gpu_more_tiles_than_workspaces():
+    """A launch with more tiles than can be resident (the big tables exist once per RESIDENT tile;
+    blocks take a workspace when they start and return it when done): every tile of three waves
+    equals the automaton of the same crop encoded alone, and the rtob o btor identity the kernel's
+    quantiser tables rely on holds on the device."""
+    g = gen_frames.frame("g1024")
+    crops = [np.ascontiguousarray(g[y:y + 64, x:x + 64]) for y in range(0, 512, 64) for x in range(0, 512, 64)]
+    p = ffi.make_params(64, 64, 1, 20.0, 0)
+    probe = F.TileEncoder(p, 1)
+    resident = probe.resident_tiles()
+    probe.close()
+    assert resident >= 148
+    n = 2 * resident + 37
+    enc = F.TileEncoder(p, n)
+    try:
+        planes = [O.planes_of(crops[i % len(crops)])[0] for i in range(n)]
+        ws, _ = enc.encode(planes)
+        ws_again, _ = enc.encode(planes)             # the flags are all free again after a launch
+    finally:
+        enc.close()
+    single = {}
+    one = F.TileEncoder(p, 1)
+    try:
+        for k in range(len(crops)):
+            single[k] = F.wfa_lines(one.encode(O.planes_of(crops[k]))[0][0])
+    finally:
+        one.close()
+    for i in range(n):
+        assert F.wfa_lines(ws[i]) == single[i % len(crops)], "tile %d of %d (resident %d)" % (i, n, resident)
+    for i in (0, resident, n - 1):
+        assert F.wfa_lines(ws_again[i]) == single[i % len(crops)]
+    for k in (0, 17, 63):
+        assert_same_wfa(ws[k], O.encode(crops[k], quality=20, optimize=0))
+
+
 def test_gpu_deterministic_and_reusable_context():
     img = gen_frames.frame("g256")
     p = ffi.make_params(256, 256, 1, 20.0, 0)
