@@ -285,6 +285,14 @@ def run_ours(args):
     alg_bytes = st["ip_bytes"] + st["mp_bytes"] + st["ss_bytes"]      # per launch, this rank
     launch_ms = step_ms / args.steps
     achieved = alg_bytes / (launch_ms / 1e3) / 1e9
+    # the inner-product phase (pixels -> range x state products, SURVEY 8d "k_leaf_ip") seen alone: its
+    # algorithmic bytes over the time the resident thread blocks spent in it (in-kernel cycle counters)
+    ip_phase = None
+    if st["cyc_T"] and clocks and clocks.get("sm_mhz"):
+        ip_s = st["cyc_T"] / (clocks["sm_mhz"] * 1e6) / min(B, resident)
+        ip_gbs = st["ip_bytes"] / ip_s / 1e9
+        ip_phase = {"achieved": ip_gbs, "unit": "GB/s", "frac": ip_gbs / peak, "share_of_launch": ip_s / (launch_ms / 1e3),
+                    "how": "ip_bytes of one launch / (sum of the blocks' cycles in the phase / SM clock / resident blocks)"}
     # CPU baseline: the reference (or the port) on ONE core, a bounded sample of the same workload
     cpu_s, kind = cpu_encode_frames(imgs[:2], 1)
     cpu_value = 2 * W_ * H_ / 1e6 / cpu_s
@@ -315,6 +323,7 @@ def run_ours(args):
                          "sample": "2 of the %d frames, one single-threaded process (%.1f s)" % (B, cpu_s)},
         "clocks": clocks,
         "phase_cycles": {k: int(st[k]) for k in ("cyc_total", "cyc_T", "cyc_mp", "cyc_append")},
+        "ip_phase": ip_phase,
         "work": {k: int(st[k]) for k in ("mp_calls", "mp_steps", "blocks", "states")},
     }
     if sum(st["lap"]):                            # only a -DFB200_LAPS diagnostics build fills the lap timers

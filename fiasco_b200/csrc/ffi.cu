@@ -244,8 +244,6 @@ derive (const fb200_params_t *p, DevParams *d, char *err, size_t errlen)
       if (e)
 	 d->big = atoi (e);
    }
-   d->first_band   = 0;
-   d->last_band	   = p->bands - 1;
    return FB200_OK;
 }
 
@@ -257,7 +255,7 @@ up256 (size_t x)
 
 /* carve the private tables of one tile out of d_work */
 static size_t
-work_layout (const DevParams &d, size_t *off /* [12] */)
+work_layout (const DevParams &d, size_t *off /* [7] */)
 {
    size_t o = 0, sc = (size_t) d.s_cap;
 
@@ -266,13 +264,8 @@ work_layout (const DevParams &d, size_t *off /* [12] */)
    off [2] = o; o += up256 ((size_t) d.nlev * sc * sc * 4);		/* SS */
    off [3] = o; o += up256 ((size_t) d.nlev * sc * 4);			/* diag */
    off [4] = o; o += up256 ((size_t) FB_MAXDEPTH * 2 * d.blob_len * 2);	/* snap */
-   off [5] = o; o += up256 ((size_t) FB_MAXDEPTH * 2 * FB200_MAXLEVEL * 4); /* treesnap */
-   off [6] = o; o += up256 ((size_t) d.blob_len * 2);			/* blob_save */
-   off [7] = o; o += up256 ((size_t) 2 * FB200_MAXLEVEL * 4);		/* tree_save */
-   off [8] = o; o += up256 (sc * 2);					/* pool_save */
-   off [9] = o; o += up256 (sc * sizeof (Trans));			/* trans */
-   off [10] = o; o += up256 ((sc + 1) * 4 * FB_MAXEDGES);		/* Gglob */
-   off [11] = o; o += up256 ((sc + 64) * 4);				/* bndglob */
+   off [5] = o; o += up256 (sc * sizeof (Trans));			/* trans */
+   off [6] = o; o += up256 ((sc + 1) * 4 * FB_MAXEDGES);		/* Gglob */
    return o;
 }
 
@@ -337,7 +330,7 @@ ctx_alloc (fb200_ctx_t *c, char *err, size_t errlen)
 	 return FB200_EINVAL;
       }
    }
-   size_t woff [12], aoff [10];
+   size_t woff [7], aoff [10];
    c->work_stride = work_layout (d, woff);
    c->wfa_block	  = wfa_layout (d, aoff);
    c->pix_elems	  = (size_t) d.bands * d.width * d.height;
@@ -386,13 +379,8 @@ ctx_alloc (fb200_ctx_t *c, char *err, size_t errlen)
       w.SS	  = (float *) (wb + woff [2]);
       w.diag	  = (float *) (wb + woff [3]);
       w.snap	  = (int16_t *) (wb + woff [4]);
-      w.treesnap  = (unsigned *) (wb + woff [5]);
-      w.blob_save = (int16_t *) (wb + woff [6]);
-      w.tree_save = (unsigned *) (wb + woff [7]);
-      w.pool_save = (int16_t *) (wb + woff [8]);
-      w.trans	  = (Trans *) (wb + woff [9]);
-      w.Gglob	  = (float *) (wb + woff [10]);
-      w.bndglob	  = (float *) (wb + woff [11]);
+      w.trans	  = (Trans *) (wb + woff [5]);
+      w.Gglob	  = (float *) (wb + woff [6]);
       w.final_d	       = (float *) (ab + aoff [0]);
       w.weight	       = (float *) (ab + aoff [1]);
       w.into	       = (int16_t *) (ab + aoff [2]);

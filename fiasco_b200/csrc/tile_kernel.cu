@@ -219,7 +219,6 @@ struct Frame			/* one activation record of subdivide() */
 
 struct MpRes			/* mp_t, codec/approx.c:41-51 */
 {
-   short exclude [FB_MAXEDGES];
    short indices [FB_MAXEDGES + 1];
    short into [FB_MAXEDGES + 1];
    float weight [FB_MAXEDGES];
@@ -295,7 +294,6 @@ struct Sh			/* pointers into dynamic shared memory */
    int	   *norm_i;		/* [tn] integer sum of squares per node */
    float   *bnd;		/* [dcap32] pass-1 bound per domain (INF: not usable) */
    unsigned *cmask;		/* [dcap32 / 32] candidate bit masks of the current wave */
-   int	   *cand;		/* [32] candidates of the current wave, index order */
    short   *blob;		/* [blob_len] current probability models */
    short   *snaps;		/* [ndepth][2][blob_len] model snapshots of the DFS, or NULL */
    double  *l2;			/* [aac_dc_size + aac_lvl_size] */
@@ -323,7 +321,7 @@ smem_layout (const DevParams &p, int nt, size_t *off /* [16] */)
    off [5] = o; o += align16 ((size_t) p.s_cap * 2);		/* pool */
    off [6] = o; o += align16 (((size_t) 1 << p.lc_max) * 4);	/* pixels */
    off [7] = o; o += align16 ((size_t) p.tn * 4);		/* norm_i */
-   off [9] = o; o += align16 (((dcap + 31) / 32) * 4 + 32 * 4);	/* cmask, cand */
+   off [9] = o; o += align16 (((dcap + 31) / 32) * 4);		/* cmask */
    off [10] = o; o += align16 ((size_t) p.blob_len * 2);	/* blob */
    {
       /* model snapshots of the DFS stay on chip when they are small (default models:
@@ -342,7 +340,7 @@ smem_layout (const DevParams &p, int nt, size_t *off /* [16] */)
 }
 
 __device__ __forceinline__ Sh
-carve (unsigned char *base, const DevParams &p, int nt, float *gglob, float *bndglob)
+carve (unsigned char *base, const DevParams &p, int nt, float *gglob)
 {
    size_t off [16];
    Sh	  s;
@@ -356,10 +354,8 @@ carve (unsigned char *base, const DevParams &p, int nt, float *gglob, float *bnd
    s.pool   = (short *) (base + off [5]);
    s.pixels = (float *) (base + off [6]);
    s.norm_i = (int *) (base + off [7]);
-   (void) bndglob;
    s.bnd    = (float *) (base + off [8]);
    s.cmask  = (unsigned *) (base + off [9]);
-   s.cand   = (int *) (s.cmask + ((size_t) p.s_cap + 1 + 31) / 32);
    s.blob   = (short *) (base + off [10]);
    s.snaps  = off [11] == (size_t) -1 ? (short *) 0 : (short *) (base + off [11]);
    s.dcap   = p.s_cap + 1;
@@ -1537,7 +1533,8 @@ cta_mp_find (const DevParams &P, const Sh &sh, MpRes &mp, float price, int n)
 
 /*
  *  One matching pursuit over the current pool for the range (level, image, address).
- *  'mp' lives in shared memory; mp.exclude must be set by the caller.
+ *  'mp' lives in shared memory; 'excluded' is the domain index the second_domain_block retry
+ *  must not use (approx.c:112-116), or -1.
  */
 template <int NT>
 __device__ void
@@ -1857,19 +1854,12 @@ cta_approximate_range (const DevParams &P, const TileWs &W, const Sh &sh, float 
    {
       MpRes &m = round ? h->tmp : h->mp;
 
-      if (threadIdx.x == 0)
-      {
-	 if (round)
-	 {
-	    h->tmp	       = h->mp;
-	    h->tmp.exclude [0] = h->tmp.indices [0];
-	    h->tmp.exclude [1] = FB_NO_EDGE;
-	 }
-	 else
-	    h->mp.exclude [0] = FB_NO_EDGE;
-      }
       if (round)
+      {
+	 if (threadIdx.x == 0)
+	    h->tmp = h->mp;
 	 __syncthreads ();
+      }
       /* (the prologue of the pursuit starts with thread-0 work followed by a barrier) */
       cta_matching_pursuit<NT> (P, W, sh, m, level, image, address, out->tree_bits, price,
 				y_state, round ? (int) h->mp.indices [0] : -1);
@@ -2499,15 +2489,10 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
       W.SS	  = S.SS;
       W.diag	  = S.diag;
       W.trans	  = S.trans;
-      W.bndglob	  = S.bndglob;
       W.Gglob	  = S.Gglob;
       W.snap	  = S.snap;
-      W.treesnap  = S.treesnap;
-      W.blob_save = S.blob_save;
-      W.tree_save = S.tree_save;
-      W.pool_save = S.pool_save;
    }
-   const Sh	sh  = carve (smem_raw, P, NT, W.Gglob, W.bndglob);
+   const Sh	sh  = carve (smem_raw, P, NT, W.Gglob);
    ShHdr       *h   = sh.h;
    const int	tid = threadIdx.x;
 
@@ -2540,7 +2525,6 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
    }
    __syncthreads ();
 
-   if (P.first_band == 0)
    {
       cta_init_basis<NT> (P, W, sh);
       /* init_tree_model (bintree.c:70-93), rle_model_alloc (domain-pool.c:655-672),

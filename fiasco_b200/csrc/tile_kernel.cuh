@@ -45,7 +45,6 @@ struct DevParams
    int	 coeff_min_level;	/* context base of the aac model (coder.c:731) */
    int	 aac_dc_size, aac_lvl_size, blob_len;
    int	 trace_cap;
-   int	 first_band, last_band; /* bands processed by this launch */
    int	 n_slots;		/* workspaces (img, T, SS, ...); tiles beyond that share them */
    int	*slot_flags;		/* [n_slots] 0 = free */
    int	 big;			/* large state capacity, so that more tiles fit on an SM: bit 0 =
@@ -69,7 +68,6 @@ struct TileWs
    float   *SS;			/* [nlev][s_cap][s_cap]	  state x state products */
    float   *diag;		/* [nlev][s_cap]	  <s,s> */
    Trans   *trans;		/* [s_cap]		  packed transitions */
-   float   *bndglob;		/* [s_cap+32] pass-1 bounds when not in smem */
    float   *Gglob;		/* [max_elements-1][s_cap+1] Gram-Schmidt rows when not in smem */
    /* automaton */
    float   *final_d;		/* [s_cap] */
@@ -83,11 +81,6 @@ struct TileWs
    uint8_t *y_column;		/* [s_cap][2] */
    /* model snapshots of the DFS */
    int16_t *snap;		/* [FB_MAXDEPTH][2][blob_len] */
-   unsigned *treesnap;		/* [FB_MAXDEPTH][2 * MAXLEVEL] */
-   /* persistent coder state between band launches */
-   int16_t *blob_save;		/* [blob_len] */
-   unsigned *tree_save;		/* [2 * MAXLEVEL] */
-   int16_t *pool_save;		/* [s_cap] */
    struct TileResult *result;
    fb200_trace_rec_t *trace;	/* [trace_cap] or NULL */
 };
