@@ -904,7 +904,6 @@ cta_state_products (const DevParams &P, const TileWs &W, const Sh &sh, unsigned 
 {
    const int tid  = threadIdx.x;
    ShHdr    *h	  = sh.h;
-   const int dcap = sh.dcap;
    /* scratch rows: the pursuit's work arrays are idle while a state is appended */
    /* scratch rows: the pursuit's work arrays (one contiguous area) are idle while a state is
       appended; rows of s + 1 floats are packed into it, so the shorter the rows the more
@@ -1543,8 +1542,6 @@ cta_matching_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &
 		      float price, int y_state_in, int excluded)
 {
    const int	tid	 = threadIdx.x;
-   const int	lane	 = tid & 31;
-   const int	warp	 = tid >> 5;
    MpWork      &w	 = sh.h->w;
    const float	min_norm = 2e-3f;
    const int	dcap	 = sh.dcap;
@@ -2454,7 +2451,7 @@ t0_virtual_state (const DevParams &P, const TileWs &W, ShHdr *h, int child0, int
 *****************************************************************************/
 
 template <int NT>
-__global__ void __launch_bounds__ (NT, (NT >= 512 ? 1 : NT >= 256 ? 2 : FB200_MINB))
+__global__ void __launch_bounds__ (NT, (NT >= 512 ? 1 : NT >= 256 ? 2 : NT >= 128 ? FB200_MINB : 5))
 fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
 {
    extern __shared__ __align__ (16) unsigned char smem_raw [];
@@ -2694,7 +2691,7 @@ fb_tile_kernel_threads (const DevParams &p, int n_tiles)
    /* threads span the domain pool: small tiles have ~100-250 domains, a 1024^2 frame
       up to ~1500 */
    const char *e = getenv ("FB200_NT");	/* experiments only */
-   if (e && (atoi (e) == 128 || atoi (e) == 256 || atoi (e) == 512))
+   if (e && (atoi (e) == 96 || atoi (e) == 128 || atoi (e) == 256 || atoi (e) == 512))
       return atoi (e);
    (void) p;
    /* few tiles: latency matters, give each tile a whole SM's worth of threads; a full
@@ -2773,6 +2770,7 @@ fb_launch_tile_kernel (const DevParams &p, const TileWs *d_ws, int n_tiles,
       return e;
    switch (fb_tile_kernel_threads (p, n_tiles))
    {
+      case 96:	return launch_nt<96> (p, d_ws, n_tiles, stream);
       case 128: return launch_nt<128> (p, d_ws, n_tiles, stream);
       case 256: return launch_nt<256> (p, d_ws, n_tiles, stream);
       default:	return launch_nt<512> (p, d_ws, n_tiles, stream);
@@ -2802,6 +2800,7 @@ fb_tile_kernel_occupancy (const DevParams &p)
 {
    switch (fb_tile_kernel_threads (p, 1 << 20))
    {
+      case 96:	return occupancy_nt<96> (p);
       case 128: return occupancy_nt<128> (p);
       case 256: return occupancy_nt<256> (p);
       default:	return occupancy_nt<512> (p);
