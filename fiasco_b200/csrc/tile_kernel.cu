@@ -342,10 +342,11 @@ smem_layout (const DevParams &p, int nt, size_t *off /* [16] */)
 __device__ __forceinline__ Sh
 carve (unsigned char *base, const DevParams &p, int nt, float *gglob)
 {
-   size_t off [16];
-   Sh	  s;
+   /* the offsets come ready-made from the host (launch_nt): what the compiler rematerialises
+      when it is short of registers is then one constant-bank load, not the layout arithmetic */
+   const unsigned *off = p.sm_off;
+   Sh		   s;
 
-   smem_layout (p, nt, off);
    s.h	    = (ShHdr *) (base + off [0]);
    s.num    = (float *) (base + off [1]);
    s.den    = (float *) (base + off [2]);
@@ -357,7 +358,7 @@ carve (unsigned char *base, const DevParams &p, int nt, float *gglob)
    s.bnd    = (float *) (base + off [8]);
    s.cmask  = (unsigned *) (base + off [9]);
    s.blob   = (short *) (base + off [10]);
-   s.snaps  = off [11] == (size_t) -1 ? (short *) 0 : (short *) (base + off [11]);
+   s.snaps  = off [11] == 0xffffffffu ? (short *) 0 : (short *) (base + off [11]);
    s.dcap   = p.s_cap + 1;
    s.scratch_len = (int) ((off [4] - off [1]) / 4);
    s.l2	    = (double *) (base + off [12]);
@@ -2744,9 +2745,14 @@ upload_tables (void)
 
 template <int NT>
 static cudaError_t
-launch_nt (const DevParams &p, const TileWs *d_ws, int n_tiles, cudaStream_t stream)
+launch_nt (const DevParams &p_in, const TileWs *d_ws, int n_tiles, cudaStream_t stream)
 {
-   const size_t smem = fb_tile_kernel_smem (p, NT);
+   DevParams	p = p_in;
+   size_t	off [16];
+   const size_t smem = smem_layout (p, NT, off);
+
+   for (int i = 0; i < 16; i++)
+      p.sm_off [i] = off [i] == (size_t) -1 ? 0xffffffffu : (unsigned) off [i];
    cudaError_t	e    = cudaFuncSetAttribute (fiasco_tile_kernel<NT>,
 					     cudaFuncAttributeMaxDynamicSharedMemorySize,
 					     (int) smem);

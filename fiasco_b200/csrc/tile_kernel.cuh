@@ -45,6 +45,7 @@ struct DevParams
    int	 coeff_min_level;	/* context base of the aac model (coder.c:731) */
    int	 aac_dc_size, aac_lvl_size, blob_len;
    int	 trace_cap;
+   unsigned sm_off [16];	/* shared-memory layout of the block (filled by the launcher) */
    int	 n_slots;		/* workspaces (img, T, SS, ...); tiles beyond that share them */
    int	*slot_flags;		/* [n_slots] 0 = free */
    int	 big;			/* large state capacity, so that more tiles fit on an SM: bit 0 =
