@@ -2456,8 +2456,13 @@ __global__ void __launch_bounds__ (NT, (NT >= 512 ? 1 : NT >= 256 ? 2 : NT >= 12
 fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
 {
    extern __shared__ __align__ (16) unsigned char smem_raw [];
-   TileWs	W    = ws_array [blockIdx.x];
-   int		slot = -1;
+   /* the tile's pointer table lives in shared memory: 19 pointers are 38 registers that the
+      pursuit loops need more urgently */
+   __shared__ TileWs s_W;
+   int		     slot = -1;
+
+   if (threadIdx.x == 0)
+      s_W = ws_array [blockIdx.x];
 
    /*
     *  More tiles than workspaces: take a free one (entry i of ws_array also describes
@@ -2481,15 +2486,20 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
       }
       __syncthreads ();
       slot = s_slot;
-      const TileWs &S = ws_array [slot];
-      W.img	  = S.img;
-      W.T	  = S.T;
-      W.SS	  = S.SS;
-      W.diag	  = S.diag;
-      W.trans	  = S.trans;
-      W.Gglob	  = S.Gglob;
-      W.snap	  = S.snap;
+      if (threadIdx.x == 0)
+      {
+	 const TileWs &S = ws_array [slot];
+	 s_W.img   = S.img;
+	 s_W.T	   = S.T;
+	 s_W.SS	   = S.SS;
+	 s_W.diag  = S.diag;
+	 s_W.trans = S.trans;
+	 s_W.Gglob = S.Gglob;
+	 s_W.snap  = S.snap;
+      }
    }
+   __syncthreads ();
+   const TileWs &W  = s_W;
    const Sh	sh  = carve (smem_raw, P, NT, W.Gglob);
    ShHdr       *h   = sh.h;
    const int	tid = threadIdx.x;
