@@ -524,19 +524,19 @@ template <int NT>
 __device__ __forceinline__ void
 cta_copy_f32 (float *dst, const float *src, unsigned n)
 {
-   unsigned t = threadIdx.x;
-
-   for (; t + 3 * NT < n; t += 4 * NT)
+   for (unsigned t = threadIdx.x; t < n; t += 4 * NT)
    {
-      const float a = src [t], b = src [t + NT], c = src [t + 2 * NT], d = src [t + 3 * NT];
+      /* the last round is predicated, not serialised: its loads travel together too */
+      float v [4];
 
-      dst [t]	       = a;
-      dst [t + NT]     = b;
-      dst [t + 2 * NT] = c;
-      dst [t + 3 * NT] = d;
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+	 v [u] = t + u * NT < n ? src [t + u * NT] : 0.0f;
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+	 if (t + u * NT < n)
+	    dst [t + u * NT] = v [u];
    }
-   for (; t < n; t += NT)
-      dst [t] = src [t];
 }
 
 /*
@@ -1948,8 +1948,12 @@ template <int NT>
 __device__ void
 cta_copy_s16 (short *dst, const short *src, int n)
 {
-   for (int i = threadIdx.x; i < n; i += NT)
-      dst [i] = src [i];
+   /* the model blob: a multiple of 8 shorts, 16-byte aligned wherever it lives */
+   const uint4 *s4 = (const uint4 *) src;
+   uint4       *d4 = (uint4 *) dst;
+
+   for (int i = threadIdx.x; i < n / 8; i += NT)
+      d4 [i] = s4 [i];
 }
 
 /*****************************************************************************
@@ -2186,10 +2190,13 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 	    }
 	    /* keep the "lc" models, restore the snapshot (subdivide.c:226-237); element i
 	       is handled by one thread for both copies */
-	    for (int i = tid; i < P.blob_len; i += NT)
+	    for (int i = tid; i < P.blob_len / 8; i += NT)
 	    {
-	       snap [P.blob_len + i] = sh.blob [i];
-	       sh.blob [i]	     = snap [i];
+	       const uint4 lc = ((const uint4 *) sh.blob) [i];
+	       const uint4 sn = ((const uint4 *) snap) [i];
+
+	       ((uint4 *) (snap + P.blob_len)) [i] = lc;
+	       ((uint4 *) sh.blob) [i]		   = sn;
 	    }
 	    if (tid == 0)
 	    {
