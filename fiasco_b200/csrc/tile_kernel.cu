@@ -124,6 +124,20 @@ __device__ __forceinline__ unsigned dev_bits_bin_code (unsigned value, unsigned 
    return value < maxval + 1 - 2 * r ? k : k + 1;
 }
 
+/*
+ *  The tile's pointers are read from a table in shared memory, so the compiler cannot know
+ *  that they point to global memory and would emit generic loads / stores -- which it must
+ *  also keep in order with every shared-memory store.  GP () tells it.
+ */
+template <typename T>
+__device__ __forceinline__ T *
+as_global (T *p)
+{
+   __builtin_assume (__isGlobal (p));
+   return p;
+}
+#define GP(p) as_global (p)
+
 /* transitions of a state in registers */
 struct TransReg
 {
@@ -177,11 +191,11 @@ t0_store_trans (const TileWs &W, unsigned s)
 
    for (int label = 0; label < 2; label++)
    {
-      const short *in = W.into + (size_t) (2 * s + label) * 6;
-      const float *wt = W.weight + (size_t) (2 * s + label) * 6;
+      const short *in = GP (W.into) + (size_t) (2 * s + label) * 6;
+      const float *wt = GP (W.weight) + (size_t) (2 * s + label) * 6;
       bool	   end = false;
 
-      t.child [label] = W.tree [2 * s + label];
+      t.child [label] = GP (W.tree) [2 * s + label];
       for (int e = 0; e < FB_MAXEDGES; e++)
       {
 	 end = end || in [e] == FB_NO_EDGE;
@@ -189,7 +203,7 @@ t0_store_trans (const TileWs &W, unsigned s)
 	 t.w [label][e]	   = end ? 0.0f : wt [e];
       }
    }
-   W.trans [s] = t;
+   GP (W.trans) [s] = t;
 }
 
 /*****************************************************************************
@@ -574,16 +588,16 @@ cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
 	    reads are shared-memory broadcasts, product writes are coalesced */
 	 for (unsigned s = from + tid; s < S; s += NT)
 	 {
-	    if (!W.domain_type [s])
+	    if (!GP (W.domain_type) [s])
 	       continue;
-	    const float *im = W.img + (size_t) s * FB_IMG_STRIDE + (len - 1);
+	    const float *im = GP (W.img) + (size_t) s * FB_IMG_STRIDE + (len - 1);
 	    if (l == 5)
 	    {
 	       float r [32];
-	       const float4 *im4 = (const float4 *) (W.img + (size_t) s * FB_IMG_STRIDE + 32);
+	       const float4 *im4 = (const float4 *) (GP (W.img) + (size_t) s * FB_IMG_STRIDE + 32);
 	       /* level-5 part starts at float 31; rows are 256 B aligned, so read the
 		  aligned float4s 7..15 and shift by one */
-	       float prev = W.img [(size_t) s * FB_IMG_STRIDE + 31];
+	       float prev = GP (W.img) [(size_t) s * FB_IMG_STRIDE + 31];
 #pragma unroll
 	       for (int q = 0; q < 8; q++)
 	       {
@@ -607,7 +621,7 @@ cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
 		     ip += p4.z * r [4 * q + 2];
 		     ip += p4.w * r [4 * q + 3];
 		  }
-		  W.T [(size_t) (node0 + k) * scap + s] = ip;
+		  GP (W.T) [(size_t) (node0 + k) * scap + s] = ip;
 	       }
 	    }
 	    else
@@ -618,7 +632,7 @@ cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
 		  float	       ip = 0;
 		  for (unsigned i = 0; i < len; i++)
 		     ip += px [i] * im [i];
-		  W.T [(size_t) (node0 + k) * scap + s] = ip;
+		  GP (W.T) [(size_t) (node0 + k) * scap + s] = ip;
 	       }
 	    }
 	 }
@@ -631,14 +645,14 @@ cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
 	    const unsigned s = from + item / nn;
 	    const unsigned k = item % nn;
 
-	    if (!W.domain_type [s])
+	    if (!GP (W.domain_type) [s])
 	       continue;
-	    const float *im = W.img + (size_t) s * FB_IMG_STRIDE + (len - 1);
+	    const float *im = GP (W.img) + (size_t) s * FB_IMG_STRIDE + (len - 1);
 	    const float *px = sh.pixels + (size_t) (adr0 + k) * len;
 	    float	 ip = 0;
 	    for (unsigned i = 0; i < len; i++)
 	       ip += px [i] * im [i];
-	    W.T [(size_t) (node0 + k) * scap + s] = ip;
+	    GP (W.T) [(size_t) (node0 + k) * scap + s] = ip;
 	 }
       }
    }
@@ -658,11 +672,11 @@ cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
 	    the nodes of this level; the gathers hit the two child rows of a node */
 	 for (unsigned s = from + tid; s < S; s += NT)
 	 {
-	    if (!W.domain_type [s])
+	    if (!GP (W.domain_type) [s])
 	       continue;
 	    TransReg tr;
 
-	    load_trans (W.trans + s, tr);
+	    load_trans (GP (W.trans) + s, tr);
 	    /* gather indices with the unused slots pointing at entry 0 (always valid): the
 	       loads are unconditional and independent, so several nodes' worth of L2 round
 	       trips overlap; only the additions are predicated (the value stays exact) */
@@ -678,11 +692,11 @@ cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
 	    if (nn >= 2)
 #pragma unroll 1
 	       for (unsigned k = 0; k < nn; k += 2)
-		  upsweep_nodes<2> (W.T, scap, node0 + k, s, tr, idx);
+		  upsweep_nodes<2> (GP (W.T), scap, node0 + k, s, tr, idx);
 	    else
 #pragma unroll 1
 	       for (unsigned k = 0; k < nn; k++)
-		  upsweep_nodes<1> (W.T, scap, node0 + k, s, tr, idx);
+		  upsweep_nodes<1> (GP (W.T), scap, node0 + k, s, tr, idx);
 	 }
       }
       else
@@ -692,16 +706,16 @@ cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
 	    const unsigned s	= from + item % ns;
 	    const unsigned node = node0 + item / ns;
 
-	    if (!W.domain_type [s])
+	    if (!GP (W.domain_type) [s])
 	       continue;
 	    TransReg tr;
 	    float    acc = 0;
 
-	    load_trans (W.trans + s, tr);
+	    load_trans (GP (W.trans) + s, tr);
 #pragma unroll
 	    for (int label = 0; label < 2; label++)
 	    {
-	       const float *src = W.T + (size_t) (2 * node + 1 + label) * scap;
+	       const float *src = GP (W.T) + (size_t) (2 * node + 1 + label) * scap;
 
 	       if (tr.child [label] != FB_RANGE)
 		  acc += src [tr.child [label]];
@@ -710,7 +724,7 @@ cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
 		  if (tr.into [label][e] != FB_NO_EDGE)
 		     acc += src [tr.into [label][e]] * tr.w [label][e];
 	    }
-	    W.T [(size_t) node * scap + s] = acc;
+	    GP (W.T) [(size_t) node * scap + s] = acc;
 	 }
       }
       __syncthreads ();
@@ -726,7 +740,7 @@ cta_init_range (const DevParams &P, const TileWs &W, const Sh &sh, unsigned x0,
 {
    const int	  tid  = threadIdx.x;
    const unsigned size = 1u << P.lc_max;
-   const int16_t *src  = W.pix + (size_t) band * P.width * P.height;
+   const int16_t *src  = GP (W.pix) + (size_t) band * P.width * P.height;
 
    for (unsigned i = tid; i < size; i += NT)
    {
@@ -807,7 +821,7 @@ t0_node_norm (const DevParams &P, const Sh &sh, unsigned image, unsigned address
 __device__ __forceinline__ float
 ss_get (const DevParams &P, const TileWs &W, int li, unsigned a, unsigned b)
 {
-   return W.SS [((size_t) li * P.s_cap + a) * P.s_cap + b];
+   return GP (W.SS) [((size_t) li * P.s_cap + a) * P.s_cap + b];
 }
 
 /* one entry <s, t> at level lmin + li for a state s whose images exist
@@ -820,8 +834,8 @@ dev_ss_entry (const DevParams &P, const TileWs &W, int li, unsigned s, unsigned 
    if (level <= P.il)
    {
       const unsigned len = 1u << level;
-      const float   *a	 = W.img + (size_t) s * FB_IMG_STRIDE + (len - 1);
-      const float   *b	 = W.img + (size_t) t * FB_IMG_STRIDE + (len - 1);
+      const float   *a	 = GP (W.img) + (size_t) s * FB_IMG_STRIDE + (len - 1);
+      const float   *b	 = GP (W.img) + (size_t) t * FB_IMG_STRIDE + (len - 1);
       float	     ip	 = 0;
       for (unsigned i = 0; i < len; i++)
 	 ip += a [i] * b [i];
@@ -830,15 +844,15 @@ dev_ss_entry (const DevParams &P, const TileWs &W, int li, unsigned s, unsigned 
    float ip = 0;
    for (int label = 0; label < 2; label++)
    {
-      const short *in1 = W.into + (size_t) (2 * s + label) * 6;
-      const float *wt1 = W.weight + (size_t) (2 * s + label) * 6;
-      const short *in2 = W.into + (size_t) (2 * t + label) * 6;
-      const float *wt2 = W.weight + (size_t) (2 * t + label) * 6;
-      const int	   c2  = W.tree [2 * t + label];
+      const short *in1 = GP (W.into) + (size_t) (2 * s + label) * 6;
+      const float *wt1 = GP (W.weight) + (size_t) (2 * s + label) * 6;
+      const short *in2 = GP (W.into) + (size_t) (2 * t + label) * 6;
+      const float *wt2 = GP (W.weight) + (size_t) (2 * t + label) * 6;
+      const int	   c2  = GP (W.tree) [2 * t + label];
       int	   d1, d2;
       float	   sum;
 
-      if ((d1 = W.tree [2 * s + label]) != FB_RANGE)
+      if ((d1 = GP (W.tree) [2 * s + label]) != FB_RANGE)
       {
 	 sum = 0;
 	 if (c2 != FB_RANGE)
@@ -877,16 +891,16 @@ cta_state_images (const DevParams &P, const TileWs &W, unsigned s)
       const int label = pos >= half;
       const int i     = pos - label * half;
       const int so    = (half - 1) + i;		   /* offset in the source image */
-      int	dom   = W.tree [2 * s + label];
+      int	dom   = GP (W.tree) [2 * s + label];
       float	v     = 0;
 
       if (dom != FB_RANGE)
-	 v = W.img [(size_t) dom * FB_IMG_STRIDE + so];
-      const short *in = W.into + (size_t) (2 * s + label) * 6;
-      const float *wt = W.weight + (size_t) (2 * s + label) * 6;
+	 v = GP (W.img) [(size_t) dom * FB_IMG_STRIDE + so];
+      const short *in = GP (W.into) + (size_t) (2 * s + label) * 6;
+      const float *wt = GP (W.weight) + (size_t) (2 * s + label) * 6;
       for (int k = 0; (dom = in [k]) != FB_NO_EDGE; k++)
-	 v += W.img [(size_t) dom * FB_IMG_STRIDE + so] * wt [k];
-      W.img [(size_t) s * FB_IMG_STRIDE + e] = v;
+	 v += GP (W.img) [(size_t) dom * FB_IMG_STRIDE + so] * wt [k];
+      GP (W.img) [(size_t) s * FB_IMG_STRIDE + e] = v;
    }
    __syncthreads ();
 }
@@ -919,9 +933,9 @@ cta_state_products (const DevParams &P, const TileWs &W, const Sh &sh, unsigned 
       for (int label = 0; label < 2; label++)
       {
 	 int	      n	 = 0;
-	 const int    c	 = W.tree [2 * s + label];
-	 const short *in = W.into + (size_t) (2 * s + label) * 6;
-	 const float *wp = W.weight + (size_t) (2 * s + label) * 6;
+	 const int    c	 = GP (W.tree) [2 * s + label];
+	 const short *in = GP (W.into) + (size_t) (2 * s + label) * 6;
+	 const float *wp = GP (W.weight) + (size_t) (2 * s + label) * 6;
 
 	 h->ap_child [label] = c != FB_RANGE;
 	 if (c != FB_RANGE)
@@ -960,21 +974,21 @@ cta_state_products (const DevParams &P, const TileWs &W, const Sh &sh, unsigned 
       {
 	 /* direct dot products of the state images (ip.c:297-323) */
 	 const unsigned len = 1u << level;
-	 const float   *a   = W.img + (size_t) s * FB_IMG_STRIDE + (len - 1);
+	 const float   *a   = GP (W.img) + (size_t) s * FB_IMG_STRIDE + (len - 1);
 
 	 for (unsigned t = tid; t <= s; t += NT)
 	 {
-	    if (!W.domain_type [t])
+	    if (!GP (W.domain_type) [t])
 	       continue;
-	    const float *b  = W.img + (size_t) t * FB_IMG_STRIDE + (len - 1);
+	    const float *b  = GP (W.img) + (size_t) t * FB_IMG_STRIDE + (len - 1);
 	    float	 ip = 0;
 	    if (level == 5)
 	    {
 	       /* the level-5 part is floats 31..62 of a 256-byte row: load the whole
 		  upper half with aligned float4s (independent loads, one L2 round trip) */
-	       const float4 *b4 = (const float4 *) (W.img + (size_t) t * FB_IMG_STRIDE + 32);
+	       const float4 *b4 = (const float4 *) (GP (W.img) + (size_t) t * FB_IMG_STRIDE + 32);
 	       float4	     v [8];
-	       float	     prev = W.img [(size_t) t * FB_IMG_STRIDE + 31];
+	       float	     prev = GP (W.img) [(size_t) t * FB_IMG_STRIDE + 31];
 #pragma unroll
 	       for (int q = 0; q < 8; q++)
 		  v [q] = b4 [q];
@@ -991,10 +1005,10 @@ cta_state_products (const DevParams &P, const TileWs &W, const Sh &sh, unsigned 
 	    else
 	       for (unsigned i = 0; i < len; i++)
 		  ip += a [i] * b [i];
-	    W.SS [((size_t) li * P.s_cap + s) * P.s_cap + t] = ip;
-	    W.SS [((size_t) li * P.s_cap + t) * P.s_cap + s] = ip;
+	    GP (W.SS) [((size_t) li * P.s_cap + s) * P.s_cap + t] = ip;
+	    GP (W.SS) [((size_t) li * P.s_cap + t) * P.s_cap + s] = ip;
 	    if (t == s)
-	       W.diag [(size_t) li * P.s_cap + s] = ip;
+	       GP (W.diag) [(size_t) li * P.s_cap + s] = ip;
 	 }
 	 LAP (h, LAP_AP_DIRECT);
 	 continue;
@@ -1004,18 +1018,18 @@ cta_state_products (const DevParams &P, const TileWs &W, const Sh &sh, unsigned 
       for (int j = 0; j < nsrc; j++)
       {
 	 float	     *row = sh.num + (size_t) j * stride;
-	 const float *src = W.SS + ((size_t) (li - 1) * P.s_cap + h->ap_src [j]) * P.s_cap;
+	 const float *src = GP (W.SS) + ((size_t) (li - 1) * P.s_cap + h->ap_src [j]) * P.s_cap;
 	 cta_copy_f32<NT> (row, src, s + 1);
       }
       __syncthreads ();
       for (unsigned t = tid; t <= s; t += NT)
       {
-	 if (!W.domain_type [t])
+	 if (!GP (W.domain_type) [t])
 	    continue;
 	 float	  ip = 0;
 	 TransReg tr;
 
-	 load_trans (W.trans + t, tr);
+	 load_trans (GP (W.trans) + t, tr);
 #pragma unroll
 	 for (int label = 0; label < 2; label++)
 	 {
@@ -1025,7 +1039,7 @@ cta_state_products (const DevParams &P, const TileWs &W, const Sh &sh, unsigned 
 	    for (int k = 0; k < n1; k++)
 	    {
 	       const int    j	= h->ap_row [label][k];
-	       const float *row = j < 0 ? W.SS + ((size_t) (li - 1) * P.s_cap
+	       const float *row = j < 0 ? GP (W.SS) + ((size_t) (li - 1) * P.s_cap
 						  + h->ap_dom [label][k]) * P.s_cap
 					: sh.num + (size_t) j * stride;
 	       float sum = 0;
@@ -1042,10 +1056,10 @@ cta_state_products (const DevParams &P, const TileWs &W, const Sh &sh, unsigned 
 		  ip += h->ap_w [label][k] * sum;
 	    }
 	 }
-	 W.SS [((size_t) li * P.s_cap + s) * P.s_cap + t] = ip;
-	 W.SS [((size_t) li * P.s_cap + t) * P.s_cap + s] = ip;
+	 GP (W.SS) [((size_t) li * P.s_cap + s) * P.s_cap + t] = ip;
+	 GP (W.SS) [((size_t) li * P.s_cap + t) * P.s_cap + s] = ip;
 	 if (t == s)
-	    W.diag [(size_t) li * P.s_cap + s] = ip;
+	    GP (W.diag) [(size_t) li * P.s_cap + s] = ip;
       }
       __syncthreads ();
       LAP (h, LAP_AP_STAGED);
@@ -1060,14 +1074,14 @@ t0_final_distribution (const TileWs &W, unsigned s)
 
    for (int label = 0; label < 2; label++)
    {
-      int dom = W.tree [2 * s + label];
+      int dom = GP (W.tree) [2 * s + label];
 
       if (dom != FB_RANGE)
-	 final += W.final_d [dom];
-      const short *in = W.into + (size_t) (2 * s + label) * 6;
-      const float *wt = W.weight + (size_t) (2 * s + label) * 6;
+	 final += GP (W.final_d) [dom];
+      const short *in = GP (W.into) + (size_t) (2 * s + label) * 6;
+      const float *wt = GP (W.weight) + (size_t) (2 * s + label) * 6;
       for (int e = 0; (dom = in [e]) != FB_NO_EDGE; e++)
-	 final += wt [e] * W.final_d [dom];
+	 final += wt [e] * GP (W.final_d) [dom];
    }
    return final / 2;
 }
@@ -1076,8 +1090,8 @@ t0_final_distribution (const TileWs &W, unsigned s)
 __device__ void
 t0_append_edge (const TileWs &W, unsigned from, int into, float weight, int label)
 {
-   short *in = W.into + (size_t) (2 * from + label) * 6;
-   float *wt = W.weight + (size_t) (2 * from + label) * 6;
+   short *in = GP (W.into) + (size_t) (2 * from + label) * 6;
+   float *wt = GP (W.weight) + (size_t) (2 * from + label) * 6;
    int	  pos, edge;
 
    for (pos = 0; in [pos] != FB_NO_EDGE && in [pos] < into; pos++)
@@ -1108,11 +1122,11 @@ cta_append_state (const DevParams &P, const TileWs &W, const Sh &sh, int auxilia
    {
       const float final = t0_final_distribution (W, s);
 
-      W.final_d [s]	   = final;
-      W.level_of_state [s] = (uint8_t) level_of_state;
-      W.domain_type [s]	   = auxiliary ? 0 : 2;
+      GP (W.final_d) [s]	   = final;
+      GP (W.level_of_state) [s] = (uint8_t) level_of_state;
+      GP (W.domain_type) [s]	   = auxiliary ? 0 : 2;
       if (!auxiliary)
-	 W.img [(size_t) s * FB_IMG_STRIDE] = final;
+	 GP (W.img) [(size_t) s * FB_IMG_STRIDE] = final;
    }
    __syncthreads ();
    if (!auxiliary)
@@ -1146,30 +1160,30 @@ cta_init_basis (const DevParams &P, const TileWs &W, const Sh &sh)
    /* empty automaton (alloc_wfa, wfalib.c:98-113) for the states we may touch */
    for (unsigned i = tid; i < (unsigned) P.s_cap * 2; i += NT)
    {
-      W.tree [i]     = FB_RANGE;
-      W.y_state [i]  = FB_RANGE;
-      W.into [(size_t) i * 6] = FB_NO_EDGE;
-      W.y_column [i] = 0;
-      W.x [i] = 0;
-      W.y [i] = 0;
+      GP (W.tree) [i]     = FB_RANGE;
+      GP (W.y_state) [i]  = FB_RANGE;
+      GP (W.into) [(size_t) i * 6] = FB_NO_EDGE;
+      GP (W.y_column) [i] = 0;
+      GP (W.x) [i] = 0;
+      GP (W.y) [i] = 0;
    }
    for (unsigned i = tid; i < (unsigned) P.s_cap; i += NT)
    {
-      W.domain_type [i]	   = 0;
-      W.final_d [i]	   = 0;
-      W.level_of_state [i] = 0;
+      GP (W.domain_type) [i]	   = 0;
+      GP (W.final_d) [i]	   = 0;
+      GP (W.level_of_state) [i] = 0;
    }
    __syncthreads ();
    if (tid == 0)
    {
-      W.domain_type [0] = 2;
-      W.final_d [0]	= 128;
+      GP (W.domain_type) [0] = 2;
+      GP (W.final_d) [0]	= 128;
       t0_append_edge (W, 0, 0, 1.0f, 0);
       t0_append_edge (W, 0, 0, 1.0f, 1);
-      W.final_d [1] = 64;
-      W.final_d [2] = 64;
-      W.domain_type [1] = 2;
-      W.domain_type [2] = 2;
+      GP (W.final_d) [1] = 64;
+      GP (W.final_d) [2] = 64;
+      GP (W.domain_type) [1] = 2;
+      GP (W.domain_type) [2] = 2;
       t0_append_edge (W, 1, 2, 0.5f, 0);
       t0_append_edge (W, 1, 2, 0.5f, 1);
       t0_append_edge (W, 1, 0, 0.5f, 1);
@@ -1178,8 +1192,8 @@ cta_init_basis (const DevParams &P, const TileWs &W, const Sh &sh)
       for (unsigned s = 0; s < 3; s++)
       {
 	 t0_store_trans (W, s);
-	 W.img [(size_t) s * FB_IMG_STRIDE] = W.final_d [s];
-	 W.level_of_state [s]		    = (uint8_t) -1;
+	 GP (W.img) [(size_t) s * FB_IMG_STRIDE] = GP (W.final_d) [s];
+	 GP (W.level_of_state) [s]		    = (uint8_t) -1;
       }
       /* compute_images (0, 2): level outermost because the basis states refer to
 	 each other */
@@ -1188,18 +1202,18 @@ cta_init_basis (const DevParams &P, const TileWs &W, const Sh &sh)
 	    for (int label = 0; label < 2; label++)
 	    {
 	       const int half = 1 << (level - 1);
-	       float	*dst  = W.img + (size_t) s * FB_IMG_STRIDE + ((1 << level) - 1)
+	       float	*dst  = GP (W.img) + (size_t) s * FB_IMG_STRIDE + ((1 << level) - 1)
 				+ label * half;
-	       int	 dom  = W.tree [2 * s + label];
+	       int	 dom  = GP (W.tree) [2 * s + label];
 
 	       for (int i = 0; i < half; i++)
 		  dst [i] = dom != FB_RANGE
-			    ? W.img [(size_t) dom * FB_IMG_STRIDE + (half - 1) + i] : 0.0f;
-	       const short *in = W.into + (size_t) (2 * s + label) * 6;
-	       const float *wt = W.weight + (size_t) (2 * s + label) * 6;
+			    ? GP (W.img) [(size_t) dom * FB_IMG_STRIDE + (half - 1) + i] : 0.0f;
+	       const short *in = GP (W.into) + (size_t) (2 * s + label) * 6;
+	       const float *wt = GP (W.weight) + (size_t) (2 * s + label) * 6;
 	       for (int e = 0; (dom = in [e]) != FB_NO_EDGE; e++)
 		  for (int i = 0; i < half; i++)
-		     dst [i] += W.img [(size_t) dom * FB_IMG_STRIDE + (half - 1) + i] * wt [e];
+		     dst [i] += GP (W.img) [(size_t) dom * FB_IMG_STRIDE + (half - 1) + i] * wt [e];
 	    }
       /* compute_ip_states_state (0, 2): level outermost */
       for (int li = 0; li < P.nlev; li++)
@@ -1208,10 +1222,10 @@ cta_init_basis (const DevParams &P, const TileWs &W, const Sh &sh)
 	    {
 	       const float ip = dev_ss_entry (P, W, li, s1, s2);
 
-	       W.SS [((size_t) li * P.s_cap + s1) * P.s_cap + s2] = ip;
-	       W.SS [((size_t) li * P.s_cap + s2) * P.s_cap + s1] = ip;
+	       GP (W.SS) [((size_t) li * P.s_cap + s1) * P.s_cap + s2] = ip;
+	       GP (W.SS) [((size_t) li * P.s_cap + s2) * P.s_cap + s1] = ip;
 	       if (s1 == s2)
-		  W.diag [(size_t) li * P.s_cap + s1] = ip;
+		  GP (W.diag) [(size_t) li * P.s_cap + s1] = ip;
 	    }
       sh.h->states = 3;
    }
@@ -1553,7 +1567,7 @@ cta_matching_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &
    {
       int y_state = y_state_in;
 
-      if (y_state >= 0 && !(W.domain_type [y_state] & 2))
+      if (y_state >= 0 && !(GP (W.domain_type) [y_state] & 2))
 	 y_state = -1;
       w.y_state = y_state;
       w.pool_n	= BLOB_U16 (sh, MB_N);
@@ -1637,8 +1651,8 @@ cta_matching_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &
 	 const int d  = d0 + u * NT;
 	 const int st = d < D ? dom_state (sh, w, d) : 0;
 
-	 dn [u] = W.diag [(size_t) li * P.s_cap + st];
-	 nm [u] = W.T [(size_t) image * P.s_cap + st];
+	 dn [u] = GP (W.diag) [(size_t) li * P.s_cap + st];
+	 nm [u] = GP (W.T) [(size_t) image * P.s_cap + st];
       }
 #pragma unroll
       for (int u = 0; u < 4; u++)
@@ -1723,7 +1737,7 @@ cta_matching_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &
       {
 	 const int   sidx = dom_state (sh, w, index);
 	 const float Nn	  = w.N [n], Bn = w.B [n];
-	 const float *row = W.SS + ((size_t) li * P.s_cap + sidx) * P.s_cap;
+	 const float *row = GP (W.SS) + ((size_t) li * P.s_cap + sidx) * P.s_cap;
 
 	 for (int d = tid; d < D; d += NT)
 	    if (!sh.used [d])
@@ -1909,9 +1923,9 @@ cta_approximate_range (const DevParams &P, const TileWs &W, const Sh &sh, float 
 	 costs	       = FB_MAXCOSTS;
       }
       h->ret_costs = costs;
-      if (W.trace && h->trace_len < P.trace_cap)
+      if (GP (W.trace) && h->trace_len < P.trace_cap)
       {
-	 fb200_trace_rec_t *t = W.trace + h->trace_len;
+	 fb200_trace_rec_t *t = GP (W.trace) + h->trace_len;
 
 	 t->level   = (uint16_t) level;
 	 t->image   = (uint16_t) image;
@@ -1933,7 +1947,7 @@ cta_approximate_range (const DevParams &P, const TileWs &W, const Sh &sh, float 
 	    t->weight [e] = e < n_edges ? out->weight [e] : 0;
 	 }
       }
-      if (W.trace)
+      if (GP (W.trace))
 	 h->trace_len++;
    }
    __syncthreads ();
@@ -2141,7 +2155,7 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 	 case ST_ENTER:
 	 {
 	    const int level = F.level;
-	    short    *snap  = (sh.snaps ? sh.snaps : W.snap) + (size_t) depth * 2 * P.blob_len;
+	    short    *snap  = (sh.snaps ? sh.snaps : GP (W.snap)) + (size_t) depth * 2 * P.blob_len;
 	    unsigned *tsnap = sh.tsnap + (size_t) depth * 2 * FB200_MAXLEVEL;
 
 	    /* snapshot of the models (subdivide.c:188-194); tree_counts and tree_total are
@@ -2161,7 +2175,7 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 	       /* y states of the children (subdivide.c:172-183) */
 	       for (int label = 0; label < 2; label++)
 		  F.new_y_state [label] = (band != 0 && F.y_state != FB_RANGE)
-					  ? (int) W.tree [2 * F.y_state + label] : FB_RANGE;
+					  ? (int) GP (W.tree) [2 * F.y_state + label] : FB_RANGE;
 	       F.lincomb_costs = FB_MAXCOSTS;
 	       if (level <= P.lc_max)
 	       {
@@ -2238,7 +2252,7 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 	 case ST_DECIDE:
 	 {
 	    const float lin = F.lincomb_costs, sub = F.subdivide_costs;
-	    short      *snap  = (sh.snaps ? sh.snaps : W.snap) + (size_t) depth * 2 * P.blob_len;
+	    short      *snap  = (sh.snaps ? sh.snaps : GP (W.snap)) + (size_t) depth * 2 * P.blob_len;
 	    unsigned   *tsnap = sh.tsnap + (size_t) depth * 2 * FB200_MAXLEVEL;
 
 	    if ((lin >= FB_MAXCOSTS && sub >= FB_MAXCOSTS) || lin < sub)
@@ -2300,17 +2314,17 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 		  {
 		     const RangeRes &c = F.child [label];
 
-		     W.tree [2 * s + label]    = c.tree;
-		     W.y_state [2 * s + label] = (short) F.new_y_state [label];
-		     W.x [2 * s + label]       = c.x;
-		     W.y [2 * s + label]       = c.y;
-		     W.y_column [2 * s + label] = 0;
-		     W.into [(size_t) (2 * s + label) * 6] = FB_NO_EDGE;
+		     GP (W.tree) [2 * s + label]    = c.tree;
+		     GP (W.y_state) [2 * s + label] = (short) F.new_y_state [label];
+		     GP (W.x) [2 * s + label]       = c.x;
+		     GP (W.y) [2 * s + label]       = c.y;
+		     GP (W.y_column) [2 * s + label] = 0;
+		     GP (W.into) [(size_t) (2 * s + label) * 6] = FB_NO_EDGE;
 		     for (int e = 0; c.into [e] != FB_NO_EDGE; e++)
 		     {
 			t0_append_edge (W, s, c.into [e], c.weight [e], label);
 			if (c.into [e] == F.new_y_state [label])
-			   W.y_column [2 * s + label] = 1;
+			   GP (W.y_column) [2 * s + label] = 1;
 		     }
 		  }
 		  t0_store_trans (W, s);
@@ -2380,7 +2394,7 @@ t0_chroma_setup (const DevParams &P, const TileWs &W, const Sh &sh, int *hits)
       for (unsigned s = from; s <= to; s++)
 	 for (int label = 0; label < 2; label++)
 	 {
-	    const short *in = W.into + (size_t) (2 * s + label) * 6;
+	    const short *in = GP (W.into) + (size_t) (2 * s + label) * 6;
 	    for (int e = 0; in [e] != FB_NO_EDGE; e++)
 	       hits [in [e]]++;
 	 }
@@ -2416,9 +2430,9 @@ t0_chroma_setup (const DevParams &P, const TileWs &W, const Sh &sh, int *hits)
       unsigned min_level = FB200_MAXLEVEL;
 
       for (unsigned s = 3; s < states; s++)
-	 if (W.tree [2 * s] == FB_RANGE || W.tree [2 * s + 1] == FB_RANGE)
+	 if (GP (W.tree) [2 * s] == FB_RANGE || GP (W.tree) [2 * s + 1] == FB_RANGE)
 	 {
-	    const unsigned l = (unsigned) W.level_of_state [s] - 1;
+	    const unsigned l = (unsigned) GP (W.level_of_state) [s] - 1;
 	    if (l < min_level)
 	       min_level = l;
 	 }
@@ -2436,16 +2450,16 @@ t0_virtual_state (const DevParams &P, const TileWs &W, ShHdr *h, int child0, int
 
    for (int label = 0; label < 2; label++)
    {
-      W.tree [2 * s + label]	 = (short) (label ? child1 : child0);
-      W.y_state [2 * s + label]	 = FB_RANGE;
-      W.x [2 * s + label]	 = 0;
-      W.y [2 * s + label]	 = 0;
-      W.y_column [2 * s + label] = 0;
-      W.into [(size_t) (2 * s + label) * 6] = FB_NO_EDGE;
+      GP (W.tree) [2 * s + label]	 = (short) (label ? child1 : child0);
+      GP (W.y_state) [2 * s + label]	 = FB_RANGE;
+      GP (W.x) [2 * s + label]	 = 0;
+      GP (W.y) [2 * s + label]	 = 0;
+      GP (W.y_column) [2 * s + label] = 0;
+      GP (W.into) [(size_t) (2 * s + label) * 6] = FB_NO_EDGE;
    }
-   W.final_d [s]	= t0_final_distribution (W, s);
-   W.level_of_state [s] = (uint8_t) level;
-   W.domain_type [s]	= 0;
+   GP (W.final_d) [s]	= t0_final_distribution (W, s);
+   GP (W.level_of_state) [s] = (uint8_t) level;
+   GP (W.domain_type) [s]	= 0;
    h->states		= s + 1;
    if (s + 1 >= FB200_MAXSTATES)
       h->status = FB200_EMAXSTATES;
@@ -2507,7 +2521,7 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
    }
    __syncthreads ();
    const TileWs &W  = s_W;
-   const Sh	sh  = carve (smem_raw, P, NT, W.Gglob);
+   const Sh	sh  = carve (smem_raw, P, NT, GP (W.Gglob));
    ShHdr       *h   = sh.h;
    const int	tid = threadIdx.x;
 
