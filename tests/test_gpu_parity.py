@@ -293,3 +293,16 @@ def test_gpu_capacity_error_is_reported():
         assert e.value.code == ffi.ECAPACITY
     finally:
         enc.close()
+
+
+def test_gpu_random_crops_match_oracle():
+    """Seeded random campaign (tools/fuzz_gpu.py): 60 random crops, sizes, qualities, optimisation
+    levels, grey and colour, flat blocks -- device vs oracle, bit for bit."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_gpu.py"), "60", "11"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "60 cases, 0 mismatches" in r.stdout
