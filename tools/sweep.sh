@@ -6,7 +6,7 @@ for lib in ${LIBS:-product}; do
   for shape in ${SHAPES:-128:4}; do
     for big in ${BIGS:-default}; do
       if [ "$big" = default ]; then unset FB200_BIG; else export FB200_BIG=$big; fi
-      FB200_NT=${shape%%:*} timeout 600 python tools/sweep_nt.py ${shape##*:} ${DISTINCT:-74} 2>&1 | tail -2 | grep -v "laps: ctrl=0.0"
+      FB200_NT=${shape%%:*} timeout 600 python tools/sweep_nt.py ${shape##*:} ${DISTINCT:-74} 2>&1 | tail -3 | grep -v "laps: ctrl=0.0"
     done
   done
 done

@@ -62,6 +62,9 @@ def main():
         os.environ.get("FB200_LIB", "product"), os.environ.get("FB200_NT", "-"), os.environ.get("FB200_BIG", "-"), res, B, B / sms,
         B * 1.048576 / min(t), 1e3 * min(t), ok, w["states"], hashlib.md5("\n".join(lines).encode()).hexdigest()[:8]),
         flush=True)
+    print("   work/frame: mp_calls %.0f steps %.0f pass2 evaluations %.0f (%.1f per step, incl. failing last steps: %.1f per find)"
+          % (st["mp_calls"] / B, st["mp_steps"] / B, st["pass2"] / B, st["pass2"] / max(1, st["mp_steps"]),
+             st["pass2"] / max(1, st["mp_steps"] + st["mp_calls"])), flush=True)
     print("   laps: " + " ".join("%s=%.1f" % (n, 100 * v / tot) for n, v in zip(NAMES, st["lap"])), flush=True)
 
 
