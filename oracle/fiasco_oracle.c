@@ -2000,3 +2000,180 @@ fo_dump_wfa (const fo_wfa_t *w, const fo_params_t *p, FILE *f)
    }
    fprintf (f, "end\n");
 }
+
+/*****************************************************************************
+
+	    image regeneration from an automaton  (codec/decoder.c)
+
+  The coder regenerates every frame it has coded (codec/coder.c:647-651): the result is
+  the reference frame of the next predicted frame, so this side of the codec belongs to
+  the encoder path of videos.  decode_image (decoder.c:412-535) with
+  alloc_state_images (:878-1016) and compute_state_images (:1107-1498), restated per
+  pixel: the reference adds two pixels per 32-bit int with a guard bit each (bit 0 and
+  bit 16 are masked after every addition), which is a wrapping 16-bit addition of even
+  numbers per pixel.
+
+*****************************************************************************/
+
+typedef struct simg
+{
+   int16_t *pix [MAXSTATES][MAXLEVEL + 1];	/* image of a state at a level, or NULL */
+   const fo_wfa_t *w;
+} simg_t;
+
+/* codec/wfalib.c:273: the integer form of a weight the decoder multiplies with */
+static int
+int_weight_of (float weight)
+{
+   return (int16_t) (weight * 512 + 0.5);
+}
+
+/* image of 'state' at 'level' (width_of_level x height_of_level shorts, row-major) */
+static const int16_t *
+state_image (simg_t *si, unsigned state, unsigned level)
+{
+   const fo_wfa_t *w = si->w;
+
+   if (si->pix [state][level])
+      return si->pix [state][level];
+
+   int16_t *img = calloc (size_of_level (level), sizeof (int16_t));
+
+   si->pix [state][level] = img;
+   if (level == 0)			/* decoder.c:1128-1130 */
+   {
+      img [0] = (int16_t) ((int) (w->final_distribution [state] * 8 + .5) * 2);
+      return img;
+   }
+   const unsigned width	 = width_of_level (level - 1);
+   const unsigned height = height_of_level (level - 1);
+   const unsigned stride = width_of_level (level);
+
+   for (unsigned label = 0; label < MAXLABELS; label++)
+   {
+      /* odd levels are split into an upper and a lower half, even ones into a left and a
+	 right half (decoder.c:1166-1177) */
+      int16_t *range = (level & 1) ? img + label * height * stride : img + label * width;
+      int      child = w->tree [state][label];
+
+      if (child != RANGE)		/* copy the child's image (decoder.c:1197-1209) */
+      {
+	 const int16_t *src = state_image (si, (unsigned) child, level - 1);
+
+	 for (unsigned y = 0; y < height; y++)
+	    memcpy (range + y * stride, src + y * width, width * sizeof (int16_t));
+      }
+      for (unsigned edge = 0; w->into [state][label][edge] != NO_EDGE; edge++)
+      {
+	 const int domain = w->into [state][label][edge];
+
+	 if (domain != 0)		/* decoder.c:1219-1300, 1355-1440 */
+	 {
+	    const int16_t *src	  = state_image (si, (unsigned) domain, level - 1);
+	    const int	   weight = int_weight_of (w->weight [state][label][edge]);
+
+	    for (unsigned y = 0; y < height; y++)
+	       for (unsigned x = 0; x < width; x++)
+	       {
+		  const int v = ((weight * (int) src [y * width + x]) >> 10) << 1;
+
+		  range [y * stride + x] = (int16_t) (range [y * stride + x] + v);
+	       }
+	 }
+	 else				/* the constant state (decoder.c:1302-1345, 1442-1492) */
+	 {
+	    const int weight = (int) (w->weight [state][label][edge]
+				      * w->final_distribution [0] * 8 + .5) * 2;
+
+	    for (unsigned y = 0; y < height; y++)
+	       for (unsigned x = 0; x < width; x++)
+		  range [y * stride + x] = (int16_t) (range [y * stride + x] + weight);
+	 }
+      }
+   }
+   return img;
+}
+
+/*
+ *  decode_image (decoder.c:412-535), 4:4:4.  planes [b] receive width * height shorts each
+ *  (1 band grey, 3 bands Y Cb Cr).  Returns 0 on success.
+ */
+int
+fo_decode_image (const fo_wfa_t *w, int color, unsigned width, unsigned height,
+		 int16_t *const planes [3])
+{
+   simg_t  *si = calloc (1, sizeof *si);
+   unsigned root [3], max_level = 0, aw = 0, ah = 0, state;
+   uint8_t  level_of_state [MAXSTATES];
+
+   if (!si)
+      return 1;
+   si->w = w;
+   memcpy (level_of_state, w->level_of_state, sizeof level_of_state);
+   if (color)				/* decoder.c:436-444, 467-472 */
+   {
+      root [0] = (unsigned) w->tree [w->tree [w->root_state][0]][0];
+      root [1] = (unsigned) w->tree [w->tree [w->root_state][0]][1];
+      root [2] = (unsigned) w->tree [w->tree [w->root_state][1]][0];
+      level_of_state [w->root_state]		       = 128;
+      level_of_state [w->tree [w->root_state][0]] = 128;
+      level_of_state [w->tree [w->root_state][1]] = 128;
+   }
+   else
+      root [0] = root [1] = root [2] = w->root_state;
+   /* highest level of a linear combination; frame size the bintree covers
+      (decoder.c:449-461, compute_actual_size :843-875 for 4:4:4) */
+   for (state = w->basis_states; state < w->states; state++)
+      if (w->into [state][0][0] != NO_EDGE || w->into [state][1][0] != NO_EDGE)
+      {
+	 const unsigned l = w->level_of_state [state];
+
+	 if (l > max_level)
+	    max_level = l;
+	 if (w->x [state][0] + width_of_level (l) > aw)
+	    aw = w->x [state][0] + width_of_level (l);
+	 if (w->y [state][0] + height_of_level (l) > ah)
+	    ah = w->y [state][0] + height_of_level (l);
+      }
+   aw += aw & 1;
+   ah += ah & 1;
+   if (aw < width)
+      aw = width;
+   if (ah < height)
+      ah = height;
+
+   const unsigned bands = color ? 3 : 1;
+   int16_t	 *frame [3] = {NULL, NULL, NULL};
+
+   for (unsigned b = 0; b < bands; b++)
+      frame [b] = calloc ((size_t) aw * ah, sizeof (int16_t));
+   /* every state of level max_level is one block of the frame (decoder.c:913-937) */
+   for (state = w->basis_states; state < w->states; state++)
+      if (level_of_state [state] == max_level)
+      {
+	 const unsigned b   = !color || state <= root [0] ? 0 : state > root [1] ? 2 : 1;
+	 const unsigned bw  = width_of_level (max_level), bh = height_of_level (max_level);
+	 const int16_t *img = state_image (si, state, max_level);
+	 int16_t       *dst = frame [b] + (size_t) w->y [state][0] * aw + w->x [state][0];
+
+	 /* the block may reach beyond the frame where the bintree has no (visible) ranges:
+	    the reference computes such blocks in place and simply never writes there */
+	 const unsigned cw = w->x [state][0] >= aw ? 0 : (aw - w->x [state][0] < bw ? aw - w->x [state][0] : bw);
+
+	 for (unsigned y = 0; y < bh && w->y [state][0] + y < ah; y++)
+	    memcpy (dst + (size_t) y * aw, img + y * bw, cw * sizeof (int16_t));
+      }
+   /* crop to the size at coding time (decoder.c:500-527) */
+   for (unsigned b = 0; b < bands; b++)
+   {
+      for (unsigned y = 0; y < height; y++)
+	 memcpy (planes [b] + (size_t) y * width, frame [b] + (size_t) y * aw,
+		 width * sizeof (int16_t));
+      free (frame [b]);
+   }
+   for (state = 0; state < MAXSTATES; state++)
+      for (unsigned l = 0; l <= MAXLEVEL; l++)
+	 free (si->pix [state][l]);
+   free (si);
+   return 0;
+}

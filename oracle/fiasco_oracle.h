@@ -108,6 +108,14 @@ void	 fo_tree_model_kat (unsigned level, unsigned *counts, unsigned *total,
 			    float *child_bits, float *leaf_bits); /* bintree.c:55,70 */
 unsigned fo_image_level (unsigned width, unsigned height);	  /* coder.c:249-256 */
 
+/*
+ *  Regenerate the frame an automaton describes (decode_image, codec/decoder.c:412, 4:4:4): what
+ *  the coder itself does after every frame of a video (codec/coder.c:647).  planes [b]:
+ *  width * height shorts per band in the reference's pixel format.  Returns 0 on success.
+ */
+int fo_decode_image (const fo_wfa_t *wfa, int color, unsigned width, unsigned height,
+		     int16_t *const planes [3]);
+
 /* canonical text dump, same grammar as oracle/wfadump.c ("s"/"e" lines of one frame) */
 void fo_dump_wfa (const fo_wfa_t *wfa, const fo_params_t *p, FILE *f);
 

@@ -42,6 +42,12 @@ CASES = {
 }
 
 
+# predicted sequences: name -> (frames, width, height, quality, pattern)
+VIDEOS = {
+    "v160_q20_ippp": (4, 160, 128, 20, "ippp"),
+}
+
+
 def md5(b):
     return hashlib.md5(b).hexdigest()
 
@@ -83,6 +89,10 @@ def main():
             psnr = [float(v) for v in re.findall(r"([0-9.]+) dB", ps)]
             with gzip.GzipFile(os.path.join(GOLD, name + ".wfa.gz"), "wb", mtime=0) as f:
                 f.write(dump)
+            # the frame as the coder itself regenerates it (decode_image, codec/coder.c:647)
+            raw = os.path.join(tmp, name + ".raw")
+            subprocess.run([os.path.join(REF, "decdump"), fco, raw], check=True, env=env, capture_output=True)
+            decoded_md5 = md5(open(raw, "rb").read())
             tr = open(trace, "rb").read()
             lc = b"".join(l for l in tr.splitlines(True) if l.startswith(b"lc "))
             if keep_trace:
@@ -93,9 +103,34 @@ def main():
                 "width": int(img.shape[1]), "height": int(img.shape[0]), "color": int(img.ndim == 3),
                 "pnm_md5": md5(gen_frames.pnm_bytes(img)), "fco_md5": md5(fb), "fco_bytes": len(fb),
                 "lc_trace_md5": md5(lc), "lc_calls": lc.count(b"\n"),
-                "psnr_db": psnr,
+                "psnr_db": psnr, "decoded_md5": decoded_md5,
             }
             print(name, manifest[name]["fco_md5"], len(fb), psnr, flush=True)
+        # a short predicted sequence (BASELINE config 5 in small): I P P P, CLI defaults
+        for name, (n, w, h, q, pattern) in VIDEOS.items():
+            frames = list(gen_frames.video(n, w, h))
+            for i, fr_ in enumerate(frames):
+                gen_frames.write_pnm(os.path.join(tmp, "%s_%02d.pgm" % (name, i)), fr_)
+            fco = os.path.join(tmp, name + ".fco")
+            subprocess.run([os.path.join(REF, "cfiasco"), "--progress-meter=0", "-V", "0", "-q", str(q),
+                            "--pattern=" + pattern, "-i", "%s_[00-%02d+1].pgm" % (name, n - 1), "-o", fco],
+                           check=True, env=env, stderr=subprocess.DEVNULL)
+            fb = open(fco, "rb").read()
+            dump = subprocess.run([os.path.join(REF, "wfadump"), fco], check=True, env=env, capture_output=True).stdout
+            raw = os.path.join(tmp, name + ".raw")
+            subprocess.run([os.path.join(REF, "decdump"), fco, raw], check=True, env=env, capture_output=True)
+            rb = open(raw, "rb").read()
+            with gzip.GzipFile(os.path.join(GOLD, name + ".wfa.gz"), "wb", mtime=0) as f:
+                f.write(dump)
+            with gzip.GzipFile(os.path.join(GOLD, name + ".decoded.raw.gz"), "wb", mtime=0) as f:
+                f.write(rb)
+            per = len(rb) // n
+            manifest[name] = {
+                "video": True, "frames": n, "width": w, "height": h, "quality": q, "pattern": pattern,
+                "fco_md5": md5(fb), "fco_bytes": len(fb),
+                "decoded_md5": [md5(rb[i * per:(i + 1) * per]) for i in range(n)],
+            }
+            print(name, manifest[name]["fco_md5"], len(fb), flush=True)
     kat = subprocess.run([os.path.join(REF, "seamdump"), "--kat"], check=True, capture_output=True).stdout
     with gzip.GzipFile(os.path.join(GOLD, "kat.txt.gz"), "wb", mtime=0) as f:
         f.write(kat)

@@ -79,6 +79,16 @@ main (int argc, char **argv)
 		    (unsigned) wfa->x [state][1], (unsigned) wfa->y [state][1],
 		    (int) wfa->prediction [state][0],
 		    (int) wfa->prediction [state][1]);
+	    /* motion vectors and delta flags (predicted frames only: the lines are absent
+	       from intra frames, so the still-image goldens do not change) */
+	    for (label = 0; label < MAXLABELS; label++)
+	       if (wfa->mv_tree [state][label].type != NONE)
+		  printf ("m %u %u %d %d %d %d %d\n", state, label,
+			  (int) wfa->mv_tree [state][label].type,
+			  wfa->mv_tree [state][label].fx, wfa->mv_tree [state][label].fy,
+			  wfa->mv_tree [state][label].bx, wfa->mv_tree [state][label].by);
+	    if (wfa->delta_state [state])
+	       printf ("d %u\n", state);
 	    for (label = 0; label < MAXLABELS; label++)
 	       for (edge = 0; isedge (wfa->into [state][label][edge]); edge++)
 		  printf ("e %u %u %d %08x %.9g\n", state, label,

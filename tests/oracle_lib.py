@@ -85,6 +85,7 @@ def lib():
         L.fo_tree_model_kat.argtypes = [C.c_uint, C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(C.c_float),
                                         C.POINTER(C.c_float)]
         L.fo_tree_model_kat.restype = None
+        L.fo_decode_image.argtypes = [C.POINTER(FoWfa), C.c_int, C.c_uint, C.c_uint, C.POINTER(C.c_void_p)]
         L.fo_grey_to_plane.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         L.fo_rgb_to_planes.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
         libc = C.CDLL(None)
@@ -157,8 +158,22 @@ def encode(img, quality=20.0, optimize=0, want_trace=False, params=None):
         "matrix_bits": list(wfa.matrix_bits), "weights_bits": list(wfa.weights_bits),
         "stats": {k: getattr(st, k) for k, _ in FoStats._fields_},
         "trace": trace_lines,
+        "_struct": wfa,                            # for decode()
+        "_shape": (h, w, 3 if img.ndim == 3 else 1),
     }
     return d
+
+
+def decode(w):
+    """Regenerate the frame of an oracle automaton (fo_decode_image): list of int16 (h, w) planes in
+    the coder's pixel format."""
+    h, wd, bands = w["_shape"]
+    planes = [np.zeros((h, wd), np.int16) for _ in range(bands)]
+    ptrs = (C.c_void_p * 3)(*([p.ctypes.data for p in planes] + [None] * (3 - bands)))
+    rc = lib().fo_decode_image(C.byref(w["_struct"]), int(bands == 3), wd, h, ptrs)
+    if rc:
+        raise RuntimeError("oracle decode failed")
+    return planes
 
 
 def wfa_lines(w):
