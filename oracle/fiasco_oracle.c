@@ -2177,3 +2177,152 @@ fo_decode_image (const fo_wfa_t *w, int color, unsigned width, unsigned height,
    free (si);
    return 0;
 }
+
+/*****************************************************************************
+
+	     motion compensation of a regenerated frame  (codec/motion.c)
+
+*****************************************************************************/
+
+/* extract_mc_block (motion.c:232-334): the reference block displaced by (mx, my) */
+static void
+extract_mc_block (int16_t *mcblock, unsigned width, unsigned height,
+		  const int16_t *reference, unsigned ref_width, int half_pixel,
+		  unsigned xo, unsigned yo, int mx, int my)
+{
+   if (!half_pixel)
+   {
+      /* the reference adds the vector as unsigned numbers: same result modulo 2^32 */
+      const int16_t *rblock = reference + (ptrdiff_t) ((int) yo + my) * ref_width + ((int) xo + mx);
+
+      for (unsigned y = 0; y < height; y++)
+	 memcpy (mcblock + y * width, rblock + (size_t) y * ref_width, width * sizeof (int16_t));
+   }
+   else
+   {
+      const int16_t *r = reference + (ptrdiff_t) ((int) yo + my / 2) * ref_width + ((int) xo + mx / 2);
+
+      for (unsigned y = 0; y < height; y++)
+	 for (unsigned x = 0; x < width; x++)
+	 {
+	    const int16_t *q = r + (size_t) y * ref_width + x;
+
+	    if (!(mx & 1) && !(my & 1))
+	       mcblock [y * width + x] = q [0];
+	    else if (!(mx & 1))
+	       mcblock [y * width + x] = (int16_t) ((q [0] + q [ref_width]) >> 1);
+	    else if (!(my & 1))
+	       mcblock [y * width + x] = (int16_t) ((q [0] + q [1]) >> 1);
+	    else
+	       mcblock [y * width + x] = (int16_t) ((q [0] + q [1] + q [ref_width] + q [ref_width + 1]) >> 2);
+	 }
+   }
+}
+
+void
+fo_restore_mc (const fo_wfa_t *w, unsigned width, unsigned height, int half_pixel,
+	       int16_t *image, const int16_t *past)
+{
+   int16_t *mcblock = malloc (size_of_level (MAXLEVEL > 16 ? 16 : MAXLEVEL) * sizeof (int16_t));
+
+   (void) height;
+   for (unsigned state = w->basis_states; state <= w->root_state; state++)
+      for (unsigned label = 0; label < MAXLABELS; label++)
+	 if (w->mv_type [state][label] == 1)	/* FORWARD (motion.c:78-108) */
+	 {
+	    const unsigned level = w->level_of_state [state] - 1u;
+	    const unsigned bw = width_of_level (level), bh = height_of_level (level);
+
+	    extract_mc_block (mcblock, bw, bh, past, width, half_pixel, w->x [state][label],
+			      w->y [state][label], w->mv_fx [state][label], w->mv_fy [state][label]);
+	    for (unsigned y = 0; y < bh; y++)
+	       for (unsigned x = 0; x < bw; x++)
+	       {
+		  int16_t *o = image + (size_t) (w->y [state][label] + y) * width + w->x [state][label] + x;
+
+		  *o = (int16_t) (*o + mcblock [y * bw + x]);
+	       }
+	 }
+   free (mcblock);
+}
+
+int
+fo_wfa_from_dump (const char *text, unsigned root_state, fo_wfa_t *w)
+{
+   memset (w, 0, sizeof *w);
+   for (unsigned s = 0; s < MAXSTATES; s++)
+      for (unsigned l = 0; l < MAXLABELS; l++)
+      {
+	 w->into [s][l][0] = NO_EDGE;
+	 w->tree [s][l]	   = RANGE;
+	 w->y_state [s][l] = RANGE;
+      }
+   /* input/basis.c:126-131 */
+   w->basis_states = w->states = 3;
+   w->final_distribution [0] = 128;
+   w->final_distribution [1] = 64;
+   w->final_distribution [2] = 64;
+   append_edge (0, 0, 1.0f, 0, w);
+   append_edge (0, 0, 1.0f, 1, w);
+   append_edge (1, 2, 0.5f, 0, w);
+   append_edge (1, 2, 0.5f, 1, w);
+   append_edge (1, 0, 0.5f, 1, w);
+   append_edge (2, 1, 1.0f, 0, w);
+   append_edge (2, 1, 1.0f, 1, w);
+   for (unsigned s = 0; s < 3; s++)
+      w->level_of_state [s] = (uint8_t) -1;
+
+   const char *p = text;
+
+   while (*p)
+   {
+      unsigned s, l, a, b, c2, d2;
+      int      t0, t1, lv, into, ty, fx, fy, bx, by;
+      unsigned bits;
+
+      if (sscanf (p, "s %u %d %d %d %u %u %u %u", &s, &lv, &t0, &t1, &a, &b, &c2, &d2) == 8)
+      {
+	 if (s >= MAXSTATES)
+	    return 1;
+	 w->level_of_state [s] = (uint8_t) lv;
+	 w->tree [s][0] = (int16_t) t0;
+	 w->tree [s][1] = (int16_t) t1;
+	 w->x [s][0] = (uint16_t) a;
+	 w->y [s][0] = (uint16_t) b;
+	 w->x [s][1] = (uint16_t) c2;
+	 w->y [s][1] = (uint16_t) d2;
+	 if (s + 1 > w->states)
+	    w->states = s + 1;
+      }
+      else if (sscanf (p, "e %u %u %d %x", &s, &l, &into, &bits) == 4)
+      {
+	 float    f;
+	 unsigned e;
+
+	 memcpy (&f, &bits, sizeof f);
+	 for (e = 0; w->into [s][l][e] != NO_EDGE; e++)
+	    ;
+	 w->into [s][l][e]     = (int16_t) into;	/* the dump lists them in stored order */
+	 w->weight [s][l][e]   = f;
+	 w->into [s][l][e + 1] = NO_EDGE;
+      }
+      else if (sscanf (p, "m %u %u %d %d %d %d %d", &s, &l, &ty, &fx, &fy, &bx, &by) == 7)
+      {
+	 w->mv_type [s][l] = (int8_t) ty;
+	 w->mv_fx [s][l]   = (int8_t) fx;
+	 w->mv_fy [s][l]   = (int8_t) fy;
+	 w->mv_bx [s][l]   = (int8_t) bx;
+	 w->mv_by [s][l]   = (int8_t) by;
+      }
+      else if (sscanf (p, "d %u", &s) == 1)
+	 w->delta_state [s] = 1;
+      while (*p && *p != '\n')
+	 p++;
+      if (*p)
+	 p++;
+   }
+   w->root_state = root_state;
+   for (unsigned s = w->basis_states; s < w->states; s++)
+      w->final_distribution [s] = compute_final_distribution (s, w);
+   return 0;
+}

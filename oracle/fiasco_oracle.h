@@ -68,6 +68,14 @@ typedef struct fo_wfa
    uint8_t  y_column [FO_MAXSTATES][FO_MAXLABELS];
    /* root range summary per band (what print_statistics reports, coder.c:894) */
    float    costs [3], err [3], tree_bits [3], matrix_bits [3], weights_bits [3];
+   /* predicted frames (codec/wfa.h:62-71,126,137): motion compensation of the range
+      [state][label] -- type 0 none, 1 forward, 2 backward, 3 interpolated -- and the
+      states that describe a prediction error instead of image content */
+   int8_t   mv_type [FO_MAXSTATES][FO_MAXLABELS];
+   int8_t   mv_fx [FO_MAXSTATES][FO_MAXLABELS], mv_fy [FO_MAXSTATES][FO_MAXLABELS];
+   int8_t   mv_bx [FO_MAXSTATES][FO_MAXLABELS], mv_by [FO_MAXSTATES][FO_MAXLABELS];
+   uint8_t  delta_state [FO_MAXSTATES];
+   int	    frame_type;		/* 0 intra, 1 predicted, 2 bidirectional */
 } fo_wfa_t;
 
 /* work counters */
@@ -115,6 +123,21 @@ unsigned fo_image_level (unsigned width, unsigned height);	  /* coder.c:249-256 
  */
 int fo_decode_image (const fo_wfa_t *wfa, int color, unsigned width, unsigned height,
 		     int16_t *const planes [3]);
+
+/*
+ *  Build an automaton from the canonical text of ONE frame ("s" / "e" / "m" / "d" lines of
+ *  oracle/wfadump.c): the basis states as in input/basis.c:126-131, transitions and motion
+ *  vectors from the text, final distributions recomputed (codec/wfalib.c:154).  Used to pin the
+ *  decoder side on automata the reference produced.  Returns 0 on success.
+ */
+int fo_wfa_from_dump (const char *text, unsigned root_state, fo_wfa_t *wfa);
+
+/*
+ *  restore_mc (codec/motion.c:37-230) for a grey predicted frame: add the motion compensated
+ *  blocks of the regenerated previous frame 'past' to 'image' (both width * height shorts).
+ */
+void fo_restore_mc (const fo_wfa_t *wfa, unsigned width, unsigned height, int half_pixel,
+		    int16_t *image, const int16_t *past);
 
 /* canonical text dump, same grammar as oracle/wfadump.c ("s"/"e" lines of one frame) */
 void fo_dump_wfa (const fo_wfa_t *wfa, const fo_params_t *p, FILE *f);

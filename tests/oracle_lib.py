@@ -49,6 +49,9 @@ class FoWfa(C.Structure):
         ("y_column", C.c_uint8 * 2 * MAXSTATES),
         ("costs", C.c_float * 3), ("err", C.c_float * 3), ("tree_bits", C.c_float * 3),
         ("matrix_bits", C.c_float * 3), ("weights_bits", C.c_float * 3),
+        ("mv_type", C.c_int8 * 2 * MAXSTATES), ("mv_fx", C.c_int8 * 2 * MAXSTATES), ("mv_fy", C.c_int8 * 2 * MAXSTATES),
+        ("mv_bx", C.c_int8 * 2 * MAXSTATES), ("mv_by", C.c_int8 * 2 * MAXSTATES),
+        ("delta_state", C.c_uint8 * MAXSTATES), ("frame_type", C.c_int),
     ]
 
 
@@ -86,6 +89,9 @@ def lib():
                                         C.POINTER(C.c_float)]
         L.fo_tree_model_kat.restype = None
         L.fo_decode_image.argtypes = [C.POINTER(FoWfa), C.c_int, C.c_uint, C.c_uint, C.POINTER(C.c_void_p)]
+        L.fo_wfa_from_dump.argtypes = [C.c_char_p, C.c_uint, C.POINTER(FoWfa)]
+        L.fo_restore_mc.argtypes = [C.POINTER(FoWfa), C.c_uint, C.c_uint, C.c_int, C.c_void_p, C.c_void_p]
+        L.fo_restore_mc.restype = None
         L.fo_grey_to_plane.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         L.fo_rgb_to_planes.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
         libc = C.CDLL(None)
@@ -162,6 +168,33 @@ def encode(img, quality=20.0, optimize=0, want_trace=False, params=None):
         "_shape": (h, w, 3 if img.ndim == 3 else 1),
     }
     return d
+
+
+def golden_video_frames(name):
+    """[(frame number, frame type, states, root state, text of the frame's lines)] of a golden stream."""
+    txt = gzip.open(os.path.join(GOLDEN, name + ".wfa.gz"), "rt").read()
+    out = []
+    for part in txt.split("frame ")[1:]:
+        head, _, body = part.partition("\n")
+        number, ftype, states, root = (int(v) for v in head.split())
+        out.append((number, ftype, states, root, body))
+    return out
+
+
+def wfa_from_dump(text, root_state, width, height):
+    """Automaton (dict with the ctypes struct, for decode()) from the canonical text of one frame."""
+    w = FoWfa()
+    if lib().fo_wfa_from_dump(text.encode(), root_state, C.byref(w)):
+        raise RuntimeError("bad dump")
+    return {"_struct": w, "_shape": (height, width, 1), "states": w.states}
+
+
+def restore_mc(w, image, past, half_pixel=0):
+    """restore_mc (codec/motion.c:37) on a regenerated grey frame, in place."""
+    h, wd, _ = w["_shape"]
+    past = np.ascontiguousarray(past, np.int16)
+    lib().fo_restore_mc(C.byref(w["_struct"]), wd, h, half_pixel, image.ctypes.data, past.ctypes.data)
+    return image
 
 
 def decode(w):
