@@ -570,9 +570,10 @@ typedef struct range
    int16_t  into [MAXEDGES + 1];
    int	    tree;
    float    err, tree_bits, matrix_bits, weights_bits;
-   /* mv_tree_bits, mv_coord_bits, nd_tree_bits, nd_weights_bits are identically 0 on
-      the still-image path without prediction; they are kept as explicit zeros in the
-      sums below so that the order of fp32 additions matches cwfa.h:46-75 users */
+   /* prediction (cwfa.h:46-75): identically 0 / "none" on the still-image path */
+   float    mv_tree_bits, mv_coord_bits, nd_tree_bits, nd_weights_bits;
+   int	    prediction;		/* range is coded as motion compensation + delta image */
+   int	    mv_type, mv_fx, mv_fy;	/* codec/wfa.h:62-71 (forward vectors only: P frames) */
 } range_t;
 
 typedef struct coder
@@ -588,9 +589,19 @@ typedef struct coder
    float       *images_of_state [MAXSTATES];
    float       *ip_images_state [MAXSTATES];
    float       *ip_states_state [MAXSTATES][MAXLEVEL];
-   tree_model_t tree;
-   rle_model_t	pool;
-   coeff_t	coeff;
+   tree_model_t tree, p_tree;	/* bintree model, prediction-tree model (cwfa.h:96-97) */
+   rle_model_t	pool, d_pool;	/* domain pool; pool of the delta approximations */
+   coeff_t	coeff, d_coeff;
+   int		d_pool_is_rle;	/* predicted frames: the delta pool is a real "rle" pool,
+				   else the "constant" one (coder.c:720-725) */
+   rle_model_t *ap;		/* the pool / coefficient model approximate_range works with */
+   coeff_t     *ac;
+   /* motion (cwfa.h:33-44, mwfa.c:86-126) */
+   int		frame_type;	/* 0 intra, 1 predicted */
+   unsigned	p_min_level, p_max_level, search_range;
+   const int16_t *past;		/* regenerated previous frame */
+   float	xbits [64], ybits [64];
+   float       *mc_forward_norms [MAXLEVEL];
    fo_wfa_t    *wfa;
    fo_stats_t  *st;
    FILE	       *trace;
@@ -893,8 +904,12 @@ remove_states (unsigned from, fo_wfa_t *w) /* wfalib.c:276-310 */
 	 w->into [state][label][0] = NO_EDGE;
 	 w->tree [state][label]	   = RANGE;
 	 w->y_state [state][label] = RANGE;
+	 w->mv_type [state][label] = 0;
+	 w->mv_fx [state][label]   = w->mv_fy [state][label] = 0;
+	 w->mv_bx [state][label]   = w->mv_by [state][label] = 0;
       }
       w->domain_type [state] = 0;
+      w->delta_state [state] = 0;
    }
    w->states = from;
 }
@@ -1074,7 +1089,7 @@ matching_pursuit (mp_t *mp, int full_search, float price, unsigned max_edges,
    static int16_t  domain_blocks [MAXSTATES + 2];
 
    c->st->mp_calls++;
-   rle_generate (domain_blocks, y_state, w->domain_type, &c->pool);
+   rle_generate (domain_blocks, y_state, w->domain_type, c->ap);
    for (domain = 0; domain_blocks [domain] >= 0; domain++)
    {
       used [domain] = 0;
@@ -1099,12 +1114,13 @@ matching_pursuit (mp_t *mp, int full_search, float price, unsigned max_edges,
       norm += c->pixels [range->address * size + n]
 	      * c->pixels [range->address * size + n];
 
-   additional_bits = range->tree_bits + 0.0f + 0.0f + 0.0f + 0.0f;
+   additional_bits = range->tree_bits + range->mv_tree_bits + range->mv_coord_bits
+		     + range->nd_tree_bits + range->nd_weights_bits;
 
    mp->err	    = norm;
    mp->weights_bits = 0;
    mp->matrix_bits  = rle_bits (domain_blocks, NULL, y_state, w->domain_type,
-				&c->pool);
+				c->ap);
    mp->costs	    = (mp->matrix_bits + mp->weights_bits + additional_bits)
 		      * price + mp->err;
 
@@ -1140,9 +1156,9 @@ matching_pursuit (mp_t *mp, int full_search, float price, unsigned max_edges,
 	       vectors [i + 1] = -1;
 	       states [i + 1]  = -1;
 
-	       weights_bits = aac_bits (weights, states, range->level, &c->coeff);
+	       weights_bits = aac_bits (weights, states, range->level, c->ac);
 	       matrix_bits  = rle_bits (domain_blocks, vectors, y_state,
-					w->domain_type, &c->pool);
+					w->domain_type, c->ap);
 	    }
 	    if (((matrix_bits + weights_bits + additional_bits) * price
 		 + mp->err
@@ -1165,8 +1181,8 @@ matching_pursuit (mp_t *mp, int full_search, float price, unsigned max_edges,
 	       }
 	       for (l = (int) n; l >= 0; l--)
 	       {
-		  const rpf_t *rpf = domain_blocks [v [l]] ? &c->coeff.rpf
-							   : &c->coeff.dc_rpf;
+		  const rpf_t *rpf = domain_blocks [v [l]] ? &c->ac->rpf
+							   : &c->ac->dc_rpf;
 
 		  r [l] = f [l] = btor (rtob (f [l], rpf), rpf);
 		  for (k = 0; k < (unsigned) l; k++)
@@ -1188,9 +1204,9 @@ matching_pursuit (mp_t *mp, int full_search, float price, unsigned max_edges,
 		     }
 		  vectors [i] = -1;
 		  states [i]  = -1;
-		  w_bits = aac_bits (weights, states, range->level, &c->coeff);
+		  w_bits = aac_bits (weights, states, range->level, c->ac);
 		  m_bits = rle_bits (domain_blocks, vectors, y_state,
-				     w->domain_type, &c->pool);
+				     w->domain_type, c->ap);
 	       }
 	       /* the <v_l, o_n> loop of approx.c:554-569 only writes entries [..][n]
 		  that are never read again; it is kept because it is
@@ -1264,7 +1280,7 @@ matching_pursuit (mp_t *mp, int full_search, float price, unsigned max_edges,
 static int
 is_overflow_weight (float weight, int index, const coder_t *c) /* approx.c:172-176 */
 {
-   const rpf_t *rpf = index ? &c->coeff.rpf : &c->coeff.dc_rpf;
+   const rpf_t *rpf = index ? &c->ac->rpf : &c->ac->dc_rpf;
 
    return weight == btor (rtob (200, rpf), rpf)
 	  || weight == btor (rtob (-200, rpf), rpf);
@@ -1366,9 +1382,9 @@ approximate_range (float max_costs, float price, int max_edges, int y_state,
       mp.indices [new_index] = NO_EDGE;
       mp.into [new_index]    = NO_EDGE;
 
-      rle_generate (domain_blocks, y_state, w->domain_type, &c->pool);
-      rle_update (domain_blocks, mp.indices, y_state, w->domain_type, &c->pool);
-      aac_update (mp.weight, mp.into, range->level, &c->coeff);
+      rle_generate (domain_blocks, y_state, w->domain_type, c->ap);
+      rle_update (domain_blocks, mp.indices, y_state, w->domain_type, c->ap);
+      aac_update (mp.weight, mp.into, range->level, c->ac);
 
       for (edge = 0; mp.indices [edge] != NO_EDGE; edge++)
       {
@@ -1457,19 +1473,23 @@ init_range (range_t *range, unsigned band, coder_t *c) /* subdivide.c:612-644 */
 }
 
 static void
-init_new_state (int auxiliary_state, range_t *range, const range_t *child,
+init_new_state (int auxiliary_state, int delta, range_t *range, const range_t *child,
 		const int *y_state, coder_t *c) /* subdivide.c:549-610 */
 {
    fo_wfa_t *w = c->wfa;
    unsigned  label, edge;
    int	     state_is_domain = 0;
 
+   /* options.delta_domains = options.normal_domains = YES (options.c:91-92): every state
+      that may be a domain enters both pools.  The delta pool of an intra frame is the
+      "constant" pool whose append() always says YES (domain-pool.c:962-967,
+      coder.c:720-725) */
    if (!auxiliary_state)
+   {
       state_is_domain = rle_append (&c->pool, w->states);
-   /* the delta pool on a still is the "constant" pool whose append() always says
-      YES (domain-pool.c:962-967, coder.c:720-725; options.normal_domains = YES) */
-   if (!auxiliary_state)
-      state_is_domain = 1 || state_is_domain;
+      state_is_domain = (c->d_pool_is_rle ? rle_append (&c->d_pool, w->states) : 1)
+			|| state_is_domain;
+   }
 
    range->into [0] = NO_EDGE;
    range->tree	   = (int) w->states;
@@ -1477,6 +1497,9 @@ init_new_state (int auxiliary_state, range_t *range, const range_t *child,
    {
       w->tree [w->states][label]    = (int16_t) child [label].tree;
       w->y_state [w->states][label] = (int16_t) y_state [label];
+      w->mv_type [w->states][label] = (int8_t) child [label].mv_type;
+      w->mv_fx [w->states][label]   = (int8_t) child [label].mv_fx;
+      w->mv_fy [w->states][label]   = (int8_t) child [label].mv_fy;
       w->x [w->states][label]	    = (uint16_t) child [label].x;
       w->y [w->states][label]	    = (uint16_t) child [label].y;
       /* append_transitions, control.c:175-197 */
@@ -1489,21 +1512,417 @@ init_new_state (int auxiliary_state, range_t *range, const range_t *child,
 	    w->y_column [w->states][label] = 1;
       }
    }
+   w->delta_state [w->states] = (uint8_t) delta;
    append_state (!state_is_domain, compute_final_distribution (w->states, w),
 		 range->level, c);
 }
 
+static float subdivide (float max_costs, unsigned band, int y_state, range_t *range,
+			coder_t *c, int prediction, int delta);
+
+/*****************************************************************************
+		 motion search  (codec/mwfa.c, codec/prediction.c)
+*****************************************************************************/
+
+static void extract_mc_block (int16_t *mcblock, unsigned width, unsigned height,
+			      const int16_t *reference, unsigned ref_width, int half_pixel,
+			      unsigned xo, unsigned yo, int mx, int my);
+
+/* MPEG's code lengths of the vector components (mwfa.c:40-52, second column) */
+static const unsigned char mv_code_length [33] =
+{11, 11, 11, 11, 11, 11, 10, 10, 10, 8, 8, 8, 7, 5, 4, 3, 1, 3, 4, 5, 7, 8, 8, 8, 10, 10, 10,
+ 11, 11, 11, 11, 11, 11};
+
+static unsigned
+norms_size (const coder_t *c)	/* full-pixel search: (2 * search_range)^2 vectors */
+{
+   return 4 * c->search_range * c->search_range;
+}
+
+/* clear_norms_table (prediction.c:195-211) */
+static void
+clear_norms_table (unsigned level, coder_t *c)
+{
+   if (level > c->p_min_level)
+      memset (c->mc_forward_norms [level], 0, norms_size (c) * sizeof (float));
+}
+
+/* update_norms_table (prediction.c:213-238): a level's norms are the sums of its children's */
+static void
+update_norms_table (unsigned level, coder_t *c)
+{
+   if (level > c->p_min_level)
+      for (unsigned index = 0; index < norms_size (c); index++)
+	 c->mc_forward_norms [level][index] += c->mc_forward_norms [level - 1][index];
+}
+
+/* mcpe_norm (mwfa.c:651-684) over get_mcpe (:604-649), forward prediction: the squared
+   norm of (original - displaced reference) / 16, summed in row order in fp32 */
+static float
+mcpe_norm (const coder_t *c, unsigned x0, unsigned y0, unsigned width, unsigned height,
+	   const int16_t *mcblock)
+{
+   const int16_t *o    = c->planes [0] + (size_t) y0 * (unsigned) c->opt.width + x0;
+   float	  norm = 0;
+
+   for (unsigned y = 0; y < height; y++)
+      for (unsigned x = 0; x < width; x++)
+      {
+	 const int16_t d = (int16_t) (o [(size_t) y * (unsigned) c->opt.width + x] - mcblock [y * width + x]);
+	 const int     q = d / 16;
+
+	 norm += (float) (q * q);
+      }
+   return norm;
+}
+
+/* fill_norms_table (mwfa.c:544-602), P frames */
+static void
+fill_norms_table (unsigned x0, unsigned y0, unsigned level, coder_t *c)
+{
+   const int	  sr	 = (int) c->search_range;
+   const unsigned width	 = width_of_level (level), height = height_of_level (level);
+   int16_t	 *mcblock = malloc ((size_t) width * height * sizeof (int16_t));
+   unsigned	  index	 = 0;
+
+   for (int my = -sr; my < sr; my++)
+      for (int mx = -sr; mx < sr; mx++, index++)
+      {
+	 if ((int) x0 + mx < 0 || x0 + mx + width > (unsigned) c->opt.width
+	     || (int) y0 + my < 0 || y0 + my + height > (unsigned) c->opt.height)
+	    c->mc_forward_norms [level][index] = 0.0f;
+	 else
+	 {
+	    extract_mc_block (mcblock, width, height, c->past, (unsigned) c->opt.width, 0,
+			      x0, y0, mx, my);
+	    c->mc_forward_norms [level][index] = mcpe_norm (c, x0, y0, width, height, mcblock);
+	 }
+      }
+   free (mcblock);
+}
+
+/* find_best_mv (mwfa.c:686-795), full-pixel search */
+static float
+find_best_mv (float price, unsigned x0, unsigned y0, unsigned width, unsigned height,
+	      float *bits, int *mx, int *my, const float *mc_norms, const coder_t *c)
+{
+   const int sr	      = (int) c->search_range;
+   float     mincosts = MAXCOSTS;
+   unsigned  index    = 0;
+
+   *mx = *my = 0;
+   for (int y = -sr; y < sr; y++)
+      for (int x = -sr; x < sr; x++, index++)
+	 if ((int) x0 + x >= 0 && (int) y0 + y >= 0
+	     && x0 + x + width <= (unsigned) c->opt.width
+	     && y0 + y + height <= (unsigned) c->opt.height)
+	 {
+	    const float costs = mc_norms [index] + (c->xbits [x + sr] + c->ybits [y + sr]) * price;
+
+	    if (costs < mincosts)
+	    {
+	       mincosts = costs;
+	       *mx	= x;
+	       *my	= y;
+	    }
+	 }
+   *bits = c->xbits [*mx + sr] + c->ybits [*my + sr];
+   return mincosts;
+}
+
+/* saved state data (prediction.c:47-70) */
+typedef struct state_data
+{
+   float    final_distribution;
+   uint8_t  level_of_state, domain_type;
+   float   *images_of_state, *inner_products, *ip_states_state [MAXLEVEL];
+   int16_t  tree [MAXLABELS], y_state [MAXLABELS], into [MAXLABELS][MAXEDGES + 1];
+   uint8_t  y_column [MAXLABELS];
+   int8_t   mv_type [MAXLABELS], mv_fx [MAXLABELS], mv_fy [MAXLABELS];
+   uint16_t x [MAXLABELS], y [MAXLABELS];
+   float    weight [MAXLABELS][MAXEDGES + 1];
+} state_data_t;
+
+/* store_state_data (prediction.c:502-560): move the states from..to aside.  The delta
+   flag of a state is NOT part of the saved data (nor of the restored data below) */
+static state_data_t *
+store_state_data (unsigned from, unsigned to, coder_t *c)
+{
+   fo_wfa_t	*w = c->wfa;
+   state_data_t *data;
+
+   if (to + 1 <= from)
+      return NULL;
+   data = calloc (to - from + 1, sizeof *data);
+   for (unsigned state = from; state <= to; state++)
+   {
+      state_data_t *sd = &data [state - from];
+
+      sd->final_distribution = w->final_distribution [state];
+      sd->level_of_state     = w->level_of_state [state];
+      sd->domain_type	     = w->domain_type [state];
+      sd->images_of_state    = c->images_of_state [state];
+      sd->inner_products     = c->ip_images_state [state];
+      w->domain_type [state]	 = 0;
+      c->images_of_state [state] = NULL;
+      c->ip_images_state [state] = NULL;
+      for (unsigned label = 0; label < MAXLABELS; label++)
+      {
+	 sd->tree [label]     = w->tree [state][label];
+	 sd->y_state [label]  = w->y_state [state][label];
+	 sd->y_column [label] = w->y_column [state][label];
+	 sd->mv_type [label]  = w->mv_type [state][label];
+	 sd->mv_fx [label]    = w->mv_fx [state][label];
+	 sd->mv_fy [label]    = w->mv_fy [state][label];
+	 sd->x [label]	      = w->x [state][label];
+	 sd->y [label]	      = w->y [state][label];
+	 memcpy (sd->weight [label], w->weight [state][label], sizeof sd->weight [label]);
+	 memcpy (sd->into [label], w->into [state][label], sizeof sd->into [label]);
+	 w->into [state][label][0] = NO_EDGE;
+	 w->tree [state][label]	   = RANGE;
+	 w->y_state [state][label] = RANGE;
+      }
+      for (unsigned level = (unsigned) c->opt.images_level + 1;
+	   level <= (unsigned) c->opt.lc_max_level; level++)
+      {
+	 sd->ip_states_state [level]	   = c->ip_states_state [state][level];
+	 c->ip_states_state [state][level] = NULL;
+      }
+   }
+   return data;
+}
+
+/* restore_state_data (prediction.c:562-625) */
+static void
+restore_state_data (unsigned from, unsigned to, state_data_t *data, coder_t *c)
+{
+   fo_wfa_t *w = c->wfa;
+
+   if (to + 1 <= from)
+      return;
+   for (unsigned state = from; state <= to; state++)
+   {
+      state_data_t *sd = &data [state - from];
+
+      w->final_distribution [state] = sd->final_distribution;
+      w->level_of_state [state]	    = sd->level_of_state;
+      w->domain_type [state]	    = sd->domain_type;
+      free (c->images_of_state [state]);
+      c->images_of_state [state] = sd->images_of_state;
+      free (c->ip_images_state [state]);
+      c->ip_images_state [state] = sd->inner_products;
+      for (unsigned label = 0; label < MAXLABELS; label++)
+      {
+	 w->tree [state][label]	    = sd->tree [label];
+	 w->y_state [state][label]  = sd->y_state [label];
+	 w->y_column [state][label] = sd->y_column [label];
+	 w->mv_type [state][label]  = sd->mv_type [label];
+	 w->mv_fx [state][label]    = sd->mv_fx [label];
+	 w->mv_fy [state][label]    = sd->mv_fy [label];
+	 w->x [state][label]	    = sd->x [label];
+	 w->y [state][label]	    = sd->y [label];
+	 memcpy (w->weight [state][label], sd->weight [label], sizeof sd->weight [label]);
+	 memcpy (w->into [state][label], sd->into [label], sizeof sd->into [label]);
+      }
+      for (unsigned level = (unsigned) c->opt.images_level + 1;
+	   level <= (unsigned) c->opt.lc_max_level; level++)
+      {
+	 free (c->ip_states_state [state][level]);
+	 c->ip_states_state [state][level] = sd->ip_states_state [level];
+      }
+   }
+   free (data);
+   w->states = to + 1;
+}
+
+static void
+free_state_data (unsigned from, unsigned to, state_data_t *data, coder_t *c)
+{
+   if (to + 1 <= from)
+      return;
+   for (unsigned state = from; state <= to; state++)
+   {
+      state_data_t *sd = &data [state - from];
+
+      for (unsigned level = (unsigned) c->opt.images_level + 1;
+	   level <= (unsigned) c->opt.lc_max_level; level++)
+	 free (sd->ip_states_state [level]);
+      free (sd->images_of_state);
+      free (sd->inner_products);
+   }
+   free (data);
+}
+
+/* mc_prediction (prediction.c:262-370), P frames */
+static float
+mc_prediction (float max_costs, float price, unsigned band, int y_state, range_t *range,
+	       coder_t *c)
+{
+   fo_wfa_t	 *w	 = c->wfa;
+   range_t	  prange = *range;
+   const unsigned width	 = width_of_level (range->level);
+   const unsigned height = height_of_level (range->level);
+   int16_t	 *mcpe	 = calloc ((size_t) width * height, sizeof (int16_t));
+   float	  costs;
+
+   if (prange.level == c->p_min_level)
+      fill_norms_table (prange.x, prange.y, prange.level, c);
+   /* find_P_frame_mc (mwfa.c:301-339) */
+   {
+      int16_t *mcblock = calloc ((size_t) width * height, sizeof (int16_t));
+
+      prange.mv_tree_bits = 1;
+      prange.mv_type	  = 1;	/* FORWARD */
+      find_best_mv (price, prange.x, prange.y, width, height, &prange.mv_coord_bits,
+		    &prange.mv_fx, &prange.mv_fy, c->mc_forward_norms [prange.level], c);
+      extract_mc_block (mcblock, width, height, c->past, (unsigned) c->opt.width, 0,
+			prange.x, prange.y, prange.mv_fx, prange.mv_fy);
+      for (unsigned y = 0; y < height; y++)	/* get_mcpe (mwfa.c:604-649) */
+	 for (unsigned x = 0; x < width; x++)
+	    mcpe [y * width + x]
+	       = (int16_t) (c->planes [0][(size_t) (prange.y + y) * (unsigned) c->opt.width + prange.x + x]
+			    - mcblock [y * width + x]);
+      free (mcblock);
+   }
+   costs = (prange.mv_tree_bits + prange.mv_coord_bits) * price;
+
+   if (costs < max_costs)
+   {
+      const unsigned last_state = w->states - 1;
+      float	    *rec_pixels = c->pixels;
+      float	   **ipi	= calloc (MAXSTATES, sizeof (float *));
+      float	     mvt, mvc;
+
+      c->pixels = calloc ((size_t) width * height, sizeof (float));
+      cut_to_bintree (c->pixels, mcpe, width, height, 0, 0, width, height);
+      for (unsigned state = 0; state <= last_state; state++)
+	 if (need_image (state, w))
+	 {
+	    ipi [state]		       = c->ip_images_state [state];
+	    c->ip_images_state [state] = calloc (size_of_tree (c->products_level), sizeof (float));
+	 }
+      mvc = prange.mv_coord_bits;
+      mvt = prange.mv_tree_bits;
+      prange.image	     = 0;
+      prange.address	     = 0;
+      prange.tree_bits	     = 0;
+      prange.matrix_bits     = 0;
+      prange.weights_bits    = 0;
+      prange.mv_coord_bits   = 0;
+      prange.mv_tree_bits    = 0;
+      prange.nd_weights_bits = 0;
+      prange.nd_tree_bits    = 0;
+
+      compute_ip_images_state (prange.image, prange.address, prange.level, 1, 0, c);
+      costs += subdivide (max_costs - costs, band, y_state, &prange, c, 0, 1);
+
+      if (costs < max_costs)
+      {
+	 const unsigned img = range->image, adr = range->address;
+
+	 *range		      = prange;
+	 range->image	      = img;
+	 range->address	      = adr;
+	 range->mv_coord_bits = mvc;
+	 range->mv_tree_bits  = mvt;
+	 range->prediction    = 1;
+	 for (unsigned state = last_state + 1; state < w->states; state++)
+	    if (need_image (state, w))
+	       memset (c->ip_images_state [state], 0,
+		       size_of_tree (c->products_level) * sizeof (float));
+	 costs = (range->tree_bits + range->matrix_bits + range->weights_bits
+		  + range->mv_tree_bits + range->mv_coord_bits + range->nd_tree_bits
+		  + range->nd_weights_bits) * price + range->err;
+      }
+      else
+	 costs = MAXCOSTS;
+      for (unsigned state = 0; state <= last_state; state++)
+	 if (need_image (state, w))
+	 {
+	    free (c->ip_images_state [state]);
+	    c->ip_images_state [state] = ipi [state];
+	 }
+      free (ipi);
+      free (c->pixels);
+      c->pixels = rec_pixels;
+   }
+   else
+      costs = MAXCOSTS;
+   free (mcpe);
+   return costs;
+}
+
+/* predict_range (prediction.c:96-191), P frames */
+static float
+predict_range (float max_costs, float price, range_t *range, coder_t *c, unsigned band,
+	       int y_state, unsigned states, const tree_model_t *tree_model,
+	       const tree_model_t *p_tree_model, const rle_model_t *domain_model,
+	       const rle_model_t *d_domain_model, const aac_model_t *coeff_model,
+	       const aac_model_t *d_coeff_model)
+{
+   fo_wfa_t	*w = c->wfa;
+   rle_model_t	*rec_domain_model   = malloc (sizeof (rle_model_t));
+   rle_model_t	*rec_d_domain_model = malloc (sizeof (rle_model_t));
+   aac_model_t	 rec_coeff_model    = c->coeff.model;
+   aac_model_t	 rec_d_coeff_model  = c->d_coeff.model;
+   tree_model_t	 rec_tree_model	    = c->tree;
+   tree_model_t	 rec_p_tree_model   = c->p_tree;
+   unsigned	 rec_states	    = w->states;
+   state_data_t *rec_state_data;
+   float	 costs;
+
+   rle_copy (rec_domain_model, &c->pool);
+   rle_copy (rec_d_domain_model, &c->d_pool);
+   rec_state_data = store_state_data (states, rec_states - 1, c);
+
+   w->states	    = states;
+   c->tree	    = *tree_model;
+   c->p_tree	    = *p_tree_model;
+   rle_copy (&c->pool, domain_model);
+   rle_copy (&c->d_pool, d_domain_model);
+   c->coeff.model   = *coeff_model;
+   c->d_coeff.model = *d_coeff_model;
+
+   costs = mc_prediction (max_costs, price, band, y_state, range, c);
+
+   if (costs < MAXCOSTS)
+   {
+      free_state_data (states, rec_states - 1, rec_state_data, c);
+      costs = (range->tree_bits + range->matrix_bits + range->weights_bits
+	       + range->mv_tree_bits + range->mv_coord_bits + range->nd_tree_bits
+	       + range->nd_weights_bits) * price + range->err;
+   }
+   else
+   {
+      rle_copy (&c->pool, rec_domain_model);
+      rle_copy (&c->d_pool, rec_d_domain_model);
+      c->coeff.model   = rec_coeff_model;
+      c->d_coeff.model = rec_d_coeff_model;
+      c->tree	       = rec_tree_model;
+      c->p_tree	       = rec_p_tree_model;
+      range->prediction = 0;
+      if (w->states != states)
+	 remove_states (states, w);
+      restore_state_data (states, rec_states - 1, rec_state_data, c);
+      costs = MAXCOSTS;
+   }
+   free (rec_domain_model);
+   free (rec_d_domain_model);
+   return costs;
+}
+
 static float
 subdivide (float max_costs, unsigned band, int y_state, range_t *range,
-	   coder_t *c) /* subdivide.c:60-502, still-image path (no prediction) */
+	   coder_t *c, int prediction, int delta) /* subdivide.c:60-502 */
 {
    fo_wfa_t    *w = c->wfa;
    float	subdivide_costs, lincomb_costs, price;
    int		new_y_state [MAXLABELS];
    unsigned	states;
-   rle_model_t *domain_model, *lc_domain_model;
-   aac_model_t	coeff_model, lc_coeff_model;
-   tree_model_t tree_model;
+   int		try_mc;
+   rle_model_t *domain_model, *lc_domain_model, *d_domain_model, *lc_d_domain_model;
+   aac_model_t	coeff_model, lc_coeff_model, d_coeff_model, lc_d_coeff_model;
+   tree_model_t tree_model, p_tree_model;
    range_t	lrange, rrange, child [MAXLABELS];
 
    c->st->subdivide_calls++;
@@ -1513,6 +1932,14 @@ subdivide (float max_costs, unsigned band, int y_state, range_t *range,
       return MAXCOSTS;
    if (range->x >= (unsigned) c->opt.width || range->y >= (unsigned) c->opt.height)
       return 0;
+
+   /* motion compensation allowed for this range? (subdivide.c:141-147) */
+   try_mc = (prediction && c->frame_type != 0
+	     && range->level >= c->p_min_level && range->level <= c->p_max_level
+	     && range->x + width_of_level (range->level) <= (unsigned) c->opt.width
+	     && range->y + height_of_level (range->level) <= (unsigned) c->opt.height);
+   if (try_mc)
+      clear_norms_table (range->level, c);
 
    if (range->level == (unsigned) c->opt.lc_max_level)
       init_range (range, band, c);
@@ -1535,21 +1962,33 @@ subdivide (float max_costs, unsigned band, int y_state, range_t *range,
       new_y_state [0] = new_y_state [1] = RANGE;
 
    /* snapshot of every model the recursion may modify (subdivide.c:188-194) */
-   domain_model	   = malloc (sizeof (rle_model_t));
-   lc_domain_model = malloc (sizeof (rle_model_t));
+   domain_model	     = malloc (sizeof (rle_model_t));
+   lc_domain_model   = malloc (sizeof (rle_model_t));
+   d_domain_model    = malloc (sizeof (rle_model_t));
+   lc_d_domain_model = malloc (sizeof (rle_model_t));
    rle_copy (domain_model, &c->pool);
-   coeff_model = c->coeff.model;
-   tree_model  = c->tree;
-   states      = w->states;
+   rle_copy (d_domain_model, &c->d_pool);
+   coeff_model	 = c->coeff.model;
+   d_coeff_model = c->d_coeff.model;
+   tree_model	 = c->tree;
+   p_tree_model	 = c->p_tree;
+   states	 = w->states;
 
    /* alternative 1: linear combination */
    if (range->level <= (unsigned) c->opt.lc_max_level)
    {
-      lrange		  = *range;
-      lrange.tree	  = RANGE;
-      lrange.tree_bits	  = tree_bits (0, lrange.level, &c->tree);
-      lrange.matrix_bits  = 0;
-      lrange.weights_bits = 0;
+      lrange		     = *range;
+      lrange.tree	     = RANGE;
+      lrange.tree_bits	     = tree_bits (0, lrange.level, &c->tree);
+      lrange.matrix_bits     = 0;
+      lrange.weights_bits    = 0;
+      lrange.mv_tree_bits    = try_mc ? 1 : 0;	/* mc allowed but not used */
+      lrange.mv_coord_bits   = 0;
+      lrange.nd_tree_bits    = 0;
+      lrange.nd_weights_bits = 0;
+      lrange.prediction	     = 0;
+      c->ap = delta ? &c->d_pool : &c->pool;
+      c->ac = delta ? &c->d_coeff : &c->coeff;
       lincomb_costs = approximate_range (max_costs, price, c->opt.max_elements,
 					 y_state, &lrange, c);
       if (c->trace)
@@ -1577,9 +2016,13 @@ subdivide (float max_costs, unsigned band, int y_state, range_t *range,
 
    /* keep the "lc" models, restore the snapshot (subdivide.c:226-237) */
    rle_copy (lc_domain_model, &c->pool);
-   lc_coeff_model = c->coeff.model;
+   rle_copy (lc_d_domain_model, &c->d_pool);
+   lc_coeff_model   = c->coeff.model;
+   lc_d_coeff_model = c->d_coeff.model;
    rle_copy (&c->pool, domain_model);
-   c->coeff.model = coeff_model;
+   rle_copy (&c->d_pool, d_domain_model);
+   c->coeff.model   = coeff_model;
+   c->d_coeff.model = d_coeff_model;
 
    /* alternative 2: recursive subdivision */
    if (range->level > (unsigned) c->opt.lc_min_level)
@@ -1587,13 +2030,20 @@ subdivide (float max_costs, unsigned band, int y_state, range_t *range,
       unsigned label;
 
       memset (child, 0, sizeof child);
-      rrange		  = *range;
-      rrange.tree_bits	  = tree_bits (1, rrange.level, &c->tree);
-      rrange.matrix_bits  = 0;
-      rrange.weights_bits = 0;
-      rrange.err	  = 0;
+      rrange		     = *range;
+      rrange.tree_bits	     = tree_bits (1, rrange.level, &c->tree);
+      rrange.matrix_bits     = 0;
+      rrange.weights_bits    = 0;
+      rrange.err	     = 0;
+      rrange.mv_tree_bits    = try_mc ? 1 : 0;
+      rrange.mv_coord_bits   = 0;
+      rrange.nd_tree_bits    = 0;
+      rrange.nd_weights_bits = 0;
+      rrange.prediction	     = 0;
       subdivide_costs = (rrange.tree_bits + rrange.weights_bits
-			 + rrange.matrix_bits + 0.0f + 0.0f + 0.0f + 0.0f) * price;
+			 + rrange.matrix_bits + rrange.mv_tree_bits
+			 + rrange.mv_coord_bits + rrange.nd_tree_bits
+			 + rrange.nd_weights_bits) * price;
 
       for (label = 0; label < MAXLABELS; label++)
       {
@@ -1615,47 +2065,78 @@ subdivide (float max_costs, unsigned band, int y_state, range_t *range,
 
 	 remaining_costs = fmin2 (lincomb_costs, max_costs) - subdivide_costs;
 	 if (remaining_costs > 0)
-	    subdivide_costs += subdivide (remaining_costs, band,
-					  new_y_state [label], &child [label], c);
+	    subdivide_costs += subdivide (remaining_costs, band, new_y_state [label],
+					  &child [label], c, prediction, delta);
+	 else if (try_mc && child [label].level >= c->p_min_level)
+	    fill_norms_table (child [label].x, child [label].y, child [label].level, c);
+
+	 if (try_mc)
+	    update_norms_table (rrange.level, c);
 
 	 if (subdivide_costs >= fmin2 (lincomb_costs, max_costs))
 	 {
 	    subdivide_costs = MAXCOSTS;
 	    break;
 	 }
-	 rrange.err	     += child [label].err;
-	 rrange.tree_bits    += child [label].tree_bits;
-	 rrange.matrix_bits  += child [label].matrix_bits;
-	 rrange.weights_bits += child [label].weights_bits;
+	 rrange.err		+= child [label].err;
+	 rrange.tree_bits	+= child [label].tree_bits;
+	 rrange.matrix_bits	+= child [label].matrix_bits;
+	 rrange.weights_bits	+= child [label].weights_bits;
+	 rrange.mv_tree_bits	+= child [label].mv_tree_bits;
+	 rrange.mv_coord_bits	+= child [label].mv_coord_bits;
+	 rrange.nd_weights_bits += child [label].nd_weights_bits;
+	 rrange.nd_tree_bits	+= child [label].nd_tree_bits;
 
 	 tree_update (child [label].tree != RANGE, child [label].level, &c->tree);
+	 tree_update (child [label].prediction ? 0 : 1, child [label].level, &c->p_tree);
       }
    }
    else
       subdivide_costs = MAXCOSTS;
 
+   /* alternative 3: motion compensation + approximation of the prediction error
+      (subdivide.c:383-407) */
+   if (try_mc)
+   {
+      const float prediction_costs
+	 = predict_range (fmin2 (fmin2 (lincomb_costs, subdivide_costs), max_costs), price,
+			  range, c, band, y_state, states, &tree_model, &p_tree_model,
+			  domain_model, d_domain_model, &coeff_model, &d_coeff_model);
+
+      if (prediction_costs < MAXCOSTS)
+      {
+	 free (domain_model);
+	 free (lc_domain_model);
+	 free (d_domain_model);
+	 free (lc_d_domain_model);
+	 return prediction_costs;
+      }
+   }
+
    if (lincomb_costs >= MAXCOSTS && subdivide_costs >= MAXCOSTS)
    {
       rle_copy (&c->pool, domain_model);
-      c->coeff.model = coeff_model;
-      c->tree	     = tree_model;
+      rle_copy (&c->d_pool, d_domain_model);
+      c->coeff.model   = coeff_model;
+      c->d_coeff.model = d_coeff_model;
+      c->tree	       = tree_model;
+      c->p_tree	       = p_tree_model;
       if (w->states != states)
 	 remove_states (states, w);
-      free (domain_model);
-      free (lc_domain_model);
-      return MAXCOSTS;
+      subdivide_costs = MAXCOSTS;
    }
    else if (lincomb_costs < subdivide_costs)
    {
       rle_copy (&c->pool, lc_domain_model);
-      c->coeff.model = lc_coeff_model;
-      c->tree	     = tree_model;
-      *range	     = lrange;
+      rle_copy (&c->d_pool, lc_d_domain_model);
+      c->coeff.model   = lc_coeff_model;
+      c->d_coeff.model = lc_d_coeff_model;
+      c->tree	       = tree_model;
+      c->p_tree	       = p_tree_model;
+      *range	       = lrange;
       if (w->states != states)
 	 remove_states (states, w);
-      free (domain_model);
-      free (lc_domain_model);
-      return lincomb_costs;
+      subdivide_costs = lincomb_costs;
    }
    else
    {
@@ -1663,12 +2144,14 @@ subdivide (float max_costs, unsigned band, int y_state, range_t *range,
 		|| range->x + width_of_level (range->level) > (unsigned) c->opt.width
 		|| range->y + height_of_level (range->level) > (unsigned) c->opt.height;
 
-      init_new_state (aux, &rrange, child, new_y_state, c);
+      init_new_state (aux, delta, &rrange, child, new_y_state, c);
       *range = rrange;
-      free (domain_model);
-      free (lc_domain_model);
-      return subdivide_costs;
    }
+   free (domain_model);
+   free (lc_domain_model);
+   free (d_domain_model);
+   free (lc_d_domain_model);
+   return subdivide_costs;
 }
 
 /*****************************************************************************
@@ -1892,6 +2375,15 @@ fo_encode (const fo_params_t *p, const int16_t *const planes [3], fo_wfa_t *out,
 	 rle_append (&c->pool, state);
    aac_init (&c->coeff, c->rpf, c->dc_rpf, (unsigned) c->opt.lc_min_level,
 	     (unsigned) c->opt.lc_max_level);
+   /* the delta side of a still: "constant" pool, its own (never used) coefficient model */
+   init_tree_model (&c->p_tree);
+   rle_init (&c->d_pool, (unsigned) c->opt.max_states);
+   aac_init (&c->d_coeff, c->rpf, c->dc_rpf, (unsigned) c->opt.lc_min_level,
+	     (unsigned) c->opt.lc_max_level);
+   c->d_pool_is_rle = 0;
+   c->frame_type    = 0;
+   c->ap	    = &c->pool;
+   c->ac	    = &c->coeff;
 
    if (!p->color)
    {
@@ -1899,7 +2391,7 @@ fo_encode (const fo_params_t *p, const int16_t *const planes [3], fo_wfa_t *out,
 
       memset (&range, 0, sizeof range);
       range.level = c->level;
-      out->costs [0] = subdivide (MAXCOSTS, 0, RANGE, &range, c);
+      out->costs [0] = subdivide (MAXCOSTS, 0, RANGE, &range, c, 0, 0);
       if (range.tree == RANGE)
 	 fail (c, "No root state generated!");
       w->root_state	    = (unsigned) range.tree;
@@ -1938,7 +2430,7 @@ fo_encode (const fo_params_t *p, const int16_t *const planes [3], fo_wfa_t *out,
 	 }
 	 memset (&range, 0, sizeof range);
 	 range.level = c->level;
-	 out->costs [band] = subdivide (MAXCOSTS, band, tree [0], &range, c);
+	 out->costs [band] = subdivide (MAXCOSTS, band, tree [0], &range, c, 0, 0);
 	 out->err [band]	  = range.err;
 	 out->tree_bits [band]	  = range.tree_bits;
 	 out->matrix_bits [band]  = range.matrix_bits;
@@ -2325,4 +2817,192 @@ fo_wfa_from_dump (const char *text, unsigned root_state, fo_wfa_t *w)
    for (unsigned s = w->basis_states; s < w->states; s++)
       w->final_distribution [s] = compute_final_distribution (s, w);
    return 0;
+}
+
+/*****************************************************************************
+
+	      sequences  (video_coder / frame_coder, codec/coder.c:490-892)
+
+*****************************************************************************/
+
+/*
+ *  Encode a grey sequence: frame 0 intra, the others by 'pattern' (I or P per frame,
+ *  coder.c:522-535, 684-706), every predicted frame against the regenerated previous
+ *  frame (coder.c:560-651).  out [f] receives the automaton of frame f, reconst (if not
+ *  NULL) the regenerated frames, width * height shorts each.  Returns 0 on success.
+ */
+int
+fo_encode_video (const fo_params_t *p, int n_frames, const int16_t *const *frames,
+		 const char *pattern, int p_min_level, int p_max_level, int search_range,
+		 fo_wfa_t *out, int16_t *reconst, char *errbuf, size_t errlen)
+{
+   static int  tables_ready = 0;
+   coder_t    *c = calloc (1, sizeof (coder_t));
+   fo_wfa_t   *w = calloc (1, sizeof (fo_wfa_t));
+   fo_stats_t  dummy;
+   const size_t npix = (size_t) p->width * p->height;
+   int16_t    *past = calloc (npix, sizeof (int16_t)), *cur = calloc (npix, sizeof (int16_t));
+   unsigned    state, label, level;
+   int	       rc = 0;
+
+   if (!tables_ready)
+   {
+      init_matrix_probabilities ();
+      tables_ready = 1;
+   }
+   memset (&dummy, 0, sizeof dummy);
+   c->st     = &dummy;
+   c->errbuf = errbuf;
+   c->errlen = errlen;
+   c->wfa    = w;
+   c->opt    = *p;
+   if (setjmp (c->env))
+   {
+      rc = 1;
+      goto cleanup;
+   }
+   if (p->color)
+      fail (c, "fo_encode_video: grey sequences only");
+   if ((p->width & 1) || (p->height & 1))
+      fail (c, "Width and height of images must be even numbers.");
+   if (p->quality <= 0)
+      fail (c, "Compression quality has to be positive.");
+   if (search_range < 1 || search_range > 16)
+      fail (c, "search range must be in 1..16");
+
+   for (state = 0; state < MAXSTATES; state++)
+      for (label = 0; label < MAXLABELS; label++)
+      {
+	 w->into [state][label][0] = NO_EDGE;
+	 w->tree [state][label]	   = RANGE;
+	 w->y_state [state][label] = RANGE;
+      }
+   /* alloc_coder (coder.c:249-327) */
+   c->level = w->level = fo_image_level ((unsigned) p->width, (unsigned) p->height);
+   c->opt.lc_min_level = p->lc_min_level > 3 ? p->lc_min_level : 3;
+   c->opt.lc_max_level = fmin2 (p->lc_max_level, (int) c->level - 1);
+   if (c->opt.lc_min_level > c->opt.lc_max_level)
+      c->opt.lc_min_level = c->opt.lc_max_level;
+   c->opt.images_level = fmin2 (p->images_level, c->opt.lc_max_level - 1);
+   c->products_level
+      = (unsigned) (c->opt.lc_max_level - c->opt.images_level - 1 > 0
+		    ? c->opt.lc_max_level - c->opt.images_level - 1 : 0);
+   c->pixels = calloc (size_of_level ((unsigned) c->opt.lc_max_level), sizeof (float));
+   {
+      int ms = fmin2 (p->max_states, MAXSTATES);
+      c->opt.max_states = ms > 1 ? ms : 1;
+      ms = fmin2 (p->max_elements, MAXEDGES);
+      c->opt.max_elements = ms > 1 ? ms : 1;
+   }
+   c->rpf    = make_rpf ((unsigned) p->rpf_mantissa, p->rpf_range_e);
+   c->dc_rpf = make_rpf ((unsigned) p->dc_rpf_mantissa, p->dc_rpf_range_e);
+   /* prediction levels are a subset of the range levels (coder.c:284-290) */
+   c->p_min_level = (unsigned) (p_min_level > c->opt.lc_min_level ? p_min_level : c->opt.lc_min_level);
+   c->p_max_level = (unsigned) fmin2 (p_max_level, c->opt.lc_max_level);
+   if (c->p_min_level > c->p_max_level)
+      c->p_min_level = c->p_max_level;
+   c->search_range = (unsigned) search_range;
+   /* alloc_motion (mwfa.c:86-126) */
+   for (int dx = -search_range; dx < search_range; dx++)
+      c->xbits [dx + search_range] = c->ybits [dx + search_range]
+				   = (float) mv_code_length [dx + search_range];
+   for (level = c->p_min_level; level <= c->p_max_level; level++)
+      c->mc_forward_norms [level] = calloc (norms_size (c), sizeof (float));
+
+   append_basis_states (c);
+   c->price = 128 * 64 / p->quality;
+
+   for (int f = 0; f < n_frames; f++)
+   {
+      range_t range;
+      int     type = 0;
+
+      if (f > 0)
+      {
+	 const int t = pattern [(size_t) f % strlen (pattern)];
+
+	 if (t == 'p' || t == 'P')
+	    type = 1;
+	 else if (t != 'i' && t != 'I')
+	    fail (c, "fo_encode_video: frame type %c is not handled (I and P only)", t);
+      }
+      c->frame_type = type;
+      c->planes [0] = frames [f];
+      c->past	    = type ? past : NULL;
+
+      /* frame_coder (coder.c:692-755) */
+      init_tree_model (&c->tree);
+      init_tree_model (&c->p_tree);
+      rle_init (&c->pool, (unsigned) c->opt.max_states);
+      rle_init (&c->d_pool, (unsigned) c->opt.max_states);
+      c->d_pool_is_rle = type != 0;
+      for (state = 0; state < w->basis_states; state++)
+	 if (usedomain (state, w))
+	 {
+	    rle_append (&c->pool, state);
+	    if (c->d_pool_is_rle)
+	       rle_append (&c->d_pool, state);
+	 }
+      aac_init (&c->coeff, c->rpf, c->dc_rpf, (unsigned) c->opt.lc_min_level,
+		(unsigned) c->opt.lc_max_level);
+      aac_init (&c->d_coeff, c->rpf, c->dc_rpf, (unsigned) c->opt.lc_min_level,
+		(unsigned) c->opt.lc_max_level);
+      c->ap = &c->pool;
+      c->ac = &c->coeff;
+
+      memset (&range, 0, sizeof range);
+      range.level = c->level;
+      w->costs [0] = subdivide (MAXCOSTS, 0, RANGE, &range, c, type != 0, 0);
+      if (range.tree == RANGE)
+	 fail (c, "No root state generated!");
+      w->root_state	  = (unsigned) range.tree;
+      w->frame_type	  = type;
+      /* locate_delta_images (wfalib.c:699-730, called at coder.c:876): the delta flags the
+	 stream carries are derived from the structure, top down */
+      for (state = w->root_state; state >= w->basis_states; state--)
+	 w->delta_state [state] = 0;
+      for (state = w->root_state; state >= w->basis_states; state--)
+	 for (label = 0; label < MAXLABELS; label++)
+	    if (w->tree [state][label] != RANGE
+		&& (w->mv_type [state][label] != 0 || w->into [state][label][0] != NO_EDGE
+		    || w->delta_state [state]))
+	       w->delta_state [w->tree [state][label]] = 1;
+      w->err [0]	  = range.err;
+      w->tree_bits [0]	  = range.tree_bits;
+      w->matrix_bits [0]  = range.matrix_bits;
+      w->weights_bits [0] = range.weights_bits;
+      memcpy (&out [f], w, sizeof *w);
+
+      /* regenerate the frame: the next frame's reference (coder.c:642-651) */
+      {
+	 int16_t *planes [3] = {cur, NULL, NULL};
+
+	 fo_decode_image (w, 0, (unsigned) p->width, (unsigned) p->height, planes);
+	 if (type)
+	    fo_restore_mc (w, (unsigned) p->width, (unsigned) p->height, 0, cur, past);
+	 if (reconst)
+	    memcpy (reconst + (size_t) f * npix, cur, npix * sizeof (int16_t));
+	 int16_t *t = past;
+	 past = cur;
+	 cur  = t;
+      }
+      remove_states (w->basis_states, w);
+   }
+
+cleanup:
+   for (state = 0; state < MAXSTATES; state++)
+   {
+      free (c->images_of_state [state]);
+      free (c->ip_images_state [state]);
+      for (level = 0; level < MAXLEVEL; level++)
+	 free (c->ip_states_state [state][level]);
+   }
+   for (level = 0; level < MAXLEVEL; level++)
+      free (c->mc_forward_norms [level]);
+   free (c->pixels);
+   free (c);
+   free (w);
+   free (past);
+   free (cur);
+   return rc;
 }

@@ -139,6 +139,16 @@ int fo_wfa_from_dump (const char *text, unsigned root_state, fo_wfa_t *wfa);
 void fo_restore_mc (const fo_wfa_t *wfa, unsigned width, unsigned height, int half_pixel,
 		    int16_t *image, const int16_t *past);
 
+/*
+ *  Encode a grey sequence (video_coder / frame_coder, codec/coder.c:490-892): frame 0 intra, the
+ *  others I or P by 'pattern'; predicted frames use motion compensation against the regenerated
+ *  previous frame (codec/prediction.c, codec/mwfa.c).  frames [f]: width * height shorts.
+ *  out [f]: automaton of frame f; reconst (or NULL): the regenerated frames.  0 on success.
+ */
+int fo_encode_video (const fo_params_t *p, int n_frames, const int16_t *const *frames,
+		     const char *pattern, int p_min_level, int p_max_level, int search_range,
+		     fo_wfa_t *out, int16_t *reconst, char *errbuf, size_t errlen);
+
 /* canonical text dump, same grammar as oracle/wfadump.c ("s"/"e" lines of one frame) */
 void fo_dump_wfa (const fo_wfa_t *wfa, const fo_params_t *p, FILE *f);
 

@@ -45,6 +45,7 @@ CASES = {
 # predicted sequences: name -> (frames, width, height, quality, pattern)
 VIDEOS = {
     "v160_q20_ippp": (4, 160, 128, 20, "ippp"),
+    "v352_q30_ippip": (5, 352, 288, 30, "ippip"),   # the regenerated frames of this one: md5 only
 }
 
 
@@ -122,8 +123,9 @@ def main():
             rb = open(raw, "rb").read()
             with gzip.GzipFile(os.path.join(GOLD, name + ".wfa.gz"), "wb", mtime=0) as f:
                 f.write(dump)
-            with gzip.GzipFile(os.path.join(GOLD, name + ".decoded.raw.gz"), "wb", mtime=0) as f:
-                f.write(rb)
+            if len(rb) < 400000:
+                with gzip.GzipFile(os.path.join(GOLD, name + ".decoded.raw.gz"), "wb", mtime=0) as f:
+                    f.write(rb)
             per = len(rb) // n
             manifest[name] = {
                 "video": True, "frames": n, "width": w, "height": h, "quality": q, "pattern": pattern,

@@ -89,6 +89,8 @@ def lib():
                                         C.POINTER(C.c_float)]
         L.fo_tree_model_kat.restype = None
         L.fo_decode_image.argtypes = [C.POINTER(FoWfa), C.c_int, C.c_uint, C.c_uint, C.POINTER(C.c_void_p)]
+        L.fo_encode_video.argtypes = [C.POINTER(FoParams), C.c_int, C.POINTER(C.c_void_p), C.c_char_p, C.c_int, C.c_int,
+                                      C.c_int, C.POINTER(FoWfa), C.c_void_p, C.c_char_p, C.c_size_t]
         L.fo_wfa_from_dump.argtypes = [C.c_char_p, C.c_uint, C.POINTER(FoWfa)]
         L.fo_restore_mc.argtypes = [C.POINTER(FoWfa), C.c_uint, C.c_uint, C.c_int, C.c_void_p, C.c_void_p]
         L.fo_restore_mc.restype = None
@@ -207,6 +209,46 @@ def decode(w):
     if rc:
         raise RuntimeError("oracle decode failed")
     return planes
+
+
+def encode_video(frames, quality=20.0, pattern="ippp", p_min_level=6, p_max_level=10, search_range=16):
+    """Run the oracle on a grey sequence (list of u8 (h, w) frames; CLI defaults of cfiasco).  Returns
+    (list of automata as ctypes structs wrapped like wfa_from_dump(), regenerated frames int16 [n][h][w])."""
+    L = lib()
+    h, w = frames[0].shape
+    planes = [planes_of(f)[0] for f in frames]
+    ptrs = (C.c_void_p * len(planes))(*[pl.ctypes.data for pl in planes])
+    p = default_params(w, h, 0, quality, 0)
+    out = (FoWfa * len(frames))()
+    rec = np.zeros((len(frames), h, w), np.int16)
+    err = C.create_string_buffer(256)
+    rc = L.fo_encode_video(C.byref(p), len(frames), ptrs, pattern.encode(), p_min_level, p_max_level, search_range,
+                           out, rec.ctypes.data, err, 256)
+    if rc:
+        raise RuntimeError("oracle: " + err.value.decode())
+    return [{"_struct": out[i], "_shape": (h, w, 1), "states": out[i].states} for i in range(len(frames))], rec
+
+
+def struct_lines(st):
+    """Canonical lines ('s', 'm', 'd', 'e' in the order of oracle/wfadump.c) of a ctypes automaton."""
+    out = []
+    for s in range(st.basis_states, st.states):
+        out.append("s %d %d %d %d %d %d %d %d 0 0" % (s, st.level_of_state[s], st.tree[s][0], st.tree[s][1],
+                                                   st.x[s][0], st.y[s][0], st.x[s][1], st.y[s][1]))
+        for label in range(2):
+            if st.mv_type[s][label]:
+                out.append("m %d %d %d %d %d %d %d" % (s, label, st.mv_type[s][label], st.mv_fx[s][label],
+                                                     st.mv_fy[s][label], st.mv_bx[s][label], st.mv_by[s][label]))
+        if st.delta_state[s]:
+            out.append("d %d" % s)
+        for label in range(2):
+            for e in range(6):
+                t = st.into[s][label][e]
+                if t < 0:
+                    break
+                wgt = np.float32(st.weight[s][label][e])
+                out.append("e %d %d %d %08x %.9g" % (s, label, t, int(wgt.view(np.uint32)), float(wgt)))
+    return out
 
 
 def wfa_lines(w):
