@@ -275,6 +275,7 @@ fiasco_coder (char const *const *inputname, const char *outputname, float qualit
       {
 	 fi_wfa_t w;
 
+	 memset (&w, 0, sizeof w);	/* intra frame: no motion data */
 	 w.info		  = &wi;
 	 w.states	  = wfas [n].states;
 	 w.basis_states	  = wfas [n].basis_states;
@@ -344,6 +345,14 @@ int
 fiasco_write_stream (const char *filename, const fiasco_stream_info_t *info,
 		     const fb200_wfa_t *frames, int n_frames)
 {
+   return fiasco_write_video_stream (filename, info, frames, NULL, n_frames, 16);
+}
+
+int
+fiasco_write_video_stream (const char *filename, const fiasco_stream_info_t *info,
+			   const fb200_wfa_t *frames, const fiasco_frame_motion_t *motion,
+			   int n_frames, unsigned search_range)
+{
    fi_try
    {
       fi_wfainfo_t wi;
@@ -352,7 +361,7 @@ fiasco_write_stream (const char *filename, const fiasco_stream_info_t *info,
 
       if (!info || !frames || n_frames < 1)
       {
-	 fi_set_error ("fiasco_write_stream: bad arguments");
+	 fi_set_error ("fiasco_write_video_stream: bad arguments");
 	 return 0;
       }
       memset (&wi, 0, sizeof wi);
@@ -372,7 +381,7 @@ fiasco_write_stream (const char *filename, const fiasco_stream_info_t *info,
       wi.fps	       = info->fps;
       wi.p_min_level   = info->p_min_level;
       wi.p_max_level   = info->p_max_level;
-      wi.search_range  = 16;
+      wi.search_range  = search_range;
       wi.half_pixel    = 0;
       wi.B_as_past_ref = 1;
       wi.smoothing     = info->smoothing;
@@ -389,6 +398,7 @@ fiasco_write_stream (const char *filename, const fiasco_stream_info_t *info,
 
 	 if (frames [n].status != FB200_OK)
 	    fi_error ("frame %d holds no automaton (status %d)", n, frames [n].status);
+	 memset (&w, 0, sizeof w);
 	 w.info		  = &wi;
 	 w.states	  = frames [n].states;
 	 w.basis_states	  = frames [n].basis_states;
@@ -400,6 +410,18 @@ fiasco_write_stream (const char *filename, const fiasco_stream_info_t *info,
 	 w.weight	  = (const float (*)[2][6]) frames [n].weight;
 	 w.y_state	  = (const int16_t (*)[2]) frames [n].y_state;
 	 w.y_column	  = (const uint8_t (*)[2]) frames [n].y_column;
+	 if (motion && motion [n].frame_type != 0)
+	 {
+	    if (motion [n].frame_type != 1 || info->color)
+	       fi_error ("frame %d: only grey P frames can be written", n);
+	    w.frame_type  = motion [n].frame_type;
+	    w.x		  = (const uint16_t (*)[2]) frames [n].x;
+	    w.y		  = (const uint16_t (*)[2]) frames [n].y;
+	    w.mv_type	  = (const int8_t (*)[2]) motion [n].mv_type;
+	    w.mv_fx	  = (const int8_t (*)[2]) motion [n].mv_fx;
+	    w.mv_fy	  = (const int8_t (*)[2]) motion [n].mv_fy;
+	    w.delta_state = motion [n].delta_state;
+	 }
 	 fi_write_next_wfa (&w, (unsigned) n, n == 0, 1, 1, out);
       }
       fi_bits_close (out);

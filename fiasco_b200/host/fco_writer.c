@@ -488,33 +488,59 @@ write_matrices (int use_normal_domains, int use_delta_domains, const fi_wfa_t *w
 static void
 write_weights (unsigned total, const fi_wfa_t *wfa, fi_bits_t *out)
 {
-   unsigned  state, label, offset1, offset2, offset3, i;
+   unsigned  state, label, offset1, offset2, offset3, offset4, i;
    unsigned *weights = fiasco_calloc (total, sizeof (unsigned));
    unsigned *levels  = fiasco_calloc (total, sizeof (unsigned));
    unsigned *c_symbols;
    unsigned  n = 0;
    int	     min_level = FI_MAXLEVEL, max_level = 0, dc = 0;
+   int	     d_min_level = FI_MAXLEVEL, d_max_level = 0, d_dc = 0, delta_approx = 0;
 
+   /* has a delta approximation (prediction error of a predicted range) been used?
+      (output/weights.c:60-68) */
+   if (wfa->delta_state)
+      for (state = wfa->basis_states; state < wfa->states; state++)
+	 if (wfa->delta_state [state])
+	 {
+	    delta_approx = 1;
+	    break;
+	 }
+#define IS_DELTA(s) (delta_approx && wfa->delta_state [s])
    for (state = wfa->basis_states; state < wfa->states; state++)
       for (label = 0; label < FI_MAXLABELS; label++)
 	 if (isrange (wfa->tree [state][label]))
 	 {
 	    const int l = (int) wfa->level_of_state [state] - 1;
 
-	    if (l < min_level)
-	       min_level = l;
-	    if (l > max_level)
-	       max_level = l;
-	    if (wfa->into [state][label][0] == 0)
-	       dc = 1;
+	    if (IS_DELTA (state))
+	    {
+	       if (l < d_min_level)
+		  d_min_level = l;
+	       if (l > d_max_level)
+		  d_max_level = l;
+	       if (wfa->into [state][label][0] == 0)
+		  d_dc = 1;
+	    }
+	    else
+	    {
+	       if (l < min_level)
+		  min_level = l;
+	       if (l > max_level)
+		  max_level = l;
+	       if (wfa->into [state][label][0] == 0)
+		  dc = 1;
+	    }
 	 }
    if (min_level > max_level)
       max_level = min_level - 1;
-   /* contexts: [0] DC weights, then one per range level (no delta contexts on an
-      intra frame; their level interval is empty: d_max = d_min - 1) */
+   if (d_min_level > d_max_level)
+      d_max_level = d_min_level - 1;
+   /* contexts (output/weights.c:104-115): [0] DC weights, [1] delta DC weights, one per
+      range level, one per delta range level */
    offset1 = dc ? 1 : 0;
-   offset2 = offset1;
+   offset2 = offset1 + (d_dc ? 1 : 0);
    offset3 = offset2 + (unsigned) (max_level - min_level + 1);
+   offset4 = offset3 + (unsigned) (d_max_level - d_min_level + 1);
 
    for (state = wfa->basis_states; state < wfa->states; state++)
       for (label = 0; label < FI_MAXLABELS; label++)
@@ -529,28 +555,115 @@ write_weights (unsigned total, const fi_wfa_t *wfa, fi_bits_t *out)
 		  fi_error ("Can't write more than %d weights.", total);
 	       if (domain)
 	       {
-		  weights [n] = (unsigned) fi_rtob (wfa->weight [state][label][edge],
-						    &wfa->info->rpf);
-		  levels [n]  = offset2 + (unsigned) ((int) wfa->level_of_state [state]
-						      - 1 - min_level);
+		  if (IS_DELTA (state))
+		  {
+		     weights [n] = (unsigned) fi_rtob (wfa->weight [state][label][edge],
+						       &wfa->info->d_rpf);
+		     levels [n]	 = offset3 + (unsigned) ((int) wfa->level_of_state [state]
+							 - 1 - d_min_level);
+		  }
+		  else
+		  {
+		     weights [n] = (unsigned) fi_rtob (wfa->weight [state][label][edge],
+						       &wfa->info->rpf);
+		     levels [n]	 = offset2 + (unsigned) ((int) wfa->level_of_state [state]
+							 - 1 - min_level);
+		  }
 	       }
 	       else
 	       {
-		  weights [n] = (unsigned) fi_rtob (wfa->weight [state][label][edge],
-						    &wfa->info->dc_rpf);
-		  levels [n]  = 0;
+		  if (IS_DELTA (state))
+		  {
+		     weights [n] = (unsigned) fi_rtob (wfa->weight [state][label][edge],
+						       &wfa->info->d_dc_rpf);
+		     levels [n]	 = offset1;
+		  }
+		  else
+		  {
+		     weights [n] = (unsigned) fi_rtob (wfa->weight [state][label][edge],
+						       &wfa->info->dc_rpf);
+		     levels [n]	 = 0;
+		  }
 	       }
 	       n++;
 	    }
 	 }
-   c_symbols	 = fiasco_calloc (offset3 ? offset3 : 1, sizeof (unsigned));
+#undef IS_DELTA
+   c_symbols	 = fiasco_calloc (offset4 ? offset4 : 1, sizeof (unsigned));
    c_symbols [0] = 1u << (wfa->info->dc_rpf.mantissa_bits + 1);
+   if (offset1 != offset2)
+      c_symbols [offset1] = 1u << (wfa->info->d_dc_rpf.mantissa_bits + 1);
    for (i = offset2; i < offset3; i++)
       c_symbols [i] = 1u << (wfa->info->rpf.mantissa_bits + 1);
-   fi_encode_array (out, weights, levels, c_symbols, offset3, total, 500);
+   for (; i < offset4; i++)
+      c_symbols [i] = 1u << (wfa->info->d_rpf.mantissa_bits + 1);
+   fi_encode_array (out, weights, levels, c_symbols, offset4, total, 500);
    free (c_symbols);
    free (weights);
    free (levels);
+}
+
+/* ------------------------------------------------------- motion (output/mc.c) ---- */
+
+/* MPEG's Huffman code of a vector component: value, length (codec/mwfa.c:40-52) */
+static const unsigned short mv_code_table [33][2] =
+{
+   {0x19, 11}, {0x1b, 11}, {0x1d, 11}, {0x1f, 11}, {0x21, 11}, {0x23, 11}, {0x13, 10},
+   {0x15, 10}, {0x17, 10}, {0x7, 8}, {0x9, 8}, {0xb, 8}, {0x7, 7}, {0x3, 5}, {0x3, 4},
+   {0x3, 3}, {0x1, 1}, {0x2, 3}, {0x2, 4}, {0x2, 5}, {0x6, 7}, {0xa, 8}, {0x8, 8},
+   {0x6, 8}, {0x16, 10}, {0x14, 10}, {0x12, 10}, {0x22, 11}, {0x20, 11}, {0x1e, 11},
+   {0x1c, 11}, {0x1a, 11}, {0x18, 11}
+};
+
+/*
+ *  write_mc (output/mc.c:75-84) for a predicted (P) frame: the tree of "motion compensated
+ *  or not" decisions in breadth-first order from the highest prediction level down
+ *  (encode_mc_tree, :91-150; P frames: one bit per decision, 1 = none), then the vector
+ *  components in state order (encode_mc_coords, :152-251).
+ */
+static void
+write_mc (const fi_wfa_t *wfa, fi_bits_t *out)
+{
+   const fi_wfainfo_t *wi	 = wfa->info;
+   const unsigned      max_state = wi->color ? (unsigned) wfa->tree [wfa->tree [wfa->root_state][0]][0]
+					     : wfa->states;
+   unsigned	      *queue	 = fiasco_calloc (wfa->states + 1, sizeof (unsigned));
+   unsigned	       last = 0, current, state, label;
+
+   if (!wfa->mv_type || !wfa->x || !wfa->y)
+      fi_error ("predicted frame without motion data");
+   for (state = wfa->basis_states; state < max_state; state++)
+      if ((int) wfa->level_of_state [state] - 1 == (int) wi->p_max_level)
+	 queue [last++] = state;
+   for (current = 0; current < last; current++)
+      for (label = 0; label < FI_MAXLABELS; label++)
+      {
+	 state = queue [current];
+	 const int	type  = wfa->mv_type [state][label];
+	 const unsigned level = (unsigned) wfa->level_of_state [state] - 1;
+
+	 if (wfa->x [state][label] + (1u << (level >> 1)) <= wi->width
+	     && wfa->y [state][label] + (1u << ((level + 1) >> 1)) <= wi->height)
+	    fi_put_bit (out, type == 0);	/* p_frame_codes: none = 1, forward = 0 */
+	 if (type == 0 && !isrange (wfa->tree [state][label])
+	     && (int) level >= (int) wi->p_min_level)
+	    queue [last++] = (unsigned) wfa->tree [state][label];
+      }
+   fi_byte_align (out);
+   for (state = wfa->basis_states; state < max_state; state++)
+      for (label = 0; label < FI_MAXLABELS; label++)
+	 if (wfa->mv_type [state][label] == 1)		/* FORWARD */
+	 {
+	    const unsigned ix = (unsigned) (wfa->mv_fx [state][label] + (int) wi->search_range);
+	    const unsigned iy = (unsigned) (wfa->mv_fy [state][label] + (int) wi->search_range);
+
+	    fi_put_bits (out, mv_code_table [ix][0], mv_code_table [ix][1]);
+	    fi_put_bits (out, mv_code_table [iy][0], mv_code_table [iy][1]);
+	 }
+	 else if (wfa->mv_type [state][label] != 0)
+	    fi_error ("only forward motion vectors (P frames) can be written");
+   fi_byte_align (out);
+   free (queue);
 }
 
 /* ------------------------------------------------------------------ frame ---- */
@@ -566,13 +679,15 @@ fi_write_next_wfa (const fi_wfa_t *wfa, unsigned frame_number, int first,
    if (first)
       fi_write_header (wfa->info, out);
    fi_write_rice (out, wfa->states, RICE_K);
-   fi_write_rice (out, 0, RICE_K);		/* frame type: I_FRAME */
+   fi_write_rice (out, (unsigned) wfa->frame_type, RICE_K);	/* 0 I_FRAME, 1 P_FRAME */
    fi_write_rice (out, frame_number, RICE_K);
    fi_byte_align (out);
    fi_put_bit (out, 0);				/* no tiling permutation */
    fi_byte_align (out);
    write_tree (wfa, out);
    fi_put_bit (out, 0);				/* no nondeterministic prediction */
+   if (wfa->frame_type != 0)
+      write_mc (wfa, out);
    edges = write_matrices (normal_domains, delta_domains, wfa, out);
    if (edges)
       write_weights (edges, wfa, out);

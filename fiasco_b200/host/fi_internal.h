@@ -152,6 +152,11 @@ typedef struct fi_wfa
    const float	  (*weight) [2][6];
    const int16_t  (*y_state) [2];
    const uint8_t  (*y_column) [2];
+   /* predicted frames (NULL / 0 for an intra frame): codec/wfa.h:62-71,126,137 */
+   int		   frame_type;		/* 0 intra, 1 predicted */
+   const uint16_t (*x) [2], (*y) [2];	/* range coordinates (the motion tree asks for them) */
+   const int8_t	  (*mv_type) [2], (*mv_fx) [2], (*mv_fy) [2];
+   const uint8_t  *delta_state;
 } fi_wfa_t;
 
 void fi_write_header (const fi_wfainfo_t *wi, fi_bits_t *out);

@@ -19,6 +19,11 @@ class StreamInfo(C.Structure):
     ]
 
 
+class FrameMotion(C.Structure):
+    _fields_ = [("frame_type", C.c_int), ("mv_type", C.c_void_p), ("mv_fx", C.c_void_p), ("mv_fy", C.c_void_p),
+                ("delta_state", C.c_void_p)]
+
+
 def lib_path():
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libfiasco.so")
 
@@ -32,6 +37,8 @@ def load():
         L.fiasco_stream_info_init.argtypes = [C.POINTER(StreamInfo), C.POINTER(ffi.Params)]
         L.fiasco_stream_info_init.restype = None
         L.fiasco_write_stream.argtypes = [C.c_char_p, C.POINTER(StreamInfo), C.POINTER(ffi._Wfa), C.c_int]
+        L.fiasco_write_video_stream.argtypes = [C.c_char_p, C.POINTER(StreamInfo), C.POINTER(ffi._Wfa),
+                                                C.POINTER(FrameMotion), C.c_int, C.c_uint]
         L.fiasco_coder.argtypes = [C.POINTER(C.c_char_p), C.c_char_p, C.c_float, C.c_void_p]
         L.fiasco_c_options_new.restype = C.c_void_p
         L.fiasco_c_options_delete.argtypes = [C.c_void_p]
@@ -84,6 +91,29 @@ def write_stream(path, params, wfas, title=None, comment=None):
         keep.append(k)
     if not L.fiasco_write_stream(path.encode(), C.byref(info), arr, len(wfas)):
         raise RuntimeError("fiasco_write_stream: " + error_message())
+
+
+def write_video_stream(path, params, wfas, p_min_level=6, p_max_level=10, search_range=16):
+    """Serialise a sequence with predicted frames: every automaton dict also holds "frame_type" and, for
+    predicted frames, "mv_type", "mv_fx", "mv_fy" ([states][2] int8) and "delta_state" ([states] uint8)."""
+    L = load()
+    info = StreamInfo()
+    L.fiasco_stream_info_init(C.byref(info), C.byref(params))
+    info.p_min_level, info.p_max_level = p_min_level, p_max_level
+    arr = (ffi._Wfa * len(wfas))()
+    mot = (FrameMotion * len(wfas))()
+    keep = []
+    for i, w in enumerate(wfas):
+        arr[i], k = wfa_struct(w)
+        keep.append(k)
+        mot[i].frame_type = int(w.get("frame_type", 0))
+        if mot[i].frame_type:
+            for name, dt in (("mv_type", np.int8), ("mv_fx", np.int8), ("mv_fy", np.int8), ("delta_state", np.uint8)):
+                a = np.ascontiguousarray(w[name], dtype=dt)
+                k[name] = a
+                setattr(mot[i], name, a.ctypes.data)
+    if not L.fiasco_write_video_stream(path.encode(), C.byref(info), arr, mot, len(wfas), search_range):
+        raise RuntimeError("fiasco_write_video_stream: " + error_message())
 
 
 def cli_options(optimize=0):

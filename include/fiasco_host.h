@@ -42,6 +42,31 @@ void fiasco_stream_info_init (fiasco_stream_info_t *info, const fb200_params_t *
 int fiasco_write_stream (const char *filename, const fiasco_stream_info_t *info,
 			 const fb200_wfa_t *frames, int n_frames);
 
+/*
+ *  Predicted frames (reference: mv_t / delta_state of wfa_t, codec/wfa.h:62-71,126,137): what a
+ *  P frame's automaton carries beside the fields of fb200_wfa_t.  Arrays are [states][2]
+ *  (mv_*) and [states] (delta_state); frame_type 0 = intra (the pointers may be NULL), 1 =
+ *  predicted from the previous frame.
+ */
+typedef struct fiasco_frame_motion
+{
+   int		  frame_type;
+   const int8_t	 *mv_type;	/* 0 none, 1 forward */
+   const int8_t	 *mv_fx, *mv_fy;
+   const uint8_t *delta_state;	/* states that describe a prediction error */
+} fiasco_frame_motion_t;
+
+/*
+ *  fiasco_write_stream() for sequences with predicted frames: writes the motion tree and the
+ *  vectors (output/mc.c:75) and codes the weights of delta states in their own contexts
+ *  (output/weights.c:38).  motion == NULL: all frames intra.  The GPU path does not produce
+ *  predicted frames yet; this is the host half of that row, checked against
+ *  the reference's stream on automata of the test oracle.
+ */
+int fiasco_write_video_stream (const char *filename, const fiasco_stream_info_t *info,
+			       const fb200_wfa_t *frames, const fiasco_frame_motion_t *motion,
+			       int n_frames, unsigned search_range);
+
 #ifdef __cplusplus
 }
 #endif

@@ -229,6 +229,16 @@ def encode_video(frames, quality=20.0, pattern="ippp", p_min_level=6, p_max_leve
     return [{"_struct": out[i], "_shape": (h, w, 1), "states": out[i].states} for i in range(len(frames))], rec
 
 
+def struct_dict(st):
+    """numpy view of a ctypes automaton (the fields the stream writer takes)."""
+    n = st.states
+    d = {"states": n, "basis_states": st.basis_states, "root_state": st.root_state, "frame_type": st.frame_type}
+    for name in ("final_distribution", "level_of_state", "domain_type", "tree", "x", "y", "into", "weight",
+                 "y_state", "y_column", "mv_type", "mv_fx", "mv_fy", "delta_state"):
+        d[name] = np.ctypeslib.as_array(getattr(st, name))[:n].copy()
+    return d
+
+
 def struct_lines(st):
     """Canonical lines ('s', 'm', 'd', 'e' in the order of oracle/wfadump.c) of a ctypes automaton."""
     out = []

@@ -99,3 +99,21 @@ def test_cfiasco_links_unchanged():
     sy = subprocess.run(["nm", "-D", "--undefined-only", exe], capture_output=True, text=True).stdout
     for s in ("fiasco_coder", "fiasco_c_options_new", "fiasco_c_options_set_optimizations", "fiasco_calloc", "open_file"):
         assert s in sy
+
+
+@pytest.mark.parametrize("name", ["v160_q20_ippp", "v352_q30_ippip"])
+def test_video_stream_is_byte_identical_to_reference(name, tmp_path):
+    """Host half of the motion path: fiasco_write_video_stream() (frame types, the motion tree and
+    vectors of output/mc.c, delta contexts of output/weights.c) writes the reference coder's bytes
+    for sequences with predicted frames.  The automata come from the test oracle here -- the GPU
+    path does not produce predicted frames yet."""
+    import hashlib
+    m = O.manifest()[name]
+    frames = list(O.gen_frames.video(m["frames"], m["width"], m["height"]))
+    ws, _ = O.encode_video(frames, quality=m["quality"], pattern=m["pattern"])
+    p = ffi.make_params(m["width"], m["height"], 1, float(m["quality"]), 0)
+    out = str(tmp_path / "v.fco")
+    hostlib.write_video_stream(out, p, [O.struct_dict(w["_struct"]) for w in ws])
+    b = open(out, "rb").read()
+    assert len(b) == m["fco_bytes"]
+    assert hashlib.md5(b).hexdigest() == m["fco_md5"]
