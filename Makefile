@@ -18,7 +18,7 @@ product: $(LIBDIR)/libfiasco_b200.so $(LIBDIR)/libfiasco.so cfiasco
 
 # host side of libfiasco (plain C): options, PNM input, .fco writer, fiasco_coder()
 HOST     := fiasco_b200/host
-HOSTSRC  := messages host_util c_options pnm_input bitstream fco_writer coder_api
+HOSTSRC  := messages host_util c_options pnm_input bitstream fco_writer regenerate coder_api
 HOSTOBJ  := $(addprefix $(LIBDIR)/host_,$(addsuffix .o,$(HOSTSRC)))
 HCFLAGS  := -O2 -g -std=gnu11 -fPIC -Wall -Wno-unused-function -ffp-contract=off -Iinclude -I$(HOST)
 

@@ -1,0 +1,178 @@
+/*
+ *  regenerate.c -- the image an automaton describes, in the coder's pixel format.
+ *
+ *  A coder of sequences regenerates every frame it has coded: the result is the reference
+ *  of the next predicted frame (reference: codec/coder.c:642-651 -- decode_image,
+ *  codec/decoder.c:412-535 with alloc_state_images :878 and compute_state_images :1107;
+ *  restore_mc, codec/motion.c:37-230 with extract_mc_block :232).  Host side of the motion
+ *  path; integer arithmetic throughout, so it is exact by
+ *  construction: the reference adds two pixels per 32-bit int with one guard bit each,
+ *  which per pixel is a wrapping 16-bit addition of even numbers.
+ */
+#include <stdlib.h>
+#include <string.h>
+
+#include "fiasco_host.h"
+#include "fi_internal.h"
+
+#define W_OF(l) (1u << ((l) >> 1))
+#define H_OF(l) (1u << (((l) + 1) >> 1))
+
+typedef struct regen
+{
+   const fb200_wfa_t *w;
+   int16_t	    **pix;	/* [states * (max_level + 1)] image of a state at a level */
+   unsigned	      levels;
+} regen_t;
+
+static const int16_t *
+state_image (regen_t *r, unsigned state, unsigned level)
+{
+   const fb200_wfa_t *w	   = r->w;
+   int16_t	    **slot = &r->pix [(size_t) state * r->levels + level];
+
+   if (*slot)
+      return *slot;
+   int16_t *img = fiasco_calloc ((size_t) 1 << level, sizeof (int16_t));
+
+   *slot = img;
+   if (level == 0)			/* decoder.c:1128-1130 */
+   {
+      img [0] = (int16_t) ((int) (w->final_distribution [state] * 8 + .5) * 2);
+      return img;
+   }
+   const unsigned width = W_OF (level - 1), height = H_OF (level - 1), stride = W_OF (level);
+
+   for (unsigned label = 0; label < 2; label++)
+   {
+      /* odd levels split into an upper and a lower half, even ones into left and right */
+      int16_t  *range = (level & 1) ? img + label * height * stride : img + label * width;
+      const int child = w->tree [2 * state + label];
+
+      if (child >= 0)
+      {
+	 const int16_t *src = state_image (r, (unsigned) child, level - 1);
+
+	 for (unsigned y = 0; y < height; y++)
+	    memcpy (range + y * stride, src + y * width, width * sizeof (int16_t));
+      }
+      for (unsigned e = 0; w->into [(2 * state + label) * 6 + e] >= 0; e++)
+      {
+	 const int   domain = w->into [(2 * state + label) * 6 + e];
+	 const float weight = w->weight [(2 * state + label) * 6 + e];
+
+	 if (domain != 0)
+	 {
+	    const int16_t *src = state_image (r, (unsigned) domain, level - 1);
+	    const int	   iw  = (int16_t) (weight * 512 + 0.5);	/* wfalib.c:273 */
+
+	    for (unsigned y = 0; y < height; y++)
+	       for (unsigned x = 0; x < width; x++)
+		  range [y * stride + x]
+		     = (int16_t) (range [y * stride + x] + (((iw * (int) src [y * width + x]) >> 10) << 1));
+	 }
+	 else			/* the constant state: one value for the whole range */
+	 {
+	    const int c = (int) (weight * w->final_distribution [0] * 8 + .5) * 2;
+
+	    for (unsigned y = 0; y < height; y++)
+	       for (unsigned x = 0; x < width; x++)
+		  range [y * stride + x] = (int16_t) (range [y * stride + x] + c);
+	 }
+      }
+   }
+   return img;
+}
+
+int
+fiasco_regenerate_frame (const fb200_wfa_t *w, const fiasco_frame_motion_t *motion,
+			 int width, int height, const int16_t *past, int16_t *out)
+{
+   fi_try
+   {
+      regen_t  r;
+      unsigned max_level = 0, aw = 0, ah = 0, state;
+
+      if (!w || !out || width < 1 || height < 1 || w->status != FB200_OK)
+      {
+	 fi_set_error ("fiasco_regenerate_frame: bad arguments");
+	 return 0;
+      }
+      if (motion && motion->frame_type != 0 && (motion->frame_type != 1 || !past))
+      {
+	 fi_set_error ("fiasco_regenerate_frame: only P frames with a previous frame");
+	 return 0;
+      }
+      /* highest level of a linear combination; the size the bintree covers (decoder.c:449-461,
+	 843-875) */
+      for (state = w->basis_states; state < w->states; state++)
+	 if (w->into [(2 * state) * 6] >= 0 || w->into [(2 * state + 1) * 6] >= 0)
+	 {
+	    const unsigned l = w->level_of_state [state];
+
+	    if (l > max_level)
+	       max_level = l;
+	    if (w->x [2 * state] + W_OF (l) > aw)
+	       aw = w->x [2 * state] + W_OF (l);
+	    if (w->y [2 * state] + H_OF (l) > ah)
+	       ah = w->y [2 * state] + H_OF (l);
+	 }
+      aw += aw & 1;
+      ah += ah & 1;
+      if (aw < (unsigned) width)
+	 aw = (unsigned) width;
+      if (ah < (unsigned) height)
+	 ah = (unsigned) height;
+      r.w      = w;
+      r.levels = max_level + 1;
+      r.pix    = fiasco_calloc ((size_t) w->states * r.levels, sizeof (int16_t *));
+
+      int16_t *frame = fiasco_calloc ((size_t) aw * ah, sizeof (int16_t));
+
+      /* every state of level max_level is one block of the frame (decoder.c:913-937) */
+      for (state = w->basis_states; state < w->states; state++)
+	 if (w->level_of_state [state] == max_level)
+	 {
+	    const unsigned bw = W_OF (max_level), bh = H_OF (max_level);
+	    const unsigned x0 = w->x [2 * state], y0 = w->y [2 * state];
+	    const unsigned cw = x0 >= aw ? 0 : (aw - x0 < bw ? aw - x0 : bw);
+	    const int16_t *img = state_image (&r, state, max_level);
+
+	    for (unsigned y = 0; y < bh && y0 + y < ah; y++)
+	       memcpy (frame + (size_t) (y0 + y) * aw + x0, img + y * bw, cw * sizeof (int16_t));
+	 }
+      for (int y = 0; y < height; y++)
+	 memcpy (out + (size_t) y * width, frame + (size_t) y * aw, (size_t) width * sizeof (int16_t));
+      free (frame);
+      for (size_t i = 0; i < (size_t) w->states * r.levels; i++)
+	 free (r.pix [i]);
+      free (r.pix);
+
+      /* restore_mc (motion.c:37-108), forward prediction with full-pixel vectors: add the
+	 displaced block of the previous frame */
+      if (motion && motion->frame_type == 1)
+	 for (state = w->basis_states; state <= w->root_state; state++)
+	    for (unsigned label = 0; label < 2; label++)
+	       if (motion->mv_type [2 * state + label] == 1)
+	       {
+		  const unsigned level = (unsigned) w->level_of_state [state] - 1;
+		  const unsigned bw = W_OF (level), bh = H_OF (level);
+		  const int	 x0 = w->x [2 * state + label], y0 = w->y [2 * state + label];
+		  const int	 mx = motion->mv_fx [2 * state + label];
+		  const int	 my = motion->mv_fy [2 * state + label];
+
+		  for (unsigned y = 0; y < bh; y++)
+		     for (unsigned x = 0; x < bw; x++)
+		     {
+			int16_t *o = out + (size_t) (y0 + (int) y) * width + x0 + (int) x;
+
+			*o = (int16_t) (*o + past [(size_t) (y0 + my + (int) y) * width + x0 + mx + (int) x]);
+		     }
+	       }
+      return 1;
+   }
+   fi_catch
+   {
+      return 0;
+   }
+}

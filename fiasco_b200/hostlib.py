@@ -39,6 +39,8 @@ def load():
         L.fiasco_write_stream.argtypes = [C.c_char_p, C.POINTER(StreamInfo), C.POINTER(ffi._Wfa), C.c_int]
         L.fiasco_write_video_stream.argtypes = [C.c_char_p, C.POINTER(StreamInfo), C.POINTER(ffi._Wfa),
                                                 C.POINTER(FrameMotion), C.c_int, C.c_uint]
+        L.fiasco_regenerate_frame.argtypes = [C.POINTER(ffi._Wfa), C.POINTER(FrameMotion), C.c_int, C.c_int,
+                                              C.c_void_p, C.c_void_p]
         L.fiasco_coder.argtypes = [C.POINTER(C.c_char_p), C.c_char_p, C.c_float, C.c_void_p]
         L.fiasco_c_options_new.restype = C.c_void_p
         L.fiasco_c_options_delete.argtypes = [C.c_void_p]
@@ -114,6 +116,26 @@ def write_video_stream(path, params, wfas, p_min_level=6, p_max_level=10, search
                 setattr(mot[i], name, a.ctypes.data)
     if not L.fiasco_write_video_stream(path.encode(), C.byref(info), arr, mot, len(wfas), search_range):
         raise RuntimeError("fiasco_write_video_stream: " + error_message())
+
+
+def regenerate_frame(w, width, height, past=None):
+    """The grey frame an automaton describes, int16 (h, w) in the coder's pixel format
+    (fiasco_regenerate_frame); predicted frames ("frame_type" 1) need the previous regenerated frame."""
+    L = load()
+    s, keep = wfa_struct(w)
+    mot = FrameMotion()
+    mot.frame_type = int(w.get("frame_type", 0))
+    if mot.frame_type:
+        for name, dt in (("mv_type", np.int8), ("mv_fx", np.int8), ("mv_fy", np.int8), ("delta_state", np.uint8)):
+            a = np.ascontiguousarray(w[name], dtype=dt)
+            keep[name] = a
+            setattr(mot, name, a.ctypes.data)
+        past = np.ascontiguousarray(past, np.int16)
+    out = np.zeros((height, width), np.int16)
+    if not L.fiasco_regenerate_frame(C.byref(s), C.byref(mot), width, height,
+                                     past.ctypes.data if past is not None else None, out.ctypes.data):
+        raise RuntimeError("fiasco_regenerate_frame: " + error_message())
+    return out
 
 
 def cli_options(optimize=0):

@@ -67,6 +67,15 @@ int fiasco_write_video_stream (const char *filename, const fiasco_stream_info_t 
 			       const fb200_wfa_t *frames, const fiasco_frame_motion_t *motion,
 			       int n_frames, unsigned search_range);
 
+/*
+ *  Regenerate the grey frame an automaton describes, in the coder's pixel format (shorts, 12.4
+ *  fixed point), the way the reference coder does after every frame of a sequence (decode_image,
+ *  codec/decoder.c:412; restore_mc, codec/motion.c:37, when 'motion' says the frame is predicted
+ *  from 'past').  out / past: width * height shorts.  Returns 1 on success, 0 on failure.
+ */
+int fiasco_regenerate_frame (const fb200_wfa_t *wfa, const fiasco_frame_motion_t *motion,
+			     int width, int height, const int16_t *past, int16_t *out);
+
 #ifdef __cplusplus
 }
 #endif

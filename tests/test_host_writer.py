@@ -117,3 +117,23 @@ def test_video_stream_is_byte_identical_to_reference(name, tmp_path):
     b = open(out, "rb").read()
     assert len(b) == m["fco_bytes"]
     assert hashlib.md5(b).hexdigest() == m["fco_md5"]
+
+
+def test_host_regenerates_frames_like_the_reference():
+    """fiasco_regenerate_frame() (host side of the motion path: decode_image + restore_mc of the
+    reference, codec/decoder.c:412, codec/motion.c:37): intra and predicted frames of the golden
+    sequence and a ragged still, from the oracle's automata, equal the frames the reference coder
+    regenerated (md5 of the shorts, written by oracle/decdump.c)."""
+    m = O.manifest()["v160_q20_ippp"]
+    frames = list(O.gen_frames.video(m["frames"], m["width"], m["height"]))
+    ws, _ = O.encode_video(frames, quality=m["quality"], pattern=m["pattern"])
+    past = None
+    for f, w in enumerate(ws):
+        img = hostlib.regenerate_frame(O.struct_dict(w["_struct"]), m["width"], m["height"], past)
+        assert hashlib.md5(img.tobytes()).hexdigest() == m["decoded_md5"][f], "frame %d" % f
+        past = img
+    for name in ("g1024r_q20_z0", "g256_q20_z0"):
+        m = O.manifest()[name]
+        w = O.encode(O.case_image(name), quality=m["quality"], optimize=m["optimize"])
+        img = hostlib.regenerate_frame(O.struct_dict(w["_struct"]), m["width"], m["height"])
+        assert hashlib.md5(img.tobytes()).hexdigest() == m["decoded_md5"], name
