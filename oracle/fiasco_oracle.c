@@ -1852,6 +1852,137 @@ mc_prediction (float max_costs, float price, unsigned band, int y_state, range_t
    return costs;
 }
 
+/*
+ *  Design check for the device: with holes_mode set, predict_range keeps
+ *  the split alternative's states where they are instead of moving them aside -- the
+ *  prediction alternative builds its states behind them; a lost prediction drops its own
+ *  states, a won one leaves the split's states as dead holes that fo_close_holes() removes
+ *  at the end by a monotone renumbering.  The result must equal the reference's.
+ */
+static int holes_mode = 0;
+
+void
+fo_set_holes_mode (int on)
+{
+   holes_mode = on;
+}
+
+static float
+predict_range_holes (float max_costs, float price, range_t *range, coder_t *c, unsigned band,
+		     int y_state, unsigned states, const tree_model_t *tree_model,
+		     const tree_model_t *p_tree_model, const rle_model_t *domain_model,
+		     const rle_model_t *d_domain_model, const aac_model_t *coeff_model,
+		     const aac_model_t *d_coeff_model)
+{
+   fo_wfa_t	*w = c->wfa;
+   rle_model_t	*rec_domain_model   = malloc (sizeof (rle_model_t));
+   rle_model_t	*rec_d_domain_model = malloc (sizeof (rle_model_t));
+   aac_model_t	 rec_coeff_model    = c->coeff.model;
+   aac_model_t	 rec_d_coeff_model  = c->d_coeff.model;
+   tree_model_t	 rec_tree_model	    = c->tree;
+   tree_model_t	 rec_p_tree_model   = c->p_tree;
+   const unsigned rec_states	    = w->states;
+   uint8_t	*rec_domain_type    = malloc (rec_states - states + 1);
+   float	 costs;
+
+   rle_copy (rec_domain_model, &c->pool);
+   rle_copy (rec_d_domain_model, &c->d_pool);
+   /* hide the split's states: nobody may use them as domains or needs their images */
+   for (unsigned s2 = states; s2 < rec_states; s2++)
+   {
+      rec_domain_type [s2 - states] = w->domain_type [s2];
+      w->domain_type [s2]	    = 0;
+   }
+   c->tree	    = *tree_model;
+   c->p_tree	    = *p_tree_model;
+   rle_copy (&c->pool, domain_model);
+   rle_copy (&c->d_pool, d_domain_model);
+   c->coeff.model   = *coeff_model;
+   c->d_coeff.model = *d_coeff_model;
+
+   costs = mc_prediction (max_costs, price, band, y_state, range, c);
+
+   if (costs < MAXCOSTS)
+   {
+      /* the split's states stay behind as holes: inert, never referenced */
+      for (unsigned s2 = states; s2 < rec_states; s2++)
+	 for (unsigned label = 0; label < MAXLABELS; label++)
+	 {
+	    w->into [s2][label][0] = NO_EDGE;
+	    w->tree [s2][label]	   = RANGE;
+	    w->mv_type [s2][label] = 0;
+	    w->level_of_state [s2] = 255;	/* marks a hole for fo_close_holes */
+	 }
+      costs = (range->tree_bits + range->matrix_bits + range->weights_bits
+	       + range->mv_tree_bits + range->mv_coord_bits + range->nd_tree_bits
+	       + range->nd_weights_bits) * price + range->err;
+   }
+   else
+   {
+      rle_copy (&c->pool, rec_domain_model);
+      rle_copy (&c->d_pool, rec_d_domain_model);
+      c->coeff.model   = rec_coeff_model;
+      c->d_coeff.model = rec_d_coeff_model;
+      c->tree	       = rec_tree_model;
+      c->p_tree	       = rec_p_tree_model;
+      range->prediction = 0;
+      if (w->states != rec_states)
+	 remove_states (rec_states, w);
+      for (unsigned s2 = states; s2 < rec_states; s2++)
+	 w->domain_type [s2] = rec_domain_type [s2 - states];
+      costs = MAXCOSTS;
+   }
+   free (rec_domain_model);
+   free (rec_d_domain_model);
+   free (rec_domain_type);
+   return costs;
+}
+
+/* renumber the live states of a holes-mode automaton consecutively (what the host would do) */
+void
+fo_close_holes (fo_wfa_t *w)
+{
+   static int16_t map [MAXSTATES];
+   unsigned	  n = 0;
+
+   for (unsigned s2 = 0; s2 < w->states; s2++)
+      map [s2] = (s2 >= w->basis_states && w->level_of_state [s2] == 255) ? (int16_t) -1 : (int16_t) n++;
+   for (unsigned s2 = 0; s2 < w->states; s2++)
+   {
+      const int t = map [s2];
+
+      if (t < 0 || (unsigned) t == s2)
+	 continue;
+      w->final_distribution [t] = w->final_distribution [s2];
+      w->level_of_state [t]	= w->level_of_state [s2];
+      w->domain_type [t]	= w->domain_type [s2];
+      w->delta_state [t]	= w->delta_state [s2];
+      for (unsigned label = 0; label < MAXLABELS; label++)
+      {
+	 w->tree [t][label]	= w->tree [s2][label];
+	 w->x [t][label]	= w->x [s2][label];
+	 w->y [t][label]	= w->y [s2][label];
+	 w->y_state [t][label]	= w->y_state [s2][label];
+	 w->y_column [t][label] = w->y_column [s2][label];
+	 w->mv_type [t][label]	= w->mv_type [s2][label];
+	 w->mv_fx [t][label]	= w->mv_fx [s2][label];
+	 w->mv_fy [t][label]	= w->mv_fy [s2][label];
+	 memcpy (w->into [t][label], w->into [s2][label], sizeof w->into [t][label]);
+	 memcpy (w->weight [t][label], w->weight [s2][label], sizeof w->weight [t][label]);
+      }
+   }
+   for (unsigned s2 = 0; s2 < n; s2++)
+      for (unsigned label = 0; label < MAXLABELS; label++)
+      {
+	 if (w->tree [s2][label] != RANGE)
+	    w->tree [s2][label] = map [w->tree [s2][label]];
+	 for (unsigned e = 0; w->into [s2][label][e] != NO_EDGE; e++)
+	    w->into [s2][label][e] = map [w->into [s2][label][e]];
+      }
+   w->root_state = (unsigned) map [w->root_state];
+   w->states	 = n;
+}
+
 /* predict_range (prediction.c:96-191), P frames */
 static float
 predict_range (float max_costs, float price, range_t *range, coder_t *c, unsigned band,
@@ -1871,6 +2002,14 @@ predict_range (float max_costs, float price, range_t *range, coder_t *c, unsigne
    state_data_t *rec_state_data;
    float	 costs;
 
+   if (holes_mode)
+   {
+      free (rec_domain_model);
+      free (rec_d_domain_model);
+      return predict_range_holes (max_costs, price, range, c, band, y_state, states, tree_model,
+				  p_tree_model, domain_model, d_domain_model, coeff_model,
+				  d_coeff_model);
+   }
    rle_copy (rec_domain_model, &c->pool);
    rle_copy (rec_d_domain_model, &c->d_pool);
    rec_state_data = store_state_data (states, rec_states - 1, c);

@@ -149,6 +149,10 @@ int fo_encode_video (const fo_params_t *p, int n_frames, const int16_t *const *f
 		     const char *pattern, int p_min_level, int p_max_level, int search_range,
 		     fo_wfa_t *out, int16_t *reconst, char *errbuf, size_t errlen);
 
+/* design check of the device's state handling for predicted frames (see fiasco_oracle.c) */
+void fo_set_holes_mode (int on);
+void fo_close_holes (fo_wfa_t *wfa);
+
 /* canonical text dump, same grammar as oracle/wfadump.c ("s"/"e" lines of one frame) */
 void fo_dump_wfa (const fo_wfa_t *wfa, const fo_params_t *p, FILE *f);
 
