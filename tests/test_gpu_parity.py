@@ -306,3 +306,45 @@ def test_gpu_random_crops_match_oracle():
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "60 cases, 0 mismatches" in r.stdout
+
+
+def test_gpu_config3_colour_2048_all_tiles():
+    """BASELINE config 3 at full size: 2048^2 colour (4:4:4), q = 30, 64 independent 256^2 tiles in ONE
+    launch: tile 0 is the reference's golden automaton, sampled tiles equal the oracle, every tile
+    is a complete automaton (three bands under two virtual roots)."""
+    img = gen_frames.frame("c2048")
+    crops = gen_frames.crops(img, 256)
+    assert len(crops) == 64
+    p = ffi.make_params(256, 256, 3, 30.0, 0)
+    enc = F.TileEncoder(p, 64)
+    try:
+        planes = [pl for c in crops for pl in O.planes_of(c)]
+        ws, _ = enc.encode(planes)
+    finally:
+        enc.close()
+    level = O.lib().fo_image_level(256, 256)
+    assert O.mask_virtual(F.wfa_lines(ws[0]), level) == O.golden_wfa_lines("c2048t0_q30_z0")
+    for k in (7, 36, 63):
+        ow = O.encode(crops[k], quality=30, optimize=0)
+        assert ws[k]["states"] == ow["states"]
+        assert O.mask_virtual(F.wfa_lines(ws[k]), level) == O.mask_virtual(O.wfa_lines(ow), level), "tile %d" % k
+    for w in ws:
+        assert int(w["level_of_state"][w["root_state"]]) == level + 2
+
+
+def test_gpu_config4_grey_4096_all_tiles():
+    """BASELINE config 4 at full size: 4096^2 grey, q = 20, 64 independent 512^2 tiles in one launch."""
+    img = gen_frames.frame("g4096")
+    crops = gen_frames.crops(img, 512)
+    assert len(crops) == 64
+    p = ffi.make_params(512, 512, 1, 20.0, 0)
+    enc = F.TileEncoder(p, 64)
+    try:
+        ws, _ = enc.encode([O.planes_of(c)[0] for c in crops])
+    finally:
+        enc.close()
+    assert F.wfa_lines(ws[0]) == O.golden_wfa_lines("g4096t0_q20_z0")
+    for k in (21, 63):
+        assert_same_wfa(ws[k], O.encode(crops[k], quality=20, optimize=0))
+    for w in ws:
+        assert int(w["level_of_state"][w["root_state"]]) == 18
