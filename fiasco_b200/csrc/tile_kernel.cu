@@ -533,24 +533,19 @@ upsweep_nodes (float *T, unsigned scap, unsigned node, unsigned s, const TransRe
    }
 }
 
-/* block-wide copy of n floats with four independent loads in flight per thread */
+/*
+ *  Block-wide asynchronous copy of nfloats (a multiple of 4) floats from global to shared
+ *  memory, both 16-byte aligned: cp.async moves 16 bytes per instruction past the register
+ *  file and leaves the thread free to issue the next one; the caller commits and waits.
+ */
 template <int NT>
 __device__ __forceinline__ void
-cta_copy_f32 (float *dst, const float *src, unsigned n)
+cta_copy_f32_async (float *dst_smem, const float *src, unsigned nfloats)
 {
-   for (unsigned t = threadIdx.x; t < n; t += 4 * NT)
-   {
-      /* the last round is predicated, not serialised: its loads travel together too */
-      float v [4];
+   const unsigned saddr = (unsigned) __cvta_generic_to_shared (dst_smem);
 
-#pragma unroll
-      for (int u = 0; u < 4; u++)
-	 v [u] = t + u * NT < n ? src [t + u * NT] : 0.0f;
-#pragma unroll
-      for (int u = 0; u < 4; u++)
-	 if (t + u * NT < n)
-	    dst [t + u * NT] = v [u];
-   }
+   for (unsigned i = threadIdx.x; i < (nfloats >> 2); i += NT)
+      asm volatile ("cp.async.cg.shared.global [%0], [%1], 16;" :: "r" (saddr + i * 16), "l" (src + i * 4) : "memory");
 }
 
 /*
@@ -1019,8 +1014,11 @@ cta_state_products (const DevParams &P, const TileWs &W, const Sh &sh, unsigned 
       {
 	 float	     *row = sh.num + (size_t) j * stride;
 	 const float *src = GP (W.SS) + ((size_t) (li - 1) * P.s_cap + h->ap_src [j]) * P.s_cap;
-	 cta_copy_f32<NT> (row, src, s + 1);
+	 /* rows are 16-byte aligned at both ends; the padded length stays inside the table row */
+	 cta_copy_f32_async<NT> (row, src, (unsigned) stride);
       }
+      asm volatile ("cp.async.commit_group;" ::: "memory");
+      asm volatile ("cp.async.wait_group 0;" ::: "memory");
       __syncthreads ();
       for (unsigned t = tid; t <= s; t += NT)
       {
