@@ -548,6 +548,22 @@ cta_copy_f32_async (float *dst_smem, const float *src, unsigned nfloats)
       asm volatile ("cp.async.cg.shared.global [%0], [%1], 16;" :: "r" (saddr + i * 16), "l" (src + i * 4) : "memory");
 }
 
+/* one float from global to shared memory, asynchronously (a gather that costs no register
+   and does not make the thread wait: all gathers of a thread are in flight together) */
+__device__ __forceinline__ void
+gather_f32_async (float *dst_smem, const float *src)
+{
+   asm volatile ("cp.async.ca.shared.global [%0], [%1], 4;"
+		 :: "r" ((unsigned) __cvta_generic_to_shared (dst_smem)), "l" (src) : "memory");
+}
+
+__device__ __forceinline__ void
+async_wait_all (void)
+{
+   asm volatile ("cp.async.commit_group;" ::: "memory");
+   asm volatile ("cp.async.wait_group 0;" ::: "memory");
+}
+
 /*
  *  Fill T[node][s] for the nodes of the subtree rooted at (node_root, level_root) of the
  *  current lc_max block and every state s >= from whose image is needed.
@@ -1637,41 +1653,27 @@ cta_matching_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &
    const float fsize = (float) (1 << level);
 
    /* ---- numerators / denominators (approx.c:358-374) ---- */
-   for (int d0 = tid; d0 < D; d0 += 4 * NT)
+   /* every thread's gathers are in flight together (cp.async, 4 bytes each), then the tests
+      run on the thread's own entries */
+   for (int d = tid; d < D; d += NT)
    {
-      /* four domains per round: all eight gathers are issued up front (one L2 round
-	 trip); a numerator that belongs to an unusable domain is never looked at */
-      float dn [4], nm [4];
+      const int st = dom_state (sh, w, d);
 
-#pragma unroll
-      for (int u = 0; u < 4; u++)
-      {
-	 const int d  = d0 + u * NT;
-	 const int st = d < D ? dom_state (sh, w, d) : 0;
+      gather_f32_async (sh.den + d, GP (W.diag) + (size_t) li * P.s_cap + st);
+      gather_f32_async (sh.num + d, GP (W.T) + (size_t) image * P.s_cap + st);
+   }
+   async_wait_all ();
+   for (int d = tid; d < D; d += NT)
+   {
+      unsigned char used = 0;
 
-	 dn [u] = GP (W.diag) [(size_t) li * P.s_cap + st];
-	 nm [u] = GP (W.T) [(size_t) image * P.s_cap + st];
-      }
-#pragma unroll
-      for (int u = 0; u < 4; u++)
-      {
-	 const int d = d0 + u * NT;
-
-	 if (d < D)
-	 {
-	    unsigned char used = 0;
-
-	    if (dn [u] / fsize < min_norm)
-	       used = 1;
-	    else if (fabsf (nm [u]) < min_norm)
-	       used = 1;
-	    if (d == excluded)
-	       used = 1;
-	    sh.num [d]	= nm [u];
-	    sh.den [d]	= dn [u];
-	    sh.used [d] = used;
-	 }
-      }
+      if (sh.den [d] / fsize < min_norm)
+	 used = 1;
+      else if (fabsf (sh.num [d]) < min_norm)
+	 used = 1;
+      if (d == excluded)
+	 used = 1;
+      sh.used [d] = used;
    }
    __syncthreads ();
    if (tid == 0)
@@ -1737,10 +1739,15 @@ cta_matching_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &
 	 const float Nn	  = w.N [n], Bn = w.B [n];
 	 const float *row = GP (W.SS) + ((size_t) li * P.s_cap + sidx) * P.s_cap;
 
+	 /* the row entries of the thread's domains travel together into the (idle) bound array */
+	 for (int d = tid; d < D; d += NT)
+	    if (!sh.used [d])
+	       gather_f32_async (sh.bnd + d, row + dom_state (sh, w, d));
+	 async_wait_all ();
 	 for (int d = tid; d < D; d += NT)
 	    if (!sh.used [d])
 	    {
-	       float tmp = row [dom_state (sh, w, d)];
+	       float tmp = sh.bnd [d];
 
 #pragma unroll 1
 	       for (int k = 0; k < n; k++)
