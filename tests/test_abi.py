@@ -93,3 +93,22 @@ def test_product_does_not_reference_oracle():
                     if re.search(r"fiasco_oracle|oracle_lib|liboracle|oracle/", txt):
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the reference's own CPU coder, all host cores, no GPU): one JSON line
+    with the keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.exists(os.path.join(root, "oracle", "_ref", "cfiasco")):
+        pytest.skip("reference binary not built here")
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "Mpixels/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] in ("reference", "port")
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["metric"].startswith("encoder Mpixels/s")
