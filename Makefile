@@ -9,7 +9,7 @@ NVFLAGS  := $(ARCH) -O3 -lineinfo -fmad=false -prec-div=true -prec-sqrt=true -ft
             -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function -Iinclude -Ifiasco_b200/csrc
 LIBDIR   := fiasco_b200/lib
 CSRC     := fiasco_b200/csrc
-KOBJ     := $(LIBDIR)/tile_kernel.o $(LIBDIR)/ffi.o
+KOBJ     := $(LIBDIR)/tile_kernel.o $(LIBDIR)/ffi.o $(LIBDIR)/motion_kernel.o
 
 .PHONY: all product oracle clean ptxas
 all: product oracle

@@ -94,6 +94,7 @@ def load():
     lib.fb200_get_stats.restype = None
     lib.fb200_resident_tiles.argtypes = [vp]
     lib.fb200_state_capacity.argtypes = [vp]
+    lib.fb200_motion_norms.argtypes = [ip, vp, vp, ip, ip, ip, ip, vp, C.POINTER(C.c_float), cp, C.c_size_t]
     lib.fb200_probe.argtypes = [ip, ip, vp, vp, vp, vp, vp, vp, cp, C.c_size_t]
     _LIB = lib
     return lib
@@ -241,6 +242,21 @@ class TileEncoder:
         d = {k: getattr(s, k) for k, _ in Stats._fields_}
         d["lap"] = list(s.lap)
         return d
+
+
+def motion_norms(orig, past, level=6, search_range=16, device=0):
+    """Norms tables of the motion search for all blocks of `level` (fb200_motion_norms): orig / past int16
+    (h, w) in the coder's pixel format.  Returns (float32 [block rows][block columns][(2 sr)^2], kernel ms)."""
+    orig = np.ascontiguousarray(orig, np.int16)
+    past = np.ascontiguousarray(past, np.int16)
+    h, w = orig.shape
+    bw, bh = 1 << (level >> 1), 1 << ((level + 1) >> 1)
+    out = np.zeros(((h + bh - 1) // bh, (w + bw - 1) // bw, 4 * search_range * search_range), np.float32)
+    ms = C.c_float(0)
+    err = C.create_string_buffer(512)
+    _check(load().fb200_motion_norms(device, orig.ctypes.data, past.ctypes.data, w, h, level, search_range,
+                                     out.ctypes.data, C.byref(ms), err, 512), err)
+    return out, ms.value
 
 
 def probe(kind, f=None, a=None, b=None, c=None):

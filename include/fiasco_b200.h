@@ -190,6 +190,21 @@ void fb200_wfa_free (fb200_wfa_t *wfa);
 int fb200_probe (int kind, int n, const float *f, const int *a, const int *b,
 		 const int *c, int *out_i, float *out_f, char *err, size_t errlen);
 
+/*
+ *  Norms tables of the motion search for a predicted frame (replaces the lazy, per-block
+ *  fill_norms_table() of the reference, codec/mwfa.c:544-602, by one launch over all blocks): for
+ *  every block of bintree level 'level' that lies completely inside the frame and every
+ *  displacement (mx, my) in [-search_range, search_range)^2 the squared norm of
+ *  (original - reference displaced by (mx, my)) / 16, bit-identical to the reference's sums.
+ *  orig / past: width * height shorts (the coder's pixel format, host memory).  norms (host):
+ *  [rows of blocks][columns of blocks][(my + sr) * 2 sr + (mx + sr)], 0 for blocks or
+ *  displacements that leave the frame.  kernel_ms (or NULL): device time of the kernel.  Building
+ *  block of the motion path; the tile kernel does not consume it yet.
+ */
+int fb200_motion_norms (int device, const int16_t *orig, const int16_t *past, int width,
+			int height, int level, int search_range, float *norms, float *kernel_ms,
+			char *err, size_t errlen);
+
 const char *fb200_version (void);
 
 #ifdef __cplusplus

@@ -3145,3 +3145,21 @@ cleanup:
    free (cur);
    return rc;
 }
+
+/* fill_norms_table (mwfa.c:544-602) for one block, exported for the parity test of the
+   device's norms kernel */
+void
+fo_fill_norms_table (const int16_t *orig, const int16_t *past, unsigned width, unsigned height,
+		     unsigned x0, unsigned y0, unsigned level, unsigned search_range, float *out)
+{
+   coder_t *c = calloc (1, sizeof (coder_t));
+
+   c->planes [0]	       = orig;
+   c->past		       = past;
+   c->opt.width		       = (int) width;
+   c->opt.height	       = (int) height;
+   c->search_range	       = search_range;
+   c->mc_forward_norms [level] = out;
+   fill_norms_table (x0, y0, level, c);
+   free (c);
+}

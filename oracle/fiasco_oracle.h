@@ -149,6 +149,11 @@ int fo_encode_video (const fo_params_t *p, int n_frames, const int16_t *const *f
 		     const char *pattern, int p_min_level, int p_max_level, int search_range,
 		     fo_wfa_t *out, int16_t *reconst, char *errbuf, size_t errlen);
 
+/* fill_norms_table (codec/mwfa.c:544-602) for the block at (x0, y0) of bintree level 'level':
+   out [(my + sr) * 2 sr + (mx + sr)] */
+void fo_fill_norms_table (const int16_t *orig, const int16_t *past, unsigned width, unsigned height,
+			  unsigned x0, unsigned y0, unsigned level, unsigned search_range, float *out);
+
 /* design check of the device's state handling for predicted frames (see fiasco_oracle.c) */
 void fo_set_holes_mode (int on);
 void fo_close_holes (fo_wfa_t *wfa);

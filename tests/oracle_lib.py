@@ -91,6 +91,9 @@ def lib():
         L.fo_decode_image.argtypes = [C.POINTER(FoWfa), C.c_int, C.c_uint, C.c_uint, C.POINTER(C.c_void_p)]
         L.fo_encode_video.argtypes = [C.POINTER(FoParams), C.c_int, C.POINTER(C.c_void_p), C.c_char_p, C.c_int, C.c_int,
                                       C.c_int, C.POINTER(FoWfa), C.c_void_p, C.c_char_p, C.c_size_t]
+        L.fo_fill_norms_table.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint,
+                                          C.c_uint, C.c_void_p]
+        L.fo_fill_norms_table.restype = None
         L.fo_set_holes_mode.argtypes = [C.c_int]
         L.fo_set_holes_mode.restype = None
         L.fo_close_holes.argtypes = [C.POINTER(FoWfa)]

@@ -2,6 +2,7 @@
 oracle on the same seeded inputs, and against the golden vectors taken from the reference
 binary.  Integer / index work must be bit exact; the fp32 weights are quantised codes, so they
 are compared bit-for-bit as well (tolerance 0, stricter than the 1e-4 the north star allows)."""
+import os
 import struct
 
 import numpy as np
@@ -348,3 +349,36 @@ def test_gpu_config4_grey_4096_all_tiles():
         assert_same_wfa(ws[k], O.encode(crops[k], quality=20, optimize=0))
     for w in ws:
         assert int(w["level_of_state"][w["root_state"]]) == 18
+
+
+@pytest.mark.parametrize("level,sr", [(6, 16), (8, 16), (9, 8), (7, 5)])
+def test_gpu_motion_norms_match_reference_loops(level, sr):
+    """The norms tables of the motion search (fb200_motion_norms: all blocks of a frame in one launch)
+    against the oracle's restatement of the reference's per-block fill_norms_table (codec/mwfa.c:544),
+    bit for bit: frame 1 of the golden sequence against the REGENERATED frame 0, blocks in the
+    interior, on every border and partly outside."""
+    import gzip
+    m = O.manifest()["v160_q20_ippp"]
+    frames = list(gen_frames.video(2, m["width"], m["height"]))
+    orig = O.planes_of(frames[1])[0].reshape(m["height"], m["width"])
+    raw = np.frombuffer(gzip.open(os.path.join(O.GOLDEN, "v160_q20_ippp.decoded.raw.gz")).read(), np.int16)
+    past = raw.reshape(m["frames"], m["height"], m["width"])[0].copy()
+    got, ms = ffi.motion_norms(orig, past, level, sr)
+    bw, bh = 1 << (level >> 1), 1 << ((level + 1) >> 1)
+    L = O.lib()
+    ref = np.zeros(4 * sr * sr, np.float32)
+    nby, nbx = got.shape[:2]
+    assert (nby, nbx) == ((m["height"] + bh - 1) // bh, (m["width"] + bw - 1) // bw)
+    checked = 0
+    for by in range(nby):
+        for bx in range(nbx):
+            if bx * bw + bw > m["width"] or by * bh + bh > m["height"]:
+                assert not got[by, bx].any()
+                continue
+            if (bx + 3 * by) % 3 and 0 < bx < nbx - 2 and 0 < by < nby - 2:
+                continue                              # sample the interior, take every border block
+            L.fo_fill_norms_table(orig.ctypes.data, past.ctypes.data, m["width"], m["height"], bx * bw, by * bh,
+                                  level, sr, ref.ctypes.data)
+            assert np.array_equal(got[by, bx].view(np.uint32), ref.view(np.uint32)), (bx, by)
+            checked += 1
+    assert checked > 20 and ms > 0
