@@ -176,3 +176,86 @@ fiasco_regenerate_frame (const fb200_wfa_t *w, const fiasco_frame_motion_t *moti
       return 0;
    }
 }
+
+/*
+ *  Finish the automaton of a predicted frame as the device leaves it:
+ *  the states the losing split alternatives left behind are holes (level_of_state == 255);
+ *  close them by a monotone renumbering, then derive the delta flags from the structure
+ *  (reference: locate_delta_images, codec/wfalib.c:699-730, called at codec/coder.c:876).
+ *  Works in place on the automaton's arrays and the motion arrays; returns the new number
+ *  of states.
+ */
+int
+fiasco_finish_predicted_frame (fb200_wfa_t *w, int8_t *mv_type, int8_t *mv_fx, int8_t *mv_fy,
+			       uint8_t *delta_state)
+{
+   fi_try
+   {
+      if (!w || !mv_type || !mv_fx || !mv_fy || !delta_state || w->status != FB200_OK)
+      {
+	 fi_set_error ("fiasco_finish_predicted_frame: bad arguments");
+	 return 0;
+      }
+      int16_t *map = fiasco_calloc (w->states + 1, sizeof (int16_t));
+      unsigned n   = 0, s;
+
+      for (s = 0; s < w->states; s++)
+	 map [s] = (s >= w->basis_states && w->level_of_state [s] == 255) ? (int16_t) -1 : (int16_t) n++;
+      for (s = 0; s < w->states; s++)
+      {
+	 const int t = map [s];
+
+	 if (t < 0 || (unsigned) t == s)
+	    continue;
+	 w->final_distribution [t] = w->final_distribution [s];
+	 w->level_of_state [t]	   = w->level_of_state [s];
+	 w->domain_type [t]	   = w->domain_type [s];
+	 for (unsigned label = 0; label < 2; label++)
+	 {
+	    const unsigned a = 2 * (unsigned) t + label, b = 2 * s + label;
+
+	    w->tree [a]	    = w->tree [b];
+	    w->x [a]	    = w->x [b];
+	    w->y [a]	    = w->y [b];
+	    w->y_state [a]  = w->y_state [b];
+	    w->y_column [a] = w->y_column [b];
+	    mv_type [a]	    = mv_type [b];
+	    mv_fx [a]	    = mv_fx [b];
+	    mv_fy [a]	    = mv_fy [b];
+	    memcpy (w->into + a * 6, w->into + b * 6, 6 * sizeof (int16_t));
+	    memcpy (w->weight + a * 6, w->weight + b * 6, 6 * sizeof (float));
+	 }
+      }
+      for (s = 0; s < n; s++)
+	 for (unsigned label = 0; label < 2; label++)
+	 {
+	    const unsigned a = 2 * s + label;
+
+	    if (w->tree [a] >= 0)
+	       w->tree [a] = map [w->tree [a]];
+	    for (unsigned e = 0; w->into [a * 6 + e] >= 0; e++)
+	       w->into [a * 6 + e] = map [w->into [a * 6 + e]];
+	 }
+      w->root_state = (unsigned) map [w->root_state];
+      w->states	    = n;
+      free (map);
+
+      /* locate_delta_images: top down, a child is a delta state if its range is motion
+	 compensated, or has edges beside the child, or its parent is a delta state */
+      for (s = w->basis_states; s < n; s++)
+	 delta_state [s] = 0;
+      for (s = w->root_state + 1; s-- > w->basis_states; )
+	 for (unsigned label = 0; label < 2; label++)
+	 {
+	    const unsigned a = 2 * s + label;
+
+	    if (w->tree [a] >= 0 && (mv_type [a] != 0 || w->into [a * 6] >= 0 || delta_state [s]))
+	       delta_state [w->tree [a]] = 1;
+	 }
+      return (int) n;
+   }
+   fi_catch
+   {
+      return 0;
+   }
+}

@@ -41,6 +41,7 @@ def load():
                                                 C.POINTER(FrameMotion), C.c_int, C.c_uint]
         L.fiasco_regenerate_frame.argtypes = [C.POINTER(ffi._Wfa), C.POINTER(FrameMotion), C.c_int, C.c_int,
                                               C.c_void_p, C.c_void_p]
+        L.fiasco_finish_predicted_frame.argtypes = [C.POINTER(ffi._Wfa), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.fiasco_coder.argtypes = [C.POINTER(C.c_char_p), C.c_char_p, C.c_float, C.c_void_p]
         L.fiasco_c_options_new.restype = C.c_void_p
         L.fiasco_c_options_delete.argtypes = [C.c_void_p]
@@ -135,6 +136,24 @@ def regenerate_frame(w, width, height, past=None):
     if not L.fiasco_regenerate_frame(C.byref(s), C.byref(mot), width, height,
                                      past.ctypes.data if past is not None else None, out.ctypes.data):
         raise RuntimeError("fiasco_regenerate_frame: " + error_message())
+    return out
+
+
+def finish_predicted_frame(w):
+    """fiasco_finish_predicted_frame() on an automaton dict with holes (level_of_state 255): returns a new
+    dict with the holes closed and the delta flags derived from the structure."""
+    L = load()
+    w = {k: (np.array(v, copy=True) if isinstance(v, np.ndarray) else v) for k, v in w.items()}
+    s, keep = wfa_struct(w)
+    extra = {name: np.ascontiguousarray(w[name], dtype=dt)
+             for name, dt in (("mv_type", np.int8), ("mv_fx", np.int8), ("mv_fy", np.int8), ("delta_state", np.uint8))}
+    n = L.fiasco_finish_predicted_frame(C.byref(s), extra["mv_type"].ctypes.data, extra["mv_fx"].ctypes.data,
+                                        extra["mv_fy"].ctypes.data, extra["delta_state"].ctypes.data)
+    if not n:
+        raise RuntimeError("fiasco_finish_predicted_frame: " + error_message())
+    out = {"states": n, "basis_states": s.basis_states, "root_state": s.root_state, "frame_type": w.get("frame_type", 0)}
+    for name, a in list(keep.items()) + list(extra.items()):
+        out[name] = a[:n]
     return out
 
 

@@ -76,6 +76,16 @@ int fiasco_write_video_stream (const char *filename, const fiasco_stream_info_t 
 int fiasco_regenerate_frame (const fb200_wfa_t *wfa, const fiasco_frame_motion_t *motion,
 			     int width, int height, const int16_t *past, int16_t *out);
 
+/*
+ *  Finish the automaton of a predicted frame the way the device will leave it:
+ *  close the holes of losing split alternatives (states marked level_of_state == 255) by a monotone
+ *  renumbering and derive the delta flags from the structure (locate_delta_images,
+ *  codec/wfalib.c:699, called at codec/coder.c:876).  In place; mv_* are [states][2], delta_state
+ *  [states].  Returns the new number of states, 0 on failure.
+ */
+int fiasco_finish_predicted_frame (fb200_wfa_t *wfa, int8_t *mv_type, int8_t *mv_fx, int8_t *mv_fy,
+				   uint8_t *delta_state);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,6 +7,8 @@ import hashlib
 import os
 import re
 
+import numpy as np
+
 import pytest
 
 from fiasco_b200 import ffi, hostlib
@@ -137,3 +139,32 @@ def test_host_regenerates_frames_like_the_reference():
         w = O.encode(O.case_image(name), quality=m["quality"], optimize=m["optimize"])
         img = hostlib.regenerate_frame(O.struct_dict(w["_struct"]), m["width"], m["height"])
         assert hashlib.md5(img.tobytes()).hexdigest() == m["decoded_md5"], name
+
+
+def test_host_finishes_predicted_frames_with_holes():
+    """The automaton of a predicted frame as the device will leave it (states of losing split
+    alternatives left as holes, delta flags not set): fiasco_finish_predicted_frame() closes the
+    holes and derives the flags; the stream written from the result is the reference's, byte for byte."""
+    name = "v352_q30_ippip"
+    m = O.manifest()[name]
+    frames = list(O.gen_frames.video(m["frames"], m["width"], m["height"]))
+    L = O.lib()
+    L.fo_set_holes_mode(1)
+    try:
+        ws, _ = O.encode_video(frames, quality=m["quality"], pattern=m["pattern"])
+    finally:
+        L.fo_set_holes_mode(0)
+    done, holes = [], 0
+    for w in ws:
+        d = O.struct_dict(w["_struct"])
+        d["delta_state"] = np.zeros_like(d["delta_state"])          # the host has to find them itself
+        f = hostlib.finish_predicted_frame(d)
+        holes += d["states"] - f["states"]
+        done.append(f)
+    assert holes > 100
+    p = ffi.make_params(m["width"], m["height"], 1, float(m["quality"]), 0)
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        out = os.path.join(tmp, "v.fco")
+        hostlib.write_video_stream(out, p, done)
+        assert hashlib.md5(open(out, "rb").read()).hexdigest() == m["fco_md5"]
