@@ -1775,6 +1775,9 @@ mc_prediction (float max_costs, float price, unsigned band, int y_state, range_t
       prange.mv_type	  = 1;	/* FORWARD */
       find_best_mv (price, prange.x, prange.y, width, height, &prange.mv_coord_bits,
 		    &prange.mv_fx, &prange.mv_fy, c->mc_forward_norms [prange.level], c);
+      if (c->trace)
+	 fprintf (c->trace, "mv %u %u %u %d %d %08x\n", prange.level, prange.x, prange.y,
+		  prange.mv_fx, prange.mv_fy, fbits (prange.mv_coord_bits));
       extract_mc_block (mcblock, width, height, c->past, (unsigned) c->opt.width, 0,
 			prange.x, prange.y, prange.mv_fx, prange.mv_fy);
       for (unsigned y = 0; y < height; y++)	/* get_mcpe (mwfa.c:604-649) */
@@ -1932,6 +1935,9 @@ predict_range_holes (float max_costs, float price, range_t *range, coder_t *c, u
 	 w->domain_type [s2] = rec_domain_type [s2 - states];
       costs = MAXCOSTS;
    }
+   if (c->trace)
+      fprintf (c->trace, "pr %u %u %u %u %u %08x %08x %u\n", range->level, range->x, range->y, states,
+	       rec_states, fbits (max_costs), fbits (costs), w->states);
    free (rec_domain_model);
    free (rec_d_domain_model);
    free (rec_domain_type);
@@ -2045,6 +2051,9 @@ predict_range (float max_costs, float price, range_t *range, coder_t *c, unsigne
       restore_state_data (states, rec_states - 1, rec_state_data, c);
       costs = MAXCOSTS;
    }
+   if (c->trace)
+      fprintf (c->trace, "pr %u %u %u %u %u %08x %08x %u\n", range->level, range->x, range->y, states,
+	       rec_states, fbits (max_costs), fbits (costs), w->states);
    free (rec_domain_model);
    free (rec_d_domain_model);
    return costs;
@@ -2973,7 +2982,7 @@ fo_wfa_from_dump (const char *text, unsigned root_state, fo_wfa_t *w)
 int
 fo_encode_video (const fo_params_t *p, int n_frames, const int16_t *const *frames,
 		 const char *pattern, int p_min_level, int p_max_level, int search_range,
-		 fo_wfa_t *out, int16_t *reconst, char *errbuf, size_t errlen)
+		 fo_wfa_t *out, int16_t *reconst, FILE *trace, char *errbuf, size_t errlen)
 {
    static int  tables_ready = 0;
    coder_t    *c = calloc (1, sizeof (coder_t));
@@ -2991,6 +3000,7 @@ fo_encode_video (const fo_params_t *p, int n_frames, const int16_t *const *frame
    }
    memset (&dummy, 0, sizeof dummy);
    c->st     = &dummy;
+   c->trace  = trace;
    c->errbuf = errbuf;
    c->errlen = errlen;
    c->wfa    = w;

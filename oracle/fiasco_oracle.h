@@ -147,7 +147,7 @@ void fo_restore_mc (const fo_wfa_t *wfa, unsigned width, unsigned height, int ha
  */
 int fo_encode_video (const fo_params_t *p, int n_frames, const int16_t *const *frames,
 		     const char *pattern, int p_min_level, int p_max_level, int search_range,
-		     fo_wfa_t *out, int16_t *reconst, char *errbuf, size_t errlen);
+		     fo_wfa_t *out, int16_t *reconst, FILE *trace, char *errbuf, size_t errlen);
 
 /* fill_norms_table (codec/mwfa.c:544-602) for the block at (x0, y0) of bintree level 'level':
    out [(my + sr) * 2 sr + (mx + sr)] */

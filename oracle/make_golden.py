@@ -117,6 +117,14 @@ def main():
                             "--pattern=" + pattern, "-i", "%s_[00-%02d+1].pgm" % (name, n - 1), "-o", fco],
                            check=True, env=env, stderr=subprocess.DEVNULL)
             fb = open(fco, "rb").read()
+            if len(frames) * w * h < 200000:      # seam trace of the unmodified coder (oracle/seamdump.c)
+                fco2, trace = os.path.join(tmp, name + ".seam.fco"), os.path.join(tmp, name + ".trace")
+                subprocess.run([os.path.join(REF, "seamdump"), "%s_[00-%02d+1].pgm" % (name, n - 1), fco2, str(q), "0",
+                                trace], check=True, env=env)
+                assert open(fco2, "rb").read() == fb, name
+                assert pattern.lower() == "ippppppppp"[:len(pattern)], "seamdump codes with the CLI's default pattern"
+                with gzip.GzipFile(os.path.join(GOLD, name + ".trace.gz"), "wb", mtime=0) as f:
+                    f.write(open(trace, "rb").read())
             dump = subprocess.run([os.path.join(REF, "wfadump"), fco], check=True, env=env, capture_output=True).stdout
             raw = os.path.join(tmp, name + ".raw")
             subprocess.run([os.path.join(REF, "decdump"), fco, raw], check=True, env=env, capture_output=True)

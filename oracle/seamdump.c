@@ -36,6 +36,8 @@
 #include "rpf.h"
 #include "misc.h"
 #include "bintree.h"
+#include "mwfa.h"
+#include "prediction.h"
 #include "fiasco.h"
 
 static FILE    *trace      = NULL;
@@ -62,6 +64,48 @@ void
 __real_compute_ip_images_state (unsigned image, unsigned address,
 				unsigned level, unsigned n, unsigned from,
 				const wfa_t *wfa, coding_t *c);
+
+/* predicted frames: the motion vector every mc_prediction() finds and the outcome of every
+   predict_range() (codec/mwfa.c:301, codec/prediction.c:96) */
+void
+__real_find_P_frame_mc (word_t *mcpe, real_t price, range_t *range,
+			const wfa_info_t *wi, const motion_t *mt);
+real_t
+__real_predict_range (real_t max_costs, real_t price, range_t *range, wfa_t *wfa,
+		      coding_t *c, unsigned band, int y_state, unsigned states,
+		      const tree_t *tree_model, const tree_t *p_tree_model,
+		      const void *domain_model, const void *d_domain_model,
+		      const void *coeff_model, const void *d_coeff_model);
+
+void
+__wrap_find_P_frame_mc (word_t *mcpe, real_t price, range_t *range,
+			const wfa_info_t *wi, const motion_t *mt)
+{
+   __real_find_P_frame_mc (mcpe, price, range, wi, mt);
+   if (trace)
+      fprintf (trace, "mv %u %u %u %d %d %08x\n", range->level, range->x, range->y,
+	       range->mv.fx, range->mv.fy, fbits (range->mv_coord_bits));
+}
+
+real_t
+__wrap_predict_range (real_t max_costs, real_t price, range_t *range, wfa_t *wfa,
+		      coding_t *c, unsigned band, int y_state, unsigned states,
+		      const tree_t *tree_model, const tree_t *p_tree_model,
+		      const void *domain_model, const void *d_domain_model,
+		      const void *coeff_model, const void *d_coeff_model)
+{
+   const unsigned level = range->level, x = range->x, y = range->y;
+   const unsigned before = wfa->states;
+   real_t	  costs;
+
+   costs = __real_predict_range (max_costs, price, range, wfa, c, band, y_state, states,
+				 tree_model, p_tree_model, domain_model, d_domain_model,
+				 coeff_model, d_coeff_model);
+   if (trace)
+      fprintf (trace, "pr %u %u %u %u %u %08x %08x %u\n", level, x, y, states, before,
+	       fbits (max_costs), fbits (costs), wfa->states);
+   return costs;
+}
 
 real_t
 __wrap_approximate_range (real_t max_costs, real_t price, int max_edges,

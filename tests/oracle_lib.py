@@ -90,7 +90,7 @@ def lib():
         L.fo_tree_model_kat.restype = None
         L.fo_decode_image.argtypes = [C.POINTER(FoWfa), C.c_int, C.c_uint, C.c_uint, C.POINTER(C.c_void_p)]
         L.fo_encode_video.argtypes = [C.POINTER(FoParams), C.c_int, C.POINTER(C.c_void_p), C.c_char_p, C.c_int, C.c_int,
-                                      C.c_int, C.POINTER(FoWfa), C.c_void_p, C.c_char_p, C.c_size_t]
+                                      C.c_int, C.POINTER(FoWfa), C.c_void_p, C.c_void_p, C.c_char_p, C.c_size_t]
         L.fo_fill_norms_table.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint,
                                           C.c_uint, C.c_void_p]
         L.fo_fill_norms_table.restype = None
@@ -218,7 +218,7 @@ def decode(w):
     return planes
 
 
-def encode_video(frames, quality=20.0, pattern="ippp", p_min_level=6, p_max_level=10, search_range=16):
+def encode_video(frames, quality=20.0, pattern="ippp", p_min_level=6, p_max_level=10, search_range=16, trace_path=None):
     """Run the oracle on a grey sequence (list of u8 (h, w) frames; CLI defaults of cfiasco).  Returns
     (list of automata as ctypes structs wrapped like wfa_from_dump(), regenerated frames int16 [n][h][w])."""
     L = lib()
@@ -229,8 +229,11 @@ def encode_video(frames, quality=20.0, pattern="ippp", p_min_level=6, p_max_leve
     out = (FoWfa * len(frames))()
     rec = np.zeros((len(frames), h, w), np.int16)
     err = C.create_string_buffer(256)
+    fp = L._libc.fopen(trace_path.encode(), b"w") if trace_path else None
     rc = L.fo_encode_video(C.byref(p), len(frames), ptrs, pattern.encode(), p_min_level, p_max_level, search_range,
-                           out, rec.ctypes.data, err, 256)
+                           out, rec.ctypes.data, fp, err, 256)
+    if fp:
+        L._libc.fclose(fp)
     if rc:
         raise RuntimeError("oracle: " + err.value.decode())
     return [{"_struct": out[i], "_shape": (h, w, 1), "states": out[i].states} for i in range(len(frames))], rec
