@@ -43,8 +43,12 @@ main (int argc, char **argv)
       wfa_t	*wfa   = alloc_wfa (NO);
       bitfile_t *input = open_wfa (argv [1], wfa->wfainfo);
       FILE	*out   = fopen (argv [2], "wb");
-      image_t	*past  = NULL;
+      image_t	*past = NULL, *future = NULL, *reconst = NULL;
+      bool_t	 future_frame = NO;	/* the previous frame of the stream was a future reference */
+      unsigned	 seen [4096], expected = 0;
       unsigned	 f;
+
+      memset (seen, 0, sizeof seen);
 
       if (!out)
 	 error ("cannot write %s", argv [2]);
@@ -56,18 +60,54 @@ main (int argc, char **argv)
 					  FORMAT_4_4_4, NULL, wfa);
 	 unsigned  bands  = frame->color ? 3 : 1, b;
 
-	 if (wfa->frame_type == P_FRAME)	/* B frames would also need the future frame */
-	    restore_mc (0, frame, past, NULL, wfa);
-	 else if (wfa->frame_type != I_FRAME)
-	    error ("decdump: B frames are not handled");
+	 /* reference frames exactly as video_coder() keeps them (codec/coder.c:560-627): frames
+	    arrive in coding order, a frame that is ahead of the display order is the future
+	    reference of the B frames that follow */
+	 if (wfa->frame_type == I_FRAME)
+	 {
+	    if (past) free_image (past);
+	    if (future) free_image (future);
+	    if (reconst) free_image (reconst);
+	    past = future = reconst = NULL;
+	 }
+	 else if (wfa->frame_type == P_FRAME)
+	 {
+	    if (past) free_image (past);
+	    past    = reconst;
+	    reconst = NULL;
+	    if (future) free_image (future);
+	    future = NULL;
+	 }
+	 else if (future_frame)
+	 {
+	    if (future) free_image (future);
+	    future  = reconst;
+	    reconst = NULL;
+	 }
+	 else if (wfa->wfainfo->B_as_past_ref == YES)
+	 {
+	    if (past) free_image (past);
+	    past    = reconst;
+	    reconst = NULL;
+	 }
+	 else
+	 {
+	    if (reconst) free_image (reconst);
+	    reconst = NULL;
+	 }
+	 if (number < 4096)
+	    seen [number] = 1;
+	 future_frame = number > expected;
+	 while (expected < 4096 && seen [expected])
+	    expected++;
+	 if (wfa->frame_type != I_FRAME)
+	    restore_mc (0, frame, past, future, wfa);
 	 printf ("frame %u %d %u %u %u\n", number, (int) wfa->frame_type,
 		 frame->width, frame->height, bands);
 	 for (b = 0; b < bands; b++)
 	    fwrite (frame->pixels [frame->color ? b : GRAY], sizeof (word_t),
 		    (size_t) frame->width * frame->height, out);
-	 if (past)
-	    free_image (past);
-	 past = frame;
+	 reconst = frame;
 	 remove_states (wfa->basis_states, wfa);
       }
       fclose (out);

@@ -573,7 +573,7 @@ typedef struct range
    /* prediction (cwfa.h:46-75): identically 0 / "none" on the still-image path */
    float    mv_tree_bits, mv_coord_bits, nd_tree_bits, nd_weights_bits;
    int	    prediction;		/* range is coded as motion compensation + delta image */
-   int	    mv_type, mv_fx, mv_fy;	/* codec/wfa.h:62-71 (forward vectors only: P frames) */
+   int	    mv_type, mv_fx, mv_fy, mv_bx, mv_by;	/* codec/wfa.h:62-71 */
 } range_t;
 
 typedef struct coder
@@ -599,7 +599,9 @@ typedef struct coder
    /* motion (cwfa.h:33-44, mwfa.c:86-126) */
    int		frame_type;	/* 0 intra, 1 predicted */
    unsigned	p_min_level, p_max_level, search_range;
-   const int16_t *past;		/* regenerated previous frame */
+   const int16_t *past;		/* regenerated reference frames (B frames: both) */
+   const int16_t *future;
+   float       *mc_backward_norms [MAXLEVEL];
    float	xbits [64], ybits [64];
    float       *mc_forward_norms [MAXLEVEL];
    fo_wfa_t    *wfa;
@@ -1500,6 +1502,8 @@ init_new_state (int auxiliary_state, int delta, range_t *range, const range_t *c
       w->mv_type [w->states][label] = (int8_t) child [label].mv_type;
       w->mv_fx [w->states][label]   = (int8_t) child [label].mv_fx;
       w->mv_fy [w->states][label]   = (int8_t) child [label].mv_fy;
+      w->mv_bx [w->states][label]   = (int8_t) child [label].mv_bx;
+      w->mv_by [w->states][label]   = (int8_t) child [label].mv_by;
       w->x [w->states][label]	    = (uint16_t) child [label].x;
       w->y [w->states][label]	    = (uint16_t) child [label].y;
       /* append_transitions, control.c:175-197 */
@@ -1544,7 +1548,10 @@ static void
 clear_norms_table (unsigned level, coder_t *c)
 {
    if (level > c->p_min_level)
+   {
       memset (c->mc_forward_norms [level], 0, norms_size (c) * sizeof (float));
+      memset (c->mc_backward_norms [level], 0, norms_size (c) * sizeof (float));
+   }
 }
 
 /* update_norms_table (prediction.c:213-238): a level's norms are the sums of its children's */
@@ -1552,15 +1559,20 @@ static void
 update_norms_table (unsigned level, coder_t *c)
 {
    if (level > c->p_min_level)
+   {
       for (unsigned index = 0; index < norms_size (c); index++)
 	 c->mc_forward_norms [level][index] += c->mc_forward_norms [level - 1][index];
+      if (c->frame_type == 2)
+	 for (unsigned index = 0; index < norms_size (c); index++)
+	    c->mc_backward_norms [level][index] += c->mc_backward_norms [level - 1][index];
+   }
 }
 
 /* mcpe_norm (mwfa.c:651-684) over get_mcpe (:604-649), forward prediction: the squared
    norm of (original - displaced reference) / 16, summed in row order in fp32 */
 static float
 mcpe_norm (const coder_t *c, unsigned x0, unsigned y0, unsigned width, unsigned height,
-	   const int16_t *mcblock)
+	   const int16_t *mcblock, const int16_t *mcblock2)
 {
    const int16_t *o    = c->planes [0] + (size_t) y0 * (unsigned) c->opt.width + x0;
    float	  norm = 0;
@@ -1568,8 +1580,11 @@ mcpe_norm (const coder_t *c, unsigned x0, unsigned y0, unsigned width, unsigned 
    for (unsigned y = 0; y < height; y++)
       for (unsigned x = 0; x < width; x++)
       {
-	 const int16_t d = (int16_t) (o [(size_t) y * (unsigned) c->opt.width + x] - mcblock [y * width + x]);
-	 const int     q = d / 16;
+	 /* get_mcpe (mwfa.c:604-649): one reference block, or the mean of two (truncating) */
+	 const int     ref = mcblock2 ? (mcblock [y * width + x] + mcblock2 [y * width + x]) / 2
+				      : mcblock [y * width + x];
+	 const int16_t d   = (int16_t) (o [(size_t) y * (unsigned) c->opt.width + x] - ref);
+	 const int     q   = d / 16;
 
 	 norm += (float) (q * q);
       }
@@ -1590,12 +1605,21 @@ fill_norms_table (unsigned x0, unsigned y0, unsigned level, coder_t *c)
       {
 	 if ((int) x0 + mx < 0 || x0 + mx + width > (unsigned) c->opt.width
 	     || (int) y0 + my < 0 || y0 + my + height > (unsigned) c->opt.height)
-	    c->mc_forward_norms [level][index] = 0.0f;
+	 {
+	    c->mc_forward_norms [level][index]	= 0.0f;
+	    c->mc_backward_norms [level][index] = 0.0f;
+	 }
 	 else
 	 {
 	    extract_mc_block (mcblock, width, height, c->past, (unsigned) c->opt.width, 0,
 			      x0, y0, mx, my);
-	    c->mc_forward_norms [level][index] = mcpe_norm (c, x0, y0, width, height, mcblock);
+	    c->mc_forward_norms [level][index] = mcpe_norm (c, x0, y0, width, height, mcblock, NULL);
+	    if (c->frame_type == 2)
+	    {
+	       extract_mc_block (mcblock, width, height, c->future, (unsigned) c->opt.width, 0,
+				 x0, y0, mx, my);
+	       c->mc_backward_norms [level][index] = mcpe_norm (c, x0, y0, width, height, mcblock, NULL);
+	    }
 	 }
       }
    free (mcblock);
@@ -1638,7 +1662,7 @@ typedef struct state_data
    float   *images_of_state, *inner_products, *ip_states_state [MAXLEVEL];
    int16_t  tree [MAXLABELS], y_state [MAXLABELS], into [MAXLABELS][MAXEDGES + 1];
    uint8_t  y_column [MAXLABELS];
-   int8_t   mv_type [MAXLABELS], mv_fx [MAXLABELS], mv_fy [MAXLABELS];
+   int8_t   mv_type [MAXLABELS], mv_fx [MAXLABELS], mv_fy [MAXLABELS], mv_bx [MAXLABELS], mv_by [MAXLABELS];
    uint16_t x [MAXLABELS], y [MAXLABELS];
    float    weight [MAXLABELS][MAXEDGES + 1];
 } state_data_t;
@@ -1674,6 +1698,8 @@ store_state_data (unsigned from, unsigned to, coder_t *c)
 	 sd->mv_type [label]  = w->mv_type [state][label];
 	 sd->mv_fx [label]    = w->mv_fx [state][label];
 	 sd->mv_fy [label]    = w->mv_fy [state][label];
+	 sd->mv_bx [label]    = w->mv_bx [state][label];
+	 sd->mv_by [label]    = w->mv_by [state][label];
 	 sd->x [label]	      = w->x [state][label];
 	 sd->y [label]	      = w->y [state][label];
 	 memcpy (sd->weight [label], w->weight [state][label], sizeof sd->weight [label]);
@@ -1719,6 +1745,8 @@ restore_state_data (unsigned from, unsigned to, state_data_t *data, coder_t *c)
 	 w->mv_type [state][label]  = sd->mv_type [label];
 	 w->mv_fx [state][label]    = sd->mv_fx [label];
 	 w->mv_fy [state][label]    = sd->mv_fy [label];
+	 w->mv_bx [state][label]    = sd->mv_bx [label];
+	 w->mv_by [state][label]    = sd->mv_by [label];
 	 w->x [state][label]	    = sd->x [label];
 	 w->y [state][label]	    = sd->y [label];
 	 memcpy (w->weight [state][label], sd->weight [label], sizeof sd->weight [label]);
@@ -1767,6 +1795,68 @@ mc_prediction (float max_costs, float price, unsigned band, int y_state, range_t
 
    if (prange.level == c->p_min_level)
       fill_norms_table (prange.x, prange.y, prange.level, c);
+   if (c->frame_type == 2)
+   {
+      /* find_B_frame_mc (mwfa.c:341-542) without cross-B search (coder.c:359 sets that flag
+	 from the half-pixel option): best forward vector, best backward vector, both together */
+      int16_t *mcblock1 = calloc ((size_t) width * height, sizeof (int16_t));
+      int16_t *mcblock2 = calloc ((size_t) width * height, sizeof (int16_t));
+      float    forward_bits, backward_bits, interp_bits, forward_costs, backward_costs, interp_costs;
+      int      fx, fy, bx, by, mctype;
+
+      forward_costs = find_best_mv (price, prange.x, prange.y, width, height, &forward_bits, &fx, &fy,
+				    c->mc_forward_norms [prange.level], c) + 3 * price;
+      backward_costs = find_best_mv (price, prange.x, prange.y, width, height, &backward_bits, &bx, &by,
+				     c->mc_backward_norms [prange.level], c) + 3 * price;
+      interp_bits = forward_bits + backward_bits;
+      extract_mc_block (mcblock1, width, height, c->past, (unsigned) c->opt.width, 0,
+			prange.x, prange.y, fx, fy);
+      extract_mc_block (mcblock2, width, height, c->future, (unsigned) c->opt.width, 0,
+			prange.x, prange.y, bx, by);
+      interp_costs = mcpe_norm (c, prange.x, prange.y, width, height, mcblock1, mcblock2)
+		     + (interp_bits + 2) * price;
+      if (forward_costs <= interp_costs)
+	 mctype = forward_costs <= backward_costs ? 1 : 2;
+      else
+	 mctype = backward_costs <= interp_costs ? 2 : 3;
+      prange.mv_type = mctype;
+      if (mctype == 1)
+      {
+	 prange.mv_tree_bits  = 3;
+	 prange.mv_coord_bits = forward_bits;
+	 prange.mv_fx	      = fx;
+	 prange.mv_fy	      = fy;
+      }
+      else if (mctype == 2)
+      {
+	 prange.mv_tree_bits  = 3;
+	 prange.mv_coord_bits = backward_bits;
+	 prange.mv_bx	      = bx;
+	 prange.mv_by	      = by;
+	 memcpy (mcblock1, mcblock2, (size_t) width * height * sizeof (int16_t));
+      }
+      else
+      {
+	 prange.mv_tree_bits  = 2;
+	 prange.mv_coord_bits = interp_bits;
+	 prange.mv_fx	      = fx;
+	 prange.mv_fy	      = fy;
+	 prange.mv_bx	      = bx;
+	 prange.mv_by	      = by;
+      }
+      for (unsigned y = 0; y < height; y++)
+	 for (unsigned x = 0; x < width; x++)
+	 {
+	    const int ref = mctype == 3 ? (mcblock1 [y * width + x] + mcblock2 [y * width + x]) / 2
+					: mcblock1 [y * width + x];
+
+	    mcpe [y * width + x]
+	       = (int16_t) (c->planes [0][(size_t) (prange.y + y) * (unsigned) c->opt.width + prange.x + x] - ref);
+	 }
+      free (mcblock1);
+      free (mcblock2);
+   }
+   else
    /* find_P_frame_mc (mwfa.c:301-339) */
    {
       int16_t *mcblock = calloc ((size_t) width * height, sizeof (int16_t));
@@ -1973,6 +2063,8 @@ fo_close_holes (fo_wfa_t *w)
 	 w->mv_type [t][label]	= w->mv_type [s2][label];
 	 w->mv_fx [t][label]	= w->mv_fx [s2][label];
 	 w->mv_fy [t][label]	= w->mv_fy [s2][label];
+	 w->mv_bx [t][label]	= w->mv_bx [s2][label];
+	 w->mv_by [t][label]	= w->mv_by [s2][label];
 	 memcpy (w->into [t][label], w->into [s2][label], sizeof w->into [t][label]);
 	 memcpy (w->weight [t][label], w->weight [s2][label], sizeof w->weight [t][label]);
       }
@@ -2861,29 +2953,39 @@ extract_mc_block (int16_t *mcblock, unsigned width, unsigned height,
 
 void
 fo_restore_mc (const fo_wfa_t *w, unsigned width, unsigned height, int half_pixel,
-	       int16_t *image, const int16_t *past)
+	       int16_t *image, const int16_t *past, const int16_t *future)
 {
-   int16_t *mcblock = malloc (size_of_level (MAXLEVEL > 16 ? 16 : MAXLEVEL) * sizeof (int16_t));
+   int16_t *mcblock  = malloc (size_of_level (MAXLEVEL > 16 ? 16 : MAXLEVEL) * sizeof (int16_t));
+   int16_t *mcblock2 = malloc (size_of_level (MAXLEVEL > 16 ? 16 : MAXLEVEL) * sizeof (int16_t));
 
    (void) height;
    for (unsigned state = w->basis_states; state <= w->root_state; state++)
       for (unsigned label = 0; label < MAXLABELS; label++)
-	 if (w->mv_type [state][label] == 1)	/* FORWARD (motion.c:78-108) */
+	 if (w->mv_type [state][label] != 0)	/* motion.c:69-190 */
 	 {
 	    const unsigned level = w->level_of_state [state] - 1u;
 	    const unsigned bw = width_of_level (level), bh = height_of_level (level);
+	    const int	   type	 = w->mv_type [state][label];
 
-	    extract_mc_block (mcblock, bw, bh, past, width, half_pixel, w->x [state][label],
-			      w->y [state][label], w->mv_fx [state][label], w->mv_fy [state][label]);
+	    if (type == 1 || type == 3)
+	       extract_mc_block (mcblock, bw, bh, past, width, half_pixel, w->x [state][label],
+				 w->y [state][label], w->mv_fx [state][label], w->mv_fy [state][label]);
+	    if (type == 2 || type == 3)
+	       extract_mc_block (type == 2 ? mcblock : mcblock2, bw, bh, future, width, half_pixel,
+				 w->x [state][label], w->y [state][label], w->mv_bx [state][label],
+				 w->mv_by [state][label]);
 	    for (unsigned y = 0; y < bh; y++)
 	       for (unsigned x = 0; x < bw; x++)
 	       {
-		  int16_t *o = image + (size_t) (w->y [state][label] + y) * width + w->x [state][label] + x;
+		  int16_t  *o	= image + (size_t) (w->y [state][label] + y) * width + w->x [state][label] + x;
+		  const int ref = type == 3 ? (mcblock [y * bw + x] + mcblock2 [y * bw + x]) >> 1
+					    : mcblock [y * bw + x];
 
-		  *o = (int16_t) (*o + mcblock [y * bw + x]);
+		  *o = (int16_t) (*o + ref);
 	       }
 	 }
    free (mcblock);
+   free (mcblock2);
 }
 
 int
@@ -3056,86 +3158,153 @@ fo_encode_video (const fo_params_t *p, int n_frames, const int16_t *const *frame
       c->xbits [dx + search_range] = c->ybits [dx + search_range]
 				   = (float) mv_code_length [dx + search_range];
    for (level = c->p_min_level; level <= c->p_max_level; level++)
-      c->mc_forward_norms [level] = calloc (norms_size (c), sizeof (float));
+   {
+      c->mc_forward_norms [level]  = calloc (norms_size (c), sizeof (float));
+      c->mc_backward_norms [level] = calloc (norms_size (c), sizeof (float));
+   }
 
    append_basis_states (c);
    c->price = 128 * 64 / p->quality;
 
-   for (int f = 0; f < n_frames; f++)
+   /* video_coder (coder.c:490-680): frames are coded in display order except that a B frame
+      waits for the next non-B frame (its future reference), which is coded first; the last
+      frame of the sequence is forced to be a P frame */
    {
-      range_t range;
-      int     type = 0;
+      int display = 0, future_display = -1, future_frame = 0, coded = 0;
+      int16_t *fut = calloc (npix, sizeof (int16_t));
+      int have_reconst = 0;
 
-      if (f > 0)
+      while (display < n_frames)
       {
-	 const int t = pattern [(size_t) f % strlen (pattern)];
+	 range_t range;
+	 int	 type, frame;
 
-	 if (t == 'p' || t == 'P')
-	    type = 1;
-	 else if (t != 'i' && t != 'I')
-	    fail (c, "fo_encode_video: frame type %c is not handled (I and P only)", t);
-      }
-      c->frame_type = type;
-      c->planes [0] = frames [f];
-      c->past	    = type ? past : NULL;
-
-      /* frame_coder (coder.c:692-755) */
-      init_tree_model (&c->tree);
-      init_tree_model (&c->p_tree);
-      rle_init (&c->pool, (unsigned) c->opt.max_states);
-      rle_init (&c->d_pool, (unsigned) c->opt.max_states);
-      c->d_pool_is_rle = type != 0;
-      for (state = 0; state < w->basis_states; state++)
-	 if (usedomain (state, w))
+	 if (display == 0)
+	    type = 0;
+	 else
 	 {
-	    rle_append (&c->pool, state);
-	    if (c->d_pool_is_rle)
-	       rle_append (&c->d_pool, state);
+	    const int t = pattern [(size_t) display % strlen (pattern)];
+
+	    type = (t == 'p' || t == 'P') ? 1 : (t == 'b' || t == 'B') ? 2 : (t == 'i' || t == 'I') ? 0 : -1;
+	    if (type < 0)
+	       fail (c, "Frame type %c not valid. Choose one of I,B or P.", t);
 	 }
-      aac_init (&c->coeff, c->rpf, c->dc_rpf, (unsigned) c->opt.lc_min_level,
-		(unsigned) c->opt.lc_max_level);
-      aac_init (&c->d_coeff, c->rpf, c->dc_rpf, (unsigned) c->opt.lc_min_level,
-		(unsigned) c->opt.lc_max_level);
-      c->ap = &c->pool;
-      c->ac = &c->coeff;
+	 if (display == future_display)		/* already coded as a future reference */
+	 {
+	    display++;
+	    continue;
+	 }
+	 else if (type == 2 && display > future_display)
+	 {
+	    int i = display;
 
-      memset (&range, 0, sizeof range);
-      range.level = c->level;
-      w->costs [0] = subdivide (MAXCOSTS, 0, RANGE, &range, c, type != 0, 0);
-      if (range.tree == RANGE)
-	 fail (c, "No root state generated!");
-      w->root_state	  = (unsigned) range.tree;
-      w->frame_type	  = type;
-      /* locate_delta_images (wfalib.c:699-730, called at coder.c:876): the delta flags the
-	 stream carries are derived from the structure, top down */
-      for (state = w->root_state; state >= w->basis_states; state--)
-	 w->delta_state [state] = 0;
-      for (state = w->root_state; state >= w->basis_states; state--)
-	 for (label = 0; label < MAXLABELS; label++)
-	    if (w->tree [state][label] != RANGE
-		&& (w->mv_type [state][label] != 0 || w->into [state][label][0] != NO_EDGE
-		    || w->delta_state [state]))
-	       w->delta_state [w->tree [state][label]] = 1;
-      w->err [0]	  = range.err;
-      w->tree_bits [0]	  = range.tree_bits;
-      w->matrix_bits [0]  = range.matrix_bits;
-      w->weights_bits [0] = range.weights_bits;
-      memcpy (&out [f], w, sizeof *w);
+	    while (type == 2)
+	    {
+	       i++;
+	       if (i >= n_frames)
+	       {
+		  future_display = i - 1;
+		  type		 = 1;
+	       }
+	       else
+	       {
+		  const int t = pattern [(size_t) i % strlen (pattern)];
 
-      /* regenerate the frame: the next frame's reference (coder.c:642-651) */
-      {
-	 int16_t *planes [3] = {cur, NULL, NULL};
+		  future_display = i;
+		  type = (t == 'p' || t == 'P') ? 1 : (t == 'b' || t == 'B') ? 2 : 0;
+	       }
+	       frame = future_display;
+	    }
+	 }
+	 else
+	 {
+	    frame = display;
+	    display++;
+	 }
 
-	 fo_decode_image (w, 0, (unsigned) p->width, (unsigned) p->height, planes);
-	 if (type)
-	    fo_restore_mc (w, (unsigned) p->width, (unsigned) p->height, 0, cur, past);
-	 if (reconst)
-	    memcpy (reconst + (size_t) f * npix, cur, npix * sizeof (int16_t));
-	 int16_t *t = past;
-	 past = cur;
-	 cur  = t;
+	 /* reference frames (coder.c:571-627); 'cur' holds the last regenerated frame */
+	 if (type == 0)
+	    have_reconst = 0;
+	 else if (type == 1)
+	 {
+	    int16_t *t = past; past = cur; cur = t;	/* past <- current */
+	    have_reconst = 0;
+	 }
+	 else if (future_frame)
+	 {
+	    int16_t *t = fut; fut = cur; cur = t;	/* future <- current */
+	    have_reconst = 0;
+	 }
+	 else					/* B_as_past_ref = YES (options.c:99) */
+	 {
+	    int16_t *t = past; past = cur; cur = t;
+	    have_reconst = 0;
+	 }
+	 (void) have_reconst;
+	 future_frame  = frame == future_display;
+	 c->frame_type = type;
+	 c->planes [0] = frames [frame];
+	 c->past       = past;
+	 c->future     = fut;
+
+	 /* frame_coder (coder.c:692-755) */
+	 init_tree_model (&c->tree);
+	 init_tree_model (&c->p_tree);
+	 rle_init (&c->pool, (unsigned) c->opt.max_states);
+	 rle_init (&c->d_pool, (unsigned) c->opt.max_states);
+	 c->d_pool_is_rle = type != 0;
+	 for (state = 0; state < w->basis_states; state++)
+	    if (usedomain (state, w))
+	    {
+	       rle_append (&c->pool, state);
+	       if (c->d_pool_is_rle)
+		  rle_append (&c->d_pool, state);
+	    }
+	 aac_init (&c->coeff, c->rpf, c->dc_rpf, (unsigned) c->opt.lc_min_level,
+		   (unsigned) c->opt.lc_max_level);
+	 aac_init (&c->d_coeff, c->rpf, c->dc_rpf, (unsigned) c->opt.lc_min_level,
+		   (unsigned) c->opt.lc_max_level);
+	 c->ap = &c->pool;
+	 c->ac = &c->coeff;
+
+	 memset (&range, 0, sizeof range);
+	 range.level = c->level;
+	 w->costs [0] = subdivide (MAXCOSTS, 0, RANGE, &range, c, type != 0, 0);
+	 if (range.tree == RANGE)
+	    fail (c, "No root state generated!");
+	 w->root_state	     = (unsigned) range.tree;
+	 w->frame_type	     = type;
+	 w->frame_number     = frame;
+	 w->err [0]	     = range.err;
+	 w->tree_bits [0]    = range.tree_bits;
+	 w->matrix_bits [0]  = range.matrix_bits;
+	 w->weights_bits [0] = range.weights_bits;
+	 /* locate_delta_images (wfalib.c:699-730, called at coder.c:876): the delta flags the
+	    stream carries are derived from the structure, top down */
+	 for (state = w->root_state; state >= w->basis_states; state--)
+	    w->delta_state [state] = 0;
+	 for (state = w->root_state; state >= w->basis_states; state--)
+	    for (label = 0; label < MAXLABELS; label++)
+	       if (w->tree [state][label] != RANGE
+		   && (w->mv_type [state][label] != 0 || w->into [state][label][0] != NO_EDGE
+		       || w->delta_state [state]))
+		  w->delta_state [w->tree [state][label]] = 1;
+	 memcpy (&out [coded], w, sizeof *w);
+
+	 /* regenerate the frame: a reference of the frames to come (coder.c:642-651) */
+	 {
+	    int16_t *planes [3] = {cur, NULL, NULL};
+
+	    fo_decode_image (w, 0, (unsigned) p->width, (unsigned) p->height, planes);
+	    if (type)
+	       fo_restore_mc (w, (unsigned) p->width, (unsigned) p->height, 0, cur, past, fut);
+	    if (reconst)
+	       memcpy (reconst + (size_t) coded * npix, cur, npix * sizeof (int16_t));
+	 }
+	 coded++;
+	 remove_states (w->basis_states, w);
       }
-      remove_states (w->basis_states, w);
+      free (fut);
    }
 
 cleanup:
@@ -3147,7 +3316,10 @@ cleanup:
 	 free (c->ip_states_state [state][level]);
    }
    for (level = 0; level < MAXLEVEL; level++)
+   {
       free (c->mc_forward_norms [level]);
+      free (c->mc_backward_norms [level]);
+   }
    free (c->pixels);
    free (c);
    free (w);

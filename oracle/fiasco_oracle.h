@@ -76,6 +76,7 @@ typedef struct fo_wfa
    int8_t   mv_bx [FO_MAXSTATES][FO_MAXLABELS], mv_by [FO_MAXSTATES][FO_MAXLABELS];
    uint8_t  delta_state [FO_MAXSTATES];
    int	    frame_type;		/* 0 intra, 1 predicted, 2 bidirectional */
+   int	    frame_number;	/* display number (sequences are coded out of display order) */
 } fo_wfa_t;
 
 /* work counters */
@@ -137,7 +138,7 @@ int fo_wfa_from_dump (const char *text, unsigned root_state, fo_wfa_t *wfa);
  *  blocks of the regenerated previous frame 'past' to 'image' (both width * height shorts).
  */
 void fo_restore_mc (const fo_wfa_t *wfa, unsigned width, unsigned height, int half_pixel,
-		    int16_t *image, const int16_t *past);
+		    int16_t *image, const int16_t *past, const int16_t *future);
 
 /*
  *  Encode a grey sequence (video_coder / frame_coder, codec/coder.c:490-892): frame 0 intra, the

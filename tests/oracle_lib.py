@@ -51,7 +51,7 @@ class FoWfa(C.Structure):
         ("matrix_bits", C.c_float * 3), ("weights_bits", C.c_float * 3),
         ("mv_type", C.c_int8 * 2 * MAXSTATES), ("mv_fx", C.c_int8 * 2 * MAXSTATES), ("mv_fy", C.c_int8 * 2 * MAXSTATES),
         ("mv_bx", C.c_int8 * 2 * MAXSTATES), ("mv_by", C.c_int8 * 2 * MAXSTATES),
-        ("delta_state", C.c_uint8 * MAXSTATES), ("frame_type", C.c_int),
+        ("delta_state", C.c_uint8 * MAXSTATES), ("frame_type", C.c_int), ("frame_number", C.c_int),
     ]
 
 
@@ -99,7 +99,7 @@ def lib():
         L.fo_close_holes.argtypes = [C.POINTER(FoWfa)]
         L.fo_close_holes.restype = None
         L.fo_wfa_from_dump.argtypes = [C.c_char_p, C.c_uint, C.POINTER(FoWfa)]
-        L.fo_restore_mc.argtypes = [C.POINTER(FoWfa), C.c_uint, C.c_uint, C.c_int, C.c_void_p, C.c_void_p]
+        L.fo_restore_mc.argtypes = [C.POINTER(FoWfa), C.c_uint, C.c_uint, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.fo_restore_mc.restype = None
         L.fo_grey_to_plane.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         L.fo_rgb_to_planes.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -198,11 +198,13 @@ def wfa_from_dump(text, root_state, width, height):
     return {"_struct": w, "_shape": (height, width, 1), "states": w.states}
 
 
-def restore_mc(w, image, past, half_pixel=0):
+def restore_mc(w, image, past, half_pixel=0, future=None):
     """restore_mc (codec/motion.c:37) on a regenerated grey frame, in place."""
     h, wd, _ = w["_shape"]
     past = np.ascontiguousarray(past, np.int16)
-    lib().fo_restore_mc(C.byref(w["_struct"]), wd, h, half_pixel, image.ctypes.data, past.ctypes.data)
+    future = np.ascontiguousarray(future, np.int16) if future is not None else None
+    lib().fo_restore_mc(C.byref(w["_struct"]), wd, h, half_pixel, image.ctypes.data, past.ctypes.data,
+                        future.ctypes.data if future is not None else None)
     return image
 
 
