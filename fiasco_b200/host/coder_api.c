@@ -412,9 +412,11 @@ fiasco_write_video_stream (const char *filename, const fiasco_stream_info_t *inf
 	 w.y_column	  = (const uint8_t (*)[2]) frames [n].y_column;
 	 if (motion && motion [n].frame_type != 0)
 	 {
-	    if (motion [n].frame_type != 1 || info->color)
-	       fi_error ("frame %d: only grey P frames can be written", n);
+	    if (motion [n].frame_type < 1 || motion [n].frame_type > 2 || info->color)
+	       fi_error ("frame %d: only grey P and B frames can be written", n);
 	    w.frame_type  = motion [n].frame_type;
+	    w.mv_bx	  = (const int8_t (*)[2]) motion [n].mv_bx;
+	    w.mv_by	  = (const int8_t (*)[2]) motion [n].mv_by;
 	    w.x		  = (const uint16_t (*)[2]) frames [n].x;
 	    w.y		  = (const uint16_t (*)[2]) frames [n].y;
 	    w.mv_type	  = (const int8_t (*)[2]) motion [n].mv_type;
@@ -422,7 +424,7 @@ fiasco_write_video_stream (const char *filename, const fiasco_stream_info_t *inf
 	    w.mv_fy	  = (const int8_t (*)[2]) motion [n].mv_fy;
 	    w.delta_state = motion [n].delta_state;
 	 }
-	 fi_write_next_wfa (&w, (unsigned) n, n == 0, 1, 1, out);
+	 fi_write_next_wfa (&w, motion ? (unsigned) motion [n].frame_number : (unsigned) n, n == 0, 1, 1, out);
       }
       fi_bits_close (out);
       return 1;

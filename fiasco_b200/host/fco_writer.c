@@ -616,10 +616,11 @@ static const unsigned short mv_code_table [33][2] =
 };
 
 /*
- *  write_mc (output/mc.c:75-84) for a predicted (P) frame: the tree of "motion compensated
- *  or not" decisions in breadth-first order from the highest prediction level down
- *  (encode_mc_tree, :91-150; P frames: one bit per decision, 1 = none), then the vector
- *  components in state order (encode_mc_coords, :152-251).
+ *  write_mc (output/mc.c:75-84) for a predicted frame: the tree of motion compensation
+ *  decisions in breadth-first order from the highest prediction level down (encode_mc_tree,
+ *  :91-150; P frames: one bit per decision, 1 = none; B frames: none 1, forward 000,
+ *  backward 001, interpolated 01), then the vector components in state order
+ *  (encode_mc_coords, :152-251).
  */
 static void
 write_mc (const fi_wfa_t *wfa, fi_bits_t *out)
@@ -644,7 +645,13 @@ write_mc (const fi_wfa_t *wfa, fi_bits_t *out)
 
 	 if (wfa->x [state][label] + (1u << (level >> 1)) <= wi->width
 	     && wfa->y [state][label] + (1u << ((level + 1) >> 1)) <= wi->height)
-	    fi_put_bit (out, type == 0);	/* p_frame_codes: none = 1, forward = 0 */
+	 {
+	    if (wfa->frame_type == 1)
+	       fi_put_bit (out, type == 0);	/* p_frame_codes: none = 1, forward = 0 */
+	    else			/* b_frame_codes (mc.c:46-53) */
+	       fi_put_bits (out, type == 0 ? 1 : type == 3 ? 1 : type == 2 ? 1 : 0,
+			    type == 0 ? 1 : type == 3 ? 2 : 3);
+	 }
 	 if (type == 0 && !isrange (wfa->tree [state][label])
 	     && (int) level >= (int) wi->p_min_level)
 	    queue [last++] = (unsigned) wfa->tree [state][label];
@@ -652,7 +659,10 @@ write_mc (const fi_wfa_t *wfa, fi_bits_t *out)
    fi_byte_align (out);
    for (state = wfa->basis_states; state < max_state; state++)
       for (label = 0; label < FI_MAXLABELS; label++)
-	 if (wfa->mv_type [state][label] == 1)		/* FORWARD */
+      {
+	 const int type = wfa->mv_type [state][label];
+
+	 if (type == 1 || type == 3)			/* forward vector */
 	 {
 	    const unsigned ix = (unsigned) (wfa->mv_fx [state][label] + (int) wi->search_range);
 	    const unsigned iy = (unsigned) (wfa->mv_fy [state][label] + (int) wi->search_range);
@@ -660,8 +670,17 @@ write_mc (const fi_wfa_t *wfa, fi_bits_t *out)
 	    fi_put_bits (out, mv_code_table [ix][0], mv_code_table [ix][1]);
 	    fi_put_bits (out, mv_code_table [iy][0], mv_code_table [iy][1]);
 	 }
-	 else if (wfa->mv_type [state][label] != 0)
-	    fi_error ("only forward motion vectors (P frames) can be written");
+	 if (type == 2 || type == 3)			/* backward vector */
+	 {
+	    if (!wfa->mv_bx || !wfa->mv_by)
+	       fi_error ("B frame without backward vectors");
+	    const unsigned ix = (unsigned) (wfa->mv_bx [state][label] + (int) wi->search_range);
+	    const unsigned iy = (unsigned) (wfa->mv_by [state][label] + (int) wi->search_range);
+
+	    fi_put_bits (out, mv_code_table [ix][0], mv_code_table [ix][1]);
+	    fi_put_bits (out, mv_code_table [iy][0], mv_code_table [iy][1]);
+	 }
+      }
    fi_byte_align (out);
    free (queue);
 }

@@ -155,7 +155,7 @@ typedef struct fi_wfa
    /* predicted frames (NULL / 0 for an intra frame): codec/wfa.h:62-71,126,137 */
    int		   frame_type;		/* 0 intra, 1 predicted */
    const uint16_t (*x) [2], (*y) [2];	/* range coordinates (the motion tree asks for them) */
-   const int8_t	  (*mv_type) [2], (*mv_fx) [2], (*mv_fy) [2];
+   const int8_t	  (*mv_type) [2], (*mv_fx) [2], (*mv_fy) [2], (*mv_bx) [2], (*mv_by) [2];
    const uint8_t  *delta_state;
 } fi_wfa_t;
 

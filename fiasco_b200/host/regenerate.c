@@ -86,7 +86,8 @@ state_image (regen_t *r, unsigned state, unsigned level)
 
 int
 fiasco_regenerate_frame (const fb200_wfa_t *w, const fiasco_frame_motion_t *motion,
-			 int width, int height, const int16_t *past, int16_t *out)
+			 int width, int height, const int16_t *past, const int16_t *future,
+			 int16_t *out)
 {
    fi_try
    {
@@ -98,9 +99,10 @@ fiasco_regenerate_frame (const fb200_wfa_t *w, const fiasco_frame_motion_t *moti
 	 fi_set_error ("fiasco_regenerate_frame: bad arguments");
 	 return 0;
       }
-      if (motion && motion->frame_type != 0 && (motion->frame_type != 1 || !past))
+      if (motion && motion->frame_type != 0
+	  && (motion->frame_type > 2 || !past || (motion->frame_type == 2 && !future)))
       {
-	 fi_set_error ("fiasco_regenerate_frame: only P frames with a previous frame");
+	 fi_set_error ("fiasco_regenerate_frame: a predicted frame needs its reference frame(s)");
 	 return 0;
       }
       /* highest level of a linear combination; the size the bintree covers (decoder.c:449-461,
@@ -148,27 +150,36 @@ fiasco_regenerate_frame (const fb200_wfa_t *w, const fiasco_frame_motion_t *moti
 	 free (r.pix [i]);
       free (r.pix);
 
-      /* restore_mc (motion.c:37-108), forward prediction with full-pixel vectors: add the
-	 displaced block of the previous frame */
-      if (motion && motion->frame_type == 1)
+      /* restore_mc (motion.c:37-190) with full-pixel vectors: add the displaced block of the
+	 previous frame (forward), of the future frame (backward), or their mean (interpolated,
+	 arithmetic shift) */
+      if (motion && motion->frame_type != 0)
 	 for (state = w->basis_states; state <= w->root_state; state++)
 	    for (unsigned label = 0; label < 2; label++)
-	       if (motion->mv_type [2 * state + label] == 1)
-	       {
-		  const unsigned level = (unsigned) w->level_of_state [state] - 1;
-		  const unsigned bw = W_OF (level), bh = H_OF (level);
-		  const int	 x0 = w->x [2 * state + label], y0 = w->y [2 * state + label];
-		  const int	 mx = motion->mv_fx [2 * state + label];
-		  const int	 my = motion->mv_fy [2 * state + label];
+	    {
+	       const int type = motion->mv_type [2 * state + label];
 
-		  for (unsigned y = 0; y < bh; y++)
-		     for (unsigned x = 0; x < bw; x++)
-		     {
-			int16_t *o = out + (size_t) (y0 + (int) y) * width + x0 + (int) x;
+	       if (type == 0)
+		  continue;
+	       if (type > 1 && (!future || !motion->mv_bx || !motion->mv_by))
+		  fi_error ("backward motion compensation without a future frame");
+	       const unsigned level = (unsigned) w->level_of_state [state] - 1;
+	       const unsigned bw = W_OF (level), bh = H_OF (level);
+	       const int      x0 = w->x [2 * state + label], y0 = w->y [2 * state + label];
+	       const int      fx = motion->mv_fx [2 * state + label], fy = motion->mv_fy [2 * state + label];
+	       const int      bx = type > 1 ? motion->mv_bx [2 * state + label] : 0;
+	       const int      by = type > 1 ? motion->mv_by [2 * state + label] : 0;
 
-			*o = (int16_t) (*o + past [(size_t) (y0 + my + (int) y) * width + x0 + mx + (int) x]);
-		     }
-	       }
+	       for (unsigned y = 0; y < bh; y++)
+		  for (unsigned x = 0; x < bw; x++)
+		  {
+		     int16_t  *o = out + (size_t) (y0 + (int) y) * width + x0 + (int) x;
+		     const int f = type != 2 ? past [(size_t) (y0 + fy + (int) y) * width + x0 + fx + (int) x] : 0;
+		     const int b = type != 1 ? future [(size_t) (y0 + by + (int) y) * width + x0 + bx + (int) x] : 0;
+
+		     *o = (int16_t) (*o + (type == 1 ? f : type == 2 ? b : (f + b) >> 1));
+		  }
+	    }
       return 1;
    }
    fi_catch
@@ -187,7 +198,7 @@ fiasco_regenerate_frame (const fb200_wfa_t *w, const fiasco_frame_motion_t *moti
  */
 int
 fiasco_finish_predicted_frame (fb200_wfa_t *w, int8_t *mv_type, int8_t *mv_fx, int8_t *mv_fy,
-			       uint8_t *delta_state)
+			       int8_t *mv_bx, int8_t *mv_by, uint8_t *delta_state)
 {
    fi_try
    {
@@ -222,6 +233,11 @@ fiasco_finish_predicted_frame (fb200_wfa_t *w, int8_t *mv_type, int8_t *mv_fx, i
 	    mv_type [a]	    = mv_type [b];
 	    mv_fx [a]	    = mv_fx [b];
 	    mv_fy [a]	    = mv_fy [b];
+	    if (mv_bx && mv_by)
+	    {
+	       mv_bx [a] = mv_bx [b];
+	       mv_by [a] = mv_by [b];
+	    }
 	    memcpy (w->into + a * 6, w->into + b * 6, 6 * sizeof (int16_t));
 	    memcpy (w->weight + a * 6, w->weight + b * 6, 6 * sizeof (float));
 	 }

@@ -20,8 +20,12 @@ class StreamInfo(C.Structure):
 
 
 class FrameMotion(C.Structure):
-    _fields_ = [("frame_type", C.c_int), ("mv_type", C.c_void_p), ("mv_fx", C.c_void_p), ("mv_fy", C.c_void_p),
-                ("delta_state", C.c_void_p)]
+    _fields_ = [("frame_type", C.c_int), ("frame_number", C.c_int), ("mv_type", C.c_void_p), ("mv_fx", C.c_void_p),
+                ("mv_fy", C.c_void_p), ("mv_bx", C.c_void_p), ("mv_by", C.c_void_p), ("delta_state", C.c_void_p)]
+
+
+_MOTION_ARRAYS = (("mv_type", np.int8), ("mv_fx", np.int8), ("mv_fy", np.int8), ("mv_bx", np.int8), ("mv_by", np.int8),
+                  ("delta_state", np.uint8))
 
 
 def lib_path():
@@ -40,8 +44,8 @@ def load():
         L.fiasco_write_video_stream.argtypes = [C.c_char_p, C.POINTER(StreamInfo), C.POINTER(ffi._Wfa),
                                                 C.POINTER(FrameMotion), C.c_int, C.c_uint]
         L.fiasco_regenerate_frame.argtypes = [C.POINTER(ffi._Wfa), C.POINTER(FrameMotion), C.c_int, C.c_int,
-                                              C.c_void_p, C.c_void_p]
-        L.fiasco_finish_predicted_frame.argtypes = [C.POINTER(ffi._Wfa), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+                                              C.c_void_p, C.c_void_p, C.c_void_p]
+        L.fiasco_finish_predicted_frame.argtypes = [C.POINTER(ffi._Wfa)] + [C.c_void_p] * 6
         L.fiasco_coder.argtypes = [C.POINTER(C.c_char_p), C.c_char_p, C.c_float, C.c_void_p]
         L.fiasco_c_options_new.restype = C.c_void_p
         L.fiasco_c_options_delete.argtypes = [C.c_void_p]
@@ -110,8 +114,9 @@ def write_video_stream(path, params, wfas, p_min_level=6, p_max_level=10, search
         arr[i], k = wfa_struct(w)
         keep.append(k)
         mot[i].frame_type = int(w.get("frame_type", 0))
+        mot[i].frame_number = int(w.get("frame_number", i))
         if mot[i].frame_type:
-            for name, dt in (("mv_type", np.int8), ("mv_fx", np.int8), ("mv_fy", np.int8), ("delta_state", np.uint8)):
+            for name, dt in _MOTION_ARRAYS:
                 a = np.ascontiguousarray(w[name], dtype=dt)
                 k[name] = a
                 setattr(mot[i], name, a.ctypes.data)
@@ -119,7 +124,7 @@ def write_video_stream(path, params, wfas, p_min_level=6, p_max_level=10, search
         raise RuntimeError("fiasco_write_video_stream: " + error_message())
 
 
-def regenerate_frame(w, width, height, past=None):
+def regenerate_frame(w, width, height, past=None, future=None):
     """The grey frame an automaton describes, int16 (h, w) in the coder's pixel format
     (fiasco_regenerate_frame); predicted frames ("frame_type" 1) need the previous regenerated frame."""
     L = load()
@@ -127,14 +132,16 @@ def regenerate_frame(w, width, height, past=None):
     mot = FrameMotion()
     mot.frame_type = int(w.get("frame_type", 0))
     if mot.frame_type:
-        for name, dt in (("mv_type", np.int8), ("mv_fx", np.int8), ("mv_fy", np.int8), ("delta_state", np.uint8)):
+        for name, dt in _MOTION_ARRAYS:
             a = np.ascontiguousarray(w[name], dtype=dt)
             keep[name] = a
             setattr(mot, name, a.ctypes.data)
         past = np.ascontiguousarray(past, np.int16)
+        future = np.ascontiguousarray(future, np.int16) if future is not None else None
     out = np.zeros((height, width), np.int16)
     if not L.fiasco_regenerate_frame(C.byref(s), C.byref(mot), width, height,
-                                     past.ctypes.data if past is not None else None, out.ctypes.data):
+                                     past.ctypes.data if past is not None else None,
+                                     future.ctypes.data if future is not None else None, out.ctypes.data):
         raise RuntimeError("fiasco_regenerate_frame: " + error_message())
     return out
 
@@ -145,13 +152,12 @@ def finish_predicted_frame(w):
     L = load()
     w = {k: (np.array(v, copy=True) if isinstance(v, np.ndarray) else v) for k, v in w.items()}
     s, keep = wfa_struct(w)
-    extra = {name: np.ascontiguousarray(w[name], dtype=dt)
-             for name, dt in (("mv_type", np.int8), ("mv_fx", np.int8), ("mv_fy", np.int8), ("delta_state", np.uint8))}
-    n = L.fiasco_finish_predicted_frame(C.byref(s), extra["mv_type"].ctypes.data, extra["mv_fx"].ctypes.data,
-                                        extra["mv_fy"].ctypes.data, extra["delta_state"].ctypes.data)
+    extra = {name: np.ascontiguousarray(w[name], dtype=dt) for name, dt in _MOTION_ARRAYS}
+    n = L.fiasco_finish_predicted_frame(C.byref(s), *[extra[name].ctypes.data for name, _ in _MOTION_ARRAYS])
     if not n:
         raise RuntimeError("fiasco_finish_predicted_frame: " + error_message())
-    out = {"states": n, "basis_states": s.basis_states, "root_state": s.root_state, "frame_type": w.get("frame_type", 0)}
+    out = {"states": n, "basis_states": s.basis_states, "root_state": s.root_state, "frame_type": w.get("frame_type", 0),
+           "frame_number": w.get("frame_number", 0)}
     for name, a in list(keep.items()) + list(extra.items()):
         out[name] = a[:n]
     return out

@@ -44,15 +44,16 @@ int fiasco_write_stream (const char *filename, const fiasco_stream_info_t *info,
 
 /*
  *  Predicted frames (reference: mv_t / delta_state of wfa_t, codec/wfa.h:62-71,126,137): what a
- *  P frame's automaton carries beside the fields of fb200_wfa_t.  Arrays are [states][2]
- *  (mv_*) and [states] (delta_state); frame_type 0 = intra (the pointers may be NULL), 1 =
- *  predicted from the previous frame.
+ *  predicted frame's automaton carries beside the fields of fb200_wfa_t.  Arrays are [states][2]
+ *  (mv_*) and [states] (delta_state); for intra frames the pointers may be NULL.
  */
 typedef struct fiasco_frame_motion
 {
-   int		  frame_type;
-   const int8_t	 *mv_type;	/* 0 none, 1 forward */
+   int		  frame_type;	/* 0 intra, 1 predicted (P), 2 bidirectional (B) */
+   int		  frame_number;	/* display number: sequences with B frames are coded out of order */
+   const int8_t	 *mv_type;	/* 0 none, 1 forward, 2 backward, 3 interpolated */
    const int8_t	 *mv_fx, *mv_fy;
+   const int8_t	 *mv_bx, *mv_by;	/* backward vectors (B frames), else may be NULL */
    const uint8_t *delta_state;	/* states that describe a prediction error */
 } fiasco_frame_motion_t;
 
@@ -71,10 +72,12 @@ int fiasco_write_video_stream (const char *filename, const fiasco_stream_info_t 
  *  Regenerate the grey frame an automaton describes, in the coder's pixel format (shorts, 12.4
  *  fixed point), the way the reference coder does after every frame of a sequence (decode_image,
  *  codec/decoder.c:412; restore_mc, codec/motion.c:37, when 'motion' says the frame is predicted
- *  from 'past').  out / past: width * height shorts.  Returns 1 on success, 0 on failure.
+ *  from 'past' and, for B frames, 'future').  out / past / future: width * height shorts.  Returns 1 on
+ *  success, 0 on failure.
  */
 int fiasco_regenerate_frame (const fb200_wfa_t *wfa, const fiasco_frame_motion_t *motion,
-			     int width, int height, const int16_t *past, int16_t *out);
+			     int width, int height, const int16_t *past, const int16_t *future,
+			     int16_t *out);
 
 /*
  *  Finish the automaton of a predicted frame the way the device will leave it:
@@ -84,7 +87,7 @@ int fiasco_regenerate_frame (const fb200_wfa_t *wfa, const fiasco_frame_motion_t
  *  [states].  Returns the new number of states, 0 on failure.
  */
 int fiasco_finish_predicted_frame (fb200_wfa_t *wfa, int8_t *mv_type, int8_t *mv_fx, int8_t *mv_fy,
-				   uint8_t *delta_state);
+				   int8_t *mv_bx, int8_t *mv_by, uint8_t *delta_state);
 
 #ifdef __cplusplus
 }

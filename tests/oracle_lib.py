@@ -244,9 +244,10 @@ def encode_video(frames, quality=20.0, pattern="ippp", p_min_level=6, p_max_leve
 def struct_dict(st):
     """numpy view of a ctypes automaton (the fields the stream writer takes)."""
     n = st.states
-    d = {"states": n, "basis_states": st.basis_states, "root_state": st.root_state, "frame_type": st.frame_type}
+    d = {"states": n, "basis_states": st.basis_states, "root_state": st.root_state, "frame_type": st.frame_type,
+         "frame_number": st.frame_number}
     for name in ("final_distribution", "level_of_state", "domain_type", "tree", "x", "y", "into", "weight",
-                 "y_state", "y_column", "mv_type", "mv_fx", "mv_fy", "delta_state"):
+                 "y_state", "y_column", "mv_type", "mv_fx", "mv_fy", "mv_bx", "mv_by", "delta_state"):
         d[name] = np.ctypeslib.as_array(getattr(st, name))[:n].copy()
     return d
 

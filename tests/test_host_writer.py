@@ -103,7 +103,7 @@ def test_cfiasco_links_unchanged():
         assert s in sy
 
 
-@pytest.mark.parametrize("name", ["v160_q20_ippp", "v352_q30_ippip"])
+@pytest.mark.parametrize("name", ["v160_q20_ippp", "v352_q30_ippip", "v160_q20_ibbp"])
 def test_video_stream_is_byte_identical_to_reference(name, tmp_path):
     """Host half of the motion path: fiasco_write_video_stream() (frame types, the motion tree and
     vectors of output/mc.c, delta contexts of output/weights.c) writes the reference coder's bytes
@@ -168,3 +168,31 @@ def test_host_finishes_predicted_frames_with_holes():
         out = os.path.join(tmp, "v.fco")
         hostlib.write_video_stream(out, p, done)
         assert hashlib.md5(open(out, "rb").read()).hexdigest() == m["fco_md5"]
+
+
+def test_host_regenerates_b_frames_like_the_reference():
+    """B frames: forward, backward and interpolated motion compensation against the previous and the
+    future regenerated frame, frames in coding order, B frames serving as past references
+    (codec/coder.c:571-627): every regenerated frame of the golden IBBP sequence equals the reference's."""
+    m = O.manifest()["v160_q20_ibbp"]
+    frames = list(O.gen_frames.video(m["frames"], m["width"], m["height"]))
+    ws, _ = O.encode_video(frames, quality=m["quality"], pattern=m["pattern"])
+    past = future = reconst = None
+    future_frame, expected, seen = False, 0, set()
+    assert [w["_struct"].frame_number for w in ws] == [0, 3, 1, 2, 4, 6, 5]
+    for k, w in enumerate(ws):
+        d = O.struct_dict(w["_struct"])
+        if d["frame_type"] == 0:
+            past = future = reconst = None
+        elif d["frame_type"] == 1:
+            past, future, reconst = reconst, None, None
+        elif future_frame:
+            future, reconst = reconst, None
+        else:
+            past, reconst = reconst, None
+        seen.add(d["frame_number"])
+        future_frame = d["frame_number"] > expected
+        while expected in seen:
+            expected += 1
+        reconst = hostlib.regenerate_frame(d, m["width"], m["height"], past, future)
+        assert hashlib.md5(reconst.tobytes()).hexdigest() == m["decoded_md5"][k], "coded frame %d" % k
