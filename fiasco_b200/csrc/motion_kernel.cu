@@ -21,6 +21,7 @@
 #include <stdint.h>
 #include <cuda_runtime.h>
 #include "fiasco_b200.h"
+#include "tile_kernel.cuh"
 
 namespace {
 
@@ -28,7 +29,7 @@ __global__ void __launch_bounds__ (256)
 fiasco_norms_kernel (const int16_t *orig, const int16_t *past, int width, int height,
 		     int bw, int bh, int sr, float *norms)
 {
-   extern __shared__ int16_t sm [];
+   FB_DYN_SMEM (int16_t, sm);
    const int bx = blockIdx.x, by = blockIdx.y;
    const int x0 = bx * bw, y0 = by * bh;
    const int ww = bw + 2 * sr, wh = bh + 2 * sr;	/* reference window */
@@ -124,8 +125,8 @@ fb200_motion_norms (int device, const int16_t *orig, const int16_t *past, int wi
    MN_TRY (cudaEventCreate (&e0));
    MN_TRY (cudaEventCreate (&e1));
    MN_TRY (cudaEventRecord (e0));
-   fiasco_norms_kernel<<<dim3 (nbx, nby), 256, smem>>> (d_orig, d_past, width, height, bw, bh,
-							search_range, d_norms);
+   FB_LAUNCH (fiasco_norms_kernel, dim3 (nbx, nby), 256, smem, 0, d_orig, d_past, width, height, bw, bh,
+	      search_range, d_norms);
    MN_TRY (cudaGetLastError ());
    MN_TRY (cudaEventRecord (e1));
    MN_TRY (cudaEventSynchronize (e1));

@@ -542,10 +542,15 @@ template <int NT>
 __device__ __forceinline__ void
 cta_copy_f32_async (float *dst_smem, const float *src, unsigned nfloats)
 {
+#ifdef FB200_EMU		/* tests/emu: the copy is synchronous */
+   for (unsigned i = threadIdx.x; i < (nfloats >> 2); i += NT)
+      ((uint4 *) dst_smem) [i] = ((const uint4 *) src) [i];
+#else
    const unsigned saddr = (unsigned) __cvta_generic_to_shared (dst_smem);
 
    for (unsigned i = threadIdx.x; i < (nfloats >> 2); i += NT)
       asm volatile ("cp.async.cg.shared.global [%0], [%1], 16;" :: "r" (saddr + i * 16), "l" (src + i * 4) : "memory");
+#endif
 }
 
 /* one float from global to shared memory, asynchronously (a gather that costs no register
@@ -553,15 +558,21 @@ cta_copy_f32_async (float *dst_smem, const float *src, unsigned nfloats)
 __device__ __forceinline__ void
 gather_f32_async (float *dst_smem, const float *src)
 {
+#ifdef FB200_EMU
+   *dst_smem = *src;
+#else
    asm volatile ("cp.async.ca.shared.global [%0], [%1], 4;"
 		 :: "r" ((unsigned) __cvta_generic_to_shared (dst_smem)), "l" (src) : "memory");
+#endif
 }
 
 __device__ __forceinline__ void
 async_wait_all (void)
 {
+#ifndef FB200_EMU
    asm volatile ("cp.async.commit_group;" ::: "memory");
    asm volatile ("cp.async.wait_group 0;" ::: "memory");
+#endif
 }
 
 /*
@@ -1033,8 +1044,7 @@ cta_state_products (const DevParams &P, const TileWs &W, const Sh &sh, unsigned 
 	 /* rows are 16-byte aligned at both ends; the padded length stays inside the table row */
 	 cta_copy_f32_async<NT> (row, src, (unsigned) stride);
       }
-      asm volatile ("cp.async.commit_group;" ::: "memory");
-      asm volatile ("cp.async.wait_group 0;" ::: "memory");
+      async_wait_all ();
       __syncthreads ();
       for (unsigned t = tid; t <= s; t += NT)
       {
@@ -2481,7 +2491,7 @@ template <int NT>
 __global__ void __launch_bounds__ (NT, (NT >= 512 ? 1 : NT >= 256 ? 2 : NT >= 128 ? FB200_MINB : 5))
 fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
 {
-   extern __shared__ __align__ (16) unsigned char smem_raw [];
+   FB_DYN_SMEM (unsigned char, smem_raw);
    /* the tile's pointer table lives in shared memory: 19 pointers are 38 registers that the
       pursuit loops need more urgently */
    __shared__ TileWs s_W;
@@ -2502,8 +2512,10 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
 
       if (threadIdx.x == 0)
       {
-	 unsigned smid;
+	 unsigned smid = 0;
+#ifndef FB200_EMU
 	 asm volatile ("mov.u32 %0, %%smid;" : "=r" (smid));
+#endif
 	 int i = (int) ((smid * 4u) % (unsigned) P.n_slots);
 	 while (atomicCAS (P.slot_flags + i, 0, 1) != 0)
 	    i = i + 1 == P.n_slots ? 0 : i + 1;
@@ -2799,7 +2811,7 @@ launch_nt (const DevParams &p_in, const TileWs *d_ws, int n_tiles, cudaStream_t 
       if (cv)
 	 cudaFuncSetAttribute (fiasco_tile_kernel<NT>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi (cv));
    }
-   fiasco_tile_kernel<NT><<<n_tiles, NT, smem, stream>>> (p, d_ws);
+   FB_LAUNCH (fiasco_tile_kernel<NT>, n_tiles, NT, smem, stream, p, d_ws);
    return cudaGetLastError ();
 }
 
@@ -2853,6 +2865,6 @@ cudaError_t
 fb_launch_probe (int kind, int n, const float *f, const int *a, const int *b,
 		 const int *c, int *out_i, float *out_f)
 {
-   fiasco_probe_kernel<<<(n + 255) / 256, 256>>> (kind, n, f, a, b, c, out_i, out_f);
+   FB_LAUNCH (fiasco_probe_kernel, (n + 255) / 256, 256, 0, 0, kind, n, f, a, b, c, out_i, out_f);
    return cudaGetLastError ();
 }

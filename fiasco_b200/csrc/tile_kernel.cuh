@@ -9,6 +9,21 @@
 #include <cuda_runtime.h>
 #include "fiasco_b200.h"
 
+/*
+ *  Kernel launch and dynamic shared memory, spelled so that the CPU-only test suite can compile
+ *  these sources as plain C++ against tests/emu/cuda_runtime.h (test infrastructure: a fibre
+ *  per CUDA thread; never built into the product).
+ */
+#ifdef FB200_EMU
+#define FB_LAUNCH(kernel, grid, block, smem, stream, ...) \
+   emu_launch (grid, block, smem, [&] () { kernel (__VA_ARGS__); })
+#define FB_DYN_SMEM(type, name) type *name = (type *) emu_dyn_smem ()
+#else
+#define FB_LAUNCH(kernel, grid, block, smem, stream, ...) \
+   kernel<<<grid, block, smem, stream>>> (__VA_ARGS__)
+#define FB_DYN_SMEM(type, name) extern __shared__ __align__ (16) type name []
+#endif
+
 #define FB_MAXEDGES  5
 #define FB_NO_EDGE   (-1)
 #define FB_RANGE     (-1)

@@ -3342,6 +3342,9 @@ fo_fill_norms_table (const int16_t *orig, const int16_t *past, unsigned width, u
    c->opt.height	       = (int) height;
    c->search_range	       = search_range;
    c->mc_forward_norms [level] = out;
+   /* out-of-frame displacements are zeroed in both tables whatever the frame type */
+   c->mc_backward_norms [level] = calloc ((size_t) 4 * search_range * search_range, sizeof (float));
    fill_norms_table (x0, y0, level, c);
+   free (c->mc_backward_norms [level]);
    free (c);
 }

@@ -1,0 +1,214 @@
+/*
+ *  emu_runtime.cpp -- TEST INFRASTRUCTURE (see tests/emu/cuda_runtime.h): the fibre scheduler
+ *  that runs one CUDA thread block at a time on one OS thread.
+ *
+ *  Every CUDA thread of the block is a fibre with its own stack; a fibre runs until it reaches
+ *  a rendezvous (block barrier or warp collective) that is not complete yet, then the next
+ *  fibre runs.  The last arrival completes the rendezvous and simply goes on.  Single OS
+ *  thread: no data races, fully deterministic.  x86-64 only (hand-written context switch).
+ */
+#include "cuda_runtime.h"
+#include <stdio.h>
+#include <time.h>
+#include <vector>
+
+#if !defined(__x86_64__)
+#error "the emulator's context switch is written for x86-64"
+#endif
+
+emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
+
+extern "C" void emu_switch (void **save_sp, void *new_sp);
+asm (".text\n"
+     ".globl emu_switch\n"
+     ".type emu_switch,@function\n"
+     "emu_switch:\n"
+     "  pushq %rbp\n  pushq %rbx\n  pushq %r12\n  pushq %r13\n  pushq %r14\n  pushq %r15\n"
+     "  movq %rsp, (%rdi)\n"
+     "  movq %rsi, %rsp\n"
+     "  popq %r15\n  popq %r14\n  popq %r13\n  popq %r12\n  popq %rbx\n  popq %rbp\n"
+     "  ret\n"
+     ".size emu_switch,.-emu_switch\n");
+
+namespace {
+
+enum { STACK_BYTES = 192 * 1024 };
+
+struct Warp
+{
+   unsigned count, gen;
+   unsigned slot [2][32];
+};
+
+struct Block
+{
+   int	    n, alive, cur;
+   unsigned bar_count, bar_gen;
+   std::vector<void *> sp;
+   std::vector<char>   done;
+   std::vector<Warp>   warps;
+   void	   *main_sp;
+   const std::function<void ()> *body;
+};
+
+Block	       B;
+char	      *g_stacks;
+size_t	       g_stacks_n;
+unsigned char *g_smem;
+
+void
+switch_to_next (void)
+{
+   const int from = B.cur;
+   int	     next = from;
+
+   if (B.alive == 0)
+   {
+      B.cur = -1;
+      emu_switch (&B.sp [from], B.main_sp);
+      return;
+   }
+   do
+      next = next + 1 == B.n ? 0 : next + 1;
+   while (B.done [next]);
+   if (next == from)
+   {
+      fprintf (stderr, "emu: deadlock -- thread %d waits for a rendezvous nobody else can reach\n", from);
+      abort ();
+   }
+   B.cur       = next;
+   threadIdx.x = (unsigned) next;
+   emu_switch (&B.sp [from], B.sp [next]);
+}
+
+void
+fibre_main (void)
+{
+   (*B.body) ();
+   B.done [B.cur] = 1;
+   B.alive--;
+   if (B.alive && B.bar_count == (unsigned) B.alive)	/* the others wait at a barrier */
+   {
+      B.bar_count = 0;
+      B.bar_gen++;
+   }
+   switch_to_next ();
+   abort ();			/* a finished fibre is never resumed */
+}
+
+} /* namespace */
+
+void
+emu_syncthreads (void)
+{
+   const unsigned gen = B.bar_gen;
+
+   if (++B.bar_count == (unsigned) B.alive)
+   {
+      B.bar_count = 0;
+      B.bar_gen++;
+      return;
+   }
+   while (B.bar_gen == gen)
+      switch_to_next ();
+}
+
+unsigned
+emu_warp_exchange (unsigned value, int kind, int arg)
+{
+   const unsigned tid  = threadIdx.x;
+   const unsigned lane = tid & 31u;
+   Warp		 &w    = B.warps [tid >> 5];
+   const unsigned gen  = w.gen, buf = gen & 1u;
+   const unsigned lanes = (tid | 31u) < (unsigned) B.n ? 32u : (unsigned) B.n - (tid & ~31u);
+
+   w.slot [buf][lane] = value;
+   if (++w.count == lanes)
+   {
+      w.count = 0;
+      w.gen++;
+   }
+   else
+      while (w.gen == gen)
+	 switch_to_next ();
+   switch (kind)
+   {
+      case 0:
+	 return w.slot [buf][(unsigned) arg & 31u];
+      case 1:
+	 return lane >= (unsigned) arg ? w.slot [buf][lane - (unsigned) arg] : value;
+      case 2:
+      {
+	 unsigned m = 0;
+	 for (unsigned l = 0; l < lanes; l++)
+	    m |= (w.slot [buf][l] ? 1u : 0u) << l;
+	 return m;
+      }
+      default:
+	 return 0;
+   }
+}
+
+unsigned char *
+emu_dyn_smem (void)
+{
+   return g_smem;
+}
+
+long long
+clock64 (void)
+{
+   struct timespec ts;
+   clock_gettime (CLOCK_MONOTONIC, &ts);
+   return (long long) ts.tv_sec * 1000000000LL + ts.tv_nsec;
+}
+
+void
+emu_launch (emu_dim3 grid, emu_dim3 block, size_t smem, const std::function<void ()> &body)
+{
+   const int n = (int) block.x;
+
+   if (!g_smem && posix_memalign ((void **) &g_smem, 256, 256 * 1024))
+      abort ();
+   if (smem > 256 * 1024 || block.y != 1 || block.z != 1)
+   {
+      fprintf (stderr, "emu: launch shape not supported\n");
+      abort ();
+   }
+   if (g_stacks_n < (size_t) n)
+   {
+      free (g_stacks);
+      if (posix_memalign ((void **) &g_stacks, 4096, (size_t) n * STACK_BYTES))
+	 abort ();
+      g_stacks_n = (size_t) n;
+   }
+   gridDim  = grid;
+   blockDim = block;
+   for (unsigned by = 0; by < grid.y; by++)
+      for (unsigned bx = 0; bx < grid.x; bx++)
+      {
+	 blockIdx = emu_dim3 (bx, by, 0);
+	 memset (g_smem, 0xcd, smem);	/* shared memory starts undefined */
+	 B.n = B.alive = n;
+	 B.bar_count = B.bar_gen = 0;
+	 B.sp.assign ((size_t) n, NULL);
+	 B.done.assign ((size_t) n, 0);
+	 B.warps.assign ((size_t) (n + 31) / 32, Warp ());
+	 B.body = &body;
+	 for (int t = 0; t < n; t++)
+	 {
+	    /* initial frame: six callee-saved registers, the entry point, a dummy return slot;
+	       after the ret the stack pointer is 8 mod 16 as at any function entry */
+	    void **top = (void **) (g_stacks + (size_t) (t + 1) * STACK_BYTES);
+	    void **sp  = top - 8;
+	    for (int i = 0; i < 6; i++)
+	       sp [i] = NULL;
+	    sp [6] = (void *) fibre_main;
+	    sp [7] = NULL;
+	    B.sp [t] = sp;
+	 }
+	 B.cur	     = 0;
+	 threadIdx.x = 0;
+	 emu_switch (&B.main_sp, B.sp [0]);
+      }
+}
