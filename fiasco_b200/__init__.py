@@ -7,6 +7,7 @@ bench.py; it never computes anything itself and raises if the CUDA library is mi
 """
 from .ffi import (  # noqa: F401
     FB200Error,
+    Motion,
     Params,
     TileEncoder,
     device_count,

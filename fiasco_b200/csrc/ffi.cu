@@ -15,6 +15,8 @@
 struct fb200_ctx
 {
    fb200_params_t params;
+   fb200_motion_t motion;	/* frame_type 0: a context for intra frames */
+   int16_t	 *d_past;	/* [tiles][w*h] reference frames (predicted frames only) */
    DevParams	  dp;
    int		  max_tiles, device, nt;
    size_t	  smem;
@@ -185,7 +187,7 @@ default_capacity (const fb200_params_t *p)
 }
 
 static int
-derive (const fb200_params_t *p, DevParams *d, char *err, size_t errlen)
+derive (const fb200_params_t *p, const fb200_motion_t *mo, DevParams *d, char *err, size_t errlen)
 {
    memset (d, 0, sizeof *d);
    if (p->level < 1 || p->level > FB200_MAXLEVEL || p->lc_max_level > 12
@@ -227,6 +229,28 @@ derive (const fb200_params_t *p, DevParams *d, char *err, size_t errlen)
    d->dc_range	= p->dc_rpf_range;
    d->second_domain_block = p->second_domain_block;
    d->s_cap = p->state_capacity > 0 ? p->state_capacity : default_capacity (p);
+   if (mo && mo->frame_type)
+   {
+      if (mo->frame_type != 1 || p->bands != 1 || mo->search_range < 1 || mo->search_range > 16)
+      {
+	 set_err (err, errlen, "predicted frames: P frames of grey sequences, search range 1..16");
+	 return FB200_EUNSUPPORTED;
+      }
+      /* prediction levels are a subset of the range levels (coder.c:284-290) */
+      d->motion = mo->frame_type;
+      d->p_min	= mo->p_min_level > d->lc_min ? mo->p_min_level : d->lc_min;
+      d->p_max	= mo->p_max_level < d->lc_max ? mo->p_max_level : d->lc_max;
+      if (d->p_min > d->p_max)
+	 d->p_min = d->p_max;
+      d->sr = mo->search_range;
+      /* states of losing alternatives stay behind as holes until the host closes them: up to
+	 ~3x the final states while a frame is built; the motion search also
+	 borrows 2 x 512 floats of the pursuit's work arrays */
+      if (p->state_capacity <= 0)
+	 d->s_cap = 3 * d->s_cap;
+      if (d->s_cap < 512)
+	 d->s_cap = 512;
+   }
    if (d->s_cap < 8)
       d->s_cap = 8;
    if (d->s_cap > FB200_MAXSTATES)
@@ -238,6 +262,13 @@ derive (const fb200_params_t *p, DevParams *d, char *err, size_t errlen)
    d->blob_len	   = MB_COUNTS + d->aac_dc_size
 		     + (d->lc_max - d->lc_min + 1) * d->aac_lvl_size;
    d->blob_len	   = (d->blob_len + 7) / 8 * 8;
+   d->blob_half	   = d->blob_len;
+   d->n_frames	   = d->level - d->lc_min + 2;
+   if (d->motion)
+   {
+      d->blob_len  = 2 * d->blob_half;	/* normal and delta model sets */
+      d->n_frames += d->p_max - d->lc_min + 2;	/* nested pass over the prediction error */
+   }
    d->big	   = d->s_cap > 768 ? 3 : 0;
    {
       const char *e = getenv ("FB200_BIG");	/* experiments only */
@@ -255,7 +286,7 @@ up256 (size_t x)
 
 /* carve the private tables of one tile out of d_work */
 static size_t
-work_layout (const DevParams &d, size_t *off /* [7] */)
+work_layout (const DevParams &d, size_t *off /* [12] */)
 {
    size_t o = 0, sc = (size_t) d.s_cap;
 
@@ -263,15 +294,26 @@ work_layout (const DevParams &d, size_t *off /* [7] */)
    off [1] = o; o += up256 ((size_t) d.tn * sc * 4);			/* T */
    off [2] = o; o += up256 ((size_t) d.nlev * sc * sc * 4);		/* SS */
    off [3] = o; o += up256 ((size_t) d.nlev * sc * 4);			/* diag */
-   off [4] = o; o += up256 ((size_t) FB_MAXDEPTH * 2 * d.blob_len * 2);	/* snap */
+   off [4] = o; o += up256 ((size_t) (d.n_frames > FB_MAXDEPTH ? d.n_frames : FB_MAXDEPTH)
+			   * 3 * d.blob_len * 2);				/* snap */
    off [5] = o; o += up256 (sc * sizeof (Trans));			/* trans */
    off [6] = o; o += up256 ((sc + 1) * 4 * FB_MAXEDGES);		/* Gglob */
+   for (int i = 7; i < 12; i++)
+      off [i] = o;
+   if (d.motion)
+   {
+      off [7]  = o; o += up256 ((size_t) d.tn * sc * 4);			/* T2 */
+      off [8]  = o; o += up256 ((size_t) (d.p_max - d.p_min + 1) * 4 * d.sr * d.sr * 4); /* norms */
+      off [9]  = o; o += up256 (((size_t) 1 << d.lc_max) * 4);		/* pix2 */
+      off [10] = o; o += up256 ((size_t) d.tn * 4);				/* norm2 */
+      off [11] = o; o += up256 (sc);						/* saved_dt */
+   }
    return o;
 }
 
 /* the automaton of one tile, contiguous so that it travels in one copy */
 static size_t
-wfa_layout (const DevParams &d, size_t *off /* [10] */)
+wfa_layout (const DevParams &d, size_t *off /* [13] */)
 {
    size_t o = 0, sc = (size_t) d.s_cap;
 
@@ -285,6 +327,13 @@ wfa_layout (const DevParams &d, size_t *off /* [10] */)
    off [7] = o; o += up256 (sc);		/* level_of_state */
    off [8] = o; o += up256 (sc);		/* domain_type */
    off [9] = o; o += up256 (sc * 2);		/* y_column */
+   off [10] = off [11] = off [12] = o;
+   if (d.motion)
+   {
+      off [10] = o; o += up256 (sc * 2);	/* mv_type */
+      off [11] = o; o += up256 (sc * 2);	/* mv_fx */
+      off [12] = o; o += up256 (sc * 2);	/* mv_fy */
+   }
    return o;
 }
 
@@ -297,6 +346,7 @@ fb200_destroy (fb200_ctx_t *c)
    cudaFree (c->d_work);
    cudaFree (c->d_slot_flags);
    cudaFree (c->d_pix);
+   cudaFree (c->d_past);
    cudaFree (c->d_wfa);
    cudaFree (c->d_results);
    cudaFree (c->d_trace);
@@ -330,7 +380,7 @@ ctx_alloc (fb200_ctx_t *c, char *err, size_t errlen)
 	 return FB200_EINVAL;
       }
    }
-   size_t woff [7], aoff [10];
+   size_t woff [12], aoff [13];
    c->work_stride = work_layout (d, woff);
    c->wfa_block	  = wfa_layout (d, aoff);
    c->pix_elems	  = (size_t) d.bands * d.width * d.height;
@@ -357,6 +407,8 @@ ctx_alloc (fb200_ctx_t *c, char *err, size_t errlen)
    if (!c->d_pix)
    {
       CUDA_TRY (cudaMalloc (&c->d_pix, c->pix_elems * 2 * max_tiles));
+      if (d.motion)
+	 CUDA_TRY (cudaMalloc (&c->d_past, c->pix_elems * 2 * max_tiles));
       CUDA_TRY (cudaMalloc (&c->d_results, sizeof (TileResult) * max_tiles));
       CUDA_TRY (cudaMalloc (&c->d_ws, sizeof (TileWs) * max_tiles));
       CUDA_TRY (cudaMallocHost (&c->h_results, sizeof (TileResult) * max_tiles));
@@ -391,6 +443,18 @@ ctx_alloc (fb200_ctx_t *c, char *err, size_t errlen)
       w.level_of_state = (uint8_t *) (ab + aoff [7]);
       w.domain_type    = (uint8_t *) (ab + aoff [8]);
       w.y_column       = (uint8_t *) (ab + aoff [9]);
+      if (d.motion)
+      {
+	 w.past	    = c->d_past + c->pix_elems * t;
+	 w.T2	    = (float *) (wb + woff [7]);
+	 w.norms    = (float *) (wb + woff [8]);
+	 w.pix2	    = (float *) (wb + woff [9]);
+	 w.norm2    = (int *) (wb + woff [10]);
+	 w.saved_dt = (uint8_t *) (wb + woff [11]);
+	 w.mv_type  = (int8_t *) (ab + aoff [10]);
+	 w.mv_fx    = (int8_t *) (ab + aoff [11]);
+	 w.mv_fy    = (int8_t *) (ab + aoff [12]);
+      }
       w.result	       = c->d_results + t;
       w.trace	       = t == 0 ? c->d_trace : NULL;
    }
@@ -412,7 +476,7 @@ ctx_grow (fb200_ctx_t *c, char *err, size_t errlen)
    if (cap > FB200_MAXSTATES)
       cap = FB200_MAXSTATES;
    p.state_capacity = cap;
-   int rc = derive (&p, &d, err, errlen);
+   int rc = derive (&p, &c->motion, &d, err, errlen);
    if (rc)
       return rc;
    d.trace_cap = c->dp.trace_cap;
@@ -428,9 +492,32 @@ ctx_grow (fb200_ctx_t *c, char *err, size_t errlen)
    return ctx_alloc (c, err, errlen);
 }
 
+static int
+create_ctx (fb200_ctx_t **out, const fb200_params_t *p, const fb200_motion_t *mo, int max_tiles,
+	    int device, char *err, size_t errlen);
+
 extern "C" int
 fb200_create (fb200_ctx_t **out, const fb200_params_t *p, int max_tiles, int device,
 	      char *err, size_t errlen)
+{
+   return create_ctx (out, p, NULL, max_tiles, device, err, errlen);
+}
+
+extern "C" int
+fb200_create_predicted (fb200_ctx_t **out, const fb200_params_t *p, const fb200_motion_t *motion,
+			int max_tiles, int device, char *err, size_t errlen)
+{
+   if (!motion || motion->frame_type == 0)
+   {
+      set_err (err, errlen, "fb200_create_predicted: a frame type is required");
+      return FB200_EINVAL;
+   }
+   return create_ctx (out, p, motion, max_tiles, device, err, errlen);
+}
+
+static int
+create_ctx (fb200_ctx_t **out, const fb200_params_t *p, const fb200_motion_t *mo, int max_tiles,
+	    int device, char *err, size_t errlen)
 {
    if (!out || !p || max_tiles < 1)
    {
@@ -439,7 +526,7 @@ fb200_create (fb200_ctx_t **out, const fb200_params_t *p, int max_tiles, int dev
    }
    *out = NULL;
    DevParams d;
-   int	     rc = derive (p, &d, err, errlen);
+   int	     rc = derive (p, mo, &d, err, errlen);
    if (rc)
       return rc;
    if (fb200_device_count () <= device)
@@ -450,6 +537,8 @@ fb200_create (fb200_ctx_t **out, const fb200_params_t *p, int max_tiles, int dev
    }
    fb200_ctx_t *c = new fb200_ctx_t ();
    c->params	  = *p;
+   if (mo)
+      c->motion	  = *mo;
    c->dp	  = d;
    c->max_tiles	  = max_tiles;
    c->device	  = device;
@@ -574,7 +663,7 @@ fb200_download (fb200_ctx_t *c, int n_tiles, fb200_wfa_t *out, fb200_trace_rec_t
    cudaEventElapsedTime (&c->stats.d2h_ms, c->ev [4], c->ev [5]);
    c->stats.d2h_bytes = (sizeof (TileResult) + c->wfa_block) * n_tiles;
 
-   size_t aoff [10];
+   size_t aoff [13];
    wfa_layout (c->dp, aoff);
    int rc = FB200_OK;
    c->stats.ip_bytes = c->stats.mp_calls = c->stats.mp_steps = c->stats.pass2 = 0;
@@ -644,6 +733,12 @@ fb200_download (fb200_ctx_t *c, int n_tiles, fb200_wfa_t *out, fb200_trace_rec_t
       if (o.level_of_state)	memcpy (o.level_of_state, ab + aoff [7], n);
       if (o.domain_type)	memcpy (o.domain_type, ab + aoff [8], n);
       if (o.y_column)		memcpy (o.y_column, ab + aoff [9], n * 2);
+      if (c->dp.motion)
+      {
+	 if (o.mv_type)		memcpy (o.mv_type, ab + aoff [10], n * 2);
+	 if (o.mv_fx)		memcpy (o.mv_fx, ab + aoff [11], n * 2);
+	 if (o.mv_fy)		memcpy (o.mv_fy, ab + aoff [12], n * 2);
+      }
    }
    if (trace_len)
       *trace_len = 0;
@@ -697,6 +792,38 @@ fb200_encode_tiles (fb200_ctx_t *c, int n_tiles, const int16_t *const *planes,
 }
 
 extern "C" int
+fb200_encode_predicted (fb200_ctx_t *c, int n_tiles, const int16_t *const *planes,
+			const int16_t *const *past, fb200_wfa_t *out, char *err, size_t errlen)
+{
+   int rc;
+
+   if (!c || !c->dp.motion || !past || n_tiles < 1 || n_tiles > c->max_tiles)
+   {
+      set_err (err, errlen, "fb200_encode_predicted: needs a context of fb200_create_predicted() "
+	       "and one reference frame per tile");
+      return FB200_EINVAL;
+   }
+   c->dp.trace_cap = 0;
+   if ((rc = fb200_upload (c, n_tiles, planes, err, errlen)))
+      return rc;
+   for (int t = 0; t < n_tiles; t++)
+      CUDA_TRY (cudaMemcpyAsync (c->d_past + c->pix_elems * t, past [t], c->pix_elems * 2,
+				 cudaMemcpyHostToDevice, c->stream));
+   CUDA_TRY (cudaStreamSynchronize (c->stream));
+   c->stats.h2d_bytes += c->pix_elems * 2 * n_tiles;
+   for (;;)
+   {
+      if ((rc = fb200_launch (c, n_tiles, NULL, err, errlen)))
+	 return rc;
+      rc = fb200_download (c, n_tiles, out, NULL, 0, NULL, err, errlen);
+      if (rc != FB200_ECAPACITY || !c->auto_grow)
+	 return rc;
+      if ((rc = ctx_grow (c, err, errlen)))
+	 return rc;
+   }
+}
+
+extern "C" int
 fb200_resident_tiles (const fb200_ctx_t *c)
 {
    int sms = 0;
@@ -737,8 +864,12 @@ fb200_wfa_alloc (fb200_wfa_t *w, int capacity)
    w->weight		 = (float *) calloc ((size_t) capacity * 12, 4);
    w->y_state		 = (int16_t *) calloc ((size_t) capacity * 2, 2);
    w->y_column		 = (uint8_t *) calloc ((size_t) capacity * 2, 1);
+   w->mv_type		 = (int8_t *) calloc ((size_t) capacity * 2, 1);
+   w->mv_fx		 = (int8_t *) calloc ((size_t) capacity * 2, 1);
+   w->mv_fy		 = (int8_t *) calloc ((size_t) capacity * 2, 1);
    if (!w->final_distribution || !w->level_of_state || !w->domain_type || !w->tree
-       || !w->x || !w->y || !w->into || !w->weight || !w->y_state || !w->y_column)
+       || !w->x || !w->y || !w->into || !w->weight || !w->y_state || !w->y_column
+       || !w->mv_type || !w->mv_fx || !w->mv_fy)
    {
       fb200_wfa_free (w);
       return FB200_EINVAL;
@@ -761,6 +892,9 @@ fb200_wfa_free (fb200_wfa_t *w)
    free (w->weight);
    free (w->y_state);
    free (w->y_column);
+   free (w->mv_type);
+   free (w->mv_fx);
+   free (w->mv_fy);
    memset (w, 0, sizeof *w);
 }
 

@@ -231,6 +231,28 @@ struct Frame			/* one activation record of subdivide() */
    RangeRes child [2];
 };
 
+/* what a range of a predicted frame carries beside RangeRes (range_t, codec/cwfa.h:46-75) */
+struct RangeX
+{
+   float       mv_tree_bits, mv_coord_bits;
+   signed char mv_type, mv_fx, mv_fy, prediction;
+};
+
+/* activation record of subdivide() in a predicted frame, beside Frame */
+struct FrameX
+{
+   RangeX   lrange, child [2], prange_x;
+   RangeRes prange;		/* result of the nested pass over the prediction error */
+   float    r_mvt, r_mvc;	/* rrange sums of the motion bits */
+   int	    try_mc;		/* subdivide.c:141-147 */
+   int	    delta, prediction;	/* arguments of subdivide () */
+   int	    pred_done;		/* the prediction alternative has been tried (and lost) */
+   unsigned rec_states;		/* states after the first two alternatives */
+   unsigned last_state;
+   float    max_pred, pcosts, mvc;
+   int	    mx, my;
+};
+
 struct MpRes			/* mp_t, codec/approx.c:41-51 */
 {
    short indices [FB_MAXEDGES + 1];
@@ -293,6 +315,12 @@ struct ShHdr
    MpWork   w;
    RangeRes root;
    Frame   *frames;		/* [level - lc_min + 2] */
+   /* predicted frames */
+   FrameX  *fx;			/* [n_frames] or NULL */
+   RangeX   root_x;
+   int	    nest_base;		/* depth of the root record of the nested pass, or -1 */
+   int	    top;		/* level of node 0 of the product tree in use */
+   int	    best_i;		/* find_best_mv: winning displacement index */
 };
 
 static_assert (offsetof (ShHdr, tree_total) == offsetof (ShHdr, tree_counts) + FB200_MAXLEVEL * sizeof (unsigned),
@@ -314,6 +342,7 @@ struct Sh			/* pointers into dynamic shared memory */
    float   *qt_dc, *qt_lv;	/* [aac_dc_size], [aac_lvl_size]: btor (code), lib/rpf.c:113 */
    unsigned *tsnap;		/* [ndepth][2 * MAXLEVEL] tree-model snapshots of the DFS */
    Frame   *frames;
+   FrameX  *fx;			/* predicted frames only */
    int	    dcap;
    int	    scratch_len;	/* floats from num to the end of bnd / G: row scratch of append_state */
 };
@@ -321,7 +350,7 @@ struct Sh			/* pointers into dynamic shared memory */
 __host__ __device__ inline size_t align16 (size_t x) { return (x + 15) & ~(size_t) 15; }
 
 __host__ __device__ inline size_t
-smem_layout (const DevParams &p, int nt, size_t *off /* [16] */)
+smem_layout (const DevParams &p, int nt, size_t *off /* [20] */)
 {
    size_t o    = 0;
    size_t dcap = (size_t) p.s_cap + 1;
@@ -340,16 +369,18 @@ smem_layout (const DevParams &p, int nt, size_t *off /* [16] */)
    {
       /* model snapshots of the DFS stay on chip when they are small (default models:
 	 376 B each), else they live in the tile's global workspace */
-      const size_t need = (size_t) (p.level - p.lc_min + 2) * 2 * p.blob_len * 2;
+      const size_t need = (size_t) p.n_frames * (p.motion ? 3 : 2) * p.blob_len * 2;
       const bool on_chip = need <= 24 * 1024 && !(p.big & 2);
       off [11] = on_chip ? o : (size_t) -1;
       if (on_chip)
 	 o += align16 (need);
    }
    off [12] = o; o += align16 ((size_t) (p.aac_dc_size + p.aac_lvl_size) * 8);	/* log2 tables */
-   off [13] = o; o += align16 ((size_t) (p.level - p.lc_min + 2) * sizeof (Frame));	/* DFS frames */
+   off [13] = o; o += align16 ((size_t) p.n_frames * sizeof (Frame));	/* DFS frames */
    off [14] = o; o += align16 ((size_t) (p.aac_dc_size + p.aac_lvl_size) * 4);	/* quantiser tables */
-   off [15] = o; o += align16 ((size_t) (p.level - p.lc_min + 2) * 2 * FB200_MAXLEVEL * 4); /* tsnap */
+   off [15] = o; o += align16 ((size_t) p.n_frames * (p.motion ? 2 : 1) * 2 * FB200_MAXLEVEL * 4); /* tsnap */
+   off [16] = o; o += p.motion ? align16 ((size_t) p.n_frames * sizeof (FrameX)) : 0;
+   off [17] = off [18] = off [19] = o;
    return o;
 }
 
@@ -380,6 +411,7 @@ carve (unsigned char *base, const DevParams &p, int nt, float *gglob)
    s.qt_dc  = (float *) (base + off [14]);
    s.qt_lv  = s.qt_dc + p.aac_dc_size;
    s.tsnap  = (unsigned *) (base + off [15]);
+   s.fx	    = p.motion ? (FrameX *) (base + off [16]) : (FrameX *) 0;
    return s;
 }
 
@@ -585,7 +617,7 @@ async_wait_all (void)
 template <int NT>
 __device__ void
 cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
-	       unsigned node_root, int level_root)
+	       unsigned node_root, int level_root, int top)
 {
    const int	 tid	= threadIdx.x;
    const unsigned S	= sh.h->states;
@@ -600,7 +632,7 @@ cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
    {
       const unsigned nn	   = 1u << (level_root - l);
       const unsigned node0 = ((node_root + 1) << (level_root - l)) - 1;
-      const unsigned adr0  = node0 - ((1u << (P.lc_max - l)) - 1);
+      const unsigned adr0  = node0 - ((1u << (top - l)) - 1);
       const unsigned len   = 1u << l;
       const unsigned ns	   = S - from;
 
@@ -817,7 +849,7 @@ cta_init_range (const DevParams &P, const TileWs &W, const Sh &sh, unsigned x0,
       sh.h->ip_bytes += 4ull * size + 4ull * (63 + (unsigned) ((1 << (P.lc_max - P.il)) - 1)) * ns;
    }
    LAP (sh.h, LAP_PIX);
-   cta_compute_T<NT> (P, W, sh, 0, 0, P.lc_max);
+   cta_compute_T<NT> (P, W, sh, 0, 0, P.lc_max, P.lc_max);
 }
 
 /* exact fp32 left-to-right sum of squares of a node (approx.c:388-389) */
@@ -1578,7 +1610,7 @@ template <int NT>
 __device__ void
 cta_matching_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &mp,
 		      int level, unsigned image, unsigned address, float tree_bits,
-		      float price, int y_state_in, int excluded)
+		      float mv_tree_bits, float price, int y_state_in, int excluded)
 {
    const int	tid	 = threadIdx.x;
    MpWork      &w	 = sh.h->w;
@@ -1619,7 +1651,7 @@ cta_matching_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &
       w.size  = 1 << level;
       w.price = price;
       w.norm  = t0_node_norm (P, sh, image, address, level);
-      w.additional_bits = tree_bits + 0.0f + 0.0f + 0.0f + 0.0f;
+      w.additional_bits = tree_bits + mv_tree_bits + 0.0f + 0.0f + 0.0f;
       w.d0b [0] = t0_d0_bits (sh, 0, y_state, c_matrix_0, c_matrix_1);
       w.d0b [1] = t0_d0_bits (sh, 1, y_state, c_matrix_0, c_matrix_1);
       sh.h->mp_calls++;
@@ -1871,7 +1903,7 @@ template <int NT>
 __device__ void
 cta_approximate_range (const DevParams &P, const TileWs &W, const Sh &sh, float max_costs,
 		       float price, int y_state, RangeRes *out, int level, unsigned image,
-		       unsigned address, unsigned x, unsigned y)
+			       unsigned address, unsigned x, unsigned y, float mv_tree_bits)
 {
    ShHdr *h = sh.h;
 
@@ -1888,8 +1920,8 @@ cta_approximate_range (const DevParams &P, const TileWs &W, const Sh &sh, float 
 	 __syncthreads ();
       }
       /* (the prologue of the pursuit starts with thread-0 work followed by a barrier) */
-      cta_matching_pursuit<NT> (P, W, sh, m, level, image, address, out->tree_bits, price,
-				y_state, round ? (int) h->mp.indices [0] : -1);
+      cta_matching_pursuit<NT> (P, W, sh, m, level, image, address, out->tree_bits,
+				mv_tree_bits, price, y_state, round ? (int) h->mp.indices [0] : -1);
    }
    if (P.second_domain_block)
    {
@@ -1986,10 +2018,200 @@ cta_copy_s16 (short *dst, const short *src, int n)
 }
 
 /*****************************************************************************
+	motion compensation of predicted frames  (codec/mwfa.c, codec/prediction.c)
+*****************************************************************************/
+
+/* MPEG's code lengths of the vector components (mwfa.c:40-52, second column) */
+__constant__ unsigned char c_mv_code_length [33] =
+{11, 11, 11, 11, 11, 11, 10, 10, 10, 8, 8, 8, 7, 5, 4, 3, 1, 3, 4, 5, 7, 8, 8, 8, 10, 10, 10,
+ 11, 11, 11, 11, 11, 11};
+
+__device__ __forceinline__ float *
+norms_of_level (const DevParams &P, const TileWs &W, int level)
+{
+   return GP (W.norms) + (size_t) (level - P.p_min) * (4 * P.sr * P.sr);
+}
+
+/*
+ *  fill_norms_table (mwfa.c:544-602) for the block (x0, y0) of 'level': for every vector of the
+ *  search range the squared norm of (original - displaced reference) / 16 (get_mcpe / mcpe_norm,
+ *  mwfa.c:604-684), each summed in row order in fp32 by one thread; 0 for vectors that leave the
+ *  frame.
+ */
+template <int NT>
+__device__ void
+cta_fill_norms (const DevParams &P, const TileWs &W, unsigned x0, unsigned y0, int level)
+{
+   const int	  sr = P.sr, nd = 4 * sr * sr;
+   const int	  bw = (int) width_of_level (level), bh = (int) height_of_level (level);
+   float	 *out = norms_of_level (P, W, level);
+   const int16_t *orig = GP (W.pix), *past = GP (W.past);
+
+   for (int index = threadIdx.x; index < nd; index += NT)
+   {
+      const int mx = index % (2 * sr) - sr, my = index / (2 * sr) - sr;
+      float	norm = 0.0f;
+
+      if ((int) x0 + mx >= 0 && (int) x0 + mx + bw <= P.width
+	  && (int) y0 + my >= 0 && (int) y0 + my + bh <= P.height)
+	 for (int y = 0; y < bh; y++)
+	 {
+	    const int16_t *o = orig + (size_t) (y0 + y) * P.width + x0;
+	    const int16_t *r = past + (size_t) ((int) y0 + my + y) * P.width + ((int) x0 + mx);
+
+	    for (int x = 0; x < bw; x++)
+	    {
+	       const int16_t d = (int16_t) (o [x] - r [x]);
+	       const int     q = d / 16;
+
+	       norm += (float) (q * q);
+	    }
+	 }
+      out [index] = norm;
+   }
+   __syncthreads ();
+}
+
+/*
+ *  find_best_mv (mwfa.c:686-795), full-pixel search: the first vector in index order with the
+ *  least costs norm + (bits of the components) * price.  Result in h->best_i.
+ */
+template <int NT>
+__device__ void
+cta_find_best_mv (const DevParams &P, const TileWs &W, const Sh &sh, unsigned x0, unsigned y0,
+		  int level, float price)
+{
+   const int	sr = P.sr, nd = 4 * sr * sr;
+   const int	bw = (int) width_of_level (level), bh = (int) height_of_level (level);
+   const float *norms = norms_of_level (P, W, level);
+   float	best  = FB_MAXCOSTS;
+   int		besti = -1;
+
+   for (int index = threadIdx.x; index < nd; index += NT)
+   {
+      const int mx = index % (2 * sr) - sr, my = index / (2 * sr) - sr;
+
+      if ((int) x0 + mx >= 0 && (int) y0 + my >= 0
+	  && (int) x0 + mx + bw <= P.width && (int) y0 + my + bh <= P.height)
+      {
+	 const float costs = norms [index] + ((float) c_mv_code_length [mx + sr]
+					      + (float) c_mv_code_length [my + sr]) * price;
+	 if (costs < best)
+	 {
+	    best  = costs;
+	    besti = index;
+	 }
+      }
+   }
+   /* the pursuit's work arrays are idle here */
+   sh.num [threadIdx.x]		  = best;
+   ((int *) sh.den) [threadIdx.x] = besti;
+   __syncthreads ();
+   if (threadIdx.x == 0)
+   {
+      float m  = FB_MAXCOSTS;
+      int   mi = -1;
+
+      for (int t = 0; t < NT; t++)
+      {
+	 const float c = sh.num [t];
+	 const int   i = ((const int *) sh.den) [t];
+
+	 if (i >= 0 && (c < m || (c == m && i < mi)))
+	 {
+	    m  = c;
+	    mi = i;
+	 }
+      }
+      sh.h->best_i = mi;
+   }
+   __syncthreads ();
+}
+
+/*
+ *  The prediction error of the block (x0, y0) of 'level' for the vector (mx, my) (get_mcpe,
+ *  mwfa.c:604-649), cut to bintree order as floats (cut_to_bintree, subdivide.c:504-541), with
+ *  the sums of squares of its nodes: node 0 is the whole block (top = level).
+ */
+template <int NT>
+__device__ void
+cta_mcpe_range (const DevParams &P, const TileWs &W, const Sh &cs, unsigned x0, unsigned y0,
+		int level, int mx, int my)
+{
+   const int	  tid  = threadIdx.x;
+   const unsigned size = 1u << level;
+   const int16_t *orig = GP (W.pix), *past = GP (W.past);
+
+   for (unsigned i = tid; i < size; i += NT)
+   {
+      unsigned yy = 0, xx = 0;
+      for (int b = 0; b < 11; b++)
+      {
+	 yy |= ((i >> (2 * b)) & 1u) << b;
+	 xx |= ((i >> (2 * b + 1)) & 1u) << b;
+      }
+      const unsigned px = x0 + xx, py = y0 + yy;
+      const int16_t  d	= (int16_t) (orig [(size_t) py * P.width + px]
+				     - past [(size_t) ((int) py + my) * P.width + ((int) px + mx)]);
+      cs.pixels [i] = (float) ((int) d / 16);
+   }
+   __syncthreads ();
+   {
+      const unsigned nleaf = 1u << (level - P.lmin);
+      const unsigned len   = 1u << P.lmin;
+
+      for (unsigned k = tid; k < nleaf; k += NT)
+      {
+	 int acc = 0;
+	 for (unsigned i = 0; i < len; i++)
+	 {
+	    int v = (int) cs.pixels [k * len + i];
+	    acc += v * v;
+	 }
+	 cs.norm_i [nleaf - 1 + k] = acc;
+      }
+      __syncthreads ();
+      for (int l = P.lmin + 1; l <= level; l++)
+      {
+	 const unsigned nn    = 1u << (level - l);
+	 const unsigned node0 = nn - 1;
+	 for (unsigned k = tid; k < nn; k += NT)
+	    cs.norm_i [node0 + k] = cs.norm_i [2 * (node0 + k) + 1] + cs.norm_i [2 * (node0 + k) + 2];
+	 __syncthreads ();
+      }
+   }
+}
+
+/*****************************************************************************
 		   the bintree recursion  (codec/subdivide.c:60-502)
 *****************************************************************************/
 
-enum { ST_CHILD_T = 16, ST_CHILD2 = 17 };
+enum { ST_CHILD_T = 16, ST_CHILD2 = 17,
+       /* predicted frames */
+       ST_AFTER_CHILD2 = 18, ST_NORMS_UP = 19, ST_FILL_CHILD = 20, ST_PRED_DONE = 21 };
+
+/* where the activation record at 'depth' leaves its range: the parent's child slot, the root
+   range, or -- for the root of a nested pass -- the prediction range of the record below */
+template <bool MOTION>
+__device__ __forceinline__ RangeRes *
+res_slot (ShHdr *h, int depth)
+{
+   if (depth == 0)
+      return &h->root;
+   if (MOTION && depth == h->nest_base)
+      return &h->fx [depth - 1].prange;
+   return &h->frames [depth - 1].child [h->frames [depth - 1].label];
+}
+
+__device__ __forceinline__ RangeX *
+resx_slot (ShHdr *h, int depth)
+{
+   if (depth == 0)
+      return &h->root_x;
+   if (depth == h->nest_base)
+      return &h->fx [depth - 1].prange_x;
+   return &h->fx [depth - 1].child [h->frames [depth - 1].label];
+}
 
 /*
  *  Thread 0: run the scalar part of subdivide()'s control flow -- returns, cost
@@ -1997,9 +2219,13 @@ enum { ST_CHILD_T = 16, ST_CHILD2 = 17 };
  *  exits -- until the block as a whole is needed again:
  *    ST_ENTER    a visible range of level >= 3: snapshot, linear combination, ...
  *    ST_CHILD_T  products of the states born in child 0 for child 1's subtree
- *    ST_DECIDE   restore / adopt models or append a new state
+ *    ST_DECIDE   restore / adopt models or append a new state (predicted frames: the
+ *		  motion compensated alternative first)
+ *    ST_NORMS_UP / ST_FILL_CHILD / ST_PRED_DONE  (predicted frames) norms tables, end of the
+ *		  nested pass
  *    ST_DONE
  */
+template <bool MOTION>
 __device__ void
 t0_advance (const DevParams &P, const TileWs &W, ShHdr *h, int &state, int &depth)
 {
@@ -2009,8 +2235,7 @@ t0_advance (const DevParams &P, const TileWs &W, ShHdr *h, int &state, int &dept
 
       if (state == ST_ENTER)
       {
-	 RangeRes *res = depth ? &h->frames [depth - 1].child [h->frames [depth - 1].label]
-			       : &h->root;
+	 RangeRes *res = res_slot<MOTION> (h, depth);
 
 	 res->into [0] = FB_NO_EDGE;
 	 res->tree     = FB_RANGE;
@@ -2034,11 +2259,27 @@ t0_advance (const DevParams &P, const TileWs &W, ShHdr *h, int &state, int &dept
 	    state = ST_DONE;
 	    return;
 	 }
+	 if (MOTION && depth == h->nest_base)
+	 {
+	    depth--;				/* back in mc_prediction (prediction.c:318) */
+	    state = ST_PRED_DONE;
+	    return;
+	 }
 	 h->frames [depth - 1].subdivide_costs += h->ret_costs;
 	 depth--;
 	 state = ST_AFTER_CHILD;
       }
       else if (state == ST_AFTER_CHILD)
+      {
+	 /* update_norms_table (prediction.c:213-238) */
+	 if (MOTION && h->fx [depth].try_mc && F.level > P.p_min)
+	 {
+	    state = ST_NORMS_UP;
+	    return;
+	 }
+	 state = ST_AFTER_CHILD2;
+      }
+      else if (state == ST_AFTER_CHILD2)
       {
 	 const int label = F.label;
 	 RangeRes &c	 = F.child [label];
@@ -2053,7 +2294,13 @@ t0_advance (const DevParams &P, const TileWs &W, ShHdr *h, int &state, int &dept
 	 F.r_tree_bits	  += c.tree_bits;
 	 F.r_matrix_bits  += c.matrix_bits;
 	 F.r_weights_bits += c.weights_bits;
-	 /* tree_update (bintree.c:35-53) */
+	 if (MOTION)
+	 {
+	    h->fx [depth].r_mvt += h->fx [depth].child [label].mv_tree_bits;
+	    h->fx [depth].r_mvc += h->fx [depth].child [label].mv_coord_bits;
+	 }
+	 /* tree_update (bintree.c:35-53); the prediction tree model (subdivide.c:372) is never
+	    read by the coder and is not kept */
 	 if (c.tree != FB_RANGE)
 	    h->tree_counts [F.level - 1]++;
 	 h->tree_total [F.level - 1]++;
@@ -2095,8 +2342,18 @@ t0_advance (const DevParams &P, const TileWs &W, ShHdr *h, int &state, int &dept
 	    C.address	= cadr;
 	    C.level	= level - 1;
 	    C.y_state	= F.new_y_state [label];
+	    if (MOTION)
+	    {
+	       h->fx [depth + 1].delta	    = h->fx [depth].delta;
+	       h->fx [depth + 1].prediction = h->fx [depth].prediction;
+	    }
 	    depth++;
 	    state = ST_ENTER;
+	 }
+	 else if (MOTION && h->fx [depth].try_mc && level - 1 >= P.p_min)
+	 {
+	    state = ST_FILL_CHILD;	/* subdivide.c:331-333: the child's norms are still needed */
+	    return;
 	 }
 	 else
 	    state = ST_AFTER_CHILD;	/* subdivide() not called: costs unchanged */
@@ -2106,15 +2363,24 @@ t0_advance (const DevParams &P, const TileWs &W, ShHdr *h, int &state, int &dept
    }
 }
 
-template <int NT>
+template <int NT, bool MOTION>
 __device__ void
-cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
+cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 		    int root_y_state)
 {
    ShHdr    *h	 = sh.h;
    const int tid = threadIdx.x;
    int	     it	 = 0;
+   const int SN	 = MOTION ? 3 : 2;	/* model snapshots per activation record */
+   const int TS	 = MOTION ? 2 : 1;	/* tree-model snapshots per record */
+   Sh	     shn = sh;			/* buffers and models of the nested (prediction error) pass */
 
+   if (MOTION)
+   {
+      shn.blob	 = sh.blob + P.blob_half;
+      shn.pixels = GP (W.pix2);
+      shn.norm_i = GP (W.norm2);
+   }
    if (tid == 0)
    {
       Frame &F = h->frames [0];
@@ -2126,7 +2392,14 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
       F.y_state = root_y_state;
       h->band	= band;
       h->price	= band ? P.price * P.chroma_decrease : P.price;
-      t0_advance (P, W, h, st, dp);
+      h->nest_base = -1;
+      h->top	   = P.lc_max;
+      if (MOTION)
+      {
+	 h->fx [0].delta      = 0;
+	 h->fx [0].prediction = 1;
+      }
+      t0_advance<MOTION> (P, W, h, st, dp);
       h->state [0]  = st;
       h->depthv [0] = dp;
    }
@@ -2137,9 +2410,12 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
       const int state = h->state [it & 1];
       const int depth = h->depthv [it & 1];
       Frame    &F     = h->frames [depth];
-      RangeRes *res   = depth ? &h->frames [depth - 1].child [h->frames [depth - 1].label]
-			      : &h->root;
+      RangeRes *res   = res_slot<MOTION> (h, depth);
       int	nstate = state;		/* thread 0: state after this action */
+      int	ndepth = depth;
+      /* nested pass of a prediction: the delta models, the prediction error block */
+      const bool nested = MOTION && h->nest_base >= 0 && depth >= h->nest_base;
+      const Sh	&cs	= nested ? shn : sh;
 
       if (state == ST_DONE || h->status != FB200_OK)
 	 break;
@@ -2154,9 +2430,10 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 	 const bool	 block = state == ST_ENTER;
 
 	 if (block)
-	    cta_init_range<NT> (P, W, sh, F.x, F.y, band);
+	    cta_init_range<NT> (P, W, cs, F.x, F.y, band);
 	 else
-	    cta_compute_T<NT> (P, W, sh, F.states_snap, F.image * 2 + F.label + 1, F.level - 1);
+	    cta_compute_T<NT> (P, W, cs, F.states_snap, F.image * 2 + F.label + 1, F.level - 1,
+			       MOTION ? h->top : P.lc_max);
 	 if (tid == 0)
 	 {
 	    if (block)
@@ -2170,8 +2447,8 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 	 case ST_ENTER:
 	 {
 	    const int level = F.level;
-	    short    *snap  = (sh.snaps ? sh.snaps : GP (W.snap)) + (size_t) depth * 2 * P.blob_len;
-	    unsigned *tsnap = sh.tsnap + (size_t) depth * 2 * FB200_MAXLEVEL;
+	    short    *snap  = (sh.snaps ? sh.snaps : GP (W.snap)) + (size_t) depth * SN * P.blob_len;
+	    unsigned *tsnap = sh.tsnap + (size_t) depth * TS * 2 * FB200_MAXLEVEL;
 
 	    /* snapshot of the models (subdivide.c:188-194); tree_counts and tree_total are
 	       adjacent in the header */
@@ -2186,6 +2463,30 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 	    }
 	    if (tid == 0)
 	    {
+	       float mvt = 0.0f;
+
+	       if (MOTION)
+	       {
+		  FrameX &X = h->fx [depth];
+
+		  /* motion compensation allowed for this range? (subdivide.c:141-147) */
+		  X.try_mc = X.prediction && level >= P.p_min && level <= P.p_max
+			     && F.x + width_of_level (level) <= (unsigned) P.width
+			     && F.y + height_of_level (level) <= (unsigned) P.height;
+		  X.pred_done = 0;
+		  mvt	      = X.try_mc ? 1.0f : 0.0f;	/* mc allowed but not used */
+		  X.lrange.mv_tree_bits	 = mvt;
+		  X.lrange.mv_coord_bits = 0;
+		  X.lrange.mv_type = X.lrange.mv_fx = X.lrange.mv_fy = X.lrange.prediction = 0;
+		  X.r_mvt = mvt;
+		  X.r_mvc = 0;
+		  for (int label = 0; label < 2; label++)
+		  {
+		     X.child [label].mv_tree_bits = X.child [label].mv_coord_bits = 0;
+		     X.child [label].mv_type = X.child [label].mv_fx = X.child [label].mv_fy = 0;
+		     X.child [label].prediction = 0;
+		  }
+	       }
 	       F.states_snap = h->states;
 	       /* y states of the children (subdivide.c:172-183) */
 	       for (int label = 0; label < 2; label++)
@@ -2205,12 +2506,21 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 	       }
 	    }
 	    __syncthreads ();
+	    /* clear_norms_table (prediction.c:195-211) */
+	    if (MOTION && h->fx [depth].try_mc && level > P.p_min)
+	    {
+	       float *nt = norms_of_level (P, W, level);
+
+	       for (int i = tid; i < 4 * P.sr * P.sr; i += NT)
+		  nt [i] = 0.0f;
+	    }
 	    /* alternative 1: linear combination (subdivide.c:200-221) */
 	    if (level <= P.lc_max)
 	    {
 	       const long long t0c = clock64 ();
-	       cta_approximate_range<NT> (P, W, sh, F.max_costs, h->price, F.y_state,
-					  &F.lrange, level, F.image, F.address, F.x, F.y);
+	       cta_approximate_range<NT> (P, W, cs, F.max_costs, h->price, F.y_state,
+					  &F.lrange, level, F.image, F.address, F.x, F.y,
+					  MOTION ? h->fx [depth].lrange.mv_tree_bits : 0.0f);
 	       if (tid == 0)
 	       {
 		  F.lincomb_costs = h->ret_costs;
@@ -2237,7 +2547,8 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 		  F.r_weights_bits = 0;
 		  F.r_err	   = 0;
 		  F.subdivide_costs = (F.r_tree_bits + F.r_weights_bits + F.r_matrix_bits
-				       + 0.0f + 0.0f + 0.0f + 0.0f) * h->price;
+				       + (MOTION ? h->fx [depth].r_mvt : 0.0f) + 0.0f + 0.0f + 0.0f)
+				      * h->price;
 		  F.label = 0;
 		  for (int label = 0; label < 2; label++)
 		  {
@@ -2264,11 +2575,230 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 	    break;
 	 }
 
+	 case ST_NORMS_UP:		/* update_norms_table (prediction.c:213-238) */
+	 {
+	    if (MOTION)
+	    {
+	       float	   *up = norms_of_level (P, W, F.level);
+	       const float *lo = norms_of_level (P, W, F.level - 1);
+
+	       for (int i = tid; i < 4 * P.sr * P.sr; i += NT)
+		  up [i] += lo [i];
+	       if (tid == 0)
+		  nstate = ST_AFTER_CHILD2;
+	    }
+	    break;
+	 }
+
+	 case ST_FILL_CHILD:		/* fill_norms_table for a child that is not visited */
+	 {
+	    if (MOTION)
+	    {
+	       cta_fill_norms<NT> (P, W, F.child [F.label].x, F.child [F.label].y, F.level - 1);
+	       if (tid == 0)
+		  nstate = ST_AFTER_CHILD;
+	    }
+	    break;
+	 }
+
+	 case ST_PRED_DONE:		/* mc_prediction after the nested subdivide (prediction.c:318-360) */
+	 {
+	    if (MOTION)
+	    {
+	       FrameX	  &X	 = h->fx [depth];
+	       short	  *snap	 = (sh.snaps ? sh.snaps : GP (W.snap)) + (size_t) depth * SN * P.blob_len;
+	       unsigned	  *tsnap = sh.tsnap + (size_t) depth * TS * 2 * FB200_MAXLEVEL;
+	       const float costs = X.pcosts + h->ret_costs;
+	       const bool  win	 = costs < X.max_pred;
+
+	       __syncthreads ();
+	       if (tid == 0)
+	       {
+		  if (h->nest_base >= 0)	/* the outer tables come back */
+		  {
+		     float *t = W.T;
+		     W.T      = W.T2;
+		     W.T2     = t;
+		  }
+		  h->nest_base = -1;
+		  h->top       = P.lc_max;
+	       }
+	       __syncthreads ();
+	       if (win)
+	       {
+		  /* the products of the states born in the nested pass start from zero in the
+		     outer tables (prediction.c:337-341) */
+		  const unsigned first = X.last_state + 1, nnew = h->states - first;
+
+		  for (unsigned i = tid; i < (unsigned) P.tn * nnew; i += NT)
+		     GP (W.T) [(size_t) (i / nnew) * P.s_cap + first + i % nnew] = 0.0f;
+		  /* the states of the split alternative stay behind as holes:
+		     inert, never referenced; the host closes them */
+		  for (unsigned s = F.states_snap + tid; s < X.rec_states; s += NT)
+		  {
+		     for (int label = 0; label < 2; label++)
+		     {
+			GP (W.into) [(size_t) (2 * s + label) * 6] = FB_NO_EDGE;
+			GP (W.tree) [2 * s + label]		   = FB_RANGE;
+			GP (W.mv_type) [2 * s + label]		   = 0;
+		     }
+		     GP (W.level_of_state) [s] = 255;
+		  }
+		  if (tid == 0)
+		  {
+		     RangeX *rx = resx_slot (h, depth);
+
+		     *res   = X.prange;
+		     res->x = (unsigned short) F.x;
+		     res->y = (unsigned short) F.y;
+		     rx->mv_tree_bits  = 1.0f;
+		     rx->mv_coord_bits = X.mvc;
+		     rx->mv_type       = 1;	/* FORWARD */
+		     rx->mv_fx	       = (signed char) X.mx;
+		     rx->mv_fy	       = (signed char) X.my;
+		     rx->prediction    = 1;
+		     h->ret_costs = (res->tree_bits + res->matrix_bits + res->weights_bits
+				     + rx->mv_tree_bits + rx->mv_coord_bits + 0.0f + 0.0f) * h->price
+				    + res->err;
+		     nstate = ST_RETURN;
+		  }
+	       }
+	       else
+	       {
+		  /* the prediction lost: models and automaton as the first two alternatives left
+		     them (prediction.c:159-186) */
+		  cta_copy_s16<NT> (sh.blob, snap + 2 * P.blob_len, P.blob_len);
+		  if (tid < 32)
+		  {
+		     unsigned *tm = (unsigned *) ((char *) h + offsetof (ShHdr, tree_counts));
+
+		     for (int i = tid; i < 2 * FB200_MAXLEVEL; i += 32)
+			tm [i] = tsnap [2 * FB200_MAXLEVEL + i];
+		     __syncwarp ();
+		  }
+		  for (unsigned s = F.states_snap + tid; s < X.rec_states; s += NT)
+		     GP (W.domain_type) [s] = GP (W.saved_dt) [s];
+		  __syncthreads ();
+		  if (tid == 0)
+		  {
+		     /* the tail of the shared pool list, which the attempt may have overwritten:
+			the usable states of the split alternative, in order */
+		     unsigned k = ((const unsigned short *) snap) [MB_N];
+
+		     for (unsigned s = F.states_snap; s < X.rec_states; s++)
+			if (GP (W.domain_type) [s] & 2)
+			   sh.pool [k++] = (short) s;
+		     if (k != BLOB_U16 (sh, MB_N))
+			h->status = FB200_ECUDA;	/* cannot happen: the lists are prefixes of each other */
+		     h->states	 = X.rec_states;
+		     X.pred_done = 1;
+		     nstate	 = ST_DECIDE;
+		  }
+	       }
+	    }
+	    break;
+	 }
+
 	 case ST_DECIDE:
 	 {
 	    const float lin = F.lincomb_costs, sub = F.subdivide_costs;
-	    short      *snap  = (sh.snaps ? sh.snaps : GP (W.snap)) + (size_t) depth * 2 * P.blob_len;
-	    unsigned   *tsnap = sh.tsnap + (size_t) depth * 2 * FB200_MAXLEVEL;
+	    short      *snap  = (sh.snaps ? sh.snaps : GP (W.snap)) + (size_t) depth * SN * P.blob_len;
+	    unsigned   *tsnap = sh.tsnap + (size_t) depth * TS * 2 * FB200_MAXLEVEL;
+
+	    if (MOTION && h->fx [depth].try_mc && !h->fx [depth].pred_done)
+	    {
+	       /* alternative 3: motion compensation + approximation of the prediction error
+		  (subdivide.c:383-407, predict_range prediction.c:96-191, mc_prediction :262-370) */
+	       FrameX	&X     = h->fx [depth];
+	       const int level = F.level;
+
+	       /* keep the models of the first two alternatives, hide their states, start again
+		  from the models of the node's entry */
+	       cta_copy_s16<NT> (snap + 2 * P.blob_len, sh.blob, P.blob_len);
+	       if (tid < 32)
+	       {
+		  unsigned *tm = (unsigned *) ((char *) h + offsetof (ShHdr, tree_counts));
+
+		  for (int i = tid; i < 2 * FB200_MAXLEVEL; i += 32)
+		  {
+		     tsnap [2 * FB200_MAXLEVEL + i] = tm [i];
+		     tm [i]			    = tsnap [i];
+		  }
+		  __syncwarp ();
+	       }
+	       for (unsigned s = F.states_snap + tid; s < h->states; s += NT)
+	       {
+		  GP (W.saved_dt) [s]	 = GP (W.domain_type) [s];
+		  GP (W.domain_type) [s] = 0;
+	       }
+	       __syncthreads ();
+	       cta_copy_s16<NT> (sh.blob, snap, P.blob_len);
+	       if (tid == 0)
+	       {
+		  X.rec_states = h->states;
+		  X.max_pred   = fmin2 (fmin2 (lin, sub), F.max_costs);
+	       }
+	       __syncthreads ();
+	       if (level == P.p_min)
+		  cta_fill_norms<NT> (P, W, F.x, F.y, level);
+	       cta_find_best_mv<NT> (P, W, sh, F.x, F.y, level, h->price);
+	       if (tid == 0)
+	       {
+		  /* find_P_frame_mc (mwfa.c:301-339) */
+		  const int bi = h->best_i < 0 ? 0 : h->best_i;
+
+		  X.mx	   = bi < 0 ? 0 : bi % (2 * P.sr) - P.sr;
+		  X.my	   = bi < 0 ? 0 : bi / (2 * P.sr) - P.sr;
+		  if (h->best_i < 0)
+		     X.mx = X.my = 0;
+		  X.mvc	   = (float) c_mv_code_length [X.mx + P.sr] + (float) c_mv_code_length [X.my + P.sr];
+		  X.pcosts = (1.0f + X.mvc) * h->price;
+	       }
+	       __syncthreads ();
+	       if (X.pcosts < X.max_pred)
+	       {
+		  /* the prediction error replaces the pixels, fresh product tables, and
+		     subdivide() on it with the delta models */
+		  cta_mcpe_range<NT> (P, W, shn, F.x, F.y, level, X.mx, X.my);
+		  if (tid == 0)
+		  {
+		     float *t = W.T;
+		     W.T  = W.T2;
+		     W.T2 = t;
+		     h->top	  = level;
+		     h->nest_base = depth + 1;
+		     X.last_state = h->states - 1;
+		  }
+		  __syncthreads ();
+		  cta_compute_T<NT> (P, W, shn, 0, 0, level, level);
+		  if (tid == 0)
+		  {
+		     Frame &C = h->frames [depth + 1];
+
+		     C.max_costs = X.max_pred - X.pcosts;
+		     C.x	 = F.x;
+		     C.y	 = F.y;
+		     C.image	 = 0;
+		     C.address	 = 0;
+		     C.level	 = level;
+		     C.y_state	 = F.y_state;
+		     h->fx [depth + 1].delta	  = 1;
+		     h->fx [depth + 1].prediction = 0;
+		     X.prange.into [0] = FB_NO_EDGE;
+		     X.prange.tree     = FB_RANGE;
+		     ndepth = depth + 1;
+		     nstate = ST_ENTER;
+		  }
+	       }
+	       else if (tid == 0)
+	       {
+		  /* the vector alone is too expensive: as if the nested pass had failed */
+		  h->ret_costs = FB_MAXCOSTS;
+		  h->nest_base = -2;	/* no tables to swap back */
+		  nstate       = ST_PRED_DONE;
+	       }
+	       break;
+	    }
 
 	    if ((lin >= FB_MAXCOSTS && sub >= FB_MAXCOSTS) || lin < sub)
 	    {
@@ -2299,6 +2829,8 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 		     res->tree = FB_RANGE;
 		     res->x    = rx;
 		     res->y    = ry;
+		     if (MOTION)
+			*resx_slot (h, depth) = h->fx [depth].lrange;
 		     h->ret_costs = lin;
 		  }
 		  nstate = ST_RETURN;
@@ -2317,12 +2849,15 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 
 		  if (!aux)
 		  {
-		     /* rle_append (domain-pool.c:832-852) */
+		     /* rle_append (domain-pool.c:832-852); in a predicted frame the state enters
+			the normal and the delta pool (subdivide.c:573-584), which share the list */
 		     const unsigned n = BLOB_U16 (sh, MB_N);
 		     if (n < BLOB_U16 (sh, MB_MAXDOM))
 		     {
 			sh.pool [n]	    = (short) s;
 			BLOB_U16 (sh, MB_N) = (unsigned short) (n + 1);
+			if (MOTION)
+			   BLOB_U16 (shn, MB_N) = (unsigned short) (n + 1);
 		     }
 		  }
 		  for (int label = 0; label < 2; label++)
@@ -2335,6 +2870,14 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 		     GP (W.y) [2 * s + label]       = c.y;
 		     GP (W.y_column) [2 * s + label] = 0;
 		     GP (W.into) [(size_t) (2 * s + label) * 6] = FB_NO_EDGE;
+		     if (MOTION)
+		     {
+			const RangeX &cx = h->fx [depth].child [label];
+
+			GP (W.mv_type) [2 * s + label] = cx.mv_type;
+			GP (W.mv_fx) [2 * s + label]   = cx.mv_fx;
+			GP (W.mv_fy) [2 * s + label]   = cx.mv_fy;
+		     }
 		     for (int e = 0; c.into [e] != FB_NO_EDGE; e++)
 		     {
 			t0_append_edge (W, s, c.into [e], c.weight [e], label);
@@ -2351,6 +2894,14 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
 		  res->tree_bits    = F.r_tree_bits;
 		  res->matrix_bits  = F.r_matrix_bits;
 		  res->weights_bits = F.r_weights_bits;
+		  if (MOTION)
+		  {
+		     RangeX *rx = resx_slot (h, depth);
+
+		     rx->mv_tree_bits  = h->fx [depth].r_mvt;
+		     rx->mv_coord_bits = h->fx [depth].r_mvc;
+		     rx->mv_type = rx->mv_fx = rx->mv_fy = rx->prediction = 0;
+		  }
 		  h->ret_costs	    = sub;
 		  nstate	    = ST_RETURN;
 	       }
@@ -2366,11 +2917,9 @@ cta_subdivide_band (const DevParams &P, const TileWs &W, const Sh &sh, int band,
       /* thread 0 continues with the scalar part of the control flow */
       if (tid == 0)
       {
-	 int dp = depth;
-
-	 t0_advance (P, W, h, nstate, dp);
+	 t0_advance<MOTION> (P, W, h, nstate, ndepth);
 	 h->state [(it + 1) & 1]  = nstate;
-	 h->depthv [(it + 1) & 1] = dp;
+	 h->depthv [(it + 1) & 1] = ndepth;
       }
       __syncthreads ();
    }
@@ -2487,7 +3036,7 @@ t0_virtual_state (const DevParams &P, const TileWs &W, ShHdr *h, int child0, int
 				the kernel
 *****************************************************************************/
 
-template <int NT>
+template <int NT, bool MOTION>
 __global__ void __launch_bounds__ (NT, (NT >= 512 ? 1 : NT >= 256 ? 2 : NT >= 128 ? FB200_MINB : 5))
 fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
 {
@@ -2534,11 +3083,20 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
 	 s_W.trans = S.trans;
 	 s_W.Gglob = S.Gglob;
 	 s_W.snap  = S.snap;
+	 if (MOTION)
+	 {
+	    s_W.T2	 = S.T2;
+	    s_W.norms	 = S.norms;
+	    s_W.pix2	 = S.pix2;
+	    s_W.norm2	 = S.norm2;
+	    s_W.saved_dt = S.saved_dt;
+	 }
       }
    }
    __syncthreads ();
    const TileWs &W  = s_W;
    const Sh	sh  = carve (smem_raw, P, NT, GP (W.Gglob));
+   const Sh    &sh_base = sh;
    ShHdr       *h   = sh.h;
    const int	tid = threadIdx.x;
 
@@ -2546,6 +3104,8 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
    {
       h->status	   = FB200_OK;
       h->frames	   = sh.frames;
+      h->fx	   = sh.fx;
+      h->nest_base = -1;
       h->w.l2_dc   = sh.l2;
       h->w.l2_lv   = sh.l2 + P.aac_dc_size;
       h->trace_len = 0;
@@ -2588,10 +3148,19 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
 	 }
       }
       for (int i = tid; i < P.blob_len; i += NT)
-	 sh.blob [i] = i >= MB_COUNTS - 1 ? 1 : 0;
+	 sh.blob [i] = (i % P.blob_half) >= MB_COUNTS - 1 ? 1 : 0;
+      if (MOTION)
+	 for (int i = tid; i < 2 * P.s_cap; i += NT)
+	    GP (W.mv_type) [i] = GP (W.mv_fx) [i] = GP (W.mv_fy) [i] = 0;
       __syncthreads ();
+      /* a predicted frame has a second model set for the prediction errors: the delta pool and
+	 the delta coefficient model (coder.c:713-736), initialised like the first */
+      for (int set = 0; set < (MOTION ? 2 : 1); set++)
       if (tid == 0)
       {
+	 Sh sh = sh_base;
+
+	 sh.blob += set * P.blob_half;
 	 for (int k = 0; k < FB_MAXEDGES + 1; k++)
 	    BLOB_S16 (sh, MB_COUNT + k) = 1;
 	 BLOB_U16 (sh, MB_TOTAL)  = FB_MAXEDGES + 1;
@@ -2630,7 +3199,7 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
 	    t0_chroma_setup (P, W, sh, (int *) sh.bnd);
 	 __syncthreads ();
       }
-      cta_subdivide_band<NT> (P, W, sh, band, band ? band_tree [0] : FB_RANGE);
+      cta_subdivide_band<NT, MOTION> (P, s_W, sh, band, band ? band_tree [0] : FB_RANGE);
       if (h->status != FB200_OK)
 	 break;
       band_tree [band] = h->root.tree;
@@ -2755,7 +3324,7 @@ fb_tile_kernel_threads (const DevParams &p, int n_tiles)
 size_t
 fb_tile_kernel_smem (const DevParams &p, int nt)
 {
-   size_t off [16];
+   size_t off [20];
 
    return smem_layout (p, nt, off);
 }
@@ -2791,17 +3360,18 @@ upload_tables (void)
    return cudaSuccess;
 }
 
-template <int NT>
+template <int NT, bool MOTION>
 static cudaError_t
 launch_nt (const DevParams &p_in, const TileWs *d_ws, int n_tiles, cudaStream_t stream)
 {
+   const auto kernel = fiasco_tile_kernel<NT, MOTION>;
    DevParams	p = p_in;
-   size_t	off [16];
+   size_t off [20];
    const size_t smem = smem_layout (p, NT, off);
 
-   for (int i = 0; i < 16; i++)
+   for (int i = 0; i < 20; i++)
       p.sm_off [i] = off [i] == (size_t) -1 ? 0xffffffffu : (unsigned) off [i];
-   cudaError_t	e    = cudaFuncSetAttribute (fiasco_tile_kernel<NT>,
+   cudaError_t	e    = cudaFuncSetAttribute (kernel,
 					     cudaFuncAttributeMaxDynamicSharedMemorySize,
 					     (int) smem);
    if (e != cudaSuccess)
@@ -2809,9 +3379,9 @@ launch_nt (const DevParams &p_in, const TileWs *d_ws, int n_tiles, cudaStream_t 
    {
       const char *cv = getenv ("FB200_CARVE");	/* experiments only: shared-memory carve-out in % */
       if (cv)
-	 cudaFuncSetAttribute (fiasco_tile_kernel<NT>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi (cv));
+	 cudaFuncSetAttribute (kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi (cv));
    }
-   FB_LAUNCH (fiasco_tile_kernel<NT>, n_tiles, NT, smem, stream, p, d_ws);
+   FB_LAUNCH (kernel, n_tiles, NT, smem, stream, p, d_ws);
    return cudaGetLastError ();
 }
 
@@ -2822,12 +3392,16 @@ fb_launch_tile_kernel (const DevParams &p, const TileWs *d_ws, int n_tiles,
    cudaError_t e = upload_tables ();
    if (e != cudaSuccess)
       return e;
+   if (p.motion)		/* predicted frames: the two production shapes only */
+      return fb_tile_kernel_threads (p, n_tiles) <= 128
+	     ? launch_nt<128, true> (p, d_ws, n_tiles, stream)
+	     : launch_nt<512, true> (p, d_ws, n_tiles, stream);
    switch (fb_tile_kernel_threads (p, n_tiles))
    {
-      case 96:	return launch_nt<96> (p, d_ws, n_tiles, stream);
-      case 128: return launch_nt<128> (p, d_ws, n_tiles, stream);
-      case 256: return launch_nt<256> (p, d_ws, n_tiles, stream);
-      default:	return launch_nt<512> (p, d_ws, n_tiles, stream);
+      case 96:	return launch_nt<96, false> (p, d_ws, n_tiles, stream);
+      case 128: return launch_nt<128, false> (p, d_ws, n_tiles, stream);
+      case 256: return launch_nt<256, false> (p, d_ws, n_tiles, stream);
+      default:	return launch_nt<512, false> (p, d_ws, n_tiles, stream);
    }
 }
 
@@ -2838,9 +3412,12 @@ occupancy_nt (const DevParams &p)
    int	  n    = 0;
    size_t smem = fb_tile_kernel_smem (p, NT);
 
-   if (cudaFuncSetAttribute (fiasco_tile_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+   const auto kernel = p.motion && (NT == 128 || NT == 512)
+			? fiasco_tile_kernel<(NT == 128 ? 128 : 512), true>
+			: fiasco_tile_kernel<NT, false>;
+   if (cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
 			     (int) smem) != cudaSuccess
-       || cudaOccupancyMaxActiveBlocksPerMultiprocessor (&n, fiasco_tile_kernel<NT>, NT, smem)
+       || cudaOccupancyMaxActiveBlocksPerMultiprocessor (&n, kernel, NT, smem)
 	  != cudaSuccess)
    {
       cudaGetLastError ();

@@ -60,11 +60,17 @@ struct DevParams
    int	 coeff_min_level;	/* context base of the aac model (coder.c:731) */
    int	 aac_dc_size, aac_lvl_size, blob_len;
    int	 trace_cap;
-   unsigned sm_off [16];	/* shared-memory layout of the block (filled by the launcher) */
+   unsigned sm_off [20];	/* shared-memory layout of the block (filled by the launcher) */
    int	 n_slots;		/* workspaces (img, T, SS, ...); tiles beyond that share them */
    int	*slot_flags;		/* [n_slots] 0 = free */
    int	 big;			/* large state capacity, so that more tiles fit on an SM: bit 0 =
 				   Gram rows in global memory, bit 1 = model snapshots in global */
+   /* predicted frames (codec/prediction.c, codec/mwfa.c): 0 = intra kernel */
+   int	 motion;		/* frame type: 0 intra, 1 P frame */
+   int	 p_min, p_max;		/* levels of the motion compensated ranges (coder.c:284-290) */
+   int	 sr;			/* search range: vectors in [-sr, sr) */
+   int	 blob_half;		/* shorts of one model set; blob = normal set, then delta set */
+   int	 n_frames;		/* DFS activation records (nested delta pass included) */
 };
 
 /* all transitions of one state in one 64-byte line: what the inner-product kernels gather */
@@ -99,6 +105,14 @@ struct TileWs
    int16_t *snap;		/* [FB_MAXDEPTH][2][blob_len] */
    struct TileResult *result;
    fb200_trace_rec_t *trace;	/* [trace_cap] or NULL */
+   /* predicted frames only */
+   const int16_t *past;		/* [width*height] regenerated reference frame */
+   float   *T2;			/* [tn][s_cap]	 products of the nested (prediction error) pass */
+   float   *norms;		/* [p_max - p_min + 1][4 sr^2] norms tables of the motion search */
+   float   *pix2;		/* [2^p_max]	 prediction error block, bintree order */
+   int	   *norm2;		/* [tn]		 its sums of squares per node */
+   uint8_t *saved_dt;		/* [s_cap]	 domain types of the states a prediction attempt hides */
+   int8_t  *mv_type, *mv_fx, *mv_fy;	/* [s_cap][2] motion vectors of the ranges (wfa->mv_tree) */
 };
 
 struct TileResult

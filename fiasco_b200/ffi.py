@@ -38,7 +38,13 @@ class _Wfa(C.Structure):
         ("final_distribution", C.c_void_p), ("level_of_state", C.c_void_p),
         ("domain_type", C.c_void_p), ("tree", C.c_void_p), ("x", C.c_void_p), ("y", C.c_void_p),
         ("into", C.c_void_p), ("weight", C.c_void_p), ("y_state", C.c_void_p), ("y_column", C.c_void_p),
+        ("mv_type", C.c_void_p), ("mv_fx", C.c_void_p), ("mv_fy", C.c_void_p),
     ]
+
+
+class Motion(C.Structure):
+    _fields_ = [("frame_type", C.c_int), ("p_min_level", C.c_int), ("p_max_level", C.c_int),
+                ("search_range", C.c_int)]
 
 
 class TraceRec(C.Structure):
@@ -82,6 +88,8 @@ def load():
     lib.fb200_device_count.restype = ip
     lib.fb200_params_init.argtypes = [C.POINTER(Params), ip, ip, ip, C.c_float, ip, cp, C.c_size_t]
     lib.fb200_create.argtypes = [C.POINTER(vp), C.POINTER(Params), ip, ip, cp, C.c_size_t]
+    lib.fb200_create_predicted.argtypes = [C.POINTER(vp), C.POINTER(Params), C.POINTER(Motion), ip, ip, cp, C.c_size_t]
+    lib.fb200_encode_predicted.argtypes = [vp, ip, C.POINTER(vp), C.POINTER(vp), C.POINTER(_Wfa), cp, C.c_size_t]
     lib.fb200_destroy.argtypes = [vp]
     lib.fb200_destroy.restype = None
     lib.fb200_encode_tiles.argtypes = [vp, ip, C.POINTER(vp), C.POINTER(_Wfa), C.POINTER(TraceRec), ip,
@@ -135,24 +143,33 @@ class _WfaArrays:
         self.weight = np.zeros((cap, 2, 6), np.float32)
         self.y_state = np.zeros((cap, 2), np.int16)
         self.y_column = np.zeros((cap, 2), np.uint8)
+        self.mv_type = np.zeros((cap, 2), np.int8)
+        self.mv_fx = np.zeros((cap, 2), np.int8)
+        self.mv_fy = np.zeros((cap, 2), np.int8)
 
     def fill(self, w):
         w.capacity = self.cap
         for name in ("final_distribution", "level_of_state", "domain_type", "tree", "x", "y", "into", "weight",
-                     "y_state", "y_column"):
+                     "y_state", "y_column", "mv_type", "mv_fx", "mv_fy"):
             setattr(w, name, getattr(self, name).ctypes.data)
 
 
 class TileEncoder:
     """Device workspace for up to `max_tiles` tiles of one geometry (fb200_ctx_t)."""
 
-    def __init__(self, params, max_tiles=1, device=0, out_capacity=None):
+    def __init__(self, params, max_tiles=1, device=0, out_capacity=None, motion=None):
+        """motion = Motion(...): a workspace for predicted frames (fb200_create_predicted)."""
         self.lib = load()
         self.params = params
         self.max_tiles = max_tiles
+        self.motion = motion
         self.ctx = C.c_void_p()
         err = C.create_string_buffer(512)
-        _check(self.lib.fb200_create(C.byref(self.ctx), C.byref(params), max_tiles, device, err, 512), err)
+        if motion is None:
+            _check(self.lib.fb200_create(C.byref(self.ctx), C.byref(params), max_tiles, device, err, 512), err)
+        else:
+            _check(self.lib.fb200_create_predicted(C.byref(self.ctx), C.byref(params), C.byref(motion), max_tiles,
+                                                   device, err, 512), err)
         self.out_capacity = out_capacity or 6000
         self._arrays = [_WfaArrays(self.out_capacity) for _ in range(max_tiles)]
         self._wfas = (_Wfa * max_tiles)()
@@ -191,7 +208,7 @@ class TileEncoder:
                 "matrix_bits": list(w.matrix_bits), "weights_bits": list(w.weights_bits),
             }
             for name in ("final_distribution", "level_of_state", "domain_type", "tree", "x", "y", "into", "weight",
-                         "y_state", "y_column"):
+                         "y_state", "y_column") + (("mv_type", "mv_fx", "mv_fy") if self.motion is not None else ()):
                 d[name] = getattr(a, name)[:n].copy()
             out.append(d)
         tr = None
@@ -209,6 +226,17 @@ class TileEncoder:
         rc = self.lib.fb200_encode_tiles(self.ctx, n_tiles, ptrs, self._wfas, trace, trace_cap, C.byref(tl), err, 512)
         _check(rc, err)
         return self._collect(n_tiles, trace, tl)
+
+    def encode_predicted(self, planes, past):
+        """One predicted frame per tile: planes[t] the frame, past[t] the regenerated previous frame."""
+        n_tiles = len(planes)
+        ptrs = self._plane_ptrs(planes)
+        keep = self._keep
+        pptrs = self._plane_ptrs(past)
+        self._keep = (keep, self._keep)
+        err = C.create_string_buffer(512)
+        _check(self.lib.fb200_encode_predicted(self.ctx, n_tiles, ptrs, pptrs, self._wfas, err, 512), err)
+        return self._collect(n_tiles, None, None)[0]
 
     def upload(self, planes):
         n_tiles = len(planes) // self.params.bands

@@ -105,7 +105,10 @@ typedef struct fb200_wfa
    int16_t  *into;			     /* [capacity][2][6], -1 terminated */
    float    *weight;			     /* [capacity][2][6] */
    int16_t  *y_state;			     /* [capacity][2] */
-   uint8_t  *y_column;			     /* [capacity][2] */
+   uint8_t  *y_column;		     /* [capacity][2] */
+   /* predicted frames (fb200_encode_predicted; may be NULL): motion vectors of the ranges,
+      mv_t of wfa->mv_tree, codec/wfa.h:62-71 -- type 0 none, 1 forward */
+   int8_t   *mv_type, *mv_fx, *mv_fy;	     /* [capacity][2] */
 } fb200_wfa_t;
 
 /* one record per approximate_range() call (debug / parity tracing, optional) */
@@ -204,6 +207,38 @@ int fb200_probe (int kind, int n, const float *f, const int *a, const int *b,
 int fb200_motion_norms (int device, const int16_t *orig, const int16_t *past, int width,
 			int height, int level, int search_range, float *norms, float *kernel_ms,
 			char *err, size_t errlen);
+
+/*
+ *  Predicted frames of a sequence (replaces, in the reference coder, the same subdivide() call
+ *  at codec/coder.c:743 when the frame is a P frame, i.e. with its third alternative:
+ *  predict_range / mc_prediction, codec/prediction.c:96,262; find_P_frame_mc, fill_norms_table,
+ *  find_best_mv, codec/mwfa.c:301,544,686; and the nested subdivide() over the prediction error
+ *  with the delta pool and delta coefficient model).  Levels and search range as in
+ *  c_options_t (codec/options.h: p_min_level, p_max_level, search_range; CLI defaults 6, 10, 16).
+ */
+typedef struct fb200_motion
+{
+   int frame_type;		/* 1 = P frame (B frames: not on the device yet) */
+   int p_min_level, p_max_level;
+   int search_range;		/* vectors in [-search_range, search_range), full pixel */
+} fb200_motion_t;
+
+/* A device workspace for predicted frames of geometry 'p' (one independent sequence per tile). */
+int fb200_create_predicted (fb200_ctx_t **ctx, const fb200_params_t *p,
+			    const fb200_motion_t *motion, int max_tiles, int device,
+			    char *err, size_t errlen);
+
+/*
+ *  Encode one predicted frame per tile: planes[t] is the frame, past[t] the REGENERATED previous
+ *  frame of the same sequence (fiasco_regenerate_frame() of include/fiasco_host.h; what
+ *  decode_image + restore_mc leave in the reference, codec/coder.c:642-651), both width*height
+ *  shorts in host memory.  The automata come back as the device leaves them: states of losing
+ *  alternatives are holes (level_of_state == 255) and out[t].mv_* hold the vectors;
+ *  fiasco_finish_predicted_frame() closes the holes and derives the delta flags.
+ */
+int fb200_encode_predicted (fb200_ctx_t *ctx, int n_tiles, const int16_t *const *planes,
+			    const int16_t *const *past, fb200_wfa_t *out,
+			    char *err, size_t errlen);
 
 const char *fb200_version (void);
 
