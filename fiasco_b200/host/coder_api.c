@@ -18,6 +18,7 @@
 #include <string.h>
 
 #include "fi_internal.h"
+#include "fiasco_host.h"
 
 #define fi_min(a, b) ((a) > (b) ? (b) : (a))
 #define fi_max(a, b) ((a) < (b) ? (b) : (a))
@@ -105,7 +106,12 @@ fiasco_coder (char const *const *inputname, const char *outputname, float qualit
       fb200_wfa_t	 *wfas;
       fi_image_t	**images;
       const int16_t	**planes;
-      unsigned		  frames, width = 0, height = 0, n, bands;
+      unsigned		  frames, width = 0, height = 0, n, bands, n_predicted = 0;
+      unsigned		  n_intra = 0;
+      fb200_ctx_t	 *pctx = NULL;
+      int16_t		**recon = NULL;		/* regenerated frames (references of P frames) */
+      uint8_t		**delta = NULL;		/* delta flags of the states of P frames */
+      const int16_t	**iplanes;
       int		  color = 0, rc;
       char		  err [512] = "";
       char		 *name;
@@ -175,9 +181,22 @@ fiasco_coder (char const *const *inputname, const char *outputname, float qualit
       /* what this build does not do is refused, not approximated */
       for (n = 0; n < frames; n++)
 	 if (!is_intra (n, cop->pattern))
-	    fi_error ("Frame %d is a predicted frame (pattern `%s'): motion compensated "
-		      "coding is not available in the B200 build, use a pattern of I frames.",
-		      n, cop->pattern);
+	 {
+	    if (toupper ((unsigned char) cop->pattern [n % strlen (cop->pattern)]) != 'P')
+	       fi_error ("Frame %d (pattern `%s'): of the predicted frame types only P frames "
+			 "are available in the B200 build.", n, cop->pattern);
+	    if (color)
+	       fi_error ("Predicted frames are available for grey sequences only.");
+	    if (cop->half_pixel_prediction)
+	       fi_error ("Half pixel motion compensation is not available in the B200 build.");
+	    if (!cop->normal_domains || !cop->delta_domains
+		|| cop->d_rpf_mantissa != cop->rpf_mantissa || cop->d_rpf_range != cop->rpf_range
+		|| cop->d_dc_rpf_mantissa != cop->dc_rpf_mantissa
+		|| cop->d_dc_rpf_range != cop->dc_rpf_range)
+	       fi_error ("Predicted frames: only the default domain pool and quantisation "
+			 "settings of the prediction errors are available.");
+	    n_predicted++;
+	 }
       if (cop->prediction)
 	 fi_error ("Nondeterministic (DC) prediction is not available in the B200 build.");
       if (cop->full_search)
@@ -262,20 +281,148 @@ fiasco_coder (char const *const *inputname, const char *outputname, float qualit
 	 if (fb200_wfa_alloc (&wfas [n], FI_MAXSTATES))
 	    fi_error ("Out of memory!");
       }
-      rc = fb200_create (&ctx, &p, (int) frames, 0, err, sizeof err);
-      if (rc == FB200_OK)
-	 rc = fb200_encode_tiles (ctx, (int) frames, planes, wfas, NULL, 0, NULL, err,
-				  sizeof err);
-      if (ctx)
-	 fb200_destroy (ctx);
-      if (rc != FB200_OK)
-	 fi_error ("%s", err [0] ? err : "GPU encoder failed");
+      /* the intra frames of the sequence: one launch */
+      iplanes = fiasco_calloc ((size_t) frames * bands, sizeof (int16_t *));
+      {
+	 fb200_wfa_t *batch = fiasco_calloc (frames, sizeof (fb200_wfa_t));
+	 unsigned     b, i;
+
+	 for (n = 0; n < frames; n++)
+	    if (is_intra (n, cop->pattern))
+	    {
+	       for (b = 0; b < bands; b++)
+		  iplanes [n_intra * bands + b] = planes [n * bands + b];
+	       batch [n_intra++] = wfas [n];
+	    }
+	 rc = fb200_create (&ctx, &p, (int) n_intra, 0, err, sizeof err);
+	 if (rc == FB200_OK)
+	    rc = fb200_encode_tiles (ctx, (int) n_intra, iplanes, batch, NULL, 0, NULL, err,
+				     sizeof err);
+	 if (ctx)
+	    fb200_destroy (ctx);
+	 if (rc != FB200_OK)
+	    fi_error ("%s", err [0] ? err : "GPU encoder failed");
+	 for (n = 0, i = 0; n < frames; n++)
+	    if (is_intra (n, cop->pattern))
+	       wfas [n] = batch [i++];
+	 free (batch);
+      }
+
+      /*
+       *  Predicted frames (video_coder, coder.c:490-680): a P frame needs the REGENERATED
+       *  previous frame, so the frames of one group of pictures are a chain; the groups are
+       *  independent.  Step k codes the k-th P frame of every group in one launch (one thread
+       *  block per group), then the host closes the holes of the automata, derives the delta
+       *  flags and regenerates the frames for step k + 1.
+       */
+      if (n_predicted)
+      {
+	 fb200_motion_t	 mo;
+	 fb200_wfa_t	*batch	= fiasco_calloc (frames, sizeof (fb200_wfa_t));
+	 const int16_t **bplane = fiasco_calloc (frames, sizeof (int16_t *));
+	 const int16_t **bpast	= fiasco_calloc (frames, sizeof (int16_t *));
+	 unsigned	*bframe = fiasco_calloc (frames, sizeof (unsigned));
+	 unsigned	 k, groups = 0;
+	 jmp_buf	 saved;
+
+	 recon = fiasco_calloc (frames, sizeof (int16_t *));
+	 delta = fiasco_calloc (frames, sizeof (uint8_t *));
+	 for (n = 1; n < frames; n++)
+	    if (!is_intra (n, cop->pattern) && is_intra (n - 1, cop->pattern))
+	       groups++;
+	 mo.frame_type	 = 1;
+	 mo.p_min_level	 = (int) wi.p_min_level;
+	 mo.p_max_level	 = (int) wi.p_max_level;
+	 mo.search_range = (int) cop->search_range;
+	 rc = fb200_create_predicted (&pctx, &p, &mo, (int) groups, 0, err, sizeof err);
+	 if (rc != FB200_OK)
+	    fi_error ("%s", err [0] ? err : "GPU encoder failed");
+	 for (k = 1; ; k++)
+	 {
+	    unsigned cnt = 0, i;
+
+	    for (n = k; n < frames; n++)
+	    {
+	       unsigned j;
+
+	       if (is_intra (n, cop->pattern))
+		  continue;
+	       for (j = 1; j < k && !is_intra (n - j, cop->pattern); j++)
+		  ;
+	       if (j != k || !is_intra (n - k, cop->pattern))
+		  continue;			/* not the k-th frame of its group */
+	       if (!recon [n - 1])
+	       {
+		  /* the reference frame: regenerate the frame before (coder.c:642-651) */
+		  fiasco_frame_motion_t fm;
+
+		  memset (&fm, 0, sizeof fm);
+		  recon [n - 1] = fiasco_calloc ((size_t) width * height, sizeof (int16_t));
+		  if (k > 1)
+		  {
+		     fm.frame_type  = 1;
+		     fm.mv_type	    = wfas [n - 1].mv_type;
+		     fm.mv_fx	    = wfas [n - 1].mv_fx;
+		     fm.mv_fy	    = wfas [n - 1].mv_fy;
+		     fm.delta_state = delta [n - 1];
+		  }
+		  memcpy (saved, fi_env, sizeof saved);
+		  rc = fiasco_regenerate_frame (&wfas [n - 1], &fm, (int) width, (int) height,
+						k > 1 ? recon [n - 2] : NULL, NULL, recon [n - 1]);
+		  memcpy (fi_env, saved, sizeof saved);
+		  if (!rc)
+		     fi_error ("%s", fiasco_get_error_message ());
+	       }
+	       bplane [cnt] = planes [n];
+	       bpast [cnt]  = recon [n - 1];
+	       bframe [cnt] = n;
+	       batch [cnt]  = wfas [n];
+	       cnt++;
+	    }
+	    if (!cnt)
+	       break;
+	    rc = fb200_encode_predicted (pctx, (int) cnt, bplane, bpast, batch, err, sizeof err);
+	    if (rc != FB200_OK)
+	    {
+	       fb200_destroy (pctx);
+	       fi_error ("%s", err [0] ? err : "GPU encoder failed");
+	    }
+	    for (i = 0; i < cnt; i++)
+	    {
+	       n	 = bframe [i];
+	       wfas [n]	 = batch [i];
+	       delta [n] = fiasco_calloc (FI_MAXSTATES, 1);
+	       memcpy (saved, fi_env, sizeof saved);
+	       rc = fiasco_finish_predicted_frame (&wfas [n], wfas [n].mv_type, wfas [n].mv_fx,
+						   wfas [n].mv_fy, NULL, NULL, delta [n]);
+	       memcpy (fi_env, saved, sizeof saved);
+	       if (!rc)
+		  fi_error ("%s", fiasco_get_error_message ());
+	    }
+	 }
+	 fb200_destroy (pctx);
+	 free (batch);
+	 free (bplane);
+	 free (bpast);
+	 free (bframe);
+      }
+      free (iplanes);
 
       for (n = 0; n < frames; n++)
       {
 	 fi_wfa_t w;
 
 	 memset (&w, 0, sizeof w);	/* intra frame: no motion data */
+	 if (!is_intra (n, cop->pattern))
+	 {
+	    w.frame_type  = 1;
+	    w.x		  = (const uint16_t (*)[2]) wfas [n].x;
+	    w.y		  = (const uint16_t (*)[2]) wfas [n].y;
+	    w.mv_type	  = (const int8_t (*)[2]) wfas [n].mv_type;
+	    w.mv_fx	  = (const int8_t (*)[2]) wfas [n].mv_fx;
+	    w.mv_fy	  = (const int8_t (*)[2]) wfas [n].mv_fy;
+	    w.delta_state = delta [n];
+	 }
 	 w.info		  = &wi;
 	 w.states	  = wfas [n].states;
 	 w.basis_states	  = wfas [n].basis_states;
@@ -293,7 +440,13 @@ fiasco_coder (char const *const *inputname, const char *outputname, float qualit
 	 fi_write_next_wfa (&w, n, n == 0, cop->normal_domains, cop->delta_domains, output);
 	 fb200_wfa_free (&wfas [n]);
 	 fi_free_image (images [n]);
+	 if (recon)
+	    free (recon [n]);
+	 if (delta)
+	    free (delta [n]);
       }
+      free (recon);
+      free (delta);
       if (cop->progress_meter != FIASCO_PROGRESS_NONE)
 	 fi_message ("");
       fi_bits_close (output);
@@ -314,7 +467,6 @@ fiasco_coder (char const *const *inputname, const char *outputname, float qualit
 		      fiasco_host.h: stream writing for callers of the C ABI
 *****************************************************************************/
 
-#include "fiasco_host.h"
 
 void
 fiasco_stream_info_init (fiasco_stream_info_t *info, const fb200_params_t *p)

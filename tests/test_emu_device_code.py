@@ -81,3 +81,85 @@ def test_emulated_motion_norms(emu):
         for bx in range(got.shape[1]):
             L.fo_fill_norms_table(orig.ctypes.data, past.ctypes.data, 96, 64, bx * 8, by * 8, 6, 16, ref.ctypes.data)
             assert np.array_equal(got[by, bx].view(np.uint32), ref.view(np.uint32)), (bx, by)
+
+
+# ------------------------------------------------------------------ predicted frames (motion path)
+
+def _holes_mode_automata(name):
+    m = O.manifest()[name]
+    frames = list(gen_frames.video(m["frames"], m["width"], m["height"]))
+    L = O.lib()
+    L.fo_set_holes_mode(1)
+    try:
+        ws, rec = O.encode_video(frames, quality=m["quality"], pattern=m["pattern"])
+    finally:
+        L.fo_set_holes_mode(0)
+    return m, frames, ws, rec
+
+
+def assert_same_predicted_automaton(g, od):
+    """Device automaton of a predicted frame (holes still open) against the oracle's in holes mode."""
+    n = od["states"]
+    assert g["status"] == 0 and g["states"] == n and g["root_state"] == od["root_state"]
+    assert np.array_equal(g["level_of_state"][:n], od["level_of_state"][:n])
+    live = od["level_of_state"][:n] != 255
+    for k in ("tree", "x", "y", "mv_type", "mv_fx", "mv_fy", "domain_type"):
+        assert np.array_equal(g[k][:n][live], od[k][:n][live]), k
+    assert np.array_equal(g["final_distribution"][:n][live].view(np.uint32),
+                          od["final_distribution"][:n][live].view(np.uint32))
+    for s in np.nonzero(live)[0]:
+        if s < 3:
+            continue
+        for label in range(2):
+            for e in range(6):
+                assert g["into"][s][label][e] == od["into"][s][label][e], (s, label, e)
+                if od["into"][s][label][e] < 0:
+                    break
+                assert g["weight"][s][label][e].view(np.uint32) == od["weight"][s][label][e].view(np.uint32)
+
+
+@pytest.mark.parametrize("name", ["v160_q20_ippp", "v352_q30_ippip"])
+def test_emulated_device_code_predicted_frames(emu, name):
+    """P frames: the kernel's third alternative (motion search over the norms tables, nested pass over
+    the prediction error with the delta models, holes scheme) state for state against the oracle run in
+    holes mode, each frame predicted from the oracle's regenerated previous frame."""
+    m, frames, ws, rec = _holes_mode_automata(name)
+    p = ffi.make_params(m["width"], m["height"], 1, float(m["quality"]), 0)
+    enc = F.TileEncoder(p, 1, motion=F.Motion(1, 6, 10, 16))
+    checked = 0
+    try:
+        for f in range(1, len(frames)):
+            od = O.struct_dict(ws[f]["_struct"])
+            if od["frame_type"] != 1:
+                continue
+            g = enc.encode_predicted([O.planes_of(frames[f])[0]], [rec[f - 1]])[0]
+            assert_same_predicted_automaton(g, od)
+            checked += 1
+    finally:
+        enc.close()
+    assert checked >= 3
+
+
+@pytest.mark.parametrize("name", ["v160_q20_ippp", "v352_q30_ippip"])
+def test_emulated_fiasco_coder_writes_the_reference_stream_for_sequences(emu, name, tmp_path):
+    """fiasco_coder() on a sequence with P frames -- I frames in one launch, the P frames group by
+    group along their chains, holes closed and frames regenerated on the host between the steps -- writes
+    the stream the reference cfiasco writes, byte for byte (md5 of the golden .fco)."""
+    import hashlib
+    from fiasco_b200 import hostlib
+    saved = (hostlib._LIB, hostlib.lib_path)
+    hostlib._LIB, hostlib.lib_path = None, (lambda: os.path.join(EMU_DIR, "_build", "libfiasco_emu.so"))
+    try:
+        m = O.manifest()[name]
+        names = []
+        for i, f in enumerate(gen_frames.video(m["frames"], m["width"], m["height"])):
+            names.append(str(tmp_path / ("f%02d.pgm" % i)))
+            gen_frames.write_pnm(names[-1], f)
+        o = hostlib.cli_options(0)
+        hostlib.load().fiasco_c_options_set_frame_pattern(o, m["pattern"].encode())
+        out = str(tmp_path / "v.fco")
+        ok, msg = hostlib.coder(names, out, float(m["quality"]), options=o)
+        assert ok, msg
+        assert hashlib.md5(open(out, "rb").read()).hexdigest() == m["fco_md5"]
+    finally:
+        hostlib._LIB, hostlib.lib_path = saved

@@ -1,0 +1,70 @@
+"""Motion path on the GPU (BASELINE config 5): P frames through the C ABI
+(fb200_create_predicted / fb200_encode_predicted) and through fiasco_coder(), against the oracle and the
+golden streams of the reference coder.  Bit exact: states, edges, weights, vectors, stream bytes."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import fiasco_b200 as F
+from fiasco_b200 import ffi, hostlib
+import oracle_lib as O
+import gen_frames
+from test_emu_device_code import _holes_mode_automata, assert_same_predicted_automaton
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["v160_q20_ippp", "v352_q30_ippip"])
+def test_gpu_predicted_frames_match_oracle(name):
+    m, frames, ws, rec = _holes_mode_automata(name)
+    p = ffi.make_params(m["width"], m["height"], 1, float(m["quality"]), 0)
+    enc = F.TileEncoder(p, 1, motion=F.Motion(1, 6, 10, 16))
+    golden = list(O.golden_video_frames(name))
+    try:
+        for f in range(1, len(frames)):
+            od = O.struct_dict(ws[f]["_struct"])
+            if od["frame_type"] != 1:
+                continue
+            g = enc.encode_predicted([O.planes_of(frames[f])[0]], [rec[f - 1]])[0]
+            assert_same_predicted_automaton(g, od)
+            # holes closed by the host: the reference's own automaton (golden dump of the reference binary)
+            g["frame_type"], g["frame_number"] = 1, f
+            g["mv_bx"] = np.zeros_like(g["mv_fx"])
+            g["mv_by"] = np.zeros_like(g["mv_fx"])
+            g["delta_state"] = np.zeros(g["states"], np.uint8)
+            done = hostlib.finish_predicted_frame(g)
+            number, ftype, states, root, body = golden[f]
+            assert (done["states"], done["root_state"]) == (states, root)
+    finally:
+        enc.close()
+
+
+def test_gpu_predicted_frames_of_several_sequences_in_one_launch():
+    """One thread block per sequence: the same P frame as three tiles of one launch and alone."""
+    m, frames, ws, rec = _holes_mode_automata("v160_q20_ippp")
+    p = ffi.make_params(m["width"], m["height"], 1, float(m["quality"]), 0)
+    enc = F.TileEncoder(p, 3, motion=F.Motion(1, 6, 10, 16))
+    try:
+        planes = [O.planes_of(frames[f])[0] for f in (1, 2, 3)]
+        gs = enc.encode_predicted(planes, [rec[0], rec[1], rec[2]])
+        for f, g in zip((1, 2, 3), gs):
+            assert_same_predicted_automaton(g, O.struct_dict(ws[f]["_struct"]))
+    finally:
+        enc.close()
+
+
+@pytest.mark.parametrize("name", ["v160_q20_ippp", "v352_q30_ippip"])
+def test_gpu_fiasco_coder_sequence_stream_is_byte_identical(name, tmp_path):
+    m = O.manifest()[name]
+    names = []
+    for i, f in enumerate(gen_frames.video(m["frames"], m["width"], m["height"])):
+        names.append(str(tmp_path / ("f%02d.pgm" % i)))
+        gen_frames.write_pnm(names[-1], f)
+    o = hostlib.cli_options(0)
+    hostlib.load().fiasco_c_options_set_frame_pattern(o, m["pattern"].encode())
+    out = str(tmp_path / "v.fco")
+    ok, msg = hostlib.coder(names, out, float(m["quality"]), options=o)
+    assert ok, msg
+    assert hashlib.md5(open(out, "rb").read()).hexdigest() == m["fco_md5"]
