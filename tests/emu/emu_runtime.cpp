@@ -52,6 +52,10 @@ struct Block
 };
 
 Block	       B;
+/* scheduling order between rendezvous points (FB200_EMU_ORDER): 0 ascending thread index,
+   1 descending, 2 pseudo-random.  A result that depends on it is a race between barriers. */
+int	       g_order = -1;
+unsigned       g_rand  = 12345u;
 char	      *g_stacks;
 size_t	       g_stacks_n;
 unsigned char *g_smem;
@@ -69,8 +73,18 @@ switch_to_next (void)
       return;
    }
    do
-      next = next + 1 == B.n ? 0 : next + 1;
-   while (B.done [next]);
+   {
+      if (g_order == 1)
+	 next = next == 0 ? B.n - 1 : next - 1;
+      else if (g_order == 2)
+      {
+	 g_rand = g_rand * 1664525u + 1013904223u;
+	 next	= (int) ((g_rand >> 8) % (unsigned) B.n);
+      }
+      else
+	 next = next + 1 == B.n ? 0 : next + 1;
+   }
+   while (B.done [next] || (g_order == 2 && next == from && B.alive > 1));
    if (next == from)
    {
       fprintf (stderr, "emu: deadlock -- thread %d waits for a rendezvous nobody else can reach\n", from);
@@ -168,6 +182,10 @@ emu_launch (emu_dim3 grid, emu_dim3 block, size_t smem, const std::function<void
 {
    const int n = (int) block.x;
 
+   {
+      const char *o = getenv ("FB200_EMU_ORDER");	/* read per launch: tests switch it */
+      g_order = o ? atoi (o) : 0;
+   }
    if (!g_smem && posix_memalign ((void **) &g_smem, 256, 256 * 1024))
       abort ();
    if (smem > 256 * 1024 || block.y != 1 || block.z != 1)
@@ -207,8 +225,8 @@ emu_launch (emu_dim3 grid, emu_dim3 block, size_t smem, const std::function<void
 	    sp [7] = NULL;
 	    B.sp [t] = sp;
 	 }
-	 B.cur	     = 0;
-	 threadIdx.x = 0;
-	 emu_switch (&B.main_sp, B.sp [0]);
+	 B.cur	     = g_order == 1 ? n - 1 : 0;
+	 threadIdx.x = (unsigned) B.cur;
+	 emu_switch (&B.main_sp, B.sp [B.cur]);
       }
 }

@@ -163,3 +163,24 @@ def test_emulated_fiasco_coder_writes_the_reference_stream_for_sequences(emu, na
         assert hashlib.md5(open(out, "rb").read()).hexdigest() == m["fco_md5"]
     finally:
         hostlib._LIB, hostlib.lib_path = saved
+
+
+@pytest.mark.parametrize("order", ["1", "2"])
+def test_emulated_results_do_not_depend_on_thread_scheduling(emu, order):
+    """The emulator runs the threads of a block between two rendezvous points in ascending order by
+    default; descending (1) and pseudo-random (2) orders must give the same automata -- a result that
+    depended on the order would be a race between barriers on the GPU."""
+    os.environ["FB200_EMU_ORDER"] = order
+    try:
+        img = gen_frames.chan(128, 128, 4)
+        T.assert_same_wfa(T.gpu_encode(img)[0], O.encode(img))
+        m, frames, ws, rec = _holes_mode_automata("v160_q20_ippp")
+        p = ffi.make_params(m["width"], m["height"], 1, float(m["quality"]), 0)
+        enc = F.TileEncoder(p, 1, motion=F.Motion(1, 6, 10, 16))
+        try:
+            g = enc.encode_predicted([O.planes_of(frames[1])[0]], [rec[0]])[0]
+            assert_same_predicted_automaton(g, O.struct_dict(ws[1]["_struct"]))
+        finally:
+            enc.close()
+    finally:
+        os.environ.pop("FB200_EMU_ORDER", None)
