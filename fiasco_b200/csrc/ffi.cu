@@ -17,6 +17,7 @@ struct fb200_ctx
    fb200_params_t params;
    fb200_motion_t motion;	/* frame_type 0: a context for intra frames */
    int16_t	 *d_past;	/* [tiles][w*h] reference frames (predicted frames only) */
+   int16_t	 *d_future;	/* [tiles][w*h] backward references (B frames only) */
    DevParams	  dp;
    int		  max_tiles, device, nt;
    size_t	  smem;
@@ -231,9 +232,10 @@ derive (const fb200_params_t *p, const fb200_motion_t *mo, DevParams *d, char *e
    d->s_cap = p->state_capacity > 0 ? p->state_capacity : default_capacity (p);
    if (mo && mo->frame_type)
    {
-      if (mo->frame_type != 1 || p->bands != 1 || mo->search_range < 1 || mo->search_range > 16)
+      if (mo->frame_type < 1 || mo->frame_type > 2 || p->bands != 1 || mo->search_range < 1
+	  || mo->search_range > 16)
       {
-	 set_err (err, errlen, "predicted frames: P frames of grey sequences, search range 1..16");
+	 set_err (err, errlen, "predicted frames: P and B frames of grey sequences, search range 1..16");
 	 return FB200_EUNSUPPORTED;
       }
       /* prediction levels are a subset of the range levels (coder.c:284-290) */
@@ -303,7 +305,8 @@ work_layout (const DevParams &d, size_t *off /* [12] */)
    if (d.motion)
    {
       off [7]  = o; o += up256 ((size_t) d.tn * sc * 4);			/* T2 */
-      off [8]  = o; o += up256 ((size_t) (d.p_max - d.p_min + 1) * 4 * d.sr * d.sr * 4); /* norms */
+      off [8]  = o; o += up256 ((size_t) (d.motion == 2 ? 2 : 1) * (d.p_max - d.p_min + 1)
+				* 4 * d.sr * d.sr * 4);				/* norms */
       off [9]  = o; o += up256 (((size_t) 1 << d.lc_max) * 4);		/* pix2 */
       off [10] = o; o += up256 ((size_t) d.tn * 4);				/* norm2 */
       off [11] = o; o += up256 (sc);						/* saved_dt */
@@ -313,7 +316,7 @@ work_layout (const DevParams &d, size_t *off /* [12] */)
 
 /* the automaton of one tile, contiguous so that it travels in one copy */
 static size_t
-wfa_layout (const DevParams &d, size_t *off /* [13] */)
+wfa_layout (const DevParams &d, size_t *off /* [15] */)
 {
    size_t o = 0, sc = (size_t) d.s_cap;
 
@@ -327,12 +330,14 @@ wfa_layout (const DevParams &d, size_t *off /* [13] */)
    off [7] = o; o += up256 (sc);		/* level_of_state */
    off [8] = o; o += up256 (sc);		/* domain_type */
    off [9] = o; o += up256 (sc * 2);		/* y_column */
-   off [10] = off [11] = off [12] = o;
+   off [10] = off [11] = off [12] = off [13] = off [14] = o;
    if (d.motion)
    {
       off [10] = o; o += up256 (sc * 2);	/* mv_type */
       off [11] = o; o += up256 (sc * 2);	/* mv_fx */
       off [12] = o; o += up256 (sc * 2);	/* mv_fy */
+      off [13] = o; o += up256 (sc * 2);	/* mv_bx */
+      off [14] = o; o += up256 (sc * 2);	/* mv_by */
    }
    return o;
 }
@@ -347,6 +352,7 @@ fb200_destroy (fb200_ctx_t *c)
    cudaFree (c->d_slot_flags);
    cudaFree (c->d_pix);
    cudaFree (c->d_past);
+   cudaFree (c->d_future);
    cudaFree (c->d_wfa);
    cudaFree (c->d_results);
    cudaFree (c->d_trace);
@@ -380,7 +386,7 @@ ctx_alloc (fb200_ctx_t *c, char *err, size_t errlen)
 	 return FB200_EINVAL;
       }
    }
-   size_t woff [12], aoff [13];
+   size_t woff [12], aoff [15];
    c->work_stride = work_layout (d, woff);
    c->wfa_block	  = wfa_layout (d, aoff);
    c->pix_elems	  = (size_t) d.bands * d.width * d.height;
@@ -409,6 +415,8 @@ ctx_alloc (fb200_ctx_t *c, char *err, size_t errlen)
       CUDA_TRY (cudaMalloc (&c->d_pix, c->pix_elems * 2 * max_tiles));
       if (d.motion)
 	 CUDA_TRY (cudaMalloc (&c->d_past, c->pix_elems * 2 * max_tiles));
+      if (d.motion == 2)
+	 CUDA_TRY (cudaMalloc (&c->d_future, c->pix_elems * 2 * max_tiles));
       CUDA_TRY (cudaMalloc (&c->d_results, sizeof (TileResult) * max_tiles));
       CUDA_TRY (cudaMalloc (&c->d_ws, sizeof (TileWs) * max_tiles));
       CUDA_TRY (cudaMallocHost (&c->h_results, sizeof (TileResult) * max_tiles));
@@ -446,6 +454,9 @@ ctx_alloc (fb200_ctx_t *c, char *err, size_t errlen)
       if (d.motion)
       {
 	 w.past	    = c->d_past + c->pix_elems * t;
+	 w.future   = d.motion == 2 ? c->d_future + c->pix_elems * t : w.past;
+	 w.mv_bx    = (int8_t *) (ab + aoff [13]);
+	 w.mv_by    = (int8_t *) (ab + aoff [14]);
 	 w.T2	    = (float *) (wb + woff [7]);
 	 w.norms    = (float *) (wb + woff [8]);
 	 w.pix2	    = (float *) (wb + woff [9]);
@@ -663,7 +674,7 @@ fb200_download (fb200_ctx_t *c, int n_tiles, fb200_wfa_t *out, fb200_trace_rec_t
    cudaEventElapsedTime (&c->stats.d2h_ms, c->ev [4], c->ev [5]);
    c->stats.d2h_bytes = (sizeof (TileResult) + c->wfa_block) * n_tiles;
 
-   size_t aoff [13];
+   size_t aoff [15];
    wfa_layout (c->dp, aoff);
    int rc = FB200_OK;
    c->stats.ip_bytes = c->stats.mp_calls = c->stats.mp_steps = c->stats.pass2 = 0;
@@ -738,6 +749,8 @@ fb200_download (fb200_ctx_t *c, int n_tiles, fb200_wfa_t *out, fb200_trace_rec_t
 	 if (o.mv_type)		memcpy (o.mv_type, ab + aoff [10], n * 2);
 	 if (o.mv_fx)		memcpy (o.mv_fx, ab + aoff [11], n * 2);
 	 if (o.mv_fy)		memcpy (o.mv_fy, ab + aoff [12], n * 2);
+	 if (o.mv_bx)		memcpy (o.mv_bx, ab + aoff [13], n * 2);
+	 if (o.mv_by)		memcpy (o.mv_by, ab + aoff [14], n * 2);
       }
    }
    if (trace_len)
@@ -793,22 +806,29 @@ fb200_encode_tiles (fb200_ctx_t *c, int n_tiles, const int16_t *const *planes,
 
 extern "C" int
 fb200_encode_predicted (fb200_ctx_t *c, int n_tiles, const int16_t *const *planes,
-			const int16_t *const *past, fb200_wfa_t *out, char *err, size_t errlen)
+			const int16_t *const *past, const int16_t *const *future,
+			fb200_wfa_t *out, char *err, size_t errlen)
 {
    int rc;
 
-   if (!c || !c->dp.motion || !past || n_tiles < 1 || n_tiles > c->max_tiles)
+   if (!c || !c->dp.motion || !past || n_tiles < 1 || n_tiles > c->max_tiles
+       || (c->dp.motion == 2 && !future))
    {
       set_err (err, errlen, "fb200_encode_predicted: needs a context of fb200_create_predicted() "
-	       "and one reference frame per tile");
+	       "and one reference frame per tile (two for B frames)");
       return FB200_EINVAL;
    }
    c->dp.trace_cap = 0;
    if ((rc = fb200_upload (c, n_tiles, planes, err, errlen)))
       return rc;
    for (int t = 0; t < n_tiles; t++)
+      {
       CUDA_TRY (cudaMemcpyAsync (c->d_past + c->pix_elems * t, past [t], c->pix_elems * 2,
 				 cudaMemcpyHostToDevice, c->stream));
+      if (c->dp.motion == 2)
+	 CUDA_TRY (cudaMemcpyAsync (c->d_future + c->pix_elems * t, future [t], c->pix_elems * 2,
+				    cudaMemcpyHostToDevice, c->stream));
+   }
    CUDA_TRY (cudaStreamSynchronize (c->stream));
    c->stats.h2d_bytes += c->pix_elems * 2 * n_tiles;
    for (;;)
@@ -867,9 +887,11 @@ fb200_wfa_alloc (fb200_wfa_t *w, int capacity)
    w->mv_type		 = (int8_t *) calloc ((size_t) capacity * 2, 1);
    w->mv_fx		 = (int8_t *) calloc ((size_t) capacity * 2, 1);
    w->mv_fy		 = (int8_t *) calloc ((size_t) capacity * 2, 1);
+   w->mv_bx		 = (int8_t *) calloc ((size_t) capacity * 2, 1);
+   w->mv_by		 = (int8_t *) calloc ((size_t) capacity * 2, 1);
    if (!w->final_distribution || !w->level_of_state || !w->domain_type || !w->tree
        || !w->x || !w->y || !w->into || !w->weight || !w->y_state || !w->y_column
-       || !w->mv_type || !w->mv_fx || !w->mv_fy)
+       || !w->mv_type || !w->mv_fx || !w->mv_fy || !w->mv_bx || !w->mv_by)
    {
       fb200_wfa_free (w);
       return FB200_EINVAL;
@@ -895,6 +917,8 @@ fb200_wfa_free (fb200_wfa_t *w)
    free (w->mv_type);
    free (w->mv_fx);
    free (w->mv_fy);
+   free (w->mv_bx);
+   free (w->mv_by);
    memset (w, 0, sizeof *w);
 }
 

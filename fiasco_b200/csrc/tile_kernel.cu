@@ -235,7 +235,7 @@ struct Frame			/* one activation record of subdivide() */
 struct RangeX
 {
    float       mv_tree_bits, mv_coord_bits;
-   signed char mv_type, mv_fx, mv_fy, prediction;
+   signed char mv_type, mv_fx, mv_fy, mv_bx, mv_by, prediction;
 };
 
 /* activation record of subdivide() in a predicted frame, beside Frame */
@@ -249,8 +249,8 @@ struct FrameX
    int	    pred_done;		/* the prediction alternative has been tried (and lost) */
    unsigned rec_states;		/* states after the first two alternatives */
    unsigned last_state;
-   float    max_pred, pcosts, mvc;
-   int	    mx, my;
+   float    max_pred, pcosts, mvc, mvt;
+   int	    mx, my, bx, by, mctype;
 };
 
 struct MpRes			/* mp_t, codec/approx.c:41-51 */
@@ -321,6 +321,10 @@ struct ShHdr
    int	    nest_base;		/* depth of the root record of the nested pass, or -1 */
    int	    top;		/* level of node 0 of the product tree in use */
    int	    best_i;		/* find_best_mv: winning displacement index */
+   float    best_c;		/* and its costs */
+   float    fcosts, bcosts;	/* find_B_frame_mc */
+   int	    fi, bi;
+   long long isum;		/* integer sum of squares of the interpolated prediction error */
 };
 
 static_assert (offsetof (ShHdr, tree_total) == offsetof (ShHdr, tree_counts) + FB200_MAXLEVEL * sizeof (unsigned),
@@ -2027,9 +2031,10 @@ __constant__ unsigned char c_mv_code_length [33] =
  11, 11, 11, 11, 11, 11};
 
 __device__ __forceinline__ float *
-norms_of_level (const DevParams &P, const TileWs &W, int level)
+norms_of_level (const DevParams &P, const TileWs &W, int level, int backward = 0)
 {
-   return GP (W.norms) + (size_t) (level - P.p_min) * (4 * P.sr * P.sr);
+   return GP (W.norms) + ((size_t) backward * (P.p_max - P.p_min + 1) + (level - P.p_min))
+			 * (4 * P.sr * P.sr);
 }
 
 /*
@@ -2044,11 +2049,13 @@ cta_fill_norms (const DevParams &P, const TileWs &W, unsigned x0, unsigned y0, i
 {
    const int	  sr = P.sr, nd = 4 * sr * sr;
    const int	  bw = (int) width_of_level (level), bh = (int) height_of_level (level);
-   float	 *out = norms_of_level (P, W, level);
-   const int16_t *orig = GP (W.pix), *past = GP (W.past);
+   const int16_t *orig = GP (W.pix);
 
+   for (int dir = 0; dir < (P.motion == 2 ? 2 : 1); dir++)
    for (int index = threadIdx.x; index < nd; index += NT)
    {
+      float	    *out  = norms_of_level (P, W, level, dir);
+      const int16_t *past = dir ? GP (W.future) : GP (W.past);
       const int mx = index % (2 * sr) - sr, my = index / (2 * sr) - sr;
       float	norm = 0.0f;
 
@@ -2079,11 +2086,11 @@ cta_fill_norms (const DevParams &P, const TileWs &W, unsigned x0, unsigned y0, i
 template <int NT>
 __device__ void
 cta_find_best_mv (const DevParams &P, const TileWs &W, const Sh &sh, unsigned x0, unsigned y0,
-		  int level, float price)
+		  int level, float price, int backward)
 {
    const int	sr = P.sr, nd = 4 * sr * sr;
    const int	bw = (int) width_of_level (level), bh = (int) height_of_level (level);
-   const float *norms = norms_of_level (P, W, level);
+   const float *norms = norms_of_level (P, W, level, backward);
    float	best  = FB_MAXCOSTS;
    int		besti = -1;
 
@@ -2124,6 +2131,7 @@ cta_find_best_mv (const DevParams &P, const TileWs &W, const Sh &sh, unsigned x0
 	 }
       }
       sh.h->best_i = mi;
+      sh.h->best_c = m;
    }
    __syncthreads ();
 }
@@ -2136,11 +2144,11 @@ cta_find_best_mv (const DevParams &P, const TileWs &W, const Sh &sh, unsigned x0
 template <int NT>
 __device__ void
 cta_mcpe_range (const DevParams &P, const TileWs &W, const Sh &cs, unsigned x0, unsigned y0,
-		int level, int mx, int my)
+		int level, int mctype, int mx, int my, int bx, int by)
 {
    const int	  tid  = threadIdx.x;
    const unsigned size = 1u << level;
-   const int16_t *orig = GP (W.pix), *past = GP (W.past);
+   const int16_t *orig = GP (W.pix), *past = GP (W.past), *fut = GP (W.future);
 
    for (unsigned i = tid; i < size; i += NT)
    {
@@ -2151,8 +2159,17 @@ cta_mcpe_range (const DevParams &P, const TileWs &W, const Sh &cs, unsigned x0, 
 	 xx |= ((i >> (2 * b + 1)) & 1u) << b;
       }
       const unsigned px = x0 + xx, py = y0 + yy;
-      const int16_t  d	= (int16_t) (orig [(size_t) py * P.width + px]
-				     - past [(size_t) ((int) py + my) * P.width + ((int) px + mx)]);
+      int ref;
+
+      /* get_mcpe (mwfa.c:604-649): one reference block, or the mean of two (truncating) */
+      if (mctype == 1)
+	 ref = past [(size_t) ((int) py + my) * P.width + ((int) px + mx)];
+      else if (mctype == 2)
+	 ref = fut [(size_t) ((int) py + by) * P.width + ((int) px + bx)];
+      else
+	 ref = ((int) past [(size_t) ((int) py + my) * P.width + ((int) px + mx)]
+		+ (int) fut [(size_t) ((int) py + by) * P.width + ((int) px + bx)]) / 2;
+      const int16_t  d	= (int16_t) (orig [(size_t) py * P.width + px] - ref);
       cs.pixels [i] = (float) ((int) d / 16);
    }
    __syncthreads ();
@@ -2478,12 +2495,14 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 		  X.lrange.mv_tree_bits	 = mvt;
 		  X.lrange.mv_coord_bits = 0;
 		  X.lrange.mv_type = X.lrange.mv_fx = X.lrange.mv_fy = X.lrange.prediction = 0;
+		  X.lrange.mv_bx = X.lrange.mv_by = 0;
 		  X.r_mvt = mvt;
 		  X.r_mvc = 0;
 		  for (int label = 0; label < 2; label++)
 		  {
 		     X.child [label].mv_tree_bits = X.child [label].mv_coord_bits = 0;
 		     X.child [label].mv_type = X.child [label].mv_fx = X.child [label].mv_fy = 0;
+		     X.child [label].mv_bx = X.child [label].mv_by = 0;
 		     X.child [label].prediction = 0;
 		  }
 	       }
@@ -2509,10 +2528,13 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 	    /* clear_norms_table (prediction.c:195-211) */
 	    if (MOTION && h->fx [depth].try_mc && level > P.p_min)
 	    {
-	       float *nt = norms_of_level (P, W, level);
+	       for (int dir = 0; dir < (P.motion == 2 ? 2 : 1); dir++)
+	       {
+		  float *nt = norms_of_level (P, W, level, dir);
 
-	       for (int i = tid; i < 4 * P.sr * P.sr; i += NT)
-		  nt [i] = 0.0f;
+		  for (int i = tid; i < 4 * P.sr * P.sr; i += NT)
+		     nt [i] = 0.0f;
+	       }
 	    }
 	    /* alternative 1: linear combination (subdivide.c:200-221) */
 	    if (level <= P.lc_max)
@@ -2579,11 +2601,14 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 	 {
 	    if (MOTION)
 	    {
-	       float	   *up = norms_of_level (P, W, F.level);
-	       const float *lo = norms_of_level (P, W, F.level - 1);
+	       for (int dir = 0; dir < (P.motion == 2 ? 2 : 1); dir++)
+	       {
+		  float	      *up = norms_of_level (P, W, F.level, dir);
+		  const float *lo = norms_of_level (P, W, F.level - 1, dir);
 
-	       for (int i = tid; i < 4 * P.sr * P.sr; i += NT)
-		  up [i] += lo [i];
+		  for (int i = tid; i < 4 * P.sr * P.sr; i += NT)
+		     up [i] += lo [i];
+	       }
 	       if (tid == 0)
 		  nstate = ST_AFTER_CHILD2;
 	    }
@@ -2651,11 +2676,13 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 		     *res   = X.prange;
 		     res->x = (unsigned short) F.x;
 		     res->y = (unsigned short) F.y;
-		     rx->mv_tree_bits  = 1.0f;
+		     rx->mv_tree_bits  = X.mvt;
 		     rx->mv_coord_bits = X.mvc;
-		     rx->mv_type       = 1;	/* FORWARD */
-		     rx->mv_fx	       = (signed char) X.mx;
-		     rx->mv_fy	       = (signed char) X.my;
+		     rx->mv_type       = (signed char) X.mctype;	/* 1 FORWARD, 2 BACKWARD, 3 INTERPOLATED */
+		     rx->mv_fx	       = (signed char) (X.mctype != 2 ? X.mx : 0);
+		     rx->mv_fy	       = (signed char) (X.mctype != 2 ? X.my : 0);
+		     rx->mv_bx	       = (signed char) (X.mctype != 1 ? X.bx : 0);
+		     rx->mv_by	       = (signed char) (X.mctype != 1 ? X.by : 0);
 		     rx->prediction    = 1;
 		     h->ret_costs = (res->tree_bits + res->matrix_bits + res->weights_bits
 				     + rx->mv_tree_bits + rx->mv_coord_bits + 0.0f + 0.0f) * h->price
@@ -2741,25 +2768,106 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 	       __syncthreads ();
 	       if (level == P.p_min)
 		  cta_fill_norms<NT> (P, W, F.x, F.y, level);
-	       cta_find_best_mv<NT> (P, W, sh, F.x, F.y, level, h->price);
+	       cta_find_best_mv<NT> (P, W, sh, F.x, F.y, level, h->price, 0);
 	       if (tid == 0)
 	       {
-		  /* find_P_frame_mc (mwfa.c:301-339) */
-		  const int bi = h->best_i < 0 ? 0 : h->best_i;
+		  h->fi	    = h->best_i;
+		  h->fcosts = h->best_c;
+	       }
+	       if (P.motion == 2)
+	       {
+		  /* find_B_frame_mc (mwfa.c:341-542) without cross-B search: the best forward vector,
+		     the best backward vector, and both together */
+		  cta_find_best_mv<NT> (P, W, sh, F.x, F.y, level, h->price, 1);
+		  if (tid == 0)
+		  {
+		     h->bi     = h->best_i;
+		     h->bcosts = h->best_c;
+		     h->isum   = -1;
+		  }
+		  __syncthreads ();
+		  {
+		     /* squared norm of the interpolated prediction error (mcpe_norm, mwfa.c:651-684):
+			a sum of integers, exact in fp32 in any order while it stays below 2^24 */
+		     const int	    sr = P.sr;
+		     const int	    fx = h->fi < 0 ? 0 : h->fi % (2 * sr) - sr, fy = h->fi < 0 ? 0 : h->fi / (2 * sr) - sr;
+		     const int	    bx = h->bi < 0 ? 0 : h->bi % (2 * sr) - sr, by = h->bi < 0 ? 0 : h->bi / (2 * sr) - sr;
+		     const int	    bw = (int) width_of_level (level), bh = (int) height_of_level (level);
+		     const int16_t *orig = GP (W.pix), *past = GP (W.past), *fut = GP (W.future);
+		     long long	    acc = 0;
 
-		  X.mx	   = bi < 0 ? 0 : bi % (2 * P.sr) - P.sr;
-		  X.my	   = bi < 0 ? 0 : bi / (2 * P.sr) - P.sr;
-		  if (h->best_i < 0)
-		     X.mx = X.my = 0;
+		     for (int i = tid; i < bw * bh; i += NT)
+		     {
+			const int x = (int) F.x + i % bw, y = (int) F.y + i / bw;
+			const int ref = ((int) past [(size_t) (y + fy) * P.width + x + fx]
+					 + (int) fut [(size_t) (y + by) * P.width + x + bx]) / 2;
+			const int16_t d = (int16_t) (orig [(size_t) y * P.width + x] - ref);
+			const int     q = d / 16;
+
+			acc += q * q;
+		     }
+		     ((long long *) sh.num) [tid] = acc;
+		     __syncthreads ();
+		     if (tid == 0)
+		     {
+			long long tot = 0;
+			float	  norm;
+
+			for (int t = 0; t < NT; t++)
+			   tot += ((const long long *) sh.num) [t];
+			if (tot <= (1ll << 24))
+			   norm = (float) tot;
+			else
+			{
+			   norm = 0;		/* the reference's order: rows, left to right */
+			   for (int i = 0; i < bw * bh; i++)
+			   {
+			      const int x = (int) F.x + i % bw, y = (int) F.y + i / bw;
+			      const int ref = ((int) past [(size_t) (y + fy) * P.width + x + fx]
+					       + (int) fut [(size_t) (y + by) * P.width + x + bx]) / 2;
+			      const int16_t d = (int16_t) (orig [(size_t) y * P.width + x] - ref);
+			      const int	    q = d / 16;
+
+			      norm += (float) (q * q);
+			   }
+			}
+			const float fbits = (float) c_mv_code_length [fx + sr] + (float) c_mv_code_length [fy + sr];
+			const float bbits = (float) c_mv_code_length [bx + sr] + (float) c_mv_code_length [by + sr];
+			const float ibits = fbits + bbits;
+			const float fc	  = h->fcosts + 3 * h->price;
+			const float bc	  = h->bcosts + 3 * h->price;
+			const float ic	  = norm + (ibits + 2) * h->price;
+
+			if (fc <= ic)
+			   X.mctype = fc <= bc ? 1 : 2;
+			else
+			   X.mctype = bc <= ic ? 2 : 3;
+			X.mx = fx; X.my = fy; X.bx = bx; X.by = by;
+			X.mvt = X.mctype == 3 ? 2.0f : 3.0f;
+			X.mvc = X.mctype == 1 ? fbits : X.mctype == 2 ? bbits : ibits;
+			X.pcosts = (X.mvt + X.mvc) * h->price;
+		     }
+		  }
+	       }
+	       else if (tid == 0)
+	       {
+		  /* find_P_frame_mc (mwfa.c:301-339) */
+		  const int bi = h->fi < 0 ? 0 : h->fi;
+
+		  X.mx	   = bi % (2 * P.sr) - P.sr;
+		  X.my	   = bi / (2 * P.sr) - P.sr;
+		  X.bx	   = X.by = 0;
+		  X.mctype = 1;
+		  X.mvt	   = 1.0f;
 		  X.mvc	   = (float) c_mv_code_length [X.mx + P.sr] + (float) c_mv_code_length [X.my + P.sr];
-		  X.pcosts = (1.0f + X.mvc) * h->price;
+		  X.pcosts = (X.mvt + X.mvc) * h->price;
 	       }
 	       __syncthreads ();
 	       if (X.pcosts < X.max_pred)
 	       {
 		  /* the prediction error replaces the pixels, fresh product tables, and
 		     subdivide() on it with the delta models */
-		  cta_mcpe_range<NT> (P, W, shn, F.x, F.y, level, X.mx, X.my);
+		  cta_mcpe_range<NT> (P, W, shn, F.x, F.y, level, X.mctype, X.mx, X.my, X.bx, X.by);
 		  if (tid == 0)
 		  {
 		     float *t = W.T;
@@ -2877,6 +2985,8 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 			GP (W.mv_type) [2 * s + label] = cx.mv_type;
 			GP (W.mv_fx) [2 * s + label]   = cx.mv_fx;
 			GP (W.mv_fy) [2 * s + label]   = cx.mv_fy;
+			GP (W.mv_bx) [2 * s + label]   = cx.mv_bx;
+			GP (W.mv_by) [2 * s + label]   = cx.mv_by;
 		     }
 		     for (int e = 0; c.into [e] != FB_NO_EDGE; e++)
 		     {
@@ -2900,7 +3010,7 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 
 		     rx->mv_tree_bits  = h->fx [depth].r_mvt;
 		     rx->mv_coord_bits = h->fx [depth].r_mvc;
-		     rx->mv_type = rx->mv_fx = rx->mv_fy = rx->prediction = 0;
+		     rx->mv_type = rx->mv_fx = rx->mv_fy = rx->mv_bx = rx->mv_by = rx->prediction = 0;
 		  }
 		  h->ret_costs	    = sub;
 		  nstate	    = ST_RETURN;
@@ -3151,7 +3261,7 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
 	 sh.blob [i] = (i % P.blob_half) >= MB_COUNTS - 1 ? 1 : 0;
       if (MOTION)
 	 for (int i = tid; i < 2 * P.s_cap; i += NT)
-	    GP (W.mv_type) [i] = GP (W.mv_fx) [i] = GP (W.mv_fy) [i] = 0;
+	    GP (W.mv_type) [i] = GP (W.mv_fx) [i] = GP (W.mv_fy) [i] = GP (W.mv_bx) [i] = GP (W.mv_by) [i] = 0;
       __syncthreads ();
       /* a predicted frame has a second model set for the prediction errors: the delta pool and
 	 the delta coefficient model (coder.c:713-736), initialised like the first */

@@ -66,7 +66,7 @@ struct DevParams
    int	 big;			/* large state capacity, so that more tiles fit on an SM: bit 0 =
 				   Gram rows in global memory, bit 1 = model snapshots in global */
    /* predicted frames (codec/prediction.c, codec/mwfa.c): 0 = intra kernel */
-   int	 motion;		/* frame type: 0 intra, 1 P frame */
+   int	 motion;		/* frame type: 0 intra, 1 P frame, 2 B frame */
    int	 p_min, p_max;		/* levels of the motion compensated ranges (coder.c:284-290) */
    int	 sr;			/* search range: vectors in [-sr, sr) */
    int	 blob_half;		/* shorts of one model set; blob = normal set, then delta set */
@@ -107,12 +107,15 @@ struct TileWs
    fb200_trace_rec_t *trace;	/* [trace_cap] or NULL */
    /* predicted frames only */
    const int16_t *past;		/* [width*height] regenerated reference frame */
+   const int16_t *future;	/* the same for the backward prediction of a B frame */
    float   *T2;			/* [tn][s_cap]	 products of the nested (prediction error) pass */
-   float   *norms;		/* [p_max - p_min + 1][4 sr^2] norms tables of the motion search */
+   float   *norms;		/* [1 or 2][p_max - p_min + 1][4 sr^2] norms tables of the motion search
+				   (forward; B frames: then backward) */
    float   *pix2;		/* [2^p_max]	 prediction error block, bintree order */
    int	   *norm2;		/* [tn]		 its sums of squares per node */
    uint8_t *saved_dt;		/* [s_cap]	 domain types of the states a prediction attempt hides */
    int8_t  *mv_type, *mv_fx, *mv_fy;	/* [s_cap][2] motion vectors of the ranges (wfa->mv_tree) */
+   int8_t  *mv_bx, *mv_by;
 };
 
 struct TileResult

@@ -39,6 +39,7 @@ class _Wfa(C.Structure):
         ("domain_type", C.c_void_p), ("tree", C.c_void_p), ("x", C.c_void_p), ("y", C.c_void_p),
         ("into", C.c_void_p), ("weight", C.c_void_p), ("y_state", C.c_void_p), ("y_column", C.c_void_p),
         ("mv_type", C.c_void_p), ("mv_fx", C.c_void_p), ("mv_fy", C.c_void_p),
+        ("mv_bx", C.c_void_p), ("mv_by", C.c_void_p),
     ]
 
 
@@ -89,7 +90,8 @@ def load():
     lib.fb200_params_init.argtypes = [C.POINTER(Params), ip, ip, ip, C.c_float, ip, cp, C.c_size_t]
     lib.fb200_create.argtypes = [C.POINTER(vp), C.POINTER(Params), ip, ip, cp, C.c_size_t]
     lib.fb200_create_predicted.argtypes = [C.POINTER(vp), C.POINTER(Params), C.POINTER(Motion), ip, ip, cp, C.c_size_t]
-    lib.fb200_encode_predicted.argtypes = [vp, ip, C.POINTER(vp), C.POINTER(vp), C.POINTER(_Wfa), cp, C.c_size_t]
+    lib.fb200_encode_predicted.argtypes = [vp, ip, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(_Wfa), cp,
+                                           C.c_size_t]
     lib.fb200_destroy.argtypes = [vp]
     lib.fb200_destroy.restype = None
     lib.fb200_encode_tiles.argtypes = [vp, ip, C.POINTER(vp), C.POINTER(_Wfa), C.POINTER(TraceRec), ip,
@@ -146,11 +148,13 @@ class _WfaArrays:
         self.mv_type = np.zeros((cap, 2), np.int8)
         self.mv_fx = np.zeros((cap, 2), np.int8)
         self.mv_fy = np.zeros((cap, 2), np.int8)
+        self.mv_bx = np.zeros((cap, 2), np.int8)
+        self.mv_by = np.zeros((cap, 2), np.int8)
 
     def fill(self, w):
         w.capacity = self.cap
         for name in ("final_distribution", "level_of_state", "domain_type", "tree", "x", "y", "into", "weight",
-                     "y_state", "y_column", "mv_type", "mv_fx", "mv_fy"):
+                     "y_state", "y_column", "mv_type", "mv_fx", "mv_fy", "mv_bx", "mv_by"):
             setattr(w, name, getattr(self, name).ctypes.data)
 
 
@@ -208,7 +212,7 @@ class TileEncoder:
                 "matrix_bits": list(w.matrix_bits), "weights_bits": list(w.weights_bits),
             }
             for name in ("final_distribution", "level_of_state", "domain_type", "tree", "x", "y", "into", "weight",
-                         "y_state", "y_column") + (("mv_type", "mv_fx", "mv_fy") if self.motion is not None else ()):
+                         "y_state", "y_column") + (("mv_type", "mv_fx", "mv_fy", "mv_bx", "mv_by") if self.motion is not None else ()):
                 d[name] = getattr(a, name)[:n].copy()
             out.append(d)
         tr = None
@@ -227,15 +231,21 @@ class TileEncoder:
         _check(rc, err)
         return self._collect(n_tiles, trace, tl)
 
-    def encode_predicted(self, planes, past):
-        """One predicted frame per tile: planes[t] the frame, past[t] the regenerated previous frame."""
+    def encode_predicted(self, planes, past, future=None):
+        """One predicted frame per tile: planes[t] the frame, past[t] the regenerated previous frame
+        (future[t]: the regenerated next reference, B frames)."""
         n_tiles = len(planes)
         ptrs = self._plane_ptrs(planes)
-        keep = self._keep
+        keep = [self._keep]
         pptrs = self._plane_ptrs(past)
-        self._keep = (keep, self._keep)
+        keep.append(self._keep)
+        fptrs = None
+        if future is not None:
+            fptrs = self._plane_ptrs(future)
+            keep.append(self._keep)
+        self._keep = keep
         err = C.create_string_buffer(512)
-        _check(self.lib.fb200_encode_predicted(self.ctx, n_tiles, ptrs, pptrs, self._wfas, err, 512), err)
+        _check(self.lib.fb200_encode_predicted(self.ctx, n_tiles, ptrs, pptrs, fptrs, self._wfas, err, 512), err)
         return self._collect(n_tiles, None, None)[0]
 
     def upload(self, planes):

@@ -381,7 +381,7 @@ fiasco_coder (char const *const *inputname, const char *outputname, float qualit
 	    }
 	    if (!cnt)
 	       break;
-	    rc = fb200_encode_predicted (pctx, (int) cnt, bplane, bpast, batch, err, sizeof err);
+	    rc = fb200_encode_predicted (pctx, (int) cnt, bplane, bpast, NULL, batch, err, sizeof err);
 	    if (rc != FB200_OK)
 	    {
 	       fb200_destroy (pctx);

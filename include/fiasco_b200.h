@@ -107,8 +107,10 @@ typedef struct fb200_wfa
    int16_t  *y_state;			     /* [capacity][2] */
    uint8_t  *y_column;		     /* [capacity][2] */
    /* predicted frames (fb200_encode_predicted; may be NULL): motion vectors of the ranges,
-      mv_t of wfa->mv_tree, codec/wfa.h:62-71 -- type 0 none, 1 forward */
+      mv_t of wfa->mv_tree, codec/wfa.h:62-71 -- type 0 none, 1 forward, 2 backward,
+      3 interpolated */
    int8_t   *mv_type, *mv_fx, *mv_fy;	     /* [capacity][2] */
+   int8_t   *mv_bx, *mv_by;		     /* [capacity][2] backward vectors (B frames) */
 } fb200_wfa_t;
 
 /* one record per approximate_range() call (debug / parity tracing, optional) */
@@ -210,15 +212,16 @@ int fb200_motion_norms (int device, const int16_t *orig, const int16_t *past, in
 
 /*
  *  Predicted frames of a sequence (replaces, in the reference coder, the same subdivide() call
- *  at codec/coder.c:743 when the frame is a P frame, i.e. with its third alternative:
- *  predict_range / mc_prediction, codec/prediction.c:96,262; find_P_frame_mc, fill_norms_table,
- *  find_best_mv, codec/mwfa.c:301,544,686; and the nested subdivide() over the prediction error
+ *  at codec/coder.c:743 when the frame is a P or B frame, i.e. with its third alternative:
+ *  predict_range / mc_prediction, codec/prediction.c:96,262; find_P_frame_mc, find_B_frame_mc
+ *  (without the cross-B search, which the reference ties to the half-pixel flag, coder.c:359),
+ *  fill_norms_table, find_best_mv, codec/mwfa.c:301,341,544,686; and the nested subdivide() over the prediction error
  *  with the delta pool and delta coefficient model).  Levels and search range as in
  *  c_options_t (codec/options.h: p_min_level, p_max_level, search_range; CLI defaults 6, 10, 16).
  */
 typedef struct fb200_motion
 {
-   int frame_type;		/* 1 = P frame (B frames: not on the device yet) */
+   int frame_type;		/* 1 = P frame, 2 = B frame */
    int p_min_level, p_max_level;
    int search_range;		/* vectors in [-search_range, search_range), full pixel */
 } fb200_motion_t;
@@ -230,15 +233,16 @@ int fb200_create_predicted (fb200_ctx_t **ctx, const fb200_params_t *p,
 
 /*
  *  Encode one predicted frame per tile: planes[t] is the frame, past[t] the REGENERATED previous
- *  frame of the same sequence (fiasco_regenerate_frame() of include/fiasco_host.h; what
+ *  frame of the same sequence (future[t]: the regenerated next reference frame, B frames only, else
+ *  NULL) (fiasco_regenerate_frame() of include/fiasco_host.h; what
  *  decode_image + restore_mc leave in the reference, codec/coder.c:642-651), both width*height
  *  shorts in host memory.  The automata come back as the device leaves them: states of losing
  *  alternatives are holes (level_of_state == 255) and out[t].mv_* hold the vectors;
  *  fiasco_finish_predicted_frame() closes the holes and derives the delta flags.
  */
 int fb200_encode_predicted (fb200_ctx_t *ctx, int n_tiles, const int16_t *const *planes,
-			    const int16_t *const *past, fb200_wfa_t *out,
-			    char *err, size_t errlen);
+			    const int16_t *const *past, const int16_t *const *future,
+			    fb200_wfa_t *out, char *err, size_t errlen);
 
 const char *fb200_version (void);
 
