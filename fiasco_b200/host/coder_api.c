@@ -89,6 +89,66 @@ is_intra (unsigned frame, const char *pattern)
    return frame == 0 || toupper ((unsigned char) pattern [frame % strlen (pattern)]) == 'I';
 }
 
+/* 0 = I, 1 = P, 2 = B by the pattern (frame 0 is always intra) */
+static int
+pattern_type (unsigned frame, const char *pattern)
+{
+   const int t = toupper ((unsigned char) pattern [frame % strlen (pattern)]);
+
+   return frame == 0 || t == 'I' ? 0 : t == 'P' ? 1 : t == 'B' ? 2 : -1;
+}
+
+/*
+ *  The order in which video_coder() codes the frames (coder.c:490-680): display order, except
+ *  that a B frame waits for the next non-B frame (its future reference), which is coded first;
+ *  a B frame at the very end of the sequence is coded as a P frame.  order [k] = display number
+ *  of the k-th coded frame, ctype [display number] = type it is coded with.
+ */
+static void
+coding_order (unsigned frames, const char *pattern, unsigned *order, int *ctype)
+{
+   int display = 0, future_display = -1, coded = 0;
+
+   while (display < (int) frames)
+   {
+      int type = pattern_type ((unsigned) display, pattern), frame;
+
+      if (display == future_display)		/* already coded as a future reference */
+      {
+	 display++;
+	 continue;
+      }
+      else if (type == 2 && display > future_display)
+      {
+	 int i = display;
+
+	 frame = display;
+	 while (type == 2)
+	 {
+	    i++;
+	    if (i >= (int) frames)
+	    {
+	       future_display = i - 1;
+	       type	      = 1;
+	    }
+	    else
+	    {
+	       future_display = i;
+	       type	      = pattern_type ((unsigned) i, pattern);
+	    }
+	    frame = future_display;
+	 }
+      }
+      else
+      {
+	 frame = display;
+	 display++;
+      }
+      order [coded++] = (unsigned) frame;
+      ctype [frame]   = type;
+   }
+}
+
 int
 fiasco_coder (char const *const *inputname, const char *outputname, float quality,
 	      const fiasco_c_options_t *options)
@@ -107,7 +167,9 @@ fiasco_coder (char const *const *inputname, const char *outputname, float qualit
       fi_image_t	**images;
       const int16_t	**planes;
       unsigned		  frames, width = 0, height = 0, n, bands, n_predicted = 0;
-      unsigned		  n_intra = 0;
+      unsigned		  n_intra = 0, has_b = 0;
+      unsigned		 *order;		/* coding order */
+      int		 *ctype;		/* frame types as coded */
       fb200_ctx_t	 *pctx = NULL;
       int16_t		**recon = NULL;		/* regenerated frames (references of P frames) */
       uint8_t		**delta = NULL;		/* delta flags of the states of P frames */
@@ -179,12 +241,20 @@ fiasco_coder (char const *const *inputname, const char *outputname, float qualit
       bands = color ? 3 : 1;
 
       /* what this build does not do is refused, not approximated */
+      order = fiasco_calloc (frames, sizeof (unsigned));
+      ctype = fiasco_calloc (frames, sizeof (int));
       for (n = 0; n < frames; n++)
-	 if (!is_intra (n, cop->pattern))
+	 if (pattern_type (n, cop->pattern) < 0)
+	    fi_error ("Frame type %c not valid. Choose one of I,B or P.",
+		      cop->pattern [n % strlen (cop->pattern)]);
+      coding_order (frames, cop->pattern, order, ctype);
+      for (n = 0; n < frames; n++)
+	 if (ctype [n])
 	 {
-	    if (toupper ((unsigned char) cop->pattern [n % strlen (cop->pattern)]) != 'P')
-	       fi_error ("Frame %d (pattern `%s'): of the predicted frame types only P frames "
-			 "are available in the B200 build.", n, cop->pattern);
+	    if (ctype [n] == 2)
+	       has_b = 1;
+	    if (ctype [n] == 2 && !cop->B_as_past_ref)
+	       fi_error ("B frames: only the default `B frames as past references' is available.");
 	    if (color)
 	       fi_error ("Predicted frames are available for grey sequences only.");
 	    if (cop->half_pixel_prediction)
@@ -288,7 +358,7 @@ fiasco_coder (char const *const *inputname, const char *outputname, float qualit
 	 unsigned     b, i;
 
 	 for (n = 0; n < frames; n++)
-	    if (is_intra (n, cop->pattern))
+	    if ((ctype [n] == 0))
 	    {
 	       for (b = 0; b < bands; b++)
 		  iplanes [n_intra * bands + b] = planes [n * bands + b];
@@ -303,7 +373,7 @@ fiasco_coder (char const *const *inputname, const char *outputname, float qualit
 	 if (rc != FB200_OK)
 	    fi_error ("%s", err [0] ? err : "GPU encoder failed");
 	 for (n = 0, i = 0; n < frames; n++)
-	    if (is_intra (n, cop->pattern))
+	    if ((ctype [n] == 0))
 	       wfas [n] = batch [i++];
 	 free (batch);
       }
@@ -315,7 +385,105 @@ fiasco_coder (char const *const *inputname, const char *outputname, float qualit
        *  block per group), then the host closes the holes of the automata, derives the delta
        *  flags and regenerates the frames for step k + 1.
        */
-      if (n_predicted)
+      if (n_predicted && has_b)
+      {
+	 /*
+	  *  Sequences with B frames: the frames in coding order, one launch per predicted frame,
+	  *  with the reference bookkeeping of video_coder() (coder.c:571-627): a P frame is
+	  *  predicted from the last regenerated frame; a B frame from a past and a future frame,
+	  *  where the frame regenerated last becomes the future reference if it was coded ahead
+	  *  of its display time, else (B frames serve as past references) the past one.
+	  */
+	 fb200_ctx_t	*bctx = NULL;
+	 fb200_motion_t	 mo;
+	 const int16_t	*past = NULL, *future = NULL, *cur = NULL;
+	 int		 future_frame = 0, expected = 0;
+	 unsigned	 k;
+	 uint8_t	*seen = fiasco_calloc (frames + 1, 1);
+	 jmp_buf	 saved;
+
+	 recon = fiasco_calloc (frames, sizeof (int16_t *));
+	 delta = fiasco_calloc (frames, sizeof (uint8_t *));
+	 mo.p_min_level	 = (int) wi.p_min_level;
+	 mo.p_max_level	 = (int) wi.p_max_level;
+	 mo.search_range = (int) cop->search_range;
+	 for (k = 0; k < frames; k++)
+	 {
+	    fiasco_frame_motion_t fm;
+	    const int		  type = ctype [n = order [k]];
+
+	    if (type == 1)
+	    {
+	       past   = cur;
+	       future = NULL;
+	    }
+	    else if (type == 2)
+	    {
+	       if (future_frame)
+		  future = cur;
+	       else
+		  past = cur;
+	    }
+	    else
+	       past = future = NULL;
+	    seen [n]	 = 1;
+	    future_frame = (int) n > expected;
+	    while (expected < (int) frames && seen [expected])
+	       expected++;
+	    memset (&fm, 0, sizeof fm);
+	    if (type)
+	    {
+	       fb200_ctx_t **cx = type == 2 ? &bctx : &pctx;
+
+	       /* e.g. a B frame whose future reference is an I frame: the reference coder drops
+		  the past frame there (coder.c:581-591) and then reads through the NULL pointer */
+	       if (!past || (type == 2 && !future))
+		  fi_error ("Frame %d (pattern `%s') has no reference frame to be predicted from.",
+			    n, cop->pattern);
+	       if (!*cx)
+	       {
+		  mo.frame_type = type;
+		  rc = fb200_create_predicted (cx, &p, &mo, 1, 0, err, sizeof err);
+		  if (rc != FB200_OK)
+		     fi_error ("%s", err [0] ? err : "GPU encoder failed");
+	       }
+	       rc = fb200_encode_predicted (*cx, 1, &planes [n], &past, type == 2 ? &future : NULL,
+					    &wfas [n], err, sizeof err);
+	       if (rc != FB200_OK)
+		  fi_error ("%s", err [0] ? err : "GPU encoder failed");
+	       delta [n] = fiasco_calloc (FI_MAXSTATES, 1);
+	       memcpy (saved, fi_env, sizeof saved);
+	       rc = fiasco_finish_predicted_frame (&wfas [n], wfas [n].mv_type, wfas [n].mv_fx,
+						   wfas [n].mv_fy, wfas [n].mv_bx, wfas [n].mv_by,
+						   delta [n]);
+	       memcpy (fi_env, saved, sizeof saved);
+	       if (!rc)
+		  fi_error ("%s", fiasco_get_error_message ());
+	       fm.frame_type  = type;
+	       fm.mv_type     = wfas [n].mv_type;
+	       fm.mv_fx	      = wfas [n].mv_fx;
+	       fm.mv_fy	      = wfas [n].mv_fy;
+	       fm.mv_bx	      = wfas [n].mv_bx;
+	       fm.mv_by	      = wfas [n].mv_by;
+	       fm.delta_state = delta [n];
+	    }
+	    /* regenerate the frame: a reference of the frames to come (coder.c:642-651) */
+	    recon [n] = fiasco_calloc ((size_t) width * height, sizeof (int16_t));
+	    memcpy (saved, fi_env, sizeof saved);
+	    rc = fiasco_regenerate_frame (&wfas [n], &fm, (int) width, (int) height, past, future,
+					  recon [n]);
+	    memcpy (fi_env, saved, sizeof saved);
+	    if (!rc)
+	       fi_error ("%s", fiasco_get_error_message ());
+	    cur = recon [n];
+	 }
+	 if (pctx)
+	    fb200_destroy (pctx);
+	 if (bctx)
+	    fb200_destroy (bctx);
+	 free (seen);
+      }
+      else if (n_predicted)
       {
 	 fb200_motion_t	 mo;
 	 fb200_wfa_t	*batch	= fiasco_calloc (frames, sizeof (fb200_wfa_t));
@@ -328,7 +496,7 @@ fiasco_coder (char const *const *inputname, const char *outputname, float qualit
 	 recon = fiasco_calloc (frames, sizeof (int16_t *));
 	 delta = fiasco_calloc (frames, sizeof (uint8_t *));
 	 for (n = 1; n < frames; n++)
-	    if (!is_intra (n, cop->pattern) && is_intra (n - 1, cop->pattern))
+	    if ((ctype [n] != 0) && (ctype [n - 1] == 0))
 	       groups++;
 	 mo.frame_type	 = 1;
 	 mo.p_min_level	 = (int) wi.p_min_level;
@@ -345,11 +513,11 @@ fiasco_coder (char const *const *inputname, const char *outputname, float qualit
 	    {
 	       unsigned j;
 
-	       if (is_intra (n, cop->pattern))
+	       if ((ctype [n] == 0))
 		  continue;
-	       for (j = 1; j < k && !is_intra (n - j, cop->pattern); j++)
+	       for (j = 1; j < k && (ctype [n - j] != 0); j++)
 		  ;
-	       if (j != k || !is_intra (n - k, cop->pattern))
+	       if (j != k || (ctype [n - k] != 0))
 		  continue;			/* not the k-th frame of its group */
 	       if (!recon [n - 1])
 	       {
@@ -408,14 +576,17 @@ fiasco_coder (char const *const *inputname, const char *outputname, float qualit
       }
       free (iplanes);
 
-      for (n = 0; n < frames; n++)
+      for (unsigned coded = 0; coded < frames; coded++)
       {
 	 fi_wfa_t w;
 
+	 n = order [coded];		/* the stream holds the frames in coding order */
 	 memset (&w, 0, sizeof w);	/* intra frame: no motion data */
-	 if (!is_intra (n, cop->pattern))
+	 if ((ctype [n] != 0))
 	 {
-	    w.frame_type  = 1;
+	    w.frame_type  = ctype [n];
+	    w.mv_bx	  = (const int8_t (*)[2]) wfas [n].mv_bx;
+	    w.mv_by	  = (const int8_t (*)[2]) wfas [n].mv_by;
 	    w.x		  = (const uint16_t (*)[2]) wfas [n].x;
 	    w.y		  = (const uint16_t (*)[2]) wfas [n].y;
 	    w.mv_type	  = (const int8_t (*)[2]) wfas [n].mv_type;
@@ -437,7 +608,7 @@ fiasco_coder (char const *const *inputname, const char *outputname, float qualit
 	 fi_debug_message ("WFA contains %d states (%d basis states).", w.states,
 			   w.basis_states);
 	 fi_debug_message ("Total costs : %.2f", (double) wfas [n].costs [0]);
-	 fi_write_next_wfa (&w, n, n == 0, cop->normal_domains, cop->delta_domains, output);
+	 fi_write_next_wfa (&w, n, coded == 0, cop->normal_domains, cop->delta_domains, output);
 	 fb200_wfa_free (&wfas [n]);
 	 fi_free_image (images [n]);
 	 if (recon)
@@ -447,6 +618,8 @@ fiasco_coder (char const *const *inputname, const char *outputname, float qualit
       }
       free (recon);
       free (delta);
+      free (order);
+      free (ctype);
       if (cop->progress_meter != FIASCO_PROGRESS_NONE)
 	 fi_message ("");
       fi_bits_close (output);

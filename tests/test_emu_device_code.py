@@ -140,11 +140,67 @@ def test_emulated_device_code_predicted_frames(emu, name):
     assert checked >= 3
 
 
-@pytest.mark.parametrize("name", ["v160_q20_ippp", "v352_q30_ippip"])
+def predicted_frames_in_coding_order(name):
+    """(frame type, display number, plane, past, future, oracle automaton in holes mode) of every predicted
+    frame of a golden sequence, with the reference bookkeeping of video_coder() (codec/coder.c:571-627)
+    and the oracle's regenerated frames as references."""
+    m, frames, ws, rec = _holes_mode_automata(name)
+    past = future = reconst = None
+    future_frame, expected, seen, out = False, 0, set(), []
+    for k, w in enumerate(ws):
+        d = O.struct_dict(w["_struct"])
+        if d["frame_type"] == 0:
+            past = future = None
+        elif d["frame_type"] == 1:
+            past, future = reconst, None
+        elif future_frame:
+            future = reconst
+        else:
+            past = reconst
+        seen.add(d["frame_number"])
+        future_frame = d["frame_number"] > expected
+        while expected in seen:
+            expected += 1
+        if d["frame_type"]:
+            out.append((d["frame_type"], d["frame_number"], O.planes_of(frames[d["frame_number"]])[0], past, future, d))
+        reconst = rec[k]
+    return m, out
+
+
+def check_b_frame_sequence(name="v160_q20_ibbp"):
+    m, todo = predicted_frames_in_coding_order(name)
+    p = ffi.make_params(m["width"], m["height"], 1, float(m["quality"]), 0)
+    encs = {t: F.TileEncoder(p, 1, motion=F.Motion(t, 6, 10, 16)) for t in (1, 2)}
+    used = np.zeros(4, int)
+    try:
+        for t, number, plane, past, future, d in todo:
+            g = encs[t].encode_predicted([plane], [past], [future] if t == 2 else None)[0]
+            assert_same_predicted_automaton(g, d)
+            n = d["states"]
+            live = d["level_of_state"][:n] != 255
+            assert np.array_equal(g["mv_bx"][:n][live], d["mv_bx"][:n][live])
+            assert np.array_equal(g["mv_by"][:n][live], d["mv_by"][:n][live])
+            if t == 2:
+                used += np.bincount(d["mv_type"][:n][live].ravel(), minlength=4)
+    finally:
+        for e_ in encs.values():
+            e_.close()
+    assert used[1] and used[2] and used[3]          # forward, backward and interpolated ranges occurred
+
+
+def test_emulated_device_code_b_frames(emu):
+    """B frames (find_B_frame_mc: best forward vector, best backward vector, both together; backward
+    norms tables; interpolated prediction error), coded out of display order, B frames as past
+    references: every predicted frame of the golden IBBP sequence against the oracle in holes mode."""
+    check_b_frame_sequence()
+
+
+@pytest.mark.parametrize("name", ["v160_q20_ippp", "v352_q30_ippip", "v160_q20_ibbp"])
 def test_emulated_fiasco_coder_writes_the_reference_stream_for_sequences(emu, name, tmp_path):
-    """fiasco_coder() on a sequence with P frames -- I frames in one launch, the P frames group by
-    group along their chains, holes closed and frames regenerated on the host between the steps -- writes
-    the stream the reference cfiasco writes, byte for byte (md5 of the golden .fco)."""
+    """fiasco_coder() on a sequence with predicted frames -- I frames in one launch, the P frames group by
+    group along their chains (sequences with B frames: frame by frame in coding order), holes closed and
+    frames regenerated on the host between the steps -- writes the stream the reference cfiasco writes,
+    byte for byte (md5 of the golden .fco)."""
     import hashlib
     from fiasco_b200 import hostlib
     saved = (hostlib._LIB, hostlib.lib_path)

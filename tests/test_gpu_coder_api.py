@@ -109,17 +109,17 @@ def test_intra_sequence_matches_reference_cli(tmp_path):
         assert md5(out) == md5(ref_out)
 
 
-def test_b_frames_are_refused_not_approximated(tmp_path):
-    """P frames are coded (tests/test_gpu_predicted.py); B frames are not on the device yet and are
-    refused with a message."""
+def test_frames_without_reference_are_refused(tmp_path):
+    """A B frame whose future reference is an I frame: the reference coder drops the past frame there
+    (codec/coder.c:581-591) and reads through the NULL pointer; we refuse with a message."""
     p = str(tmp_path / "f.pgm")
     gen_frames.write_pnm(p, gen_frames.frame("g256")[:64, :64])
     L = hostlib.load()
     o = hostlib.cli_options(0)
-    L.fiasco_c_options_set_frame_pattern(o, b"ibp")
+    L.fiasco_c_options_set_frame_pattern(o, b"ibi")
     ok, msg = hostlib.coder([p, p, p], str(tmp_path / "o.fco"), options=o)
     L.fiasco_c_options_delete(o)
-    assert not ok and "only P frames" in msg
+    assert not ok and "no reference frame" in msg
 
 
 def test_default_pattern_sequence_matches_reference_cli(tmp_path):

@@ -11,7 +11,7 @@ import fiasco_b200 as F
 from fiasco_b200 import ffi, hostlib
 import oracle_lib as O
 import gen_frames
-from test_emu_device_code import _holes_mode_automata, assert_same_predicted_automaton
+from test_emu_device_code import _holes_mode_automata, assert_same_predicted_automaton, check_b_frame_sequence
 
 pytestmark = pytest.mark.gpu
 
@@ -55,7 +55,11 @@ def test_gpu_predicted_frames_of_several_sequences_in_one_launch():
         enc.close()
 
 
-@pytest.mark.parametrize("name", ["v160_q20_ippp", "v352_q30_ippip"])
+def test_gpu_b_frames_match_oracle():
+    check_b_frame_sequence()
+
+
+@pytest.mark.parametrize("name", ["v160_q20_ippp", "v352_q30_ippip", "v160_q20_ibbp"])
 def test_gpu_fiasco_coder_sequence_stream_is_byte_identical(name, tmp_path):
     m = O.manifest()[name]
     names = []
