@@ -4,13 +4,13 @@
  *  Host-side control flow in the order of the reference (codec/coder.c:85-187 fiasco_coder,
  *  :190-372 alloc_coder, :390-488 input name templates, :490-690 video_coder, :692-892
  *  frame_coder); everything below frame_coder's subdivide() call runs on the GPU through
- *  fb200_encode_tiles() (include/fiasco_b200.h), the finished automaton comes back and is
- *  serialised by fco_writer.c.
+ *  fb200_encode_tiles() / fb200_encode_predicted() (include/fiasco_b200.h), the finished
+ *  automaton comes back and is serialised by fco_writer.c.
  *
- *  Supported: still images and sequences of intra frames (frame pattern of I only), grey
- *  and colour (4:4:4), the built-in initial basis "small.fco", rle domain pool, adaptive
- *  coefficient model, optimisation levels 0..2 of the command line.  Everything else is
- *  refused with an error message (never silently approximated).
+ *  Supported: still images and sequences, grey and colour (4:4:4) intra frames, P and B frames
+ *  of grey sequences (full-pixel vectors), the built-in initial basis "small.fco", rle domain
+ *  pool, adaptive coefficient model, optimisation levels 0..2 of the command line.  Everything
+ *  else is refused with an error message (never silently approximated).
  */
 #include <ctype.h>
 #include <math.h>
@@ -83,11 +83,7 @@ input_name (char const *const *templptr, unsigned ith_image)
    return NULL;
 }
 
-static int
-is_intra (unsigned frame, const char *pattern)
-{
-   return frame == 0 || toupper ((unsigned char) pattern [frame % strlen (pattern)]) == 'I';
-}
+
 
 /* 0 = I, 1 = P, 2 = B by the pattern (frame 0 is always intra) */
 static int

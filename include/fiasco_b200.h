@@ -203,8 +203,10 @@ int fb200_probe (int kind, int n, const float *f, const int *a, const int *b,
  *  (original - reference displaced by (mx, my)) / 16, bit-identical to the reference's sums.
  *  orig / past: width * height shorts (the coder's pixel format, host memory).  norms (host):
  *  [rows of blocks][columns of blocks][(my + sr) * 2 sr + (mx + sr)], 0 for blocks or
- *  displacements that leave the frame.  kernel_ms (or NULL): device time of the kernel.  Building
- *  block of the motion path; the tile kernel does not consume it yet.
+ *  displacements that leave the frame.  kernel_ms (or NULL): device time of the kernel.  A
+ *  stand-alone kernel (analysis, benchmarks): fb200_encode_predicted() computes its tables inside
+ *  the tile kernel in the reference's lazy order, because the partial sums that aborted subtrees
+ *  leave behind are part of the reference's result.
  */
 int fb200_motion_norms (int device, const int16_t *orig, const int16_t *past, int width,
 			int height, int level, int search_range, float *norms, float *kernel_ms,

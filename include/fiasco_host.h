@@ -60,9 +60,9 @@ typedef struct fiasco_frame_motion
 /*
  *  fiasco_write_stream() for sequences with predicted frames: writes the motion tree and the
  *  vectors (output/mc.c:75) and codes the weights of delta states in their own contexts
- *  (output/weights.c:38).  motion == NULL: all frames intra.  The GPU path does not produce
- *  predicted frames yet; this is the host half of that row, checked against
- *  the reference's stream on automata of the test oracle.
+ *  (output/weights.c:38).  motion == NULL: all frames intra.  The automata of predicted frames
+ *  come from fb200_encode_predicted() + fiasco_finish_predicted_frame(); frames are passed in
+ *  coding order (fiasco_frame_motion_t.frame_number is the display number).
  */
 int fiasco_write_video_stream (const char *filename, const fiasco_stream_info_t *info,
 			       const fb200_wfa_t *frames, const fiasco_frame_motion_t *motion,
@@ -80,7 +80,7 @@ int fiasco_regenerate_frame (const fb200_wfa_t *wfa, const fiasco_frame_motion_t
 			     int16_t *out);
 
 /*
- *  Finish the automaton of a predicted frame the way the device will leave it:
+ *  Finish the automaton of a predicted frame the way the device leaves it:
  *  close the holes of losing split alternatives (states marked level_of_state == 255) by a monotone
  *  renumbering and derive the delta flags from the structure (locate_delta_images,
  *  codec/wfalib.c:699, called at codec/coder.c:876).  In place; mv_* are [states][2], delta_state

@@ -120,22 +120,3 @@ def test_frames_without_reference_are_refused(tmp_path):
     ok, msg = hostlib.coder([p, p, p], str(tmp_path / "o.fco"), options=o)
     L.fiasco_c_options_delete(o)
     assert not ok and "no reference frame" in msg
-
-
-def test_default_pattern_sequence_matches_reference_cli(tmp_path):
-    """The CLI's default frame pattern (ippppppppp): a short sequence through fiasco_coder() gives the
-    reference CLI's bytes when the reference binary is available on the box."""
-    names = []
-    for i, f in enumerate(gen_frames.video(4, 176, 144)):
-        names.append(str(tmp_path / ("f%02d.pgm" % i)))
-        gen_frames.write_pnm(names[-1], f)
-    out = str(tmp_path / "seq.fco")
-    ok, msg = hostlib.coder(names, out)
-    assert ok, msg
-    cf = os.path.join(REF, "cfiasco")
-    if os.path.exists(cf):
-        ref_out = str(tmp_path / "ref.fco")
-        env = dict(os.environ, FIASCO_DATA=os.path.join(REF, "data"), FIASCO_IMAGES=str(tmp_path))
-        subprocess.run([cf, "--progress-meter=0", "-V", "0", "-q", "20", "-o", ref_out] + names,
-                       env=env, check=True, capture_output=True)
-        assert md5(out) == md5(ref_out)

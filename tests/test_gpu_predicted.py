@@ -3,6 +3,7 @@
 golden streams of the reference coder.  Bit exact: states, edges, weights, vectors, stream bytes."""
 import hashlib
 import os
+import subprocess
 
 import numpy as np
 import pytest
@@ -14,6 +15,12 @@ import gen_frames
 from test_emu_device_code import _holes_mode_automata, assert_same_predicted_automaton, check_b_frame_sequence
 
 pytestmark = pytest.mark.gpu
+
+REF = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+
+
+def md5(path):
+    return hashlib.md5(open(path, "rb").read()).hexdigest()
 
 
 @pytest.mark.parametrize("name", ["v160_q20_ippp", "v352_q30_ippip"])
@@ -72,3 +79,22 @@ def test_gpu_fiasco_coder_sequence_stream_is_byte_identical(name, tmp_path):
     ok, msg = hostlib.coder(names, out, float(m["quality"]), options=o)
     assert ok, msg
     assert hashlib.md5(open(out, "rb").read()).hexdigest() == m["fco_md5"]
+
+
+def test_default_pattern_sequence_matches_reference_cli(tmp_path):
+    """The CLI's default frame pattern (ippppppppp): a short sequence through fiasco_coder() gives the
+    reference CLI's bytes when the reference binary is available on the box."""
+    names = []
+    for i, f in enumerate(gen_frames.video(4, 176, 144)):
+        names.append(str(tmp_path / ("f%02d.pgm" % i)))
+        gen_frames.write_pnm(names[-1], f)
+    out = str(tmp_path / "seq.fco")
+    ok, msg = hostlib.coder(names, out)
+    assert ok, msg
+    cf = os.path.join(REF, "cfiasco")
+    if os.path.exists(cf):
+        ref_out = str(tmp_path / "ref.fco")
+        env = dict(os.environ, FIASCO_DATA=os.path.join(REF, "data"), FIASCO_IMAGES=str(tmp_path))
+        subprocess.run([cf, "--progress-meter=0", "-V", "0", "-q", "20", "-o", ref_out] + names,
+                       env=env, check=True, capture_output=True)
+        assert md5(out) == md5(ref_out)
