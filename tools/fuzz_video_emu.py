@@ -4,7 +4,7 @@ under the thread emulator (tests/emu, test infrastructure) against the unmodifie
 (oracle/_ref/cfiasco) on random short sequences -- sizes, qualities, frame patterns with P and B frames,
 thread scheduling orders of the emulator.  The streams must be identical byte for byte.
 
-    python tools/fuzz_video_emu.py [cases] [seed]
+    python tools/fuzz_video_emu.py [cases] [seed] [largest side, default 200]
 """
 import hashlib
 import os
@@ -47,6 +47,7 @@ def sequence(rng, n, w, h):
 def main():
     cases = int(sys.argv[1]) if len(sys.argv) > 1 else 20
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    side = int(sys.argv[3]) if len(sys.argv) > 3 else 200
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tests", "emu")], check=True)
     ffi.lib_path = lambda: os.path.join(EMU, "libfiasco_b200_emu.so")
     hostlib.lib_path = lambda: os.path.join(EMU, "libfiasco_emu.so")
@@ -56,8 +57,8 @@ def main():
     rng = np.random.default_rng(seed)
     bad = 0
     for case in range(cases):
-        w = int(rng.integers(16, 100)) * 2
-        h = int(rng.integers(16, 100)) * 2
+        w = int(rng.integers(16, side // 2)) * 2
+        h = int(rng.integers(16, side // 2)) * 2
         n = int(rng.integers(2, 7))
         q = float(rng.choice([5, 10, 20, 35, 60]))
         pattern = str(rng.choice(["ippp", "ip", "ippip", "ibbp", "ibp", "ibbbp", "ipbp", "ippppppppp"]))
