@@ -56,6 +56,7 @@ Block	       B;
    1 descending, 2 pseudo-random.  A result that depends on it is a race between barriers. */
 int	       g_order = -1;
 unsigned       g_rand  = 12345u;
+unsigned long long g_barriers, g_warp_ops;	/* rendezvous counters (whole process) */
 char	      *g_stacks;
 size_t	       g_stacks_n;
 unsigned char *g_smem;
@@ -112,6 +113,15 @@ fibre_main (void)
 
 } /* namespace */
 
+/* block barriers and warp collectives executed so far: the length of the dependent chain of a
+   launch in units the GPU pays latency for (tools) */
+extern "C" void
+emu_counters (unsigned long long *barriers, unsigned long long *warp_ops)
+{
+   *barriers = g_barriers;
+   *warp_ops = g_warp_ops;
+}
+
 void
 emu_syncthreads (void)
 {
@@ -119,6 +129,7 @@ emu_syncthreads (void)
 
    if (++B.bar_count == (unsigned) B.alive)
    {
+      g_barriers++;
       B.bar_count = 0;
       B.bar_gen++;
       return;
@@ -139,6 +150,8 @@ emu_warp_exchange (unsigned value, int kind, int arg)
    w.slot [buf][lane] = value;
    if (++w.count == lanes)
    {
+      if ((tid >> 5) == 0)
+	 g_warp_ops++;		/* warp 0's collectives: the resolution loops run in every warp alike */
       w.count = 0;
       w.gen++;
    }
