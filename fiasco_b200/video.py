@@ -76,11 +76,12 @@ def encode_groups(planes, my_groups, params, p_min_level=6, p_max_level=10, sear
             for f in todo:                         # the references: regenerate the frames before
                 prev = out[f - 1]
                 recon[f - 1] = hostlib.regenerate_frame(prev, W, H, recon.get(f - 2) if prev["frame_type"] else None)
-                recon.pop(f - 3, None)
             gs = penc.encode_predicted([planes[f] for f in todo], [recon[f - 1] for f in todo])
             kernel_ms += penc.stats()["kernel_ms"]
             for f, g in zip(todo, gs):
                 out[f] = hostlib.finish_predicted_frame(_with_motion_fields(g, 1, f))
+                if k >= 2:
+                    recon.pop(f - 2, None)         # two frames back in the same chain: no longer a reference
             k += 1
     finally:
         penc.close()

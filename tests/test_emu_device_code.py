@@ -240,3 +240,30 @@ def test_emulated_results_do_not_depend_on_thread_scheduling(emu, order):
             enc.close()
     finally:
         os.environ.pop("FB200_EMU_ORDER", None)
+
+
+def test_emulated_python_group_loop_equals_fiasco_coder(emu, tmp_path):
+    """fiasco_b200/video.py (groups of pictures for several GPUs) against the C frame loop of
+    fiasco_coder() on groups of two frames each (pattern "ip": adjacent groups, each reference regenerated
+    from an I frame)."""
+    import hashlib
+    from fiasco_b200 import hostlib, video
+    saved = (hostlib._LIB, hostlib.lib_path)
+    hostlib._LIB, hostlib.lib_path = None, (lambda: os.path.join(EMU_DIR, "_build", "libfiasco_emu.so"))
+    try:
+        frames = list(gen_frames.video(4, 176, 144))
+        names = []
+        for i, f in enumerate(frames):
+            names.append(str(tmp_path / ("f%02d.pgm" % i)))
+            gen_frames.write_pnm(names[-1], f)
+        o = hostlib.cli_options(0)
+        hostlib.load().fiasco_c_options_set_frame_pattern(o, b"ip")
+        ok, msg = hostlib.coder(names, str(tmp_path / "c.fco"), 20.0, options=o)
+        assert ok, msg
+        p = ffi.make_params(176, 144, 1, 20.0, 0)
+        seq, _ = video.encode_sequence([ffi.pixels_from_grey(f) for f in frames], "ip", p)
+        hostlib.write_video_stream(str(tmp_path / "p.fco"), p, seq)
+        md5 = lambda n: hashlib.md5(open(str(tmp_path / n), "rb").read()).hexdigest()
+        assert md5("p.fco") == md5("c.fco")
+    finally:
+        hostlib._LIB, hostlib.lib_path = saved

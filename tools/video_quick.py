@@ -26,10 +26,12 @@ def main():
     n, w, h, pattern, q = int(os.environ.get("FBQ_FRAMES", "30")), 720, 576, "ippp", 20.0
     planes = [ffi.pixels_from_grey(f) for f in gen_frames.video(n, w, h)]
     p = ffi.make_params(w, h, 1, q, 0)
-    gl = video.groups(n, pattern)
+    # FBQ_REPLICAS = R: R copies of the sequence as independent sequences (R x the groups in flight)
+    reps = int(os.environ.get("FBQ_REPLICAS", "1"))
+    gl = [(s + k * n, e + k * n) for k in range(reps) for s, e in video.groups(n, pattern)]
     for r in range(runs):
         t0 = time.perf_counter()
-        done, kernel_ms = video.encode_groups({f: planes[f] for f in range(n)}, gl, p)
+        done, kernel_ms = video.encode_groups({f: planes[f % n] for f in range(n * reps)}, gl, p)
         t1 = time.perf_counter()
         with tempfile.TemporaryDirectory() as tmp:
             out = os.path.join(tmp, "v.fco")
@@ -39,8 +41,9 @@ def main():
         md5 = hashlib.md5(data).hexdigest()
         print(json.dumps({"workload": "%d frames %dx%d grey q=%g pattern %s, %d groups, 1 GPU" % (n, w, h, q, pattern, len(gl)),
                           "run": r, "encode_s": t1 - t0, "write_s": t2 - t1, "kernel_ms": kernel_ms,
-                          "mpixels_per_s_e2e": n * w * h / 1e6 / (t2 - t0),
-                          "mpixels_per_s_kernels": n * w * h / 1e3 / kernel_ms if kernel_ms else None,
+                          "sequences": reps, "groups_in_flight": len(gl),
+                          "mpixels_per_s_e2e": reps * n * w * h / 1e6 / (t2 - t0),
+                          "mpixels_per_s_kernels": reps * n * w * h / 1e3 / kernel_ms if kernel_ms else None,
                           "bytes": len(data), "fco_md5": md5, "md5_matches_reference": (md5 == want) if want else None,
                           "states": [int(done[f]["states"]) for f in range(min(n, 8))]}), flush=True)
 
