@@ -245,11 +245,12 @@ derive (const fb200_params_t *p, const fb200_motion_t *mo, DevParams *d, char *e
       if (d->p_min > d->p_max)
 	 d->p_min = d->p_max;
       d->sr = mo->search_range;
-      /* states of losing alternatives stay behind as holes until the host closes them: up to
-	 ~3x the final states while a frame is built; the motion search also
-	 borrows 2 x 512 floats of the pursuit's work arrays */
+      /* states of losing alternatives stay behind as holes until the host closes them: ~3x the
+	 final states while a frame is built (2773 on BASELINE config 5, whose
+	 frames end with ~930); the motion search also borrows 2 x 512 floats of the pursuit's
+	 work arrays.  Too small a guess costs a second launch (FB200_ECAPACITY, ctx_grow). */
       if (p->state_capacity <= 0)
-	 d->s_cap = 3 * d->s_cap;
+	 d->s_cap = 4 * d->s_cap;
       if (d->s_cap < 512)
 	 d->s_cap = 512;
    }
@@ -791,11 +792,17 @@ fb200_encode_tiles (fb200_ctx_t *c, int n_tiles, const int16_t *const *planes,
       c->dp.trace_cap = 0;
    if ((rc = fb200_upload (c, n_tiles, planes, err, errlen)))
       return rc;
+   float total_ms = 0;
+   int	 launches = 0;
    for (;;)
    {
       if ((rc = fb200_launch (c, n_tiles, NULL, err, errlen)))
 	 return rc;
       rc = fb200_download (c, n_tiles, out, trace, trace_cap, trace_len, err, errlen);
+      /* a launch that ran out of state capacity is part of the bill */
+      total_ms += c->stats.kernel_ms;
+      c->stats.kernel_ms       = total_ms;
+      c->stats.kernel_launches = ++launches;
       if (rc != FB200_ECAPACITY || !c->auto_grow)
 	 return rc;
       /* a tile outgrew the workspace we sized ourselves: enlarge it and run again */
@@ -831,11 +838,16 @@ fb200_encode_predicted (fb200_ctx_t *c, int n_tiles, const int16_t *const *plane
    }
    CUDA_TRY (cudaStreamSynchronize (c->stream));
    c->stats.h2d_bytes += c->pix_elems * 2 * n_tiles;
+   float total_ms = 0;
+   int	 launches = 0;
    for (;;)
    {
       if ((rc = fb200_launch (c, n_tiles, NULL, err, errlen)))
 	 return rc;
       rc = fb200_download (c, n_tiles, out, NULL, 0, NULL, err, errlen);
+      total_ms += c->stats.kernel_ms;
+      c->stats.kernel_ms       = total_ms;
+      c->stats.kernel_launches = ++launches;
       if (rc != FB200_ECAPACITY || !c->auto_grow)
 	 return rc;
       if ((rc = ctx_grow (c, err, errlen)))
