@@ -267,3 +267,18 @@ def test_emulated_python_group_loop_equals_fiasco_coder(emu, tmp_path):
         assert md5("p.fco") == md5("c.fco")
     finally:
         hostlib._LIB, hostlib.lib_path = saved
+
+
+def test_emulated_random_sequences_match_the_reference_binary(emu):
+    """A few cases of tools/fuzz_video_emu.py: random short sequences with P and B frames through
+    fiasco_coder() (device code under the emulator) against the unmodified reference binary of
+    oracle/_ref, byte for byte.  Skipped where the reference binary was not built."""
+    import subprocess
+    import sys
+    root = os.path.dirname(HERE)
+    if not os.path.exists(os.path.join(root, "oracle", "_ref", "cfiasco")):
+        pytest.skip("oracle/_ref/cfiasco not built")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_video_emu.py"), "8", "3"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "8 cases, 0 mismatches" in r.stdout
