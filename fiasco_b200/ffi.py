@@ -89,9 +89,11 @@ def load():
     lib.fb200_device_count.restype = ip
     lib.fb200_params_init.argtypes = [C.POINTER(Params), ip, ip, ip, C.c_float, ip, cp, C.c_size_t]
     lib.fb200_create.argtypes = [C.POINTER(vp), C.POINTER(Params), ip, ip, cp, C.c_size_t]
-    lib.fb200_create_predicted.argtypes = [C.POINTER(vp), C.POINTER(Params), C.POINTER(Motion), ip, ip, cp, C.c_size_t]
-    lib.fb200_encode_predicted.argtypes = [vp, ip, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(_Wfa), cp,
-                                           C.c_size_t]
+    if hasattr(lib, "fb200_create_predicted"):      # absent in A/B builds of older revisions (tools/build_prev.sh)
+        lib.fb200_create_predicted.argtypes = [C.POINTER(vp), C.POINTER(Params), C.POINTER(Motion), ip, ip, cp,
+                                               C.c_size_t]
+        lib.fb200_encode_predicted.argtypes = [vp, ip, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(_Wfa),
+                                               cp, C.c_size_t]
     lib.fb200_destroy.argtypes = [vp]
     lib.fb200_destroy.restype = None
     lib.fb200_encode_tiles.argtypes = [vp, ip, C.POINTER(vp), C.POINTER(_Wfa), C.POINTER(TraceRec), ip,
@@ -104,7 +106,8 @@ def load():
     lib.fb200_get_stats.restype = None
     lib.fb200_resident_tiles.argtypes = [vp]
     lib.fb200_state_capacity.argtypes = [vp]
-    lib.fb200_motion_norms.argtypes = [ip, vp, vp, ip, ip, ip, ip, vp, C.POINTER(C.c_float), cp, C.c_size_t]
+    if hasattr(lib, "fb200_motion_norms"):
+        lib.fb200_motion_norms.argtypes = [ip, vp, vp, ip, ip, ip, ip, vp, C.POINTER(C.c_float), cp, C.c_size_t]
     lib.fb200_probe.argtypes = [ip, ip, vp, vp, vp, vp, vp, vp, cp, C.c_size_t]
     _LIB = lib
     return lib
