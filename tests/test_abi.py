@@ -112,3 +112,20 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] in ("reference", "port")
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["metric"].startswith("encoder Mpixels/s")
+
+
+def test_product_does_not_know_the_emulator():
+    """tests/emu (the device sources compiled for a CPU thread emulator) is test infrastructure: nothing
+    the product builds, imports or runs refers to it -- the Python binding loads the CUDA library only,
+    the Makefile, bench.py and the driver entry points do not mention it, and the device sources carry
+    nothing but the launch / shared-memory spelling (#ifdef FB200_EMU) that lets them compile as C++."""
+    import re
+    from fiasco_b200 import ffi, hostlib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    assert ffi.lib_path().endswith(os.path.join("fiasco_b200", "lib", "libfiasco_b200.so"))
+    assert hostlib.lib_path().endswith(os.path.join("fiasco_b200", "lib", "libfiasco.so"))
+    for rel in ("Makefile", "bench.py", "__graft_entry__.py", "fiasco_b200/ffi.py", "fiasco_b200/hostlib.py",
+                "fiasco_b200/video.py", "fiasco_b200/distributed.py", "fiasco_b200/__init__.py",
+                "fiasco_b200/host/coder_api.c", "fiasco_b200/csrc/ffi.cu"):
+        text = open(os.path.join(root, rel)).read()
+        assert not re.search(r"\bemu\b|_emu|emu_", text), rel
