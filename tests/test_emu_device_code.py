@@ -282,3 +282,26 @@ def test_emulated_random_sequences_match_the_reference_binary(emu):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "8 cases, 0 mismatches" in r.stdout
+
+
+@pytest.mark.parametrize("p_min,p_max,sr", [(7, 9, 8), (6, 10, 5), (8, 8, 16)])
+def test_emulated_predicted_frames_other_levels_and_search_ranges(emu, p_min, p_max, sr):
+    """Prediction levels and search ranges other than the CLI's 6..10 / 16 (c_options_t.p_min_level,
+    p_max_level, search_range): the tables hold 4 sr^2 vectors, levels outside [p_min, p_max] are not
+    predicted."""
+    frames = list(gen_frames.video(3, 176, 144))
+    L = O.lib()
+    L.fo_set_holes_mode(1)
+    try:
+        ws, rec = O.encode_video(frames, quality=20.0, pattern="ipp", p_min_level=p_min, p_max_level=p_max,
+                                 search_range=sr)
+    finally:
+        L.fo_set_holes_mode(0)
+    p = ffi.make_params(176, 144, 1, 20.0, 0)
+    enc = F.TileEncoder(p, 1, motion=F.Motion(1, p_min, p_max, sr))
+    try:
+        for f in (1, 2):
+            g = enc.encode_predicted([O.planes_of(frames[f])[0]], [rec[f - 1]])[0]
+            assert_same_predicted_automaton(g, O.struct_dict(ws[f]["_struct"]))
+    finally:
+        enc.close()

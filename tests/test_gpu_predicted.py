@@ -62,6 +62,26 @@ def test_gpu_predicted_frames_of_several_sequences_in_one_launch():
         enc.close()
 
 
+@pytest.mark.parametrize("p_min,p_max,sr", [(7, 9, 8), (6, 10, 5)])
+def test_gpu_predicted_frames_other_levels_and_search_ranges(p_min, p_max, sr):
+    frames = list(gen_frames.video(3, 176, 144))
+    L = O.lib()
+    L.fo_set_holes_mode(1)
+    try:
+        ws, rec = O.encode_video(frames, quality=20.0, pattern="ipp", p_min_level=p_min, p_max_level=p_max,
+                                 search_range=sr)
+    finally:
+        L.fo_set_holes_mode(0)
+    p = ffi.make_params(176, 144, 1, 20.0, 0)
+    enc = F.TileEncoder(p, 1, motion=F.Motion(1, p_min, p_max, sr))
+    try:
+        for f in (1, 2):
+            g = enc.encode_predicted([O.planes_of(frames[f])[0]], [rec[f - 1]])[0]
+            assert_same_predicted_automaton(g, O.struct_dict(ws[f]["_struct"]))
+    finally:
+        enc.close()
+
+
 def test_gpu_b_frames_match_oracle():
     check_b_frame_sequence()
 
