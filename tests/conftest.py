@@ -29,7 +29,9 @@ def pytest_configure(config):
         emu = os.path.join(ROOT, "tests", "emu")
         subprocess.run(["make", "-s", "-C", emu], check=True)
         from fiasco_b200 import ffi, hostlib
-        ffi.lib_path = lambda: os.path.join(emu, "_build", "libfiasco_b200_emu.so")
+        # FB200_EMU_ASAN=1: the sanitizer build (make -C tests/emu asan; LD_PRELOAD libasan.so)
+        sub = "_asan" if os.environ.get("FB200_EMU_ASAN") else "_build"
+        ffi.lib_path = lambda: os.path.join(emu, sub, "libfiasco_b200_emu.so")
         hostlib.lib_path = lambda: os.path.join(emu, "_build", "libfiasco_emu.so")
         os.environ.setdefault("FB200_NT", "128")
 
