@@ -249,8 +249,7 @@ fiasco_coder (char const *const *inputname, const char *outputname, float qualit
 	 {
 	    if (ctype [n] == 2)
 	       has_b = 1;
-	    if (ctype [n] == 2 && !cop->B_as_past_ref)
-	       fi_error ("B frames: only the default `B frames as past references' is available.");
+	    
 	    if (color)
 	       fi_error ("Predicted frames are available for grey sequences only.");
 	    if (cop->half_pixel_prediction)
@@ -417,7 +416,7 @@ fiasco_coder (char const *const *inputname, const char *outputname, float qualit
 	    {
 	       if (future_frame)
 		  future = cur;
-	       else
+	       else if (cop->B_as_past_ref)	/* else the last frame is dropped (coder.c:612-625) */
 		  past = cur;
 	    }
 	    else

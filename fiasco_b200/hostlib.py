@@ -53,6 +53,7 @@ def load():
         L.fiasco_c_options_set_quantization.argtypes = [C.c_void_p, C.c_uint, C.c_int, C.c_uint, C.c_int]
         L.fiasco_c_options_set_frame_pattern.argtypes = [C.c_void_p, C.c_char_p]
         L.fiasco_c_options_set_title.argtypes = [C.c_void_p, C.c_char_p]
+        L.fiasco_c_options_set_video_param.argtypes = [C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_int]
         L.fiasco_c_options_set_chroma_quality.argtypes = [C.c_void_p, C.c_float, C.c_uint]
         L.fiasco_c_options_set_prediction.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.c_uint]
         L.fiasco_c_options_set_smoothing.argtypes = [C.c_void_p, C.c_int]

@@ -305,3 +305,44 @@ def test_emulated_predicted_frames_other_levels_and_search_ranges(emu, p_min, p_
             assert_same_predicted_automaton(g, O.struct_dict(ws[f]["_struct"]))
     finally:
         enc.close()
+
+
+def check_video_param_against_reference_library(tmp_path):
+    """fiasco_c_options_set_video_param (frames per second, B frames as past references or not): the
+    reference CLI parses these flags but never passes them on, so the comparison goes through
+    oracle/_ref/refcoder (our harness around the unmodified reference LIBRARY).  Byte for byte."""
+    import hashlib
+    import subprocess
+    from fiasco_b200 import hostlib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    rc = os.path.join(root, "oracle", "_ref", "refcoder")
+    if not os.path.exists(rc):
+        pytest.skip("oracle/_ref/refcoder not built")
+    L = hostlib.load()
+    names = []
+    for i, f in enumerate(gen_frames.video(7, 176, 144)):
+        names.append(str(tmp_path / ("f%02d.pgm" % i)))
+        gen_frames.write_pnm(names[-1], f)
+    env = dict(os.environ, FIASCO_DATA=os.path.join(root, "oracle", "_ref", "data"), FIASCO_IMAGES=str(tmp_path))
+    for pattern, fps, b_as_past in (("ibbp", 25, 0), ("ibbbp", 12, 0), ("ibbp", 30, 1)):
+        o = hostlib.cli_options(0)
+        L.fiasco_c_options_set_frame_pattern(o, pattern.encode())
+        assert L.fiasco_c_options_set_video_param(o, fps, 0, 0, b_as_past)
+        out, ref = str(tmp_path / "ours.fco"), str(tmp_path / "ref.fco")
+        ok, msg = hostlib.coder(names, out, 20.0, options=o)
+        L.fiasco_c_options_delete(o)
+        assert ok, msg
+        subprocess.run([rc, ref, "20", pattern, str(fps), "0", "0", str(b_as_past)] + names, env=env, check=True,
+                       capture_output=True)
+        assert hashlib.md5(open(out, "rb").read()).hexdigest() == hashlib.md5(open(ref, "rb").read()).hexdigest(), \
+            (pattern, fps, b_as_past)
+
+
+def test_emulated_video_param_against_reference_library(emu, tmp_path):
+    from fiasco_b200 import hostlib
+    saved = (hostlib._LIB, hostlib.lib_path)
+    hostlib._LIB, hostlib.lib_path = None, (lambda: os.path.join(EMU_DIR, "_build", "libfiasco_emu.so"))
+    try:
+        check_video_param_against_reference_library(tmp_path)
+    finally:
+        hostlib._LIB, hostlib.lib_path = saved

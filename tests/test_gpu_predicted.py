@@ -12,7 +12,8 @@ import fiasco_b200 as F
 from fiasco_b200 import ffi, hostlib
 import oracle_lib as O
 import gen_frames
-from test_emu_device_code import _holes_mode_automata, assert_same_predicted_automaton, check_b_frame_sequence
+from test_emu_device_code import (_holes_mode_automata, assert_same_predicted_automaton, check_b_frame_sequence,
+                                  check_video_param_against_reference_library)
 
 pytestmark = pytest.mark.gpu
 
@@ -80,6 +81,10 @@ def test_gpu_predicted_frames_other_levels_and_search_ranges(p_min, p_max, sr):
             assert_same_predicted_automaton(g, O.struct_dict(ws[f]["_struct"]))
     finally:
         enc.close()
+
+
+def test_gpu_video_param_against_reference_library(tmp_path):
+    check_video_param_against_reference_library(tmp_path)
 
 
 def test_gpu_b_frames_match_oracle():
