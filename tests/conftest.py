@@ -32,7 +32,7 @@ def pytest_configure(config):
         # FB200_EMU_ASAN=1: the sanitizer build (make -C tests/emu asan; LD_PRELOAD libasan.so)
         sub = "_asan" if os.environ.get("FB200_EMU_ASAN") else "_build"
         ffi.lib_path = lambda: os.path.join(emu, sub, "libfiasco_b200_emu.so")
-        hostlib.lib_path = lambda: os.path.join(emu, "_build", "libfiasco_emu.so")
+        hostlib.lib_path = lambda: os.path.join(emu, sub, "libfiasco_emu.so")
         os.environ.setdefault("FB200_NT", "128")
 
 

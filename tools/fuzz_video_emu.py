@@ -49,8 +49,10 @@ def main():
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
     side = int(sys.argv[3]) if len(sys.argv) > 3 else 200
     subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "tests", "emu")], check=True)
-    ffi.lib_path = lambda: os.path.join(EMU, "libfiasco_b200_emu.so")
-    hostlib.lib_path = lambda: os.path.join(EMU, "libfiasco_emu.so")
+    # FB200_EMU_ASAN=1 (after `make -C tests/emu asan`, with LD_PRELOAD=libasan.so): the sanitizer build
+    dev = os.path.join(os.path.dirname(EMU), "_asan") if os.environ.get("FB200_EMU_ASAN") else EMU
+    ffi.lib_path = lambda: os.path.join(dev, "libfiasco_b200_emu.so")
+    hostlib.lib_path = lambda: os.path.join(dev, "libfiasco_emu.so")
     os.environ.setdefault("FB200_NT", "128")
     L = hostlib.load()
     cf = os.path.join(REF, "cfiasco")
