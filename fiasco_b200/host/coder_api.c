@@ -251,7 +251,8 @@ fiasco_coder (char const *const *inputname, const char *outputname, float qualit
 	       has_b = 1;
 	    
 	    if (color)
-	       fi_error ("Predicted frames are available for grey sequences only.");
+	       fi_error ("Predicted frames are available for grey sequences only: code colour "
+			 "sequences with a frame pattern of I frames (--pattern=i).");
 	    if (cop->half_pixel_prediction)
 	       fi_error ("Half pixel motion compensation is not available in the B200 build.");
 	    if (!cop->normal_domains || !cop->delta_domains
