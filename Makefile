@@ -54,6 +54,15 @@ $(LIBDIR)/%.o: $(CSRC)/%.cu $(CSRC)/tile_kernel.cuh include/fiasco_b200.h | $(LI
 $(LIBDIR)/libfiasco_b200.so: $(KOBJ)
 	$(NVCC) $(ARCH) -shared -o $@ $(KOBJ) -cudart static
 
+# diagnostics build: thread-0 lap timers per sub-phase (FB200_LIB=gpurun_exp/laps/libfiasco_b200.so)
+.PHONY: laps
+laps:
+	mkdir -p gpurun_exp/laps
+	for f in tile_kernel ffi motion_kernel; do \
+	  $(NVCC) $(NVFLAGS) -DFB200_LAPS -c $(CSRC)/$$f.cu -o gpurun_exp/laps/$$f.o || exit 1; done
+	$(NVCC) $(ARCH) -shared -o gpurun_exp/laps/libfiasco_b200.so gpurun_exp/laps/tile_kernel.o \
+	    gpurun_exp/laps/ffi.o gpurun_exp/laps/motion_kernel.o -cudart static
+
 oracle:
 	$(MAKE) -C oracle all
 

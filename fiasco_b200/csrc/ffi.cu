@@ -34,6 +34,7 @@ struct fb200_ctx
    fb200_trace_rec_t *d_trace;	/* tile 0 only */
    int		  trace_cap;
    TileWs	 *d_ws;
+   int		 *d_lc_min;	/* [tiles] lc_min_level the tiles start with (fb200_wfa_t.lc_min_level) */
    /* pinned host staging */
    unsigned char *h_wfa;
    TileResult	 *h_results;
@@ -358,6 +359,7 @@ fb200_destroy (fb200_ctx_t *c)
    cudaFree (c->d_results);
    cudaFree (c->d_trace);
    cudaFree (c->d_ws);
+   cudaFree (c->d_lc_min);
    cudaFreeHost (c->h_wfa);
    cudaFreeHost (c->h_results);
    for (int i = 0; i < 6; i++)
@@ -420,6 +422,8 @@ ctx_alloc (fb200_ctx_t *c, char *err, size_t errlen)
 	 CUDA_TRY (cudaMalloc (&c->d_future, c->pix_elems * 2 * max_tiles));
       CUDA_TRY (cudaMalloc (&c->d_results, sizeof (TileResult) * max_tiles));
       CUDA_TRY (cudaMalloc (&c->d_ws, sizeof (TileWs) * max_tiles));
+      CUDA_TRY (cudaMalloc (&c->d_lc_min, sizeof (int) * max_tiles));
+      CUDA_TRY (cudaMemset (c->d_lc_min, 0, sizeof (int) * max_tiles));
       CUDA_TRY (cudaMallocHost (&c->h_results, sizeof (TileResult) * max_tiles));
       CUDA_TRY (cudaStreamCreateWithFlags (&c->stream, cudaStreamNonBlocking));
       for (int i = 0; i < 6; i++)
@@ -491,7 +495,8 @@ ctx_grow (fb200_ctx_t *c, char *err, size_t errlen)
    int rc = derive (&p, &c->motion, &d, err, errlen);
    if (rc)
       return rc;
-   d.trace_cap = c->dp.trace_cap;
+   d.trace_cap	 = c->dp.trace_cap;
+   d.tile_lc_min = c->dp.tile_lc_min;
    CUDA_TRY (cudaSetDevice (c->device));
    cudaFree (c->d_work);
    cudaFree (c->d_wfa);
@@ -693,6 +698,8 @@ fb200_download (fb200_ctx_t *c, int n_tiles, fb200_wfa_t *out, fb200_trace_rec_t
       o.states	     = r.states;
       o.basis_states = r.basis_states;
       o.root_state   = r.root_state;
+      o.lc_min_level = r.lc_min_end;
+      memcpy (o.progress, r.progress, sizeof o.progress);
       for (int b = 0; b < 3; b++)
       {
 	 o.costs [b]	    = r.costs [b];
@@ -790,6 +797,25 @@ fb200_encode_tiles (fb200_ctx_t *c, int n_tiles, const int16_t *const *planes,
    }
    else
       c->dp.trace_cap = 0;
+   if (n_tiles < 1 || n_tiles > c->max_tiles || !out)
+   {
+      set_err (err, errlen, "fb200_encode_tiles: bad arguments");
+      return FB200_EINVAL;
+   }
+   {
+      /* the range levels the tiles start with, when a caller chains frames (colour sequences) */
+      std::vector<int> lc (n_tiles);
+      bool		any = false;
+
+      for (int t = 0; t < n_tiles; t++)
+	 any |= (lc [t] = out [t].lc_min_level) > 0;
+      c->dp.tile_lc_min = any ? c->d_lc_min : NULL;
+      if (any)
+      {
+	 CUDA_TRY (cudaSetDevice (c->device));
+	 CUDA_TRY (cudaMemcpy (c->d_lc_min, lc.data (), sizeof (int) * n_tiles, cudaMemcpyHostToDevice));
+      }
+   }
    if ((rc = fb200_upload (c, n_tiles, planes, err, errlen)))
       return rc;
    float total_ms = 0;

@@ -223,6 +223,7 @@ struct Frame			/* one activation record of subdivide() */
 {
    float    max_costs, lincomb_costs, subdivide_costs;
    unsigned x, y, image, address;
+   unsigned gaddr;		/* range->global_address: address in the whole picture (progress meter) */
    int	    level, y_state, label;
    int	    new_y_state [2];
    unsigned states_snap;
@@ -325,6 +326,8 @@ struct ShHdr
    float    fcosts, bcosts;	/* find_B_frame_mc */
    int	    fi, bi;
    long long isum;		/* integer sum of squares of the interpolated prediction error */
+   /* the percent meter of subdivide() (subdivide.c:105-108,323-337): last value, values shown */
+   unsigned percent, progress [4];
 };
 
 static_assert (offsetof (ShHdr, tree_total) == offsetof (ShHdr, tree_counts) + FB200_MAXLEVEL * sizeof (unsigned),
@@ -2301,6 +2304,19 @@ t0_advance (const DevParams &P, const TileWs &W, ShHdr *h, int &state, int &dept
 	 const int label = F.label;
 	 RangeRes &c	 = F.child [label];
 
+	 /* progress meter (subdivide.c:323-337): (global_address + 1) * 100.0 / 2^k, truncated --
+	    exact in integers.  Nothing is printed here; the host replays the values. */
+	 {
+	    const unsigned long long pos = (unsigned long long) F.gaddr * 2 + label + 1;
+	    const unsigned np = (unsigned) ((pos * 100) >> (P.level - (F.level - 1)));
+
+	    if (np > h->percent)
+	    {
+	       h->percent = np;
+	       h->progress [(np >> 5) & 3] |= 1u << (np & 31);
+	    }
+	 }
+
 	 if (F.subdivide_costs >= fmin2 (F.lincomb_costs, F.max_costs))
 	 {
 	    F.subdivide_costs = FB_MAXCOSTS;	/* subdivide.c:355-359 */
@@ -2357,6 +2373,7 @@ t0_advance (const DevParams &P, const TileWs &W, ShHdr *h, int &state, int &dept
 	    C.y		= cy;
 	    C.image	= cimg;
 	    C.address	= cadr;
+	    C.gaddr	= F.gaddr * 2 + label;
 	    C.level	= level - 1;
 	    C.y_state	= F.new_y_state [label];
 	    if (MOTION)
@@ -2404,8 +2421,10 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
       int    st = ST_ENTER, dp = 0;
 
       F.max_costs = FB_MAXCOSTS;
-      F.x = F.y = F.image = F.address = 0;
+      F.x = F.y = F.image = F.address = F.gaddr = 0;
       F.level	= P.level;
+      h->percent = 0;
+      h->progress [0] = h->progress [1] = h->progress [2] = h->progress [3] = 0;
       F.y_state = root_y_state;
       h->band	= band;
       h->price	= band ? P.price * P.chroma_decrease : P.price;
@@ -2888,6 +2907,7 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 		     C.y	 = F.y;
 		     C.image	 = 0;
 		     C.address	 = 0;
+		     C.gaddr	 = F.gaddr;
 		     C.level	 = level;
 		     C.y_state	 = F.y_state;
 		     h->fx [depth + 1].delta	  = 1;
@@ -3299,7 +3319,13 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
    int ycb_node	     = -1;
 
    if (tid == 0)
-      h->lc_min = P.lc_min;
+   {
+      /* a frame of a colour sequence starts with the range levels the chroma bands of the frame
+	 before left behind (coder.c:797: c->options.lc_min_level is never set back) */
+      const int given = P.tile_lc_min ? P.tile_lc_min [blockIdx.x] : 0;
+
+      h->lc_min = given > P.lc_min && given <= P.lc_max ? given : P.lc_min;
+   }
    __syncthreads ();
    for (int band = 0; band < P.bands && h->status == FB200_OK; band++)
    {
@@ -3324,6 +3350,8 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
 	 r->tree_bits [band]	= h->root.tree_bits;
 	 r->matrix_bits [band]	= h->root.matrix_bits;
 	 r->weights_bits [band] = h->root.weights_bits;
+	 for (int i = 0; i < 4; i++)
+	    r->progress [band][i] = h->progress [i];
 	 if (band == 1 && h->status == FB200_OK)
 	    h->w.index = t0_virtual_state (P, W, h, band_tree [0], band_tree [1], P.level + 1);
       }
@@ -3348,6 +3376,7 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
       r->basis_states = 3;
       r->root_state   = h->root.tree >= 0 ? (unsigned) h->root.tree : 0;
       r->trace_len = h->trace_len;
+      r->lc_min_end = h->lc_min;
       r->mp_calls  = h->mp_calls;
       r->mp_steps  = h->mp_steps;
       r->pass2	   = h->pass2;

@@ -71,6 +71,7 @@ struct DevParams
    int	 sr;			/* search range: vectors in [-sr, sr) */
    int	 blob_half;		/* shorts of one model set; blob = normal set, then delta set */
    int	 n_frames;		/* DFS activation records (nested delta pass included) */
+   const int *tile_lc_min;	/* [tiles] lc_min_level a tile starts with (0: lc_min), or NULL */
 };
 
 /* all transitions of one state in one 64-byte line: what the inner-product kernels gather */
@@ -125,6 +126,8 @@ struct TileResult
    float    costs [3], err [3], tree_bits [3], matrix_bits [3], weights_bits [3];
    int	    band_root [3];
    int	    trace_len;
+   int	    lc_min_end;		/* lc_min_level after the frame (raised by the chroma bands) */
+   unsigned progress [3][4];	/* percent values the reference's progress meter shows, per band */
    unsigned long long mp_calls, mp_steps, pass2, blocks, ip_bytes;
    unsigned long long mp_bytes, ss_bytes;	/* algorithmic bytes of the other phases */
    unsigned long long cyc_total, cyc_T, cyc_mp, cyc_append; /* SM cycles per phase */

@@ -40,6 +40,7 @@ class _Wfa(C.Structure):
         ("into", C.c_void_p), ("weight", C.c_void_p), ("y_state", C.c_void_p), ("y_column", C.c_void_p),
         ("mv_type", C.c_void_p), ("mv_fx", C.c_void_p), ("mv_fy", C.c_void_p),
         ("mv_bx", C.c_void_p), ("mv_by", C.c_void_p),
+        ("lc_min_level", C.c_int), ("progress", (C.c_uint32 * 4) * 3),
     ]
 
 
@@ -72,6 +73,8 @@ class Stats(C.Structure):
 
 
 def lib_path():
+    if os.environ.get("FB200_LIB"):         # experiment builds (make laps): never the default
+        return os.path.abspath(os.environ["FB200_LIB"])
     return os.path.join(_HERE, "lib", "libfiasco_b200.so")
 
 
@@ -213,6 +216,8 @@ class TileEncoder:
                 "status": w.status, "states": n, "basis_states": w.basis_states, "root_state": w.root_state,
                 "costs": list(w.costs), "err": list(w.err), "tree_bits": list(w.tree_bits),
                 "matrix_bits": list(w.matrix_bits), "weights_bits": list(w.weights_bits),
+                "lc_min_level": w.lc_min_level,
+                "progress": [[p for p in range(128) if w.progress[b][p >> 5] >> (p & 31) & 1] for b in range(3)],
             }
             for name in ("final_distribution", "level_of_state", "domain_type", "tree", "x", "y", "into", "weight",
                          "y_state", "y_column") + (("mv_type", "mv_fx", "mv_fy", "mv_bx", "mv_by") if self.motion is not None else ()):

@@ -24,7 +24,7 @@
 #define FI_USE_DOMAIN 2
 
 /* ---- errors: same try/catch discipline as the reference (lib/error.h:43-45) ---- */
-extern jmp_buf fi_env;
+extern __thread jmp_buf fi_env;
 #define fi_try	 if (setjmp (fi_env) == 0)
 #define fi_catch else
 void fi_set_error (const char *format, ...);
@@ -32,6 +32,7 @@ void fi_error (const char *format, ...);		/* set text, longjmp */
 void fi_file_error (const char *filename);
 void fi_warning (const char *format, ...);
 void fi_message (const char *format, ...);
+void fi_info (const char *format, ...);
 void fi_debug_message (const char *format, ...);
 const char *fi_system_error (void);
 

@@ -11,10 +11,11 @@
 
 #include "fi_internal.h"
 
-jmp_buf fi_env;
+/* per thread: the GPU worker threads of fiasco_coder() run host code that reports errors too */
+__thread jmp_buf fi_env;
 
 static fiasco_verbosity_e verboselevel = FIASCO_SOME_VERBOSITY;
-static char		  error_message [2048];
+static __thread char	  error_message [2048];
 
 static void
 store (const char *format, va_list args)
@@ -85,6 +86,20 @@ fi_message (const char *format, ...)
    va_start (args, format);
    vfprintf (stderr, format, args);
    fputc ('\n', stderr);
+   va_end (args);
+}
+
+/* lib/error.c:279: no newline, flushed (the progress meter) */
+void
+fi_info (const char *format, ...)
+{
+   va_list args;
+
+   if (verboselevel == FIASCO_NO_VERBOSITY)
+      return;
+   va_start (args, format);
+   vfprintf (stderr, format, args);
+   fflush (stderr);
    va_end (args);
 }
 

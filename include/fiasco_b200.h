@@ -111,6 +111,13 @@ typedef struct fb200_wfa
       3 interpolated */
    int8_t   *mv_type, *mv_fx, *mv_fy;	     /* [capacity][2] */
    int8_t   *mv_bx, *mv_by;		     /* [capacity][2] backward vectors (B frames) */
+   /* in: smallest range level this tile starts with when > 0 (0: params.lc_min_level); out: the
+      level after the frame.  The chroma bands of a colour frame raise c->options.lc_min_level for
+      good (codec/coder.c:785-797), so the frames of a colour sequence hand it on. */
+   int	     lc_min_level;
+   /* out: the values the reference's percent meter prints while it codes band b
+      (codec/subdivide.c:323-337), bit p of the 128-bit set = "p%" was shown */
+   uint32_t  progress [3][4];
 } fb200_wfa_t;
 
 /* one record per approximate_range() call (debug / parity tracing, optional) */

@@ -84,3 +84,24 @@ if __name__ == "__main__":
         p = os.path.join(out, nm + (".pgm" if img.ndim == 2 else ".ppm"))
         write_pnm(p, img)
         print(nm, hashlib.md5(open(p, "rb").read()).hexdigest())
+
+
+def box_blur(a, k):
+    """Mean over a (2k)x(2k) window with replicated borders, back to u8."""
+    a = a.astype(np.float32)
+    c = np.cumsum(np.pad(a, ((k, k), (0, 0)), mode="edge"), axis=0)
+    a = (c[2 * k:] - c[:-2 * k]) / (2 * k)
+    c = np.cumsum(np.pad(a, ((0, 0), (k, k)), mode="edge"), axis=1)
+    a = (c[:, 2 * k:] - c[:, :-2 * k]) / (2 * k)
+    return np.clip(a, 0, 255).astype(np.uint8)
+
+
+def colour_sequence(n=2, w=128, h=128, k=8):
+    """A colour sequence whose FIRST frame is smooth (its luminance band stops above the finest range
+    level), followed by detailed frames: the case where the reference's chroma set-up of frame j
+    changes how frame j + 1 is coded (codec/coder.c:797).  With k = 12 the smooth frame is one the
+    reference coder refuses ("Can't write more than N weights.", output/weights.c:137)."""
+    out = [np.stack([box_blur(chan(w, h, s), k) for s in (4, 5, 6)], axis=-1)]
+    for j in range(1, n):
+        out.append(np.stack([chan(w, h, s + 20 * j) for s in (4, 5, 6)], axis=-1))
+    return out

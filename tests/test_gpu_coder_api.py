@@ -120,3 +120,154 @@ def test_frames_without_reference_are_refused(tmp_path):
     ok, msg = hostlib.coder([p, p, p], str(tmp_path / "o.fco"), options=o)
     L.fiasco_c_options_delete(o)
     assert not ok and "no reference frame" in msg
+
+
+# ---------------------------------------------------------------------------------------------
+# round 2: colour sequences, the big frame at -z 1 / -z 2, tile-split mode and several GPUs inside
+# the library, every tile of BASELINE configs 2, 3, 4 and config 5 at its full size
+# ---------------------------------------------------------------------------------------------
+
+def _with_env(**kv):
+    saved = {k: os.environ.get(k) for k in kv}
+    for k, v in kv.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = str(v)
+    return saved
+
+
+def _restore_env(saved):
+    for k, v in saved.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+
+
+@pytest.mark.parametrize("name", ["cseq128_sd_q25_z0", "cseq128_sd_q25_z1", "cseq128_sd_q40_z1", "cseq128_ds_q25_z0",
+                                  "cseq128_ds_q40_z1"])
+def test_colour_sequence_of_intra_frames_hands_lc_min_level_on(name, tmp_path):
+    """codec/coder.c:797: the chroma set-up of a frame raises c->options.lc_min_level and nothing sets
+    it back, so frame k + 1 of a colour sequence starts where frame k ended.  Smooth frame first
+    ("sd"): the second frame's bytes differ from coding it alone; the reference's stream is the pin."""
+    m = O.manifest()[name]
+    seq = gen_frames.colour_sequence(2, m["width"], m["height"])
+    names = []
+    for i, k in enumerate(m["order"]):
+        names.append(str(tmp_path / ("f%d.ppm" % i)))
+        gen_frames.write_pnm(names[-1], seq[k])
+    L = hostlib.load()
+    o = hostlib.cli_options(m["optimize"])
+    L.fiasco_c_options_set_frame_pattern(o, b"i")
+    out = str(tmp_path / "seq.fco")
+    ok, msg = hostlib.coder(names, out, quality=float(m["quality"]), options=o)
+    L.fiasco_c_options_delete(o)
+    assert ok, msg
+    assert md5(out) == m["fco_md5"]
+
+
+def test_frame_the_reference_refuses_is_refused_alike(tmp_path):
+    """A very smooth colour frame: the reference's writer stops with "Can't write more than N weights."
+    (output/weights.c:137); so do we, with the same text."""
+    m = O.manifest()["csmooth128_q25_refused"]
+    p = str(tmp_path / "s.ppm")
+    gen_frames.write_pnm(p, gen_frames.colour_sequence(1, 128, 128, 12)[0])
+    ok, msg = hostlib.coder([p], str(tmp_path / "s.fco"), quality=float(m["quality"]))
+    assert not ok and msg == m["message"]
+
+
+@pytest.mark.parametrize("z", [1, 2])
+def test_fiasco_coder_1024_higher_optimisation_levels(z, tmp_path):
+    m = O.manifest()["g1024_q20_z%d" % z]
+    pnm = str(tmp_path / "g1024.pgm")
+    gen_frames.write_pnm(pnm, gen_frames.frame("g1024"))
+    out = str(tmp_path / "g1024.fco")
+    ok, msg = hostlib.coder([pnm], out, quality=20.0, optimize=z)
+    assert ok, msg
+    assert md5(out) == m["fco_md5"]
+
+
+def _tile_split_case(key, split, gpus, tmp_path):
+    m = O.manifest()[key]
+    img = gen_frames.frame(m["frame"])
+    pnm = str(tmp_path / ("img" + (".pgm" if img.ndim == 2 else ".ppm")))
+    gen_frames.write_pnm(pnm, img)
+    out = str(tmp_path / "out.fco")
+    saved = _with_env(FIASCO_TILE_SPLIT=split, FIASCO_GPUS=gpus)
+    try:
+        ok, msg = hostlib.coder([pnm], out, quality=float(m["quality"]), optimize=m["optimize"])
+    finally:
+        _restore_env(saved)
+    assert ok, msg
+    n = 1 << split
+    got = [md5(str(tmp_path / ("out.t%02d.fco" % t))) for t in range(n)]
+    bad = [t for t in range(n) if got[t] != m["fco_md5"][t]]
+    assert not bad, "tiles %s differ from the reference coder run on the crops" % bad
+    assert not os.path.exists(out)
+
+
+def test_tile_split_config2_all_16_tiles(tmp_path):
+    """BASELINE config 2 in its tile-split form (FIASCO_TILE_SPLIT=4): every one of the 16 streams has the
+    bytes the reference writes for the 256^2 crop."""
+    _tile_split_case("tiles_g1024_256", 4, 1, tmp_path)
+
+
+def test_tile_split_config3_all_64_colour_tiles(tmp_path):
+    """BASELINE config 3: 2048^2 colour, q = 30, 64 streams."""
+    _tile_split_case("tiles_c2048_256", 6, 1, tmp_path)
+
+
+def test_tile_split_config4_all_64_tiles(tmp_path):
+    """BASELINE config 4: 4096^2 grey, q = 20, 64 streams of 512^2."""
+    _tile_split_case("tiles_g4096_512", 6, 1, tmp_path)
+
+
+def test_tile_split_over_all_gpus_of_the_box(tmp_path):
+    """FIASCO_GPUS: the tiles are dealt to the devices, one host thread each; same bytes.  (On a box
+    with one GPU the library clamps to it and this repeats the single-device case.)"""
+    import fiasco_b200 as F
+    _tile_split_case("tiles_g1024_256", 4, max(1, min(8, F.device_count())), tmp_path)
+
+
+def test_config5_full_size_stream_md5(tmp_path):
+    """BASELINE config 5 at its own size: 30 frames 720x576, IPPP, q = 20 (e9d88f99...)."""
+    m = O.manifest()["v720_q20_ippp"]
+    for i, f in enumerate(gen_frames.video(m["frames"], m["width"], m["height"])):
+        gen_frames.write_pnm(str(tmp_path / ("w%02d.pgm" % i)), f)
+    L = hostlib.load()
+    o = hostlib.cli_options(0)
+    L.fiasco_c_options_set_frame_pattern(o, m["pattern"].encode())
+    out = str(tmp_path / "v.fco")
+    saved = _with_env(FIASCO_GPUS=8)
+    try:
+        ok, msg = hostlib.coder([str(tmp_path / "w[00-29].pgm")], out, quality=20.0, options=o)
+    finally:
+        _restore_env(saved)
+        L.fiasco_c_options_delete(o)
+    assert ok, msg
+    assert md5(out) == m["fco_md5"] == "e9d88f99690abf5b88c449478ff1dbf3"
+
+
+def test_progress_meter_output(tmp_path):
+    """The meter of subdivide() (codec/subdivide.c:323-349) as the reference CLI shows it: the bar is 50
+    marks and a newline per band, the percent counter the values the traversal passes."""
+    exe = os.path.join(ROOT, "fiasco_b200", "lib", "cfiasco")
+    cf = os.path.join(REF, "cfiasco")
+    if not (os.path.exists(exe) and os.path.exists(cf)):
+        pytest.skip("needs both command line binaries")
+    pnm = str(tmp_path / "g.pgm")
+    gen_frames.write_pnm(pnm, gen_frames.frame("g1024")[:136, :200].copy())
+    data = tmp_path / "data"
+    data.mkdir()
+    (data / "small.fco").write_text("Fiasco\n")
+    for meter in ("1", "2"):
+        outs = []
+        for binary, datadir in ((exe, str(data)), (cf, os.path.join(REF, "data"))):
+            env = dict(os.environ, FIASCO_DATA=datadir, FIASCO_IMAGES=str(tmp_path))
+            r = subprocess.run([binary, "--progress-meter=" + meter, "-V", "1", "-q", "20", "-i", pnm, "-o",
+                                str(tmp_path / "o.fco")], env=env, capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr
+            outs.append([ln for ln in r.stderr.replace("\r", "\n").split("\n")
+                         if ln.strip() and "resource file" not in ln and "params.c" not in ln])
+        assert outs[0] == outs[1], meter
