@@ -301,7 +301,7 @@ work_layout (const DevParams &d, size_t *off /* [12] */)
    off [4] = o; o += up256 ((size_t) (d.n_frames > FB_MAXDEPTH ? d.n_frames : FB_MAXDEPTH)
 			   * 3 * d.blob_len * 2);				/* snap */
    off [5] = o; o += up256 (sc * sizeof (Trans));			/* trans */
-   off [6] = o; o += up256 ((sc + 1) * 4 * FB_MAXEDGES);		/* Gglob */
+   off [6] = o; o += up256 ((sc + 1) * 4 * FB_MAXEDGES) * FB_MAXCLUSTER;	/* Gglob, per block of a cluster */
    for (int i = 7; i < 12; i++)
       off [i] = o;
    if (d.motion)

@@ -138,6 +138,45 @@ as_global (T *p)
 }
 #define GP(p) as_global (p)
 
+/*
+ *  Thread-block cluster per stream (latency mode: fewer streams than SMs).  Rank 0 walks the
+ *  recursion; the other blocks of the cluster wait at the cluster barrier for jobs: their share
+ *  of the range x state products of a new block, of the state x state rows of a new state, and
+ *  the pursuits of the label-0 descendants of a range, which see the same models and states as
+ *  the range itself (codec/subdivide.c:188-237, 303-310).  Job descriptors, models and results
+ *  travel through distributed shared memory (mapa + ordinary stores), ordered by
+ *  barrier.cluster.arrive.release / wait.acquire, which also orders the global tables.
+ */
+#ifdef FB200_EMU
+__device__ inline unsigned cl_rank (void) { return emu_cluster_rank (); }
+__device__ inline void	   cl_sync (void) { emu_cluster_sync (); }
+template <typename T> __device__ inline T *cl_map (T *p, unsigned rank) { return (T *) emu_map_shared_rank (p, rank); }
+#else
+__device__ __forceinline__ unsigned
+cl_rank (void)
+{
+   unsigned r;
+   asm volatile ("mov.u32 %0, %%cluster_ctarank;" : "=r" (r));
+   return r;
+}
+__device__ __forceinline__ void
+cl_sync (void)
+{
+   asm volatile ("barrier.cluster.arrive.release.aligned;\n\t"
+		 "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+/* the address of the same shared-memory object in the block of another rank (generic address
+   of the shared::cluster window: ordinary loads and stores work on it) */
+template <typename T>
+__device__ __forceinline__ T *
+cl_map (T *p, unsigned rank)
+{
+   unsigned long long out;
+   asm volatile ("mapa.u64 %0, %1, %2;" : "=l" (out) : "l" ((unsigned long long) p), "r" (rank));
+   return (T *) out;
+}
+#endif
+
 /* transitions of a state in registers */
 struct TransReg
 {
@@ -225,6 +264,7 @@ struct Frame			/* one activation record of subdivide() */
    unsigned x, y, image, address;
    unsigned gaddr;		/* range->global_address: address in the whole picture (progress meter) */
    int	    level, y_state, label;
+   int	    spec_k;		/* position in the current spine of speculated pursuits, or -1 */
    int	    new_y_state [2];
    unsigned states_snap;
    float    r_err, r_tree_bits, r_matrix_bits, r_weights_bits; /* rrange sums */
@@ -286,6 +326,35 @@ struct MpWork
    short  best_c [FB_MAXEDGES];
    short  half_lv, half_dc;	/* rtob (0.5) of the two quantisers */
    float  best_mbits, best_wbits, best_err, best_costs;
+   unsigned st_steps, st_pass2;	/* work counters of this pursuit (added to the tile's when it is used) */
+};
+
+/* jobs of the helper blocks of a cluster */
+#define FB_SPINE_MAX 8
+enum { CJ_EXIT, CJ_SPINE, CJ_TINIT, CJ_APPEND };
+
+struct SpineNode		/* one pursuit of a spine: the range (level, image, address) */
+{
+   int	    level;
+   unsigned image, address;
+   float    tree_bits, norm;
+};
+
+struct ClJob
+{
+   int	     type, n;		/* CJ_*; SPINE: number of nodes */
+   unsigned  states;		/* wfa->states */
+   unsigned  pool_n;		/* SPINE: entries of the pool list */
+   int	     x, y, band;	/* TINIT: the block */
+   unsigned  s;			/* APPEND: the new state */
+   float     price;
+   SpineNode node [FB_SPINE_MAX];
+};
+
+struct SpecRes			/* result of a speculated pursuit */
+{
+   MpRes    mp;
+   unsigned steps, pass2, D;
 };
 
 struct ShHdr
@@ -328,6 +397,11 @@ struct ShHdr
    long long isum;		/* integer sum of squares of the interpolated prediction error */
    /* the percent meter of subdivide() (subdivide.c:105-108,323-337): last value, values shown */
    unsigned percent, progress [4];
+   /* cluster per stream */
+   ClJob    job;		/* rank 0: the job being posted; helpers: the job received */
+   SpecRes  spec [FB_SPINE_MAX];	/* rank 0: pursuits of the current spine (entry 0 unused) */
+   int	    spec_len;		/* nodes of the current spine */
+   int	    pool_lo;		/* lowest pool-list entry written since the list was last posted */
 };
 
 static_assert (offsetof (ShHdr, tree_total) == offsetof (ShHdr, tree_counts) + FB200_MAXLEVEL * sizeof (unsigned),
@@ -433,7 +507,7 @@ carve (unsigned char *base, const DevParams &p, int nt, float *gglob)
 #define LAP(h, i) do { if (threadIdx.x == 0) { const long long now_ = clock64 (); (h)->lap [i] += now_ - (h)->lap_last; (h)->lap_last = now_; } } while (0)
 #endif
 enum { LAP_CTRL, LAP_PIX, LAP_DOTS, LAP_UPSWEEP, LAP_ENTER, LAP_MP_PRO, LAP_MP_P1, LAP_MP_WAVES,
-       LAP_MP_COMMIT, LAP_MP_ORTHO, LAP_AR_EPI, LAP_AP_IMG, LAP_AP_DIRECT, LAP_AP_STAGED, LAP_DECIDE, LAP_N };
+       LAP_MP_COMMIT, LAP_MP_ORTHO, LAP_AR_EPI, LAP_AP_IMG, LAP_AP_DIRECT, LAP_AP_STAGED, LAP_DECIDE, LAP_CLUSTER, LAP_N };
 
 enum { ST_ENTER, ST_CHILD, ST_AFTER_CHILD, ST_DECIDE, ST_RETURN, ST_DONE, ST_ABORT };
 
@@ -624,9 +698,13 @@ async_wait_all (void)
 template <int NT>
 __device__ void
 cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
-	       unsigned node_root, int level_root, int top)
+	       unsigned node_root, int level_root, int top, unsigned g0 = 0, unsigned gnt = NT)
 {
-   const int	 tid	= threadIdx.x;
+   /* g0, gnt: the block's first thread and the number of threads when the blocks of a cluster
+      share the work (gnt > NT): the loops are strided over all of them and the levels are
+      separated by the cluster barrier */
+   const unsigned tid	= g0 + threadIdx.x;
+   const bool	 cl	= gnt > (unsigned) NT;
    const unsigned S	= sh.h->states;
    const unsigned scap	= (unsigned) P.s_cap;
 
@@ -647,7 +725,7 @@ cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
       {
 	 /* a warp covers 32 consecutive states and walks the nodes together: pixel
 	    reads are shared-memory broadcasts, product writes are coalesced */
-	 for (unsigned s = from + tid; s < S; s += NT)
+	 for (unsigned s = from + tid; s < S; s += gnt)
 	 {
 	    if (!GP (W.domain_type) [s])
 	       continue;
@@ -701,7 +779,7 @@ cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
       else
       {
 	 /* few new states: spread (state, node) pairs over the threads */
-	 for (unsigned item = tid; item < ns * nn; item += NT)
+	 for (unsigned item = tid; item < ns * nn; item += gnt)
 	 {
 	    const unsigned s = from + item / nn;
 	    const unsigned k = item % nn;
@@ -717,7 +795,10 @@ cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
 	 }
       }
    }
-   __syncthreads ();
+   if (cl)
+      cl_sync ();
+   else
+      __syncthreads ();
    LAP (sh.h, LAP_DOTS);
 
    /* upsweep */
@@ -727,11 +808,11 @@ cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
       const unsigned node0 = ((node_root + 1) << (level_root - l)) - 1;
       const unsigned ns	   = S - from;
 
-      if (ns >= (unsigned) NT / 2)
+      if (ns >= gnt / 2)
       {
 	 /* many states: a thread keeps one state's transitions in registers and walks
 	    the nodes of this level; the gathers hit the two child rows of a node */
-	 for (unsigned s = from + tid; s < S; s += NT)
+	 for (unsigned s = from + tid; s < S; s += gnt)
 	 {
 	    if (!GP (W.domain_type) [s])
 	       continue;
@@ -762,7 +843,7 @@ cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
       }
       else
       {
-	 for (unsigned item = tid; item < ns * nn; item += NT)
+	 for (unsigned item = tid; item < ns * nn; item += gnt)
 	 {
 	    const unsigned s	= from + item % ns;
 	    const unsigned node = node0 + item / ns;
@@ -788,7 +869,10 @@ cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
 	    GP (W.T) [(size_t) node * scap + s] = acc;
 	 }
       }
-      __syncthreads ();
+      if (cl)
+	 cl_sync ();
+      else
+	 __syncthreads ();
    }
    LAP (sh.h, LAP_UPSWEEP);
 }
@@ -797,7 +881,7 @@ cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
 template <int NT>
 __device__ void
 cta_init_range (const DevParams &P, const TileWs &W, const Sh &sh, unsigned x0,
-		unsigned y0, int band)
+		unsigned y0, int band, unsigned g0 = 0, unsigned gnt = NT)
 {
    const int	  tid  = threadIdx.x;
    const unsigned size = 1u << P.lc_max;
@@ -847,7 +931,7 @@ cta_init_range (const DevParams &P, const TileWs &W, const Sh &sh, unsigned x0,
 	 __syncthreads ();
       }
    }
-   if (tid == 0)
+   if (tid == 0 && g0 == 0)
    {
       unsigned ns = 0;
       /* need_image states: all states inside the image; count for the byte model */
@@ -856,7 +940,7 @@ cta_init_range (const DevParams &P, const TileWs &W, const Sh &sh, unsigned x0,
       sh.h->ip_bytes += 4ull * size + 4ull * (63 + (unsigned) ((1 << (P.lc_max - P.il)) - 1)) * ns;
    }
    LAP (sh.h, LAP_PIX);
-   cta_compute_T<NT> (P, W, sh, 0, 0, P.lc_max, P.lc_max);
+   cta_compute_T<NT> (P, W, sh, 0, 0, P.lc_max, P.lc_max, g0, gnt);
 }
 
 /* exact fp32 left-to-right sum of squares of a node (approx.c:388-389) */
@@ -976,8 +1060,11 @@ cta_state_images (const DevParams &P, const TileWs &W, unsigned s)
  */
 template <int NT>
 __device__ void
-cta_state_products (const DevParams &P, const TileWs &W, const Sh &sh, unsigned s)
+cta_state_products (const DevParams &P, const TileWs &W, const Sh &sh, unsigned s,
+		    int first_li = 0, int step_li = 1)
 {
+   /* first_li, step_li: the table levels of this block when the blocks of a cluster share the
+      new state's rows (the levels do not depend on each other) */
    const int tid  = threadIdx.x;
    ShHdr    *h	  = sh.h;
    /* scratch rows: the pursuit's work arrays are idle while a state is appended */
@@ -1027,7 +1114,7 @@ cta_state_products (const DevParams &P, const TileWs &W, const Sh &sh, unsigned 
    }
    __syncthreads ();
 
-   for (int li = 0; li < P.nlev; li++)
+   for (int li = first_li; li < P.nlev; li += step_li)
    {
       const int level = P.lmin + li;
 
@@ -1170,6 +1257,8 @@ t0_append_edge (const TileWs &W, unsigned from, int into, float weight, int labe
    wt [edge] = weight;
 }
 
+template <int NT> __device__ void cta_cluster_post (const DevParams &P, const Sh &sh, bool with_models);
+
 /*
  *  codec/control.c:48-131 (append_state).  The state's tree / edges are already in place.
  *  Must be called by all threads; 'auxiliary' and 'level' are uniform.
@@ -1197,7 +1286,22 @@ cta_append_state (const DevParams &P, const TileWs &W, const Sh &sh, int auxilia
       LAP (sh.h, LAP_DECIDE);
       cta_state_images<NT> (P, W, s);
       LAP (sh.h, LAP_AP_IMG);
-      cta_state_products<NT> (P, W, sh, s);
+      if (P.cluster > 1)
+      {
+	 /* the table levels are shared out over the blocks of the cluster */
+	 if (threadIdx.x == 0)
+	 {
+	    sh.h->job.type   = CJ_APPEND;
+	    sh.h->job.states = s;
+	    sh.h->job.s	     = s;
+	 }
+	 cta_cluster_post<NT> (P, sh, false);
+	 cta_state_products<NT> (P, W, sh, s, 0, P.cluster);
+	 cl_sync ();
+	 LAP (sh.h, LAP_CLUSTER);
+      }
+      else
+	 cta_state_products<NT> (P, W, sh, s);
    }
    if (threadIdx.x == 0)
    {
@@ -1596,7 +1700,7 @@ cta_mp_find (const DevParams &P, const Sh &sh, MpRes &mp, float price, int n)
 	    w.wave_done = !more;
 	    w.wave_pos	= more ? last_cand + 1 : D;
 	    if (taken)
-	       sh.h->pass2 += (unsigned) taken;
+	       w.st_pass2 += (unsigned) taken;
 	 }
       }
       __syncthreads ();
@@ -1609,16 +1713,18 @@ cta_mp_find (const DevParams &P, const Sh &sh, MpRes &mp, float price, int n)
 }
 
 /*
- *  One matching pursuit over the current pool for the range (level, image, address).
- *  'mp' lives in shared memory; 'excluded' is the domain index the second_domain_block retry
+ *  One matching pursuit over the current pool for the range (level, image) of the block's
+ *  product tree.  'mp' lives in shared memory; the work counters of the call are left in
+ *  w.st_* / w.D for whoever uses the result; 'excluded' is the domain index the second_domain_block retry
  *  must not use (approx.c:112-116), or -1.
  */
 template <int NT>
 __device__ void
 cta_matching_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &mp,
-		      int level, unsigned image, unsigned address, float tree_bits,
+		      int level, unsigned image, float norm, float tree_bits,
 		      float mv_tree_bits, float price, int y_state_in, int excluded)
 {
+   /* norm: the squared norm of the range (t0_node_norm), needed by thread 0 only */
    const int	tid	 = threadIdx.x;
    MpWork      &w	 = sh.h->w;
    const float	min_norm = 2e-3f;
@@ -1651,18 +1757,19 @@ cta_matching_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &
 	    w.ydom = w.pool_n;
 	    w.D	   = w.pool_n + 1;
 	    sh.pool [w.pool_n] = (short) y_state;
+	    if (w.pool_n < sh.h->pool_lo)
+	       sh.h->pool_lo = w.pool_n;
 	 }
       }
       w.level = level;
       w.li    = level - P.lmin;
       w.size  = 1 << level;
       w.price = price;
-      w.norm  = t0_node_norm (P, sh, image, address, level);
+      w.norm  = norm;
       w.additional_bits = tree_bits + mv_tree_bits + 0.0f + 0.0f + 0.0f;
       w.d0b [0] = t0_d0_bits (sh, 0, y_state, c_matrix_0, c_matrix_1);
       w.d0b [1] = t0_d0_bits (sh, 1, y_state, c_matrix_0, c_matrix_1);
-      sh.h->mp_calls++;
-      sh.h->mp_bytes += 8ull * (unsigned) w.D;
+      w.st_steps = w.st_pass2 = 0;
    }
    /*
     *  Grey bands (no y-state): nothing the other threads need depends on thread 0's scalars,
@@ -1770,8 +1877,7 @@ cta_matching_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &
 	 sh.used [index] = 1;
 	 w.B [n] = sh.num [index];
 	 w.N [n] = sh.den [index];
-	 sh.h->mp_steps++;
-	 sh.h->mp_bytes += 4ull * (unsigned) w.D;
+	 w.st_steps++;
 	 if (n + 1 < P.max_elements)
 	    t0_mp_prepare_step (P, sh, mp, n + 1);
       }
@@ -1910,12 +2016,31 @@ template <int NT>
 __device__ void
 cta_approximate_range (const DevParams &P, const TileWs &W, const Sh &sh, float max_costs,
 		       float price, int y_state, RangeRes *out, int level, unsigned image,
-			       unsigned address, unsigned x, unsigned y, float mv_tree_bits)
+			       unsigned address, unsigned x, unsigned y, float mv_tree_bits,
+		       int spec_k = 0)
 {
    ShHdr *h = sh.h;
 
    /* one call site (one copy of the pursuit's code); the second round is the
       second_domain_block retry without the first domain (approx.c:103-127) */
+   if (spec_k > 0)
+   {
+      /* the pursuit of this range ran ahead, next to the one of the range at the head of the
+	 spine: same models, same states (cluster per stream) */
+      if (threadIdx.x == 0)
+      {
+	 const SpecRes &r = h->spec [spec_k];
+
+	 h->mp	      = r.mp;
+	 h->w.y_state = -1;
+	 h->mp_calls++;
+	 h->mp_steps += r.steps;
+	 h->pass2    += r.pass2;
+	 h->mp_bytes += 8ull * r.D + 4ull * r.D * r.steps;
+      }
+      __syncthreads ();
+   }
+   else
    for (int round = 0; round <= (P.second_domain_block ? 1 : 0); round++)
    {
       MpRes &m = round ? h->tmp : h->mp;
@@ -1927,8 +2052,19 @@ cta_approximate_range (const DevParams &P, const TileWs &W, const Sh &sh, float 
 	 __syncthreads ();
       }
       /* (the prologue of the pursuit starts with thread-0 work followed by a barrier) */
-      cta_matching_pursuit<NT> (P, W, sh, m, level, image, address, out->tree_bits,
-				mv_tree_bits, price, y_state, round ? (int) h->mp.indices [0] : -1);
+      cta_matching_pursuit<NT> (P, W, sh, m, level, image,
+				threadIdx.x == 0 ? t0_node_norm (P, sh, image, address, level) : 0.0f,
+				out->tree_bits, mv_tree_bits, price, y_state,
+				round ? (int) h->mp.indices [0] : -1);
+      if (threadIdx.x == 0)
+      {
+	 const MpWork &w = h->w;
+
+	 h->mp_calls++;
+	 h->mp_steps += w.st_steps;
+	 h->pass2    += w.st_pass2;
+	 h->mp_bytes += 8ull * (unsigned) w.D + 4ull * (unsigned) w.D * w.st_steps;
+      }
    }
    if (P.second_domain_block)
    {
@@ -2203,6 +2339,120 @@ cta_mcpe_range (const DevParams &P, const TileWs &W, const Sh &cs, unsigned x0, 
 }
 
 /*****************************************************************************
+			  cluster per stream: jobs
+*****************************************************************************/
+
+/*
+ *  Rank 0: hand the job in h->job (filled by thread 0) to the helper blocks, which wait at the
+ *  cluster barrier.  with_models: the pursuits of a spine also need the probability models and
+ *  the entries of the pool list written since the last time.  Everything is stored into the
+ *  helpers' shared memory BEFORE the barrier, so nothing of rank 0 is read afterwards.
+ */
+template <int NT>
+__device__ void
+cta_cluster_post (const DevParams &P, const Sh &sh, bool with_models)
+{
+   ShHdr    *h	 = sh.h;
+   const int tid = threadIdx.x;
+   const int C	 = P.cluster;
+   const int jw	 = (int) (sizeof (ClJob) / 4);
+
+   LAP (h, LAP_CTRL);
+   __syncthreads ();
+   for (int it = tid; it < (C - 1) * jw; it += NT)
+   {
+      const unsigned r = 1u + (unsigned) (it / jw);
+      const int	     i = it % jw;
+
+      ((unsigned *) &cl_map (h, r)->job) [i] = ((const unsigned *) &h->job) [i];
+   }
+   if (with_models)
+   {
+      const int bw = P.blob_len / 8;
+      const int lo = h->pool_lo, np = (int) h->job.pool_n - lo;
+
+      for (int it = tid; it < (C - 1) * bw; it += NT)
+      {
+	 const unsigned r = 1u + (unsigned) (it / bw);
+	 const int	i = it % bw;
+
+	 ((uint4 *) cl_map (sh.blob, r)) [i] = ((const uint4 *) sh.blob) [i];
+      }
+      if (np > 0)
+	 for (int it = tid; it < (C - 1) * np; it += NT)
+	 {
+	    const unsigned r = 1u + (unsigned) (it / np);
+	    const int	   i = lo + it % np;
+
+	    cl_map (sh.pool, r) [i] = sh.pool [i];
+	 }
+      __syncthreads ();
+      if (tid == 0)
+	 h->pool_lo = (int) h->job.pool_n;
+   }
+   cl_sync ();
+   LAP (h, LAP_CLUSTER);
+}
+
+/* one pursuit of a spine on this block; the result goes to slot k of rank 0 */
+template <int NT>
+__device__ void
+cta_spine_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, int k, SpecRes *dst)
+{
+   ShHdr	  *h  = sh.h;
+   const SpineNode nd = h->job.node [k];
+
+   cta_matching_pursuit<NT> (P, W, sh, h->mp, nd.level, nd.image, nd.norm, nd.tree_bits, 0.0f,
+			     h->job.price, FB_RANGE, -1);
+   for (int i = threadIdx.x; i < (int) (sizeof (MpRes) / 4); i += NT)
+      ((unsigned *) &dst->mp) [i] = ((const unsigned *) &h->mp) [i];
+   if (threadIdx.x == 0)
+   {
+      dst->steps = h->w.st_steps;
+      dst->pass2 = h->w.st_pass2;
+      dst->D	 = (unsigned) h->w.D;
+   }
+   __syncthreads ();
+}
+
+/* ranks > 0: serve rank 0 until it says the frame is done */
+template <int NT>
+__device__ void
+cta_helper_loop (const DevParams &P, const TileWs &W, const Sh &sh, unsigned rank)
+{
+   ShHdr    *h = sh.h;
+   const int C = P.cluster;
+
+   for (;;)
+   {
+      cl_sync ();			/* a job has been posted */
+      const int type = h->job.type;
+
+      if (type == CJ_EXIT)
+	 break;
+      if (threadIdx.x == 0)
+	 h->states = h->job.states;
+      __syncthreads ();
+      if (type == CJ_TINIT)
+	 /* this block's share of the products of a new lc_max block; ends with the cluster barrier
+	    after the last level */
+	 cta_init_range<NT> (P, W, sh, (unsigned) h->job.x, (unsigned) h->job.y, h->job.band,
+			     rank * NT, (unsigned) C * NT);
+      else if (type == CJ_APPEND)
+      {
+	 cta_state_products<NT> (P, W, sh, h->job.s, (int) rank, C);
+	 cl_sync ();
+      }
+      else
+      {
+	 for (int k = (int) rank; k < h->job.n; k += C)
+	    cta_spine_pursuit<NT> (P, W, sh, k, &cl_map (h, 0)->spec [k]);
+	 cl_sync ();
+      }
+   }
+}
+
+/*****************************************************************************
 		   the bintree recursion  (codec/subdivide.c:60-502)
 *****************************************************************************/
 
@@ -2376,6 +2626,8 @@ t0_advance (const DevParams &P, const TileWs &W, ShHdr *h, int &state, int &dept
 	    C.gaddr	= F.gaddr * 2 + label;
 	    C.level	= level - 1;
 	    C.y_state	= F.new_y_state [label];
+	    /* the label-0 descendants of the head of a spine find their pursuit done */
+	    C.spec_k	= (label == 0 && F.spec_k >= 0 && F.spec_k + 1 < h->spec_len) ? F.spec_k + 1 : -1;
 	    if (MOTION)
 	    {
 	       h->fx [depth + 1].delta	    = h->fx [depth].delta;
@@ -2405,6 +2657,7 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
    ShHdr    *h	 = sh.h;
    const int tid = threadIdx.x;
    int	     it	 = 0;
+   const bool CL = !MOTION && P.cluster > 1;	/* helper blocks at hand */
    const int SN	 = MOTION ? 3 : 2;	/* model snapshots per activation record */
    const int TS	 = MOTION ? 2 : 1;	/* tree-model snapshots per record */
    Sh	     shn = sh;			/* buffers and models of the nested (prediction error) pass */
@@ -2423,6 +2676,8 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
       F.max_costs = FB_MAXCOSTS;
       F.x = F.y = F.image = F.address = F.gaddr = 0;
       F.level	= P.level;
+      F.spec_k	= -1;
+      h->spec_len = 0;
       h->percent = 0;
       h->progress [0] = h->progress [1] = h->progress [2] = h->progress [3] = 0;
       F.y_state = root_y_state;
@@ -2465,7 +2720,21 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 	 const long long t0c   = clock64 ();
 	 const bool	 block = state == ST_ENTER;
 
-	 if (block)
+	 if (block && CL)
+	 {
+	    /* every block of the cluster takes its share of the states */
+	    if (tid == 0)
+	    {
+	       h->job.type   = CJ_TINIT;
+	       h->job.states = h->states;
+	       h->job.x	     = (int) F.x;
+	       h->job.y	     = (int) F.y;
+	       h->job.band   = band;
+	    }
+	    cta_cluster_post<NT> (P, sh, false);
+	    cta_init_range<NT> (P, W, cs, F.x, F.y, band, 0, (unsigned) P.cluster * NT);
+	 }
+	 else if (block)
 	    cta_init_range<NT> (P, W, cs, F.x, F.y, band);
 	 else
 	    cta_compute_T<NT> (P, W, cs, F.states_snap, F.image * 2 + F.label + 1, F.level - 1,
@@ -2558,10 +2827,62 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 	    /* alternative 1: linear combination (subdivide.c:200-221) */
 	    if (level <= P.lc_max)
 	    {
-	       const long long t0c = clock64 ();
+	       const long long t0c   = clock64 ();
+	       const int       sk    = CL ? F.spec_k : 0;
+	       bool	       spine = false;
+
+	       if (CL && sk < 0 && F.y_state < 0 && !P.second_domain_block)
+	       {
+		  /*
+		   *  Head of a spine: the ranges reached from here by label 0 alone, down to
+		   *  lc_min_level, are approximated with the models and states of this moment
+		   *  (subdivide.c:188-237: the models are put back before the first child is
+		   *  entered; states are appended only when a child returns) -- their pursuits run
+		   *  now, one per block of the cluster, next to this range's own.
+		   */
+		  int n = level - h->lc_min + 1;
+
+		  if (n > FB_SPINE_MAX)
+		     n = FB_SPINE_MAX;
+		  if (n >= 2)
+		  {
+		     if (tid == 0)
+		     {
+			h->job.type   = CJ_SPINE;
+			h->job.n      = n;
+			h->job.states = h->states;
+			h->job.pool_n = BLOB_U16 (sh, MB_N);
+			h->job.price  = h->price;
+			for (int k = 0; k < n; k++)
+			{
+			   SpineNode &nd = h->job.node [k];
+
+			   nd.level	= level - k;
+			   nd.image	= ((F.image + 1) << k) - 1;
+			   nd.address	= F.address << k;
+			   nd.tree_bits = k ? t0_tree_bits (h, 0, level - k) : F.lrange.tree_bits;
+			   nd.norm	= t0_node_norm (P, cs, nd.image, nd.address, nd.level);
+			}
+			h->spec_len = n;
+		     }
+		     cta_cluster_post<NT> (P, sh, true);
+		     if (tid == 0)
+			F.spec_k = 0;	/* (after the barriers of the post: every thread has read it) */
+		     /* a spine longer than the cluster: this block's further nodes */
+		     for (int k = P.cluster; k < n; k += P.cluster)
+			cta_spine_pursuit<NT> (P, W, sh, k, &h->spec [k]);
+		     spine = true;
+		  }
+	       }
 	       cta_approximate_range<NT> (P, W, cs, F.max_costs, h->price, F.y_state,
 					  &F.lrange, level, F.image, F.address, F.x, F.y,
-					  MOTION ? h->fx [depth].lrange.mv_tree_bits : 0.0f);
+					  MOTION ? h->fx [depth].lrange.mv_tree_bits : 0.0f,
+					  sk > 0 ? sk : 0);
+	       if (spine)
+	       {
+		  cl_sync ();		/* the helpers' results are in h->spec */
+		  LAP (h, LAP_CLUSTER);
+	       }
 	       if (tid == 0)
 	       {
 		  F.lincomb_costs = h->ret_costs;
@@ -2910,6 +3231,7 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 		     C.gaddr	 = F.gaddr;
 		     C.level	 = level;
 		     C.y_state	 = F.y_state;
+		     C.spec_k	 = -1;
 		     h->fx [depth + 1].delta	  = 1;
 		     h->fx [depth + 1].prediction = 0;
 		     X.prange.into [0] = FB_NO_EDGE;
@@ -2983,6 +3305,8 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 		     if (n < BLOB_U16 (sh, MB_MAXDOM))
 		     {
 			sh.pool [n]	    = (short) s;
+			if ((int) n < h->pool_lo)
+			   h->pool_lo = (int) n;
 			BLOB_U16 (sh, MB_N) = (unsigned short) (n + 1);
 			if (MOTION)
 			   BLOB_U16 (shn, MB_N) = (unsigned short) (n + 1);
@@ -3116,6 +3440,7 @@ t0_chroma_setup (const DevParams &P, const TileWs &W, const Sh &sh, int *hits)
 	    sh.pool [cnt++] = (short) d;
       BLOB_U16 (sh, MB_N) = (unsigned short) cnt;
    }
+   h->pool_lo = 0;
    BLOB_U16 (sh, MB_YINDEX) = 0;
    BLOB_U16 (sh, MB_MAXDOM) = BLOB_U16 (sh, MB_N);
 
@@ -3175,9 +3500,13 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
       pursuit loops need more urgently */
    __shared__ TileWs s_W;
    int		     slot = -1;
+   /* cluster per stream: rank 0 encodes, the others serve it */
+   const unsigned    crank  = P.cluster > 1 ? cl_rank () : 0u;
+   const unsigned    tile   = P.cluster > 1 ? blockIdx.x / (unsigned) P.cluster : blockIdx.x;
+   const unsigned    ntiles = P.cluster > 1 ? gridDim.x / (unsigned) P.cluster : gridDim.x;
 
    if (threadIdx.x == 0)
-      s_W = ws_array [blockIdx.x];
+      s_W = ws_array [tile];
 
    /*
     *  More tiles than workspaces: take a free one (entry i of ws_array also describes
@@ -3185,7 +3514,7 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
     *  the scan starts at a different place on every SM.  Everything the kernel reads from a
     *  workspace it has written itself before, so the previous user's data never shows.
     */
-   if ((int) gridDim.x > P.n_slots)	/* uniform */
+   if ((int) ntiles > P.n_slots)	/* uniform; never with a cluster (launcher) */
    {
       __shared__ int s_slot;
 
@@ -3225,7 +3554,7 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
    }
    __syncthreads ();
    const TileWs &W  = s_W;
-   const Sh	sh  = carve (smem_raw, P, NT, GP (W.Gglob));
+   const Sh	sh  = carve (smem_raw, P, NT, GP (W.Gglob) + (size_t) crank * FB_MAXEDGES * (P.s_cap + 1));
    const Sh    &sh_base = sh;
    ShHdr       *h   = sh.h;
    const int	tid = threadIdx.x;
@@ -3247,6 +3576,8 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
       for (int i = 0; i < 16; i++)
 	 h->lap [i] = 0;
       h->states	   = 0;
+      h->pool_lo   = 0;
+      h->spec_len  = 0;
    }
    __syncthreads ();
 
@@ -3260,6 +3591,12 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
       h->w.half_dc = (short) dev_rtob (0.5f, P.dc_m, P.dc_range);
    }
    __syncthreads ();
+
+   if (crank != 0)
+   {
+      cta_helper_loop<NT> (P, W, sh, crank);
+      return;
+   }
 
    {
       cta_init_basis<NT> (P, W, sh);
@@ -3322,7 +3659,7 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
    {
       /* a frame of a colour sequence starts with the range levels the chroma bands of the frame
 	 before left behind (coder.c:797: c->options.lc_min_level is never set back) */
-      const int given = P.tile_lc_min ? P.tile_lc_min [blockIdx.x] : 0;
+      const int given = P.tile_lc_min ? P.tile_lc_min [tile] : 0;
 
       h->lc_min = given > P.lc_min && given <= P.lc_max ? given : P.lc_min;
    }
@@ -3399,6 +3736,12 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
 	 __threadfence ();
 	 atomicExch (P.slot_flags + slot, 0);
       }
+   }
+   if (P.cluster > 1)
+   {
+      if (tid == 0)
+	 h->job.type = CJ_EXIT;
+      cta_cluster_post<NT> (P, sh, false);
    }
 }
 
@@ -3501,7 +3844,7 @@ upload_tables (void)
 
 template <int NT, bool MOTION>
 static cudaError_t
-launch_nt (const DevParams &p_in, const TileWs *d_ws, int n_tiles, cudaStream_t stream)
+launch_nt (const DevParams &p_in, const TileWs *d_ws, int n_tiles, cudaStream_t stream, int cluster = 1)
 {
    const auto kernel = fiasco_tile_kernel<NT, MOTION>;
    DevParams	p = p_in;
@@ -3520,7 +3863,30 @@ launch_nt (const DevParams &p_in, const TileWs *d_ws, int n_tiles, cudaStream_t 
       if (cv)
 	 cudaFuncSetAttribute (kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi (cv));
    }
-   FB_LAUNCH (kernel, n_tiles, NT, smem, stream, p, d_ws);
+   p.cluster = cluster > 1 ? cluster : 1;
+   if (p.cluster > 1)
+   {
+#ifdef FB200_EMU
+      FB_LAUNCH_CLUSTER (kernel, n_tiles * p.cluster, NT, p.cluster, smem, stream, p, d_ws);
+#else
+      cudaLaunchConfig_t  cfg = {};
+      cudaLaunchAttribute at [1];
+
+      cfg.gridDim	   = dim3 ((unsigned) (n_tiles * p.cluster));
+      cfg.blockDim	   = dim3 (NT);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream	   = stream;
+      at [0].id		       = cudaLaunchAttributeClusterDimension;
+      at [0].val.clusterDim.x = (unsigned) p.cluster;
+      at [0].val.clusterDim.y = 1;
+      at [0].val.clusterDim.z = 1;
+      cfg.attrs	   = at;
+      cfg.numAttrs = 1;
+      return cudaLaunchKernelEx (&cfg, kernel, p, d_ws);
+#endif
+   }
+   else
+      FB_LAUNCH (kernel, n_tiles, NT, smem, stream, p, d_ws);
    return cudaGetLastError ();
 }
 
@@ -3540,8 +3906,61 @@ fb_launch_tile_kernel (const DevParams &p, const TileWs *d_ws, int n_tiles,
       case 96:	return launch_nt<96, false> (p, d_ws, n_tiles, stream);
       case 128: return launch_nt<128, false> (p, d_ws, n_tiles, stream);
       case 256: return launch_nt<256, false> (p, d_ws, n_tiles, stream);
-      default:	return launch_nt<512, false> (p, d_ws, n_tiles, stream);
+      default:	return launch_nt<512, false> (p, d_ws, n_tiles, stream, fb_tile_kernel_cluster (p, n_tiles));
    }
+}
+
+/*
+ *  Thread blocks per stream.  A full batch keeps every SM busy with streams of its own; with
+ *  fewer streams than SMs the idle SMs join the streams as helper blocks (powers of two up to
+ *  the portable cluster size 8): a single 1024^2 frame runs on 8 SMs, the 64 tiles of a
+ *  4096^2 frame on 128.
+ */
+int
+fb_tile_kernel_cluster (const DevParams &p, int n_tiles)
+{
+   int sms = 148, dev = 0, c = 1;
+
+   if (p.motion || n_tiles <= 0 || n_tiles > p.n_slots)
+      return 1;
+   if (fb_tile_kernel_threads (p, n_tiles) != 512)
+      return 1;
+   if (cudaGetDevice (&dev) == cudaSuccess)
+      cudaDeviceGetAttribute (&sms, cudaDevAttrMultiProcessorCount, dev);
+   while (c * 2 <= FB_MAXCLUSTER && n_tiles * c * 2 <= sms)
+      c *= 2;
+   {
+      const char *e = getenv ("FB200_CLUSTER");	/* experiments / tests: force the size */
+      if (e && atoi (e) >= 1 && atoi (e) <= FB_MAXCLUSTER)
+	 c = atoi (e);
+   }
+#ifndef FB200_EMU
+   /* as many clusters as streams must be able to run at once (they are co-scheduled per GPC) */
+   while (c > 1)
+   {
+      cudaLaunchConfig_t  cfg = {};
+      cudaLaunchAttribute at [1];
+      int		  n = 0;
+      DevParams		  q = p;
+      size_t		  off [20];
+
+      cfg.gridDim	   = dim3 ((unsigned) (n_tiles * c));
+      cfg.blockDim	   = dim3 (512);
+      cfg.dynamicSmemBytes = smem_layout (q, 512, off);
+      at [0].id		       = cudaLaunchAttributeClusterDimension;
+      at [0].val.clusterDim.x = (unsigned) c;
+      at [0].val.clusterDim.y = at [0].val.clusterDim.z = 1;
+      cfg.attrs	   = at;
+      cfg.numAttrs = 1;
+      cudaFuncSetAttribute (fiasco_tile_kernel<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+			    (int) cfg.dynamicSmemBytes);
+      if (cudaOccupancyMaxActiveClusters (&n, fiasco_tile_kernel<512, false>, &cfg) == cudaSuccess && n >= n_tiles)
+	 break;
+      cudaGetLastError ();
+      c /= 2;
+   }
+#endif
+   return c;
 }
 
 template <int NT>

@@ -17,6 +17,8 @@
 #ifdef FB200_EMU
 #define FB_LAUNCH(kernel, grid, block, smem, stream, ...) \
    emu_launch (grid, block, smem, [&] () { kernel (__VA_ARGS__); })
+#define FB_LAUNCH_CLUSTER(kernel, grid, block, cluster, smem, stream, ...) \
+   emu_launch_cluster (grid, block, cluster, smem, [&] () { kernel (__VA_ARGS__); })
 #define FB_DYN_SMEM(type, name) type *name = (type *) emu_dyn_smem ()
 #else
 #define FB_LAUNCH(kernel, grid, block, smem, stream, ...) \
@@ -72,7 +74,10 @@ struct DevParams
    int	 blob_half;		/* shorts of one model set; blob = normal set, then delta set */
    int	 n_frames;		/* DFS activation records (nested delta pass included) */
    const int *tile_lc_min;	/* [tiles] lc_min_level a tile starts with (0: lc_min), or NULL */
+   int	 cluster;		/* thread blocks per stream (filled by the launcher): rank 0 walks the
+				   recursion, the others serve it (tile_kernel.cu, "cluster per stream") */
 };
+#define FB_MAXCLUSTER 8
 
 /* all transitions of one state in one 64-byte line: what the inner-product kernels gather */
 struct __align__ (64) Trans
@@ -91,7 +96,8 @@ struct TileWs
    float   *SS;			/* [nlev][s_cap][s_cap]	  state x state products */
    float   *diag;		/* [nlev][s_cap]	  <s,s> */
    Trans   *trans;		/* [s_cap]		  packed transitions */
-   float   *Gglob;		/* [max_elements-1][s_cap+1] Gram-Schmidt rows when not in smem */
+   float   *Gglob;		/* [FB_MAXCLUSTER][max_elements-1][s_cap+1] Gram-Schmidt rows when not in
+				   smem, one set per block of the cluster */
    /* automaton */
    float   *final_d;		/* [s_cap] */
    uint8_t *level_of_state;	/* [s_cap] */
@@ -136,6 +142,7 @@ struct TileResult
 
 size_t fb_tile_kernel_smem (const DevParams &p, int nt);
 int    fb_tile_kernel_threads (const DevParams &p, int n_tiles);
+int    fb_tile_kernel_cluster (const DevParams &p, int n_tiles);	/* blocks per stream */
 int    fb_tile_kernel_occupancy (const DevParams &p);	/* resident tiles per SM */
 cudaError_t fb_launch_tile_kernel (const DevParams &p, const TileWs *d_ws, int n_tiles,
 				   cudaStream_t stream);

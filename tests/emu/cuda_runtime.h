@@ -49,7 +49,13 @@ struct __attribute__ ((aligned (16))) uint4  { unsigned x, y, z, w; };
 
 /* ---- scheduler entry points (emu_runtime.cpp) ---- */
 void	 emu_launch (emu_dim3 grid, emu_dim3 block, size_t smem, const std::function<void ()> &body);
+void	 emu_launch_cluster (emu_dim3 grid, emu_dim3 block, unsigned cluster, size_t smem,
+			     const std::function<void ()> &body);
 void	 emu_syncthreads (void);
+void	 emu_cluster_sync (void);		/* barrier.cluster arrive + wait */
+unsigned emu_cluster_rank (void);
+unsigned emu_cluster_size (void);
+void	*emu_map_shared_rank (const void *p, unsigned rank);	/* mapa */
 unsigned emu_warp_exchange (unsigned value, int kind, int arg);	/* 0 shfl, 1 shfl_up, 2 ballot, 3 sync */
 unsigned char *emu_dyn_smem (void);
 

@@ -40,10 +40,16 @@ struct Warp
    unsigned slot [2][32];
 };
 
-struct Block
+enum { MAX_CLUSTER = 8 };
+
+struct Block			/* the thread blocks of one cluster (usually one), run together */
 {
-   int	    n, alive, cur;
-   unsigned bar_count, bar_gen;
+   int	    n, alive, cur;	/* n: fibres of the whole cluster; per_cta threads each */
+   int	    per_cta, ctas;
+   unsigned first_block;	/* blockIdx.x of rank 0 */
+   unsigned bar_count [MAX_CLUSTER], bar_gen [MAX_CLUSTER];
+   int	    cta_alive [MAX_CLUSTER];
+   unsigned cl_count, cl_gen;	/* barrier.cluster */
    std::vector<void *> sp;
    std::vector<char>   done;
    std::vector<Warp>   warps;
@@ -52,6 +58,11 @@ struct Block
 };
 
 Block	       B;
+/* what each fibre waits for (0 runs, 1 block barrier, 2 cluster barrier, 3 warp collective), and
+   the number of switches since a rendezvous last completed: a cycle through all fibres without
+   progress is a deadlock */
+std::vector<char> g_wait;
+unsigned long	  g_idle;
 /* scheduling order between rendezvous points (FB200_EMU_ORDER): 0 ascending thread index,
    1 descending, 2 pseudo-random.  A result that depends on it is a race between barriers. */
 int	       g_order = -1;
@@ -59,7 +70,10 @@ unsigned       g_rand  = 12345u;
 unsigned long long g_barriers, g_warp_ops;	/* rendezvous counters (whole process) */
 char	      *g_stacks;
 size_t	       g_stacks_n;
-unsigned char *g_smem;
+unsigned char *g_smem;		/* MAX_CLUSTER regions of SMEM_BYTES */
+enum { SMEM_BYTES = 256 * 1024 };
+
+inline int cur_rank (void) { return B.cur / B.per_cta; }
 
 void
 switch_to_next (void)
@@ -67,6 +81,24 @@ switch_to_next (void)
    const int from = B.cur;
    int	     next = from;
 
+   if (++g_idle > (g_order == 2 ? 400ul : 4ul) * (unsigned long) B.n + 64)
+   {
+      int cnt [4] = {0, 0, 0, 0};
+      for (int i = 0; i < B.n; i++)
+	 if (!B.done [i])
+	    cnt [(int) g_wait [i]]++;
+      fprintf (stderr, "emu: deadlock -- %d threads alive: %d at a block barrier, %d at the cluster barrier, "
+	       "%d in a warp collective, %d running\n", B.alive, cnt [1], cnt [2], cnt [3], cnt [0]);
+      for (int r = 0; r < B.ctas; r++)
+      {
+	 int c [4] = {0, 0, 0, 0};
+	 for (int i = r * B.per_cta; i < (r + 1) * B.per_cta; i++)
+	    if (!B.done [i])
+	       c [(int) g_wait [i]]++;
+	 fprintf (stderr, "   rank %d: block barrier %d, cluster barrier %d, warp %d, running %d\n", r, c [1], c [2], c [3], c [0]);
+      }
+      abort ();
+   }
    if (B.alive == 0)
    {
       B.cur = -1;
@@ -92,7 +124,8 @@ switch_to_next (void)
       abort ();
    }
    B.cur       = next;
-   threadIdx.x = (unsigned) next;
+   threadIdx.x = (unsigned) (next % B.per_cta);
+   blockIdx.x  = B.first_block + (unsigned) (next / B.per_cta);
    emu_switch (&B.sp [from], B.sp [next]);
 }
 
@@ -100,12 +133,20 @@ void
 fibre_main (void)
 {
    (*B.body) ();
+   const int r = cur_rank ();
    B.done [B.cur] = 1;
+   g_idle = 0;
    B.alive--;
-   if (B.alive && B.bar_count == (unsigned) B.alive)	/* the others wait at a barrier */
+   B.cta_alive [r]--;
+   if (B.cta_alive [r] && B.bar_count [r] == (unsigned) B.cta_alive [r])	/* the others wait at a barrier */
    {
-      B.bar_count = 0;
-      B.bar_gen++;
+      B.bar_count [r] = 0;
+      B.bar_gen [r]++;
+   }
+   if (B.alive && B.cl_count == (unsigned) B.alive)
+   {
+      B.cl_count = 0;
+      B.cl_gen++;
    }
    switch_to_next ();
    abort ();			/* a finished fibre is never resumed */
@@ -125,17 +166,58 @@ emu_counters (unsigned long long *barriers, unsigned long long *warp_ops)
 void
 emu_syncthreads (void)
 {
-   const unsigned gen = B.bar_gen;
+   const int	  r   = cur_rank ();
+   const unsigned gen = B.bar_gen [r];
 
-   if (++B.bar_count == (unsigned) B.alive)
+   if (++B.bar_count [r] == (unsigned) B.cta_alive [r])
    {
-      g_barriers++;
-      B.bar_count = 0;
-      B.bar_gen++;
+      if (r == 0)
+	 g_barriers++;
+      B.bar_count [r] = 0;
+      B.bar_gen [r]++;
+      g_idle = 0;
       return;
    }
-   while (B.bar_gen == gen)
+   g_wait [B.cur] = 1;
+   while (B.bar_gen [r] == gen)
       switch_to_next ();
+   g_wait [B.cur] = 0;
+}
+
+/* barrier.cluster.arrive + wait of every thread of the cluster */
+void
+emu_cluster_sync (void)
+{
+   const unsigned gen = B.cl_gen;
+
+   if (++B.cl_count == (unsigned) B.alive)
+   {
+      B.cl_count = 0;
+      B.cl_gen++;
+      g_idle = 0;
+      return;
+   }
+   g_wait [B.cur] = 2;
+   while (B.cl_gen == gen)
+      switch_to_next ();
+   g_wait [B.cur] = 0;
+}
+
+unsigned emu_cluster_rank (void) { return (unsigned) cur_rank (); }
+unsigned emu_cluster_size (void) { return (unsigned) B.ctas; }
+
+/* mapa: the same shared-memory offset in the block of another rank */
+void *
+emu_map_shared_rank (const void *p, unsigned rank)
+{
+   const size_t off = (size_t) ((const unsigned char *) p - (g_smem + (size_t) cur_rank () * SMEM_BYTES));
+
+   if (off >= SMEM_BYTES || rank >= (unsigned) B.ctas)
+   {
+      fprintf (stderr, "emu: map_shared_rank of an address outside dynamic shared memory\n");
+      abort ();
+   }
+   return g_smem + (size_t) rank * SMEM_BYTES + off;
 }
 
 unsigned
@@ -143,21 +225,26 @@ emu_warp_exchange (unsigned value, int kind, int arg)
 {
    const unsigned tid  = threadIdx.x;
    const unsigned lane = tid & 31u;
-   Warp		 &w    = B.warps [tid >> 5];
+   Warp		 &w    = B.warps [(unsigned) B.cur >> 5];	/* per_cta is a multiple of 32 */
    const unsigned gen  = w.gen, buf = gen & 1u;
-   const unsigned lanes = (tid | 31u) < (unsigned) B.n ? 32u : (unsigned) B.n - (tid & ~31u);
+   const unsigned lanes = (tid | 31u) < (unsigned) B.per_cta ? 32u : (unsigned) B.per_cta - (tid & ~31u);
 
    w.slot [buf][lane] = value;
    if (++w.count == lanes)
    {
-      if ((tid >> 5) == 0)
+      if ((tid >> 5) == 0 && cur_rank () == 0)
 	 g_warp_ops++;		/* warp 0's collectives: the resolution loops run in every warp alike */
       w.count = 0;
       w.gen++;
+      g_idle = 0;
    }
    else
+   {
+      g_wait [B.cur] = 3;
       while (w.gen == gen)
 	 switch_to_next ();
+      g_wait [B.cur] = 0;
+   }
    switch (kind)
    {
       case 0:
@@ -179,7 +266,7 @@ emu_warp_exchange (unsigned value, int kind, int arg)
 unsigned char *
 emu_dyn_smem (void)
 {
-   return g_smem;
+   return g_smem + (size_t) cur_rank () * SMEM_BYTES;
 }
 
 long long
@@ -191,17 +278,19 @@ clock64 (void)
 }
 
 void
-emu_launch (emu_dim3 grid, emu_dim3 block, size_t smem, const std::function<void ()> &body)
+emu_launch_cluster (emu_dim3 grid, emu_dim3 block, unsigned cluster, size_t smem, const std::function<void ()> &body)
 {
-   const int n = (int) block.x;
+   const int per_cta = (int) block.x;
+   const int n	     = per_cta * (int) cluster;
 
    {
       const char *o = getenv ("FB200_EMU_ORDER");	/* read per launch: tests switch it */
       g_order = o ? atoi (o) : 0;
    }
-   if (!g_smem && posix_memalign ((void **) &g_smem, 256, 256 * 1024))
+   if (!g_smem && posix_memalign ((void **) &g_smem, 256, (size_t) MAX_CLUSTER * SMEM_BYTES))
       abort ();
-   if (smem > 256 * 1024 || block.y != 1 || block.z != 1)
+   if (smem > SMEM_BYTES || block.y != 1 || block.z != 1 || cluster < 1 || cluster > MAX_CLUSTER
+       || grid.x % cluster || (cluster > 1 && per_cta % 32))
    {
       fprintf (stderr, "emu: launch shape not supported\n");
       abort ();
@@ -216,30 +305,47 @@ emu_launch (emu_dim3 grid, emu_dim3 block, size_t smem, const std::function<void
    gridDim  = grid;
    blockDim = block;
    for (unsigned by = 0; by < grid.y; by++)
-      for (unsigned bx = 0; bx < grid.x; bx++)
+   for (unsigned bx = 0; bx < grid.x; bx += cluster)
+   {
+      for (unsigned r = 0; r < cluster; r++)
+	 memset (g_smem + (size_t) r * SMEM_BYTES, 0xcd, smem);	/* shared memory starts undefined */
+      B.n = B.alive = n;
+      B.per_cta	    = per_cta;
+      B.ctas	    = (int) cluster;
+      B.first_block = bx;
+      B.cl_count = B.cl_gen = 0;
+      for (unsigned r = 0; r < MAX_CLUSTER; r++)
       {
-	 blockIdx = emu_dim3 (bx, by, 0);
-	 memset (g_smem, 0xcd, smem);	/* shared memory starts undefined */
-	 B.n = B.alive = n;
-	 B.bar_count = B.bar_gen = 0;
-	 B.sp.assign ((size_t) n, NULL);
-	 B.done.assign ((size_t) n, 0);
-	 B.warps.assign ((size_t) (n + 31) / 32, Warp ());
-	 B.body = &body;
-	 for (int t = 0; t < n; t++)
-	 {
-	    /* initial frame: six callee-saved registers, the entry point, a dummy return slot;
-	       after the ret the stack pointer is 8 mod 16 as at any function entry */
-	    void **top = (void **) (g_stacks + (size_t) (t + 1) * STACK_BYTES);
-	    void **sp  = top - 8;
-	    for (int i = 0; i < 6; i++)
-	       sp [i] = NULL;
-	    sp [6] = (void *) fibre_main;
-	    sp [7] = NULL;
-	    B.sp [t] = sp;
-	 }
-	 B.cur	     = g_order == 1 ? n - 1 : 0;
-	 threadIdx.x = (unsigned) B.cur;
-	 emu_switch (&B.main_sp, B.sp [B.cur]);
+	 B.bar_count [r] = B.bar_gen [r] = 0;
+	 B.cta_alive [r] = per_cta;
       }
+      g_wait.assign ((size_t) n, 0);
+      g_idle = 0;
+      B.sp.assign ((size_t) n, NULL);
+      B.done.assign ((size_t) n, 0);
+      B.warps.assign ((size_t) (n + 31) / 32, Warp ());
+      B.body = &body;
+      for (int t = 0; t < n; t++)
+      {
+	 /* initial frame: six callee-saved registers, the entry point, a dummy return slot;
+	    after the ret the stack pointer is 8 mod 16 as at any function entry */
+	 void **top = (void **) (g_stacks + (size_t) (t + 1) * STACK_BYTES);
+	 void **sp  = top - 8;
+	 for (int i = 0; i < 6; i++)
+	    sp [i] = NULL;
+	 sp [6] = (void *) fibre_main;
+	 sp [7] = NULL;
+	 B.sp [t] = sp;
+      }
+      B.cur	  = g_order == 1 ? n - 1 : 0;
+      threadIdx.x = (unsigned) (B.cur % per_cta);
+      blockIdx	  = emu_dim3 (bx + (unsigned) (B.cur / per_cta), by, 0);
+      emu_switch (&B.main_sp, B.sp [B.cur]);
+   }
+}
+
+void
+emu_launch (emu_dim3 grid, emu_dim3 block, size_t smem, const std::function<void ()> &body)
+{
+   emu_launch_cluster (grid, block, 1, smem, body);
 }

@@ -66,7 +66,7 @@ def run_case(img, quality=20.0, optimize=0, label="", cap=0):
           % (label, w, h, quality, optimize, "OK" if ok else "MISMATCH", gw["states"], t1 - t0, st["kernel_ms"],
              st["h2d_ms"], st["d2h_ms"], st["mp_calls"], st["mp_steps"]), flush=True)
     names = ["ctrl", "pix", "dots", "upsweep", "enter", "mp_pro", "mp_p1", "mp_waves", "mp_commit", "mp_ortho", "ar_epi",
-             "ap_img", "ap_direct", "ap_staged", "decide"]
+             "ap_img", "ap_direct", "ap_staged", "decide", "cluster"]
     tot = float(sum(st["lap"])) or 1.0
     print("   laps: " + " ".join("%s=%.1f%%" % (n, 100 * v / tot) for n, v in zip(names, st["lap"])) +
           "  total %.1f Mcyc" % (tot / 1e6), flush=True)

@@ -6,6 +6,7 @@ set -u
 OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_event_reasons.active --format=csv > $OUT/r02a_smi.txt
+timeout 900 python -m pytest tests -m gpu -x -q > $OUT/r02a_pytest.txt 2>&1; tail -5 $OUT/r02a_pytest.txt
 # 1. one 1024^2 frame, lap shares per thread-block shape (diagnostics build)
 for nt in 512 256 128; do
   FB200_LIB=gpurun_exp/laps/libfiasco_b200.so FB200_NT=$nt timeout 300 python tools/gpu_check.py big \
