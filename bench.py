@@ -30,10 +30,18 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
+# one process per GPU: every rank sees only its own device (as device 0), so that the library's own
+# entry points -- fiasco_coder() included, which uses devices 0 .. FIASCO_GPUS - 1 -- run on it
+if "LOCAL_RANK" in os.environ and "reference" not in sys.argv[1:]:
+    _vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    _ids = _vis.split(",") if _vis else None
+    _lr = int(os.environ["LOCAL_RANK"])
+    os.environ["CUDA_VISIBLE_DEVICES"] = _ids[_lr] if _ids and _lr < len(_ids) else str(_lr)
+
 W_ = H_ = 1024
 QUALITY = 20.0
 LAP_NAMES = ["ctrl", "pix", "dots", "upsweep", "enter", "mp_pro", "mp_p1", "mp_waves", "mp_commit", "mp_ortho",
-             "ar_epi", "ap_img", "ap_direct", "ap_staged", "decide"]
+             "ar_epi", "ap_img", "ap_direct", "ap_staged", "decide", "cluster"]
 METRIC = "encoder Mpixels/s at fixed PSNR (1024^2 grey, q=20)"
 
 
@@ -182,32 +190,213 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------- our arm
 
+def md5_of(path):
+    import hashlib
+    return hashlib.md5(open(path, "rb").read()).hexdigest()
+
+
+def scratch_dir(need_bytes):
+    """A directory for the input frames 'on disk': tmpfs when it has the room (the metric excludes the
+    medium: SURVEY 8d 'image already on disk'), else the default temporary directory."""
+    import shutil
+    for d in ("/dev/shm", tempfile.gettempdir()):
+        try:
+            if shutil.disk_usage(d).free > 1.5 * need_bytes:
+                return tempfile.mkdtemp(prefix="fb200_bench_", dir=d)
+        except OSError:
+            pass
+    return tempfile.mkdtemp(prefix="fb200_bench_")
+
+
+def coder_call(inputs, out, quality, pattern=None, optimize=0, env=None):
+    """One fiasco_coder() call (the reference's public entry point, include/fiasco.h) with the CLI's
+    default options.  Returns (seconds, work counters of the call)."""
+    from fiasco_b200 import ffi, hostlib
+    L = hostlib.load()
+    o = hostlib.cli_options(optimize)
+    L.fiasco_c_options_set_progress_meter(o, 0)
+    if pattern:
+        L.fiasco_c_options_set_frame_pattern(o, pattern.encode())
+    saved = {k: os.environ.get(k) for k in (env or {})}
+    for k, v in (env or {}).items():
+        os.environ[k] = str(v)
+    ffi.counters(reset=True)
+    t0 = time.perf_counter()
+    try:
+        ok, msg = hostlib.coder(inputs, out, quality=quality, options=o)
+    finally:
+        dt = time.perf_counter() - t0
+        L.fiasco_c_options_delete(o)
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    if not ok:
+        raise RuntimeError("fiasco_coder: " + msg)
+    return dt, ffi.counters()
+
+
+def config_records(tmp):
+    """BASELINE.json configs 2 (tile-split form), 3, 4 and 5 through fiasco_coder(): files on disk ->
+    .fco files, the library's FIASCO_TILE_SPLIT mode, bytes compared with the reference
+    coder's (tests/golden/manifest.json: the reference binary run on the crops / the sequence)."""
+    import gen_frames
+    man = json.load(open(os.path.join(ROOT, "tests", "golden", "manifest.json")))
+    out = {}
+    for key, mkey, split in (("c2_tiles16", "tiles_g1024_256", 4), ("c3", "tiles_c2048_256", 6),
+                             ("c4", "tiles_g4096_512", 6)):
+        m = man[mkey]
+        img = gen_frames.frame(m["frame"])
+        pnm = os.path.join(tmp, key + (".pgm" if img.ndim == 2 else ".ppm"))
+        gen_frames.write_pnm(pnm, img)
+        dst = os.path.join(tmp, key + ".fco")
+        best, cnt = None, None
+        for _ in range(3):
+            dt, c = coder_call([pnm], dst, float(m["quality"]), env={"FIASCO_TILE_SPLIT": split, "FIASCO_GPUS": 1})
+            if best is None or dt < best:
+                best, cnt = dt, c
+        n = 1 << split
+        got = [md5_of(os.path.join(tmp, "%s.t%02d.fco" % (key, t))) for t in range(n)]
+        mpx = img.shape[0] * img.shape[1] / 1e6
+        out[key] = {"workload": "%s as %d streams of %dx%d, q=%g" % (m["frame"], n, m["tile"], m["tile"], m["quality"]),
+                    "mpixels_per_s": mpx / best, "seconds": best, "kernel_ms": cnt["kernel_ms"],
+                    "kernel_launches": cnt["launches"], "md5_matches_reference": got == m["fco_md5"],
+                    "through": "fiasco_coder(), FIASCO_TILE_SPLIT=%d, best of 3 calls (context creation included)" % split}
+    m = man["v720_q20_ippp"]
+    vd = os.path.join(tmp, "video")
+    os.makedirs(vd, exist_ok=True)
+    for i, f in enumerate(gen_frames.video(m["frames"], m["width"], m["height"])):
+        gen_frames.write_pnm(os.path.join(vd, "w%02d.pgm" % i), f)
+    dst = os.path.join(tmp, "c5.fco")
+    best, cnt = None, None
+    for _ in range(2):
+        dt, c = coder_call([os.path.join(vd, "w[00-%02d].pgm" % (m["frames"] - 1))], dst, float(m["quality"]),
+                           pattern=m["pattern"], env={"FIASCO_GPUS": 1})
+        if best is None or dt < best:
+            best, cnt = dt, c
+    mpx = m["frames"] * m["width"] * m["height"] / 1e6
+    out["c5"] = {"workload": "%d frames %dx%d, pattern %s, q=%g" % (m["frames"], m["width"], m["height"], m["pattern"],
+                                                                      m["quality"]),
+                 "mpixels_per_s": mpx / best, "seconds": best, "kernel_ms": cnt["kernel_ms"],
+                 "kernel_launches": cnt["launches"], "md5_matches_reference": md5_of(dst) == m["fco_md5"],
+                 "through": "fiasco_coder(), one process, one GPU, best of 2 calls"}
+    return out
+
+
+def strong_records(rank, world, dist, torch):
+    """Strong scaling: ONE job split over the ranks, the gather inside the timed region.  Config 4: the 64
+    tiles of the 4096^2 frame dealt to the ranks, every rank codes its tiles and writes their .fco bytes,
+    two all_gathers (sizes, padded payloads; NCCL) bring them to rank 0.  Config 5: the 8 groups of pictures
+    dealt to the ranks, the automata gathered the same way, rank 0 writes the stream."""
+    import gen_frames
+    import fiasco_b200 as F
+    from fiasco_b200 import ffi, hostlib, distributed as D, video as V
+    man = json.load(open(os.path.join(ROOT, "tests", "golden", "manifest.json")))
+    dev = "cuda" if world > 1 else "cpu"
+    rec = {}
+
+    def timed(fn, reps):
+        best = None
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            res = fn()
+            torch.cuda.synchronize()
+            t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if best is None or float(t[0]) < best[0]:
+                best = (float(t[0]), res)
+        return best
+
+    # ---- config 4
+    m = man["tiles_g4096_512"]
+    img = gen_frames.frame(m["frame"])
+    crops = gen_frames.crops(img, m["tile"])
+    mine = D.shard(len(crops), rank, world)
+    p = ffi.make_params(m["tile"], m["tile"], 1, float(m["quality"]), 0)
+    enc = F.TileEncoder(p, max(1, len(mine)), device=0)
+    planes = [ffi.pixels_from_grey(crops[i]).reshape(-1) for i in mine]
+    tmp = tempfile.mkdtemp(prefix="fb200_strong_")
+
+    def job4():
+        wfas, _ = enc.encode(planes)
+        streams = {}
+        for i, w in zip(mine, wfas):
+            path = os.path.join(tmp, "t%03d.fco" % i)
+            hostlib.write_stream(path, p, [w])
+            streams[i] = open(path, "rb").read()
+        return D.gather_streams(streams, len(crops), rank, world, device=dev), enc.stats()["kernel_ms"]
+
+    job4()
+    sec, (allb, kms) = timed(job4, 3)
+    enc.close()
+    if rank == 0:
+        import hashlib
+        ok = [hashlib.md5(b).hexdigest() for b in allb] == m["fco_md5"]
+        rec["c4"] = {"workload": "g4096 as 64 streams of 512x512 dealt to %d rank(s)" % world, "seconds": sec,
+                     "mpixels_per_s": img.shape[0] * img.shape[1] / 1e6 / sec, "kernel_ms_rank0": kms,
+                     "md5_matches_reference": ok, "collective": "2 x all_gather (sizes, padded .fco payloads), "
+                     + ("nccl" if world > 1 else "none (one rank)"), "timed": "planes on the host -> tile kernel -> "
+                     ".fco bytes of every tile on rank 0, max over ranks, best of 3"}
+    # ---- config 5
+    m = man["v720_q20_ippp"]
+    seq = [ffi.pixels_from_grey(f) for f in gen_frames.video(m["frames"], m["width"], m["height"])]
+    pv = ffi.make_params(m["width"], m["height"], 1, float(m["quality"]), 0)
+
+    def job5():
+        auto, ms = V.encode_sequence(seq, m["pattern"], pv, rank=rank, world=world, gather_device=dev)
+        if rank == 0:
+            path = os.path.join(tmp, "v.fco")
+            hostlib.write_video_stream(path, pv, auto)
+            return md5_of(path), ms
+        return None, ms
+
+    job5()
+    sec, (digest, kms) = timed(job5, 2)
+    if rank == 0:
+        rec["c5"] = {"workload": "30 frames 720x576 IPPP: 8 groups of pictures dealt to %d rank(s)" % world,
+                     "seconds": sec, "mpixels_per_s": m["frames"] * m["width"] * m["height"] / 1e6 / sec,
+                     "kernel_ms_rank0": kms, "md5_matches_reference": digest == m["fco_md5"],
+                     "collective": "2 x all_gather (sizes, packed automata), " + ("nccl" if world > 1 else "none (one rank)"),
+                     "timed": "planes on the host -> I launch + 3 P steps per rank -> automata gathered -> "
+                              "stream written by rank 0, max over ranks, best of 2"}
+    import shutil
+    shutil.rmtree(tmp, ignore_errors=True)
+    return rec
+
+
 def run_ours(args):
     import torch
     import fiasco_b200 as F
     from fiasco_b200 import ffi
+    import gen_frames
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", 0))
     if not torch.cuda.is_available() or F.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback)")
+    local = 0                                       # CUDA_VISIBLE_DEVICES holds this rank's GPU only
     torch.cuda.set_device(local)
     sms = torch.cuda.get_device_properties(local).multi_processor_count
     p = ffi.make_params(W_, H_, 1, QUALITY, 0)
     probe = F.TileEncoder(p, 1, device=local)
     resident = probe.resident_tiles() or sms         # SM count x resident thread blocks per SM
     probe.close()
-    # default: two waves of frames per launch -- the frames take different times, a second wave fills
+    # default: three waves of frames per launch -- the frames take different times, later waves fill
     # the SMs that finish early (the big tables exist once per RESIDENT frame, see ffi.cu)
     B = args.batch if args.batch else args.waves * resident
     imgs = frames(rank * B, B)
     planes = [ffi.pixels_from_grey(im).reshape(-1) for im in imgs]
-    # inputs of the e2e leg live in pinned host memory
+    # inputs of the C-ABI end-to-end leg live in pinned host memory
     pinned = torch.empty((B, W_ * H_), dtype=torch.int16).pin_memory()
     pinned.numpy()[:] = np.stack(planes)
     host_planes = [pinned.numpy()[i] for i in range(B)]
@@ -226,13 +415,19 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(*vals):
+        t = torch.tensor(list(vals), dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
     # ---- device-resident leg: inputs already in HBM, kernel only ----
     enc.upload(host_planes)
     l2_flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device="cuda")
     for _ in range(max(args.warmup, 3)):
         enc.launch(B, stream)
     barrier()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0])
     if rank == 0:
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -248,26 +443,59 @@ def run_ours(args):
     kernel_ms = [a.elapsed_time(b) for a, b in ev]
     clocks = sampler.stop() if rank == 0 else None
     step_ms = float(np.sum(kernel_ms))
-    wfas = enc.download(B)
+    enc.download(B)
     st = enc.stats()
 
-    # ---- end-to-end leg: host buffers -> C ABI -> automata on the host ----
-    for _ in range(1):
-        enc.encode(host_planes)
+    # ---- end to end through the C ABI: pinned host planes -> fb200_encode_tiles -> automata on the host ----
+    enc.encode(host_planes)
     barrier()
     t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 3))
     for _ in range(e2e_steps):
-        out, _ = enc.encode(host_planes)
+        enc.encode(host_planes)
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    abi_s = time.perf_counter() - t0
     st2 = enc.stats()
     enc.close()
+    del pinned, host_planes, l2_flush
+    torch.cuda.empty_cache()
 
-    t = torch.tensor([step_ms, e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    step_ms_max, e2e_max = float(t[0]), float(t[1])
+    # ---- end to end through the reference's own entry point: fiasco_coder() ----
+    # (ii) throughput: the B frames of this rank as PGM files on disk, one --pattern=i sequence -> one .fco
+    tmp = scratch_dir(B * (W_ * H_ + 64))
+    try:
+        for k, im in enumerate(imgs):
+            gen_frames.write_pnm(os.path.join(tmp, "f%04d.pgm" % k), im)
+        template = os.path.join(tmp, "f[0000-%04d].pgm" % (B - 1))
+        seq_out = os.path.join(tmp, "seq.fco")
+        coder_call([template], seq_out, QUALITY, pattern="i")          # warm-up (page cache, CUDA context)
+        barrier()
+        t0 = time.perf_counter()
+        seq_cnt = None
+        for _ in range(e2e_steps):
+            _, seq_cnt = coder_call([template], seq_out, QUALITY, pattern="i")
+        seq_s = time.perf_counter() - t0
+        seq_bytes = os.path.getsize(seq_out)
+        # (i) latency: one 1024^2 frame per call (what cfiasco does), context creation included
+        one = os.path.join(tmp, "f0000.pgm")
+        one_out = os.path.join(tmp, "one.fco")
+        coder_call([one], one_out, QUALITY)
+        lat_steps = 20
+        barrier()
+        lat, lat_kernel = [], []
+        for _ in range(lat_steps):
+            dt, c = coder_call([one], one_out, QUALITY)
+            lat.append(dt)
+            lat_kernel.append(c["kernel_ms"])
+        one_md5_ok = (md5_of(one_out) == json.load(open(os.path.join(ROOT, "tests", "golden", "manifest.json")))
+                      ["g1024_q20_z0"]["fco_md5"]) if rank == 0 else None
+        configs = config_records(tmp) if rank == 0 and world == 1 and not args.no_configs else None
+    finally:
+        import shutil
+        shutil.rmtree(tmp, ignore_errors=True)
+    strong = strong_records(rank, world, dist, torch) if not args.no_configs else None
+
+    step_ms_max, abi_max, seq_max = max_over_ranks(step_ms, abi_s, seq_s)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -275,7 +503,8 @@ def run_ours(args):
 
     mpx_step = world * B * W_ * H_ / 1e6
     value = mpx_step * args.steps / (step_ms_max / 1e3)
-    e2e_value = mpx_step * e2e_steps / e2e_max
+    abi_value = mpx_step * e2e_steps / abi_max
+    seq_value = mpx_step * e2e_steps / seq_max
     peak, peak_src = peaks()
     traffic, traffic_src = None, None
     tj = os.path.join(ROOT, "profiles", "traffic.json")
@@ -296,6 +525,7 @@ def run_ours(args):
     # CPU baseline: the reference (or the port) on ONE core, a bounded sample of the same workload
     cpu_s, kind = cpu_encode_frames(imgs[:2], 1)
     cpu_value = 2 * W_ * H_ / 1e6 / cpu_s
+    lat_ms = float(np.median(lat)) * 1e3
     line = {
         "metric": METRIC, "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": step_ms_max / args.steps, "higher_is_better": True,
@@ -307,9 +537,23 @@ def run_ours(args):
                    "frames_per_step_per_gpu": B, "timing": "CUDA events on the launch stream, L2 flushed "
                    "(192 MiB memset) between timed launches", "states_per_frame": st["states"] / B,
                    "wall_s_timed_region": wall},
-        "e2e": {"value": e2e_value, "unit": "Mpixels/s", "h2d_bytes_per_step": int(st2["h2d_bytes"]),
-                "d2h_bytes_per_step": int(st2["d2h_bytes"]), "steps": e2e_steps,
-                "note": "fb200_encode_tiles(): pinned host int16 planes -> H2D -> tile kernel -> D2H automata"},
+        "e2e": {"value": seq_value, "unit": "Mpixels/s", "h2d_bytes_per_step": int(seq_cnt["h2d_bytes"]),
+                "d2h_bytes_per_step": int(seq_cnt["d2h_bytes"]), "steps": e2e_steps,
+                "through": "fiasco_coder() (include/fiasco.h, the reference's public entry point): %d PGM files on disk "
+                           "(%s), frame pattern `i' -> one .fco file (%d bytes); PNM parsing, context creation, "
+                           "host-to-device copies, tile kernel, device-to-host copies and the stream writer all inside "
+                           "the timed region; wall clock, max over ranks" % (B, "tmpfs" if tmp.startswith("/dev/shm")
+                                                                             else "temporary directory", seq_bytes),
+                "kernel_ms_per_step": seq_cnt["kernel_ms"], "kernel_launches_per_step": seq_cnt["launches"]},
+        "e2e_latency": {"value": W_ * H_ / 1e6 / (lat_ms / 1e3), "unit": "Mpixels/s", "ms_per_frame": lat_ms,
+                        "kernel_ms_per_frame": float(np.median(lat_kernel)), "steps": lat_steps,
+                        "md5_matches_reference": one_md5_ok,
+                        "through": "fiasco_coder() on ONE 1024x1024 PGM per call (what cfiasco does): file -> .fco, "
+                                   "context creation included; the frame runs on a cluster of thread blocks; median"},
+        "e2e_abi": {"value": abi_value, "unit": "Mpixels/s", "h2d_bytes_per_step": int(st2["h2d_bytes"]),
+                    "d2h_bytes_per_step": int(st2["d2h_bytes"]), "steps": e2e_steps,
+                    "through": "fb200_encode_tiles() (include/fiasco_b200.h): pinned host int16 planes -> H2D -> tile "
+                               "kernel -> D2H automata"},
         "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "fiasco_tile_kernel",
@@ -325,6 +569,8 @@ def run_ours(args):
         "phase_cycles": {k: int(st[k]) for k in ("cyc_total", "cyc_T", "cyc_mp", "cyc_append")},
         "ip_phase": ip_phase,
         "work": {k: int(st[k]) for k in ("mp_calls", "mp_steps", "blocks", "states")},
+        "configs": configs,
+        "strong": strong,
     }
     if sum(st["lap"]):                            # only a -DFB200_LAPS diagnostics build fills the lap timers
         line["lap_share"] = {n: round(v / float(sum(st["lap"])), 4) for n, v in zip(LAP_NAMES, st["lap"])}
@@ -341,6 +587,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="frames per GPU per step (default: waves x resident frames)")
     ap.add_argument("--waves", type=int, default=3, help="frames per step in units of the resident frames per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config and strong-scaling sub-records")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

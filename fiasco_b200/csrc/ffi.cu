@@ -70,6 +70,40 @@ set_err (char *err, size_t errlen, const char *fmt, ...)
       }                                                                             \
    } while (0)
 
+/* process-wide work counters (fb200_counters_get): what the launches of this process have done
+   since the last reset, whichever entry point -- fiasco_coder() included -- made them */
+#include <mutex>
+static std::mutex	g_counters_lock;
+static fb200_counters_t g_counters;
+
+static void
+count_work (double kernel_ms, uint64_t launches, uint64_t h2d, uint64_t d2h)
+{
+   std::lock_guard<std::mutex> hold (g_counters_lock);
+
+   g_counters.kernel_ms += kernel_ms;
+   g_counters.launches	+= launches;
+   g_counters.h2d_bytes += h2d;
+   g_counters.d2h_bytes += d2h;
+}
+
+extern "C" void
+fb200_counters_get (fb200_counters_t *out)
+{
+   std::lock_guard<std::mutex> hold (g_counters_lock);
+
+   if (out)
+      *out = g_counters;
+}
+
+extern "C" void
+fb200_counters_reset (void)
+{
+   std::lock_guard<std::mutex> hold (g_counters_lock);
+
+   memset (&g_counters, 0, sizeof g_counters);
+}
+
 extern "C" const char *
 fb200_version (void)
 {
@@ -610,6 +644,7 @@ fb200_upload (fb200_ctx_t *c, int n_tiles, const int16_t *const *planes, char *e
    CUDA_TRY (cudaStreamSynchronize (c->stream));
    cudaEventElapsedTime (&c->stats.h2d_ms, c->ev [0], c->ev [1]);
    c->stats.h2d_bytes = c->pix_elems * 2 * n_tiles;
+   count_work (0, 0, c->stats.h2d_bytes, 0);
    return FB200_OK;
 }
 
@@ -679,6 +714,7 @@ fb200_download (fb200_ctx_t *c, int n_tiles, fb200_wfa_t *out, fb200_trace_rec_t
    cudaEventElapsedTime (&c->stats.kernel_ms, c->ev [2], c->ev [3]);
    cudaEventElapsedTime (&c->stats.d2h_ms, c->ev [4], c->ev [5]);
    c->stats.d2h_bytes = (sizeof (TileResult) + c->wfa_block) * n_tiles;
+   count_work (c->stats.kernel_ms, 1, 0, c->stats.d2h_bytes);
 
    size_t aoff [15];
    wfa_layout (c->dp, aoff);
@@ -863,7 +899,8 @@ fb200_encode_predicted (fb200_ctx_t *c, int n_tiles, const int16_t *const *plane
 				    cudaMemcpyHostToDevice, c->stream));
    }
    CUDA_TRY (cudaStreamSynchronize (c->stream));
-   c->stats.h2d_bytes += c->pix_elems * 2 * n_tiles;
+   c->stats.h2d_bytes += c->pix_elems * 2 * n_tiles * (c->dp.motion == 2 ? 2 : 1);
+   count_work (0, 0, c->pix_elems * 2 * n_tiles * (c->dp.motion == 2 ? 2 : 1), 0);
    float total_ms = 0;
    int	 launches = 0;
    for (;;)

@@ -724,10 +724,23 @@ cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
       if (ns >= 32)
       {
 	 /* a warp covers 32 consecutive states and walks the nodes together: pixel
-	    reads are shared-memory broadcasts, product writes are coalesced */
-	 for (unsigned s = from + tid; s < S; s += gnt)
+	    reads are shared-memory broadcasts, product writes are coalesced.  With the
+	    threads of a whole cluster at hand the nodes of a state are split up as well, so
+	    that every thread has an item */
+	 const unsigned ns32 = (ns + 31) & ~31u;
+	 unsigned	split = 1;
+
+	 if (cl)
+	    while (split < nn && ns32 * split < gnt)
+	       split <<= 1;
+	 const unsigned per = nn / split;
+
+	 for (unsigned item = tid; item < ns32 * split; item += gnt)
 	 {
-	    if (!GP (W.domain_type) [s])
+	    const unsigned s  = from + item % ns32;
+	    const unsigned k0 = (item / ns32) * per;
+
+	    if (s >= S || !GP (W.domain_type) [s])
 	       continue;
 	    const float *im = GP (W.img) + (size_t) s * FB_IMG_STRIDE + (len - 1);
 	    if (l == 5)
@@ -747,7 +760,7 @@ cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
 		  r [4 * q + 3] = v.z;
 		  prev		= v.w;
 	       }
-	       for (unsigned k = 0; k < nn; k++)
+	       for (unsigned k = k0; k < k0 + per; k++)
 	       {
 		  const float4 *px = (const float4 *) (sh.pixels + (size_t) (adr0 + k) * 32);
 		  float		ip = 0;
@@ -765,7 +778,7 @@ cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
 	    }
 	    else
 	    {
-	       for (unsigned k = 0; k < nn; k++)
+	       for (unsigned k = k0; k < k0 + per; k++)
 	       {
 		  const float *px = sh.pixels + (size_t) (adr0 + k) * len;
 		  float	       ip = 0;
@@ -851,22 +864,19 @@ cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
 	    if (!GP (W.domain_type) [s])
 	       continue;
 	    TransReg tr;
-	    float    acc = 0;
 
 	    load_trans (GP (W.trans) + s, tr);
+	    /* (unconditional, independent gathers as above: one L2 round trip per item) */
+	    int idx [2][FB_MAXEDGES + 1];
 #pragma unroll
 	    for (int label = 0; label < 2; label++)
 	    {
-	       const float *src = GP (W.T) + (size_t) (2 * node + 1 + label) * scap;
-
-	       if (tr.child [label] != FB_RANGE)
-		  acc += src [tr.child [label]];
+	       idx [label][0] = tr.child [label] != FB_RANGE ? tr.child [label] : 0;
 #pragma unroll
 	       for (int e = 0; e < FB_MAXEDGES; e++)
-		  if (tr.into [label][e] != FB_NO_EDGE)
-		     acc += src [tr.into [label][e]] * tr.w [label][e];
+		  idx [label][e + 1] = tr.into [label][e] != FB_NO_EDGE ? tr.into [label][e] : 0;
 	    }
-	    GP (W.T) [(size_t) node * scap + s] = acc;
+	    upsweep_nodes<1> (GP (W.T), scap, node, s, tr, idx);
 	 }
       }
       if (cl)
@@ -2754,11 +2764,21 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 	    const int level = F.level;
 	    short    *snap  = (sh.snaps ? sh.snaps : GP (W.snap)) + (size_t) depth * SN * P.blob_len;
 	    unsigned *tsnap = sh.tsnap + (size_t) depth * TS * 2 * FB200_MAXLEVEL;
+	    /*
+	     *  A range of the lowest level cannot be subdivided: its linear combination is the
+	     *  result or the range fails.  An accepted approximation leaves the models it has
+	     *  updated, a rejected one leaves them untouched (approx.c:219-252), and nothing else
+	     *  has changed -- exactly what restoring / adopting the snapshots of
+	     *  subdivide.c:409-467 amounts to -- so no snapshot is taken and the range returns
+	     *  from here.  (Predicted frames keep the general path: a third alternative follows.)
+	     */
+	    const bool leaf = !MOTION && level <= h->lc_min && level <= P.lc_max;
 
 	    /* snapshot of the models (subdivide.c:188-194); tree_counts and tree_total are
 	       adjacent in the header */
-	    cta_copy_s16<NT> (snap, sh.blob, P.blob_len);
-	    if (tid < 32)
+	    if (!leaf)
+	       cta_copy_s16<NT> (snap, sh.blob, P.blob_len);
+	    if (!leaf && tid < 32)
 	    {
 	       const unsigned *tm = (const unsigned *) ((const char *) h + offsetof (ShHdr, tree_counts));
 
@@ -2796,22 +2816,29 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 	       }
 	       F.states_snap = h->states;
 	       /* y states of the children (subdivide.c:172-183) */
-	       for (int label = 0; label < 2; label++)
-		  F.new_y_state [label] = (band != 0 && F.y_state != FB_RANGE)
-					  ? (int) GP (W.tree) [2 * F.y_state + label] : FB_RANGE;
+	       if (!leaf)
+		  for (int label = 0; label < 2; label++)
+		     F.new_y_state [label] = (band != 0 && F.y_state != FB_RANGE)
+					     ? (int) GP (W.tree) [2 * F.y_state + label] : FB_RANGE;
 	       F.lincomb_costs = FB_MAXCOSTS;
 	       if (level <= P.lc_max)
 	       {
-		  F.lrange.tree		= FB_RANGE;
-		  F.lrange.x		= (unsigned short) F.x;
-		  F.lrange.y		= (unsigned short) F.y;
-		  F.lrange.tree_bits	= t0_tree_bits (h, 0, level);
-		  F.lrange.matrix_bits	= 0;
-		  F.lrange.weights_bits = 0;
-		  F.lrange.err		= 0;
-		  F.lrange.into [0]	= FB_NO_EDGE;
+		  RangeRes &lr = leaf ? *res : F.lrange;	/* a leaf fills its result slot directly */
+
+		  lr.tree	  = FB_RANGE;
+		  lr.x		  = (unsigned short) F.x;
+		  lr.y		  = (unsigned short) F.y;
+		  lr.tree_bits	  = t0_tree_bits (h, 0, level);
+		  lr.matrix_bits  = 0;
+		  lr.weights_bits = 0;
+		  lr.err	  = 0;
+		  lr.into [0]	  = FB_NO_EDGE;
 	       }
 	    }
+	    else if (tid == 32 && !leaf && level > h->lc_min)
+	       /* bits of the "subdivided" symbol (subdivide.c:243-248), next to thread 0's: the tree
+		  model does not change before they are used */
+	       F.r_tree_bits = t0_tree_bits (h, 1, level);
 	    __syncthreads ();
 	    /* clear_norms_table (prediction.c:195-211) */
 	    if (MOTION && h->fx [depth].try_mc && level > P.p_min)
@@ -2853,17 +2880,18 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 			h->job.states = h->states;
 			h->job.pool_n = BLOB_U16 (sh, MB_N);
 			h->job.price  = h->price;
-			for (int k = 0; k < n; k++)
-			{
-			   SpineNode &nd = h->job.node [k];
+			h->spec_len   = n;
+		     }
+		     if (tid < n)	/* one thread per node: the log2 of the tree bits side by side */
+		     {
+			const int  k  = tid;
+			SpineNode &nd = h->job.node [k];
 
-			   nd.level	= level - k;
-			   nd.image	= ((F.image + 1) << k) - 1;
-			   nd.address	= F.address << k;
-			   nd.tree_bits = k ? t0_tree_bits (h, 0, level - k) : F.lrange.tree_bits;
-			   nd.norm	= t0_node_norm (P, cs, nd.image, nd.address, nd.level);
-			}
-			h->spec_len = n;
+			nd.level     = level - k;
+			nd.image     = ((F.image + 1) << k) - 1;
+			nd.address   = F.address << k;
+			nd.tree_bits = k ? t0_tree_bits (h, 0, level - k) : F.lrange.tree_bits;
+			nd.norm	     = t0_node_norm (P, cs, nd.image, nd.address, nd.level);
 		     }
 		     cta_cluster_post<NT> (P, sh, true);
 		     if (tid == 0)
@@ -2875,7 +2903,7 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 		  }
 	       }
 	       cta_approximate_range<NT> (P, W, cs, F.max_costs, h->price, F.y_state,
-					  &F.lrange, level, F.image, F.address, F.x, F.y,
+					  leaf ? res : &F.lrange, level, F.image, F.address, F.x, F.y,
 					  MOTION ? h->fx [depth].lrange.mv_tree_bits : 0.0f,
 					  sk > 0 ? sk : 0);
 	       if (spine)
@@ -2888,6 +2916,13 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 		  F.lincomb_costs = h->ret_costs;
 		  h->cyc_mp += clock64 () - t0c;
 	       }
+	    }
+	    if (leaf)
+	    {
+	       /* the result slot holds the range (or nothing), ret_costs its costs (or MAXCOSTS) */
+	       if (tid == 0)
+		  nstate = ST_RETURN;
+	       break;
 	    }
 	    /* keep the "lc" models, restore the snapshot (subdivide.c:226-237); element i
 	       is handled by one thread for both copies */
@@ -2903,8 +2938,7 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 	    {
 	       if (level > h->lc_min)
 	       {
-		  /* alternative 2: recursive subdivision (subdivide.c:243-272) */
-		  F.r_tree_bits	   = t0_tree_bits (h, 1, level);
+		  /* alternative 2: recursive subdivision (subdivide.c:243-272); r_tree_bits: thread 32 */
 		  F.r_matrix_bits  = 0;
 		  F.r_weights_bits = 0;
 		  F.r_err	   = 0;
@@ -3842,6 +3876,22 @@ upload_tables (void)
    return cudaSuccess;
 }
 
+/* the 512-thread shape has an SM to itself: Gram-Schmidt rows and model snapshots on chip
+   whenever they fit (the batch shape keeps them in global memory to fit four blocks per SM) */
+static void
+shape_params (DevParams &p, int nt)
+{
+   if (nt >= 512 && p.big && !getenv ("FB200_BIG"))
+   {
+      DevParams q = p;
+      size_t	off [20];
+
+      q.big = 0;
+      if (smem_layout (q, nt, off) <= 200 * 1024)
+	 p.big = 0;
+   }
+}
+
 template <int NT, bool MOTION>
 static cudaError_t
 launch_nt (const DevParams &p_in, const TileWs *d_ws, int n_tiles, cudaStream_t stream, int cluster = 1)
@@ -3849,6 +3899,8 @@ launch_nt (const DevParams &p_in, const TileWs *d_ws, int n_tiles, cudaStream_t 
    const auto kernel = fiasco_tile_kernel<NT, MOTION>;
    DevParams	p = p_in;
    size_t off [20];
+
+   shape_params (p, NT);
    const size_t smem = smem_layout (p, NT, off);
 
    for (int i = 0; i < 20; i++)
@@ -3944,6 +3996,7 @@ fb_tile_kernel_cluster (const DevParams &p, int n_tiles)
       DevParams		  q = p;
       size_t		  off [20];
 
+      shape_params (q, 512);
       cfg.gridDim	   = dim3 ((unsigned) (n_tiles * c));
       cfg.blockDim	   = dim3 (512);
       cfg.dynamicSmemBytes = smem_layout (q, 512, off);

@@ -72,6 +72,11 @@ class Stats(C.Structure):
     ]
 
 
+class Counters(C.Structure):
+    _fields_ = [("kernel_ms", C.c_double), ("launches", C.c_uint64), ("h2d_bytes", C.c_uint64),
+                ("d2h_bytes", C.c_uint64)]
+
+
 def lib_path():
     if os.environ.get("FB200_LIB"):         # experiment builds (make laps): never the default
         return os.path.abspath(os.environ["FB200_LIB"])
@@ -112,8 +117,23 @@ def load():
     if hasattr(lib, "fb200_motion_norms"):
         lib.fb200_motion_norms.argtypes = [ip, vp, vp, ip, ip, ip, ip, vp, C.POINTER(C.c_float), cp, C.c_size_t]
     lib.fb200_probe.argtypes = [ip, ip, vp, vp, vp, vp, vp, vp, cp, C.c_size_t]
+    if hasattr(lib, "fb200_counters_get"):
+        lib.fb200_counters_get.argtypes = [C.POINTER(Counters)]
+        lib.fb200_counters_get.restype = None
+        lib.fb200_counters_reset.restype = None
     _LIB = lib
     return lib
+
+
+def counters(reset=False):
+    """Process-wide work counters of the library (whoever launched: TileEncoder or fiasco_coder())."""
+    c = Counters()
+    lib = load()
+    lib.fb200_counters_get(C.byref(c))
+    if reset:
+        lib.fb200_counters_reset()
+    return {"kernel_ms": c.kernel_ms, "launches": int(c.launches), "h2d_bytes": int(c.h2d_bytes),
+            "d2h_bytes": int(c.d2h_bytes)}
 
 
 def device_count():

@@ -29,6 +29,56 @@ fi_bits_open (const char *filename)
    return b;
 }
 
+/* a stream that is not tied to a file: frames are coded side by side into streams of their own
+   and appended to the output in coding order (fi_bits_append) */
+fi_bits_t *
+fi_bits_open_mem (void)
+{
+   fi_bits_t *b = fiasco_calloc (1, sizeof (fi_bits_t));
+
+   b->file = NULL;
+   b->cap  = 1 << 14;
+   b->buf  = fiasco_calloc (b->cap, 1);
+   return b;
+}
+
+void
+fi_bits_free_mem (fi_bits_t *b)
+{
+   if (b)
+   {
+      free (b->buf);
+      free (b);
+   }
+}
+
+void
+fi_bits_append (fi_bits_t *dst, const fi_bits_t *src)
+{
+   if ((dst->nbits & 7) == 0)
+   {
+      const size_t at = dst->nbits >> 3, bytes = (src->nbits + 7) >> 3;
+
+      if (at + bytes + 1 > dst->cap)
+      {
+	 size_t cap = dst->cap;
+
+	 while (at + bytes + 1 > cap)
+	    cap *= 2;
+	 dst->buf = realloc (dst->buf, cap);
+	 if (!dst->buf)
+	    fi_error ("Out of memory!");
+	 memset (dst->buf + dst->cap, 0, cap - dst->cap);
+	 dst->cap = cap;
+      }
+      memcpy (dst->buf + at, src->buf, bytes);
+      dst->nbits += src->nbits;
+   }
+   else
+      for (size_t i = 0; i < src->nbits; i++)
+	 fi_put_bit (dst, (src->buf [i >> 3] >> (7 - (i & 7))) & 1u);
+}
+
 void
 fi_put_bit (fi_bits_t *b, unsigned value)
 {

@@ -464,6 +464,8 @@ static struct
    unsigned	       n_gpus;
    unit_t	     **wave_u, **wave_past, **wave_future;
    char		      *tile_name;
+   fi_bits_t	     **frame_bits;	/* the frames' own bit streams until they are joined */
+   size_t	       n_frame_bits;
 } job;
 
 static void
@@ -480,7 +482,7 @@ job_release (void)
       free (job.units [i].delta);
    }
    free (job.units);
-   for (size_t i = 0; i < job.n_crops; i++)
+   for (size_t i = 0; job.crops && i < job.n_crops; i++)
       free (job.crops [i]);
    free (job.crops);
    for (unsigned i = 0; i < job.n_images; i++)
@@ -493,6 +495,9 @@ job_release (void)
       fi_bits_close (job.output);
    if (job.default_options)
       fiasco_c_options_delete (job.default_options);
+   for (size_t i = 0; i < job.n_frame_bits; i++)
+      fi_bits_free_mem (job.frame_bits [i]);
+   free (job.frame_bits);
    free (job.wave_u);
    free (job.wave_past);
    free (job.wave_future);
@@ -577,6 +582,93 @@ env_unsigned (const char *name, unsigned dflt, unsigned max)
    if (*end || v < 0 || v > (long) max)
       fi_error ("Environment variable %s=`%s': a number in 0..%u is expected.", name, e, max);
    return (unsigned) v;
+}
+
+/* frame n of the job: read it, cut it into the streams' pictures (host threads, side by side) */
+typedef struct read_ctx
+{
+   unsigned split, streams, frames, bands, cols, tw, th, width;
+} read_ctx_t;
+
+static void
+read_frame (size_t n, void *ctx)
+{
+   const read_ctx_t *r = ctx;
+
+   job.images [n] = fi_read_image (job.names.v [n]);
+   for (unsigned s = 0; s < r->streams; s++)
+   {
+      unit_t *u = &job.units [(size_t) s * r->frames + n];
+
+      if (fb200_wfa_alloc (&u->wfa, FI_MAXSTATES))
+	 fi_error ("Out of memory!");
+      for (unsigned b = 0; b < r->bands; b++)
+	 if (!r->split)
+	    u->plane [b] = job.images [n]->pixels [b];
+	 else
+	 {
+	    const unsigned x0 = (s % r->cols) * r->tw, y0 = (s / r->cols) * r->th;
+	    int16_t	  *c  = fiasco_calloc ((size_t) r->tw * r->th, sizeof (int16_t));
+
+	    job.crops [((size_t) n * r->streams + s) * r->bands + b] = c;
+	    for (unsigned y = 0; y < r->th; y++)
+	       memcpy (c + (size_t) y * r->tw,
+		       job.images [n]->pixels [b] + (size_t) (y0 + y) * r->width + x0,
+		       (size_t) r->tw * sizeof (int16_t));
+	    u->plane [b] = c;
+	 }
+   }
+   if (r->split)		/* the tiles hold their own copies */
+   {
+      fi_free_image (job.images [n]);
+      job.images [n] = NULL;
+   }
+}
+
+/* frame 'coded' (in coding order) of stream s as a bit stream of its own (host threads) */
+typedef struct write_ctx
+{
+   unsigned	       frames, bands;
+   const fi_wfainfo_t *wi;
+   const c_options_t  *cop;
+   fi_bits_t	     **out;	/* [streams * frames] */
+} write_ctx_t;
+
+static void
+write_frame (size_t i, void *ctx)
+{
+   const write_ctx_t *wc    = ctx;
+   const unsigned     s	    = (unsigned) (i / wc->frames), coded = (unsigned) (i % wc->frames);
+   const unsigned     n	    = (unsigned) job.sched.order [coded];
+   unit_t	     *u	    = &job.units [(size_t) s * wc->frames + n];
+   fi_wfa_t	      w;
+
+   memset (&w, 0, sizeof w);	/* intra frame: no motion data */
+   if (job.sched.ctype [n])
+   {
+      w.frame_type  = job.sched.ctype [n];
+      w.mv_bx	    = (const int8_t (*)[2]) u->wfa.mv_bx;
+      w.mv_by	    = (const int8_t (*)[2]) u->wfa.mv_by;
+      w.x	    = (const uint16_t (*)[2]) u->wfa.x;
+      w.y	    = (const uint16_t (*)[2]) u->wfa.y;
+      w.mv_type	    = (const int8_t (*)[2]) u->wfa.mv_type;
+      w.mv_fx	    = (const int8_t (*)[2]) u->wfa.mv_fx;
+      w.mv_fy	    = (const int8_t (*)[2]) u->wfa.mv_fy;
+      w.delta_state = u->delta;
+   }
+   w.info	    = wc->wi;
+   w.states	    = u->wfa.states;
+   w.basis_states   = u->wfa.basis_states;
+   w.root_state	    = u->wfa.root_state;
+   w.level_of_state = u->wfa.level_of_state;
+   w.domain_type    = u->wfa.domain_type;
+   w.tree	    = (const int16_t (*)[2]) u->wfa.tree;
+   w.into	    = (const int16_t (*)[2][6]) u->wfa.into;
+   w.weight	    = (const float (*)[2][6]) u->wfa.weight;
+   w.y_state	    = (const int16_t (*)[2]) u->wfa.y_state;
+   w.y_column	    = (const uint8_t (*)[2]) u->wfa.y_column;
+   wc->out [i]	    = fi_bits_open_mem ();
+   fi_write_next_wfa (&w, n, coded == 0, wc->cop->normal_domains, wc->cop->delta_domains, wc->out [i]);
 }
 
 static int
@@ -789,36 +881,20 @@ coder (char const *const *inputname, const char *outputname, float quality,
    job.n_units	= (size_t) streams * frames;
    if (split)
       job.crops = fiasco_calloc ((size_t) streams * frames * bands, sizeof (int16_t *));
-   for (n = 0; n < frames; n++)
    {
-      job.images [n] = fi_read_image (job.names.v [n]);
-      for (unsigned s = 0; s < streams; s++)
-      {
-	 unit_t *u = &job.units [(size_t) s * frames + n];
+      read_ctx_t rc = {split, streams, frames, bands, cols, tw, th, width};
+      int	 serial = 0;
 
-	 if (fb200_wfa_alloc (&u->wfa, FI_MAXSTATES))
-	    fi_error ("Out of memory!");
-	 for (unsigned b = 0; b < bands; b++)
-	    if (!split)
-	       u->plane [b] = job.images [n]->pixels [b];
-	    else
-	    {
-	       const unsigned x0 = (s % cols) * tw, y0 = (s / cols) * th;
-	       int16_t	     *c	 = fiasco_calloc ((size_t) tw * th, sizeof (int16_t));
-
-	       job.crops [job.n_crops++] = c;
-	       for (unsigned y = 0; y < th; y++)
-		  memcpy (c + (size_t) y * tw,
-			  job.images [n]->pixels [b] + (size_t) (y0 + y) * width + x0,
-			  (size_t) tw * sizeof (int16_t));
-	       u->plane [b] = c;
-	    }
-      }
-      if (split)		/* the tiles hold their own copies */
-      {
-	 fi_free_image (job.images [n]);
-	 job.images [n] = NULL;
-      }
+      if (split)
+	 job.n_crops = (size_t) streams * frames * bands;
+      for (n = 0; n < frames; n++)		/* standard input is read in order */
+	 if (!job.names.v [n] || strcmp (job.names.v [n], "-") == 0)
+	    serial = 1;
+      if (serial)
+	 for (n = 0; n < frames; n++)
+	    read_frame (n, &rc);
+      else if (fi_parallel_for (frames, read_frame, &rc))
+	 fi_rethrow ();
    }
    for (n = 0; n < frames; n++)
       for (unsigned s = 0; s < streams; s++)
@@ -895,7 +971,17 @@ coder (char const *const *inputname, const char *outputname, float quality,
 	    job.gpus [g].ctx [t] = NULL;
 	 }
 
-   /* the streams: frames in coding order */
+   /* the streams: every frame is coded into a bit stream of its own on the host threads, then
+      the frames of a stream are joined in coding order */
+   fi_write_tables_init ();
+   job.frame_bits   = fiasco_calloc ((size_t) streams * frames, sizeof (fi_bits_t *));
+   job.n_frame_bits = (size_t) streams * frames;
+   {
+      write_ctx_t wc = {frames, bands, &wi, cop, job.frame_bits};
+
+      if (fi_parallel_for ((size_t) streams * frames, write_frame, &wc))
+	 fi_rethrow ();
+   }
    for (unsigned s = 0; s < streams; s++)
    {
       if (split)
@@ -907,42 +993,18 @@ coder (char const *const *inputname, const char *outputname, float quality,
       }
       for (unsigned coded = 0; coded < frames; coded++)
       {
-	 unit_t	 *u;
-	 fi_wfa_t w;
+	 unit_t *u;
 
 	 n = job.sched.order [coded];
 	 u = &job.units [(size_t) s * frames + n];
-	 memset (&w, 0, sizeof w);	/* intra frame: no motion data */
-	 if (job.sched.ctype [n])
-	 {
-	    w.frame_type  = job.sched.ctype [n];
-	    w.mv_bx	  = (const int8_t (*)[2]) u->wfa.mv_bx;
-	    w.mv_by	  = (const int8_t (*)[2]) u->wfa.mv_by;
-	    w.x		  = (const uint16_t (*)[2]) u->wfa.x;
-	    w.y		  = (const uint16_t (*)[2]) u->wfa.y;
-	    w.mv_type	  = (const int8_t (*)[2]) u->wfa.mv_type;
-	    w.mv_fx	  = (const int8_t (*)[2]) u->wfa.mv_fx;
-	    w.mv_fy	  = (const int8_t (*)[2]) u->wfa.mv_fy;
-	    w.delta_state = u->delta;
-	 }
-	 w.info		  = &wi;
-	 w.states	  = u->wfa.states;
-	 w.basis_states	  = u->wfa.basis_states;
-	 w.root_state	  = u->wfa.root_state;
-	 w.level_of_state = u->wfa.level_of_state;
-	 w.domain_type	  = u->wfa.domain_type;
-	 w.tree		  = (const int16_t (*)[2]) u->wfa.tree;
-	 w.into		  = (const int16_t (*)[2][6]) u->wfa.into;
-	 w.weight	  = (const float (*)[2][6]) u->wfa.weight;
-	 w.y_state	  = (const int16_t (*)[2]) u->wfa.y_state;
-	 w.y_column	  = (const uint8_t (*)[2]) u->wfa.y_column;
 	 for (unsigned b = 0; b < bands; b++)
 	    draw_progress (cop->progress_meter, &u->wfa, b);
-	 fi_debug_message ("WFA contains %d states (%d basis states).", w.states,
-			   w.basis_states);
+	 fi_debug_message ("WFA contains %d states (%d basis states).", u->wfa.states,
+			   u->wfa.basis_states);
 	 fi_debug_message ("Total costs : %.2f", (double) u->wfa.costs [0]);
-	 fi_write_next_wfa (&w, n, coded == 0, cop->normal_domains, cop->delta_domains,
-			    job.output);
+	 fi_bits_append (job.output, job.frame_bits [(size_t) s * frames + coded]);
+	 fi_bits_free_mem (job.frame_bits [(size_t) s * frames + coded]);
+	 job.frame_bits [(size_t) s * frames + coded] = NULL;
       }
       fi_bits_close (job.output);
       job.output = NULL;

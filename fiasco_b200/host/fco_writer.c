@@ -687,6 +687,14 @@ write_mc (const fi_wfa_t *wfa, fi_bits_t *out)
 
 /* ------------------------------------------------------------------ frame ---- */
 
+/* the writer's static tables, before host threads share them */
+void
+fi_write_tables_init (void)
+{
+   if (!prob_table [0])
+      init_prob_table ();
+}
+
 void
 fi_write_next_wfa (const fi_wfa_t *wfa, unsigned frame_number, int first,
 		   int normal_domains, int delta_domains, fi_bits_t *out)

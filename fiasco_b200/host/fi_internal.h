@@ -29,6 +29,7 @@ extern __thread jmp_buf fi_env;
 #define fi_catch else
 void fi_set_error (const char *format, ...);
 void fi_error (const char *format, ...);		/* set text, longjmp */
+void fi_rethrow (void);				/* longjmp, the stored text stays */
 void fi_file_error (const char *filename);
 void fi_warning (const char *format, ...);
 void fi_message (const char *format, ...);
@@ -41,6 +42,9 @@ typedef enum {READ_ACCESS, WRITE_ACCESS} openmode_e;
 void *fiasco_calloc (size_t n, size_t size);
 void  fiasco_free (void *ptr);
 FILE *open_file (const char *filename, const char *env_var, openmode_e mode);
+/* fn (i, ctx) for i in 0..n-1 on up to FIASCO_HOST_THREADS host threads (default: the cores of the
+   process, at most 16); returns 0, or 1 if a call failed through fi_error (the message is kept) */
+int   fi_parallel_for (size_t n, void (*fn) (size_t i, void *ctx), void *ctx);
 
 /* ---- options (codec/options.h:20-65) ---- */
 typedef struct c_options
@@ -109,6 +113,9 @@ typedef struct fi_bits
 } fi_bits_t;
 
 fi_bits_t *fi_bits_open (const char *filename);
+fi_bits_t *fi_bits_open_mem (void);
+void	   fi_bits_free_mem (fi_bits_t *b);
+void	   fi_bits_append (fi_bits_t *dst, const fi_bits_t *src);
 void	   fi_bits_close (fi_bits_t *b);
 void	   fi_put_bit (fi_bits_t *b, unsigned value);
 void	   fi_put_bits (fi_bits_t *b, unsigned value, unsigned bits);
@@ -161,6 +168,7 @@ typedef struct fi_wfa
 } fi_wfa_t;
 
 void fi_write_header (const fi_wfainfo_t *wi, fi_bits_t *out);
+void fi_write_tables_init (void);
 void fi_write_next_wfa (const fi_wfa_t *wfa, unsigned frame_number, int first,
 			int normal_domains, int delta_domains, fi_bits_t *out);
 

@@ -3,6 +3,9 @@
  *  (SURVEY.md 8b): fiasco_calloc (lib/misc.c:51) and open_file (lib/bit-io.c:48), plus
  *  fiasco_free.
  */
+#define _GNU_SOURCE
+#include <pthread.h>
+#include <sched.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -79,4 +82,90 @@ open_file (const char *filename, const char *env_var, openmode_e mode)
       fp = try_dir (FIASCO_SHARE, filename, fmode);
    free (dirs);
    return fp;
+}
+
+/*****************************************************************************
+		host threads for the per-frame work around the launches
+*****************************************************************************/
+
+typedef struct pfor
+{
+   size_t	   n;
+   volatile size_t next;
+   volatile int	   failed;
+   char		   err [2048];	/* message of the first call that failed */
+   void		 (*fn) (size_t, void *);
+   void		  *ctx;
+   pthread_mutex_t lock;
+} pfor_t;
+
+static void *
+pfor_worker (void *arg)
+{
+   pfor_t *p = arg;
+
+   for (;;)
+   {
+      size_t i;
+
+      pthread_mutex_lock (&p->lock);
+      i = p->next++;
+      pthread_mutex_unlock (&p->lock);
+      if (i >= p->n || p->failed)
+	 return NULL;
+      /* fi_error () jumps to the thread's own fi_env */
+      fi_try
+      {
+	 p->fn (i, p->ctx);
+      }
+      fi_catch
+      {
+	 pthread_mutex_lock (&p->lock);
+	 if (!p->failed)
+	    snprintf (p->err, sizeof p->err, "%s", fiasco_get_error_message ());
+	 p->failed = 1;
+	 pthread_mutex_unlock (&p->lock);
+	 return NULL;
+      }
+   }
+}
+
+int
+fi_parallel_for (size_t n, void (*fn) (size_t i, void *ctx), void *ctx)
+{
+   pfor_t      p;
+   pthread_t   th [16];
+   unsigned    threads = 0, started = 0;
+   const char *e = getenv ("FIASCO_HOST_THREADS");
+   jmp_buf     caller;
+
+   if (e && atoi (e) > 0)
+      threads = (unsigned) atoi (e);
+   else
+   {
+      cpu_set_t set;
+
+      threads = sched_getaffinity (0, sizeof set, &set) == 0 ? (unsigned) CPU_COUNT (&set) : 1;
+   }
+   if (threads > 16)
+      threads = 16;
+   if (threads > n)
+      threads = (unsigned) n;
+   memset (&p, 0, sizeof p);
+   p.n	 = n;
+   p.fn	 = fn;
+   p.ctx = ctx;
+   pthread_mutex_init (&p.lock, NULL);
+   memcpy (caller, fi_env, sizeof caller);	/* the calling thread takes part with a try of its own */
+   for (; started + 1 < threads; started++)
+      if (pthread_create (&th [started], NULL, pfor_worker, &p))
+	 break;
+   pfor_worker (&p);
+   for (unsigned t = 0; t < started; t++)
+      pthread_join (th [t], NULL);
+   memcpy (fi_env, caller, sizeof caller);
+   pthread_mutex_destroy (&p.lock);
+   if (p.failed)
+      fi_set_error ("%s", p.err);	/* the message lives per thread: hand it to the caller's */
+   return p.failed;
 }

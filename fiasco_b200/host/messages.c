@@ -44,6 +44,13 @@ fi_error (const char *format, ...)
    longjmp (fi_env, 1);
 }
 
+/* jump with the message that is already stored */
+void
+fi_rethrow (void)
+{
+   longjmp (fi_env, 1);
+}
+
 const char *
 fi_system_error (void)
 {

@@ -105,29 +105,31 @@ fi_read_image (const char *name)
    n	       = width * height;
    for (i = 0; i < (color ? 3u : 1u); i++)
       img->pixels [i] = fiasco_calloc (n, sizeof (int16_t));
-   if (!color)
    {
-      for (i = 0; i < n; i++)
-      {
-	 int g = getc (f);
+      /* the raster in one read; a short read is the reference's I/O error (lib/image.c:357-388) */
+      const size_t   bytes = (size_t) n * (color ? 3u : 1u);
+      unsigned char *raw   = malloc (bytes);
 
-	 if (g == EOF)
-	    fi_file_error (name ? name : "stdin");
-	 img->pixels [0][i] = (int16_t) ((g - 128) * 16);
-      }
-   }
-   else
-   {
-      for (i = 0; i < n; i++)
+      if (!raw)
+	 fi_error ("Out of memory!");
+      if (fread (raw, 1, bytes, f) != bytes)
       {
-	 int r = getc (f), g = getc (f), b = getc (f);
-
-	 if (r == EOF || g == EOF || b == EOF)
-	    fi_file_error (name ? name : "stdin");
-	 img->pixels [0][i] = (int16_t) ((+0.2989 * r + 0.5866 * g + 0.1145 * b - 128) * 16);
-	 img->pixels [1][i] = (int16_t) ((-0.1687 * r - 0.3312 * g + 0.5000 * b) * 16);
-	 img->pixels [2][i] = (int16_t) ((+0.5000 * r - 0.4183 * g - 0.0816 * b) * 16);
+	 free (raw);
+	 fi_file_error (name ? name : "stdin");
       }
+      if (!color)
+	 for (i = 0; i < n; i++)
+	    img->pixels [0][i] = (int16_t) (((int) raw [i] - 128) * 16);
+      else
+	 for (i = 0; i < n; i++)
+	 {
+	    const int r = raw [3 * i], g = raw [3 * i + 1], b = raw [3 * i + 2];
+
+	    img->pixels [0][i] = (int16_t) ((+0.2989 * r + 0.5866 * g + 0.1145 * b - 128) * 16);
+	    img->pixels [1][i] = (int16_t) ((-0.1687 * r - 0.3312 * g + 0.5000 * b) * 16);
+	    img->pixels [2][i] = (int16_t) ((+0.5000 * r - 0.4183 * g - 0.0816 * b) * 16);
+	 }
+      free (raw);
    }
    if (f != stdin)
       fclose (f);

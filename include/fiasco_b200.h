@@ -149,6 +149,21 @@ typedef struct fb200_stats
    int	    kernel_launches;
 } fb200_stats_t;
 
+/*
+ *  Work done by every launch of this process since the last reset, whichever entry point made it
+ *  (fiasco_coder() of libfiasco included): for measurement harnesses that call the public API and
+ *  still want the kernel time and the bytes that crossed the bus.
+ */
+typedef struct fb200_counters
+{
+   double   kernel_ms;		/* device time of the tile kernel launches (CUDA events) */
+   uint64_t launches;		/* tile kernel launches, capacity retries included */
+   uint64_t h2d_bytes, d2h_bytes;
+} fb200_counters_t;
+void fb200_counters_get (fb200_counters_t *out);
+void fb200_counters_reset (void);
+
+
 /* Fill 'p' from user-level options the way alloc_coder() does (coder.c:249-327).
    optimize follows the CLI: 0 => levels [6,10], 3 edges; 1 => [4,12], 5 edges;
    2 => 1 + second_domain_block; >= 3 => FB200_EUNSUPPORTED (full_search has

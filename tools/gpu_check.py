@@ -64,7 +64,7 @@ def run_case(img, quality=20.0, optimize=0, label="", cap=0):
         print("  wfa lines: oracle %d gpu %d; states oracle %d gpu %d" % (len(ol), len(gl), ow["states"], gw["states"]))
     print("%s %dx%d q=%g z=%d: %s  states %d  oracle %.3fs  gpu kernel %.3f ms (h2d %.2f d2h %.2f ms) mp %d steps %d"
           % (label, w, h, quality, optimize, "OK" if ok else "MISMATCH", gw["states"], t1 - t0, st["kernel_ms"],
-             st["h2d_ms"], st["d2h_ms"], st["mp_calls"], st["mp_steps"]), flush=True)
+             st["h2d_ms"], st["d2h_ms"], st["mp_calls"], st["mp_steps"]) + " pass2 %d" % st.get("pass2", -1), flush=True)
     names = ["ctrl", "pix", "dots", "upsweep", "enter", "mp_pro", "mp_p1", "mp_waves", "mp_commit", "mp_ortho", "ar_epi",
              "ap_img", "ap_direct", "ap_staged", "decide", "cluster"]
     tot = float(sum(st["lap"])) or 1.0
