@@ -177,6 +177,16 @@ cl_map (T *p, unsigned rank)
 }
 #endif
 
+/* only the shape that runs with an SM to itself can be clustered: the batch shapes (and the kernel
+   of predicted frames) are compiled without any of it, so that their registers and their code
+   size stay what they were */
+template <int NT, bool MOTION>
+__host__ __device__ constexpr bool
+clustered_shape (void)
+{
+   return NT >= 512 && !MOTION;
+}
+
 /* transitions of a state in registers */
 struct TransReg
 {
@@ -265,6 +275,8 @@ struct Frame			/* one activation record of subdivide() */
    unsigned gaddr;		/* range->global_address: address in the whole picture (progress meter) */
    int	    level, y_state, label;
    int	    spec_k;		/* position in the current spine of speculated pursuits, or -1 */
+   short    lc_code [FB_MAXEDGES];	/* quantiser codes of lrange's weights and the y-state its pursuit */
+   short    lc_ystate;		/* saw: the models take the range when it wins (ST_DECIDE) */
    int	    new_y_state [2];
    unsigned states_snap;
    float    r_err, r_tree_bits, r_matrix_bits, r_weights_bits; /* rrange sums */
@@ -401,6 +413,7 @@ struct ShHdr
    ClJob    job;		/* rank 0: the job being posted; helpers: the job received */
    SpecRes  spec [FB_SPINE_MAX];	/* rank 0: pursuits of the current spine (entry 0 unused) */
    int	    spec_len;		/* nodes of the current spine */
+   float    spec_rbits [FB_SPINE_MAX];	/* tree bits of "subdivided" at the levels of its nodes */
    int	    pool_lo;		/* lowest pool-list entry written since the list was last posted */
 };
 
@@ -695,7 +708,7 @@ async_wait_all (void)
  *  levels the weighted sums over the state's transitions (ip.c:98-151), each entry
  *  accumulated in the reference's order: label 0 child, label 0 edges, label 1 ...
  */
-template <int NT>
+template <int NT, bool CLU = false>
 __device__ void
 cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
 	       unsigned node_root, int level_root, int top, unsigned g0 = 0, unsigned gnt = NT)
@@ -704,7 +717,7 @@ cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
       share the work (gnt > NT): the loops are strided over all of them and the levels are
       separated by the cluster barrier */
    const unsigned tid	= g0 + threadIdx.x;
-   const bool	 cl	= gnt > (unsigned) NT;
+   const bool	 cl	= CLU && gnt > (unsigned) NT;
    const unsigned S	= sh.h->states;
    const unsigned scap	= (unsigned) P.s_cap;
 
@@ -866,17 +879,38 @@ cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
 	    TransReg tr;
 
 	    load_trans (GP (W.trans) + s, tr);
-	    /* (unconditional, independent gathers as above: one L2 round trip per item) */
-	    int idx [2][FB_MAXEDGES + 1];
-#pragma unroll
-	    for (int label = 0; label < 2; label++)
+	    if (CLU)
 	    {
-	       idx [label][0] = tr.child [label] != FB_RANGE ? tr.child [label] : 0;
+	       /* (unconditional, independent gathers as above: one L2 round trip per item; the
+		  batch shapes, whose frames compete for L2, only load what exists) */
+	       int idx [2][FB_MAXEDGES + 1];
 #pragma unroll
-	       for (int e = 0; e < FB_MAXEDGES; e++)
-		  idx [label][e + 1] = tr.into [label][e] != FB_NO_EDGE ? tr.into [label][e] : 0;
+	       for (int label = 0; label < 2; label++)
+	       {
+		  idx [label][0] = tr.child [label] != FB_RANGE ? tr.child [label] : 0;
+#pragma unroll
+		  for (int e = 0; e < FB_MAXEDGES; e++)
+		     idx [label][e + 1] = tr.into [label][e] != FB_NO_EDGE ? tr.into [label][e] : 0;
+	       }
+	       upsweep_nodes<1> (GP (W.T), scap, node, s, tr, idx);
 	    }
-	    upsweep_nodes<1> (GP (W.T), scap, node, s, tr, idx);
+	    else
+	    {
+	       float acc = 0;
+#pragma unroll
+	       for (int label = 0; label < 2; label++)
+	       {
+		  const float *src = GP (W.T) + (size_t) (2 * node + 1 + label) * scap;
+
+		  if (tr.child [label] != FB_RANGE)
+		     acc += src [tr.child [label]];
+#pragma unroll
+		  for (int e = 0; e < FB_MAXEDGES; e++)
+		     if (tr.into [label][e] != FB_NO_EDGE)
+			acc += src [tr.into [label][e]] * tr.w [label][e];
+	       }
+	       GP (W.T) [(size_t) node * scap + s] = acc;
+	    }
 	 }
       }
       if (cl)
@@ -888,7 +922,7 @@ cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
 }
 
 /* codec/subdivide.c:612-644 (init_range) + :504-541 (cut_to_bintree) */
-template <int NT>
+template <int NT, bool CLU = false>
 __device__ void
 cta_init_range (const DevParams &P, const TileWs &W, const Sh &sh, unsigned x0,
 		unsigned y0, int band, unsigned g0 = 0, unsigned gnt = NT)
@@ -950,7 +984,7 @@ cta_init_range (const DevParams &P, const TileWs &W, const Sh &sh, unsigned x0,
       sh.h->ip_bytes += 4ull * size + 4ull * (63 + (unsigned) ((1 << (P.lc_max - P.il)) - 1)) * ns;
    }
    LAP (sh.h, LAP_PIX);
-   cta_compute_T<NT> (P, W, sh, 0, 0, P.lc_max, P.lc_max, g0, gnt);
+   cta_compute_T<NT, CLU> (P, W, sh, 0, 0, P.lc_max, P.lc_max, g0, gnt);
 }
 
 /* exact fp32 left-to-right sum of squares of a node (approx.c:388-389) */
@@ -1273,7 +1307,7 @@ template <int NT> __device__ void cta_cluster_post (const DevParams &P, const Sh
  *  codec/control.c:48-131 (append_state).  The state's tree / edges are already in place.
  *  Must be called by all threads; 'auxiliary' and 'level' are uniform.
  */
-template <int NT>
+template <int NT, bool CLU>
 __device__ void
 cta_append_state (const DevParams &P, const TileWs &W, const Sh &sh, int auxiliary,
 		  int level_of_state)
@@ -1296,7 +1330,7 @@ cta_append_state (const DevParams &P, const TileWs &W, const Sh &sh, int auxilia
       LAP (sh.h, LAP_DECIDE);
       cta_state_images<NT> (P, W, s);
       LAP (sh.h, LAP_AP_IMG);
-      if (P.cluster > 1)
+      if (CLU && P.cluster > 1)
       {
 	 /* the table levels are shared out over the blocks of the cluster */
 	 if (threadIdx.x == 0)
@@ -1941,14 +1975,14 @@ cta_matching_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &
 
 /* rle_update (domain-pool.c:795-830) + inlined qac_update of the DC model (:404-446) */
 __device__ void
-t0_rle_update (const Sh &sh, const MpWork &w, const short *used_domains)
+t0_rle_update (const Sh &sh, const short *into, int y_state)
 {
+   /* into: the states of the used domains (what the reference looks up through the pool list) */
    int	    state_0 = 0, state_y = 0, edge = 0;
-   const int y_state = w.y_state;
 
-   for (edge = 0; used_domains [edge] != FB_NO_EDGE; edge++)
+   for (edge = 0; into [edge] != FB_NO_EDGE; edge++)
    {
-      const int st = dom_state (sh, w, used_domains [edge]);
+      const int st = into [edge];
 
       if (st == 0)
 	 state_0 = 1;
@@ -2019,6 +2053,97 @@ t0_aac_update (const DevParams &P, const Sh &sh, const short *code, const short 
 }
 
 /*
+ *  Thread 0: approximate_range after its pursuit(s) (approx.c:208-271) for the result 'mp': accept it
+ *  if it is cheaper than max_costs, drop zero weights, fill the range.  lazy == NULL: the models take the
+ *  range at once (rle_update, aac_update) -- a range that cannot be subdivided.  Otherwise the codes and
+ *  the y-state go into the activation record 'lazy' and the models are updated if and when the linear
+ *  combination wins (ST_DECIDE): the reference updates at once, keeps the result aside as "lc models" and
+ *  restores the models it had (subdivide.c:226-237) -- the same thing, one copy of the models later.
+ *  Returns the costs (MAXCOSTS: rejected), also left in h->ret_costs.
+ */
+__device__ float
+t0_range_epilogue (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &mp, int eff_ystate,
+		   float max_costs, float price, int y_state, RangeRes *out, int level, unsigned image,
+		   unsigned address, unsigned x, unsigned y, Frame *lazy)
+{
+   ShHdr *h = sh.h;
+   float  costs;
+   int	  n_edges = -1;
+
+   if (mp.costs < max_costs)
+   {
+      int new_index = 0, edge;
+
+      for (int old = 0; mp.indices [old] != FB_NO_EDGE; old++)
+	 if (mp.weight [old] != 0)
+	 {
+	    mp.indices [new_index] = mp.indices [old];
+	    mp.into [new_index]	   = mp.into [old];
+	    mp.weight [new_index]  = mp.weight [old];
+	    mp.code [new_index]	   = mp.code [old];
+	    new_index++;
+	 }
+      mp.indices [new_index] = FB_NO_EDGE;
+      mp.into [new_index]    = FB_NO_EDGE;
+      if (!lazy)
+      {
+	 t0_rle_update (sh, mp.into, eff_ystate);
+	 t0_aac_update (P, sh, mp.code, mp.into, level);
+      }
+      else
+      {
+	 for (edge = 0; edge < FB_MAXEDGES; edge++)
+	    lazy->lc_code [edge] = mp.code [edge];
+	 lazy->lc_ystate = (short) eff_ystate;
+      }
+      for (edge = 0; mp.indices [edge] != FB_NO_EDGE; edge++)
+      {
+	 out->into [edge]   = mp.into [edge];
+	 out->weight [edge] = mp.weight [edge];
+      }
+      out->into [edge]	= FB_NO_EDGE;
+      out->matrix_bits	= mp.matrix_bits;
+      out->weights_bits = mp.weights_bits;
+      out->err		= mp.err;
+      costs		= mp.costs;
+      n_edges		= edge;
+   }
+   else
+   {
+      out->into [0] = FB_NO_EDGE;
+      costs	    = FB_MAXCOSTS;
+   }
+   h->ret_costs = costs;
+   if (GP (W.trace) && h->trace_len < P.trace_cap)
+   {
+      fb200_trace_rec_t *t = GP (W.trace) + h->trace_len;
+
+      t->level	 = (uint16_t) level;
+      t->image	 = (uint16_t) image;
+      t->address = (uint16_t) address;
+      t->x	 = (uint16_t) x;
+      t->y	 = (uint16_t) y;
+      t->y_state = (int16_t) y_state;
+      t->states	 = (uint16_t) h->states;
+      t->n_edges = (int16_t) n_edges;
+      t->max_costs    = max_costs;
+      t->price	      = price;
+      t->costs	      = costs;
+      t->err	      = n_edges >= 0 ? out->err : 0;
+      t->matrix_bits  = n_edges >= 0 ? out->matrix_bits : 0;
+      t->weights_bits = n_edges >= 0 ? out->weights_bits : 0;
+      for (int e = 0; e < 6; e++)
+      {
+	 t->into [e]   = e < n_edges ? out->into [e] : (int16_t) -1;
+	 t->weight [e] = e < n_edges ? out->weight [e] : 0;
+      }
+   }
+   if (GP (W.trace))
+      h->trace_len++;
+   return costs;
+}
+
+/*
  *  codec/approx.c:74-271 (approximate_range) for the still-image option set
  *  (second_domain_block optional).  Result in 'out' / return value in sh.h->ret_costs.
  */
@@ -2027,7 +2152,7 @@ __device__ void
 cta_approximate_range (const DevParams &P, const TileWs &W, const Sh &sh, float max_costs,
 		       float price, int y_state, RangeRes *out, int level, unsigned image,
 			       unsigned address, unsigned x, unsigned y, float mv_tree_bits,
-		       int spec_k = 0)
+		       Frame *lazy, int spec_k = 0)
 {
    ShHdr *h = sh.h;
 
@@ -2083,73 +2208,8 @@ cta_approximate_range (const DevParams &P, const TileWs &W, const Sh &sh, float 
       __syncthreads ();
    }
    if (threadIdx.x == 0)
-   {
-      MpRes &mp = h->mp;
-      float  costs;
-      int    n_edges = -1;
-
-      if (mp.costs < max_costs)
-      {
-	 int new_index = 0, edge;
-
-	 for (int old = 0; mp.indices [old] != FB_NO_EDGE; old++)
-	    if (mp.weight [old] != 0)
-	    {
-	       mp.indices [new_index] = mp.indices [old];
-	       mp.into [new_index]    = mp.into [old];
-	       mp.weight [new_index]  = mp.weight [old];
-	       mp.code [new_index]    = mp.code [old];
-	       new_index++;
-	    }
-	 mp.indices [new_index] = FB_NO_EDGE;
-	 mp.into [new_index]	= FB_NO_EDGE;
-	 t0_rle_update (sh, h->w, mp.indices);
-	 t0_aac_update (P, sh, mp.code, mp.into, level);
-	 for (edge = 0; mp.indices [edge] != FB_NO_EDGE; edge++)
-	 {
-	    out->into [edge]   = mp.into [edge];
-	    out->weight [edge] = mp.weight [edge];
-	 }
-	 out->into [edge]  = FB_NO_EDGE;
-	 out->matrix_bits  = mp.matrix_bits;
-	 out->weights_bits = mp.weights_bits;
-	 out->err	   = mp.err;
-	 costs		   = mp.costs;
-	 n_edges	   = edge;
-      }
-      else
-      {
-	 out->into [0] = FB_NO_EDGE;
-	 costs	       = FB_MAXCOSTS;
-      }
-      h->ret_costs = costs;
-      if (GP (W.trace) && h->trace_len < P.trace_cap)
-      {
-	 fb200_trace_rec_t *t = GP (W.trace) + h->trace_len;
-
-	 t->level   = (uint16_t) level;
-	 t->image   = (uint16_t) image;
-	 t->address = (uint16_t) address;
-	 t->x	    = (uint16_t) x;
-	 t->y	    = (uint16_t) y;
-	 t->y_state = (int16_t) y_state;
-	 t->states  = (uint16_t) h->states;
-	 t->n_edges = (int16_t) n_edges;
-	 t->max_costs	 = max_costs;
-	 t->price	 = price;
-	 t->costs	 = costs;
-	 t->err		 = n_edges >= 0 ? out->err : 0;
-	 t->matrix_bits	 = n_edges >= 0 ? out->matrix_bits : 0;
-	 t->weights_bits = n_edges >= 0 ? out->weights_bits : 0;
-	 for (int e = 0; e < 6; e++)
-	 {
-	    t->into [e]	  = e < n_edges ? out->into [e] : (int16_t) -1;
-	    t->weight [e] = e < n_edges ? out->weight [e] : 0;
-	 }
-      }
-      if (GP (W.trace))
-	 h->trace_len++;
-   }
+      t0_range_epilogue (P, W, sh, h->mp, h->w.y_state, max_costs, price, y_state, out, level, image, address,
+			 x, y, lazy);
    __syncthreads ();
    LAP (h, LAP_AR_EPI);
 }
@@ -2446,8 +2506,8 @@ cta_helper_loop (const DevParams &P, const TileWs &W, const Sh &sh, unsigned ran
       if (type == CJ_TINIT)
 	 /* this block's share of the products of a new lc_max block; ends with the cluster barrier
 	    after the last level */
-	 cta_init_range<NT> (P, W, sh, (unsigned) h->job.x, (unsigned) h->job.y, h->job.band,
-			     rank * NT, (unsigned) C * NT);
+	 cta_init_range<NT, true> (P, W, sh, (unsigned) h->job.x, (unsigned) h->job.y, h->job.band,
+				   rank * NT, (unsigned) C * NT);
       else if (type == CJ_APPEND)
       {
 	 cta_state_products<NT> (P, W, sh, h->job.s, (int) rank, C);
@@ -2505,10 +2565,72 @@ resx_slot (ShHdr *h, int depth)
  *		  nested pass
  *    ST_DONE
  */
-template <bool MOTION>
+/*
+ *  Thread 0: a range whose pursuit ran with the spine it belongs to (F.spec_k > 0) is entered
+ *  without the block: what ST_ENTER does for it -- the range's bookkeeping, approximate_range
+ *  after the pursuit (t0_range_epilogue), the start of the subdivision alternative -- is scalar
+ *  work on the result in h->spec; the snapshots of the models were taken for the whole spine
+ *  when it was started.  Leaves the range in ST_CHILD (first child next) or, at the lowest
+ *  level, in ST_RETURN.
+ */
 __device__ void
-t0_advance (const DevParams &P, const TileWs &W, ShHdr *h, int &state, int &depth)
+t0_enter_speculated (const DevParams &P, const TileWs &W, const Sh &sh, Frame &F, RangeRes *res,
+		     int &state)
 {
+   ShHdr	 *h	= sh.h;
+   const int	  level = F.level;
+   const int	  k	= F.spec_k;
+   const SpecRes &r	= h->spec [k];
+   const bool	  leaf	= level <= h->lc_min;
+   RangeRes	 &lr	= leaf ? *res : F.lrange;
+
+   F.states_snap     = h->states;
+   F.new_y_state [0] = F.new_y_state [1] = FB_RANGE;	/* (speculated ranges have no y-state) */
+   lr.tree	   = FB_RANGE;
+   lr.x		   = (unsigned short) F.x;
+   lr.y		   = (unsigned short) F.y;
+   lr.tree_bits	   = h->job.node [k].tree_bits;
+   lr.matrix_bits  = 0;
+   lr.weights_bits = 0;
+   lr.err	   = 0;
+   lr.into [0]	   = FB_NO_EDGE;
+   h->mp = r.mp;
+   h->mp_calls++;
+   h->mp_steps += r.steps;
+   h->pass2    += r.pass2;
+   h->mp_bytes += 8ull * r.D + 4ull * r.D * r.steps;
+   F.lincomb_costs = t0_range_epilogue (P, W, sh, h->mp, -1, F.max_costs, h->price, F.y_state, &lr, level,
+					F.image, F.address, F.x, F.y, leaf ? (Frame *) 0 : &F);
+   if (leaf)
+   {
+      state = ST_RETURN;
+      return;
+   }
+   /* alternative 2: recursive subdivision (subdivide.c:243-272) */
+   F.r_tree_bits     = h->spec_rbits [k];
+   F.r_matrix_bits   = 0;
+   F.r_weights_bits  = 0;
+   F.r_err	     = 0;
+   F.subdivide_costs = (F.r_tree_bits + F.r_weights_bits + F.r_matrix_bits + 0.0f + 0.0f + 0.0f + 0.0f)
+		       * h->price;
+   F.label = 0;
+   for (int label = 0; label < 2; label++)
+   {
+      RangeRes &c = F.child [label];
+
+      c.tree = 0;
+      c.into [0] = 0;
+      c.err = c.tree_bits = c.matrix_bits = c.weights_bits = 0;
+   }
+   state = ST_CHILD;
+}
+
+template <bool MOTION, bool CLU>
+__device__ void
+t0_advance (const DevParams &P, const TileWs &W, const Sh &sh, int &state, int &depth)
+{
+   ShHdr *h = sh.h;
+
    for (;;)
    {
       Frame &F = h->frames [depth];
@@ -2529,6 +2651,8 @@ t0_advance (const DevParams &P, const TileWs &W, ShHdr *h, int &state, int &dept
 	    h->ret_costs = 0;			/* subdivide.c:133-135 */
 	    state	 = ST_RETURN;
 	 }
+	 else if (CLU && F.spec_k > 0)
+	    t0_enter_speculated (P, W, sh, F, res, state);
 	 else
 	    return;
       }
@@ -2667,7 +2791,7 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
    ShHdr    *h	 = sh.h;
    const int tid = threadIdx.x;
    int	     it	 = 0;
-   const bool CL = !MOTION && P.cluster > 1;	/* helper blocks at hand */
+   const bool CL = clustered_shape<NT, MOTION> () && P.cluster > 1;	/* helper blocks at hand */
    const int SN	 = MOTION ? 3 : 2;	/* model snapshots per activation record */
    const int TS	 = MOTION ? 2 : 1;	/* tree-model snapshots per record */
    Sh	     shn = sh;			/* buffers and models of the nested (prediction error) pass */
@@ -2700,7 +2824,7 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 	 h->fx [0].delta      = 0;
 	 h->fx [0].prediction = 1;
       }
-      t0_advance<MOTION> (P, W, h, st, dp);
+      t0_advance<MOTION, clustered_shape<NT, MOTION> ()> (P, W, sh, st, dp);
       h->state [0]  = st;
       h->depthv [0] = dp;
    }
@@ -2742,12 +2866,12 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 	       h->job.band   = band;
 	    }
 	    cta_cluster_post<NT> (P, sh, false);
-	    cta_init_range<NT> (P, W, cs, F.x, F.y, band, 0, (unsigned) P.cluster * NT);
+	    cta_init_range<NT, clustered_shape<NT, MOTION> ()> (P, W, cs, F.x, F.y, band, 0, (unsigned) P.cluster * NT);
 	 }
 	 else if (block)
 	    cta_init_range<NT> (P, W, cs, F.x, F.y, band);
 	 else
-	    cta_compute_T<NT> (P, W, cs, F.states_snap, F.image * 2 + F.label + 1, F.level - 1,
+	    cta_compute_T<NT, clustered_shape<NT, MOTION> ()> (P, W, cs, F.states_snap, F.image * 2 + F.label + 1, F.level - 1,
 			       MOTION ? h->top : P.lc_max);
 	 if (tid == 0)
 	 {
@@ -2835,7 +2959,7 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 		  lr.into [0]	  = FB_NO_EDGE;
 	       }
 	    }
-	    else if (tid == 32 && !leaf && level > h->lc_min)
+	    else if (clustered_shape<NT, MOTION> () && tid == 32 && !leaf && level > h->lc_min)
 	       /* bits of the "subdivided" symbol (subdivide.c:243-248), next to thread 0's: the tree
 		  model does not change before they are used */
 	       F.r_tree_bits = t0_tree_bits (h, 1, level);
@@ -2893,6 +3017,23 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 			nd.tree_bits = k ? t0_tree_bits (h, 0, level - k) : F.lrange.tree_bits;
 			nd.norm	     = t0_node_norm (P, cs, nd.image, nd.address, nd.level);
 		     }
+		     else if (tid >= 32 && tid < 32 + n)
+			h->spec_rbits [tid - 32] = t0_tree_bits (h, 1, level - (tid - 32));
+		     /* the snapshots of the models (subdivide.c:188-194) for the ranges below: they are
+			entered with the models and the tree model of this moment (t0_enter_speculated) */
+		     for (int i = tid; i < (n - 1) * (P.blob_len / 8); i += NT)
+		     {
+			const int k = 1 + i / (P.blob_len / 8), j = i % (P.blob_len / 8);
+
+			((uint4 *) (snap + (size_t) k * SN * P.blob_len)) [j] = ((const uint4 *) sh.blob) [j];
+		     }
+		     for (int i = tid; i < (n - 1) * 2 * FB200_MAXLEVEL; i += NT)
+		     {
+			const int	k  = 1 + i / (2 * FB200_MAXLEVEL), j = i % (2 * FB200_MAXLEVEL);
+			const unsigned *tm = (const unsigned *) ((const char *) h + offsetof (ShHdr, tree_counts));
+
+			(tsnap + (size_t) k * TS * 2 * FB200_MAXLEVEL) [j] = tm [j];
+		     }
 		     cta_cluster_post<NT> (P, sh, true);
 		     if (tid == 0)
 			F.spec_k = 0;	/* (after the barriers of the post: every thread has read it) */
@@ -2905,7 +3046,7 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 	       cta_approximate_range<NT> (P, W, cs, F.max_costs, h->price, F.y_state,
 					  leaf ? res : &F.lrange, level, F.image, F.address, F.x, F.y,
 					  MOTION ? h->fx [depth].lrange.mv_tree_bits : 0.0f,
-					  sk > 0 ? sk : 0);
+					  leaf ? (Frame *) 0 : &F, sk > 0 ? sk : 0);
 	       if (spine)
 	       {
 		  cl_sync ();		/* the helpers' results are in h->spec */
@@ -2924,21 +3065,16 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 		  nstate = ST_RETURN;
 	       break;
 	    }
-	    /* keep the "lc" models, restore the snapshot (subdivide.c:226-237); element i
-	       is handled by one thread for both copies */
-	    for (int i = tid; i < P.blob_len / 8; i += NT)
-	    {
-	       const uint4 lc = ((const uint4 *) sh.blob) [i];
-	       const uint4 sn = ((const uint4 *) snap) [i];
-
-	       ((uint4 *) (snap + P.blob_len)) [i] = lc;
-	       ((uint4 *) sh.blob) [i]		   = sn;
-	    }
+	    /* (the models have not taken the linear combination: no "lc" models to keep, nothing
+	       to restore, subdivide.c:226-237 -- see t0_range_epilogue) */
 	    if (tid == 0)
 	    {
 	       if (level > h->lc_min)
 	       {
-		  /* alternative 2: recursive subdivision (subdivide.c:243-272); r_tree_bits: thread 32 */
+		  /* alternative 2: recursive subdivision (subdivide.c:243-272); the shape with an SM
+		     to itself had thread 32 work out r_tree_bits next to thread 0's bits */
+		  if (!clustered_shape<NT, MOTION> ())
+		     F.r_tree_bits = t0_tree_bits (h, 1, level);
 		  F.r_matrix_bits  = 0;
 		  F.r_weights_bits = 0;
 		  F.r_err	   = 0;
@@ -3288,15 +3424,16 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 	    {
 	       const bool fail = (lin >= FB_MAXCOSTS && sub >= FB_MAXCOSTS);
 
-	       /* restore snapshot or adopt the lc models; restore the tree model; drop
-		  the states created below this node (subdivide.c:409-467) */
-	       cta_copy_s16<NT> (sh.blob, fail ? snap : snap + P.blob_len, P.blob_len);
+	       /* the models and the tree model of the node's entry -- plus, if the linear
+		  combination wins, what it adds to them ("lc" models, t0_range_epilogue); drop the
+		  states created below this node (subdivide.c:409-467).  Warp 0 only: thread 0 goes
+		  on without a block-wide barrier in between */
 	       if (tid < 32)
 	       {
-		  /* warp 0 only: thread 0 goes on to update the tree model without a
-		     block-wide barrier in between */
 		  unsigned *tm = (unsigned *) ((char *) h + offsetof (ShHdr, tree_counts));
 
+		  for (int i = tid; i < P.blob_len / 8; i += 32)
+		     ((uint4 *) sh.blob) [i] = ((const uint4 *) snap) [i];
 		  for (int i = tid; i < 2 * FB200_MAXLEVEL; i += 32)
 		     tm [i] = tsnap [i];
 		  __syncwarp ();
@@ -3308,6 +3445,8 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 		     h->ret_costs = FB_MAXCOSTS;
 		  else
 		  {
+		     t0_rle_update (cs, F.lrange.into, F.lc_ystate);
+		     t0_aac_update (P, cs, F.lc_code, F.lrange.into, F.level);
 		     const unsigned short rx = (unsigned short) F.x, ry = (unsigned short) F.y;
 		     *res      = F.lrange;
 		     res->tree = FB_RANGE;
@@ -3395,7 +3534,7 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 	       }
 	       __syncthreads ();
 	       const long long t0c = clock64 ();
-	       cta_append_state<NT> (P, W, sh, aux, F.level);
+	       cta_append_state<NT, clustered_shape<NT, MOTION> ()> (P, W, sh, aux, F.level);
 	       if (tid == 0)
 		  h->cyc_append += clock64 () - t0c;
 	    }
@@ -3405,7 +3544,11 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
       /* thread 0 continues with the scalar part of the control flow */
       if (tid == 0)
       {
-	 t0_advance<MOTION> (P, W, h, nstate, ndepth);
+	 if (clustered_shape<NT, MOTION> ())
+	    LAP (h, LAP_DECIDE);	/* (diagnostics: what the case left unaccounted) */
+	 t0_advance<MOTION, clustered_shape<NT, MOTION> ()> (P, W, sh, nstate, ndepth);
+	 if (clustered_shape<NT, MOTION> ())
+	    LAP (h, LAP_AP_STAGED);	/* (diagnostics of the clustered shape: the scalar walk) */
 	 h->state [(it + 1) & 1]  = nstate;
 	 h->depthv [(it + 1) & 1] = ndepth;
       }
@@ -3535,9 +3678,10 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
    __shared__ TileWs s_W;
    int		     slot = -1;
    /* cluster per stream: rank 0 encodes, the others serve it */
-   const unsigned    crank  = P.cluster > 1 ? cl_rank () : 0u;
-   const unsigned    tile   = P.cluster > 1 ? blockIdx.x / (unsigned) P.cluster : blockIdx.x;
-   const unsigned    ntiles = P.cluster > 1 ? gridDim.x / (unsigned) P.cluster : gridDim.x;
+   constexpr bool    CLU    = clustered_shape<NT, MOTION> ();
+   const unsigned    crank  = CLU && P.cluster > 1 ? cl_rank () : 0u;
+   const unsigned    tile   = CLU && P.cluster > 1 ? blockIdx.x / (unsigned) P.cluster : blockIdx.x;
+   const unsigned    ntiles = CLU && P.cluster > 1 ? gridDim.x / (unsigned) P.cluster : gridDim.x;
 
    if (threadIdx.x == 0)
       s_W = ws_array [tile];
@@ -3626,7 +3770,7 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
    }
    __syncthreads ();
 
-   if (crank != 0)
+   if (CLU && crank != 0)
    {
       cta_helper_loop<NT> (P, W, sh, crank);
       return;
@@ -3771,7 +3915,7 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
 	 atomicExch (P.slot_flags + slot, 0);
       }
    }
-   if (P.cluster > 1)
+   if (CLU && P.cluster > 1)
    {
       if (tid == 0)
 	 h->job.type = CJ_EXIT;
