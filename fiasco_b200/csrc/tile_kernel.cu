@@ -2691,8 +2691,9 @@ t0_advance (const DevParams &P, const TileWs &W, const Sh &sh, int &state, int &
 	 /* progress meter (subdivide.c:323-337): (global_address + 1) * 100.0 / 2^k, truncated --
 	    exact in integers.  Nothing is printed here; the host replays the values. */
 	 {
-	    const unsigned long long pos = (unsigned long long) F.gaddr * 2 + label + 1;
-	    const unsigned np = (unsigned) ((pos * 100) >> (P.level - (F.level - 1)));
+	    /* (32 bits are enough: at most 2^22 ranges, times 100) */
+	    const unsigned pos = F.gaddr * 2 + (unsigned) label + 1;
+	    const unsigned np  = (pos * 100u) >> (P.level - (F.level - 1));
 
 	    if (np > h->percent)
 	    {
@@ -2792,6 +2793,12 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
    const int tid = threadIdx.x;
    int	     it	 = 0;
    const bool CL = clustered_shape<NT, MOTION> () && P.cluster > 1;	/* helper blocks at hand */
+   /* The batch shapes update the models the way the reference does: at once, the result kept aside
+      as "lc" models until the range is decided (subdivide.c:226-237).  The clustered shape leaves
+      the update to ST_DECIDE (t0_range_epilogue): its speculated ranges are entered by thread 0
+      alone, which cannot copy models.  Measured on a full batch: 786 against 762 Mpx/s for the
+      late update, whose serial part sits behind a read of the snapshot from global memory. */
+   constexpr bool EAGER = !clustered_shape<NT, MOTION> ();
    const int SN	 = MOTION ? 3 : 2;	/* model snapshots per activation record */
    const int TS	 = MOTION ? 2 : 1;	/* tree-model snapshots per record */
    Sh	     shn = sh;			/* buffers and models of the nested (prediction error) pass */
@@ -2896,7 +2903,11 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 	     *  subdivide.c:409-467 amounts to -- so no snapshot is taken and the range returns
 	     *  from here.  (Predicted frames keep the general path: a third alternative follows.)
 	     */
+#ifdef FB200_X_NOLEAF
+	    const bool leaf = false;
+#else
 	    const bool leaf = !MOTION && level <= h->lc_min && level <= P.lc_max;
+#endif
 
 	    /* snapshot of the models (subdivide.c:188-194); tree_counts and tree_total are
 	       adjacent in the header */
@@ -3046,7 +3057,7 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 	       cta_approximate_range<NT> (P, W, cs, F.max_costs, h->price, F.y_state,
 					  leaf ? res : &F.lrange, level, F.image, F.address, F.x, F.y,
 					  MOTION ? h->fx [depth].lrange.mv_tree_bits : 0.0f,
-					  leaf ? (Frame *) 0 : &F, sk > 0 ? sk : 0);
+					  leaf || EAGER ? (Frame *) 0 : &F, sk > 0 ? sk : 0);
 	       if (spine)
 	       {
 		  cl_sync ();		/* the helpers' results are in h->spec */
@@ -3067,6 +3078,15 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 	    }
 	    /* (the models have not taken the linear combination: no "lc" models to keep, nothing
 	       to restore, subdivide.c:226-237 -- see t0_range_epilogue) */
+	    if (EAGER)
+	       for (int i = tid; i < P.blob_len / 8; i += NT)
+	       {
+		  const uint4 lc = ((const uint4 *) sh.blob) [i];
+		  const uint4 sn = ((const uint4 *) snap) [i];
+
+		  ((uint4 *) (snap + P.blob_len)) [i] = lc;
+		  ((uint4 *) sh.blob) [i]	      = sn;
+	       }
 	    if (tid == 0)
 	    {
 	       if (level > h->lc_min)
@@ -3432,8 +3452,10 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 	       {
 		  unsigned *tm = (unsigned *) ((char *) h + offsetof (ShHdr, tree_counts));
 
+		  const short *from = EAGER && !fail ? snap + P.blob_len : snap;
+
 		  for (int i = tid; i < P.blob_len / 8; i += 32)
-		     ((uint4 *) sh.blob) [i] = ((const uint4 *) snap) [i];
+		     ((uint4 *) sh.blob) [i] = ((const uint4 *) from) [i];
 		  for (int i = tid; i < 2 * FB200_MAXLEVEL; i += 32)
 		     tm [i] = tsnap [i];
 		  __syncwarp ();
@@ -3445,8 +3467,11 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 		     h->ret_costs = FB_MAXCOSTS;
 		  else
 		  {
-		     t0_rle_update (cs, F.lrange.into, F.lc_ystate);
-		     t0_aac_update (P, cs, F.lc_code, F.lrange.into, F.level);
+		     if (!EAGER)
+		     {
+			t0_rle_update (cs, F.lrange.into, F.lc_ystate);
+			t0_aac_update (P, cs, F.lc_code, F.lrange.into, F.level);
+		     }
 		     const unsigned short rx = (unsigned short) F.x, ry = (unsigned short) F.y;
 		     *res      = F.lrange;
 		     res->tree = FB_RANGE;
