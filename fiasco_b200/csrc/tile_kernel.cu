@@ -2319,16 +2319,32 @@ cta_find_best_mv (const DevParams &P, const TileWs &W, const Sh &sh, unsigned x0
 	 }
       }
    }
-   /* the pursuit's work arrays are idle here */
-   sh.num [threadIdx.x]		  = best;
-   ((int *) sh.den) [threadIdx.x] = besti;
+   /* the least (costs, index) pair: inside the warps by shuffles, then over the warps' results
+      (the pursuit's work arrays are idle here) */
+#pragma unroll
+   for (int o = 16; o > 0; o >>= 1)
+   {
+      const float c = __shfl_xor_sync (0xffffffffu, best, o);
+      const int	  i = __shfl_xor_sync (0xffffffffu, besti, o);
+
+      if (i >= 0 && (besti < 0 || c < best || (c == best && i < besti)))
+      {
+	 best  = c;
+	 besti = i;
+      }
+   }
+   if ((threadIdx.x & 31) == 0)
+   {
+      sh.num [threadIdx.x >> 5]		   = best;
+      ((int *) sh.den) [threadIdx.x >> 5] = besti;
+   }
    __syncthreads ();
    if (threadIdx.x == 0)
    {
       float m  = FB_MAXCOSTS;
       int   mi = -1;
 
-      for (int t = 0; t < NT; t++)
+      for (int t = 0; t < NT / 32; t++)
       {
 	 const float c = sh.num [t];
 	 const int   i = ((const int *) sh.den) [t];
@@ -2847,7 +2863,16 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
       int	ndepth = depth;
       /* nested pass of a prediction: the delta models, the prediction error block */
       const bool nested = MOTION && h->nest_base >= 0 && depth >= h->nest_base;
-      const Sh	&cs	= nested ? shn : sh;
+      /* (a copy with the three members that differ selected one by one: a reference to one of two
+	 structs would put both into local memory) */
+      Sh	 cs	= sh;
+
+      if (MOTION && nested)
+      {
+	 cs.blob   = shn.blob;
+	 cs.pixels = shn.pixels;
+	 cs.norm_i = shn.norm_i;
+      }
 
       if (state == ST_DONE || h->status != FB200_OK)
 	 break;
@@ -3336,14 +3361,23 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 
 			acc += q * q;
 		     }
-		     ((long long *) sh.num) [tid] = acc;
+#pragma unroll
+		     for (int o = 16; o > 0; o >>= 1)
+		     {
+			const unsigned lo = __shfl_xor_sync (0xffffffffu, (unsigned) (acc & 0xffffffffll), o);
+			const unsigned hi = __shfl_xor_sync (0xffffffffu, (unsigned) (acc >> 32), o);
+
+			acc += (long long) (((unsigned long long) hi << 32) | lo);
+		     }
+		     if ((tid & 31) == 0)
+			((long long *) sh.num) [tid >> 5] = acc;
 		     __syncthreads ();
 		     if (tid == 0)
 		     {
 			long long tot = 0;
 			float	  norm;
 
-			for (int t = 0; t < NT; t++)
+			for (int t = 0; t < NT / 32; t++)
 			   tot += ((const long long *) sh.num) [t];
 			if (tot <= (1ll << 24))
 			   norm = (float) tot;

@@ -56,7 +56,7 @@ void	 emu_cluster_sync (void);		/* barrier.cluster arrive + wait */
 unsigned emu_cluster_rank (void);
 unsigned emu_cluster_size (void);
 void	*emu_map_shared_rank (const void *p, unsigned rank);	/* mapa */
-unsigned emu_warp_exchange (unsigned value, int kind, int arg);	/* 0 shfl, 1 shfl_up, 2 ballot, 3 sync */
+unsigned emu_warp_exchange (unsigned value, int kind, int arg);	/* 0 shfl, 1 shfl_up, 2 ballot, 3 sync, 4 shfl_xor */
 unsigned char *emu_dyn_smem (void);
 
 static inline void __syncthreads (void) { emu_syncthreads (); }
@@ -80,6 +80,16 @@ __shfl_up_sync (unsigned, T v, unsigned delta)
    unsigned u;
    memcpy (&u, &v, 4);
    u = emu_warp_exchange (u, 1, (int) delta);
+   memcpy (&v, &u, 4);
+   return v;
+}
+template <typename T> static inline T
+__shfl_xor_sync (unsigned, T v, int mask)
+{
+   static_assert (sizeof (T) == 4, "32-bit shuffles only");
+   unsigned u;
+   memcpy (&u, &v, 4);
+   u = emu_warp_exchange (u, 4, mask);
    memcpy (&v, &u, 4);
    return v;
 }

@@ -258,6 +258,8 @@ emu_warp_exchange (unsigned value, int kind, int arg)
 	    m |= (w.slot [buf][l] ? 1u : 0u) << l;
 	 return m;
       }
+      case 4:
+	 return (lane ^ (unsigned) arg) < lanes ? w.slot [buf][lane ^ (unsigned) arg] : value;
       default:
 	 return 0;
    }

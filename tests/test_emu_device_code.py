@@ -62,6 +62,31 @@ def test_emulated_device_code_other_block_shapes(emu, nt):
         os.environ["FB200_NT"] = "128"
 
 
+@pytest.mark.parametrize("cluster", ["2", "8"])
+def test_emulated_cluster_per_stream(emu, cluster):
+    """The clustered shape (one stream on several thread blocks: speculated pursuits of a range's label-0
+    descendants, products and table levels shared out) under the emulator, which runs the blocks of a
+    cluster together: grey, colour and -z 2 equal the oracle, work counters included."""
+    saved = os.environ.get("FB200_CLUSTER")
+    os.environ["FB200_NT"], os.environ["FB200_CLUSTER"] = "512", cluster
+    try:
+        img = gen_frames.chan(128, 96, 5)
+        gw, _, st = T.gpu_encode(img)
+        ow = O.encode(img, want_trace=True)
+        T.assert_same_wfa(gw, ow)
+        assert st["mp_calls"] == len(O.lc_lines(ow["trace"]))
+        col = np.stack([gen_frames.chan(64, 64, s) for s in (11, 12, 13)], axis=-1)
+        T.assert_same_wfa(T.gpu_encode(col, quality=30.0)[0], O.encode(col, quality=30.0), bands=3)
+        grey = gen_frames.chan(96, 64, 2)
+        T.assert_same_wfa(T.gpu_encode(grey, optimize=2)[0], O.encode(grey, optimize=2))
+    finally:
+        os.environ["FB200_NT"] = "128"
+        if saved is None:
+            os.environ.pop("FB200_CLUSTER", None)
+        else:
+            os.environ["FB200_CLUSTER"] = saved
+
+
 def test_emulated_device_code_colour_and_optimisation_levels(emu):
     img = np.stack([gen_frames.chan(128, 128, s) for s in (11, 12, 13)], axis=-1)
     T.assert_same_wfa(T.gpu_encode(img, quality=30.0)[0], O.encode(img, quality=30.0), bands=3)

@@ -382,3 +382,71 @@ def test_gpu_motion_norms_match_reference_loops(level, sr):
             assert np.array_equal(got[by, bx].view(np.uint32), ref.view(np.uint32)), (bx, by)
             checked += 1
     assert checked > 20 and ms > 0
+
+
+# ------------------------------------------------------------------ cluster per stream (round 2)
+
+def _with_cluster(c, fn):
+    saved = os.environ.get("FB200_CLUSTER")
+    os.environ["FB200_CLUSTER"] = str(c)
+    try:
+        return fn()
+    finally:
+        if saved is None:
+            os.environ.pop("FB200_CLUSTER", None)
+        else:
+            os.environ["FB200_CLUSTER"] = saved
+
+
+CLUSTER_CASES = [("g256", 0, 0, 256, 256, 20, 0), ("g1024", 0, 0, 200, 136, 20, 0), ("g256", 64, 64, 128, 128, 20, 1),
+                 ("g256", 0, 0, 128, 128, 20, 2), ("c256", 64, 128, 128, 128, 20, 0), ("c256", 0, 0, 256, 256, 30, 0)]
+
+
+@pytest.mark.parametrize("cluster", [2, 4, 8])
+@pytest.mark.parametrize("frame,x0,y0,w,h,q,z", CLUSTER_CASES)
+def test_gpu_cluster_per_stream_matches_oracle_trace_and_wfa(cluster, frame, x0, y0, w, h, q, z):
+    """One stream on a thread-block cluster: the helper blocks run the pursuits of a range's label-0
+    descendants ahead (same models, same states: subdivide.c:188-237), their share of a block's products
+    and of a new state's table levels.  Every approximate_range result, in the reference's order, and the
+    automaton: bit for bit, for every cluster size (grey, colour, -z 1, -z 2, a ragged picture)."""
+    img = np.ascontiguousarray(gen_frames.frame(frame)[y0:y0 + h, x0:x0 + w])
+    ow = O.encode(img, quality=q, optimize=z, want_trace=True)
+    gw, tr, st = _with_cluster(cluster, lambda: gpu_encode(img, q, z, trace=True))
+    olc = O.lc_lines(ow["trace"])
+    glc = [trace_line(i, r) for i, r in enumerate(tr)]
+    for i, (a, b) in enumerate(zip(olc, glc)):
+        assert a == b, "first divergence at approximate_range call %d" % i
+    assert len(olc) == len(glc)
+    assert_same_wfa(gw, ow, bands=3 if img.ndim == 3 else 1)
+    # the work counters count the pursuits that were used, not the ones that ran ahead in vain
+    # (-z 2: two pursuits per range, the second without the first one's first domain, approx.c:103-127)
+    assert st["mp_calls"] == len(olc) * (2 if z == 2 else 1)
+
+
+def test_gpu_cluster_full_frame_1024_matches_reference():
+    """BASELINE config[1], the monolithic 1024^2 frame, on the cluster the launcher picks for one stream
+    (8 blocks): the reference's golden automaton and work counters."""
+    gw, _, st = gpu_encode(O.case_image("g1024_q20_z0"), 20.0, 0)
+    assert F.wfa_lines(gw) == O.golden_wfa_lines("g1024_q20_z0")
+    assert st["mp_calls"] == 20385 and st["mp_steps"] == 27768
+
+
+def test_gpu_cluster_tiles_share_the_device():
+    """Fewer streams than SMs: every stream gets a cluster (16 tiles -> clusters of 8 on a B200); same
+    automata as the tiles coded alone on one block each."""
+    img = gen_frames.frame("g1024")
+    crops = gen_frames.crops(img, 256)
+    p = ffi.make_params(256, 256, 1, 20.0, 0)
+    planes = [ffi.pixels_from_grey(c).reshape(-1) for c in crops]
+
+    def run():
+        enc = F.TileEncoder(p, len(crops))
+        try:
+            return enc.encode(planes)[0]
+        finally:
+            enc.close()
+
+    auto = run()
+    alone = _with_cluster(1, run)
+    for a, b in zip(auto, alone):
+        assert F.wfa_lines(a) == F.wfa_lines(b)
