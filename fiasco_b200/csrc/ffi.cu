@@ -35,6 +35,10 @@ struct fb200_ctx
    int		  trace_cap;
    TileWs	 *d_ws;
    int		 *d_lc_min;	/* [tiles] lc_min_level the tiles start with (fb200_wfa_t.lc_min_level) */
+   int		 *d_ready;	/* [tiles] epoch of the launch whose pixels have arrived (pipelined batches) */
+   int		 *h_epoch;	/* pinned: the current epoch, source of the flag copies */
+   int		  epoch;
+   cudaStream_t	  copy_stream;
    /* pinned host staging */
    unsigned char *h_wfa;
    TileResult	 *h_results;
@@ -394,6 +398,10 @@ fb200_destroy (fb200_ctx_t *c)
    cudaFree (c->d_trace);
    cudaFree (c->d_ws);
    cudaFree (c->d_lc_min);
+   cudaFree (c->d_ready);
+   cudaFreeHost (c->h_epoch);
+   if (c->copy_stream)
+      cudaStreamDestroy (c->copy_stream);
    cudaFreeHost (c->h_wfa);
    cudaFreeHost (c->h_results);
    for (int i = 0; i < 6; i++)
@@ -458,6 +466,10 @@ ctx_alloc (fb200_ctx_t *c, char *err, size_t errlen)
       CUDA_TRY (cudaMalloc (&c->d_ws, sizeof (TileWs) * max_tiles));
       CUDA_TRY (cudaMalloc (&c->d_lc_min, sizeof (int) * max_tiles));
       CUDA_TRY (cudaMemset (c->d_lc_min, 0, sizeof (int) * max_tiles));
+      CUDA_TRY (cudaMalloc (&c->d_ready, sizeof (int) * max_tiles));
+      CUDA_TRY (cudaMemset (c->d_ready, 0, sizeof (int) * max_tiles));
+      CUDA_TRY (cudaMallocHost (&c->h_epoch, sizeof (int)));
+      CUDA_TRY (cudaStreamCreateWithFlags (&c->copy_stream, cudaStreamNonBlocking));
       CUDA_TRY (cudaMallocHost (&c->h_results, sizeof (TileResult) * max_tiles));
       CUDA_TRY (cudaStreamCreateWithFlags (&c->stream, cudaStreamNonBlocking));
       for (int i = 0; i < 6; i++)
@@ -852,14 +864,52 @@ fb200_encode_tiles (fb200_ctx_t *c, int n_tiles, const int16_t *const *planes,
 	 CUDA_TRY (cudaMemcpy (c->d_lc_min, lc.data (), sizeof (int) * n_tiles, cudaMemcpyHostToDevice));
       }
    }
-   if ((rc = fb200_upload (c, n_tiles, planes, err, errlen)))
+   /*
+    *  More tiles than the device holds at once: launch first, copy after.  The blocks of the launch
+    *  wait for their tile's flag, which travels behind the tile's pixels in the copy stream, so the
+    *  later tiles' pixels cross the bus while the first ones are coded (FIASCO_PIPELINE=0: the plain
+    *  order upload, launch).  The flag is the launch's epoch: nothing to clear between launches.
+    */
+   bool pipelined = n_tiles > c->n_slots && !(getenv ("FIASCO_PIPELINE") && atoi (getenv ("FIASCO_PIPELINE")) == 0);
+#ifdef FB200_EMU
+   pipelined = false;
+#endif
+   if (pipelined)
+   {
+      const size_t plane = (size_t) c->dp.width * c->dp.height;
+
+      CUDA_TRY (cudaSetDevice (c->device));
+      *c->h_epoch	= ++c->epoch;
+      c->dp.tile_ready	= c->d_ready;
+      c->dp.ready_epoch = c->epoch;
+      rc = fb200_launch (c, n_tiles, NULL, err, errlen);
+      c->dp.tile_ready = NULL;
+      if (rc)
+	 return rc;
+      CUDA_TRY (cudaEventRecord (c->ev [0], c->copy_stream));
+      for (int t = 0; t < n_tiles; t++)
+      {
+	 for (int b = 0; b < c->dp.bands; b++)
+	    CUDA_TRY (cudaMemcpyAsync (c->d_pix + c->pix_elems * t + plane * b, planes [t * c->dp.bands + b],
+				       plane * 2, cudaMemcpyHostToDevice, c->copy_stream));
+	 CUDA_TRY (cudaMemcpyAsync (c->d_ready + t, c->h_epoch, sizeof (int), cudaMemcpyHostToDevice,
+				    c->copy_stream));
+      }
+      CUDA_TRY (cudaEventRecord (c->ev [1], c->copy_stream));
+      CUDA_TRY (cudaStreamSynchronize (c->copy_stream));
+      cudaEventElapsedTime (&c->stats.h2d_ms, c->ev [0], c->ev [1]);
+      c->stats.h2d_bytes = c->pix_elems * 2 * n_tiles;
+      count_work (0, 0, c->stats.h2d_bytes, 0);
+   }
+   else if ((rc = fb200_upload (c, n_tiles, planes, err, errlen)))
       return rc;
    float total_ms = 0;
    int	 launches = 0;
    for (;;)
    {
-      if ((rc = fb200_launch (c, n_tiles, NULL, err, errlen)))
+      if (!pipelined && (rc = fb200_launch (c, n_tiles, NULL, err, errlen)))
 	 return rc;
+      pipelined = false;		/* (a capacity retry finds the pixels in place) */
       rc = fb200_download (c, n_tiles, out, trace, trace_cap, trace_len, err, errlen);
       /* a launch that ran out of state capacity is part of the bill */
       total_ms += c->stats.kernel_ms;

@@ -3743,7 +3743,23 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
    const unsigned    ntiles = CLU && P.cluster > 1 ? gridDim.x / (unsigned) P.cluster : gridDim.x;
 
    if (threadIdx.x == 0)
+   {
       s_W = ws_array [tile];
+      /* pipelined batches (fb200_encode_tiles): the tile's pixels are on their way; the copy that
+	 follows them in the same stream writes the flag */
+      if (P.tile_ready)
+      {
+#ifdef FB200_EMU
+	 (void) 0;		/* (the emulated copies are synchronous) */
+#else
+	 int v;
+
+	 do
+	    asm volatile ("ld.global.acquire.gpu.b32 %0, [%1];" : "=r" (v) : "l" (P.tile_ready + tile) : "memory");
+	 while (v != P.ready_epoch);
+#endif
+      }
+   }
 
    /*
     *  More tiles than workspaces: take a free one (entry i of ws_array also describes

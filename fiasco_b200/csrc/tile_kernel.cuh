@@ -74,6 +74,9 @@ struct DevParams
    int	 blob_half;		/* shorts of one model set; blob = normal set, then delta set */
    int	 n_frames;		/* DFS activation records (nested delta pass included) */
    const int *tile_lc_min;	/* [tiles] lc_min_level a tile starts with (0: lc_min), or NULL */
+   const int *tile_ready;	/* [tiles] or NULL: a block starts when tile_ready [tile] == ready_epoch -- the
+				   pixels of the later tiles of a batch travel while the first ones are coded */
+   int	 ready_epoch;
    int	 cluster;		/* thread blocks per stream (filled by the launcher): rank 0 walks the
 				   recursion, the others serve it (tile_kernel.cu, "cluster per stream") */
 };

@@ -32,6 +32,7 @@
 #include <ctype.h>
 #include <math.h>
 #include <pthread.h>
+#include <time.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -350,6 +351,9 @@ wave_worker (void *arg)
 	 future [k] = w->future [i] ? w->future [i]->recon : NULL;
       }
    }
+   struct timespec t0, t1, t2;
+
+   clock_gettime (CLOCK_MONOTONIC, &t0);
    if (!g->ctx [w->type] || g->ctx_tiles [w->type] < (int) share)
    {
       const int tiles = (int) fi_max (share, w->max_share);
@@ -369,6 +373,7 @@ wave_worker (void *arg)
 	 rc = fb200_create (&g->ctx [w->type], w->p, tiles, g->device, g->err, sizeof g->err);
       g->ctx_tiles [w->type] = tiles;
    }
+   clock_gettime (CLOCK_MONOTONIC, &t1);
    if (rc == FB200_OK)
    {
       if (w->type)
@@ -377,6 +382,20 @@ wave_worker (void *arg)
       else
 	 rc = fb200_encode_tiles (g->ctx [w->type], (int) share, planes, batch, NULL, 0, NULL,
 				  g->err, sizeof g->err);
+   }
+   clock_gettime (CLOCK_MONOTONIC, &t2);
+   if (getenv ("FIASCO_TIMINGS"))
+   {
+      fb200_stats_t st;
+
+      memset (&st, 0, sizeof st);
+      if (g->ctx [w->type])
+	 fb200_get_stats (g->ctx [w->type], &st);
+      fprintf (stderr, "fiasco_coder:   gpu %d, %u units: context %.1f ms, call %.1f ms (h2d %.1f, kernel %.1f, "
+	       "d2h %.1f)\n", g->device, share,
+	       1e3 * (double) (t1.tv_sec - t0.tv_sec) + 1e-6 * (double) (t1.tv_nsec - t0.tv_nsec),
+	       1e3 * (double) (t2.tv_sec - t1.tv_sec) + 1e-6 * (double) (t2.tv_nsec - t1.tv_nsec),
+	       (double) st.h2d_ms, (double) st.kernel_ms, (double) st.d2h_ms);
    }
    if (rc != FB200_OK)
    {
@@ -464,13 +483,39 @@ static struct
    unsigned	       n_gpus;
    unit_t	     **wave_u, **wave_past, **wave_future;
    char		      *tile_name;
+   fb200_params_t      prep_p;		/* workspaces set up beside the reading of the frames */
+   unsigned	       prep_tiles;
+   pthread_t	       prep_thread;
+   int		       prep_running;
    fi_bits_t	     **frame_bits;	/* the frames' own bit streams until they are joined */
    size_t	       n_frame_bits;
 } job;
 
+/* host thread: create the intra contexts of all GPUs of the job (errors are left to the launch,
+   which creates what it does not find) */
+static void *
+prepare_contexts (void *arg)
+{
+   (void) arg;
+   for (unsigned g = 0; g < job.n_gpus; g++)
+   {
+      gpu_t *gp = &job.gpus [g];
+      char   err [600];
+
+      if (!gp->ctx [0]
+	  && fb200_create (&gp->ctx [0], &job.prep_p, (int) job.prep_tiles, gp->device, err, sizeof err) == FB200_OK)
+	 gp->ctx_tiles [0] = (int) job.prep_tiles;
+      else
+	 gp->ctx [0] = NULL;
+   }
+   return NULL;
+}
+
 static void
 job_release (void)
 {
+   if (job.prep_running)
+      pthread_join (job.prep_thread, NULL);
    for (unsigned g = 0; g < FI_MAXGPUS; g++)
       for (int t = 0; t < 3; t++)
 	 if (job.gpus [g].ctx [t])
@@ -567,6 +612,22 @@ tile_output_name (const char *outputname, unsigned tile, unsigned tiles)
    else
       sprintf (s, "%s.t%0*u", outputname, width, tile);
    return s;
+}
+
+/* FIASCO_TIMINGS=1: wall time of the phases of a call on stderr (measurement aid) */
+static double
+phase_clock (const char *what)
+{
+   static double   last;
+   struct timespec ts;
+   double	   now;
+
+   clock_gettime (CLOCK_MONOTONIC, &ts);
+   now = (double) ts.tv_sec + 1e-9 * (double) ts.tv_nsec;
+   if (what && getenv ("FIASCO_TIMINGS"))
+      fprintf (stderr, "fiasco_coder: %-28s %8.1f ms\n", what, 1e3 * (now - last));
+   last = now;
+   return now;
 }
 
 static unsigned
@@ -723,6 +784,7 @@ coder (char const *const *inputname, const char *outputname, float quality,
    else if (!outputname || strcmp (outputname, "-") == 0)
       fi_error ("FIASCO_TILE_SPLIT writes one file per tile: an output file name is needed.");
 
+   phase_clock (NULL);
    /* all frames readable, same size, same colour model (coder.c:204-240) */
    expand_names (templates, &job.names);
    frames = job.names.n;
@@ -874,6 +936,29 @@ coder (char const *const *inputname, const char *outputname, float quality,
    mo.p_max_level  = (int) wi.p_max_level;
    mo.search_range = (int) cop->search_range;
 
+   phase_clock ("headers, options");
+   /* the device workspaces of the intra frames are set up while the frames are read: every GPU
+      gets the context of its largest intra launch (the launches find them, wave_worker) */
+   {
+      unsigned intra = 0;
+
+      for (unsigned wv = 0; wv < job.sched.n_waves; wv++)
+      {
+	 unsigned cnt = 0;
+
+	 for (n = 0; n < frames; n++)
+	    if ((unsigned) job.sched.wave [n] == wv && job.sched.ctype [n] == 0)
+	       cnt += streams;
+	 intra = fi_max (intra, cnt);
+      }
+      job.prep_p     = p;
+      job.prep_tiles = (intra + job.n_gpus - 1) / job.n_gpus;
+      /* (FIASCO_PREPARE=1: measured slower on the bench box -- the allocations of the context
+	 and the page faults of the reading threads contend for the address space) */
+      if (job.prep_tiles && getenv ("FIASCO_PREPARE") && atoi (getenv ("FIASCO_PREPARE"))
+	  && pthread_create (&job.prep_thread, NULL, prepare_contexts, NULL) == 0)
+	 job.prep_running = 1;
+   }
    /* read the frames, cut them into the streams' pictures */
    job.images	= fiasco_calloc (frames, sizeof (fi_image_t *));
    job.n_images = frames;
@@ -905,6 +990,12 @@ coder (char const *const *inputname, const char *outputname, float quality,
 	    job.units [(size_t) s * frames + job.sched.future [n]].is_reference = 1;
       }
 
+   if (job.prep_running)
+   {
+      pthread_join (job.prep_thread, NULL);
+      job.prep_running = 0;
+   }
+   phase_clock ("frames read");
    /* the waves: every frame whose references are ready, over all streams, in one launch per
       frame type and GPU */
    job.wave_u	   = fiasco_calloc ((size_t) streams * frames, sizeof (unit_t *));
@@ -963,6 +1054,7 @@ coder (char const *const *inputname, const char *outputname, float quality,
 	    run_wave (&w);
 	 }
    }
+   phase_clock ("launches (contexts, copies)");
    for (unsigned g = 0; g < job.n_gpus; g++)	/* the device memory is not needed any longer */
       for (int t = 0; t < 3; t++)
 	 if (job.gpus [g].ctx [t])
@@ -971,6 +1063,7 @@ coder (char const *const *inputname, const char *outputname, float quality,
 	    job.gpus [g].ctx [t] = NULL;
 	 }
 
+   phase_clock ("contexts released");
    /* the streams: every frame is coded into a bit stream of its own on the host threads, then
       the frames of a stream are joined in coding order */
    fi_write_tables_init ();
@@ -1011,6 +1104,7 @@ coder (char const *const *inputname, const char *outputname, float quality,
       free (job.tile_name);
       job.tile_name = NULL;
    }
+   phase_clock ("streams written");
    (void) n_predicted;
    return 1;
 }
