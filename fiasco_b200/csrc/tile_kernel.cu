@@ -184,7 +184,8 @@ template <int NT, bool MOTION>
 __host__ __device__ constexpr bool
 clustered_shape (void)
 {
-   return NT >= 512 && !MOTION;
+   (void) MOTION;
+   return NT >= 512;
 }
 
 /* transitions of a state in registers */
@@ -343,13 +344,14 @@ struct MpWork
 
 /* jobs of the helper blocks of a cluster */
 #define FB_SPINE_MAX 8
-enum { CJ_EXIT, CJ_SPINE, CJ_TINIT, CJ_APPEND };
+enum { CJ_EXIT, CJ_SPINE, CJ_TINIT, CJ_APPEND, CJ_TERR };
 
 struct SpineNode		/* one pursuit of a spine: the range (level, image, address) */
 {
    int	    level;
    unsigned image, address;
    float    tree_bits, norm;
+   float    mv_tree_bits;	/* predicted frames: 1 if motion compensation is allowed for the range */
 };
 
 struct ClJob
@@ -360,6 +362,9 @@ struct ClJob
    int	     x, y, band;	/* TINIT: the block */
    unsigned  s;			/* APPEND: the new state */
    float     price;
+   int	     nested;		/* predicted frames: the pass over a prediction error (delta models, its pixels) */
+   int	     tswap;		/* predicted frames: the product tables T / T2 are swapped */
+   int	     level;		/* TERR: level of the prediction-error block */
    SpineNode node [FB_SPINE_MAX];
 };
 
@@ -415,6 +420,7 @@ struct ShHdr
    int	    spec_len;		/* nodes of the current spine */
    float    spec_rbits [FB_SPINE_MAX];	/* tree bits of "subdivided" at the levels of its nodes */
    int	    pool_lo;		/* lowest pool-list entry written since the list was last posted */
+   int	    tswap;		/* predicted frames: W.T and W.T2 are swapped (nested pass) */
 };
 
 static_assert (offsetof (ShHdr, tree_total) == offsetof (ShHdr, tree_counts) + FB200_MAXLEVEL * sizeof (unsigned),
@@ -474,7 +480,8 @@ smem_layout (const DevParams &p, int nt, size_t *off /* [20] */)
    off [14] = o; o += align16 ((size_t) (p.aac_dc_size + p.aac_lvl_size) * 4);	/* quantiser tables */
    off [15] = o; o += align16 ((size_t) p.n_frames * (p.motion ? 2 : 1) * 2 * FB200_MAXLEVEL * 4); /* tsnap */
    off [16] = o; o += p.motion ? align16 ((size_t) p.n_frames * sizeof (FrameX)) : 0;
-   off [17] = off [18] = off [19] = o;
+   off [17] = o; o += align16 (sizeof (TileWs));	/* the tile's pointer table */
+   off [18] = off [19] = o;
    return o;
 }
 
@@ -1336,6 +1343,7 @@ cta_append_state (const DevParams &P, const TileWs &W, const Sh &sh, int auxilia
 	 if (threadIdx.x == 0)
 	 {
 	    sh.h->job.type   = CJ_APPEND;
+	    sh.h->job.nested = 0;
 	    sh.h->job.states = s;
 	    sh.h->job.s	     = s;
 	 }
@@ -2444,6 +2452,8 @@ cta_cluster_post (const DevParams &P, const Sh &sh, bool with_models)
    const int jw	 = (int) (sizeof (ClJob) / 4);
 
    LAP (h, LAP_CTRL);
+   if (tid == 0)
+      h->job.tswap = h->tswap;
    __syncthreads ();
    for (int it = tid; it < (C - 1) * jw; it += NT)
    {
@@ -2488,7 +2498,7 @@ cta_spine_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, int k, Spe
    ShHdr	  *h  = sh.h;
    const SpineNode nd = h->job.node [k];
 
-   cta_matching_pursuit<NT> (P, W, sh, h->mp, nd.level, nd.image, nd.norm, nd.tree_bits, 0.0f,
+   cta_matching_pursuit<NT> (P, W, sh, h->mp, nd.level, nd.image, nd.norm, nd.tree_bits, nd.mv_tree_bits,
 			     h->job.price, FB_RANGE, -1);
    for (int i = threadIdx.x; i < (int) (sizeof (MpRes) / 4); i += NT)
       ((unsigned *) &dst->mp) [i] = ((const unsigned *) &h->mp) [i];
@@ -2502,28 +2512,59 @@ cta_spine_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, int k, Spe
 }
 
 /* ranks > 0: serve rank 0 until it says the frame is done */
-template <int NT>
+template <int NT, bool MOTION>
 __device__ void
-cta_helper_loop (const DevParams &P, const TileWs &W, const Sh &sh, unsigned rank)
+cta_helper_loop (const DevParams &P, TileWs &W, const Sh &sh, unsigned rank)
 {
    ShHdr    *h = sh.h;
    const int C = P.cluster;
+   Sh	     shn = sh;		/* the nested pass of a predicted frame: delta models, prediction-error pixels */
 
+   if (MOTION)
+   {
+      shn.blob	 = sh.blob + P.blob_half;
+      shn.pixels = GP (W.pix2);
+      shn.norm_i = GP (W.norm2);
+      if (threadIdx.x == 0)
+	 h->tswap = 0;
+   }
    for (;;)
    {
       cl_sync ();			/* a job has been posted */
-      const int type = h->job.type;
+      const int	 type	= h->job.type;
+      const bool nested = MOTION && h->job.nested;
 
       if (type == CJ_EXIT)
 	 break;
       if (threadIdx.x == 0)
+      {
 	 h->states = h->job.states;
+	 if (MOTION && h->job.tswap != h->tswap)
+	 {
+	    /* rank 0 works on the other product table (prediction.c:318-341): so do we */
+	    float *t = W.T;
+
+	    W.T	     = W.T2;
+	    W.T2     = t;
+	    h->tswap = h->job.tswap;
+	 }
+      }
       __syncthreads ();
+      Sh cs = sh;
+
+      if (nested)
+      {
+	 cs.blob   = shn.blob;
+	 cs.pixels = shn.pixels;
+	 cs.norm_i = shn.norm_i;
+      }
       if (type == CJ_TINIT)
 	 /* this block's share of the products of a new lc_max block; ends with the cluster barrier
 	    after the last level */
-	 cta_init_range<NT, true> (P, W, sh, (unsigned) h->job.x, (unsigned) h->job.y, h->job.band,
+	 cta_init_range<NT, true> (P, W, cs, (unsigned) h->job.x, (unsigned) h->job.y, h->job.band,
 				   rank * NT, (unsigned) C * NT);
+      else if (MOTION && type == CJ_TERR)
+	 cta_compute_T<NT, true> (P, W, cs, 0, 0, h->job.level, h->job.level, rank * NT, (unsigned) C * NT);
       else if (type == CJ_APPEND)
       {
 	 cta_state_products<NT> (P, W, sh, h->job.s, (int) rank, C);
@@ -2532,7 +2573,7 @@ cta_helper_loop (const DevParams &P, const TileWs &W, const Sh &sh, unsigned ran
       else
       {
 	 for (int k = (int) rank; k < h->job.n; k += C)
-	    cta_spine_pursuit<NT> (P, W, sh, k, &cl_map (h, 0)->spec [k]);
+	    cta_spine_pursuit<NT> (P, W, cs, k, &cl_map (h, 0)->spec [k]);
 	 cl_sync ();
       }
    }
@@ -2589,16 +2630,39 @@ resx_slot (ShHdr *h, int depth)
  *  when it was started.  Leaves the range in ST_CHILD (first child next) or, at the lowest
  *  level, in ST_RETURN.
  */
+template <bool MOTION>
 __device__ void
-t0_enter_speculated (const DevParams &P, const TileWs &W, const Sh &sh, Frame &F, RangeRes *res,
+t0_enter_speculated (const DevParams &P, const TileWs &W, const Sh &sh, Frame &F, FrameX *X, RangeRes *res,
 		     int &state)
 {
    ShHdr	 *h	= sh.h;
    const int	  level = F.level;
    const int	  k	= F.spec_k;
    const SpecRes &r	= h->spec [k];
-   const bool	  leaf	= level <= h->lc_min;
+   const bool	  leaf	= !MOTION && level <= h->lc_min;	/* (predicted frames: a third alternative follows) */
    RangeRes	 &lr	= leaf ? *res : F.lrange;
+   float	  mvt	= 0.0f;
+
+   if (MOTION)
+   {
+      /* what ST_ENTER sets up for the motion compensated alternative (subdivide.c:141-147) */
+      mvt	   = h->job.node [k].mv_tree_bits;
+      X->try_mc	   = mvt != 0.0f;
+      X->pred_done = 0;
+      X->lrange.mv_tree_bits  = mvt;
+      X->lrange.mv_coord_bits = 0;
+      X->lrange.mv_type = X->lrange.mv_fx = X->lrange.mv_fy = X->lrange.prediction = 0;
+      X->lrange.mv_bx = X->lrange.mv_by = 0;
+      X->r_mvt = mvt;
+      X->r_mvc = 0;
+      for (int label = 0; label < 2; label++)
+      {
+	 X->child [label].mv_tree_bits = X->child [label].mv_coord_bits = 0;
+	 X->child [label].mv_type = X->child [label].mv_fx = X->child [label].mv_fy = 0;
+	 X->child [label].mv_bx = X->child [label].mv_by = 0;
+	 X->child [label].prediction = 0;
+      }
+   }
 
    F.states_snap     = h->states;
    F.new_y_state [0] = F.new_y_state [1] = FB_RANGE;	/* (speculated ranges have no y-state) */
@@ -2622,12 +2686,18 @@ t0_enter_speculated (const DevParams &P, const TileWs &W, const Sh &sh, Frame &F
       state = ST_RETURN;
       return;
    }
+   if (level <= h->lc_min)	/* (predicted frames) no subdivision: on to the motion compensated alternative */
+   {
+      F.subdivide_costs = FB_MAXCOSTS;
+      state		= ST_DECIDE;
+      return;
+   }
    /* alternative 2: recursive subdivision (subdivide.c:243-272) */
    F.r_tree_bits     = h->spec_rbits [k];
    F.r_matrix_bits   = 0;
    F.r_weights_bits  = 0;
    F.r_err	     = 0;
-   F.subdivide_costs = (F.r_tree_bits + F.r_weights_bits + F.r_matrix_bits + 0.0f + 0.0f + 0.0f + 0.0f)
+   F.subdivide_costs = (F.r_tree_bits + F.r_weights_bits + F.r_matrix_bits + mvt + 0.0f + 0.0f + 0.0f)
 		       * h->price;
    F.label = 0;
    for (int label = 0; label < 2; label++)
@@ -2668,7 +2738,14 @@ t0_advance (const DevParams &P, const TileWs &W, const Sh &sh, int &state, int &
 	    state	 = ST_RETURN;
 	 }
 	 else if (CLU && F.spec_k > 0)
-	    t0_enter_speculated (P, W, sh, F, res, state);
+	 {
+	    /* (the nested pass of a predicted frame: the delta models) */
+	    Sh cs = sh;
+
+	    if (MOTION && h->nest_base >= 0 && depth >= h->nest_base)
+	       cs.blob = sh.blob + P.blob_half;
+	    t0_enter_speculated<MOTION> (P, W, cs, F, MOTION ? &h->fx [depth] : (FrameX *) 0, res, state);
+	 }
 	 else
 	    return;
       }
@@ -2892,6 +2969,7 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 	    if (tid == 0)
 	    {
 	       h->job.type   = CJ_TINIT;
+	       h->job.nested = nested;
 	       h->job.states = h->states;
 	       h->job.x	     = (int) F.x;
 	       h->job.y	     = (int) F.y;
@@ -3036,6 +3114,7 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 		     if (tid == 0)
 		     {
 			h->job.type   = CJ_SPINE;
+			h->job.nested = nested;
 			h->job.n      = n;
 			h->job.states = h->states;
 			h->job.pool_n = BLOB_U16 (sh, MB_N);
@@ -3052,6 +3131,12 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 			nd.address   = F.address << k;
 			nd.tree_bits = k ? t0_tree_bits (h, 0, level - k) : F.lrange.tree_bits;
 			nd.norm	     = t0_node_norm (P, cs, nd.image, nd.address, nd.level);
+			/* motion compensation allowed for the range? (subdivide.c:141-147; the range shares
+			   its corner with this one, so it lies inside the frame if this one does) */
+			nd.mv_tree_bits = MOTION && h->fx [depth].prediction && level - k >= P.p_min
+					  && level - k <= P.p_max
+					  && F.x + width_of_level (level - k) <= (unsigned) P.width
+					  && F.y + height_of_level (level - k) <= (unsigned) P.height ? 1.0f : 0.0f;
 		     }
 		     else if (tid >= 32 && tid < 32 + n)
 			h->spec_rbits [tid - 32] = t0_tree_bits (h, 1, level - (tid - 32));
@@ -3070,12 +3155,30 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 
 			(tsnap + (size_t) k * TS * 2 * FB200_MAXLEVEL) [j] = tm [j];
 		     }
+		     /* clear_norms_table (prediction.c:195-211) of the ranges below, which are entered
+			without the block: nothing touches those tables before */
+		     if (MOTION && h->fx [depth].prediction)
+			for (int k = 1; k < n; k++)
+			{
+			   const int lk = level - k;
+
+			   if (lk > P.p_min && lk <= P.p_max
+			       && F.x + width_of_level (lk) <= (unsigned) P.width
+			       && F.y + height_of_level (lk) <= (unsigned) P.height)
+			      for (int dir = 0; dir < (P.motion == 2 ? 2 : 1); dir++)
+			      {
+				 float *nt = norms_of_level (P, W, lk, dir);
+
+				 for (int i = tid; i < 4 * P.sr * P.sr; i += NT)
+				    nt [i] = 0.0f;
+			      }
+			}
 		     cta_cluster_post<NT> (P, sh, true);
 		     if (tid == 0)
 			F.spec_k = 0;	/* (after the barriers of the post: every thread has read it) */
 		     /* a spine longer than the cluster: this block's further nodes */
 		     for (int k = P.cluster; k < n; k += P.cluster)
-			cta_spine_pursuit<NT> (P, W, sh, k, &h->spec [k]);
+			cta_spine_pursuit<NT> (P, W, cs, k, &h->spec [k]);
 		     spine = true;
 		  }
 	       }
@@ -3199,6 +3302,7 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 		     float *t = W.T;
 		     W.T      = W.T2;
 		     W.T2     = t;
+		     h->tswap ^= 1;
 		  }
 		  h->nest_base = -1;
 		  h->top       = P.lc_max;
@@ -3267,6 +3371,8 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 			the usable states of the split alternative, in order */
 		     unsigned k = ((const unsigned short *) snap) [MB_N];
 
+		     if ((int) k < h->pool_lo)
+			h->pool_lo = (int) k;
 		     for (unsigned s = F.states_snap; s < X.rec_states; s++)
 			if (GP (W.domain_type) [s] & 2)
 			   sh.pool [k++] = (short) s;
@@ -3437,12 +3543,28 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 		     float *t = W.T;
 		     W.T  = W.T2;
 		     W.T2 = t;
+		     h->tswap ^= 1;
 		     h->top	  = level;
 		     h->nest_base = depth + 1;
 		     X.last_state = h->states - 1;
 		  }
 		  __syncthreads ();
-		  cta_compute_T<NT> (P, W, shn, 0, 0, level, level);
+		  if (CL)
+		  {
+		     /* the products of the prediction-error block: every block of the cluster its share */
+		     if (tid == 0)
+		     {
+			h->job.type   = CJ_TERR;
+			h->job.states = h->states;
+			h->job.level  = level;
+			h->job.nested = 1;
+		     }
+		     cta_cluster_post<NT> (P, sh, false);
+		     cta_compute_T<NT, clustered_shape<NT, MOTION> ()> (P, W, shn, 0, 0, level, level, 0,
+									(unsigned) P.cluster * NT);
+		  }
+		  else
+		     cta_compute_T<NT> (P, W, shn, 0, 0, level, level);
 		  if (tid == 0)
 		  {
 		     Frame &C = h->frames [depth + 1];
@@ -3734,7 +3856,11 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
    FB_DYN_SMEM (unsigned char, smem_raw);
    /* the tile's pointer table lives in shared memory: 19 pointers are 38 registers that the
       pursuit loops need more urgently */
+#ifdef FB200_EMU		/* (the emulator's "static shared" is one object for all blocks of a cluster) */
+   TileWs	    &s_W  = *(TileWs *) (smem_raw + P.sm_off [17]);
+#else
    __shared__ TileWs s_W;
+#endif
    int		     slot = -1;
    /* cluster per stream: rank 0 encodes, the others serve it */
    constexpr bool    CLU    = clustered_shape<NT, MOTION> ();
@@ -3831,6 +3957,7 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
       h->states	   = 0;
       h->pool_lo   = 0;
       h->spec_len  = 0;
+      h->tswap	   = 0;
    }
    __syncthreads ();
 
@@ -3847,7 +3974,7 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
 
    if (CLU && crank != 0)
    {
-      cta_helper_loop<NT> (P, W, sh, crank);
+      cta_helper_loop<NT, MOTION> (P, s_W, sh, crank);
       return;
    }
 
@@ -3993,7 +4120,10 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
    if (CLU && P.cluster > 1)
    {
       if (tid == 0)
-	 h->job.type = CJ_EXIT;
+      {
+	 h->job.type   = CJ_EXIT;
+	 h->job.nested = 0;
+      }
       cta_cluster_post<NT> (P, sh, false);
    }
 }
@@ -4171,7 +4301,7 @@ fb_launch_tile_kernel (const DevParams &p, const TileWs *d_ws, int n_tiles,
    if (p.motion)		/* predicted frames: the two production shapes only */
       return fb_tile_kernel_threads (p, n_tiles) <= 128
 	     ? launch_nt<128, true> (p, d_ws, n_tiles, stream)
-	     : launch_nt<512, true> (p, d_ws, n_tiles, stream);
+	     : launch_nt<512, true> (p, d_ws, n_tiles, stream, fb_tile_kernel_cluster (p, n_tiles));
    switch (fb_tile_kernel_threads (p, n_tiles))
    {
       case 96:	return launch_nt<96, false> (p, d_ws, n_tiles, stream);
@@ -4192,7 +4322,7 @@ fb_tile_kernel_cluster (const DevParams &p, int n_tiles)
 {
    int sms = 148, dev = 0, c = 1;
 
-   if (p.motion || n_tiles <= 0 || n_tiles > p.n_slots)
+   if (n_tiles <= 0 || n_tiles > p.n_slots)
       return 1;
    if (fb_tile_kernel_threads (p, n_tiles) != 512)
       return 1;
@@ -4224,9 +4354,10 @@ fb_tile_kernel_cluster (const DevParams &p, int n_tiles)
       at [0].val.clusterDim.y = at [0].val.clusterDim.z = 1;
       cfg.attrs	   = at;
       cfg.numAttrs = 1;
-      cudaFuncSetAttribute (fiasco_tile_kernel<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-			    (int) cfg.dynamicSmemBytes);
-      if (cudaOccupancyMaxActiveClusters (&n, fiasco_tile_kernel<512, false>, &cfg) == cudaSuccess && n >= n_tiles)
+      const auto kernel = p.motion ? fiasco_tile_kernel<512, true> : fiasco_tile_kernel<512, false>;
+
+      cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) cfg.dynamicSmemBytes);
+      if (cudaOccupancyMaxActiveClusters (&n, kernel, &cfg) == cudaSuccess && n >= n_tiles)
 	 break;
       cudaGetLastError ();
       c /= 2;

@@ -165,6 +165,31 @@ def test_emulated_device_code_predicted_frames(emu, name):
     assert checked >= 3
 
 
+def test_emulated_cluster_per_stream_predicted_frames(emu):
+    """P frames on a cluster of thread blocks: the helper blocks follow rank 0 into the nested pass over a
+    prediction error (the other product table, the delta models, the error block's pixels) -- every frame of
+    the golden IPPP sequence state for state against the oracle in holes mode."""
+    saved = os.environ.get("FB200_CLUSTER")
+    os.environ["FB200_NT"], os.environ["FB200_CLUSTER"] = "512", "2"
+    try:
+        m, frames, ws, rec = _holes_mode_automata("v160_q20_ippp")
+        p = ffi.make_params(m["width"], m["height"], 1, float(m["quality"]), 0)
+        enc = F.TileEncoder(p, 1, motion=F.Motion(1, 6, 10, 16))
+        try:
+            for f in range(1, len(frames)):
+                od = O.struct_dict(ws[f]["_struct"])
+                g = enc.encode_predicted([O.planes_of(frames[f])[0]], [rec[f - 1]])[0]
+                assert_same_predicted_automaton(g, od)
+        finally:
+            enc.close()
+    finally:
+        os.environ["FB200_NT"] = "128"
+        if saved is None:
+            os.environ.pop("FB200_CLUSTER", None)
+        else:
+            os.environ["FB200_CLUSTER"] = saved
+
+
 def predicted_frames_in_coding_order(name):
     """(frame type, display number, plane, past, future, oracle automaton in holes mode) of every predicted
     frame of a golden sequence, with the reference bookkeeping of video_coder() (codec/coder.c:571-627)
