@@ -340,10 +340,12 @@ struct MpWork
    short  half_lv, half_dc;	/* rtob (0.5) of the two quantisers */
    float  best_mbits, best_wbits, best_err, best_costs;
    unsigned st_steps, st_pass2;	/* work counters of this pursuit (added to the tile's when it is used) */
+   int	  win;			/* wide waves: rank of the winning candidate or -1 */
 };
 
 /* jobs of the helper blocks of a cluster */
 #define FB_SPINE_MAX 8
+#define FB_WIDE_PAYLOAD 13	/* 5 weights, 5 codes, matrix bits, weights bits, error */
 enum { CJ_EXIT, CJ_SPINE, CJ_TINIT, CJ_APPEND, CJ_TERR };
 
 struct SpineNode		/* one pursuit of a spine: the range (level, image, address) */
@@ -445,6 +447,7 @@ struct Sh			/* pointers into dynamic shared memory */
    FrameX  *fx;			/* predicted frames only */
    int	    dcap;
    int	    scratch_len;	/* floats from num to the end of bnd / G: row scratch of append_state */
+   float   *wide;		/* [2 + FB_WIDE_PAYLOAD][NT] candidates of a wide wave (NT >= 512 only) */
 };
 
 __host__ __device__ inline size_t align16 (size_t x) { return (x + 15) & ~(size_t) 15; }
@@ -481,7 +484,10 @@ smem_layout (const DevParams &p, int nt, size_t *off /* [20] */)
    off [15] = o; o += align16 ((size_t) p.n_frames * (p.motion ? 2 : 1) * 2 * FB200_MAXLEVEL * 4); /* tsnap */
    off [16] = o; o += p.motion ? align16 ((size_t) p.n_frames * sizeof (FrameX)) : 0;
    off [17] = o; o += align16 (sizeof (TileWs));	/* the tile's pointer table */
-   off [18] = off [19] = o;
+   /* the shape with an SM to itself evaluates up to nt candidates of a pursuit step at once: key,
+      costs and the 13 words of a candidate's result, one column per thread (cta_mp_find_wide) */
+   off [18] = o; o += nt >= 512 ? align16 ((size_t) nt * 4 * (2 + FB_WIDE_PAYLOAD)) : 0;
+   off [19] = o;
    return o;
 }
 
@@ -513,6 +519,7 @@ carve (unsigned char *base, const DevParams &p, int nt, float *gglob)
    s.qt_lv  = s.qt_dc + p.aac_dc_size;
    s.tsnap  = (unsigned *) (base + off [15]);
    s.fx	    = p.motion ? (FrameX *) (base + off [16]) : (FrameX *) 0;
+   s.wide   = (float *) (base + off [18]);
    return s;
 }
 
@@ -1765,6 +1772,178 @@ cta_mp_find (const DevParams &P, const Sh &sh, MpRes &mp, float price, int n)
 }
 
 /*
+ *  The same step for the shape that has an SM to itself: ALL candidates whose bound beats the
+ *  minimum the step starts with (up to one per thread) are evaluated at once, every warp its 32;
+ *  warp 0 then resolves them in index order against the running minimum exactly as above.  More
+ *  speculative evaluations, but (almost always) a single wave: the narrow version needs 1.5 waves
+ *  per step on a 1024^2 frame, each a dependent chain of ~2500 cycles on the path of the stream.
+ *  A candidate's result travels through shared memory (sh.wide, one column per thread).
+ */
+template <int NT, int N>
+__device__ void
+cta_mp_find_wide (const DevParams &P, const Sh &sh, MpRes &mp, float price, int n)
+{
+   const int tid  = threadIdx.x;
+   const int lane = tid & 31;
+   const int warp = tid >> 5;
+   MpWork   &w	  = sh.h->w;
+   const int D	  = w.D;
+   const int D32  = (D + 31) & ~31;
+   const float err = mp.err;
+   float       m   = w.min_costs;
+   float      *ck  = sh.wide, *cc = sh.wide + NT, *pay = sh.wide + 2 * NT;
+
+   for (int d = tid; d < D32; d += NT)
+   {
+      float b = INFINITY;
+
+      if (d < D && !sh.used [d])
+	 b = mp_pass1<N> (w, d, dom_state (sh, w, d), sh.num [d], sh.den [d], price, err);
+      sh.bnd [d] = b;
+      const unsigned mask = __ballot_sync (0xffffffffu, b < m);
+      if (lane == 0)
+	 sh.cmask [d >> 5] = mask;
+   }
+   LAP (sh.h, LAP_MP_P1);
+   int	pos   = 0;
+   bool first = true;
+
+   for (;;)
+   {
+      if (!first)
+	 for (int d = tid; d < D32; d += NT)
+	 {
+	    const unsigned mask = __ballot_sync (0xffffffffu, d >= pos && sh.bnd [d] < m);
+	    if (lane == 0)
+	       sh.cmask [d >> 5] = mask;
+	 }
+      __syncthreads ();
+      /* every warp scans the candidate words (the same counts in every warp) and picks the
+	 candidates number 32 * warp ... 32 * warp + 31 */
+      const int nwords = D32 >> 5;
+      int	base = 0, cand = -1;
+      bool	more = false;
+
+      for (int g = 0; g < nwords; g += 32)
+      {
+	 const unsigned word = (g + lane < nwords) ? sh.cmask [g + lane] : 0u;
+	 const int	cnt  = __popc (word);
+	 int		incl = cnt;
+#pragma unroll
+	 for (int o = 1; o < 32; o <<= 1)
+	 {
+	    const int t = __shfl_up_sync (0xffffffffu, incl, o);
+	    if (lane >= o)
+	       incl += t;
+	 }
+	 const int total = __shfl_sync (0xffffffffu, incl, 31);
+	 const int r	 = tid - base;
+	 int	   lo = 0, hi = 31;
+#pragma unroll
+	 for (int it = 0; it < 5; it++)
+	 {
+	    const int mid = (lo + hi) >> 1;
+	    const int v	  = __shfl_sync (0xffffffffu, incl, mid);
+	    if (v > r)
+	       hi = mid;
+	    else
+	       lo = mid + 1;
+	 }
+	 const unsigned wsel = __shfl_sync (0xffffffffu, word, lo);
+	 const int	esel = __shfl_sync (0xffffffffu, incl - cnt, lo);
+	 if (r >= 0 && r < total)
+	    cand = ((g + lo) << 5) + (int) __fns (wsel, 0, r - esel + 1);
+	 base += total;
+	 if (base >= NT && g + 32 < nwords)
+	 {
+	    more = true;		/* unscanned words may hold further candidates */
+	    break;
+	 }
+      }
+      if (base > NT)
+	 more = true;
+      const int ntake = base < NT ? base : NT;
+
+      if (tid < ntake)
+      {
+	 float	     res [8];
+	 int	     cod [FB_MAXEDGES];
+	 const float b	   = sh.bnd [cand];
+	 const float costs = mp_pass2<N> (P, sh, w, mp, n, cand, sh.num [cand], sh.den [cand], price, res, cod);
+
+	 ck [tid] = b > costs ? b : costs;	/* both must beat the running minimum */
+	 cc [tid] = costs;
+#pragma unroll
+	 for (int k = 0; k < FB_MAXEDGES; k++)
+	 {
+	    pay [k * NT + tid]			= res [k];
+	    pay [(FB_MAXEDGES + k) * NT + tid] = __int_as_float (cod [k]);
+	 }
+	 pay [10 * NT + tid] = res [5];
+	 pay [11 * NT + tid] = res [6];
+	 pay [12 * NT + tid] = res [7];
+	 if (more && tid == ntake - 1)
+	    w.wave_pos = cand + 1;
+      }
+      __syncthreads ();
+      if (warp == 0)
+      {
+	 int win = -1;
+
+	 for (int c = 0; c < ntake; c += 32)
+	 {
+	    const float key   = c + lane < ntake ? ck [c + lane] : INFINITY;
+	    const float costs = c + lane < ntake ? cc [c + lane] : 0.0f;
+	    int		last  = -1;
+
+	    for (;;)
+	    {
+	       const unsigned m2 = __ballot_sync (0xffffffffu, key < m && lane > last);
+	       if (!m2)
+		  break;
+	       last = __ffs ((int) m2) - 1;
+	       m    = __shfl_sync (0xffffffffu, costs, last);
+	       win  = c + last;
+	    }
+	 }
+	 if (lane == 0)
+	 {
+	    w.win = win;
+	    if (win >= 0)
+	    {
+#pragma unroll
+	       for (int k = 0; k < FB_MAXEDGES; k++)
+	       {
+		  w.best_f [k] = pay [k * NT + win];
+		  w.best_c [k] = (short) __float_as_int (pay [(FB_MAXEDGES + k) * NT + win]);
+	       }
+	       w.best_mbits = pay [10 * NT + win];
+	       w.best_wbits = pay [11 * NT + win];
+	       w.best_err   = pay [12 * NT + win];
+	       w.best_costs = m;
+	       w.min_costs  = m;
+	    }
+	    else if (first)
+	       w.index = -1;
+	    w.wave_done = !more;
+	    if (!more)
+	       w.wave_pos = D;
+	    w.st_pass2 += (unsigned) ntake;
+	 }
+      }
+      __syncthreads ();
+      if (tid == w.win)
+	 w.index = cand;
+      __syncthreads ();
+      if (w.wave_done)
+	 break;
+      m	    = w.min_costs;
+      pos   = w.wave_pos;
+      first = false;
+   }
+}
+
+/*
  *  One matching pursuit over the current pool for the range (level, image) of the block's
  *  product tree.  'mp' lives in shared memory; the work counters of the call are left in
  *  w.st_* / w.D for whoever uses the result; 'excluded' is the domain index the second_domain_block retry
@@ -1901,7 +2080,14 @@ cta_matching_pursuit (const DevParams &P, const TileWs &W, const Sh &sh, MpRes &
    int n = 0;
    for (;;)
    {
-      if (P.max_elements <= 3)
+      if (NT >= 512)		/* (the shape with an SM to itself) */
+      {
+	 if (P.max_elements <= 3)
+	    cta_mp_find_wide<NT, 2> (P, sh, mp, price, n);
+	 else
+	    cta_mp_find_wide<NT, 4> (P, sh, mp, price, n);
+      }
+      else if (P.max_elements <= 3)
 	 cta_mp_find<NT, 2> (P, sh, mp, price, n);
       else
 	 cta_mp_find<NT, 4> (P, sh, mp, price, n);

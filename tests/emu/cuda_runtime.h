@@ -100,6 +100,8 @@ static inline int min (int a, int b) { return a < b ? a : b; }
 static inline int max (int a, int b) { return a > b ? a : b; }
 static inline unsigned __float_as_uint (float f) { unsigned u; memcpy (&u, &f, 4); return u; }
 static inline float    __uint_as_float (unsigned u) { float f; memcpy (&f, &u, 4); return f; }
+static inline float    __int_as_float (int i) { float f; memcpy (&f, &i, 4); return f; }
+static inline int      __float_as_int (float f) { int i; memcpy (&i, &f, 4); return i; }
 static inline int      __clz (int x) { return x ? __builtin_clz ((unsigned) x) : 32; }
 static inline int      __popc (unsigned x) { return __builtin_popcount (x); }
 static inline int      __ffs (int x) { return __builtin_ffs (x); }
