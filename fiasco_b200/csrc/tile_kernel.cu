@@ -887,12 +887,23 @@ cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
 	 {
 	    const unsigned s	= from + item % ns;
 	    const unsigned node = node0 + item / ns;
+	    TransReg	   tr;
 
-	    if (!GP (W.domain_type) [s])
-	       continue;
-	    TransReg tr;
+	    if (CLU)
+	    {
+	       /* (the state's type and its transitions in flight together: one round trip less) */
+	       const unsigned dt = GP (W.domain_type) [s];
 
-	    load_trans (GP (W.trans) + s, tr);
+	       load_trans (GP (W.trans) + s, tr);
+	       if (!dt)
+		  continue;
+	    }
+	    else
+	    {
+	       if (!GP (W.domain_type) [s])
+		  continue;
+	       load_trans (GP (W.trans) + s, tr);
+	    }
 	    if (CLU)
 	    {
 	       /* (unconditional, independent gathers as above: one L2 round trip per item; the
