@@ -423,6 +423,9 @@ struct ShHdr
    float    spec_rbits [FB_SPINE_MAX];	/* tree bits of "subdivided" at the levels of its nodes */
    int	    pool_lo;		/* lowest pool-list entry written since the list was last posted */
    int	    tswap;		/* predicted frames: W.T and W.T2 are swapped (nested pass) */
+   /* bulk copies (cp.async.bulk, the TMA unit) of table rows into shared memory complete on this */
+   unsigned long long mbar;
+   unsigned mbar_phase;
 };
 
 static_assert (offsetof (ShHdr, tree_total) == offsetof (ShHdr, tree_counts) + FB200_MAXLEVEL * sizeof (unsigned),
@@ -712,6 +715,60 @@ async_wait_all (void)
 #ifndef FB200_EMU
    asm volatile ("cp.async.commit_group;" ::: "memory");
    asm volatile ("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
+
+/*
+ *  Bulk copies global -> shared by the TMA unit (cp.async.bulk: one instruction per row instead of
+ *  one 16-byte cp.async per thread and 16 bytes), completion through an mbarrier in shared memory.
+ *  Rows are multiples of 16 bytes, 16-byte aligned at both ends.
+ */
+__device__ __forceinline__ void
+mbar_init (unsigned long long *mbar)
+{
+#ifndef FB200_EMU
+   asm volatile ("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r" ((unsigned) __cvta_generic_to_shared (mbar)) : "memory");
+   asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
+#else
+   *mbar = 0;
+#endif
+}
+
+/* one thread: announce the bytes of the copies that follow */
+__device__ __forceinline__ void
+mbar_expect (unsigned long long *mbar, unsigned bytes)
+{
+#ifndef FB200_EMU
+   asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+		 :: "r" ((unsigned) __cvta_generic_to_shared (mbar)), "r" (bytes) : "memory");
+#endif
+}
+
+__device__ __forceinline__ void
+bulk_copy_row (float *dst_smem, const float *src, unsigned bytes, unsigned long long *mbar)
+{
+#ifdef FB200_EMU
+   memcpy (dst_smem, src, bytes);
+#else
+   asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		 :: "r" ((unsigned) __cvta_generic_to_shared (dst_smem)), "l" (src), "r" (bytes),
+		    "r" ((unsigned) __cvta_generic_to_shared (mbar)) : "memory");
+#endif
+}
+
+/* every thread: wait until the copies of the current phase have landed */
+__device__ __forceinline__ void
+mbar_wait (unsigned long long *mbar, unsigned phase)
+{
+#ifndef FB200_EMU
+   unsigned done;
+
+   do
+      asm volatile ("{\n\t.reg .pred p;\n\t"
+		    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+		    "selp.u32 %0, 1, 0, p;\n\t}"
+		    : "=r" (done) : "r" ((unsigned) __cvta_generic_to_shared (mbar)), "r" (phase) : "memory");
+   while (!done);
 #endif
 }
 
@@ -1142,6 +1199,7 @@ cta_state_products (const DevParams &P, const TileWs &W, const Sh &sh, unsigned 
       source rows of the level below can be staged */
    const int stride = (int) ((s + 1 + 3) & ~3u);
    const int NR	    = min (2 * (FB_MAXEDGES + 1), sh.scratch_len / stride);
+   unsigned  phase  = h->mbar_phase;	/* parity of the bulk copies' barrier (kept across calls) */
 
    if (tid == 0)
    {
@@ -1232,15 +1290,24 @@ cta_state_products (const DevParams &P, const TileWs &W, const Sh &sh, unsigned 
       }
       /* stage the source rows of the level below */
       const int nsrc = h->ap_nsrc < NR ? h->ap_nsrc : NR;
-      for (int j = 0; j < nsrc; j++)
+      /* rows are 16-byte aligned at both ends; the padded length stays inside the table row: one
+	 bulk copy per row, issued by thread 0, all of them in flight together */
+      if (tid == 0)
       {
-	 float	     *row = sh.num + (size_t) j * stride;
-	 const float *src = GP (W.SS) + ((size_t) (li - 1) * P.s_cap + h->ap_src [j]) * P.s_cap;
-	 /* rows are 16-byte aligned at both ends; the padded length stays inside the table row */
-	 cta_copy_f32_async<NT> (row, src, (unsigned) stride);
+#ifndef FB200_EMU	/* the scratch rows were last touched through the generic proxy (before a barrier) */
+	 asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+	 mbar_expect (&h->mbar, (unsigned) (nsrc * stride * 4));
+	 for (int j = 0; j < nsrc; j++)
+	    bulk_copy_row (sh.num + (size_t) j * stride,
+			   GP (W.SS) + ((size_t) (li - 1) * P.s_cap + h->ap_src [j]) * P.s_cap,
+			   (unsigned) stride * 4, &h->mbar);
       }
-      async_wait_all ();
-      __syncthreads ();
+      mbar_wait (&h->mbar, phase);
+      phase ^= 1u;
+#ifdef FB200_EMU
+      __syncthreads ();		/* (the emulated copies are thread 0's own stores) */
+#endif
       for (unsigned t = tid; t <= s; t += NT)
       {
 	 if (!GP (W.domain_type) [t])
@@ -1283,6 +1350,8 @@ cta_state_products (const DevParams &P, const TileWs &W, const Sh &sh, unsigned 
       __syncthreads ();
       LAP (h, LAP_AP_STAGED);
    }
+   if (tid == 0)
+      h->mbar_phase = phase;
 }
 
 /* codec/wfalib.c:154-180 */
@@ -4155,6 +4224,8 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
       h->pool_lo   = 0;
       h->spec_len  = 0;
       h->tswap	   = 0;
+      h->mbar_phase = 0;
+      mbar_init (&h->mbar);
    }
    __syncthreads ();
 
