@@ -536,6 +536,13 @@ carve (unsigned char *base, const DevParams &p, int nt, float *gglob)
 #else
 #define LAP(h, i) do { if (threadIdx.x == 0) { const long long now_ = clock64 (); (h)->lap [i] += now_ - (h)->lap_last; (h)->lap_last = now_; } } while (0)
 #endif
+#ifdef FB200_X_WAVELAPS	/* experiment: the three product buckets time the parts of a wide wave instead */
+#define LAP_W(h, i) LAP (h, i)
+#define LAP_T(h, i) LAP (h, LAP_CTRL)
+#else
+#define LAP_W(h, i) do { } while (0)
+#define LAP_T(h, i) LAP (h, i)
+#endif
 enum { LAP_CTRL, LAP_PIX, LAP_DOTS, LAP_UPSWEEP, LAP_ENTER, LAP_MP_PRO, LAP_MP_P1, LAP_MP_WAVES,
        LAP_MP_COMMIT, LAP_MP_ORTHO, LAP_AR_EPI, LAP_AP_IMG, LAP_AP_DIRECT, LAP_AP_STAGED, LAP_DECIDE, LAP_CLUSTER, LAP_N };
 
@@ -896,7 +903,7 @@ cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
       cl_sync ();
    else
       __syncthreads ();
-   LAP (sh.h, LAP_DOTS);
+   LAP_T (sh.h, LAP_DOTS);
 
    /* upsweep */
    for (int l = (P.il + 1 > P.lmin ? P.il + 1 : P.lmin); l <= level_root; l++)
@@ -1000,7 +1007,7 @@ cta_compute_T (const DevParams &P, const TileWs &W, const Sh &sh, unsigned from,
       else
 	 __syncthreads ();
    }
-   LAP (sh.h, LAP_UPSWEEP);
+   LAP_T (sh.h, LAP_UPSWEEP);
 }
 
 /* codec/subdivide.c:612-644 (init_range) + :504-541 (cut_to_bintree) */
@@ -1065,7 +1072,7 @@ cta_init_range (const DevParams &P, const TileWs &W, const Sh &sh, unsigned x0,
       sh.h->blocks++;
       sh.h->ip_bytes += 4ull * size + 4ull * (63 + (unsigned) ((1 << (P.lc_max - P.il)) - 1)) * ns;
    }
-   LAP (sh.h, LAP_PIX);
+   LAP_T (sh.h, LAP_PIX);
    cta_compute_T<NT, CLU> (P, W, sh, 0, 0, P.lc_max, P.lc_max, g0, gnt);
 }
 
@@ -1943,6 +1950,7 @@ cta_mp_find_wide (const DevParams &P, const Sh &sh, MpRes &mp, float price, int 
       if (base > NT)
 	 more = true;
       const int ntake = base < NT ? base : NT;
+      LAP_W (sh.h, LAP_PIX);		/* barrier + scan */
 
       if (tid < ntake)
       {
@@ -1965,7 +1973,9 @@ cta_mp_find_wide (const DevParams &P, const Sh &sh, MpRes &mp, float price, int 
 	 if (more && tid == ntake - 1)
 	    w.wave_pos = cand + 1;
       }
+      LAP_W (sh.h, LAP_DOTS);		/* thread 0's own candidate */
       __syncthreads ();
+      LAP_W (sh.h, LAP_UPSWEEP);	/* waiting for the other candidates */
       if (warp == 0)
       {
 	 int win = -1;
@@ -2855,6 +2865,19 @@ enum { ST_CHILD_T = 16, ST_CHILD2 = 17,
 
 /* where the activation record at 'depth' leaves its range: the parent's child slot, the root
    range, or -- for the root of a nested pass -- the prediction range of the record below */
+/* (the records are addressed through the Sh copy in registers where one is at hand: the pointers
+   in the header cost a shared-memory load each on thread 0's path) */
+template <bool MOTION>
+__device__ __forceinline__ RangeRes *
+res_slot (const Sh &sh, int depth)
+{
+   if (depth == 0)
+      return &sh.h->root;
+   if (MOTION && depth == sh.h->nest_base)
+      return &sh.fx [depth - 1].prange;
+   return &sh.frames [depth - 1].child [sh.frames [depth - 1].label];
+}
+
 template <bool MOTION>
 __device__ __forceinline__ RangeRes *
 res_slot (ShHdr *h, int depth)
@@ -2985,11 +3008,11 @@ t0_advance (const DevParams &P, const TileWs &W, const Sh &sh, int &state, int &
 
    for (;;)
    {
-      Frame &F = h->frames [depth];
+      Frame &F = sh.frames [depth];
 
       if (state == ST_ENTER)
       {
-	 RangeRes *res = res_slot<MOTION> (h, depth);
+	 RangeRes *res = res_slot<MOTION> (sh, depth);
 
 	 res->into [0] = FB_NO_EDGE;
 	 res->tree     = FB_RANGE;
@@ -3010,7 +3033,7 @@ t0_advance (const DevParams &P, const TileWs &W, const Sh &sh, int &state, int &
 
 	    if (MOTION && h->nest_base >= 0 && depth >= h->nest_base)
 	       cs.blob = sh.blob + P.blob_half;
-	    t0_enter_speculated<MOTION> (P, W, cs, F, MOTION ? &h->fx [depth] : (FrameX *) 0, res, state);
+	    t0_enter_speculated<MOTION> (P, W, cs, F, MOTION ? &sh.fx [depth] : (FrameX *) 0, res, state);
 	 }
 	 else
 	    return;
@@ -3028,14 +3051,14 @@ t0_advance (const DevParams &P, const TileWs &W, const Sh &sh, int &state, int &
 	    state = ST_PRED_DONE;
 	    return;
 	 }
-	 h->frames [depth - 1].subdivide_costs += h->ret_costs;
+	 sh.frames [depth - 1].subdivide_costs += h->ret_costs;
 	 depth--;
 	 state = ST_AFTER_CHILD;
       }
       else if (state == ST_AFTER_CHILD)
       {
 	 /* update_norms_table (prediction.c:213-238) */
-	 if (MOTION && h->fx [depth].try_mc && F.level > P.p_min)
+	 if (MOTION && sh.fx [depth].try_mc && F.level > P.p_min)
 	 {
 	    state = ST_NORMS_UP;
 	    return;
@@ -3073,8 +3096,8 @@ t0_advance (const DevParams &P, const TileWs &W, const Sh &sh, int &state, int &
 	 F.r_weights_bits += c.weights_bits;
 	 if (MOTION)
 	 {
-	    h->fx [depth].r_mvt += h->fx [depth].child [label].mv_tree_bits;
-	    h->fx [depth].r_mvc += h->fx [depth].child [label].mv_coord_bits;
+	    sh.fx [depth].r_mvt += sh.fx [depth].child [label].mv_tree_bits;
+	    sh.fx [depth].r_mvc += sh.fx [depth].child [label].mv_coord_bits;
 	 }
 	 /* tree_update (bintree.c:35-53); the prediction tree model (subdivide.c:372) is never
 	    read by the coder and is not kept */
@@ -3110,7 +3133,7 @@ t0_advance (const DevParams &P, const TileWs &W, const Sh &sh, int &state, int &
 	 F.child [label].y = (unsigned short) cy;
 	 if (remaining > 0)
 	 {
-	    Frame &C = h->frames [depth + 1];
+	    Frame &C = sh.frames [depth + 1];
 
 	    C.max_costs = remaining;
 	    C.x		= cx;
@@ -3124,13 +3147,13 @@ t0_advance (const DevParams &P, const TileWs &W, const Sh &sh, int &state, int &
 	    C.spec_k	= (label == 0 && F.spec_k >= 0 && F.spec_k + 1 < h->spec_len) ? F.spec_k + 1 : -1;
 	    if (MOTION)
 	    {
-	       h->fx [depth + 1].delta	    = h->fx [depth].delta;
-	       h->fx [depth + 1].prediction = h->fx [depth].prediction;
+	       sh.fx [depth + 1].delta	    = sh.fx [depth].delta;
+	       sh.fx [depth + 1].prediction = sh.fx [depth].prediction;
 	    }
 	    depth++;
 	    state = ST_ENTER;
 	 }
-	 else if (MOTION && h->fx [depth].try_mc && level - 1 >= P.p_min)
+	 else if (MOTION && sh.fx [depth].try_mc && level - 1 >= P.p_min)
 	 {
 	    state = ST_FILL_CHILD;	/* subdivide.c:331-333: the child's norms are still needed */
 	    return;
