@@ -384,6 +384,10 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", 0))
     if not torch.cuda.is_available() or F.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback)")
+    if world > 1 and "FIASCO_HOST_THREADS" not in os.environ:
+        # the ranks of one box share its cores: the library's host threads (PNM readers, stream writers) are dealt out
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        os.environ["FIASCO_HOST_THREADS"] = str(max(2, min(16, cores // world)))
     local = 0                                       # CUDA_VISIBLE_DEVICES holds this rank's GPU only
     torch.cuda.set_device(local)
     sms = torch.cuda.get_device_properties(local).multi_processor_count

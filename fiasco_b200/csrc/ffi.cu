@@ -454,7 +454,8 @@ ctx_alloc (fb200_ctx_t *c, char *err, size_t errlen)
    c->dp.n_slots    = c->n_slots;
    c->dp.slot_flags = c->d_slot_flags;
    CUDA_TRY (cudaMalloc (&c->d_wfa, c->wfa_block * max_tiles));
-   CUDA_TRY (cudaMallocHost (&c->h_wfa, c->wfa_block * max_tiles));
+   c->h_wfa = NULL;		/* pinned staging of the automata: allocated by the first download, so that
+				   a context can be set up beside host threads that fault pages in */
    if (!c->d_pix)
    {
       CUDA_TRY (cudaMalloc (&c->d_pix, c->pix_elems * 2 * max_tiles));
@@ -719,6 +720,8 @@ fb200_download (fb200_ctx_t *c, int n_tiles, fb200_wfa_t *out, fb200_trace_rec_t
    CUDA_TRY (cudaEventRecord (c->ev [4], s));
    CUDA_TRY (cudaMemcpyAsync (c->h_results, c->d_results, sizeof (TileResult) * n_tiles,
 			      cudaMemcpyDeviceToHost, s));
+   if (!c->h_wfa)
+      CUDA_TRY (cudaMallocHost (&c->h_wfa, c->wfa_block * c->max_tiles));
    CUDA_TRY (cudaMemcpyAsync (c->h_wfa, c->d_wfa, c->wfa_block * n_tiles,
 			      cudaMemcpyDeviceToHost, s));
    CUDA_TRY (cudaEventRecord (c->ev [5], s));

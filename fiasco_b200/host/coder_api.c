@@ -487,6 +487,8 @@ static struct
    unsigned	       prep_tiles;
    pthread_t	       prep_thread;
    int		       prep_running;
+   pthread_t	       release_thread;
+   int		       release_running;
    fi_bits_t	     **frame_bits;	/* the frames' own bit streams until they are joined */
    size_t	       n_frame_bits;
 } job;
@@ -511,11 +513,28 @@ prepare_contexts (void *arg)
    return NULL;
 }
 
+static void *
+release_contexts (void *arg)
+{
+   (void) arg;
+   for (unsigned g = 0; g < FI_MAXGPUS; g++)
+      for (int t = 0; t < 3; t++)
+	 if (job.gpus [g].ctx [t])
+	 {
+	    fb200_destroy (job.gpus [g].ctx [t]);
+	    job.gpus [g].ctx [t] = NULL;
+	 }
+   return NULL;
+}
+
 static void
 job_release (void)
 {
    if (job.prep_running)
       pthread_join (job.prep_thread, NULL);
+   if (job.release_running)
+      pthread_join (job.release_thread, NULL);
+   job.prep_running = job.release_running = 0;
    for (unsigned g = 0; g < FI_MAXGPUS; g++)
       for (int t = 0; t < 3; t++)
 	 if (job.gpus [g].ctx [t])
@@ -1055,13 +1074,11 @@ coder (char const *const *inputname, const char *outputname, float quality,
 	 }
    }
    phase_clock ("launches (contexts, copies)");
-   for (unsigned g = 0; g < job.n_gpus; g++)	/* the device memory is not needed any longer */
-      for (int t = 0; t < 3; t++)
-	 if (job.gpus [g].ctx [t])
-	 {
-	    fb200_destroy (job.gpus [g].ctx [t]);
-	    job.gpus [g].ctx [t] = NULL;
-	 }
+   /* the device memory is not needed any longer: it is handed back beside the stream writer */
+   if (pthread_create (&job.release_thread, NULL, release_contexts, NULL) == 0)
+      job.release_running = 1;
+   else
+      release_contexts (NULL);
 
    phase_clock ("contexts released");
    /* the streams: every frame is coded into a bit stream of its own on the host threads, then
@@ -1103,6 +1120,11 @@ coder (char const *const *inputname, const char *outputname, float quality,
       job.output = NULL;
       free (job.tile_name);
       job.tile_name = NULL;
+   }
+   if (job.release_running)
+   {
+      pthread_join (job.release_thread, NULL);
+      job.release_running = 0;
    }
    phase_clock ("streams written");
    (void) n_predicted;
