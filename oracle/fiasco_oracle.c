@@ -1945,6 +1945,119 @@ mc_prediction (float max_costs, float price, unsigned band, int y_state, range_t
    return costs;
 }
 
+/* nd_prediction (prediction.c:371-500): an intra frame coded with `--prediction': the range is
+   predicted by its DC component (state 0, weight quantised with the DC format) and the
+   difference is subdivided with the delta models; taken only if the difference is split */
+static int nd_prediction_on = 0;
+
+void
+fo_set_nd_prediction (int on)
+{
+   nd_prediction_on = on;
+}
+
+static float
+nd_prediction (float max_costs, float price, unsigned band, int y_state, range_t *range,
+	       coder_t *c)
+{
+   fo_wfa_t *w	    = c->wfa;
+   range_t   lrange = *range;
+   float     costs;
+
+   {
+      const float   x	  = get_ip_image_state (range->image, range->address, range->level, 0, c);
+      const float   y	  = get_ip_state_state (0, 0, range->level, c);
+      const float   wt	  = btor (rtob (x / y, &c->dc_rpf), &c->dc_rpf);
+      const int16_t s [2] = {0, -1};
+
+      lrange.into [0]	     = 0;
+      lrange.into [1]	     = NO_EDGE;
+      lrange.weight [0]	     = wt;
+      lrange.mv_coord_bits   = 0;
+      lrange.mv_tree_bits    = 0;
+      lrange.nd_tree_bits    = tree_bits (0, lrange.level, &c->p_tree);
+      lrange.nd_weights_bits = 0;
+      lrange.tree_bits	     = 0;
+      lrange.matrix_bits     = 0;
+      lrange.weights_bits    = aac_bits (&wt, s, range->level, &c->coeff);
+   }
+   costs = price * (lrange.weights_bits + lrange.nd_tree_bits);
+
+   if (costs < max_costs)
+   {
+      const unsigned width = width_of_level (range->level), height = height_of_level (range->level);
+      const unsigned last_state = w->states - 1;
+      float	    *rec_pixels = c->pixels;
+      float	   **ipi	= calloc (MAXSTATES, sizeof (float *));
+      float	    *pixels	= calloc ((size_t) width * height, sizeof (float));
+      range_t	     rrange;
+
+      {
+	 const float  dc  = -lrange.weight [0] * c->images_of_state [0][0];
+	 const float *src = c->pixels + (size_t) range->address * size_of_level (range->level);
+
+	 for (unsigned n = 0; n < width * height; n++)
+	    pixels [n] = src [n] + dc;
+      }
+      c->pixels		     = pixels;
+      rrange		     = *range;
+      rrange.tree_bits	     = 0;
+      rrange.matrix_bits     = 0;
+      rrange.weights_bits    = 0;
+      rrange.mv_coord_bits   = 0;
+      rrange.mv_tree_bits    = 0;
+      rrange.nd_tree_bits    = 0;
+      rrange.nd_weights_bits = 0;
+      rrange.image	     = 0;
+      rrange.address	     = 0;
+      for (unsigned state = 0; state <= last_state; state++)
+	 if (need_image (state, w))
+	 {
+	    ipi [state]		       = c->ip_images_state [state];
+	    c->ip_images_state [state] = calloc (size_of_tree (c->products_level), sizeof (float));
+	 }
+      compute_ip_images_state (rrange.image, rrange.address, rrange.level, 1, 0, c);
+      costs += subdivide (max_costs - costs, band, y_state, &rrange, c, 0, 1);
+
+      if (costs < max_costs && rrange.tree != RANGE)
+      {
+	 const unsigned img = range->image, adr = range->address;
+	 unsigned	edge;
+
+	 *range			 = rrange;
+	 range->image		 = img;
+	 range->address		 = adr;
+	 range->nd_tree_bits	+= lrange.nd_tree_bits;
+	 range->nd_weights_bits += lrange.weights_bits;
+	 for (edge = 0; lrange.into [edge] != NO_EDGE; edge++)
+	 {
+	    range->into [edge]	 = lrange.into [edge];
+	    range->weight [edge] = lrange.weight [edge];
+	 }
+	 range->into [edge] = NO_EDGE;
+	 range->prediction  = (int) edge;
+	 for (unsigned state = last_state + 1; state < w->states; state++)
+	    if (need_image (state, w))
+	       memset (c->ip_images_state [state], 0,
+		       size_of_tree (c->products_level) * sizeof (float));
+      }
+      else
+	 costs = MAXCOSTS;
+      for (unsigned state = 0; state <= last_state; state++)
+	 if (need_image (state, w))
+	 {
+	    free (c->ip_images_state [state]);
+	    c->ip_images_state [state] = ipi [state];
+	 }
+      free (ipi);
+      free (pixels);
+      c->pixels = rec_pixels;
+   }
+   else
+      costs = MAXCOSTS;
+   return costs;
+}
+
 /*
  *  Design check for the device: with holes_mode set, predict_range keeps
  *  the split alternative's states where they are instead of moving them aside -- the
@@ -1993,7 +2106,8 @@ predict_range_holes (float max_costs, float price, range_t *range, coder_t *c, u
    c->coeff.model   = *coeff_model;
    c->d_coeff.model = *d_coeff_model;
 
-   costs = mc_prediction (max_costs, price, band, y_state, range, c);
+   costs = c->frame_type == 0 ? nd_prediction (max_costs, price, band, y_state, range, c)
+			      : mc_prediction (max_costs, price, band, y_state, range, c);
 
    if (costs < MAXCOSTS)
    {
@@ -2120,7 +2234,8 @@ predict_range (float max_costs, float price, range_t *range, coder_t *c, unsigne
    c->coeff.model   = *coeff_model;
    c->d_coeff.model = *d_coeff_model;
 
-   costs = mc_prediction (max_costs, price, band, y_state, range, c);
+   costs = c->frame_type == 0 ? nd_prediction (max_costs, price, band, y_state, range, c)
+			      : mc_prediction (max_costs, price, band, y_state, range, c);
 
    if (costs < MAXCOSTS)
    {
@@ -2159,7 +2274,7 @@ subdivide (float max_costs, unsigned band, int y_state, range_t *range,
    float	subdivide_costs, lincomb_costs, price;
    int		new_y_state [MAXLABELS];
    unsigned	states;
-   int		try_mc;
+   int		try_mc, try_nd;
    rle_model_t *domain_model, *lc_domain_model, *d_domain_model, *lc_d_domain_model;
    aac_model_t	coeff_model, lc_coeff_model, d_coeff_model, lc_d_coeff_model;
    tree_model_t tree_model, p_tree_model;
@@ -2178,6 +2293,8 @@ subdivide (float max_costs, unsigned band, int y_state, range_t *range,
 	     && range->level >= c->p_min_level && range->level <= c->p_max_level
 	     && range->x + width_of_level (range->level) <= (unsigned) c->opt.width
 	     && range->y + height_of_level (range->level) <= (unsigned) c->opt.height);
+   try_nd = (prediction && c->frame_type == 0
+	     && range->level >= c->p_min_level && range->level <= c->p_max_level);
    if (try_mc)
       clear_norms_table (range->level, c);
 
@@ -2277,7 +2394,7 @@ subdivide (float max_costs, unsigned band, int y_state, range_t *range,
       rrange.err	     = 0;
       rrange.mv_tree_bits    = try_mc ? 1 : 0;
       rrange.mv_coord_bits   = 0;
-      rrange.nd_tree_bits    = 0;
+      rrange.nd_tree_bits    = try_nd ? tree_bits (1, lrange.level, &c->p_tree) : 0;
       rrange.nd_weights_bits = 0;
       rrange.prediction	     = 0;
       subdivide_costs = (rrange.tree_bits + rrange.weights_bits
@@ -2336,7 +2453,7 @@ subdivide (float max_costs, unsigned band, int y_state, range_t *range,
 
    /* alternative 3: motion compensation + approximation of the prediction error
       (subdivide.c:383-407) */
-   if (try_mc)
+   if (try_mc || try_nd)
    {
       const float prediction_costs
 	 = predict_range (fmin2 (fmin2 (lincomb_costs, subdivide_costs), max_costs), price,
@@ -3252,7 +3369,7 @@ fo_encode_video (const fo_params_t *p, int n_frames, const int16_t *const *frame
 	 init_tree_model (&c->p_tree);
 	 rle_init (&c->pool, (unsigned) c->opt.max_states);
 	 rle_init (&c->d_pool, (unsigned) c->opt.max_states);
-	 c->d_pool_is_rle = type != 0;
+	 c->d_pool_is_rle = type != 0 || nd_prediction_on;	/* coder.c:720-725 */
 	 for (state = 0; state < w->basis_states; state++)
 	    if (usedomain (state, w))
 	    {
@@ -3269,7 +3386,7 @@ fo_encode_video (const fo_params_t *p, int n_frames, const int16_t *const *frame
 
 	 memset (&range, 0, sizeof range);
 	 range.level = c->level;
-	 w->costs [0] = subdivide (MAXCOSTS, 0, RANGE, &range, c, type != 0, 0);
+	 w->costs [0] = subdivide (MAXCOSTS, 0, RANGE, &range, c, type != 0 || nd_prediction_on, 0);
 	 if (range.tree == RANGE)
 	    fail (c, "No root state generated!");
 	 w->root_state	     = (unsigned) range.tree;

@@ -155,6 +155,10 @@ int fo_encode_video (const fo_params_t *p, int n_frames, const int16_t *const *f
 void fo_fill_norms_table (const int16_t *orig, const int16_t *past, unsigned width, unsigned height,
 			  unsigned x0, unsigned y0, unsigned level, unsigned search_range, float *out);
 
+/* `cfiasco --prediction' (fiasco_c_options_set_prediction): the intra frames of fo_encode_video try
+   the nondeterministic prediction of codec/prediction.c:371 (DC component + delta image) */
+void fo_set_nd_prediction (int on);
+
 /* design check of the device's state handling for predicted frames (see fiasco_oracle.c) */
 void fo_set_holes_mode (int on);
 void fo_close_holes (fo_wfa_t *wfa);
