@@ -271,10 +271,11 @@ derive (const fb200_params_t *p, const fb200_motion_t *mo, DevParams *d, char *e
    d->s_cap = p->state_capacity > 0 ? p->state_capacity : default_capacity (p);
    if (mo && mo->frame_type)
    {
-      if (mo->frame_type < 1 || mo->frame_type > 2 || p->bands != 1 || mo->search_range < 1
+      if (mo->frame_type < 1 || mo->frame_type > FB200_FRAME_ND || p->bands != 1 || mo->search_range < 1
 	  || mo->search_range > 16)
       {
-	 set_err (err, errlen, "predicted frames: P and B frames of grey sequences, search range 1..16");
+	 set_err (err, errlen, "predicted frames: P and B frames (or intra frames with nondeterministic "
+		  "prediction) of grey sequences, search range 1..16");
 	 return FB200_EUNSUPPORTED;
       }
       /* prediction levels are a subset of the range levels (coder.c:284-290) */
@@ -933,8 +934,8 @@ fb200_encode_predicted (fb200_ctx_t *c, int n_tiles, const int16_t *const *plane
 {
    int rc;
 
-   if (!c || !c->dp.motion || !past || n_tiles < 1 || n_tiles > c->max_tiles
-       || (c->dp.motion == 2 && !future))
+   if (!c || !c->dp.motion || (!past && c->dp.motion != FB200_FRAME_ND) || n_tiles < 1
+       || n_tiles > c->max_tiles || (c->dp.motion == 2 && !future))
    {
       set_err (err, errlen, "fb200_encode_predicted: needs a context of fb200_create_predicted() "
 	       "and one reference frame per tile (two for B frames)");
@@ -943,7 +944,7 @@ fb200_encode_predicted (fb200_ctx_t *c, int n_tiles, const int16_t *const *plane
    c->dp.trace_cap = 0;
    if ((rc = fb200_upload (c, n_tiles, planes, err, errlen)))
       return rc;
-   for (int t = 0; t < n_tiles; t++)
+   for (int t = 0; t < n_tiles && c->dp.motion != FB200_FRAME_ND; t++)
       {
       CUDA_TRY (cudaMemcpyAsync (c->d_past + c->pix_elems * t, past [t], c->pix_elems * 2,
 				 cudaMemcpyHostToDevice, c->stream));
@@ -952,8 +953,8 @@ fb200_encode_predicted (fb200_ctx_t *c, int n_tiles, const int16_t *const *plane
 				    cudaMemcpyHostToDevice, c->stream));
    }
    CUDA_TRY (cudaStreamSynchronize (c->stream));
-   c->stats.h2d_bytes += c->pix_elems * 2 * n_tiles * (c->dp.motion == 2 ? 2 : 1);
-   count_work (0, 0, c->pix_elems * 2 * n_tiles * (c->dp.motion == 2 ? 2 : 1), 0);
+   c->stats.h2d_bytes += c->pix_elems * 2 * n_tiles * (c->dp.motion == 2 ? 2 : c->dp.motion == 1 ? 1 : 0);
+   count_work (0, 0, c->pix_elems * 2 * n_tiles * (c->dp.motion == 2 ? 2 : c->dp.motion == 1 ? 1 : 0), 0);
    float total_ms = 0;
    int	 launches = 0;
    for (;;)

@@ -299,6 +299,8 @@ struct FrameX
    RangeRes prange;		/* result of the nested pass over the prediction error */
    float    r_mvt, r_mvc;	/* rrange sums of the motion bits */
    int	    try_mc;		/* subdivide.c:141-147 */
+   int	    try_nd;		/* subdivide.c:149-151: an intra frame coded with `--prediction' */
+   float    ndw;		/* weight of the DC component that predicts the range (prediction.c:385) */
    int	    delta, prediction;	/* arguments of subdivide () */
    int	    pred_done;		/* the prediction alternative has been tried (and lost) */
    unsigned rec_states;		/* states after the first two alternatives */
@@ -553,9 +555,19 @@ enum { ST_ENTER, ST_CHILD, ST_AFTER_CHILD, ST_DECIDE, ST_RETURN, ST_DONE, ST_ABO
 *****************************************************************************/
 
 /* codec/bintree.c:55-68 */
+/* (the kernel of predicted frames keeps the prediction tree model, c->p_tree, in the upper halves
+   of the same words: one snapshot holds both; a level's counts stay below 2 * FB200_MAXSTATES) */
 __device__ float t0_tree_bits (const ShHdr *h, int child, int level)
 {
-   float prob = h->tree_counts [level] / (float) h->tree_total [level];
+   float prob = (h->tree_counts [level] & 0xffffu) / (float) (h->tree_total [level] & 0xffffu);
+
+   return child ? neg_log2f_via_double (prob) : neg_log2f_via_double (1 - prob);
+}
+
+/* the same for the prediction tree model (subdivide.c:259-260, prediction.c:391) */
+__device__ float t0_ptree_bits (const ShHdr *h, int child, int level)
+{
+   float prob = (h->tree_counts [level] >> 16) / (float) (h->tree_total [level] >> 16);
 
    return child ? neg_log2f_via_double (prob) : neg_log2f_via_double (1 - prob);
 }
@@ -2708,6 +2720,29 @@ cta_mcpe_range (const DevParams &P, const TileWs &W, const Sh &cs, unsigned x0, 
    }
 }
 
+/*
+ *  nd_prediction (prediction.c:409-421): the difference between the range and its DC prediction
+ *  becomes the pixel block of the nested pass.  src: the range inside the outer block (bintree
+ *  order); dc = -weight * images_of_state [0][0].  The differences are no integers: the node norms
+ *  of the nested pass are the reference's left-to-right fp32 sums (t0_node_norm's long form, the
+ *  integer table holds a value beyond its limit).
+ */
+template <int NT>
+__device__ void
+cta_nd_range (const DevParams &P, const TileWs &W, const Sh &outer, const Sh &cs, unsigned address,
+	      int level, float dc)
+{
+   const int	  tid  = threadIdx.x;
+   const unsigned size = 1u << level;
+   const float	 *src  = outer.pixels + ((size_t) address << level);
+
+   for (unsigned i = tid; i < size; i += NT)
+      cs.pixels [i] = src [i] + dc;
+   for (unsigned k = tid; k < (2u << (level - P.lmin)) - 1; k += NT)
+      cs.norm_i [k] = 0x7fffffff;
+   __syncthreads ();
+}
+
 /*****************************************************************************
 			  cluster per stream: jobs
 *****************************************************************************/
@@ -2937,6 +2972,7 @@ t0_enter_speculated (const DevParams &P, const TileWs &W, const Sh &sh, Frame &F
       /* what ST_ENTER sets up for the motion compensated alternative (subdivide.c:141-147) */
       mvt	   = h->job.node [k].mv_tree_bits;
       X->try_mc	   = mvt != 0.0f;
+      X->try_nd	   = 0;		/* (no spines where nondeterministic prediction is tried) */
       X->pred_done = 0;
       X->lrange.mv_tree_bits  = mvt;
       X->lrange.mv_coord_bits = 0;
@@ -3099,11 +3135,17 @@ t0_advance (const DevParams &P, const TileWs &W, const Sh &sh, int &state, int &
 	    sh.fx [depth].r_mvt += sh.fx [depth].child [label].mv_tree_bits;
 	    sh.fx [depth].r_mvc += sh.fx [depth].child [label].mv_coord_bits;
 	 }
-	 /* tree_update (bintree.c:35-53); the prediction tree model (subdivide.c:372) is never
-	    read by the coder and is not kept */
+	 /* tree_update (bintree.c:35-53) of the tree model and of the prediction tree model
+	    (subdivide.c:370-373), which only nondeterministic prediction reads */
 	 if (c.tree != FB_RANGE)
 	    h->tree_counts [F.level - 1]++;
 	 h->tree_total [F.level - 1]++;
+	 if (MOTION)
+	 {
+	    if (!sh.fx [depth].child [label].prediction)
+	       h->tree_counts [F.level - 1] += 0x10000u;
+	    h->tree_total [F.level - 1] += 0x10000u;
+	 }
 	 F.label = label + 1;
 	 if (F.label >= 2)
 	 {
@@ -3322,12 +3364,19 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 		  FrameX &X = h->fx [depth];
 
 		  /* motion compensation allowed for this range? (subdivide.c:141-147) */
-		  X.try_mc = X.prediction && level >= P.p_min && level <= P.p_max
+		  X.try_mc = P.motion != 3 && X.prediction && level >= P.p_min && level <= P.p_max
 			     && F.x + width_of_level (level) <= (unsigned) P.width
 			     && F.y + height_of_level (level) <= (unsigned) P.height;
+		  /* an intra frame with nondeterministic prediction (subdivide.c:149-151).  Its bits
+		     travel in the motion fields, which are zero in such a frame: nd_tree_bits in
+		     mv_tree_bits, nd_weights_bits in mv_coord_bits (the sums of cwfa.h's seven bit
+		     counts are the same numbers: adding 0 is exact) */
+		  X.try_nd = P.motion == 3 && X.prediction && level >= P.p_min && level <= P.p_max;
 		  X.pred_done = 0;
 		  mvt	      = X.try_mc ? 1.0f : 0.0f;	/* mc allowed but not used */
 		  X.lrange.mv_tree_bits	 = mvt;
+		  if (X.try_nd)
+		     mvt = t0_ptree_bits (h, 1, level);	/* rrange.nd_tree_bits (subdivide.c:259-260) */
 		  X.lrange.mv_coord_bits = 0;
 		  X.lrange.mv_type = X.lrange.mv_fx = X.lrange.mv_fy = X.lrange.prediction = 0;
 		  X.lrange.mv_bx = X.lrange.mv_by = 0;
@@ -3385,7 +3434,8 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 	       const int       sk    = CL ? F.spec_k : 0;
 	       bool	       spine = false;
 
-	       if (CL && sk < 0 && F.y_state < 0 && !P.second_domain_block)
+	       if (CL && sk < 0 && F.y_state < 0 && !P.second_domain_block
+		   && !(MOTION && P.motion == 3 && h->fx [depth].prediction))
 	       {
 		  /*
 		   *  Head of a spine: the ranges reached from here by label 0 alone, down to
@@ -3581,7 +3631,9 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 	       short	  *snap	 = (sh.snaps ? sh.snaps : GP (W.snap)) + (size_t) depth * SN * P.blob_len;
 	       unsigned	  *tsnap = sh.tsnap + (size_t) depth * TS * 2 * FB200_MAXLEVEL;
 	       const float costs = X.pcosts + h->ret_costs;
-	       const bool  win	 = costs < X.max_pred;
+	       /* (nondeterministic prediction is only taken with a subdivided difference,
+		  prediction.c:447) */
+	       const bool  win	 = costs < X.max_pred && !(X.try_nd && X.prange.tree == FB_RANGE);
 
 	       __syncthreads ();
 	       if (tid == 0)
@@ -3632,6 +3684,13 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 		     rx->mv_bx	       = (signed char) (X.mctype != 1 ? X.bx : 0);
 		     rx->mv_by	       = (signed char) (X.mctype != 1 ? X.by : 0);
 		     rx->prediction    = 1;
+		     if (X.try_nd)		/* the predicting edge: state 0 (prediction.c:458-465) */
+		     {
+			res->into [0]	= 0;
+			res->into [1]	= FB_NO_EDGE;
+			res->weight [0] = X.ndw;
+			rx->mv_type	= 0;
+		     }
 		     h->ret_costs = (res->tree_bits + res->matrix_bits + res->weights_bits
 				     + rx->mv_tree_bits + rx->mv_coord_bits + 0.0f + 0.0f) * h->price
 				    + res->err;
@@ -3682,7 +3741,7 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 	    short      *snap  = (sh.snaps ? sh.snaps : GP (W.snap)) + (size_t) depth * SN * P.blob_len;
 	    unsigned   *tsnap = sh.tsnap + (size_t) depth * TS * 2 * FB200_MAXLEVEL;
 
-	    if (MOTION && h->fx [depth].try_mc && !h->fx [depth].pred_done)
+	    if (MOTION && (h->fx [depth].try_mc || h->fx [depth].try_nd) && !h->fx [depth].pred_done)
 	    {
 	       /* alternative 3: motion compensation + approximation of the prediction error
 		  (subdivide.c:383-407, predict_range prediction.c:96-191, mc_prediction :262-370) */
@@ -3716,6 +3775,29 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 		  X.max_pred   = fmin2 (fmin2 (lin, sub), F.max_costs);
 	       }
 	       __syncthreads ();
+	       if (X.try_nd)
+	       {
+		  /* nd_prediction (prediction.c:371-400): the range's DC component, quantised with the
+		     DC format, priced by the coefficient model of the node's entry and by the
+		     prediction tree model */
+		  if (tid == 0)
+		  {
+		     const float  x	 = GP (W.T) [(size_t) F.image * P.s_cap];
+		     const float  y	 = GP (W.diag) [(size_t) (level - P.lmin) * P.s_cap];
+		     const float  wt	 = dev_btor (dev_rtob (x / y, P.dc_m, P.dc_range), P.dc_m, P.dc_range);
+		     const short *counts = sh.blob + MB_COUNTS;
+		     const int	  code	 = dev_rtob (wt, P.dc_m, P.dc_range);
+
+		     X.ndw    = wt;
+		     X.mctype = 0;
+		     X.mx = X.my = X.bx = X.by = 0;
+		     X.mvt    = t0_ptree_bits (h, 0, level);
+		     X.mvc    = (float) (0.0 - dev_log2d (counts [code] / (float) sh.blob [MB_TOTALS]));
+		     X.pcosts = h->price * (X.mvc + X.mvt);
+		  }
+	       }
+	       else
+	       {
 	       if (level == P.p_min)
 		  cta_fill_norms<NT> (P, W, F.x, F.y, level);
 	       cta_find_best_mv<NT> (P, W, sh, F.x, F.y, level, h->price, 0);
@@ -3724,7 +3806,10 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 		  h->fi	    = h->best_i;
 		  h->fcosts = h->best_c;
 	       }
-	       if (P.motion == 2)
+	       }
+	       if (X.try_nd)
+		  ;
+	       else if (P.motion == 2)
 	       {
 		  /* find_B_frame_mc (mwfa.c:341-542) without cross-B search: the best forward vector,
 		     the best backward vector, and both together */
@@ -3826,7 +3911,10 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 	       {
 		  /* the prediction error replaces the pixels, fresh product tables, and
 		     subdivide() on it with the delta models */
-		  cta_mcpe_range<NT> (P, W, shn, F.x, F.y, level, X.mctype, X.mx, X.my, X.bx, X.by);
+		  if (X.try_nd)
+		     cta_nd_range<NT> (P, W, sh, shn, F.address, level, -X.ndw * GP (W.img) [0]);
+		  else
+		     cta_mcpe_range<NT> (P, W, shn, F.x, F.y, level, X.mctype, X.mx, X.my, X.bx, X.by);
 		  if (tid == 0)
 		  {
 		     float *t = W.T;
@@ -4281,8 +4369,8 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
 					       10, 15, 20, 25, 30, 35, 60, 60, 60, 60};
 	 for (int l = 0; l < FB200_MAXLEVEL; l++)
 	 {
-	    h->tree_counts [l] = c1 [l];
-	    h->tree_total [l]  = c0 [l] + c1 [l];
+	    h->tree_counts [l] = MOTION ? c1 [l] * 0x10001u : c1 [l];
+	    h->tree_total [l]  = MOTION ? (c0 [l] + c1 [l]) * 0x10001u : c0 [l] + c1 [l];
 	 }
       }
       for (int i = tid; i < P.blob_len; i += NT)

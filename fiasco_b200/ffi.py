@@ -261,12 +261,15 @@ class TileEncoder:
 
     def encode_predicted(self, planes, past, future=None):
         """One predicted frame per tile: planes[t] the frame, past[t] the regenerated previous frame
-        (future[t]: the regenerated next reference, B frames)."""
+        (future[t]: the regenerated next reference, B frames).  past=None: an intra frame with
+        nondeterministic prediction (a context of frame type FB200_FRAME_ND = 3)."""
         n_tiles = len(planes)
         ptrs = self._plane_ptrs(planes)
         keep = [self._keep]
-        pptrs = self._plane_ptrs(past)
-        keep.append(self._keep)
+        pptrs = None
+        if past is not None:
+            pptrs = self._plane_ptrs(past)
+            keep.append(self._keep)
         fptrs = None
         if future is not None:
             fptrs = self._plane_ptrs(future)

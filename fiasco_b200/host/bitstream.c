@@ -32,13 +32,14 @@ fi_bits_open (const char *filename)
 /* a stream that is not tied to a file: frames are coded side by side into streams of their own
    and appended to the output in coding order (fi_bits_append) */
 fi_bits_t *
-fi_bits_open_mem (void)
+fi_bits_open_mem (unsigned phase)
 {
    fi_bits_t *b = fiasco_calloc (1, sizeof (fi_bits_t));
 
-   b->file = NULL;
-   b->cap  = 1 << 14;
-   b->buf  = fiasco_calloc (b->cap, 1);
+   b->file  = NULL;
+   b->cap   = 1 << 14;
+   b->buf   = fiasco_calloc (b->cap, 1);
+   b->nbits = b->skip = phase & 7;
    return b;
 }
 
@@ -55,7 +56,7 @@ fi_bits_free_mem (fi_bits_t *b)
 void
 fi_bits_append (fi_bits_t *dst, const fi_bits_t *src)
 {
-   if ((dst->nbits & 7) == 0)
+   if ((dst->nbits & 7) == 0 && src->skip == 0)
    {
       const size_t at = dst->nbits >> 3, bytes = (src->nbits + 7) >> 3;
 
@@ -75,7 +76,7 @@ fi_bits_append (fi_bits_t *dst, const fi_bits_t *src)
       dst->nbits += src->nbits;
    }
    else
-      for (size_t i = 0; i < src->nbits; i++)
+      for (size_t i = src->skip; i < src->nbits; i++)
 	 fi_put_bit (dst, (src->buf [i >> 3] >> (7 - (i & 7))) & 1u);
 }
 

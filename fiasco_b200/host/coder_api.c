@@ -152,7 +152,8 @@ expand_names (char const *const *templates, name_list_t *out)
 			  frame types and coding order
 *****************************************************************************/
 
-enum {T_INTRA = 0, T_P = 1, T_B = 2};
+enum {T_INTRA = 0, T_P = 1, T_B = 2,
+      T_ND = 3};	/* (a kind of workspace only: intra frames with nondeterministic prediction) */
 
 static int
 pattern_type (unsigned frame, const char *pattern)
@@ -284,8 +285,8 @@ typedef struct unit		/* one frame of one stream */
 typedef struct gpu
 {
    int		device;
-   fb200_ctx_t *ctx [3];	/* workspaces for intra, P and B frames */
-   int		ctx_tiles [3];
+   fb200_ctx_t *ctx [4];	/* workspaces for intra, P and B frames, intra frames with ND prediction */
+   int		ctx_tiles [4];
    pthread_t	thread;
    int		failed;
    char		err [600];
@@ -293,7 +294,9 @@ typedef struct gpu
 
 typedef struct wave_work	/* what the GPU threads of one launch share */
 {
-   int			 type;
+   int			 type;		/* frame type: are there reference frames */
+   int			 kind;		/* workspace: the frame type, or T_ND for intra frames of a job with
+					   nondeterministic prediction */
    unsigned		 cnt, n_gpus;
    unit_t	       **u;
    unit_t	       **past, **future;
@@ -354,33 +357,33 @@ wave_worker (void *arg)
    struct timespec t0, t1, t2;
 
    clock_gettime (CLOCK_MONOTONIC, &t0);
-   if (!g->ctx [w->type] || g->ctx_tiles [w->type] < (int) share)
+   if (!g->ctx [w->kind] || g->ctx_tiles [w->kind] < (int) share)
    {
       const int tiles = (int) fi_max (share, w->max_share);
       fb200_motion_t mo;
 
-      if (g->ctx [w->type])
-	 fb200_destroy (g->ctx [w->type]);
-      g->ctx [w->type] = NULL;
-      if (w->type)
+      if (g->ctx [w->kind])
+	 fb200_destroy (g->ctx [w->kind]);
+      g->ctx [w->kind] = NULL;
+      if (w->kind)
       {
 	 mo	       = *w->mo;
-	 mo.frame_type = w->type;
-	 rc = fb200_create_predicted (&g->ctx [w->type], w->p, &mo, tiles, g->device, g->err,
+	 mo.frame_type = w->kind;
+	 rc = fb200_create_predicted (&g->ctx [w->kind], w->p, &mo, tiles, g->device, g->err,
 				      sizeof g->err);
       }
       else
-	 rc = fb200_create (&g->ctx [w->type], w->p, tiles, g->device, g->err, sizeof g->err);
-      g->ctx_tiles [w->type] = tiles;
+	 rc = fb200_create (&g->ctx [w->kind], w->p, tiles, g->device, g->err, sizeof g->err);
+      g->ctx_tiles [w->kind] = tiles;
    }
    clock_gettime (CLOCK_MONOTONIC, &t1);
    if (rc == FB200_OK)
    {
-      if (w->type)
-	 rc = fb200_encode_predicted (g->ctx [w->type], (int) share, planes, past,
+      if (w->kind)
+	 rc = fb200_encode_predicted (g->ctx [w->kind], (int) share, planes, w->type ? past : NULL,
 				      w->type == T_B ? future : NULL, batch, g->err, sizeof g->err);
       else
-	 rc = fb200_encode_tiles (g->ctx [w->type], (int) share, planes, batch, NULL, 0, NULL,
+	 rc = fb200_encode_tiles (g->ctx [w->kind], (int) share, planes, batch, NULL, 0, NULL,
 				  g->err, sizeof g->err);
    }
    clock_gettime (CLOCK_MONOTONIC, &t2);
@@ -389,8 +392,8 @@ wave_worker (void *arg)
       fb200_stats_t st;
 
       memset (&st, 0, sizeof st);
-      if (g->ctx [w->type])
-	 fb200_get_stats (g->ctx [w->type], &st);
+      if (g->ctx [w->kind])
+	 fb200_get_stats (g->ctx [w->kind], &st);
       fprintf (stderr, "fiasco_coder:   gpu %d, %u units: context %.1f ms, call %.1f ms (h2d %.1f, kernel %.1f, "
 	       "d2h %.1f)\n", g->device, share,
 	       1e3 * (double) (t1.tv_sec - t0.tv_sec) + 1e-6 * (double) (t1.tv_nsec - t0.tv_nsec),
@@ -414,7 +417,7 @@ wave_worker (void *arg)
       u->wfa = batch [k];
       memset (&fm, 0, sizeof fm);
       memcpy (caller, fi_env, sizeof caller);
-      if (w->type)
+      if (w->kind)
       {
 	 int ok = 0;
 
@@ -518,7 +521,7 @@ release_contexts (void *arg)
 {
    (void) arg;
    for (unsigned g = 0; g < FI_MAXGPUS; g++)
-      for (int t = 0; t < 3; t++)
+      for (int t = 0; t < 4; t++)
 	 if (job.gpus [g].ctx [t])
 	 {
 	    fb200_destroy (job.gpus [g].ctx [t]);
@@ -536,7 +539,7 @@ job_release (void)
       pthread_join (job.release_thread, NULL);
    job.prep_running = job.release_running = 0;
    for (unsigned g = 0; g < FI_MAXGPUS; g++)
-      for (int t = 0; t < 3; t++)
+      for (int t = 0; t < 4; t++)
 	 if (job.gpus [g].ctx [t])
 	    fb200_destroy (job.gpus [g].ctx [t]);
    for (size_t i = 0; i < job.n_units; i++)
@@ -712,6 +715,7 @@ typedef struct write_ctx
    const fi_wfainfo_t *wi;
    const c_options_t  *cop;
    fi_bits_t	     **out;	/* [streams * frames] */
+   unsigned	       phase;	/* position of the frame's first bit in its byte of the file */
 } write_ctx_t;
 
 static void
@@ -736,6 +740,8 @@ write_frame (size_t i, void *ctx)
       w.mv_fy	    = (const int8_t (*)[2]) u->wfa.mv_fy;
       w.delta_state = u->delta;
    }
+   else if (u->delta)		/* an intra frame with nondeterministic prediction */
+      w.delta_state = u->delta;
    w.info	    = wc->wi;
    w.states	    = u->wfa.states;
    w.basis_states   = u->wfa.basis_states;
@@ -747,7 +753,9 @@ write_frame (size_t i, void *ctx)
    w.weight	    = (const float (*)[2][6]) u->wfa.weight;
    w.y_state	    = (const int16_t (*)[2]) u->wfa.y_state;
    w.y_column	    = (const uint8_t (*)[2]) u->wfa.y_column;
-   wc->out [i]	    = fi_bits_open_mem ();
+   /* (the stream's byte alignments count from the start of the file: 'phase' = bits of the frame's
+      first byte that belong to the frame before it) */
+   wc->out [i]	    = fi_bits_open_mem (wc->phase);
    fi_write_next_wfa (&w, n, coded == 0, wc->cop->normal_domains, wc->cop->delta_domains, wc->out [i]);
 }
 
@@ -763,7 +771,7 @@ coder (char const *const *inputname, const char *outputname, float quality,
    fb200_motion_t     mo;
    unsigned	      frames, width = 0, height = 0, n, bands, n_predicted = 0;
    unsigned	      split, gpus, streams, cols, rows, tw, th;
-   int		      color = 0;
+   int		      color = 0, nd = 0;
 
    if (!inputname || !inputname [0] || strcmp (inputname [0], "-") == 0)
       templates = default_input;
@@ -862,8 +870,18 @@ coder (char const *const *inputname, const char *outputname, float quality,
 		      n, cop->pattern);
 	 n_predicted++;
       }
-   if (cop->prediction)
-      fi_error ("Nondeterministic (DC) prediction is not available in the B200 build.");
+   /* `--prediction' (nd_prediction, prediction.c:371) is tried on the intra frames of grey input
+      (coder.c:741-743, 806-807: never on a colour frame, whose delta pool merely changes its kind
+      -- no difference while the dictionary cannot fill up) */
+   nd = cop->prediction && !color;
+   if (cop->prediction && color && cop->max_states < FI_MAXSTATES)
+      fi_error ("`--prediction' on colour frames is available with the full dictionary size only.");
+   if (nd && (!cop->normal_domains || !cop->delta_domains
+	      || cop->d_rpf_mantissa != cop->rpf_mantissa || cop->d_rpf_range != cop->rpf_range
+	      || cop->d_dc_rpf_mantissa != cop->dc_rpf_mantissa
+	      || cop->d_dc_rpf_range != cop->dc_rpf_range))
+      fi_error ("Nondeterministic prediction: only the default domain pool and quantisation "
+		"settings of the prediction errors are available.");
    if (cop->full_search)
       fi_error ("Optimization level 3 (full search) is not available: the reference "
 		"coder's behaviour is undefined there.");
@@ -950,6 +968,7 @@ coder (char const *const *inputname, const char *outputname, float quality,
    wi.half_pixel    = cop->half_pixel_prediction;
    wi.B_as_past_ref = cop->B_as_past_ref;
    wi.smoothing	    = cop->smoothing;
+   wi.nd_prediction = cop->prediction;
    mo.frame_type   = T_P;
    mo.p_min_level  = (int) wi.p_min_level;
    mo.p_max_level  = (int) wi.p_max_level;
@@ -1061,6 +1080,7 @@ coder (char const *const *inputname, const char *outputname, float quality,
 	    if (!w.cnt)
 	       continue;
 	    w.type	= type;
+	    w.kind	= type == T_INTRA && nd ? T_ND : type;
 	    w.u		= job.wave_u;
 	    w.past	= job.wave_past;
 	    w.future	= job.wave_future;
@@ -1086,7 +1106,7 @@ coder (char const *const *inputname, const char *outputname, float quality,
    job.frame_bits   = fiasco_calloc ((size_t) streams * frames, sizeof (fi_bits_t *));
    job.n_frame_bits = (size_t) streams * frames;
    {
-      write_ctx_t wc = {frames, bands, &wi, cop, job.frame_bits};
+      write_ctx_t wc = {frames, bands, &wi, cop, job.frame_bits, 0};
 
       if (fi_parallel_for ((size_t) streams * frames, write_frame, &wc))
 	 fi_rethrow ();
@@ -1111,6 +1131,16 @@ coder (char const *const *inputname, const char *outputname, float quality,
 	 fi_debug_message ("WFA contains %d states (%d basis states).", u->wfa.states,
 			   u->wfa.basis_states);
 	 fi_debug_message ("Total costs : %.2f", (double) u->wfa.costs [0]);
+	 /* a frame without any edge ends with its matrices, not on a byte boundary: the frame after
+	    it is coded again, with its byte alignments where they fall in the file */
+	 if ((job.output->nbits & 7) != job.frame_bits [(size_t) s * frames + coded]->skip)
+	 {
+	    write_ctx_t again = {frames, bands, &wi, cop, job.frame_bits, (unsigned) (job.output->nbits & 7)};
+
+	    fi_bits_free_mem (job.frame_bits [(size_t) s * frames + coded]);
+	    job.frame_bits [(size_t) s * frames + coded] = NULL;
+	    write_frame ((size_t) s * frames + coded, &again);
+	 }
 	 fi_bits_append (job.output, job.frame_bits [(size_t) s * frames + coded]);
 	 fi_bits_free_mem (job.frame_bits [(size_t) s * frames + coded]);
 	 job.frame_bits [(size_t) s * frames + coded] = NULL;
@@ -1225,6 +1255,7 @@ fiasco_write_video_stream (const char *filename, const fiasco_stream_info_t *inf
       wi.half_pixel    = 0;
       wi.B_as_past_ref = 1;
       wi.smoothing     = info->smoothing;
+      wi.nd_prediction = info->nd_prediction;
       out = fi_bits_open (filename);
       if (!out)
       {
@@ -1264,6 +1295,8 @@ fiasco_write_video_stream (const char *filename, const fiasco_stream_info_t *inf
 	    w.mv_fy	  = (const int8_t (*)[2]) motion [n].mv_fy;
 	    w.delta_state = motion [n].delta_state;
 	 }
+	 else if (motion && info->nd_prediction)
+	    w.delta_state = motion [n].delta_state;	/* differences of DC-predicted ranges */
 	 fi_write_next_wfa (&w, motion ? (unsigned) motion [n].frame_number : (unsigned) n, n == 0, 1, 1, out);
       }
       fi_bits_close (out);

@@ -687,6 +687,93 @@ write_mc (const fi_wfa_t *wfa, fi_bits_t *out)
 
 /* ------------------------------------------------------------------ frame ---- */
 
+/* ------------------------------------- nondeterministic prediction (output/nd.c) ---- */
+
+/*
+ *  A stream coded with `--prediction' carries, per frame, which ranges of the prediction levels
+ *  are predicted by their DC component -- the subdivided labels that have edges as well, one
+ *  adaptive bit each in breadth-first order (encode_nd_tree, output/nd.c:70-190: counts (1, 11),
+ *  halved beyond 50; below a predicted label the walk stops) -- and the weights of those edges
+ *  (encode_nd_coefficients, :192-244: one uniform-start table in the DC format).
+ */
+static void
+write_nd (const fi_wfa_t *wfa, fi_bits_t *out)
+{
+   unsigned *queue = fiasco_calloc (FI_MAXSTATES, sizeof (unsigned));
+   unsigned  head = 0, tail = 0, used = 0;
+   fi_ac_t   ac;
+   uint16_t  sum0 = 1, sum1 = 11;
+
+   fi_ac_init (&ac, out);
+   queue [tail++] = wfa->root_state;
+   while (head < tail)
+   {
+      const unsigned next  = queue [head++];
+      const unsigned level = wfa->level_of_state [next];
+
+      if (level > wfa->info->p_max_level + 1)
+      {
+	 for (unsigned label = 0; label < FI_MAXLABELS; label++)
+	    if (!isrange (wfa->tree [next][label]))
+	       queue [tail++] = (unsigned) wfa->tree [next][label];
+      }
+      else if (level > wfa->info->p_min_level)
+	 for (unsigned label = 0; label < FI_MAXLABELS; label++)
+	 {
+	    const int child = wfa->tree [next][label];
+
+	    if (isrange (child))
+	       continue;
+	    const unsigned range = (unsigned) (ac.high - ac.low) + 1;
+
+	    if (wfa->into [next][label][0] != FI_NO_EDGE)	/* predicted */
+	    {
+	       used++;
+	       ac.low = (uint16_t) (ac.low + (uint16_t) ((range * sum0) / sum1));
+	       fi_ac_rescale (&ac);
+	    }
+	    else
+	    {
+	       if (wfa->level_of_state [child] > wfa->info->p_min_level)
+		  queue [tail++] = (unsigned) child;
+	       ac.high = (uint16_t) (ac.low + (uint16_t) ((range * sum0) / sum1 - 1));
+	       fi_ac_rescale (&ac);
+	       sum0++;
+	    }
+	    sum1++;
+	    if (sum1 > 50)
+	    {
+	       sum0 >>= 1;
+	       sum1 >>= 1;
+	       if (!sum0)
+		  sum0 = 1;
+	       if (sum0 >= sum1)
+		  sum1 = (uint16_t) (sum0 + 1);
+	    }
+	 }
+   }
+   fi_ac_flush (&ac);
+   free (queue);
+
+   if (used)
+   {
+      unsigned *coeff = fiasco_calloc (used * FI_MAXEDGES, sizeof (unsigned));
+      unsigned	n = 0, c_symbols = 1u << (wfa->info->dc_rpf.mantissa_bits + 1);
+
+      for (unsigned state = wfa->basis_states; state < wfa->states; state++)
+	 for (unsigned label = 0; label < FI_MAXLABELS; label++)
+	    if (!isrange (wfa->tree [state][label]))
+	       for (unsigned edge = 0; wfa->into [state][label][edge] != FI_NO_EDGE; edge++)
+	       {
+		  if (n >= used)
+		     fi_error ("Can't write more than %d coefficients.", used);
+		  coeff [n++] = (unsigned) fi_rtob (wfa->weight [state][label][edge], &wfa->info->dc_rpf);
+	       }
+      fi_encode_array (out, coeff, NULL, &c_symbols, 1, used, 50);
+      free (coeff);
+   }
+}
+
 /* the writer's static tables, before host threads share them */
 void
 fi_write_tables_init (void)
@@ -712,7 +799,13 @@ fi_write_next_wfa (const fi_wfa_t *wfa, unsigned frame_number, int first,
    fi_put_bit (out, 0);				/* no tiling permutation */
    fi_byte_align (out);
    write_tree (wfa, out);
-   fi_put_bit (out, 0);				/* no nondeterministic prediction */
+   if (wfa->info->nd_prediction)			/* output/write.c:100-106 */
+   {
+      fi_put_bit (out, 1);
+      write_nd (wfa, out);
+   }
+   else
+      fi_put_bit (out, 0);
    if (wfa->frame_type != 0)
       write_mc (wfa, out);
    edges = write_matrices (normal_domains, delta_domains, wfa, out);

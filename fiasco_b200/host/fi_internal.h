@@ -110,10 +110,12 @@ typedef struct fi_bits
    FILE	   *file;
    uint8_t *buf;
    size_t   nbits, cap;		/* bits written, capacity in bytes */
+   size_t   skip;		/* a stream in memory: leading bits that stand for the tail of what it will
+				   be appended to (so that byte alignments fall where they do in the file) */
 } fi_bits_t;
 
 fi_bits_t *fi_bits_open (const char *filename);
-fi_bits_t *fi_bits_open_mem (void);
+fi_bits_t *fi_bits_open_mem (unsigned phase);
 void	   fi_bits_free_mem (fi_bits_t *b);
 void	   fi_bits_append (fi_bits_t *dst, const fi_bits_t *src);
 void	   fi_bits_close (fi_bits_t *b);
@@ -148,6 +150,7 @@ typedef struct fi_wfainfo
    unsigned    frames, fps, p_min_level, p_max_level, search_range;
    int	       half_pixel, B_as_past_ref;
    unsigned    smoothing;
+   int	       nd_prediction;	/* coded with `--prediction': every frame carries its ND tree */
 } fi_wfainfo_t;
 
 typedef struct fi_wfa

@@ -15,7 +15,7 @@ class StreamInfo(C.Structure):
         ("max_states", C.c_uint), ("chroma_max_states", C.c_uint),
         ("p_min_level", C.c_uint), ("p_max_level", C.c_uint), ("smoothing", C.c_uint), ("fps", C.c_uint),
         ("rpf_mantissa", C.c_int), ("rpf_range_e", C.c_int), ("dc_rpf_mantissa", C.c_int), ("dc_rpf_range_e", C.c_int),
-        ("title", C.c_char_p), ("comment", C.c_char_p),
+        ("title", C.c_char_p), ("comment", C.c_char_p), ("nd_prediction", C.c_int),
     ]
 
 
@@ -101,13 +101,14 @@ def write_stream(path, params, wfas, title=None, comment=None):
         raise RuntimeError("fiasco_write_stream: " + error_message())
 
 
-def write_video_stream(path, params, wfas, p_min_level=6, p_max_level=10, search_range=16):
+def write_video_stream(path, params, wfas, p_min_level=6, p_max_level=10, search_range=16, nd_prediction=False):
     """Serialise a sequence with predicted frames: every automaton dict also holds "frame_type" and, for
     predicted frames, "mv_type", "mv_fx", "mv_fy" ([states][2] int8) and "delta_state" ([states] uint8)."""
     L = load()
     info = StreamInfo()
     L.fiasco_stream_info_init(C.byref(info), C.byref(params))
     info.p_min_level, info.p_max_level = p_min_level, p_max_level
+    info.nd_prediction = int(nd_prediction)
     arr = (ffi._Wfa * len(wfas))()
     mot = (FrameMotion * len(wfas))()
     keep = []
@@ -121,6 +122,10 @@ def write_video_stream(path, params, wfas, p_min_level=6, p_max_level=10, search
                 a = np.ascontiguousarray(w[name], dtype=dt)
                 k[name] = a
                 setattr(mot[i], name, a.ctypes.data)
+        elif nd_prediction:                        # the delta states of an intra frame with ND prediction
+            a = np.ascontiguousarray(w["delta_state"], dtype=np.uint8)
+            k["delta_state"] = a
+            mot[i].delta_state = a.ctypes.data
     if not L.fiasco_write_video_stream(path.encode(), C.byref(info), arr, mot, len(wfas), search_range):
         raise RuntimeError("fiasco_write_video_stream: " + error_message())
 

@@ -243,9 +243,15 @@ int fb200_motion_norms (int device, const int16_t *orig, const int16_t *past, in
  *  with the delta pool and delta coefficient model).  Levels and search range as in
  *  c_options_t (codec/options.h: p_min_level, p_max_level, search_range; CLI defaults 6, 10, 16).
  */
+#define FB200_FRAME_ND 3	/* an INTRA frame coded with nondeterministic prediction (`cfiasco
+				   --prediction', fiasco_c_options_set_prediction; nd_prediction,
+				   codec/prediction.c:371): the third alternative of subdivide() is the
+				   range's DC component plus a nested pass over the difference.  No
+				   reference frames: 'past' and 'future' may be NULL */
+
 typedef struct fb200_motion
 {
-   int frame_type;		/* 1 = P frame, 2 = B frame */
+   int frame_type;		/* 1 = P frame, 2 = B frame, FB200_FRAME_ND */
    int p_min_level, p_max_level;
    int search_range;		/* vectors in [-search_range, search_range), full pixel */
 } fb200_motion_t;

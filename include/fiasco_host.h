@@ -27,6 +27,8 @@ typedef struct fiasco_stream_info
    unsigned    fps;			/* 25 */
    int	       rpf_mantissa, rpf_range_e, dc_rpf_mantissa, dc_rpf_range_e;
    const char *title, *comment;		/* may be NULL */
+   int	       nd_prediction;		/* coded with `--prediction' (fiasco_c_options_set_prediction): every
+					   frame carries its nondeterminism tree (output/write.c:100, output/nd.c) */
 } fiasco_stream_info_t;
 
 /* defaults of the reference command line front end for a stream coded with params 'p'
@@ -54,7 +56,8 @@ typedef struct fiasco_frame_motion
    const int8_t	 *mv_type;	/* 0 none, 1 forward, 2 backward, 3 interpolated */
    const int8_t	 *mv_fx, *mv_fy;
    const int8_t	 *mv_bx, *mv_by;	/* backward vectors (B frames), else may be NULL */
-   const uint8_t *delta_state;	/* states that describe a prediction error */
+   const uint8_t *delta_state;	/* states that describe a prediction error (also of an intra frame coded
+				   with nondeterministic prediction) */
 } fiasco_frame_motion_t;
 
 /*

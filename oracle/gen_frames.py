@@ -105,3 +105,20 @@ def colour_sequence(n=2, w=128, h=128, k=8):
     for j in range(1, n):
         out.append(np.stack([chan(w, h, s + 20 * j) for s in (4, 5, 6)], axis=-1))
     return out
+
+
+def nd_sequence(n=4, w=160, h=128, seed=7):
+    """Bright frames with a fine moving texture: the kind of picture on which `cfiasco --prediction'
+    takes nondeterministic (DC) prediction (codec/prediction.c:371) on a number of ranges."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    return [np.clip(190 + 25 * np.sin((xx + 3 * t) / 3.0) * np.sin((yy + t) / 5.0) + rng.normal(0, 5, (h, w)), 0,
+                    255).astype(np.uint8) for t in range(n)]
+
+
+def nd_still(n=512, seed=11):
+    """A still for `--prediction': slow luminance ramp, fine texture, some noise."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:n, 0:n]
+    return np.clip(150 + 60 * np.sin(xx / 40.0) + 25 * np.sin(xx / 3.0) * np.sin(yy / 5.0) + rng.normal(0, 6, (n, n)),
+                   0, 255).astype(np.uint8)

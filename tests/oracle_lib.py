@@ -96,6 +96,8 @@ def lib():
         L.fo_fill_norms_table.restype = None
         L.fo_set_holes_mode.argtypes = [C.c_int]
         L.fo_set_holes_mode.restype = None
+        L.fo_set_nd_prediction.argtypes = [C.c_int]
+        L.fo_set_nd_prediction.restype = None
         L.fo_close_holes.argtypes = [C.POINTER(FoWfa)]
         L.fo_close_holes.restype = None
         L.fo_wfa_from_dump.argtypes = [C.c_char_p, C.c_uint, C.POINTER(FoWfa)]

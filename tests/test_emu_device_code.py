@@ -396,3 +396,85 @@ def test_emulated_video_param_against_reference_library(emu, tmp_path):
         check_video_param_against_reference_library(tmp_path)
     finally:
         hostlib._LIB, hostlib.lib_path = saved
+
+
+# ------------------------------------------------- nondeterministic prediction (`cfiasco --prediction')
+
+def nd_case_frames(name):
+    m = O.manifest()[name]
+    if name.startswith("nd160"):
+        frames = gen_frames.nd_sequence()
+    elif name == "nd512_q80":
+        frames = [gen_frames.nd_still()]
+    elif name == "g256_q20_nd":
+        frames = [gen_frames.frame("g256")]
+    else:
+        frames = [gen_frames.colour_sequence(2, 128, 128)[1]]
+    assert len(frames) == m["frames"]
+    return m, frames
+
+
+def check_nd_frames_against_oracle(name, which=None):
+    """Intra frames with nondeterministic prediction through the C ABI (a context of frame type
+    FB200_FRAME_ND): the device's automaton -- holes still open -- state for state against the oracle
+    run in holes mode (restatement of nd_prediction, codec/prediction.c:371)."""
+    m, frames = nd_case_frames(name)
+    L = O.lib()
+    L.fo_set_holes_mode(1)
+    L.fo_set_nd_prediction(1)
+    try:
+        ws, _ = O.encode_video(frames, quality=m["quality"], pattern="i")
+    finally:
+        L.fo_set_holes_mode(0)
+        L.fo_set_nd_prediction(0)
+    p = ffi.make_params(m["width"], m["height"], 1, float(m["quality"]), 0)
+    enc = F.TileEncoder(p, 1, motion=F.Motion(3, 6, 10, 16))
+    predicted = 0
+    try:
+        for f in (range(len(frames)) if which is None else which):
+            od = O.struct_dict(ws[f]["_struct"])
+            g = enc.encode_predicted([O.planes_of(frames[f])[0]], None)[0]
+            assert_same_predicted_automaton(g, od)
+            n = od["states"]
+            predicted += int(((od["tree"][:n] >= 0) & (od["into"][:n, :, 0] >= 0)).sum())
+    finally:
+        enc.close()
+    return predicted
+
+
+def check_nd_coder_stream(name, tmp_path):
+    """fiasco_coder() with fiasco_c_options_set_prediction (intra_prediction = YES): the bytes the
+    reference `cfiasco --prediction' writes (md5 of the golden stream)."""
+    import hashlib
+    from fiasco_b200 import hostlib
+    m, frames = nd_case_frames(name)
+    names = []
+    for i, f in enumerate(frames):
+        names.append(str(tmp_path / ("n%02d.%s" % (i, "pgm" if f.ndim == 2 else "ppm"))))
+        gen_frames.write_pnm(names[-1], f)
+    o = hostlib.cli_options(0)
+    L = hostlib.load()
+    L.fiasco_c_options_set_frame_pattern(o, m["pattern"].encode())
+    L.fiasco_c_options_set_prediction(o, 1, 6, 10)
+    out = str(tmp_path / "nd.fco")
+    ok, msg = hostlib.coder(names, out, float(m["quality"]), options=o)
+    assert ok, msg
+    b = open(out, "rb").read()
+    assert (len(b), hashlib.md5(b).hexdigest()) == (m["fco_bytes"], m["fco_md5"])
+
+
+def test_emulated_device_code_nd_prediction(emu):
+    assert check_nd_frames_against_oracle("nd160_q70_i", which=(0, 2)) > 5
+
+
+def test_emulated_fiasco_coder_nd_prediction_streams(emu, tmp_path):
+    """Under the emulator: an I-only sequence with ND prediction, and the IPPP form of the same frames,
+    two of whose frames end off a byte boundary (no edges at all)."""
+    from fiasco_b200 import hostlib
+    saved = (hostlib._LIB, hostlib.lib_path)
+    hostlib._LIB, hostlib.lib_path = None, (lambda: os.path.join(EMU_DIR, "_build", "libfiasco_emu.so"))
+    try:
+        for name in ("nd160_q70_ippp", "c128_q30_nd"):
+            check_nd_coder_stream(name, tmp_path)
+    finally:
+        hostlib._LIB, hostlib.lib_path = saved

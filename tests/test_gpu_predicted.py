@@ -123,3 +123,39 @@ def test_default_pattern_sequence_matches_reference_cli(tmp_path):
         subprocess.run([cf, "--progress-meter=0", "-V", "0", "-q", "20", "-o", ref_out] + names,
                        env=env, check=True, capture_output=True)
         assert md5(out) == md5(ref_out)
+
+
+# ------------------------------------------------- nondeterministic prediction (`cfiasco --prediction')
+
+from test_emu_device_code import check_nd_coder_stream, check_nd_frames_against_oracle  # noqa: E402
+
+
+@pytest.mark.parametrize("name", ["nd160_q70_i", "nd512_q80", "g256_q20_nd"])
+def test_gpu_nd_prediction_frames_match_oracle(name):
+    """fiasco_tile_kernel<NT, true> with frame type FB200_FRAME_ND: the third alternative of subdivide() is
+    nd_prediction (codec/prediction.c:371).  Every frame, state for state, against the oracle."""
+    assert check_nd_frames_against_oracle(name) > 0
+
+
+@pytest.mark.parametrize("name", ["nd160_q70_i", "nd160_q70_ippp", "nd512_q80", "g256_q20_nd", "c128_q30_nd"])
+def test_gpu_fiasco_coder_nd_prediction_streams(name, tmp_path):
+    check_nd_coder_stream(name, tmp_path)
+
+
+def test_gpu_cli_prediction_flag(tmp_path):
+    """The unchanged reference CLI linked against our libfiasco: `cfiasco --prediction' writes the bytes the
+    reference binary writes."""
+    from test_emu_device_code import nd_case_frames
+    m, frames = nd_case_frames("nd512_q80")
+    pnm = str(tmp_path / "nd.pgm")
+    gen_frames.write_pnm(pnm, frames[0])
+    out = str(tmp_path / "nd.fco")
+    cli = os.path.join(os.path.dirname(REF), "..", "fiasco_b200", "lib", "cfiasco")
+    data = tmp_path / "data"
+    data.mkdir()
+    (data / "small.fco").write_text("Fiasco\n")
+    env = dict(os.environ, FIASCO_IMAGES=str(tmp_path), FIASCO_DATA=str(data))
+    r = subprocess.run([cli, "--progress-meter=0", "-V", "0", "-q", str(m["quality"]), "--prediction", "-o", out, pnm],
+                       env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert md5(out) == m["fco_md5"]

@@ -196,3 +196,24 @@ def test_host_regenerates_b_frames_like_the_reference():
             expected += 1
         reconst = hostlib.regenerate_frame(d, m["width"], m["height"], past, future)
         assert hashlib.md5(reconst.tobytes()).hexdigest() == m["decoded_md5"][k], "coded frame %d" % k
+
+
+@pytest.mark.parametrize("name", ["nd160_q70_i", "nd160_q70_ippp", "nd512_q80"])
+def test_nd_prediction_stream_is_byte_identical_to_reference(name, tmp_path):
+    """Streams coded with `--prediction': the nondeterminism tree and its DC weights (output/nd.c) in every
+    frame, the delta contexts of the states below an ND-predicted range -- from the oracle's automata the
+    writer gives the bytes of the reference cfiasco."""
+    import hashlib
+    from test_emu_device_code import nd_case_frames
+    m, frames = nd_case_frames(name)
+    L = O.lib()
+    L.fo_set_nd_prediction(1)
+    try:
+        ws, _ = O.encode_video(frames, quality=m["quality"], pattern=m["pattern"])
+    finally:
+        L.fo_set_nd_prediction(0)
+    p = ffi.make_params(m["width"], m["height"], 1, float(m["quality"]), 0)
+    out = str(tmp_path / "nd.fco")
+    hostlib.write_video_stream(out, p, [O.struct_dict(w["_struct"]) for w in ws], nd_prediction=True)
+    b = open(out, "rb").read()
+    assert (len(b), hashlib.md5(b).hexdigest()) == (m["fco_bytes"], m["fco_md5"])
