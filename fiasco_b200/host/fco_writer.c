@@ -7,9 +7,9 @@
  *    bintree		      output/tree.c:46-190      (breadth first, adaptive binary coder)
  *    matrices		      output/matrices.c:53-536  (DC column, #edges, index deltas, chroma)
  *    weights		      output/weights.c:38-200   (per-level adaptive array coder)
- *  Only what an intra frame without nondeterministic prediction needs is written (the
- *  flags for ND prediction / tiling are emitted as 0, like the reference does for such a
- *  frame).
+ *    nondeterminism	      output/nd.c:53-244        (streams coded with `--prediction')
+ *    motion		      output/mc.c:75-251        (P and B frames)
+ *  The tiling flag is emitted as 0 (the reference's tiling never takes effect).
  */
 #include <math.h>
 #include <stdlib.h>
