@@ -909,6 +909,8 @@ remove_states (unsigned from, fo_wfa_t *w) /* wfalib.c:276-310 */
 	 w->mv_type [state][label] = 0;
 	 w->mv_fx [state][label]   = w->mv_fy [state][label] = 0;
 	 w->mv_bx [state][label]   = w->mv_by [state][label] = 0;
+	 w->x [state][label]	   = w->y [state][label] = 0;	/* (not in the reference: the virtual
+								   states of a colour frame never set them) */
       }
       w->domain_type [state] = 0;
       w->delta_state [state] = 0;
@@ -3068,15 +3070,14 @@ extract_mc_block (int16_t *mcblock, unsigned width, unsigned height,
    }
 }
 
-void
-fo_restore_mc (const fo_wfa_t *w, unsigned width, unsigned height, int half_pixel,
-	       int16_t *image, const int16_t *past, const int16_t *future)
+static void
+restore_mc_band (const fo_wfa_t *w, unsigned root_state, unsigned width, int half_pixel,
+		 int16_t *image, const int16_t *past, const int16_t *future)
 {
    int16_t *mcblock  = malloc (size_of_level (MAXLEVEL > 16 ? 16 : MAXLEVEL) * sizeof (int16_t));
    int16_t *mcblock2 = malloc (size_of_level (MAXLEVEL > 16 ? 16 : MAXLEVEL) * sizeof (int16_t));
 
-   (void) height;
-   for (unsigned state = w->basis_states; state <= w->root_state; state++)
+   for (unsigned state = w->basis_states; state <= root_state; state++)
       for (unsigned label = 0; label < MAXLABELS; label++)
 	 if (w->mv_type [state][label] != 0)	/* motion.c:69-190 */
 	 {
@@ -3100,6 +3101,82 @@ fo_restore_mc (const fo_wfa_t *w, unsigned width, unsigned height, int half_pixe
 
 		  *o = (int16_t) (*o + ref);
 	       }
+	 }
+   free (mcblock);
+   free (mcblock2);
+}
+
+void
+fo_restore_mc (const fo_wfa_t *w, unsigned width, unsigned height, int half_pixel,
+	       int16_t *image, const int16_t *past, const int16_t *future)
+{
+   (void) height;
+   restore_mc_band (w, w->root_state, width, half_pixel, image, past, future);
+}
+
+/* restore_mc for a colour frame (4:4:4): the vectors of the luminance tree -- the states up to the
+   root of the Y band -- move all three bands, then the chroma bands are clipped to 8 bits
+   (motion.c:59-62, 192-224).  image / past / future: three planes of width * height shorts. */
+void
+fo_restore_mc_colour (const fo_wfa_t *w, unsigned width, unsigned height, int16_t *image,
+		      const int16_t *past, const int16_t *future)
+{
+   const size_t	  npix	 = (size_t) width * height;
+   const unsigned y_root = (unsigned) w->tree [w->tree [w->root_state][0]][0];
+
+   for (unsigned b = 0; b < 3; b++)
+      restore_mc_band (w, y_root, width, 0, image + b * npix, past ? past + b * npix : NULL,
+		       future ? future + b * npix : NULL);
+   for (size_t n = npix; n < 3 * npix; n++)
+   {
+      int v = image [n] >> 4;		/* HAVE_SIGNED_SHIFT (oracle/refcfg/config.h) */
+
+      v = v < -128 ? -128 : v > 127 ? 127 : v;
+      image [n] = (int16_t) (v * 16);
+   }
+}
+
+/* subtract_mc (mwfa.c:156-299): before the chroma bands of a predicted colour frame are coded, the
+   motion compensation of the luminance tree is taken off the chroma planes of the original -- with
+   the vector components rounded towards zero to even numbers ((v / 2) * 2), which restore_mc does
+   NOT do: reproduced as it is. */
+static void
+subtract_mc (const fo_wfa_t *w, unsigned width, int16_t *const chroma [2],
+	     const int16_t *const past [2], const int16_t *const future [2])
+{
+   int16_t *mcblock  = malloc (size_of_level (MAXLEVEL > 16 ? 16 : MAXLEVEL) * sizeof (int16_t));
+   int16_t *mcblock2 = malloc (size_of_level (MAXLEVEL > 16 ? 16 : MAXLEVEL) * sizeof (int16_t));
+
+   for (unsigned state = w->basis_states; state < w->states; state++)
+      for (unsigned label = 0; label < MAXLABELS; label++)
+	 if (w->mv_type [state][label] != 0)
+	 {
+	    const unsigned level = w->level_of_state [state] - 1u;
+	    const unsigned bw = width_of_level (level), bh = height_of_level (level);
+	    const int	   type	 = w->mv_type [state][label];
+
+	    for (unsigned b = 0; b < 2; b++)
+	    {
+	       if (type == 1 || type == 3)
+		  extract_mc_block (mcblock, bw, bh, past [b], width, 0, w->x [state][label],
+				    w->y [state][label], (w->mv_fx [state][label] / 2) * 2,
+				    (w->mv_fy [state][label] / 2) * 2);
+	       if (type == 2 || type == 3)
+		  extract_mc_block (type == 2 ? mcblock : mcblock2, bw, bh, future [b], width, 0,
+				    w->x [state][label], w->y [state][label],
+				    (w->mv_bx [state][label] / 2) * 2, (w->mv_by [state][label] / 2) * 2);
+	       for (unsigned y = 0; y < bh; y++)
+		  for (unsigned x = 0; x < bw; x++)
+		  {
+		     int16_t  *o   = chroma [b] + (size_t) (w->y [state][label] + y) * width
+				     + w->x [state][label] + x;
+		     /* (a division here, mwfa.c:287, a shift in restore_mc) */
+		     const int ref = type == 3 ? (mcblock [y * bw + x] + mcblock2 [y * bw + x]) / 2
+					       : mcblock [y * bw + x];
+
+		     *o = (int16_t) (*o - ref);
+		  }
+	    }
 	 }
    free (mcblock);
    free (mcblock2);
@@ -3208,7 +3285,9 @@ fo_encode_video (const fo_params_t *p, int n_frames, const int16_t *const *frame
    fo_wfa_t   *w = calloc (1, sizeof (fo_wfa_t));
    fo_stats_t  dummy;
    const size_t npix = (size_t) p->width * p->height;
-   int16_t    *past = calloc (npix, sizeof (int16_t)), *cur = calloc (npix, sizeof (int16_t));
+   const unsigned bands = p->color ? 3 : 1;	/* colour: frames [3 f + b], reconst 3 planes per frame */
+   int16_t    *past = calloc (bands * npix, sizeof (int16_t)), *cur = calloc (bands * npix, sizeof (int16_t));
+   int16_t    *chroma = p->color ? calloc (2 * npix, sizeof (int16_t)) : NULL;
    unsigned    state, label, level;
    int	       rc = 0;
 
@@ -3229,8 +3308,6 @@ fo_encode_video (const fo_params_t *p, int n_frames, const int16_t *const *frame
       rc = 1;
       goto cleanup;
    }
-   if (p->color)
-      fail (c, "fo_encode_video: grey sequences only");
    if ((p->width & 1) || (p->height & 1))
       fail (c, "Width and height of images must be even numbers.");
    if (p->quality <= 0)
@@ -3261,6 +3338,7 @@ fo_encode_video (const fo_params_t *p, int n_frames, const int16_t *const *frame
       c->opt.max_states = ms > 1 ? ms : 1;
       ms = fmin2 (p->max_elements, MAXEDGES);
       c->opt.max_elements = ms > 1 ? ms : 1;
+      c->opt.chroma_max_states = p->chroma_max_states > 1 ? p->chroma_max_states : 1;
    }
    c->rpf    = make_rpf ((unsigned) p->rpf_mantissa, p->rpf_range_e);
    c->dc_rpf = make_rpf ((unsigned) p->dc_rpf_mantissa, p->dc_rpf_range_e);
@@ -3288,7 +3366,7 @@ fo_encode_video (const fo_params_t *p, int n_frames, const int16_t *const *frame
       frame of the sequence is forced to be a P frame */
    {
       int display = 0, future_display = -1, future_frame = 0, coded = 0;
-      int16_t *fut = calloc (npix, sizeof (int16_t));
+      int16_t *fut = calloc (bands * npix, sizeof (int16_t));
       int have_reconst = 0;
 
       while (display < n_frames)
@@ -3360,9 +3438,16 @@ fo_encode_video (const fo_params_t *p, int n_frames, const int16_t *const *frame
 	 (void) have_reconst;
 	 future_frame  = frame == future_display;
 	 c->frame_type = type;
-	 c->planes [0] = frames [frame];
+	 c->planes [0] = frames [(size_t) frame * bands];
 	 c->past       = past;
 	 c->future     = fut;
+	 if (p->color)		/* subtract_mc changes the chroma planes of the original */
+	 {
+	    memcpy (chroma, frames [(size_t) frame * 3 + 1], npix * sizeof (int16_t));
+	    memcpy (chroma + npix, frames [(size_t) frame * 3 + 2], npix * sizeof (int16_t));
+	    c->planes [1] = chroma;
+	    c->planes [2] = chroma + npix;
+	 }
 
 	 /* frame_coder (coder.c:692-755) */
 	 init_tree_model (&c->tree);
@@ -3384,18 +3469,83 @@ fo_encode_video (const fo_params_t *p, int n_frames, const int16_t *const *frame
 	 c->ap = &c->pool;
 	 c->ac = &c->coeff;
 
+	 w->frame_type	 = type;
+	 w->frame_number = frame;
+	 if (!p->color)
+	 {
 	 memset (&range, 0, sizeof range);
 	 range.level = c->level;
 	 w->costs [0] = subdivide (MAXCOSTS, 0, RANGE, &range, c, type != 0 || nd_prediction_on, 0);
 	 if (range.tree == RANGE)
 	    fail (c, "No root state generated!");
 	 w->root_state	     = (unsigned) range.tree;
-	 w->frame_type	     = type;
-	 w->frame_number     = frame;
 	 w->err [0]	     = range.err;
 	 w->tree_bits [0]    = range.tree_bits;
 	 w->matrix_bits [0]  = range.matrix_bits;
 	 w->weights_bits [0] = range.weights_bits;
+	 }
+	 else
+	 {
+	    /* the colour bands (coder.c:757-849): Y with the frame's prediction, then -- the pool cut
+	       down to the most used luminance states, the range levels limited to those the luminance
+	       used (for good: the option is never set back), the luminance tree's motion compensation
+	       taken off the chroma planes -- Cb and Cr without prediction; virtual states on top */
+	    int	     YCb_node = -1, tree [3];
+	    unsigned band;
+
+	    for (band = 0; band < 3; band++)
+	    {
+	       tree [band] = RANGE;
+	       if (band == 1)
+	       {
+		  unsigned min_level;
+
+		  rle_chroma ((unsigned) c->opt.chroma_max_states, c);
+		  for (min_level = MAXLEVEL, state = w->basis_states; state < w->states; state++)
+		  {
+		     unsigned lincomb = 0;
+
+		     for (label = 0; label < MAXLABELS; label++)
+			lincomb += w->tree [state][label] == RANGE ? 1 : 0;
+		     if (lincomb)
+			min_level = fmin2 (min_level, (unsigned) (w->level_of_state [state] - 1));
+		  }
+		  c->opt.lc_min_level = (int) min_level;
+		  if (type != 0)
+		  {
+		     int16_t *const	  ch [2] = {chroma, chroma + npix};
+		     const int16_t *const pp [2] = {past + npix, past + 2 * npix};
+		     const int16_t *const ff [2] = {fut + npix, fut + 2 * npix};
+
+		     subtract_mc (w, (unsigned) p->width, ch, pp, ff);
+		  }
+	       }
+	       memset (&range, 0, sizeof range);
+	       range.level = c->level;
+	       w->costs [band] = subdivide (MAXCOSTS, band, tree [0], &range, c, type != 0 && band == 0, 0);
+	       w->err [band]	      = range.err;
+	       w->tree_bits [band]    = range.tree_bits;
+	       w->matrix_bits [band]  = range.matrix_bits;
+	       w->weights_bits [band] = range.weights_bits;
+	       if (range.tree == RANGE)
+		  fail (c, "No root state generated for color component %d!", band);
+	       tree [band] = range.tree;
+	       if (band == 1)
+	       {
+		  w->tree [w->states][0] = (int16_t) tree [0];
+		  w->tree [w->states][1] = (int16_t) tree [1];
+		  YCb_node		 = (int) w->states;
+		  append_state (1, compute_final_distribution (w->states, w), c->level + 1, c);
+	       }
+	    }
+	    w->tree [w->states][0] = (int16_t) tree [2];
+	    w->tree [w->states][1] = RANGE;
+	    append_state (1, compute_final_distribution (w->states, w), c->level + 1, c);
+	    w->tree [w->states][0] = (int16_t) YCb_node;
+	    w->tree [w->states][1] = (int16_t) (w->states - 1);
+	    append_state (1, compute_final_distribution (w->states, w), c->level + 2, c);
+	    w->root_state = w->states - 1;
+	 }
 	 /* locate_delta_images (wfalib.c:699-730, called at coder.c:876): the delta flags the
 	    stream carries are derived from the structure, top down */
 	 for (state = w->root_state; state >= w->basis_states; state--)
@@ -3410,13 +3560,15 @@ fo_encode_video (const fo_params_t *p, int n_frames, const int16_t *const *frame
 
 	 /* regenerate the frame: a reference of the frames to come (coder.c:642-651) */
 	 {
-	    int16_t *planes [3] = {cur, NULL, NULL};
+	    int16_t *planes [3] = {cur, p->color ? cur + npix : NULL, p->color ? cur + 2 * npix : NULL};
 
-	    fo_decode_image (w, 0, (unsigned) p->width, (unsigned) p->height, planes);
-	    if (type)
+	    fo_decode_image (w, p->color, (unsigned) p->width, (unsigned) p->height, planes);
+	    if (type && p->color)
+	       fo_restore_mc_colour (w, (unsigned) p->width, (unsigned) p->height, cur, past, fut);
+	    else if (type)
 	       fo_restore_mc (w, (unsigned) p->width, (unsigned) p->height, 0, cur, past, fut);
 	    if (reconst)
-	       memcpy (reconst + (size_t) coded * npix, cur, npix * sizeof (int16_t));
+	       memcpy (reconst + (size_t) coded * bands * npix, cur, bands * npix * sizeof (int16_t));
 	 }
 	 coded++;
 	 remove_states (w->basis_states, w);
@@ -3442,6 +3594,7 @@ cleanup:
    free (w);
    free (past);
    free (cur);
+   free (chroma);
    return rc;
 }
 

@@ -139,12 +139,20 @@ int fo_wfa_from_dump (const char *text, unsigned root_state, fo_wfa_t *wfa);
  */
 void fo_restore_mc (const fo_wfa_t *wfa, unsigned width, unsigned height, int half_pixel,
 		    int16_t *image, const int16_t *past, const int16_t *future);
+/* the same for a colour frame (three planes each): the luminance tree's vectors move all bands, the
+   chroma bands are clipped to 8 bits afterwards (motion.c:59-62, 192-224) */
+void fo_restore_mc_colour (const fo_wfa_t *wfa, unsigned width, unsigned height, int16_t *image,
+			   const int16_t *past, const int16_t *future);
 
 /*
- *  Encode a grey sequence (video_coder / frame_coder, codec/coder.c:490-892): frame 0 intra, the
- *  others I or P by 'pattern'; predicted frames use motion compensation against the regenerated
- *  previous frame (codec/prediction.c, codec/mwfa.c).  frames [f]: width * height shorts.
- *  out [f]: automaton of frame f; reconst (or NULL): the regenerated frames.  0 on success.
+ *  Encode a sequence (video_coder / frame_coder, codec/coder.c:490-892): frame 0 intra, the
+ *  others I, P or B by 'pattern'; predicted frames use motion compensation against the regenerated
+ *  reference frames (codec/prediction.c, codec/mwfa.c).  Grey: frames [f], width * height shorts.
+ *  Colour (p->color): frames [3 f + b], b = Y, Cb, Cr; the luminance band is coded with prediction,
+ *  the luminance tree's motion compensation is taken off the chroma planes (subtract_mc,
+ *  codec/mwfa.c:156) before Cb and Cr are coded without prediction (coder.c:757-849).
+ *  out [f]: automaton of the f-th CODED frame; reconst (or NULL): the regenerated frames (colour:
+ *  three planes each).  0 on success.
  */
 int fo_encode_video (const fo_params_t *p, int n_frames, const int16_t *const *frames,
 		     const char *pattern, int p_min_level, int p_max_level, int search_range,

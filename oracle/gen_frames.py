@@ -122,3 +122,15 @@ def nd_still(n=512, seed=11):
     yy, xx = np.mgrid[0:n, 0:n]
     return np.clip(150 + 60 * np.sin(xx / 40.0) + 25 * np.sin(xx / 3.0) * np.sin(yy / 5.0) + rng.normal(0, 6, (n, n)),
                    0, 255).astype(np.uint8)
+
+
+def colour_video(n=4, w=160, h=128):
+    """A colour sequence with motion: the frames of video() as the green channel, shifted / inverted
+    copies of them plus a moving colour ramp as red and blue."""
+    out = []
+    yy, xx = np.mgrid[0:h, 0:w]
+    for f, g in enumerate(video(n, w, h)):
+        r = np.clip(np.roll(g, 5, axis=1).astype(np.int32) + 40 * np.sin((xx + 4 * f) / 23.0), 0, 255).astype(np.uint8)
+        b = np.clip(255 - np.roll(g, -3, axis=0).astype(np.int32) + 30 * np.cos((yy - 2 * f) / 17.0), 0, 255).astype(np.uint8)
+        out.append(np.stack([r, g, b], axis=-1))
+    return out

@@ -223,15 +223,17 @@ def decode(w):
 
 
 def encode_video(frames, quality=20.0, pattern="ippp", p_min_level=6, p_max_level=10, search_range=16, trace_path=None):
-    """Run the oracle on a grey sequence (list of u8 (h, w) frames; CLI defaults of cfiasco).  Returns
-    (list of automata as ctypes structs wrapped like wfa_from_dump(), regenerated frames int16 [n][h][w])."""
+    """Run the oracle on a sequence (list of u8 (h, w) grey or (h, w, 3) RGB frames; CLI defaults of cfiasco).
+    Returns (list of automata as ctypes structs wrapped like wfa_from_dump(), regenerated frames int16 [n][h][w],
+    colour: [n][3][h][w])."""
     L = lib()
-    h, w = frames[0].shape
-    planes = [planes_of(f)[0] for f in frames]
+    h, w = frames[0].shape[:2]
+    colour = frames[0].ndim == 3
+    planes = [pl for f in frames for pl in planes_of(f)]
     ptrs = (C.c_void_p * len(planes))(*[pl.ctypes.data for pl in planes])
-    p = default_params(w, h, 0, quality, 0)
+    p = default_params(w, h, int(colour), quality, 0)
     out = (FoWfa * len(frames))()
-    rec = np.zeros((len(frames), h, w), np.int16)
+    rec = np.zeros((len(frames), 3, h, w) if colour else (len(frames), h, w), np.int16)
     err = C.create_string_buffer(256)
     fp = L._libc.fopen(trace_path.encode(), b"w") if trace_path else None
     rc = L.fo_encode_video(C.byref(p), len(frames), ptrs, pattern.encode(), p_min_level, p_max_level, search_range,
@@ -240,7 +242,8 @@ def encode_video(frames, quality=20.0, pattern="ippp", p_min_level=6, p_max_leve
         L._libc.fclose(fp)
     if rc:
         raise RuntimeError("oracle: " + err.value.decode())
-    return [{"_struct": out[i], "_shape": (h, w, 1), "states": out[i].states} for i in range(len(frames))], rec
+    return [{"_struct": out[i], "_shape": (h, w, 3 if colour else 1), "states": out[i].states}
+            for i in range(len(frames))], rec
 
 
 def struct_dict(st):
