@@ -1283,8 +1283,8 @@ fiasco_write_video_stream (const char *filename, const fiasco_stream_info_t *inf
 	 w.y_column	  = (const uint8_t (*)[2]) frames [n].y_column;
 	 if (motion && motion [n].frame_type != 0)
 	 {
-	    if (motion [n].frame_type < 1 || motion [n].frame_type > 2 || info->color)
-	       fi_error ("frame %d: only grey P and B frames can be written", n);
+	    if (motion [n].frame_type < 1 || motion [n].frame_type > 2)
+	       fi_error ("frame %d: frame type %d", n, motion [n].frame_type);
 	    w.frame_type  = motion [n].frame_type;
 	    w.mv_bx	  = (const int8_t (*)[2]) motion [n].mv_bx;
 	    w.mv_by	  = (const int8_t (*)[2]) motion [n].mv_by;

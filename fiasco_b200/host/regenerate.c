@@ -84,15 +84,18 @@ state_image (regen_t *r, unsigned state, unsigned level)
    return img;
 }
 
-int
-fiasco_regenerate_frame (const fb200_wfa_t *w, const fiasco_frame_motion_t *motion,
-			 int width, int height, const int16_t *past, const int16_t *future,
-			 int16_t *out)
+/* grey: one plane; colour (4:4:4, what the coder regenerates: coder.c:647): three planes Y, Cb, Cr
+   of width * height shorts behind each other in out / past / future */
+static int
+regenerate (const fb200_wfa_t *w, const fiasco_frame_motion_t *motion, int width, int height,
+	    int colour, const int16_t *past, const int16_t *future, int16_t *out)
 {
    fi_try
    {
-      regen_t  r;
-      unsigned max_level = 0, aw = 0, ah = 0, state;
+      regen_t	   r;
+      unsigned	   max_level = 0, aw = 0, ah = 0, state;
+      const size_t npix	 = (size_t) width * (size_t) height;
+      unsigned	   root [2] = {0, 0};	/* colour: the roots of the Y and the Cb band (decoder.c:436-444) */
 
       if (!w || !out || width < 1 || height < 1 || w->status != FB200_OK)
       {
@@ -125,26 +128,41 @@ fiasco_regenerate_frame (const fb200_wfa_t *w, const fiasco_frame_motion_t *moti
 	 aw = (unsigned) width;
       if (ah < (unsigned) height)
 	 ah = (unsigned) height;
+      if (colour)
+      {
+	 const int top0 = w->tree [2 * w->root_state], top1 = w->tree [2 * w->root_state + 1];
+
+	 if (top0 < 0 || top1 < 0 || w->tree [2 * top0] < 0 || w->tree [2 * top0 + 1] < 0)
+	    fi_error ("fiasco_regenerate_frame: not the automaton of a colour frame");
+	 root [0] = (unsigned) w->tree [2 * top0];
+	 root [1] = (unsigned) w->tree [2 * top0 + 1];
+      }
       r.w      = w;
       r.levels = max_level + 1;
       r.pix    = fiasco_calloc ((size_t) w->states * r.levels, sizeof (int16_t *));
 
-      int16_t *frame = fiasco_calloc ((size_t) aw * ah, sizeof (int16_t));
+      const unsigned bands = colour ? 3 : 1;
+      int16_t	    *frame = fiasco_calloc ((size_t) aw * ah * bands, sizeof (int16_t));
 
-      /* every state of level max_level is one block of the frame (decoder.c:913-937) */
+      /* every state of level max_level is one block of the frame (decoder.c:913-937); the states
+	 of a colour frame's bands follow each other: Y up to its root, then Cb, then Cr */
       for (state = w->basis_states; state < w->states; state++)
 	 if (w->level_of_state [state] == max_level)
 	 {
+	    const unsigned b  = !colour || state <= root [0] ? 0 : state > root [1] ? 2 : 1;
 	    const unsigned bw = W_OF (max_level), bh = H_OF (max_level);
 	    const unsigned x0 = w->x [2 * state], y0 = w->y [2 * state];
 	    const unsigned cw = x0 >= aw ? 0 : (aw - x0 < bw ? aw - x0 : bw);
 	    const int16_t *img = state_image (&r, state, max_level);
 
 	    for (unsigned y = 0; y < bh && y0 + y < ah; y++)
-	       memcpy (frame + (size_t) (y0 + y) * aw + x0, img + y * bw, cw * sizeof (int16_t));
+	       memcpy (frame + (size_t) b * aw * ah + (size_t) (y0 + y) * aw + x0, img + y * bw,
+		       cw * sizeof (int16_t));
 	 }
-      for (int y = 0; y < height; y++)
-	 memcpy (out + (size_t) y * width, frame + (size_t) y * aw, (size_t) width * sizeof (int16_t));
+      for (unsigned b = 0; b < bands; b++)
+	 for (int y = 0; y < height; y++)
+	    memcpy (out + b * npix + (size_t) y * width, frame + (size_t) b * aw * ah + (size_t) y * aw,
+		    (size_t) width * sizeof (int16_t));
       free (frame);
       for (size_t i = 0; i < (size_t) w->states * r.levels; i++)
 	 free (r.pix [i]);
@@ -154,7 +172,7 @@ fiasco_regenerate_frame (const fb200_wfa_t *w, const fiasco_frame_motion_t *moti
 	 previous frame (forward), of the future frame (backward), or their mean (interpolated,
 	 arithmetic shift) */
       if (motion && motion->frame_type != 0)
-	 for (state = w->basis_states; state <= w->root_state; state++)
+	 for (state = w->basis_states; state <= (colour ? root [0] : w->root_state); state++)
 	    for (unsigned label = 0; label < 2; label++)
 	    {
 	       const int type = motion->mv_type [2 * state + label];
@@ -170,22 +188,49 @@ fiasco_regenerate_frame (const fb200_wfa_t *w, const fiasco_frame_motion_t *moti
 	       const int      bx = type > 1 ? motion->mv_bx [2 * state + label] : 0;
 	       const int      by = type > 1 ? motion->mv_by [2 * state + label] : 0;
 
-	       for (unsigned y = 0; y < bh; y++)
-		  for (unsigned x = 0; x < bw; x++)
-		  {
-		     int16_t  *o = out + (size_t) (y0 + (int) y) * width + x0 + (int) x;
-		     const int f = type != 2 ? past [(size_t) (y0 + fy + (int) y) * width + x0 + fx + (int) x] : 0;
-		     const int b = type != 1 ? future [(size_t) (y0 + by + (int) y) * width + x0 + bx + (int) x] : 0;
+	       /* (a colour frame: the luminance tree's vectors move all three bands, motion.c:59-62) */
+	       for (unsigned band = 0; band < bands; band++)
+		  for (unsigned y = 0; y < bh; y++)
+		     for (unsigned x = 0; x < bw; x++)
+		     {
+			int16_t	 *o = out + band * npix + (size_t) (y0 + (int) y) * width + x0 + (int) x;
+			const int f = type != 2 ? past [band * npix + (size_t) (y0 + fy + (int) y) * width + x0 + fx + (int) x] : 0;
+			const int b = type != 1 ? future [band * npix + (size_t) (y0 + by + (int) y) * width + x0 + bx + (int) x] : 0;
 
-		     *o = (int16_t) (*o + (type == 1 ? f : type == 2 ? b : (f + b) >> 1));
-		  }
+			*o = (int16_t) (*o + (type == 1 ? f : type == 2 ? b : (f + b) >> 1));
+		     }
 	    }
+      /* the chroma bands of a predicted colour frame are clipped to 8 bits (motion.c:192-224) */
+      if (colour && motion && motion->frame_type != 0)
+	 for (size_t n = npix; n < 3 * npix; n++)
+	 {
+	    int v = out [n] >> 4;
+
+	    v	    = v < -128 ? -128 : v > 127 ? 127 : v;
+	    out [n] = (int16_t) (v * 16);
+	 }
       return 1;
    }
    fi_catch
    {
       return 0;
    }
+}
+
+int
+fiasco_regenerate_frame (const fb200_wfa_t *w, const fiasco_frame_motion_t *motion,
+			 int width, int height, const int16_t *past, const int16_t *future,
+			 int16_t *out)
+{
+   return regenerate (w, motion, width, height, 0, past, future, out);
+}
+
+int
+fiasco_regenerate_colour_frame (const fb200_wfa_t *w, const fiasco_frame_motion_t *motion,
+				int width, int height, const int16_t *past, const int16_t *future,
+				int16_t *out)
+{
+   return regenerate (w, motion, width, height, 1, past, future, out);
 }
 
 /*
@@ -249,6 +294,8 @@ fiasco_finish_predicted_frame (fb200_wfa_t *w, int8_t *mv_type, int8_t *mv_fx, i
 
 	    if (w->tree [a] >= 0)
 	       w->tree [a] = map [w->tree [a]];
+	    if (w->y_state [a] >= 0)		/* (chroma bands of a colour frame) */
+	       w->y_state [a] = map [w->y_state [a]];
 	    for (unsigned e = 0; w->into [a * 6 + e] >= 0; e++)
 	       w->into [a * 6 + e] = map [w->into [a * 6 + e]];
 	 }

@@ -45,6 +45,7 @@ def load():
                                                 C.POINTER(FrameMotion), C.c_int, C.c_uint]
         L.fiasco_regenerate_frame.argtypes = [C.POINTER(ffi._Wfa), C.POINTER(FrameMotion), C.c_int, C.c_int,
                                               C.c_void_p, C.c_void_p, C.c_void_p]
+        L.fiasco_regenerate_colour_frame.argtypes = L.fiasco_regenerate_frame.argtypes
         L.fiasco_finish_predicted_frame.argtypes = [C.POINTER(ffi._Wfa)] + [C.c_void_p] * 6
         L.fiasco_coder.argtypes = [C.POINTER(C.c_char_p), C.c_char_p, C.c_float, C.c_void_p]
         L.fiasco_c_options_new.restype = C.c_void_p
@@ -130,9 +131,10 @@ def write_video_stream(path, params, wfas, p_min_level=6, p_max_level=10, search
         raise RuntimeError("fiasco_write_video_stream: " + error_message())
 
 
-def regenerate_frame(w, width, height, past=None, future=None):
-    """The grey frame an automaton describes, int16 (h, w) in the coder's pixel format
-    (fiasco_regenerate_frame); predicted frames ("frame_type" 1) need the previous regenerated frame."""
+def regenerate_frame(w, width, height, past=None, future=None, colour=False):
+    """The frame an automaton describes, int16 (h, w) -- colour: (3, h, w) -- in the coder's pixel format
+    (fiasco_regenerate_frame / fiasco_regenerate_colour_frame); predicted frames ("frame_type" 1, 2) need the
+    regenerated reference frame(s)."""
     L = load()
     s, keep = wfa_struct(w)
     mot = FrameMotion()
@@ -144,8 +146,9 @@ def regenerate_frame(w, width, height, past=None, future=None):
             setattr(mot, name, a.ctypes.data)
         past = np.ascontiguousarray(past, np.int16)
         future = np.ascontiguousarray(future, np.int16) if future is not None else None
-    out = np.zeros((height, width), np.int16)
-    if not L.fiasco_regenerate_frame(C.byref(s), C.byref(mot), width, height,
+    out = np.zeros((3, height, width) if colour else (height, width), np.int16)
+    fn = L.fiasco_regenerate_colour_frame if colour else L.fiasco_regenerate_frame
+    if not fn(C.byref(s), C.byref(mot), width, height,
                                      past.ctypes.data if past is not None else None,
                                      future.ctypes.data if future is not None else None, out.ctypes.data):
         raise RuntimeError("fiasco_regenerate_frame: " + error_message())

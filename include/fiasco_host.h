@@ -83,6 +83,16 @@ int fiasco_regenerate_frame (const fb200_wfa_t *wfa, const fiasco_frame_motion_t
 			     int16_t *out);
 
 /*
+ *  The same for a colour frame (4:4:4, as the coder regenerates it): out / past / future hold three
+ *  planes Y, Cb, Cr of width * height shorts behind each other.  The vectors of the luminance tree
+ *  move all three bands and the chroma bands of a predicted frame are clipped to 8 bits afterwards
+ *  (restore_mc, codec/motion.c:59-62, 192-224).
+ */
+int fiasco_regenerate_colour_frame (const fb200_wfa_t *wfa, const fiasco_frame_motion_t *motion,
+				    int width, int height, const int16_t *past, const int16_t *future,
+				    int16_t *out);
+
+/*
  *  Finish the automaton of a predicted frame the way the device leaves it:
  *  close the holes of losing split alternatives (states marked level_of_state == 255) by a monotone
  *  renumbering and derive the delta flags from the structure (locate_delta_images,
