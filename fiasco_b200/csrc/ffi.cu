@@ -35,6 +35,7 @@ struct fb200_ctx
    int		  trace_cap;
    TileWs	 *d_ws;
    int		 *d_lc_min;	/* [tiles] lc_min_level the tiles start with (fb200_wfa_t.lc_min_level) */
+   uint8_t	 *d_yc;		/* [tiles][2 * FB200_MAXSTATES] colour sequences: fb200_wfa_t.y_column_history */
    int		 *d_ready;	/* [tiles] epoch of the launch whose pixels have arrived (pipelined batches) */
    int		 *h_epoch;	/* pinned: the current epoch, source of the flag copies */
    int		  epoch;
@@ -271,11 +272,12 @@ derive (const fb200_params_t *p, const fb200_motion_t *mo, DevParams *d, char *e
    d->s_cap = p->state_capacity > 0 ? p->state_capacity : default_capacity (p);
    if (mo && mo->frame_type)
    {
-      if (mo->frame_type < 1 || mo->frame_type > FB200_FRAME_ND || p->bands != 1 || mo->search_range < 1
+      if (mo->frame_type < 1 || mo->frame_type > FB200_FRAME_INTRA || (p->bands != 1 && p->bands != 3)
+	  || (p->bands == 3 && mo->frame_type == FB200_FRAME_ND) || mo->search_range < 1
 	  || mo->search_range > 16)
       {
-	 set_err (err, errlen, "predicted frames: P and B frames (or intra frames with nondeterministic "
-		  "prediction) of grey sequences, search range 1..16");
+	 set_err (err, errlen, "predicted frames: P and B frames (grey or colour), or grey intra frames "
+		  "with nondeterministic prediction; search range 1..16");
 	 return FB200_EUNSUPPORTED;
       }
       /* prediction levels are a subset of the range levels (coder.c:284-290) */
@@ -399,6 +401,7 @@ fb200_destroy (fb200_ctx_t *c)
    cudaFree (c->d_trace);
    cudaFree (c->d_ws);
    cudaFree (c->d_lc_min);
+   cudaFree (c->d_yc);
    cudaFree (c->d_ready);
    cudaFreeHost (c->h_epoch);
    if (c->copy_stream)
@@ -466,6 +469,11 @@ ctx_alloc (fb200_ctx_t *c, char *err, size_t errlen)
 	 CUDA_TRY (cudaMalloc (&c->d_future, c->pix_elems * 2 * max_tiles));
       CUDA_TRY (cudaMalloc (&c->d_results, sizeof (TileResult) * max_tiles));
       CUDA_TRY (cudaMalloc (&c->d_ws, sizeof (TileWs) * max_tiles));
+      if (d.motion && d.bands == 3)
+      {
+	 CUDA_TRY (cudaMalloc (&c->d_yc, (size_t) 2 * FB200_MAXSTATES * max_tiles));
+	 CUDA_TRY (cudaMemset (c->d_yc, 0, (size_t) 2 * FB200_MAXSTATES * max_tiles));
+      }
       CUDA_TRY (cudaMalloc (&c->d_lc_min, sizeof (int) * max_tiles));
       CUDA_TRY (cudaMemset (c->d_lc_min, 0, sizeof (int) * max_tiles));
       CUDA_TRY (cudaMalloc (&c->d_ready, sizeof (int) * max_tiles));
@@ -518,6 +526,7 @@ ctx_alloc (fb200_ctx_t *c, char *err, size_t errlen)
 	 w.mv_type  = (int8_t *) (ab + aoff [10]);
 	 w.mv_fx    = (int8_t *) (ab + aoff [11]);
 	 w.mv_fy    = (int8_t *) (ab + aoff [12]);
+	 w.yc_ref   = c->d_yc ? c->d_yc + (size_t) 2 * FB200_MAXSTATES * t : NULL;
       }
       w.result	       = c->d_results + t;
       w.trace	       = t == 0 ? c->d_trace : NULL;
@@ -813,6 +822,7 @@ fb200_download (fb200_ctx_t *c, int n_tiles, fb200_wfa_t *out, fb200_trace_rec_t
 	 if (o.mv_by)		memcpy (o.mv_by, ab + aoff [14], n * 2);
       }
    }
+
    if (trace_len)
       *trace_len = 0;
    if (trace && trace_cap > 0 && c->d_trace)
@@ -934,7 +944,8 @@ fb200_encode_predicted (fb200_ctx_t *c, int n_tiles, const int16_t *const *plane
 {
    int rc;
 
-   if (!c || !c->dp.motion || (!past && c->dp.motion != FB200_FRAME_ND) || n_tiles < 1
+   if (!c || !c->dp.motion || (!past && c->dp.motion != FB200_FRAME_ND && c->dp.motion != FB200_FRAME_INTRA)
+       || n_tiles < 1
        || n_tiles > c->max_tiles || (c->dp.motion == 2 && !future))
    {
       set_err (err, errlen, "fb200_encode_predicted: needs a context of fb200_create_predicted() "
@@ -942,9 +953,23 @@ fb200_encode_predicted (fb200_ctx_t *c, int n_tiles, const int16_t *const *plane
       return FB200_EINVAL;
    }
    c->dp.trace_cap = 0;
+   {
+      /* the range levels the frames start with (colour sequences: fb200_wfa_t.lc_min_level) */
+      std::vector<int> lc (n_tiles);
+      bool		any = false;
+
+      for (int t = 0; t < n_tiles; t++)
+	 any |= (lc [t] = out [t].lc_min_level) > 0;
+      c->dp.tile_lc_min = any ? c->d_lc_min : NULL;
+      if (any)
+      {
+	 CUDA_TRY (cudaSetDevice (c->device));
+	 CUDA_TRY (cudaMemcpy (c->d_lc_min, lc.data (), sizeof (int) * n_tiles, cudaMemcpyHostToDevice));
+      }
+   }
    if ((rc = fb200_upload (c, n_tiles, planes, err, errlen)))
       return rc;
-   for (int t = 0; t < n_tiles && c->dp.motion != FB200_FRAME_ND; t++)
+   for (int t = 0; t < n_tiles && c->dp.motion != FB200_FRAME_ND && c->dp.motion != FB200_FRAME_INTRA; t++)
       {
       CUDA_TRY (cudaMemcpyAsync (c->d_past + c->pix_elems * t, past [t], c->pix_elems * 2,
 				 cudaMemcpyHostToDevice, c->stream));
@@ -959,9 +984,23 @@ fb200_encode_predicted (fb200_ctx_t *c, int n_tiles, const int16_t *const *plane
    int	 launches = 0;
    for (;;)
    {
+      /* colour frames: what the frames before left in the reference's y_column array (again before
+	 a second launch: the first one has written to it) */
+      for (int t = 0; t < n_tiles && c->d_yc; t++)
+	 if (out [t].y_column_history)
+	    CUDA_TRY (cudaMemcpyAsync (c->d_yc + (size_t) 2 * FB200_MAXSTATES * t, out [t].y_column_history,
+				       (size_t) 2 * FB200_MAXSTATES, cudaMemcpyHostToDevice, c->stream));
+	 else
+	    CUDA_TRY (cudaMemsetAsync (c->d_yc + (size_t) 2 * FB200_MAXSTATES * t, 0,
+				       (size_t) 2 * FB200_MAXSTATES, c->stream));
       if ((rc = fb200_launch (c, n_tiles, NULL, err, errlen)))
 	 return rc;
       rc = fb200_download (c, n_tiles, out, NULL, 0, NULL, err, errlen);
+      if (rc == FB200_OK && c->d_yc)
+	 for (int t = 0; t < n_tiles; t++)
+	    if (out [t].y_column_history)
+	       CUDA_TRY (cudaMemcpy (out [t].y_column_history, c->d_yc + (size_t) 2 * FB200_MAXSTATES * t,
+				     (size_t) 2 * FB200_MAXSTATES, cudaMemcpyDeviceToHost));
       total_ms += c->stats.kernel_ms;
       c->stats.kernel_ms       = total_ms;
       c->stats.kernel_launches = ++launches;
@@ -1018,7 +1057,8 @@ fb200_wfa_alloc (fb200_wfa_t *w, int capacity)
    w->mv_fy		 = (int8_t *) calloc ((size_t) capacity * 2, 1);
    w->mv_bx		 = (int8_t *) calloc ((size_t) capacity * 2, 1);
    w->mv_by		 = (int8_t *) calloc ((size_t) capacity * 2, 1);
-   if (!w->final_distribution || !w->level_of_state || !w->domain_type || !w->tree
+   w->y_column_history	 = (uint8_t *) calloc ((size_t) 2 * FB200_MAXSTATES, 1);
+   if (!w->y_column_history || !w->final_distribution || !w->level_of_state || !w->domain_type || !w->tree
        || !w->x || !w->y || !w->into || !w->weight || !w->y_state || !w->y_column
        || !w->mv_type || !w->mv_fx || !w->mv_fy || !w->mv_bx || !w->mv_by)
    {
@@ -1048,6 +1088,7 @@ fb200_wfa_free (fb200_wfa_t *w)
    free (w->mv_fy);
    free (w->mv_bx);
    free (w->mv_by);
+   free (w->y_column_history);
    memset (w, 0, sizeof *w);
 }
 

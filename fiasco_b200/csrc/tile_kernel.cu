@@ -301,6 +301,8 @@ struct FrameX
    int	    try_mc;		/* subdivide.c:141-147 */
    int	    try_nd;		/* subdivide.c:149-151: an intra frame coded with `--prediction' */
    float    ndw;		/* weight of the DC component that predicts the range (prediction.c:385) */
+   int	    saved_off;		/* hole_off before the prediction attempt */
+   int	    off_snap;		/* hole_off when the range was entered (beside Frame.states_snap) */
    int	    delta, prediction;	/* arguments of subdivide () */
    int	    pred_done;		/* the prediction alternative has been tried (and lost) */
    unsigned rec_states;		/* states after the first two alternatives */
@@ -428,6 +430,9 @@ struct ShHdr
    /* bulk copies (cp.async.bulk, the TMA unit) of table rows into shared memory complete on this */
    unsigned long long mbar;
    unsigned mbar_phase;
+   /* colour frames of a sequence: what the reference's wfa->y_column array holds (yc_ref below) */
+   int	    hole_off;		/* device state number - this = the state's number in the reference */
+   unsigned ref_max;		/* highest number of states the reference's luminance band reaches */
 };
 
 static_assert (offsetof (ShHdr, tree_total) == offsetof (ShHdr, tree_counts) + FB200_MAXLEVEL * sizeof (unsigned),
@@ -2721,6 +2726,54 @@ cta_mcpe_range (const DevParams &P, const TileWs &W, const Sh &cs, unsigned x0, 
 }
 
 /*
+ *  subtract_mc (mwfa.c:156-299): for every motion compensated range of the luminance tree the
+ *  displaced block of the reference frame(s) is taken off the Cb and Cr planes of the frame -- with
+ *  the vector components rounded towards zero to even numbers, (v / 2) * 2, which restore_mc on the
+ *  decoding side does not do; interpolated blocks as (a + b) / 2, 16-bit wrapping arithmetic.  The
+ *  ranges are disjoint: no barrier between them.
+ */
+template <int NT>
+__device__ void
+cta_subtract_mc (const DevParams &P, const TileWs &W, unsigned states)
+{
+   const int	tid   = threadIdx.x;
+   const size_t plane = (size_t) P.width * P.height;
+
+   for (unsigned a = 2 * 3; a < 2 * states; a++)
+   {
+      const int type = GP (W.mv_type) [a];
+
+      if (type == 0)
+	 continue;
+      const int level = (int) GP (W.level_of_state) [a >> 1] - 1;
+      const int bw = (int) width_of_level (level), bh = (int) height_of_level (level);
+      const int x0 = GP (W.x) [a], y0 = GP (W.y) [a];
+      const int fx = (GP (W.mv_fx) [a] / 2) * 2, fy = (GP (W.mv_fy) [a] / 2) * 2;
+      const int bx = (GP (W.mv_bx) [a] / 2) * 2, by = (GP (W.mv_by) [a] / 2) * 2;
+
+      for (int i = tid; i < 2 * bw * bh; i += NT)
+      {
+	 const int	band = 1 + i / (bw * bh), k = i % (bw * bh);
+	 const int	x = x0 + k % bw, y = y0 + k / bw;
+	 int16_t       *o    = const_cast<int16_t *> (GP (W.pix)) + band * plane + (size_t) y * P.width + x;
+	 const int16_t *past = GP (W.past) + band * plane, *fut = GP (W.future) + band * plane;
+	 int		ref;
+
+	 if (type == 1)
+	    ref = past [(size_t) (y + fy) * P.width + x + fx];
+	 else if (type == 2)
+	    ref = fut [(size_t) (y + by) * P.width + x + bx];
+	 else
+	    ref = ((int) past [(size_t) (y + fy) * P.width + x + fx]
+		   + (int) fut [(size_t) (y + by) * P.width + x + bx]) / 2;
+	 *o = (int16_t) (*o - ref);
+      }
+   }
+   __threadfence ();
+   __syncthreads ();
+}
+
+/*
  *  nd_prediction (prediction.c:409-421): the difference between the range and its DC prediction
  *  becomes the pixel block of the nested pass.  src: the range inside the outer block (bintree
  *  order); dc = -weight * images_of_state [0][0].  The differences are no integers: the node norms
@@ -2990,6 +3043,8 @@ t0_enter_speculated (const DevParams &P, const TileWs &W, const Sh &sh, Frame &F
    }
 
    F.states_snap     = h->states;
+   if (MOTION)
+      X->off_snap = h->hole_off;
    F.new_y_state [0] = F.new_y_state [1] = FB_RANGE;	/* (speculated ranges have no y-state) */
    lr.tree	   = FB_RANGE;
    lr.x		   = (unsigned short) F.x;
@@ -3253,7 +3308,7 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
       if (MOTION)
       {
 	 h->fx [0].delta      = 0;
-	 h->fx [0].prediction = 1;
+	 h->fx [0].prediction = band == 0 && P.motion != FB200_FRAME_INTRA;	/* coder.c:806-807: the chroma bands are not predicted */
       }
       t0_advance<MOTION, clustered_shape<NT, MOTION> ()> (P, W, sh, st, dp);
       h->state [0]  = st;
@@ -3391,6 +3446,8 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 		  }
 	       }
 	       F.states_snap = h->states;
+	       if (MOTION)
+		  h->fx [depth].off_snap = h->hole_off;
 	       /* y states of the children (subdivide.c:172-183) */
 	       if (!leaf)
 		  for (int label = 0; label < 2; label++)
@@ -3727,6 +3784,7 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 		     if (k != BLOB_U16 (sh, MB_N))
 			h->status = FB200_ECUDA;	/* cannot happen: the lists are prefixes of each other */
 		     h->states	 = X.rec_states;
+		     h->hole_off = X.saved_off;
 		     X.pred_done = 1;
 		     nstate	 = ST_DECIDE;
 		  }
@@ -3773,6 +3831,10 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 	       {
 		  X.rec_states = h->states;
 		  X.max_pred   = fmin2 (fmin2 (lin, sub), F.max_costs);
+		  /* the reference moves the states of the split alternative aside: the attempt's
+		     states take their numbers (store_state_data, prediction.c:502) */
+		  X.saved_off = h->hole_off;
+		  h->hole_off = X.off_snap + (int) (h->states - F.states_snap);
 	       }
 	       __syncthreads ();
 	       if (X.try_nd)
@@ -3996,6 +4058,8 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 	       if (tid == 0)
 	       {
 		  h->states = F.states_snap;	/* remove_states (wfalib.c:276-310) */
+		  if (MOTION)
+		     h->hole_off = h->fx [depth].off_snap;
 		  if (fail)
 		     h->ret_costs = FB_MAXCOSTS;
 		  else
@@ -4069,7 +4133,12 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 			if (c.into [e] == F.new_y_state [label])
 			   GP (W.y_column) [2 * s + label] = 1;
 		     }
+		     if (MOTION && W.yc_ref && band > 0)
+			GP (W.yc_ref) [2 * ((int) s - h->hole_off) + label] = GP (W.y_column) [2 * s + label];
 		  }
+		  /* (the luminance band writes zeros only: its highest state number is enough) */
+		  if (MOTION && band == 0 && s + 1 - (unsigned) h->hole_off > h->ref_max)
+		     h->ref_max = s + 1 - (unsigned) h->hole_off;
 		  t0_store_trans (W, s);
 		  res->into [0]	    = FB_NO_EDGE;
 		  res->tree	    = (short) s;
@@ -4208,7 +4277,10 @@ t0_virtual_state (const DevParams &P, const TileWs &W, ShHdr *h, int child0, int
       GP (W.y_state) [2 * s + label]	 = FB_RANGE;
       GP (W.x) [2 * s + label]	 = 0;
       GP (W.y) [2 * s + label]	 = 0;
-      GP (W.y_column) [2 * s + label] = 0;
+      /* the reference never sets this entry for a virtual state and writes it to the stream
+	 (output/matrices.c:491-516): it is what the last state that had this number left there --
+	 in this frame or in the frames before it (yc_ref, TileWs) */
+      GP (W.y_column) [2 * s + label] = W.yc_ref ? GP (W.yc_ref) [2 * ((int) s - h->hole_off) + label] : 0;
       GP (W.into) [(size_t) (2 * s + label) * 6] = FB_NO_EDGE;
    }
    GP (W.final_d) [s]	= t0_final_distribution (W, s);
@@ -4423,6 +4495,11 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
       h->lc_min = given > P.lc_min && given <= P.lc_max ? given : P.lc_min;
    }
    __syncthreads ();
+   if (tid == 0)
+   {
+      h->hole_off = 0;
+      h->ref_max  = 0;
+   }
    for (int band = 0; band < P.bands && h->status == FB200_OK; band++)
    {
       if (band == 1)
@@ -4430,6 +4507,14 @@ fiasco_tile_kernel (DevParams P, const TileWs *ws_array)
 	 if (tid == 0)
 	    t0_chroma_setup (P, W, sh, (int *) sh.bnd);
 	 __syncthreads ();
+	 /* every state number the luminance band has used holds a zero now (control.c:190) */
+	 if (MOTION && W.yc_ref)
+	    for (unsigned i = tid; i < 2 * h->ref_max; i += NT)
+	       GP (W.yc_ref) [i] = 0;
+	 /* a predicted colour frame: the motion compensation of the luminance tree comes off the
+	    chroma planes before they are coded (coder.c:798-799) */
+	 if (MOTION && (P.motion == 1 || P.motion == 2))
+	    cta_subtract_mc<NT> (P, W, h->states);
       }
       cta_subdivide_band<NT, MOTION> (P, s_W, sh, band, band ? band_tree [0] : FB_RANGE);
       if (h->status != FB200_OK)

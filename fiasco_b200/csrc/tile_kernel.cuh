@@ -126,6 +126,11 @@ struct TileWs
    uint8_t *saved_dt;		/* [s_cap]	 domain types of the states a prediction attempt hides */
    int8_t  *mv_type, *mv_fx, *mv_fy;	/* [s_cap][2] motion vectors of the ranges (wfa->mv_tree) */
    int8_t  *mv_bx, *mv_by;
+   uint8_t *yc_ref;		/* [FB200_MAXSTATES][2] or NULL: the reference's wfa->y_column array as the frames
+				   of the sequence so far have left it, by the reference's state numbers.  The
+				   reference writes the entries of a colour frame's three virtual states to the
+				   stream without ever setting them (output/matrices.c:491): stale values of states
+				   that had those numbers before, in this frame or an earlier one */
 };
 
 struct TileResult

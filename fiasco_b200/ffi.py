@@ -40,7 +40,7 @@ class _Wfa(C.Structure):
         ("into", C.c_void_p), ("weight", C.c_void_p), ("y_state", C.c_void_p), ("y_column", C.c_void_p),
         ("mv_type", C.c_void_p), ("mv_fx", C.c_void_p), ("mv_fy", C.c_void_p),
         ("mv_bx", C.c_void_p), ("mv_by", C.c_void_p),
-        ("lc_min_level", C.c_int), ("progress", (C.c_uint32 * 4) * 3),
+        ("lc_min_level", C.c_int), ("progress", (C.c_uint32 * 4) * 3), ("y_column_history", C.c_void_p),
     ]
 
 
@@ -176,11 +176,12 @@ class _WfaArrays:
         self.mv_fy = np.zeros((cap, 2), np.int8)
         self.mv_bx = np.zeros((cap, 2), np.int8)
         self.mv_by = np.zeros((cap, 2), np.int8)
+        self.y_column_history = np.zeros((6000, 2), np.uint8)
 
     def fill(self, w):
         w.capacity = self.cap
         for name in ("final_distribution", "level_of_state", "domain_type", "tree", "x", "y", "into", "weight",
-                     "y_state", "y_column", "mv_type", "mv_fx", "mv_fy", "mv_bx", "mv_by"):
+                     "y_state", "y_column", "mv_type", "mv_fx", "mv_fy", "mv_bx", "mv_by", "y_column_history"):
             setattr(w, name, getattr(self, name).ctypes.data)
 
 
@@ -259,22 +260,28 @@ class TileEncoder:
         _check(rc, err)
         return self._collect(n_tiles, trace, tl)
 
-    def encode_predicted(self, planes, past, future=None):
-        """One predicted frame per tile: planes[t] the frame, past[t] the regenerated previous frame
-        (future[t]: the regenerated next reference, B frames).  past=None: an intra frame with
-        nondeterministic prediction (a context of frame type FB200_FRAME_ND = 3)."""
-        n_tiles = len(planes)
+    def encode_predicted(self, planes, past, future=None, lc_min=None):
+        """One predicted frame per tile: planes the frames' bands (1 or 3 per tile), past[t] the regenerated
+        previous frame (all bands behind each other; future[t]: the regenerated next reference, B frames).
+        past=None: an intra frame with nondeterministic prediction (a context of frame type FB200_FRAME_ND
+        = 3).  lc_min[t]: the range level the frame starts with (frames of a colour sequence are chained)."""
+        bands = self.params.bands
+        n_tiles = len(planes) // bands
         ptrs = self._plane_ptrs(planes)
         keep = [self._keep]
-        pptrs = None
-        if past is not None:
-            pptrs = self._plane_ptrs(past)
-            keep.append(self._keep)
-        fptrs = None
-        if future is not None:
-            fptrs = self._plane_ptrs(future)
-            keep.append(self._keep)
+
+        def whole(frames):
+            frames = [np.ascontiguousarray(f, dtype=np.int16) for f in frames]
+            for f in frames:
+                assert f.size == bands * self.params.width * self.params.height
+            keep.append(frames)
+            return (C.c_void_p * len(frames))(*[f.ctypes.data for f in frames])
+
+        pptrs = whole(past) if past is not None else None
+        fptrs = whole(future) if future is not None else None
         self._keep = keep
+        for t in range(n_tiles):
+            self._wfas[t].lc_min_level = int(lc_min[t]) if lc_min is not None else 0
         err = C.create_string_buffer(512)
         _check(self.lib.fb200_encode_predicted(self.ctx, n_tiles, ptrs, pptrs, fptrs, self._wfas, err, 512), err)
         return self._collect(n_tiles, None, None)[0]

@@ -153,7 +153,8 @@ expand_names (char const *const *templates, name_list_t *out)
 *****************************************************************************/
 
 enum {T_INTRA = 0, T_P = 1, T_B = 2,
-      T_ND = 3};	/* (a kind of workspace only: intra frames with nondeterministic prediction) */
+      T_ND = 3,		/* (kinds of workspace only: intra frames with nondeterministic prediction, */
+      T_INTRA_SEQ = 4};	/* intra frames of a colour sequence that has predicted frames) */
 
 static int
 pattern_type (unsigned frame, const char *pattern)
@@ -285,8 +286,8 @@ typedef struct unit		/* one frame of one stream */
 typedef struct gpu
 {
    int		device;
-   fb200_ctx_t *ctx [4];	/* workspaces for intra, P and B frames, intra frames with ND prediction */
-   int		ctx_tiles [4];
+   fb200_ctx_t *ctx [5];	/* workspaces for intra, P and B frames, intra frames with ND prediction */
+   int		ctx_tiles [5];
    pthread_t	thread;
    int		failed;
    char		err [600];
@@ -446,11 +447,11 @@ wave_worker (void *arg)
       {
 	 int ok = 0;
 
-	 u->recon = calloc ((size_t) w->width * w->height, sizeof (int16_t));
+	 u->recon = calloc ((size_t) w->width * w->height * w->bands, sizeof (int16_t));
 	 if (u->recon)
-	    ok = fiasco_regenerate_frame (&u->wfa, &fm, (int) w->width, (int) w->height,
-					  w->type ? past [k] : NULL, w->type ? future [k] : NULL,
-					  u->recon);
+	    ok = (w->bands == 3 ? fiasco_regenerate_colour_frame : fiasco_regenerate_frame)
+		    (&u->wfa, &fm, (int) w->width, (int) w->height, w->type ? past [k] : NULL,
+		     w->type ? future [k] : NULL, u->recon);
 	 memcpy (fi_env, caller, sizeof caller);
 	 if (!ok)
 	 {
@@ -521,7 +522,7 @@ release_contexts (void *arg)
 {
    (void) arg;
    for (unsigned g = 0; g < FI_MAXGPUS; g++)
-      for (int t = 0; t < 4; t++)
+      for (int t = 0; t < 5; t++)
 	 if (job.gpus [g].ctx [t])
 	 {
 	    fb200_destroy (job.gpus [g].ctx [t]);
@@ -539,7 +540,7 @@ job_release (void)
       pthread_join (job.release_thread, NULL);
    job.prep_running = job.release_running = 0;
    for (unsigned g = 0; g < FI_MAXGPUS; g++)
-      for (int t = 0; t < 4; t++)
+      for (int t = 0; t < 5; t++)
 	 if (job.gpus [g].ctx [t])
 	    fb200_destroy (job.gpus [g].ctx [t]);
    for (size_t i = 0; i < job.n_units; i++)
@@ -852,9 +853,6 @@ coder (char const *const *inputname, const char *outputname, float quality,
    for (n = 0; n < frames; n++)
       if (job.sched.ctype [n])
       {
-	 if (color)
-	    fi_error ("Predicted frames are available for grey sequences only: code colour "
-		      "sequences with a frame pattern of I frames (--pattern=i).");
 	 if (cop->half_pixel_prediction)
 	    fi_error ("Half pixel motion compensation is not available in the B200 build.");
 	 if (!cop->normal_domains || !cop->delta_domains
@@ -1072,15 +1070,22 @@ coder (char const *const *inputname, const char *outputname, float quality,
 		  job.wave_future [w.cnt] = type == T_B ? base + job.sched.future [n] : NULL;
 		  /* a colour frame starts with the range levels its predecessor ended with */
 		  if (color && wv)
-		     base [n].wfa.lc_min_level
-			= base [job.sched.order [wv - 1]].wfa.lc_min_level;
+		  {
+		     const fb200_wfa_t *before = &base [job.sched.order [wv - 1]].wfa;
+
+		     base [n].wfa.lc_min_level = before->lc_min_level;
+		     /* ... and with what it left in the y_column entries of the state numbers
+			(fb200_wfa_t.y_column_history) */
+		     if (n_predicted && base [n].wfa.y_column_history && before->y_column_history)
+			memcpy (base [n].wfa.y_column_history, before->y_column_history, 2 * FI_MAXSTATES);
+		  }
 		  w.cnt++;
 	       }
 	    }
 	    if (!w.cnt)
 	       continue;
 	    w.type	= type;
-	    w.kind	= type == T_INTRA && nd ? T_ND : type;
+	    w.kind	= type == T_INTRA && nd ? T_ND : type == T_INTRA && color && n_predicted ? T_INTRA_SEQ : type;
 	    w.u		= job.wave_u;
 	    w.past	= job.wave_past;
 	    w.future	= job.wave_future;

@@ -118,6 +118,14 @@ typedef struct fb200_wfa
    /* out: the values the reference's percent meter prints while it codes band b
       (codec/subdivide.c:323-337), bit p of the 128-bit set = "p%" was shown */
    uint32_t  progress [3][4];
+   /* colour frames through fb200_encode_predicted (may be NULL): in / out, [FB200_MAXSTATES][2].  The
+      reference writes wfa->y_column of a colour frame's three virtual states to the stream
+      (output/matrices.c:491-516) although nothing ever sets those entries: they hold what the last
+      state with that number left there (append_transitions, codec/control.c:190-196; never cleared,
+      codec/wfalib.c:276-310) -- in this frame or in any frame of the sequence before it.  The array
+      is that history by the reference's state numbers: zeros before the first frame, then handed
+      from every coded frame to the next in coding order. */
+   uint8_t  *y_column_history;
 } fb200_wfa_t;
 
 /* one record per approximate_range() call (debug / parity tracing, optional) */
@@ -243,6 +251,9 @@ int fb200_motion_norms (int device, const int16_t *orig, const int16_t *past, in
  *  with the delta pool and delta coefficient model).  Levels and search range as in
  *  c_options_t (codec/options.h: p_min_level, p_max_level, search_range; CLI defaults 6, 10, 16).
  */
+#define FB200_FRAME_INTRA 4	/* an intra frame without any prediction on the workspace of predicted frames:
+				   the intra frames of a COLOUR sequence that has predicted frames, so that all
+				   its frames keep fb200_wfa_t.y_column_history */
 #define FB200_FRAME_ND 3	/* an INTRA frame coded with nondeterministic prediction (`cfiasco
 				   --prediction', fiasco_c_options_set_prediction; nd_prediction,
 				   codec/prediction.c:371): the third alternative of subdivide() is the
