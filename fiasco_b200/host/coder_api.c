@@ -1076,7 +1076,7 @@ coder (char const *const *inputname, const char *outputname, float quality,
 		     base [n].wfa.lc_min_level = before->lc_min_level;
 		     /* ... and with what it left in the y_column entries of the state numbers
 			(fb200_wfa_t.y_column_history) */
-		     if (n_predicted && base [n].wfa.y_column_history && before->y_column_history)
+		     if (base [n].wfa.y_column_history && before->y_column_history)
 			memcpy (base [n].wfa.y_column_history, before->y_column_history, 2 * FI_MAXSTATES);
 		  }
 		  w.cnt++;
@@ -1085,7 +1085,7 @@ coder (char const *const *inputname, const char *outputname, float quality,
 	    if (!w.cnt)
 	       continue;
 	    w.type	= type;
-	    w.kind	= type == T_INTRA && nd ? T_ND : type == T_INTRA && color && n_predicted ? T_INTRA_SEQ : type;
+	    w.kind	= type == T_INTRA && nd ? T_ND : type == T_INTRA && color && frames > 1 ? T_INTRA_SEQ : type;
 	    w.u		= job.wave_u;
 	    w.past	= job.wave_past;
 	    w.future	= job.wave_future;

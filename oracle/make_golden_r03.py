@@ -12,6 +12,16 @@ tests/golden/manifest.json, the automata (oracle/wfadump.c) of the small cases b
   g256_q20_nd      the 256^2 frame of the other goldens: --prediction never wins, the stream differs from
                    g256_q20_z0 only by its (empty) ND trees
   c128_q30_nd      a colour still: the flag changes the kind of the delta pool, nothing is predicted
+
+and of colour sequences with predicted frames (codec/coder.c:757-849, subtract_mc codec/mwfa.c:156):
+
+  cv160_q20_ippp      4 colour frames 160x128, IPPP
+  cv160_q20_ibbpbbp   7 frames with B frames (coded out of display order)
+  cv160_q20_i         5 frames, all intra: the frames still depend on each other (lc_min_level, coder.c:797,
+                      and the stale y_column entries of the virtual states, output/matrices.c:491)
+  cv160_q25_ippibp    intra frames in the middle of a sequence
+  cv160_q20_ippp_nd   IPPP with --prediction
+  cv352_q35_ipp       3 frames 352x288
 """
 import gzip
 import hashlib
@@ -54,6 +64,13 @@ def cases():
     yield "nd512_q80", [gen_frames.nd_still()], 80, "i", True
     yield "g256_q20_nd", [gen_frames.frame("g256")], 20, "i", False
     yield "c128_q30_nd", [gen_frames.colour_sequence(2, 128, 128)[1]], 30, "i", False
+    cv = gen_frames.colour_video(7, 160, 128)
+    yield "cv160_q20_ippp", cv[:4], 20, "ippp", True
+    yield "cv160_q20_ibbpbbp", cv, 20, "ibbpbbp", True
+    yield "cv160_q20_i", cv[:5], 20, "i", False
+    yield "cv160_q25_ippibp", cv, 25, "ippibp", False
+    yield "cv160_q20_ippp_nd", cv[:4], 20, "ippp", False
+    yield "cv352_q35_ipp", gen_frames.colour_video(3, 352, 288), 35, "ipp", False
 
 
 def main():
@@ -67,15 +84,17 @@ def main():
                 names.append(os.path.join(tmp, "%s_%d.%s" % (key, i, "pgm" if f.ndim == 2 else "ppm")))
                 gen_frames.write_pnm(names[-1], f)
             fco = os.path.join(tmp, key + ".fco")
-            subprocess.run([os.path.join(REF, "cfiasco"), "--progress-meter=0", "-V", "0", "-q", str(q), "--prediction",
-                            "--pattern=" + pattern, "-o", fco, *names], check=True, env=env, stderr=subprocess.DEVNULL)
+            nd = not key.startswith("cv") or key.endswith("_nd")
+            subprocess.run([os.path.join(REF, "cfiasco"), "--progress-meter=0", "-V", "0", "-q", str(q),
+                            *(["--prediction"] if nd else []), "--pattern=" + pattern, "-o", fco, *names], check=True,
+                           env=env, stderr=subprocess.DEVNULL)
             fb = open(fco, "rb").read()
             dump = subprocess.run([os.path.join(REF, "wfadump"), fco], check=True, env=env, capture_output=True).stdout
             if keep_dump:
                 with gzip.GzipFile(os.path.join(GOLD, key + ".wfa.gz"), "wb", mtime=0) as f:
                     f.write(dump)
             h, w = frames[0].shape[:2]
-            manifest[key] = {"nd_prediction": True, "frames": len(frames), "width": w, "height": h, "quality": q,
+            manifest[key] = {"nd_prediction": nd, "frames": len(frames), "width": w, "height": h, "quality": q,
                              "pattern": pattern, "color": int(frames[0].ndim == 3), "fco_md5": md5(fb),
                              "fco_bytes": len(fb), "nd_ranges": nd_labels(dump.decode())}
             print(key, manifest[key], flush=True)

@@ -478,3 +478,102 @@ def test_emulated_fiasco_coder_nd_prediction_streams(emu, tmp_path):
             check_nd_coder_stream(name, tmp_path)
     finally:
         hostlib._LIB, hostlib.lib_path = saved
+
+
+# --------------------------------------------------------- colour sequences with predicted frames
+
+def colour_case_frames(name):
+    m = O.manifest()[name]
+    frames = gen_frames.colour_video(7 if m["width"] == 160 else 3, m["width"], m["height"])[:m["frames"]]
+    return m, frames
+
+
+def check_colour_predicted_frames_against_oracle(name, which=None):
+    """Colour P / B frames through the C ABI: luminance with prediction, the luminance tree's motion
+    compensation taken off the chroma planes on the device (subtract_mc, codec/mwfa.c:156), chroma bands on
+    the same workspace -- state for state against the oracle run in holes mode, every frame predicted from
+    the oracle's regenerated reference frames, starting with the range level the frame before left."""
+    m, frames = colour_case_frames(name)
+    L = O.lib()
+    L.fo_set_holes_mode(1)
+    try:
+        ws, rec = O.encode_video(frames, quality=m["quality"], pattern=m["pattern"])
+    finally:
+        L.fo_set_holes_mode(0)
+    p = ffi.make_params(m["width"], m["height"], 3, float(m["quality"]), 0)
+    coded = {w["_struct"].frame_number: k for k, w in enumerate(ws)}
+
+    def lc_min_after(st):
+        d = O.struct_dict(st)
+        y_root = d["tree"][d["tree"][d["root_state"]][0]][0]
+        levels = [int(d["level_of_state"][s]) - 1 for s in range(3, y_root + 1)
+                  if d["level_of_state"][s] != 255 and (d["tree"][s] < 0).any()]
+        return min(levels)
+
+    encs, checked = {}, 0
+    past = future = reconst = None
+    future_frame, expected, seen = False, 0, set()
+    try:
+        for k, w in enumerate(ws):
+            od = O.struct_dict(w["_struct"])
+            t = od["frame_type"]
+            if t == 0:
+                past = future = reconst = None
+            elif t == 1:
+                past, future, reconst = reconst, None, None
+            elif future_frame:
+                future, reconst = reconst, None
+            else:
+                past, reconst = reconst, None
+            seen.add(od["frame_number"])
+            future_frame = od["frame_number"] > expected
+            while expected in seen:
+                expected += 1
+            reconst = rec[k]
+            if t == 0 or (which is not None and k not in which):
+                continue
+            if t not in encs:
+                encs[t] = F.TileEncoder(p, 1, motion=F.Motion(t, 6, 10, 16))
+            g = encs[t].encode_predicted(O.planes_of(frames[od["frame_number"]]), [past],
+                                         [future] if t == 2 else None, lc_min=[lc_min_after(ws[k - 1]["_struct"])])[0]
+            assert_same_predicted_automaton(g, od)
+            checked += 1
+    finally:
+        for e in encs.values():
+            e.close()
+    assert coded and checked
+    return checked
+
+
+def check_colour_coder_stream(name, tmp_path):
+    """fiasco_coder() on a colour sequence with predicted frames: the bytes of the reference cfiasco."""
+    import hashlib
+    from fiasco_b200 import hostlib
+    m, frames = colour_case_frames(name)
+    names = []
+    for i, f in enumerate(frames):
+        names.append(str(tmp_path / ("c%02d.ppm" % i)))
+        gen_frames.write_pnm(names[-1], f)
+    o = hostlib.cli_options(0)
+    L = hostlib.load()
+    L.fiasco_c_options_set_frame_pattern(o, m["pattern"].encode())
+    L.fiasco_c_options_set_prediction(o, int(m["nd_prediction"]), 6, 10)
+    out = str(tmp_path / "cv.fco")
+    ok, msg = hostlib.coder(names, out, float(m["quality"]), options=o)
+    assert ok, msg
+    b = open(out, "rb").read()
+    assert (len(b), hashlib.md5(b).hexdigest()) == (m["fco_bytes"], m["fco_md5"])
+
+
+def test_emulated_device_code_colour_predicted_frame(emu):
+    assert check_colour_predicted_frames_against_oracle("cv160_q20_ippp", which=(1,)) == 1
+
+
+def test_emulated_fiasco_coder_colour_sequence_with_predicted_frames(emu, tmp_path):
+    from fiasco_b200 import hostlib
+    saved = (hostlib._LIB, hostlib.lib_path)
+    hostlib._LIB, hostlib.lib_path = None, (lambda: os.path.join(EMU_DIR, "_build", "libfiasco_emu.so"))
+    try:
+        check_colour_coder_stream("cv160_q20_ippp", tmp_path)
+    finally:
+        hostlib._LIB, hostlib.lib_path = saved

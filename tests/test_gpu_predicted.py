@@ -159,3 +159,19 @@ def test_gpu_cli_prediction_flag(tmp_path):
                        env=env, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert md5(out) == m["fco_md5"]
+
+
+# --------------------------------------------------------- colour sequences with predicted frames
+
+from test_emu_device_code import check_colour_coder_stream, check_colour_predicted_frames_against_oracle  # noqa: E402
+
+
+@pytest.mark.parametrize("name", ["cv160_q20_ippp", "cv160_q20_ibbpbbp", "cv352_q35_ipp"])
+def test_gpu_colour_predicted_frames_match_oracle(name):
+    assert check_colour_predicted_frames_against_oracle(name) >= 2
+
+
+@pytest.mark.parametrize("name", ["cv160_q20_ippp", "cv160_q20_ibbpbbp", "cv160_q20_i", "cv160_q25_ippibp",
+                                  "cv160_q20_ippp_nd", "cv352_q35_ipp"])
+def test_gpu_fiasco_coder_colour_sequences(name, tmp_path):
+    check_colour_coder_stream(name, tmp_path)

@@ -217,3 +217,38 @@ def test_nd_prediction_stream_is_byte_identical_to_reference(name, tmp_path):
     hostlib.write_video_stream(out, p, [O.struct_dict(w["_struct"]) for w in ws], nd_prediction=True)
     b = open(out, "rb").read()
     assert (len(b), hashlib.md5(b).hexdigest()) == (m["fco_bytes"], m["fco_md5"])
+
+
+@pytest.mark.parametrize("name", ["cv160_q20_ippp", "cv160_q20_ibbpbbp"])
+def test_colour_video_stream_and_regenerated_frames(name, tmp_path):
+    """Host side of colour sequences with predicted frames, from the oracle's automata: the stream writer
+    gives the reference's bytes (the y_column entries of the virtual states included, which the reference
+    writes without setting them), and fiasco_regenerate_colour_frame() -- three bands, the luminance
+    tree's vectors, chroma clipping -- the frames the oracle regenerates."""
+    import hashlib
+    from test_emu_device_code import colour_case_frames
+    m, frames = colour_case_frames(name)
+    ws, rec = O.encode_video(frames, quality=m["quality"], pattern=m["pattern"])
+    p = ffi.make_params(m["width"], m["height"], 3, float(m["quality"]), 0)
+    out = str(tmp_path / "cv.fco")
+    hostlib.write_video_stream(out, p, [O.struct_dict(w["_struct"]) for w in ws])
+    b = open(out, "rb").read()
+    assert (len(b), hashlib.md5(b).hexdigest()) == (m["fco_bytes"], m["fco_md5"])
+    past = future = reconst = None
+    future_frame, expected, seen = False, 0, set()
+    for k, w in enumerate(ws):
+        d = O.struct_dict(w["_struct"])
+        if d["frame_type"] == 0:
+            past = future = reconst = None
+        elif d["frame_type"] == 1:
+            past, future, reconst = reconst, None, None
+        elif future_frame:
+            future, reconst = reconst, None
+        else:
+            past, reconst = reconst, None
+        seen.add(d["frame_number"])
+        future_frame = d["frame_number"] > expected
+        while expected in seen:
+            expected += 1
+        reconst = hostlib.regenerate_frame(d, m["width"], m["height"], past, future, colour=True)
+        assert np.array_equal(reconst, rec[k]), "coded frame %d" % k
