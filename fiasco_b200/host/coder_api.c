@@ -24,10 +24,10 @@
  *			      stream (exactly what the reference produces for the cropped pictures)
  *			      and written to <output>.tNN.<ext>, NN = row-major tile number.
  *
- *  Supported: stills and sequences, grey and colour (4:4:4) intra frames, P and B frames of grey
- *  sequences (full-pixel vectors), the built-in initial basis "small.fco", rle domain pool,
- *  adaptive coefficient model, optimisation levels 0..2 of the command line.  Everything else is
- *  refused with an error message (never silently approximated).
+ *  Supported: stills and sequences, grey and colour (4:4:4), intra, P and B frames (full-pixel
+ *  vectors), nondeterministic prediction of intra frames, the built-in initial basis "small.fco",
+ *  rle domain pool, adaptive coefficient model, optimisation levels 0..2 of the command line.
+ *  Everything else is refused with an error message (never silently approximated).
  */
 #include <ctype.h>
 #include <math.h>
