@@ -208,7 +208,7 @@ def scratch_dir(need_bytes):
     return tempfile.mkdtemp(prefix="fb200_bench_")
 
 
-def coder_call(inputs, out, quality, pattern=None, optimize=0, env=None):
+def coder_call(inputs, out, quality, pattern=None, optimize=0, env=None, prediction=False):
     """One fiasco_coder() call (the reference's public entry point, include/fiasco.h) with the CLI's
     default options.  Returns (seconds, work counters of the call)."""
     from fiasco_b200 import ffi, hostlib
@@ -217,6 +217,8 @@ def coder_call(inputs, out, quality, pattern=None, optimize=0, env=None):
     L.fiasco_c_options_set_progress_meter(o, 0)
     if pattern:
         L.fiasco_c_options_set_frame_pattern(o, pattern.encode())
+    if prediction:                                 # cfiasco --prediction (nd_prediction, codec/prediction.c:371)
+        L.fiasco_c_options_set_prediction(o, 1, 6, 10)
     saved = {k: os.environ.get(k) for k in (env or {})}
     for k, v in (env or {}).items():
         os.environ[k] = str(v)
@@ -281,6 +283,39 @@ def config_records(tmp):
                  "mpixels_per_s": mpx / best, "seconds": best, "kernel_ms": cnt["kernel_ms"],
                  "kernel_launches": cnt["launches"], "md5_matches_reference": md5_of(dst) == m["fco_md5"],
                  "through": "fiasco_coder(), one process, one GPU, best of 2 calls"}
+    # beyond BASELINE's list: the same sequence geometry in colour (every frame of a colour sequence depends on the
+    # frame coded before it -- range levels, coder.c:797, y_column history -- so the frames run one after the other),
+    # and a still with nondeterministic prediction (cfiasco --prediction)
+    if "cv720_q20_ippp" in man:
+        m = man["cv720_q20_ippp"]
+        cd = os.path.join(tmp, "cvideo")
+        os.makedirs(cd, exist_ok=True)
+        for i, f in enumerate(gen_frames.colour_video(m["frames"], m["width"], m["height"])):
+            gen_frames.write_pnm(os.path.join(cd, "c%02d.ppm" % i), f)
+        dst = os.path.join(tmp, "c5c.fco")
+        dt, cnt = coder_call([os.path.join(cd, "c[00-%02d].ppm" % (m["frames"] - 1))], dst, float(m["quality"]),
+                             pattern=m["pattern"], env={"FIASCO_GPUS": 1})
+        out["c5_colour"] = {"workload": "%d COLOUR frames %dx%d, pattern %s, q=%g" % (m["frames"], m["width"], m["height"],
+                                                                                    m["pattern"], m["quality"]),
+                            "mpixels_per_s": m["frames"] * m["width"] * m["height"] / 1e6 / dt, "seconds": dt,
+                            "kernel_ms": cnt["kernel_ms"], "kernel_launches": cnt["launches"],
+                            "md5_matches_reference": md5_of(dst) == m["fco_md5"],
+                            "through": "fiasco_coder(), one process, one GPU, one call"}
+    if "nd512_q80" in man:
+        m = man["nd512_q80"]
+        pnm = os.path.join(tmp, "nd512.pgm")
+        gen_frames.write_pnm(pnm, gen_frames.nd_still())
+        dst = os.path.join(tmp, "nd512.fco")
+        best, cnt = None, None
+        for _ in range(3):
+            dt, c = coder_call([pnm], dst, float(m["quality"]), env={"FIASCO_GPUS": 1}, prediction=True)
+            if best is None or dt < best:
+                best, cnt = dt, c
+        out["nd512"] = {"workload": "512x512 grey still, q=%g, --prediction (%d ranges predicted)" % (m["quality"],
+                                                                                                   m["nd_ranges"]),
+                        "mpixels_per_s": 512 * 512 / 1e6 / best, "seconds": best, "kernel_ms": cnt["kernel_ms"],
+                        "kernel_launches": cnt["launches"], "md5_matches_reference": md5_of(dst) == m["fco_md5"],
+                        "through": "fiasco_coder(), best of 3 calls"}
     return out
 
 

@@ -3854,7 +3854,11 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 		     X.mctype = 0;
 		     X.mx = X.my = X.bx = X.by = 0;
 		     X.mvt    = t0_ptree_bits (h, 0, level);
-		     X.mvc    = (float) (0.0 - dev_log2d (counts [code] / (float) sh.blob [MB_TOTALS]));
+		     /* (a weight that rounds to zero, code RPF_ZERO = -1: the reference reads the word in
+			front of its counts, coeff.c:237 -- zero, the upper end of the allocator's chunk
+			size -- and gets infinitely many bits: never taken) */
+		     X.mvc    = code < 0 ? FB_MAXCOSTS * FB_MAXCOSTS
+					 : (float) (0.0 - dev_log2d (counts [code] / (float) sh.blob [MB_TOTALS]));
 		     X.pcosts = h->price * (X.mvc + X.mvt);
 		  }
 	       }

@@ -231,19 +231,24 @@ fi_encode_array (fi_bits_t *b, const unsigned *data, const unsigned *context,
    fi_ac_init (&ac, b);
    for (n = 0; n < n_data; n++)
    {
-      const unsigned d = data [n];
-      unsigned	     range;
-      uint16_t	     scale, low_count, high_count;
+      /* The reference takes the symbol as an int (lib/arith.c:251): the code of a weight that rounds
+	 to zero, RPF_ZERO = -1 -- which only the DC weight of a nondeterministic prediction can be
+	 (output/nd.c:222, no zero check there) -- makes it read the 16-bit word in front of its table:
+	 the upper end of glibc's chunk size field, zero for every chunk below 2^48 bytes.  The same
+	 value is used here; the update below then starts at entry 0, as it does there. */
+      const int d = (int) data [n];
+      unsigned	range;
+      uint16_t	scale, low_count, high_count;
 
       c		 = n_context > 1 ? context [n] : 0;
       scale	 = totals [c][c_symbols [c]];
-      low_count	 = totals [c][d];
+      low_count	 = d < 0 ? 0 : totals [c][d];
       high_count = totals [c][d + 1];
       range	 = (unsigned) (ac.high - ac.low) + 1;
       ac.high	 = (uint16_t) (ac.low + (uint16_t) ((range * high_count) / scale - 1));
       ac.low	 = (uint16_t) (ac.low + (uint16_t) ((range * low_count) / scale));
       fi_ac_rescale (&ac);
-      for (i = d + 1; i < c_symbols [c] + 1; i++)
+      for (i = (unsigned) (d + 1); i < c_symbols [c] + 1; i++)
 	 totals [c][i]++;
       if (totals [c][c_symbols [c]] > scaling)
 	 for (i = 1; i < c_symbols [c] + 1; i++)

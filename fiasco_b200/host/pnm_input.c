@@ -31,6 +31,9 @@ skip_space_and_comments (FILE *f)
    }
 }
 
+/* an error while a file is open: the handle does not outlive the message (fi_error() does not return) */
+#define PNM_ERROR(f, ...) do { if ((f) && (f) != stdin) fclose (f); fi_error (__VA_ARGS__); } while (0)
+
 static int
 read_number (FILE *f)
 {
@@ -45,7 +48,7 @@ read_number (FILE *f)
    if (c != EOF)
       ungetc (c, f);
    if (!digits)
-      fi_error ("Format error: can't read PNM header.");
+      PNM_ERROR (f, "Format error: can't read PNM header.");
    return value;
 }
 
@@ -64,18 +67,18 @@ open_pnm (const char *name, unsigned *width, unsigned *height, int *color)
    else if (m0 == 'P' && m1 == '6')
       *color = 1;
    else
-      fi_error ("%s: image format '%c%c' not supported.", name ? name : "stdin", m0, m1);
+      PNM_ERROR (f, "%s: image format '%c%c' not supported.", name ? name : "stdin", m0, m1);
    v = read_number (f);
    if (v < 32)
-      fi_error ("Width of image `%s' has to be at least 32 pixels.", name ? name : "stdin");
+      PNM_ERROR (f, "Width of image `%s' has to be at least 32 pixels.", name ? name : "stdin");
    *width = (unsigned) v;
    v = read_number (f);
    if (v < 32)
-      fi_error ("Height of image `%s' has to be at least 32 pixels.", name ? name : "stdin");
+      PNM_ERROR (f, "Height of image `%s' has to be at least 32 pixels.", name ? name : "stdin");
    *height = (unsigned) v;
    (void) read_number (f);		/* maxval */
    if (fgetc (f) == EOF)		/* the single white space before the raster */
-      fi_error ("%s: EOF reached, input seems to be truncated!", name ? name : "stdin");
+      PNM_ERROR (f, "%s: EOF reached, input seems to be truncated!", name ? name : "stdin");
    return f;
 }
 
@@ -97,7 +100,7 @@ fi_read_image (const char *name)
    fi_image_t *img;
 
    if ((width & 1) || (height & 1))
-      fi_error ("Width and height of images must be even numbers.");
+      PNM_ERROR (f, "Width and height of images must be even numbers.");
    img	       = fiasco_calloc (1, sizeof (fi_image_t));
    img->width  = width;
    img->height = height;
@@ -115,6 +118,8 @@ fi_read_image (const char *name)
       if (fread (raw, 1, bytes, f) != bytes)
       {
 	 free (raw);
+	 if (f != stdin)
+	    fclose (f);
 	 fi_file_error (name ? name : "stdin");
       }
       if (!color)

@@ -1951,11 +1951,20 @@ mc_prediction (float max_costs, float price, unsigned band, int y_state, range_t
    predicted by its DC component (state 0, weight quantised with the DC format) and the
    difference is subdivided with the delta models; taken only if the difference is split */
 static int nd_prediction_on = 0;
+static unsigned nd_zero_weights = 0;	/* DC weights that rounded to zero since the last fo_set_nd_prediction() */
+
+unsigned
+fo_nd_zero_weights (void)
+{
+   return nd_zero_weights;
+}
 
 void
 fo_set_nd_prediction (int on)
 {
    nd_prediction_on = on;
+   if (on)
+      nd_zero_weights = 0;
 }
 
 static float
@@ -1981,7 +1990,13 @@ nd_prediction (float max_costs, float price, unsigned band, int y_state, range_t
       lrange.nd_weights_bits = 0;
       lrange.tree_bits	     = 0;
       lrange.matrix_bits     = 0;
-      lrange.weights_bits    = aac_bits (&wt, s, range->level, &c->coeff);
+      /* a weight that rounds to zero has the code RPF_ZERO = -1: the reference then reads the 16-bit
+	 word in front of its table of counts (coeff.c:237) -- the upper end of the allocator's chunk
+	 size, zero -- and the bits are -log2 (0) = infinite: such a prediction is never taken */
+      lrange.weights_bits    = rtob (wt, &c->dc_rpf) < 0 ? INFINITY
+						      : aac_bits (&wt, s, range->level, &c->coeff);
+      if (rtob (wt, &c->dc_rpf) < 0)
+	 nd_zero_weights++;
    }
    costs = price * (lrange.weights_bits + lrange.nd_tree_bits);
 

@@ -166,6 +166,9 @@ void fo_fill_norms_table (const int16_t *orig, const int16_t *past, unsigned wid
 /* `cfiasco --prediction' (fiasco_c_options_set_prediction): the intra frames of fo_encode_video try
    the nondeterministic prediction of codec/prediction.c:371 (DC component + delta image) */
 void fo_set_nd_prediction (int on);
+/* test aid: DC weights that rounded to zero (infinitely many bits in the reference, codec/coeff.c:237 reading in
+   front of its table: never taken) since nondeterministic prediction was last switched on */
+unsigned fo_nd_zero_weights (void);
 
 /* design check of the device's state handling for predicted frames (see fiasco_oracle.c) */
 void fo_set_holes_mode (int on);

@@ -71,6 +71,8 @@ def cases():
     yield "cv160_q25_ippibp", cv, 25, "ippibp", False
     yield "cv160_q20_ippp_nd", cv[:4], 20, "ippp", False
     yield "cv352_q35_ipp", gen_frames.colour_video(3, 352, 288), 35, "ipp", False
+    if "big" in sys.argv[1:]:       # BASELINE config 5 in colour: 30 frames 720x576 (minutes of reference time)
+        yield "cv720_q20_ippp", gen_frames.colour_video(30, 720, 576), 20, "ippp", False
 
 
 def main():
@@ -79,6 +81,8 @@ def main():
     with tempfile.TemporaryDirectory() as tmp:
         env = dict(os.environ, FIASCO_DATA=os.path.join(REF, "data"), FIASCO_IMAGES=tmp)
         for key, frames, q, pattern, keep_dump in cases():
+            if "big" in sys.argv[1:] and key != "cv720_q20_ippp":
+                continue
             names = []
             for i, f in enumerate(frames):
                 names.append(os.path.join(tmp, "%s_%d.%s" % (key, i, "pgm" if f.ndim == 2 else "ppm")))

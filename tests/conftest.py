@@ -14,7 +14,8 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 # subprocess that loads the real library, workspace counts taken from the SM count)
 _NEEDS_HARDWARE = ("test_gpu_more_tiles_than_workspaces", "test_gpu_random_crops_match_oracle",
                    "test_gpu_motion_norms_match_reference_loops", "test_unchanged_reference_cli_on_our_library",
-                   "test_progress_meter_output", "test_gpu_cli_prediction_flag")
+                   "test_progress_meter_output", "test_gpu_cli_prediction_flag",
+                   "test_gpu_fiasco_coder_colour_sequence_at_config5_size")
 
 
 def pytest_addoption(parser):

@@ -137,7 +137,8 @@ def test_gpu_nd_prediction_frames_match_oracle(name):
     assert check_nd_frames_against_oracle(name) > 0
 
 
-@pytest.mark.parametrize("name", ["nd160_q70_i", "nd160_q70_ippp", "nd512_q80", "g256_q20_nd", "c128_q30_nd"])
+@pytest.mark.parametrize("name", ["nd160_q70_i", "nd160_q70_ippp", "nd512_q80", "g256_q20_nd", "c128_q30_nd",
+                                  "nd222_q60_zero_dc"])
 def test_gpu_fiasco_coder_nd_prediction_streams(name, tmp_path):
     check_nd_coder_stream(name, tmp_path)
 
@@ -175,3 +176,10 @@ def test_gpu_colour_predicted_frames_match_oracle(name):
                                   "cv160_q20_ippp_nd", "cv352_q35_ipp"])
 def test_gpu_fiasco_coder_colour_sequences(name, tmp_path):
     check_colour_coder_stream(name, tmp_path)
+
+
+def test_gpu_fiasco_coder_colour_sequence_at_config5_size(tmp_path):
+    """BASELINE config 5's geometry in colour: 30 frames 720x576, IPPP, q = 20 -- every frame chained to the
+    one before it (range levels, y_column history); the reference's bytes (c5cbb7cf...)."""
+    check_colour_coder_stream("cv720_q20_ippp", tmp_path)
+    assert O.manifest()["cv720_q20_ippp"]["fco_md5"] == "c5cbb7cfb29d9a6368b039e9d41716c0"
