@@ -1099,6 +1099,8 @@ t0_node_norm (const DevParams &P, const Sh &sh, unsigned image, unsigned address
 {
    int s = sh.norm_i [image];
 
+   if (s < 0)			/* the difference block of a nondeterministic prediction: cta_nd_range */
+      return __uint_as_float ((unsigned) s & 0x7fffffffu);
    if (s <= (1 << 24))
       return (float) s;		/* every partial sum is an exactly representable integer */
    const float *px = sh.pixels + ((size_t) address << level);
@@ -2777,8 +2779,8 @@ cta_subtract_mc (const DevParams &P, const TileWs &W, unsigned states)
  *  nd_prediction (prediction.c:409-421): the difference between the range and its DC prediction
  *  becomes the pixel block of the nested pass.  src: the range inside the outer block (bintree
  *  order); dc = -weight * images_of_state [0][0].  The differences are no integers: the node norms
- *  of the nested pass are the reference's left-to-right fp32 sums (t0_node_norm's long form, the
- *  integer table holds a value beyond its limit).
+ *  of the nested pass are the reference's left-to-right fp32 sums, worked out here for all nodes at
+ *  once.
  */
 template <int NT>
 __device__ void
@@ -2791,8 +2793,20 @@ cta_nd_range (const DevParams &P, const TileWs &W, const Sh &outer, const Sh &cs
 
    for (unsigned i = tid; i < size; i += NT)
       cs.pixels [i] = src [i] + dc;
+   __syncthreads ();
+   /* one thread per node of the block's tree, each its own left-to-right sum (approx.c:388-389); the
+      table holds the float's bits with the sign bit set -- an integer sum is never negative */
    for (unsigned k = tid; k < (2u << (level - P.lmin)) - 1; k += NT)
-      cs.norm_i [k] = 0x7fffffff;
+   {
+      const unsigned d	  = 31u - (unsigned) __clz ((int) (k + 1));	/* depth of node k */
+      const unsigned lvl  = (unsigned) level - d;
+      const float   *px	  = cs.pixels + ((size_t) (k + 1 - (1u << d)) << lvl);
+      float	     norm = 0;
+
+      for (unsigned i = 0; i < (1u << lvl); i++)
+	 norm += px [i] * px [i];
+      cs.norm_i [k] = (int) (__float_as_uint (norm) | 0x80000000u);
+   }
    __syncthreads ();
 }
 
@@ -3025,9 +3039,14 @@ t0_enter_speculated (const DevParams &P, const TileWs &W, const Sh &sh, Frame &F
       /* what ST_ENTER sets up for the motion compensated alternative (subdivide.c:141-147) */
       mvt	   = h->job.node [k].mv_tree_bits;
       X->try_mc	   = mvt != 0.0f;
-      X->try_nd	   = 0;		/* (no spines where nondeterministic prediction is tried) */
+      /* (an intra frame with nondeterministic prediction: the prediction tree model has not changed
+	 since the spine was started -- no child has returned -- so the bits of "not predicted here"
+	 are those of this moment, as in ST_ENTER) */
+      X->try_nd	   = P.motion == 3 && X->prediction && level >= P.p_min && level <= P.p_max;
       X->pred_done = 0;
       X->lrange.mv_tree_bits  = mvt;
+      if (X->try_nd)
+	 mvt = t0_ptree_bits (h, 1, level);
       X->lrange.mv_coord_bits = 0;
       X->lrange.mv_type = X->lrange.mv_fx = X->lrange.mv_fy = X->lrange.prediction = 0;
       X->lrange.mv_bx = X->lrange.mv_by = 0;
@@ -3491,8 +3510,7 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 	       const int       sk    = CL ? F.spec_k : 0;
 	       bool	       spine = false;
 
-	       if (CL && sk < 0 && F.y_state < 0 && !P.second_domain_block
-		   && !(MOTION && P.motion == 3 && h->fx [depth].prediction))
+	       if (CL && sk < 0 && F.y_state < 0 && !P.second_domain_block)
 	       {
 		  /*
 		   *  Head of a spine: the ranges reached from here by label 0 alone, down to
@@ -3529,7 +3547,7 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 			nd.norm	     = t0_node_norm (P, cs, nd.image, nd.address, nd.level);
 			/* motion compensation allowed for the range? (subdivide.c:141-147; the range shares
 			   its corner with this one, so it lies inside the frame if this one does) */
-			nd.mv_tree_bits = MOTION && h->fx [depth].prediction && level - k >= P.p_min
+			nd.mv_tree_bits = MOTION && P.motion != 3 && h->fx [depth].prediction && level - k >= P.p_min
 					  && level - k <= P.p_max
 					  && F.x + width_of_level (level - k) <= (unsigned) P.width
 					  && F.y + height_of_level (level - k) <= (unsigned) P.height ? 1.0f : 0.0f;

@@ -183,3 +183,41 @@ def test_gpu_fiasco_coder_colour_sequence_at_config5_size(tmp_path):
     one before it (range levels, y_column history); the reference's bytes (c5cbb7cf...)."""
     check_colour_coder_stream("cv720_q20_ippp", tmp_path)
     assert O.manifest()["cv720_q20_ippp"]["fco_md5"] == "c5cbb7cfb29d9a6368b039e9d41716c0"
+
+
+def test_gpu_tile_split_of_a_colour_sequence(tmp_path):
+    """FIASCO_TILE_SPLIT on a colour sequence with predicted frames: four independent streams, each chained
+    through its own frames (range levels, y_column history), several colour frames per launch -- every tile's
+    file equals what the reference binary writes for the cropped frames."""
+    cf = os.path.join(REF, "cfiasco")
+    if not os.path.exists(cf):
+        pytest.skip("reference binary not on this box")
+    frames = gen_frames.colour_video(3, 320, 256)
+    names = []
+    for i, f in enumerate(frames):
+        names.append(str(tmp_path / ("s%02d.ppm" % i)))
+        gen_frames.write_pnm(names[-1], f)
+    L = hostlib.load()
+    o = hostlib.cli_options(0)
+    L.fiasco_c_options_set_frame_pattern(o, b"ipp")
+    saved = os.environ.get("FIASCO_TILE_SPLIT")
+    os.environ["FIASCO_TILE_SPLIT"] = "2"
+    try:
+        ok, msg = hostlib.coder(names, str(tmp_path / "sp.fco"), 20.0, options=o)
+    finally:
+        if saved is None:
+            os.environ.pop("FIASCO_TILE_SPLIT", None)
+        else:
+            os.environ["FIASCO_TILE_SPLIT"] = saved
+    assert ok, msg
+    env = dict(os.environ, FIASCO_DATA=os.path.join(REF, "data"), FIASCO_IMAGES=str(tmp_path))
+    for t in range(4):
+        ty, tx = divmod(t, 2)
+        crops = []
+        for i, f in enumerate(frames):
+            crops.append(str(tmp_path / ("c%d_%02d.ppm" % (t, i))))
+            gen_frames.write_pnm(crops[-1], np.ascontiguousarray(f[ty * 128:(ty + 1) * 128, tx * 160:(tx + 1) * 160]))
+        ref = str(tmp_path / ("ref%d.fco" % t))
+        subprocess.run([cf, "--progress-meter=0", "-V", "0", "-q", "20", "--pattern=ipp", "-o", ref] + crops, env=env,
+                       check=True, capture_output=True)
+        assert md5(str(tmp_path / ("sp.t%02d.fco" % t))) == md5(ref), "tile %d" % t
