@@ -122,6 +122,27 @@ def test_frames_without_reference_are_refused(tmp_path):
     assert not ok and "no reference frame" in msg
 
 
+def test_half_pixel_vectors_are_refused(tmp_path):
+    """Half-pixel motion compensation (and the cross-B search the reference ties to it, codec/coder.c:359): the
+    reference takes the vector as `unsigned' and halves it (extract_mc_block, codec/motion.c:232-260), so a
+    negative vector reads far outside the frame -- undefined there, refused here with a message; the same
+    sequence with full-pixel vectors is coded."""
+    names = []
+    for i, f in enumerate(gen_frames.video(2, 160, 128)):
+        names.append(str(tmp_path / ("h%d.pgm" % i)))
+        gen_frames.write_pnm(names[-1], f)
+    L = hostlib.load()
+    o = hostlib.cli_options(0)
+    L.fiasco_c_options_set_frame_pattern(o, b"ip")
+    L.fiasco_c_options_set_video_param(o, 25, 1, 0, 1)
+    ok, msg = hostlib.coder(names, str(tmp_path / "o.fco"), options=o)
+    assert not ok and "Half pixel" in msg
+    L.fiasco_c_options_set_video_param(o, 25, 0, 0, 1)
+    ok, msg = hostlib.coder(names, str(tmp_path / "o.fco"), options=o)
+    L.fiasco_c_options_delete(o)
+    assert ok, msg
+
+
 # ---------------------------------------------------------------------------------------------
 # round 2: colour sequences, the big frame at -z 1 / -z 2, tile-split mode and several GPUs inside
 # the library, every tile of BASELINE configs 2, 3, 4 and config 5 at its full size
