@@ -280,6 +280,15 @@ int fb200_create_predicted (fb200_ctx_t **ctx, const fb200_params_t *p,
  *  shorts in host memory.  The automata come back as the device leaves them: states of losing
  *  alternatives are holes (level_of_state == 255) and out[t].mv_* hold the vectors;
  *  fiasco_finish_predicted_frame() closes the holes and derives the delta flags.
+ *
+ *  Colour sequences (params.bands == 3): planes holds three pointers per tile (Y, Cb, Cr), past[t] /
+ *  future[t] point at the three regenerated planes of the reference frame behind each other
+ *  (fiasco_regenerate_colour_frame()).  The luminance band is coded with prediction, the luminance
+ *  tree's motion compensation is then taken off the chroma planes on the device (subtract_mc,
+ *  codec/mwfa.c:156-299) and Cb, Cr are coded without prediction (codec/coder.c:757-849).  The frames
+ *  of a colour sequence are chained: hand out[t].lc_min_level and out[t].y_column_history of the
+ *  frame coded before to the next call (fb200_wfa_t).  Contexts of type FB200_FRAME_ND and
+ *  FB200_FRAME_INTRA code intra frames: past and future may be NULL.
  */
 int fb200_encode_predicted (fb200_ctx_t *ctx, int n_tiles, const int16_t *const *planes,
 			    const int16_t *const *past, const int16_t *const *future,
