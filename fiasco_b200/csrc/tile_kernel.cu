@@ -3882,18 +3882,16 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 	       }
 	       else
 	       {
-	       if (level == P.p_min)
-		  cta_fill_norms<NT> (P, W, F.x, F.y, level);
-	       cta_find_best_mv<NT> (P, W, sh, F.x, F.y, level, h->price, 0);
-	       if (tid == 0)
-	       {
-		  h->fi	    = h->best_i;
-		  h->fcosts = h->best_c;
+		  if (level == P.p_min)
+		     cta_fill_norms<NT> (P, W, F.x, F.y, level);
+		  cta_find_best_mv<NT> (P, W, sh, F.x, F.y, level, h->price, 0);
+		  if (tid == 0)
+		  {
+		     h->fi     = h->best_i;
+		     h->fcosts = h->best_c;
+		  }
 	       }
-	       }
-	       if (X.try_nd)
-		  ;
-	       else if (P.motion == 2)
+	       if (!X.try_nd && P.motion == 2)
 	       {
 		  /* find_B_frame_mc (mwfa.c:341-542) without cross-B search: the best forward vector,
 		     the best backward vector, and both together */
@@ -3977,7 +3975,7 @@ cta_subdivide_band (const DevParams &P, TileWs &W, const Sh &sh, int band,
 		     }
 		  }
 	       }
-	       else if (tid == 0)
+	       else if (!X.try_nd && tid == 0)
 	       {
 		  /* find_P_frame_mc (mwfa.c:301-339) */
 		  const int bi = h->fi < 0 ? 0 : h->fi;
