@@ -4,6 +4,7 @@
  *  grey sample g -> (g - 128) * 16, colour samples -> Y, Cb, Cr with the reference's
  *  double precision matrix, scaled by 16 and truncated to short.  Always 4:4:4.
  */
+#include <errno.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -117,9 +118,12 @@ fi_read_image (const char *name)
 	 fi_error ("Out of memory!");
       if (fread (raw, 1, bytes, f) != bytes)
       {
+	 const int why = errno;		/* (closing the file must not change what the message says) */
+
 	 free (raw);
 	 if (f != stdin)
 	    fclose (f);
+	 errno = why;
 	 fi_file_error (name ? name : "stdin");
       }
       if (!color)
