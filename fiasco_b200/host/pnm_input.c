@@ -107,8 +107,9 @@ fi_read_image (const char *name)
    img->height = height;
    img->color  = color;
    n	       = width * height;
-   for (i = 0; i < (color ? 3u : 1u); i++)
-      img->pixels [i] = fiasco_calloc (n, sizeof (int16_t));
+   for (i = 0; i < (color ? 3u : 1u); i++)	/* (every sample is written below: no need for zeroed memory) */
+      if (!(img->pixels [i] = malloc ((size_t) n * sizeof (int16_t))))
+	 PNM_ERROR (f, "Out of memory!");
    {
       /* the raster in one read; a short read is the reference's I/O error (lib/image.c:357-388) */
       const size_t   bytes = (size_t) n * (color ? 3u : 1u);
